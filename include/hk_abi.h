@@ -1,0 +1,213 @@
+/*
+ * hk_abi.h — C-ABI of libhk_b200.so, the B200 (sm_100a) planning kernels behind HierarchicalKarting's
+ * C# planners.  This is what the reference-side P/Invoke stubs bind (INTEGRATION.md shows them).
+ *
+ * The reference has NO native boundary today; the drop-in boundary is the public static C# API
+ *   KartGame.AI.LQR.KartLQR.solveFeedbackLQR            Assets/Karting/Scripts/AI/LQR/KartLQR.cs:17
+ *   KartGame.AI.MCTS.KartMCTS.constructSearchTree (x2)   Assets/Karting/Scripts/AI/MCTS/KartMCTS.cs:50,80
+ *   KartGame.AI.MCTS.DiscreteGameState.{upNext,isOver,nextMoves,makeMove}
+ *                                                        Assets/Karting/Scripts/AI/MCTS/KartDiscreteGame.cs:188,251,322,420
+ * and every entry point below names the reference code whose body it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every buffer; nothing is retained after a call returns
+ *     except the immutable hk_game handle;
+ *   - every call returns HK_OK (0) or a negative hk_status; hk_last_error() gives the per-thread message;
+ *     no exceptions, no callbacks;
+ *   - re-entrant: the reference calls the LQNG solver from the Unity main thread and the MCTS from one
+ *     background thread per agent (HierarchicalKartAgent.cs:246-283), so each host thread gets its own
+ *     CUDA stream and scratch buffers lazily;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns HK_ERR_NO_DEVICE.
+ *
+ * Dimensions (KartLQRDynamics.cs:27-28, MPC/KartMPC.cs:13-20): per kart state (x,z,v,h) = 4, control (a,w) = 2;
+ * N players -> n = 4N joint states, m = 2N joint controls; T = horizon+1 backward steps (KartLQR.cs:64).
+ */
+#ifndef HK_ABI_H
+#define HK_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HK_ABI_VERSION 1
+#define HK_XDIM 4            /* LinearizedBicycle.xDim  KartLQRDynamics.cs:27 */
+#define HK_UDIM 2            /* LinearizedBicycle.uDim  KartLQRDynamics.cs:28 */
+#define HK_MAX_PLAYERS 4     /* HierarchicalKartAgent.cs:709-725 keeps N in 1..4 */
+#define HK_MAX_HORIZON 31    /* reference uses 3 (HierarchicalKartAgent.cs:1201) */
+#define HK_MAX_KARTS 4
+#define HK_MAX_ACTIONS 36    /* velocity buckets 6..14 step bucket(>=1) x 4 lanes  KartDiscreteGame.cs:329-340 */
+#define HK_MAX_PLIES 64      /* karts x treeSearchDepth upper bound for the trace buffers */
+
+typedef enum hk_status {
+    HK_OK = 0,
+    HK_ERR_INVALID_ARGUMENT = -1,   /* MathNet would throw ArgumentException on a dimension mismatch */
+    HK_ERR_NO_DEVICE = -2,          /* no CUDA device / wrong architecture: there is no CPU path */
+    HK_ERR_CUDA = -3,
+    HK_ERR_OUT_OF_MEMORY = -4,
+    HK_ERR_NO_UPNEXT = -5           /* upNext() == -1: C# would throw ArgumentOutOfRangeException at KartDiscreteGame.cs:326 */
+} hk_status;
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+int         hk_abi_version(void);
+int         hk_init(int device);                 /* binds the calling process to one CUDA device (one process per GPU) */
+void        hk_shutdown(void);
+const char* hk_last_error(void);                 /* thread-local */
+int         hk_device_count(void);
+
+/* ---- LQNG: batched feedback linear-quadratic Nash game ------------------------------------------------------ */
+/*
+ * Replaces the body of KartLQR.solveFeedbackLQR (KartLQR.cs:17-128) for `batch` independent problems.
+ * Host pointers, problem-major ("record per problem") layout; T = horizon+1; n = 4N; m = 2N.
+ * If time_varying == 0 the [T] dimension of A,B,Q,q,R is absent (reference behaviour: time invariant).
+ *   A     [batch][T?][N][4][4]   per-player A_i = KartLQRDynamics.getA()   (joint A = blockdiag, KartLQR.cs:33-37)
+ *   B     [batch][T?][N][4][2]   per-player B_i = KartLQRDynamics.getB()   (joint B_i = zero-padded, KartLQR.cs:41-52)
+ *   Q     [batch][T?][N][n][n]   KartLQRCosts.getQMatrix() of player i, row-major
+ *   q     [batch][T?][N][n]      KartLQRCosts.getQVec()
+ *   R     [batch][T?][N][2][2]   KartLQRCosts.getRMatrix()
+ *   x0    [batch][n]             concatenated initial states (KartLQR.cs:54-60)
+ * Outputs (any may be NULL except u0):
+ *   u0    [batch][m]             -P x0 - alpha at t = 0 for every player; the reference returns u0[0..1] (KartLQR.cs:121-127)
+ *   P     [batch][T][m][n]       feedback gains of every backward step t (index t = the loop variable of KartLQR.cs:64)
+ *   alpha [batch][T][m]          feedback offsets
+ *   traj  [batch][T+1][n]        closed-loop rollout x_{t+1} = A_t x_t + sum_k B_k,t u_k,t, u_t = -P_t x_t - alpha_t, x_0 = x0
+ *   status[batch]                0 ok, 1 = a pivot of the coupled m x m system was exactly zero (MathNet yields inf/NaN silently)
+ */
+int hk_lqng_solve_batch(int batch, int n_players, int horizon, int time_varying,
+                        const double* A, const double* B, const double* Q, const double* q, const double* R,
+                        const double* x0,
+                        double* u0, double* P, double* alpha, double* traj, int* status);
+
+/* Same with DEVICE pointers in the same layout, asynchronous on `cuda_stream` (a cudaStream_t; NULL = the calling
+ * thread's own stream).  Used by bench.py for the HBM-resident number and by pipelines that keep problems on the GPU. */
+int hk_lqng_solve_batch_device(int batch, int n_players, int horizon, int time_varying,
+                               const double* dA, const double* dB, const double* dQ, const double* dq, const double* dR,
+                               const double* dx0,
+                               double* du0, double* dP, double* dalpha, double* dtraj, int* dstatus,
+                               void* cuda_stream);
+
+/* What the C# shim of solveFeedbackLQR calls: batch of one, host pointers (KartLQR.cs:17). */
+int hk_lqng_solve_one(int n_players, int horizon,
+                      const double* A, const double* B, const double* Q, const double* q, const double* R,
+                      const double* x0, double* u0 /* [m] */);
+
+/*
+ * Device-side problem assembly + solve: builds A,B from LinearizedBicycle
+ * (KartLQRDynamics.cs:40-62) and Q,q,R from LQRCheckpointReachAvoidCost (KartLQRCosts.cs:57-140) on the GPU, so
+ * only the compact per-player description crosses PCIe.  Per problem and per player i (private ordering
+ * [self, its others...]; the cost blocks are used in that private order on the JOINT state, exactly as
+ * KartLQRCosts.cs:62-94 + KartLQR.cs:62 do — quirk Q3 of SURVEY.md A.3):
+ *   x0      [batch][N][4]      initial states (joint order)
+ *   target  [batch][N][4]      targetState of player i
+ *   tw      [batch][N][4]      targetWeights[x,z,v,h]
+ *   cw      [batch][N]         controlWeight
+ *   aw      [batch][N][N-1][2] avoidWeights[x],[z] of the k-th entry of player i's avoidDynamics list
+ *   otgt    [batch][N][N-1][4] opponentTargetStates
+ *   otw     [batch][N][N-1][3] opponentTargetWeights[x,z,v]
+ *   dt                          (double)Time.fixedDeltaTime  HierarchicalKartAgent.cs:707
+ */
+int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizon, double dt,
+                                 const double* x0, const double* target, const double* tw, const double* cw,
+                                 const double* aw, const double* otgt, const double* otw,
+                                 double* u0, int* status);
+
+/* ---- discrete race game + leaf-parallel rollouts ------------------------------------------------------------ */
+typedef struct hk_section {      /* DiscretePositionTracker.cs:35-40 */
+    float   insideR;             /* trackInsideRadius (0 => straight, :197) */
+    float   length;              /* trackLength */
+    float   width;               /* trackWidth */
+    float   turnDeg;             /* turnDegrees */
+    int32_t leftTurn;            /* bool */
+    int32_t optimalLane;         /* 1..4 */
+} hk_section;
+
+typedef struct hk_kart {         /* ArcadeKart.Stats fields read by the game (ArcadeKart.cs:210,517-547; KartDiscreteGame.cs:70-116,168) */
+    float accel, braking, topSpeed, reverseSpeed, maxGs, minGs, tireWearFactor;
+} hk_kart;
+
+typedef struct hk_game_params {  /* DiscreteGameParams HierarchicalKartAgent.cs:35-49 + RacingEnvController fields the game reads */
+    int32_t velocityBucketSize, timePrecision, sectionWindow, treeSearchDepth;
+    int32_t maxLaneChanges;              /* RacingEnvController.MaxLaneChanges :112 */
+    float   collisionWindow;             /* unused by the reference game (collision filter is `false &&`, KartDiscreteGame.cs:398) */
+    float   teamScoreRewardMultiplier;   /* RacingEnvController.cs:89 */
+    int32_t maxEpisodeSteps;             /* RacingEnvController.cs:126 */
+} hk_game_params;
+
+typedef struct hk_kart_state {   /* DiscreteKartState KartDiscreteGame.cs:21-33; `name` is the kart's index in the list */
+    int32_t player;              /* index into envController.Agents used by applyAction (:129); the reference always passes 0 */
+    int32_t team, section, timeAtSection, min_velocity, max_velocity, lane, tireAge, laneChanges, infeasible;
+} hk_kart_state;
+
+typedef struct hk_action { int32_t min_velocity, max_velocity, lane; } hk_action;   /* DiscreteKartAction :14-19 */
+
+typedef struct hk_game_state {   /* DiscreteGameState :174-182 (value part) */
+    int32_t       n_karts;
+    int32_t       initialSection, lastCompletedSection, finalSection;
+    hk_kart_state karts[HK_MAX_KARTS];
+} hk_game_state;
+
+typedef struct hk_game hk_game;  /* immutable after creation => shareable between caller threads */
+
+/* karts[n_karts]: constants of DiscreteGameState.kartAgents (used by nextMoves, :326-357);
+ * env_karts[n_env_karts]: constants of envController.Agents (used by applyAction through hk_kart_state.player, :129);
+ * env_karts == NULL => same table as karts. */
+int  hk_game_create(const hk_section* sections, int n_sections, const hk_kart* karts, int n_karts,
+                    const hk_kart* env_karts, int n_env_karts, const hk_game_params* params, hk_game** out);
+void hk_game_destroy(hk_game* g);
+
+/*
+ * Exact-parity entry: for each of `batch` root states, play a fixed action sequence on the GPU with
+ * DiscreteGameState.makeMove (:420-446) and report after every move the full state, upNext() (:188-243),
+ * isOver() (:251-317; scores[] holds the first 2*HK_MAX_KARTS entries of the reference's score list, n_scores its
+ * length) and the legal move set of nextMoves() (:322-415) in the rollout policy's sort order (KartMCTS.cs:256).
+ *   actions     [batch][len]
+ *   states_out  [batch][len+1]            state before move k (k = 0 is the root) ... after the last move
+ *   upnext_out  [batch][len+1]
+ *   over_out    [batch][len+1], n_scores_out [batch][len+1], scores_out [batch][len+1][2*HK_MAX_KARTS]
+ *   n_moves_out [batch][len+1], moves_out [batch][len+1][HK_MAX_ACTIONS]  (sorted; generation-order index = vi*4+lane-1
+ *                                         is stored in moves_index_out [batch][len+1][HK_MAX_ACTIONS])
+ * Any output pointer may be NULL.  Moves after a terminal state are still applied (makeMove does not check).
+ */
+int hk_game_replay_batch(const hk_game* g, int batch, int len, const hk_game_state* roots, const hk_action* actions,
+                         hk_game_state* states_out, int32_t* upnext_out, int32_t* over_out, int32_t* n_scores_out,
+                         float* scores_out, int32_t* n_moves_out, hk_action* moves_out, int32_t* moves_index_out);
+
+/*
+ * Leaf-parallel rollouts (the GPU form of KartMCTS.processLeaf :124-159 + simulate :238-278): n_rollouts independent
+ * playouts of the biased random policy from `leaf`, reduced on the GPU per FIRST action (generation-order index
+ * a = vi*4 + lane-1, vi = (min_velocity-6)/bucket).  Rollout r uses Philox4x32-10 with key = seed and counter =
+ * (rollout_offset + r, ply) — disjoint counter ranges make multi-GPU shards independent and reproducible.
+ *   visit      [HK_MAX_ACTIONS]               rollouts whose first action was a
+ *   reward_sum [HK_MAX_ACTIONS][HK_MAX_KARTS] sum over those rollouts of the terminal score list entry k (what
+ *                                             backpropagate indexes with upNext(), KartMCTS.cs:284); NaN scores
+ *                                             (max==min, KartDiscreteGame.cs:307) are counted in nan_count instead
+ *   nan_count  [HK_MAX_ACTIONS]
+ *   plies_sum  total number of plies played (for throughput accounting), may be NULL
+ * If the leaf is already terminal every output is zero and the call returns HK_OK.
+ */
+int hk_mcts_rollouts(const hk_game* g, const hk_game_state* leaf, int64_t n_rollouts, uint64_t seed,
+                     uint64_t rollout_offset, int64_t* visit, double* reward_sum, int64_t* nan_count,
+                     int64_t* plies_sum);
+
+/* Same rollouts, but every rollout also reports what it did, so that an oracle can replay it move by move:
+ *   n_plies_out [n_rollouts]; actions_out [n_rollouts][HK_MAX_PLIES]; choice_out [n_rollouts][HK_MAX_PLIES] (index into
+ *   the sorted legal list); n_scores_out [n_rollouts]; scores_out [n_rollouts][2*HK_MAX_KARTS]. */
+int hk_mcts_rollouts_trace(const hk_game* g, const hk_game_state* leaf, int64_t n_rollouts, uint64_t seed,
+                           uint64_t rollout_offset, int32_t* n_plies_out, hk_action* actions_out, int32_t* choice_out,
+                           int32_t* n_scores_out, float* scores_out);
+
+/* Many leaves in one launch (tree-parallel batches / many races): leaves[n_leaves], rollouts_per_leaf each;
+ * outputs carry a leading [n_leaves] dimension.  Rollout ids are leaf_index * rollouts_per_leaf + r + rollout_offset. */
+int hk_mcts_rollouts_multi(const hk_game* g, const hk_game_state* leaves, int n_leaves, int64_t rollouts_per_leaf,
+                           uint64_t seed, uint64_t rollout_offset, int64_t* visit, double* reward_sum,
+                           int64_t* nan_count, int64_t* plies_sum);
+
+/* The rollout policy's index distribution for `cnt` legal moves (KartMCTS.cs:266-269 via NextGaussian :218-236):
+ * cdf_out[k] = P(index <= k) as a 32-bit threshold, exactly what the kernels sample from. cnt in 1..HK_MAX_ACTIONS. */
+int hk_policy_cdf(int cnt, uint32_t* cdf_out /* [cnt] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HK_ABI_H */

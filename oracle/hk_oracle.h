@@ -1,0 +1,49 @@
+/* hk_oracle.h — CPU ORACLE (test infrastructure, NOT the product). See hk_oracle_lqng.c / hk_oracle_game.c.
+ * Shares only the plain-data struct definitions of include/hk_abi.h with the product. */
+#ifndef HK_ORACLE_H
+#define HK_ORACLE_H
+#include <stdint.h>
+#include "../include/hk_abi.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* LQNG (double) */
+void hk_oracle_bicycle_A(double dt, const double* x0, double* A);
+void hk_oracle_bicycle_B(double dt, double* B);
+void hk_oracle_cost(int n_other, const double* target, const double* tw, double cw, const double* aw, const double* otgt,
+                    const double* otw, double* Q, double* q, double* R);
+int hk_oracle_lqng_solve(int N, int horizon, int time_varying, const double* A, const double* B, const double* Q,
+                         const double* q, const double* R, const double* x0, double* u0, double* P, double* alpha, double* traj);
+int hk_oracle_lqng_solve_batch(int batch, int N, int horizon, int time_varying, const double* A, const double* B,
+                               const double* Q, const double* q, const double* R, const double* x0, double* u0, double* P,
+                               double* alpha, double* traj, int* status, int threads);
+/* discrete game (float32/int32) */
+typedef struct hk_oracle_game hk_oracle_game;
+int  hk_oracle_game_create(const hk_section* s, int n_sections, const hk_kart* karts, int n_karts, const hk_kart* env_karts,
+                           int n_env_karts, const hk_game_params* p, hk_oracle_game** out);
+void hk_oracle_game_destroy(hk_oracle_game* g);
+float hk_oracle_max_speed_for_radius_and_wear(const hk_kart* k, float radius, float wear);
+float hk_oracle_compute_toc(const hk_kart* k, float distance, float radius, float tireWear, float initV, float finalV);
+hk_kart_state hk_oracle_apply_action(const hk_oracle_game* g, const hk_kart_state* s, hk_action a);
+int  hk_oracle_up_next(const hk_oracle_game* g, const hk_game_state* st);
+int  hk_oracle_next_moves(const hk_oracle_game* g, const hk_game_state* st, hk_action* out, int* gen_index);
+hk_game_state hk_oracle_make_move(const hk_oracle_game* g, const hk_game_state* st, hk_action a, int* err);
+int  hk_oracle_is_over(const hk_oracle_game* g, const hk_game_state* st, float* scores, int* n_scores);
+int  hk_oracle_policy_moves(const hk_oracle_game* g, const hk_game_state* st, hk_action* out, int* gen_index);
+void hk_oracle_philox4x32_10(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]);
+void hk_oracle_policy_cdf(int cnt, uint32_t* cdf);
+int  hk_oracle_policy_index(int cnt, const uint32_t* cdf, uint32_t u);
+int  hk_oracle_reference_policy_index(int cnt, uint64_t* rng_state);
+int  hk_oracle_rollout(const hk_oracle_game* g, const hk_game_state* leaf, int mode, uint64_t seed, uint64_t rollout_id,
+                       uint64_t* rng_state, hk_action* actions_out, int* choice_out, float* scores, int* n_scores,
+                       hk_game_state* terminal);
+int  hk_oracle_rollouts(const hk_oracle_game* g, const hk_game_state* leaf, int64_t n_rollouts, int mode, uint64_t seed,
+                        uint64_t rollout_offset, int64_t* visit, double* reward_sum, int64_t* nan_count, int64_t* plies_sum);
+/* helpers for the KAT tests (track formulas) */
+float hk_oracle_distance_to_travel(const hk_section* s, int a, int b);
+float hk_oracle_radius_of_lane(const hk_section* s, int a, int b);
+float hk_oracle_tire_load(const hk_section* s, float velocity, int a, int b);
+#ifdef __cplusplus
+}
+#endif
+#endif

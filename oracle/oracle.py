@@ -1,0 +1,193 @@
+"""ctypes binding of oracle/libhk_oracle.so — the CPU ORACLE (test infrastructure, NOT the product).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from hierarchicalkarting_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhk_oracle.so")
+_lib = None
+_dp, _ip, _lp, _fp, _up = (C.POINTER(t) for t in (C.c_double, C.c_int32, C.c_int64, C.c_float, C.c_uint32))
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("hk_oracle_lqng.c", "hk_oracle_game.c", "hk_oracle.h", "Makefile")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.hk_oracle_bicycle_A.argtypes = [C.c_double, _dp, _dp]
+        L.hk_oracle_bicycle_B.argtypes = [C.c_double, _dp]
+        L.hk_oracle_cost.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.hk_oracle_lqng_solve.argtypes = [C.c_int, C.c_int, C.c_int] + [_dp] * 10
+        L.hk_oracle_lqng_solve_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int] + [_dp] * 10 + [_ip, C.c_int]
+        L.hk_oracle_game_create.argtypes = [C.POINTER(abi.hk_section), C.c_int, C.POINTER(abi.hk_kart), C.c_int,
+                                            C.POINTER(abi.hk_kart), C.c_int, C.POINTER(abi.hk_game_params), C.POINTER(C.c_void_p)]
+        L.hk_oracle_game_destroy.argtypes = [C.c_void_p]
+        L.hk_oracle_max_speed_for_radius_and_wear.argtypes = [C.POINTER(abi.hk_kart), C.c_float, C.c_float]
+        L.hk_oracle_max_speed_for_radius_and_wear.restype = C.c_float
+        L.hk_oracle_compute_toc.argtypes = [C.POINTER(abi.hk_kart)] + [C.c_float] * 5
+        L.hk_oracle_compute_toc.restype = C.c_float
+        L.hk_oracle_apply_action.argtypes = [C.c_void_p, C.POINTER(abi.hk_kart_state), abi.hk_action]
+        L.hk_oracle_apply_action.restype = abi.hk_kart_state
+        L.hk_oracle_up_next.argtypes = [C.c_void_p, C.POINTER(abi.hk_game_state)]
+        L.hk_oracle_next_moves.argtypes = [C.c_void_p, C.POINTER(abi.hk_game_state), C.POINTER(abi.hk_action), _ip]
+        L.hk_oracle_make_move.argtypes = [C.c_void_p, C.POINTER(abi.hk_game_state), abi.hk_action, _ip]
+        L.hk_oracle_make_move.restype = abi.hk_game_state
+        L.hk_oracle_is_over.argtypes = [C.c_void_p, C.POINTER(abi.hk_game_state), _fp, _ip]
+        L.hk_oracle_policy_moves.argtypes = [C.c_void_p, C.POINTER(abi.hk_game_state), C.POINTER(abi.hk_action), _ip]
+        L.hk_oracle_philox4x32_10.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _up]
+        L.hk_oracle_policy_cdf.argtypes = [C.c_int, _up]
+        L.hk_oracle_policy_index.argtypes = [C.c_int, _up, C.c_uint32]
+        L.hk_oracle_reference_policy_index.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
+        L.hk_oracle_rollout.argtypes = [C.c_void_p, C.POINTER(abi.hk_game_state), C.c_int, C.c_uint64, C.c_uint64,
+                                        C.POINTER(C.c_uint64), C.POINTER(abi.hk_action), _ip, _fp, _ip, C.POINTER(abi.hk_game_state)]
+        L.hk_oracle_rollouts.argtypes = [C.c_void_p, C.POINTER(abi.hk_game_state), C.c_int64, C.c_int, C.c_uint64, C.c_uint64,
+                                         _lp, _dp, _lp, _lp]
+        for f in ("hk_oracle_distance_to_travel", "hk_oracle_radius_of_lane"):
+            getattr(L, f).argtypes = [C.POINTER(abi.hk_section), C.c_int, C.c_int]
+            getattr(L, f).restype = C.c_float
+        L.hk_oracle_tire_load.argtypes = [C.POINTER(abi.hk_section), C.c_float, C.c_int, C.c_int]
+        L.hk_oracle_tire_load.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+# ---- LQNG ------------------------------------------------------------------------------------------------------
+def bicycle_A(dt: float, x0) -> np.ndarray:
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    A = np.empty((4, 4))
+    lib().hk_oracle_bicycle_A(dt, _p(x0), _p(A))
+    return A
+
+
+def bicycle_B(dt: float) -> np.ndarray:
+    B = np.empty((4, 2))
+    lib().hk_oracle_bicycle_B(dt, _p(B))
+    return B
+
+
+def cost(target, tw, cw, aw, otgt, otw):
+    aw = np.ascontiguousarray(aw, dtype=np.float64).reshape(-1, 2)
+    n_other = aw.shape[0]
+    n = 4 * (1 + n_other)
+    target, tw = (np.ascontiguousarray(v, dtype=np.float64) for v in (target, tw))
+    otgt = np.ascontiguousarray(otgt, dtype=np.float64).reshape(n_other, 4)
+    otw = np.ascontiguousarray(otw, dtype=np.float64).reshape(n_other, 3)
+    Q, q, R = np.empty((n, n)), np.empty(n), np.empty((2, 2))
+    lib().hk_oracle_cost(n_other, _p(target), _p(tw), float(cw), _p(aw), _p(otgt), _p(otw), _p(Q), _p(q), _p(R))
+    return Q, q, R
+
+
+def lqng_solve_batch(A, B, Q, q, R, x0, horizon: int, time_varying: bool = False, threads: int = 1, full: bool = True):
+    """Arrays in the hk_abi.h layout with a leading batch dimension. Returns dict(u0, P, alpha, traj, status)."""
+    A, B, Q, q, R, x0 = (np.ascontiguousarray(v, dtype=np.float64) for v in (A, B, Q, q, R, x0))
+    batch, n = x0.shape
+    N, m, T = n // 4, n // 2, horizon + 1
+    u0 = np.empty((batch, m))
+    P = np.empty((batch, T, m, n)) if full else None
+    alpha = np.empty((batch, T, m)) if full else None
+    traj = np.empty((batch, T + 1, n)) if full else None
+    status = np.zeros(batch, dtype=np.int32)
+    lib().hk_oracle_lqng_solve_batch(batch, N, horizon, int(time_varying), _p(A), _p(B), _p(Q), _p(q), _p(R), _p(x0),
+                                     _p(u0), _p(P), _p(alpha), _p(traj), status.ctypes.data_as(_ip), threads)
+    return dict(u0=u0, P=P, alpha=alpha, traj=traj, status=status)
+
+
+# ---- discrete game ---------------------------------------------------------------------------------------------
+class Game:
+    def __init__(self, sections, n_sections, karts, n_karts, params, env_karts=None, n_env_karts=0):
+        self._h = C.c_void_p()
+        rc = lib().hk_oracle_game_create(sections, n_sections, karts, n_karts, env_karts, n_env_karts, C.byref(params),
+                                         C.byref(self._h))
+        if rc != 0:
+            raise ValueError("hk_oracle_game_create failed")
+        self.params = params
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().hk_oracle_game_destroy(self._h)
+            self._h = None
+
+    def up_next(self, st) -> int:
+        return lib().hk_oracle_up_next(self._h, C.byref(st))
+
+    def apply_action(self, ks, a):
+        return lib().hk_oracle_apply_action(self._h, C.byref(ks), a)
+
+    def next_moves(self, st):
+        mv = (abi.hk_action * abi.HK_MAX_ACTIONS)()
+        gi = (C.c_int32 * abi.HK_MAX_ACTIONS)()
+        n = lib().hk_oracle_next_moves(self._h, C.byref(st), mv, gi)
+        return [mv[i].astuple() for i in range(max(n, 0))], [gi[i] for i in range(max(n, 0))], n
+
+    def policy_moves(self, st):
+        mv = (abi.hk_action * abi.HK_MAX_ACTIONS)()
+        gi = (C.c_int32 * abi.HK_MAX_ACTIONS)()
+        n = lib().hk_oracle_policy_moves(self._h, C.byref(st), mv, gi)
+        return [mv[i].astuple() for i in range(max(n, 0))], [gi[i] for i in range(max(n, 0))], n
+
+    def make_move(self, st, a):
+        if not isinstance(a, abi.hk_action):
+            a = abi.hk_action(*a)
+        return lib().hk_oracle_make_move(self._h, C.byref(st), a, None)
+
+    def is_over(self, st):
+        sc = (C.c_float * (2 * abi.HK_MAX_KARTS))()
+        ns = C.c_int32(0)
+        over = lib().hk_oracle_is_over(self._h, C.byref(st), sc, C.byref(ns))
+        return over, np.array([sc[i] for i in range(ns.value)], dtype=np.float32)
+
+    def rollout(self, leaf, mode=0, seed=0, rollout_id=0, rng_state=None):
+        acts = (abi.hk_action * abi.HK_MAX_PLIES)()
+        ch = (C.c_int32 * abi.HK_MAX_PLIES)()
+        sc = (C.c_float * (2 * abi.HK_MAX_KARTS))()
+        ns = C.c_int32(0)
+        term = abi.hk_game_state()
+        rs = C.c_uint64(rng_state if rng_state else 88172645463325252)
+        n = lib().hk_oracle_rollout(self._h, C.byref(leaf), mode, seed, rollout_id, C.byref(rs), acts, ch, sc, C.byref(ns),
+                                    C.byref(term))
+        return dict(n_plies=n, actions=[acts[i].astuple() for i in range(max(n, 0))], choices=[ch[i] for i in range(max(n, 0))],
+                    scores=np.array([sc[i] for i in range(ns.value)], dtype=np.float32), terminal=term)
+
+    def rollouts(self, leaf, n_rollouts, mode=0, seed=0, rollout_offset=0):
+        visit = np.zeros(abi.HK_MAX_ACTIONS, dtype=np.int64)
+        rsum = np.zeros((abi.HK_MAX_ACTIONS, abi.HK_MAX_KARTS))
+        nanc = np.zeros(abi.HK_MAX_ACTIONS, dtype=np.int64)
+        plies = C.c_int64(0)
+        rc = lib().hk_oracle_rollouts(self._h, C.byref(leaf), n_rollouts, mode, seed, rollout_offset,
+                                      visit.ctypes.data_as(_lp), _p(rsum), nanc.ctypes.data_as(_lp), C.byref(plies))
+        if rc != 0:
+            raise RuntimeError("oracle rollouts failed")
+        return dict(visit=visit, reward_sum=rsum, nan_count=nanc, plies=plies.value)
+
+
+def policy_cdf(cnt: int) -> np.ndarray:
+    out = np.zeros(cnt, dtype=np.uint32)
+    lib().hk_oracle_policy_cdf(cnt, out.ctypes.data_as(_up))
+    return out
+
+
+def philox(seed, c0, c1, c2, c3) -> np.ndarray:
+    out = np.zeros(4, dtype=np.uint32)
+    lib().hk_oracle_philox4x32_10(seed, c0, c1, c2, c3, out.ctypes.data_as(_up))
+    return out
