@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: LQNG solves/s (2-kart, reference horizon 3) on N B200s; MCTS rollouts/s beside it.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     the reference's CPU path (oracle port, all host threads)
+
+A "step" is one pass of the hot path over one batch of synthetic problems: BASELINE config 2, 65,536 independent 2-kart
+Oval problems per GPU (weak scaling: every rank solves its own seeded shard; no collective on the data path, one final
+gather of per-rank summaries).  `value` times hk_lqng_solve_batch_device on HBM-resident inputs with CUDA events on the
+launching stream; `e2e` times the host-pointer C-ABI call hk_lqng_solve_batch (pinned host buffers, H2D + D2H inside).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 65536
+HORIZON = 3
+FLOPS_PER_SOLVE = 41805            # dense count, SURVEY.md §8(d), 2-kart horizon 3
+IN_BYTES_PER_SOLVE = 1664          # A,B per player + Q,q,R,x0 (per-player A/B form)
+OUT_BYTES_PER_SOLVE = 32 + 4       # u0 for both players + status
+N_INPUT_SETS = 4                   # rotated so that consecutive steps never hit the same 109 MB in the 126 MB L2
+MCTS_ROLLOUTS = 1_000_000          # BASELINE config 4
+
+
+def _peaks():
+    hbm, hbm_src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm, hbm_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    fp64, fp64_src = 37.2, "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz"
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_peaks.json")) as f:
+            j = json.load(f)
+            fp64, fp64_src = float(j["fp64_tflops"]), j.get("how", "measured (profiles/fp64_peaks.json)")
+    except Exception:
+        pass
+    return hbm, hbm_src, fp64, fp64_src
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_baseline(seconds: float = 12.0, threads: int | None = None):
+    """The oracle port of the reference solver on the host cores, bounded sample of the same workload."""
+    from hierarchicalkarting_b200 import scenarios as S
+    from oracle import oracle as O
+    threads = threads or os.cpu_count() or 1
+    sample = 16384
+    A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(S.OVAL, sample, 2, seed=20260001))
+    O.lqng_solve_batch(A[:256], B[:256], Q[:256], q[:256], R[:256], x0[:256], HORIZON, threads=threads, full=False)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        O.lqng_solve_batch(A, B, Q, q, R, x0, HORIZON, threads=threads, full=False)
+        done += sample
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    t1 = time.perf_counter()
+    O.lqng_solve_batch(A[:4096], B[:4096], Q[:4096], q[:4096], R[:4096], x0[:4096], HORIZON, threads=1, full=False)
+    single = 4096 / (time.perf_counter() - t1)
+    return {"value": done / el, "unit": "solves/s", "cores": threads, "kind": "port",
+            "sample": f"{done} solves of BASELINE config 2 (16384-problem sample of the 65,536 batch, repeated for {el:.1f} s); "
+                      f"C oracle restatement of KartLQR.solveFeedbackLQR, OpenMP static split; single thread: {single:.0f} solves/s",
+            "single_thread_value": single}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path. The Unity C# sources cannot be compiled here
+    (no .NET SDK in the image or on the GPU box), so this arm is the C oracle port with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from hierarchicalkarting_b200 import scenarios as S
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    sample = 16384
+    A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(S.OVAL, sample, 2, seed=20260001))
+    for _ in range(max(args.warmup, 1)):
+        O.lqng_solve_batch(A, B, Q, q, R, x0, HORIZON, threads=threads, full=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.lqng_solve_batch(A, B, Q, q, R, x0, HORIZON, threads=threads, full=False)
+    el = time.perf_counter() - t0
+    v = sample * args.steps / el
+    line = {"impl": "reference", "metric": "lqng_solves_per_s", "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: independent 2-kart Oval LQNG problems, horizon 3, dt=(double)0.02f; "
+                                   f"bounded sample of {sample} problems per step", "batch_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": "solves/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} problems per step x {args.steps} steps; C oracle port of KartLQR.solveFeedbackLQR "
+                                       "(reference C# not compilable: no .NET in image), OpenMP over all host threads"},
+            "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mcts", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from hierarchicalkarting_b200 import abi, scenarios as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    lib = abi.load_library()                       # raises if the CUDA library is missing: there is no fallback
+    abi.check(lib.hk_init(local))
+    dev = torch.device("cuda", local)
+    batch, N, n, m = args.batch, 2, 8, 4
+
+    # ---- synthetic shard of this rank (seeded, disjoint per rank) -------------------------------------------------------
+    prob = S.make_problems(S.OVAL, batch, N, seed=20260001 + rank)
+    host = S.assemble_dense(prob)                                           # A,B,Q,q,R,x0 (numpy, record layout)
+    pinned = [torch.from_numpy(a).pin_memory() for a in host]
+    h2d_bytes = int(sum(a.nbytes for a in host))
+    sets = []
+    for k in range(N_INPUT_SETS):                                           # distinct device copies, rotated per step (L2 hygiene)
+        sets.append([p.to(dev, non_blocking=True).clone() for p in pinned])
+    u0_d = torch.empty((batch, m), dtype=torch.float64, device=dev)
+    st_d = torch.empty((batch,), dtype=torch.int32, device=dev)
+    u0_h = torch.empty((batch, m), dtype=torch.float64).pin_memory()
+    st_h = torch.empty((batch,), dtype=torch.int32).pin_memory()
+    d2h_bytes = int(u0_h.numel() * 8 + st_h.numel() * 4)
+    stream = torch.cuda.current_stream()
+    launches = 0
+
+    def step_device(k):
+        nonlocal launches
+        a = sets[k % N_INPUT_SETS]
+        abi.check(lib.hk_lqng_solve_batch_device(batch, N, HORIZON, 0, *[t.data_ptr() for t in a], u0_d.data_ptr(), None, None, None,
+                                                 st_d.data_ptr(), stream.cuda_stream))
+        launches += 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- HBM-resident throughput (`value`) -------------------------------------------------------------------------------
+    for k in range(args.warmup):
+        step_device(k)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        step_device(k)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    gpu_launches = launches
+    # per-launch kernel duration for the roofline (events around single launches, rotating inputs)
+    per = []
+    for k in range(min(args.steps, 20)):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream); step_device(k); a1.record(stream); a1.synchronize()
+        per.append(a0.elapsed_time(a1))
+    kern_ms = float(np.mean(per))
+
+    # ---- end to end through the host-pointer C-ABI call (`e2e`) ----------------------------------------------------------
+    hp = [p.numpy() for p in pinned]
+    u0_np, st_np = u0_h.numpy(), st_h.numpy()
+
+    def step_e2e():
+        abi.check(lib.hk_lqng_solve_batch(batch, N, HORIZON, 0, *[abi.dptr(a) for a in hp], abi.dptr(u0_np), None, None, None, abi.iptr(st_np)))
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.finish()
+
+    # ---- MCTS rollouts/s (BASELINE config 4: Complex, 2 karts, 10^6 leaf-parallel rollouts per decision) ------------------
+    mcts_obj = None
+    if not args.no_mcts:
+        from hierarchicalkarting_b200 import mcts as M, tracks
+        G = M.Game(tracks.COMPLEX, 2, 2)
+        leaf = tracks.root_state(tracks.COMPLEX, 3 + rank, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 80])
+        for w in range(3):
+            G.rollouts(leaf, MCTS_ROLLOUTS, seed=20260003, rollout_offset=rank * MCTS_ROLLOUTS)
+        barrier()
+        reps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        plies = 0
+        for r in range(reps):
+            out = G.rollouts(leaf, MCTS_ROLLOUTS, seed=20260003 + r, rollout_offset=rank * MCTS_ROLLOUTS)
+            plies += out["plies"]
+        el = max_over_ranks(time.perf_counter() - t0)
+        mcts_obj = {"metric": "mcts_rollouts_per_s", "value": world * MCTS_ROLLOUTS * reps / el, "unit": "rollouts/s",
+                    "plies_per_s": world * plies / el, "ms_per_decision": 1e3 * el / reps, "rollouts_per_decision": MCTS_ROLLOUTS,
+                    "config": "BASELINE config 4: Complex, 2 karts, depth 8, bucket 2, Philox4x32-10; host call incl. result D2H",
+                    "gpu_launches": reps}
+
+    # ---- final gather of per-rank summaries (the only communication) ------------------------------------------------------
+    summary = torch.tensor([float(st_d.sum().item()), float(u0_d.sum().item()), float(batch)], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(summary) for _ in range(world)]
+        dist.all_gather(gathered, summary)
+        summary = torch.stack(gathered).sum(dim=0)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, hbm_src, fp64, fp64_src = _peaks()
+    value = world * batch * args.steps / (dev_ms * 1e-3)
+    ach_tf = batch * FLOPS_PER_SOLVE / (kern_ms * 1e-3) / 1e12
+    ach_gb = batch * (IN_BYTES_PER_SOLVE + OUT_BYTES_PER_SOLVE) / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "lqng_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": "lqng_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: 65,536 independent 2-kart LQNG problems per GPU (random linearisation points along "
+                               "the Oval track, seed 20260001+rank), horizon 3, dt=(double)0.02f; output u0 of every player + status",
+                   "batch_per_gpu": batch, "horizon": HORIZON, "players": N,
+                   "l2": f"{N_INPUT_SETS} distinct device copies of the inputs rotated per step ({N_INPUT_SETS * h2d_bytes / 1e6:.0f} MB > 126 MB L2)",
+                   "parallelism": f"independent shards x{world}, no data-path collective"},
+        "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": fp64, "unit": "TFLOP/s", "frac": ach_tf / fp64, "traffic": traffic,
+                     "note": f"FP64 pipe (DFMA/DMMA share it on B200); algorithmic flops = {FLOPS_PER_SOLVE}/solve (dense count) x {batch} per launch; "
+                             f"kernel avg {kern_ms:.4f} ms per launch (CUDA events); peak = {fp64_src}",
+                     "hbm": {"achieved": ach_gb, "peak": hbm, "unit": "GB/s", "frac": ach_gb / hbm, "peak_source": hbm_src,
+                             "bytes_per_solve": IN_BYTES_PER_SOLVE + OUT_BYTES_PER_SOLVE}},
+        "e2e": {"value": world * batch * args.steps / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "hk_lqng_solve_batch (host pointers, pinned)"},
+        "gpu_launches": gpu_launches, "clocks": clocks,
+        "summary": {"status_nonzero": summary[0].item(), "u0_checksum": summary[1].item(), "problems": summary[2].item()},
+    }
+    if mcts_obj:
+        line["mcts"] = mcts_obj
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,264 @@
+// hk_abi.cu — host side of the C-ABI (include/hk_abi.h): library state, per-thread CUDA context, and the LQNG entry
+// points.  The discrete-game entry points live next to their kernels in hk_game.cu.
+#include "hk_common.cuh"
+#include <cstring>
+#include <mutex>
+#include <atomic>
+
+namespace hk {
+
+static thread_local char g_err[512] = "";
+static std::mutex g_mu;
+static std::atomic<int> g_device{-1};          // -1 = not initialised
+static std::atomic<int> g_device_state{0};     // 0 unknown, 1 ok, -1 no usable device
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int ensure_device()
+{
+    int st = g_device_state.load();
+    if (st == 1) {
+        cudaError_t e = cudaSetDevice(g_device.load());
+        if (e != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e)); return HK_ERR_CUDA; }
+        return HK_OK;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device_state.load() == 1) return HK_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        set_error("no CUDA device (%s); libhk_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return HK_ERR_NO_DEVICE;
+    }
+    int dev = g_device.load();
+    if (dev < 0) dev = 0;
+    if (dev >= n) { set_error("device %d requested, %d present", dev, n); return HK_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return HK_ERR_CUDA; }
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libhk_b200 is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+        return HK_ERR_NO_DEVICE;
+    }
+    e = cudaSetDevice(dev);
+    if (e != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e)); return HK_ERR_CUDA; }
+    g_device.store(dev);
+    g_device_state.store(1);
+    return HK_OK;
+}
+
+ThreadCtx::~ThreadCtx()
+{
+    // Streams/buffers of a dying host thread; ignore errors (the context may already be gone at process exit).
+    if (!ready) return;
+    for (auto& b : dbuf) if (b) cudaFree(b);
+    for (auto& b : hbuf) if (b) cudaFreeHost(b);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
+}
+
+ThreadCtx* ctx()
+{
+    static thread_local ThreadCtx c;
+    if (ensure_device() != HK_OK) return nullptr;
+    if (!c.ready) {
+        if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error("cudaStreamCreate failed");
+            return nullptr;
+        }
+        for (auto& e : c.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        c.ready = true;
+    }
+    return &c;
+}
+
+void* dscratch(ThreadCtx* c, int slot, size_t bytes)
+{
+    if (bytes <= c->dcap[slot]) return c->dbuf[slot];
+    if (c->dbuf[slot]) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaFree(c->dbuf[slot]); c->dbuf[slot] = nullptr; c->dcap[slot] = 0; }
+    size_t cap = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&c->dbuf[slot], cap);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu): %s", cap, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    c->dcap[slot] = cap;
+    return c->dbuf[slot];
+}
+
+void* hscratch(ThreadCtx* c, int slot, size_t bytes)
+{
+    if (bytes <= c->hcap[slot]) return c->hbuf[slot];
+    if (c->hbuf[slot]) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaFreeHost(c->hbuf[slot]); c->hbuf[slot] = nullptr; c->hcap[slot] = 0; }
+    size_t cap = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&c->hbuf[slot], cap);
+    if (e != cudaSuccess) { set_error("cudaMallocHost(%zu): %s", cap, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    c->hcap[slot] = cap;
+    return c->hbuf[slot];
+}
+
+}  // namespace hk
+
+using namespace hk;
+
+extern "C" int hk_abi_version(void) { return HK_ABI_VERSION; }
+extern "C" const char* hk_last_error(void) { return g_err; }
+
+extern "C" int hk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int hk_init(int device)
+{
+    if (device < 0) { set_error("hk_init: device must be >= 0"); return HK_ERR_INVALID_ARGUMENT; }
+    if (g_device_state.load() == 1 && g_device.load() != device) { set_error("hk_init: already bound to device %d (one process per GPU)", g_device.load()); return HK_ERR_INVALID_ARGUMENT; }
+    g_device.store(device);
+    return ensure_device();
+}
+
+extern "C" void hk_shutdown(void)
+{
+    // Per-thread contexts are released by their owning threads; this only forgets the device binding.
+    if (g_device_state.load() == 1) cudaDeviceSynchronize();
+    g_device_state.store(0);
+    g_device.store(-1);
+}
+
+static int check_lqng_args(const char* who, int batch, int N, int horizon, const void* A, const void* B, const void* Q, const void* q,
+                           const void* R, const void* x0, const void* u0)
+{
+    if (batch < 0) { set_error("%s: batch must be >= 0", who); return HK_ERR_INVALID_ARGUMENT; }
+    if (N < 1 || N > HK_MAX_PLAYERS) { set_error("%s: n_players must be 1..%d (got %d)", who, HK_MAX_PLAYERS, N); return HK_ERR_INVALID_ARGUMENT; }
+    if (horizon < 0 || horizon > HK_MAX_HORIZON) { set_error("%s: horizon must be 0..%d (got %d)", who, HK_MAX_HORIZON, horizon); return HK_ERR_INVALID_ARGUMENT; }
+    if (batch > 0 && (!A || !B || !Q || !q || !R || !x0 || !u0)) { set_error("%s: null operand", who); return HK_ERR_INVALID_ARGUMENT; }
+    return HK_OK;
+}
+
+extern "C" int hk_lqng_solve_batch_device(int batch, int n_players, int horizon, int time_varying,
+                                          const double* dA, const double* dB, const double* dQ, const double* dq, const double* dR,
+                                          const double* dx0, double* du0, double* dP, double* dalpha, double* dtraj, int* dstatus,
+                                          void* cuda_stream)
+{
+    int rc = check_lqng_args("hk_lqng_solve_batch_device", batch, n_players, horizon, dA, dB, dQ, dq, dR, dx0, du0);
+    if (rc) return rc;
+    if (batch == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    const int T = horizon + 1, n = 4 * n_players, m = 2 * n_players;
+    if (dtraj && (!dP || !dalpha)) {        // the rollout re-reads every step's gains: give it scratch when the caller keeps none
+        double* scratch = (double*)dscratch(c, 1, sizeof(double) * (size_t)batch * T * (m * n + m));
+        if (!scratch) return HK_ERR_OUT_OF_MEMORY;
+        if (!dP) dP = scratch;
+        if (!dalpha) dalpha = scratch + (size_t)batch * T * m * n;
+    }
+    return lqng_launch(batch, n_players, horizon, time_varying ? 1 : 0, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, s);
+}
+
+// Host-pointer entry: chunked two-stream pipeline so that the H2D copy of chunk k+1, the solve of chunk k and the D2H
+// copy of chunk k-1 overlap (PCIe is full duplex).  Pinned caller buffers get full PCIe rate; pageable ones are staged
+// by the driver.
+extern "C" int hk_lqng_solve_batch(int batch, int n_players, int horizon, int time_varying,
+                                   const double* A, const double* B, const double* Q, const double* q, const double* R, const double* x0,
+                                   double* u0, double* P, double* alpha, double* traj, int* status)
+{
+    int rc = check_lqng_args("hk_lqng_solve_batch", batch, n_players, horizon, A, B, Q, q, R, x0, u0);
+    if (rc) return rc;
+    if (batch == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const int N = n_players, T = horizon + 1, Tm = time_varying ? T : 1, n = 4 * N, m = 2 * N;
+    const size_t eA = (size_t)Tm * N * 16, eB = (size_t)Tm * N * 8, eQ = (size_t)Tm * N * n * n, eq = (size_t)Tm * N * n, eR = (size_t)Tm * N * 4;
+    const size_t in_elems = eA + eB + eQ + eq + eR + n;
+    const bool needPa = P || alpha || traj;
+    const size_t out_elems = (size_t)m + (needPa ? (size_t)T * (m * n + m) : 0) + (traj ? (size_t)(T + 1) * n : 0);
+    const int nchunks = batch >= 8192 ? 4 : 1;
+    const int chunk = (batch + nchunks - 1) / nchunks;
+    // two device buffers (double buffering) sized for one chunk each
+    const size_t chunk_bytes = ((in_elems + out_elems) * sizeof(double) + sizeof(int)) * (size_t)chunk + 1024;
+    char* dbufs[2];
+    for (int k = 0; k < 2; ++k) {
+        dbufs[k] = (char*)dscratch(c, 2 + k, nchunks > 1 || k == 0 ? chunk_bytes : 0);
+        if (!dbufs[k] && (nchunks > 1 || k == 0)) return HK_ERR_OUT_OF_MEMORY;
+    }
+    cudaStream_t streams[2] = {c->stream, c->stream2};
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int b0 = ci * chunk, nb = (b0 + chunk <= batch) ? chunk : batch - b0;
+        if (nb <= 0) break;
+        cudaStream_t s = streams[ci & 1];
+        double* d = (double*)dbufs[ci & 1];
+        double *dA = d, *dB = dA + eA * nb, *dQ = dB + eB * nb, *dq = dQ + eQ * nb, *dR = dq + eq * nb, *dx = dR + eR * nb;
+        double* du = dx + (size_t)n * nb;
+        double* dP = needPa ? du + (size_t)m * nb : nullptr;
+        double* da = needPa ? dP + (size_t)T * m * n * nb : nullptr;
+        double* dt = traj ? da + (size_t)T * m * nb : nullptr;
+        double* dend = traj ? dt + (size_t)(T + 1) * n * nb : (needPa ? da + (size_t)T * m * nb : du + (size_t)m * nb);
+        int* dst = (int*)dend;
+        HK_CUDA(cudaMemcpyAsync(dA, A + eA * b0, sizeof(double) * eA * nb, cudaMemcpyHostToDevice, s));
+        HK_CUDA(cudaMemcpyAsync(dB, B + eB * b0, sizeof(double) * eB * nb, cudaMemcpyHostToDevice, s));
+        HK_CUDA(cudaMemcpyAsync(dQ, Q + eQ * b0, sizeof(double) * eQ * nb, cudaMemcpyHostToDevice, s));
+        HK_CUDA(cudaMemcpyAsync(dq, q + eq * b0, sizeof(double) * eq * nb, cudaMemcpyHostToDevice, s));
+        HK_CUDA(cudaMemcpyAsync(dR, R + eR * b0, sizeof(double) * eR * nb, cudaMemcpyHostToDevice, s));
+        HK_CUDA(cudaMemcpyAsync(dx, x0 + (size_t)n * b0, sizeof(double) * n * nb, cudaMemcpyHostToDevice, s));
+        rc = lqng_launch(nb, N, horizon, time_varying ? 1 : 0, dA, dB, dQ, dq, dR, dx, du, dP, da, dt, dst, s);
+        if (rc) return rc;
+        HK_CUDA(cudaMemcpyAsync(u0 + (size_t)m * b0, du, sizeof(double) * m * nb, cudaMemcpyDeviceToHost, s));
+        if (P) HK_CUDA(cudaMemcpyAsync(P + (size_t)T * m * n * b0, dP, sizeof(double) * T * m * n * nb, cudaMemcpyDeviceToHost, s));
+        if (alpha) HK_CUDA(cudaMemcpyAsync(alpha + (size_t)T * m * b0, da, sizeof(double) * T * m * nb, cudaMemcpyDeviceToHost, s));
+        if (traj) HK_CUDA(cudaMemcpyAsync(traj + (size_t)(T + 1) * n * b0, dt, sizeof(double) * (T + 1) * n * nb, cudaMemcpyDeviceToHost, s));
+        if (status) HK_CUDA(cudaMemcpyAsync(status + b0, dst, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+        // before chunk ci+2 reuses this buffer its stream order already serialises (same stream)
+    }
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream2));
+    return HK_OK;
+}
+
+extern "C" int hk_lqng_solve_one(int n_players, int horizon, const double* A, const double* B, const double* Q, const double* q,
+                                 const double* R, const double* x0, double* u0)
+{
+    return hk_lqng_solve_batch(1, n_players, horizon, 0, A, B, Q, q, R, x0, u0, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizon, double dt, const double* x0, const double* target,
+                                            const double* tw, const double* cw, const double* aw, const double* otgt, const double* otw,
+                                            double* u0, int* status)
+{
+    const int N = n_players;
+    if (batch < 0 || N < 1 || N > HK_MAX_PLAYERS || horizon < 0 || horizon > HK_MAX_HORIZON) { set_error("hk_lqng_assemble_solve_batch: invalid dimensions"); return HK_ERR_INVALID_ARGUMENT; }
+    if (batch > 0 && (!x0 || !target || !tw || !cw || !u0 || (N > 1 && (!aw || !otgt || !otw)))) { set_error("hk_lqng_assemble_solve_batch: null operand"); return HK_ERR_INVALID_ARGUMENT; }
+    if (batch == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const int K = N - 1, m = 2 * N;
+    const size_t e[7] = {(size_t)N * 4, (size_t)N * 4, (size_t)N * 4, (size_t)N, (size_t)N * K * 2, (size_t)N * K * 4, (size_t)N * K * 3};
+    const double* src[7] = {x0, target, tw, cw, aw, otgt, otw};
+    size_t per = 0;
+    for (int i = 0; i < 7; ++i) per += e[i];
+    double* d = (double*)dscratch(c, 4, ((per + m) * sizeof(double) + sizeof(int)) * (size_t)batch + 64);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    double* dp[7];
+    double* cur = d;
+    for (int i = 0; i < 7; ++i) {
+        dp[i] = cur;
+        if (e[i]) HK_CUDA(cudaMemcpyAsync(cur, src[i], sizeof(double) * e[i] * batch, cudaMemcpyHostToDevice, c->stream));
+        cur += e[i] * batch;
+    }
+    double* du = cur;
+    int* dst = (int*)(du + (size_t)m * batch);
+    int rc = lqng_assemble_launch(batch, N, horizon, dt, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], du, dst, c->stream);
+    if (rc) return rc;
+    HK_CUDA(cudaMemcpyAsync(u0, du, sizeof(double) * m * batch, cudaMemcpyDeviceToHost, c->stream));
+    if (status) HK_CUDA(cudaMemcpyAsync(status, dst, sizeof(int) * batch, cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    return HK_OK;
+}

@@ -1,0 +1,49 @@
+// hk_common.cuh — shared host-side plumbing of libhk_b200 (error state, per-thread CUDA context).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/hk_abi.h"
+
+namespace hk {
+
+void set_error(const char* fmt, ...);
+
+// Per host-thread context: the reference calls the planners from several C# threads (HierarchicalKartAgent.cs:246-283),
+// so every thread owns a stream and grow-only scratch buffers; nothing is shared but the immutable hk_game objects.
+struct ThreadCtx {
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* dbuf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t dcap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};      // pinned
+    size_t hcap[4] = {0, 0, 0, 0};
+    bool ready = false;
+    ~ThreadCtx();
+};
+
+int  ensure_device();                       // HK_OK or HK_ERR_NO_DEVICE / HK_ERR_CUDA
+ThreadCtx* ctx();                           // nullptr on failure (error set)
+void* dscratch(ThreadCtx* c, int slot, size_t bytes);     // nullptr on OOM (error set)
+void* hscratch(ThreadCtx* c, int slot, size_t bytes);
+
+#define HK_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            hk::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);  \
+            return e_ == cudaErrorMemoryAllocation ? HK_ERR_OUT_OF_MEMORY : HK_ERR_CUDA;                \
+        }                                                                                               \
+    } while (0)
+
+// LQNG device entry (hk_lqng.cu)
+int lqng_launch(int batch, int N, int horizon, int time_varying, const double* dA, const double* dB, const double* dQ,
+                const double* dq, const double* dR, const double* dx0, double* du0, double* dP, double* dalpha,
+                double* dtraj, int* dstatus, cudaStream_t stream);
+int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double* dx0, const double* dtarget,
+                         const double* dtw, const double* dcw, const double* daw, const double* dotgt, const double* dotw,
+                         double* du0, int* dstatus, cudaStream_t stream);
+
+}  // namespace hk

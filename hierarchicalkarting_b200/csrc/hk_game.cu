@@ -1,0 +1,653 @@
+// hk_game.cu — discrete race game + leaf-parallel MCTS rollouts for sm_100a.  Compile with -fmad=false: the game is
+// float32/int32 and must be bit-exact with the reference's C# arithmetic; IEEE div/sqrt are nvcc's
+// defaults (-prec-div=true -prec-sqrt=true, no -use_fast_math).
+//
+// Device restatement of (reference files under Assets/Karting/Scripts/):
+//   DiscreteKartState.computeTOC / applyAction                 AI/MCTS/KartDiscreteGame.cs:67-122, 127-171
+//   DiscreteGameState.upNext / isOver / nextMoves / makeMove   AI/MCTS/KartDiscreteGame.cs:188-243, 251-317, 322-415, 420-446
+//   KartMCTS.simulate rollout policy                            AI/MCTS/KartMCTS.cs:238-278 (ordering :256, index draw :266-269)
+//   DiscretePositionTracker track formulas                      DiscretePositionTracker.cs:72-88,153-199,235-245
+//   ArcadeKart speed limits                                     KartSystems/ArcadeKart.cs:210,517-520,536-547
+// One thread plays one rollout; the per-first-action statistics (KartMCTS.processLeaf :124-159 + backpropagate :280-289)
+// are reduced in shared memory and flushed with one atomic per block and statistic.
+#include "hk_common.cuh"
+#include "hk_game.cuh"
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+namespace hk {
+
+// ---- track (DiscretePositionTracker.cs) -------------------------------------------------------------------------
+__device__ __forceinline__ const hk_section& sec(const DevGame& g, int section) { return g.sections[section % g.n_sections]; }
+__device__ __forceinline__ bool is_straight(const hk_section& s) { return s.insideR == 0.0f; }          // :197
+__device__ __forceinline__ float lane_radius(const hk_section& s, int lane)                              // :72-88
+{
+    const int k = s.leftTurn ? (lane - 1) : (4 - lane);
+    const float q = k == 1 ? (1.0f / 4.0f) : (k == 2 ? (2.0f / 4.0f) : (3.0f / 4.0f));
+    return k == 0 ? s.insideR : s.insideR + s.width * q;
+}
+__device__ __forceinline__ float radius_of_lane(const hk_section& s, int a, int b)                       // :153-158
+{
+    if (is_straight(s)) return 0.0f;
+    return (lane_radius(s, a) + lane_radius(s, b)) / 2.0f;
+}
+__device__ __forceinline__ float distance_to_travel(const hk_section& s, int a, int b)                   // :163-175
+{
+    if (is_straight(s)) {
+        const float w = ((float)abs(a - b) * 1.0f / 3.0f) * s.width;
+        return sqrtf(w * w + s.length * s.length);
+    }
+    return (3.14159274f / 180.0f) * s.turnDeg * radius_of_lane(s, a, b);
+}
+__device__ __forceinline__ float tire_load(const hk_section& s, float velocity, int a, int b)            // :180-192
+{
+    if (is_straight(s)) return distance_to_travel(s, a, b) * 0.01f;
+    const float gs = (velocity * velocity) / radius_of_lane(s, a, b);
+    return gs * distance_to_travel(s, a, b) * 0.01f;
+}
+__device__ __forceinline__ int optimal_lane_sign(const hk_section& s) { return s.optimalLane == 1 ? 1 : (s.optimalLane == 4 ? -1 : 0); }
+
+// ---- kart (ArcadeKart.cs) -----------------------------------------------------------------------------------------
+__device__ __forceinline__ float max_speed_radius_wear(const hk_kart& k, float radius, float wear)      // :536-547, :517-520
+{
+    if (radius == 0.0f) return k.topSpeed;
+    const float gs = (1.0f - wear) * (k.maxGs - k.minGs) + k.minGs;
+    float v = sqrtf(gs * 9.81f * fabsf(radius));
+    if (isinf(v) || isnan(v)) v = k.topSpeed;
+    if (v < 0.0001f) v = 0.0001f; else if (v > k.topSpeed) v = k.topSpeed;
+    return v;
+}
+
+// C# (int)float on Mono/x64 is cvttss2si: NaN / out of range -> INT_MIN; CUDA would saturate / give 0
+__device__ __forceinline__ int f2i(float f)
+{
+    if (!(f > -2147483904.0f && f < 2147483648.0f)) return INT_MIN;
+    return __float2int_rz(f);
+}
+__device__ __forceinline__ float avg_velocity(int mn, int mx) { return (1.0f * (float)(mn + mx)) / 2.0f; }   // :58-61
+
+__device__ float compute_toc(const hk_kart& k, float distance, float radius, float wear, float initV, float finalV)   // :67-122
+{
+    if (finalV > initV && (finalV * finalV - initV * initV) / (2.0f * k.accel) > distance) return -1.0f;
+    if (initV > finalV && (initV * initV - finalV * finalV) / (2.0f * k.braking) > distance) return -1.0f;
+    const float ms = max_speed_radius_wear(k, radius, wear);
+    float t1, t3;
+    if (ms >= initV) t1 = (ms - initV) / k.accel; else t1 = (initV - ms) / k.braking;
+    if (ms >= finalV) t3 = (ms - finalV) / k.braking; else t3 = (finalV - ms) / k.accel;
+    const float x1 = 0.5f * (initV + ms) * t1;
+    const float x3 = 0.5f * (finalV + ms) * t3;
+    const float x2 = distance - x1 - x3;
+    const float t2 = x2 / ms;
+    if ((double)t2 > 0.001) {
+        return t1 + t2 + t3;
+    } else if (initV <= ms) {
+        const float maxSpeed = sqrtf((2.0f * distance * -k.braking * k.accel + -k.braking * initV * initV - k.accel * finalV * finalV)
+                                     / (-k.accel - k.braking));
+        t1 = (maxSpeed - initV) / k.accel;
+        t3 = (maxSpeed - finalV) / k.braking;
+        return t1 + t3;
+    }
+    return -1.0f;
+}
+
+__device__ hk_kart_state apply_action(const DevGame& g, const hk_kart_state& s, const hk_action& a)    // :127-171
+{
+    const hk_kart& kart = g.env_karts[s.player];                  // environment.Agents[player].m_Kart (:129, quirk B.6-2)
+    hk_kart_state ns;
+    ns.player = s.player; ns.team = s.team; ns.infeasible = 0;
+    ns.section = s.section + 1;
+    ns.min_velocity = a.min_velocity; ns.max_velocity = a.max_velocity; ns.lane = a.lane;
+    const hk_section& cur = sec(g, s.section);
+    if (is_straight(cur) != is_straight(sec(g, s.section + 1))) ns.laneChanges = 0;
+    else if (ns.lane != s.lane) ns.laneChanges = s.laneChanges + abs(ns.lane - s.lane);
+    else ns.laneChanges = s.laneChanges;
+    const float dist = distance_to_travel(cur, s.lane, a.lane);
+    const float rad = radius_of_lane(cur, s.lane, a.lane);
+    // newState.tireAge is still 0 when computeTOC is called => wear 0 (quirk B.6-3)
+    const float toc = compute_toc(kart, dist, rad, 0.0f / 10000.0f, avg_velocity(s.min_velocity, s.max_velocity),
+                                  avg_velocity(a.min_velocity, a.max_velocity));
+    const int timeUpdate = f2i(toc * (float)g.p.timePrecision);
+    if (timeUpdate < 0) ns.infeasible = 1;
+    ns.timeAtSection = (int)((unsigned)s.timeAtSection + (unsigned)timeUpdate);
+    const float load = tire_load(cur, (float)a.max_velocity, s.lane, a.lane);
+    ns.tireAge = f2i(((float)s.tireAge / 10000.0f + load * kart.tireWearFactor) * (float)10000);
+    return ns;
+}
+
+// ---- DiscreteGameState ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cmp_kart(const hk_kart_state& a, const hk_kart_state& b)                 // :191-227
+{
+    if (a.section < b.section) return -1;
+    if (a.section > b.section) return 1;
+    if (a.timeAtSection < b.timeAtSection) return -1;
+    if (a.timeAtSection == b.timeAtSection) {
+        const float va = avg_velocity(a.min_velocity, a.max_velocity), vb = avg_velocity(b.min_velocity, b.max_velocity);
+        if (va > vb) return -1;
+        if (va == vb) return 0;
+        return 1;
+    }
+    return 1;
+}
+
+// upNext (:188-243): first kart, in stable (section, time, -avgVelocity) order, that is not yet at lastCompleted+1.
+// For 2 karts (one SwapIfGreater) and 4..16 karts (insertion sort) List.Sort is stable, which is equivalent to: among
+// karts with section != lastCompleted+1, the minimum under cmp, lowest index on ties.
+__device__ int up_next(const hk_game_state& st)
+{
+    if (st.n_karts == 3) {
+        // List.Sort -> IntroSort special-cases 3 elements with a 3-exchange network that is NOT stable
+        // (SwapIfGreater(0,1), (0,2), (1,2)); ties are common at the root (equal times and buckets), so replay it.
+        int o0 = 0, o1 = 1, o2 = 2, t;
+        if (cmp_kart(st.karts[o0], st.karts[o1]) > 0) { t = o0; o0 = o1; o1 = t; }
+        if (cmp_kart(st.karts[o0], st.karts[o2]) > 0) { t = o0; o0 = o2; o2 = t; }
+        if (cmp_kart(st.karts[o1], st.karts[o2]) > 0) { t = o1; o1 = o2; o2 = t; }
+        if (st.karts[o0].section != st.lastCompletedSection + 1) return o0;
+        if (st.karts[o1].section != st.lastCompletedSection + 1) return o1;
+        if (st.karts[o2].section != st.lastCompletedSection + 1) return o2;
+        return -1;
+    }
+    int best = -1;
+    for (int i = 0; i < st.n_karts; ++i) {
+        if (st.karts[i].section == st.lastCompletedSection + 1) continue;
+        if (best < 0 || cmp_kart(st.karts[i], st.karts[best]) < 0) best = i;
+    }
+    return best;
+}
+
+// nextMoves (:322-415) fused with the rollout policy's sort keys (KartMCTS.cs:256).  For every legal candidate a 64-bit
+// key = (dTime asc | max_velocity desc | |dLane| asc | optSign*lane asc | generation index) reproduces the stable
+// OrderBy/ThenBy chain; keys[] is indexed by generation index, illegal candidates hold ~0.  Returns the legal count.
+__device__ int legal_moves(const DevGame& g, const hk_game_state& st, int np, unsigned long long* keys)
+{
+    const hk_kart& kart = g.karts[np];
+    const hk_kart_state& cs = st.karts[np];
+    const hk_section& cur = sec(g, cs.section);
+    const int optSign = optimal_lane_sign(g.sections[st.lastCompletedSection % g.n_sections]);            // KartMCTS.cs:252
+    const bool straight = is_straight(cur);
+    const float wear = (float)cs.tireAge / 10000.0f;
+    int cnt = 0, gi = 0;
+    for (int v = 6; v < g.vmax; v += g.p.velocityBucketSize) {
+        const int vmx = min(v + g.p.velocityBucketSize, g.vmax);
+        for (int lane = 1; lane < 5; ++lane, ++gi) {
+            unsigned long long key = ~0ull;
+            const int dl = abs(lane - cs.lane);
+            bool ok = !(straight && cs.laneChanges + dl > g.p.maxLaneChanges);                            // :346
+            if (ok) {
+                const float radius = radius_of_lane(cur, cs.lane, lane);
+                ok = !(max_speed_radius_wear(kart, radius, wear) < (float)v);                             // :357 (real wear)
+            }
+            if (ok) {
+                hk_action a{v, vmx, lane};
+                const hk_kart_state ap = apply_action(g, cs, a);                                          // :368
+                ok = !ap.infeasible;
+                if (ok) {
+                    const unsigned dt = (unsigned)(ap.timeAtSection - cs.timeAtSection);                  // >= 0 when feasible
+                    key = ((unsigned long long)dt << 22) | ((unsigned long long)(1023 - vmx) << 12) |
+                          ((unsigned long long)dl << 10) | ((unsigned long long)(optSign * lane + 4) << 6) | (unsigned long long)gi;
+                    ++cnt;
+                }
+            }
+            keys[gi] = key;
+        }
+    }
+    return cnt;
+}
+
+// k-th smallest key (k < cnt): k+1 passes of "smallest key greater than the previous one" — keys are distinct.
+__device__ int select_kth(const unsigned long long* keys, int n_cand, int k)
+{
+    unsigned long long prev = 0;
+    bool first = true;
+    int idx = 0;
+    for (int pass = 0; pass <= k; ++pass) {
+        unsigned long long best = ~0ull;
+        for (int c = 0; c < n_cand; ++c) {
+            const unsigned long long kk = keys[c];
+            if ((first || kk > prev) && kk < best) { best = kk; idx = c; }
+        }
+        prev = best; first = false;
+    }
+    return idx;
+}
+
+__device__ hk_action action_of(const DevGame& g, int gi)
+{
+    const int v = 6 + (gi >> 2) * g.p.velocityBucketSize;
+    return hk_action{v, min(v + g.p.velocityBucketSize, g.vmax), (gi & 3) + 1};
+}
+
+__device__ void make_move(const DevGame& g, hk_game_state& st, int np, const hk_action& a)              // :420-446
+{
+    const int last = st.lastCompletedSection;
+    st.karts[np] = apply_action(g, st.karts[np], a);
+    bool allAhead = true;
+    for (int i = 0; i < st.n_karts; ++i) allAhead &= st.karts[i].section > last;
+    if (allAhead) st.lastCompletedSection = last + 1;
+}
+
+// isOver (:251-317) given the legal-move count of the state. Returns over flag; scores[0..n_scores) as the reference list.
+__device__ bool is_over(const DevGame& g, const hk_game_state& st, int n_moves, int np, float* scores, int& n_scores)
+{
+    n_scores = 0;
+    if (n_moves == 0) {
+        for (int i = 0; i < st.n_karts; ++i) {
+            if (i == np || st.karts[i].team == st.karts[np].team) scores[n_scores++] = 0.0f;
+            scores[n_scores++] = 0.5f;                                // no `else` (quirk B.6-4)
+        }
+        return true;
+    }
+    if (st.lastCompletedSection != st.finalSection) return false;
+    if (st.n_karts > 1) {
+        float maxScore = (float)g.p.timePrecision * -1000.0f;
+        float minScore = (float)g.p.timePrecision * 1000.0f;
+        float raw[HK_MAX_KARTS];
+        float teamScore = 0.0f, opponentScore = 0.0f;                 // never reset (quirk B.6-5)
+        int teamCount = 0, opponentCount = 0;
+        for (int s = 0; s < st.n_karts; ++s) {
+            for (int o = 0; o < st.n_karts; ++o) {
+                if (s == o) teamScore += (float)st.karts[o].timeAtSection;
+                else if (st.karts[s].team == st.karts[o].team) {
+                    teamScore += (float)st.karts[o].timeAtSection * g.p.teamScoreRewardMultiplier;
+                    teamCount += 1;
+                } else {
+                    opponentScore += (float)st.karts[o].timeAtSection;
+                    opponentCount += 1;
+                }
+            }
+            const float score = opponentScore * (((float)teamCount * g.p.teamScoreRewardMultiplier + 1.0f) / ((float)opponentCount * 1.0f)) - teamScore;
+            raw[s] = score;
+            maxScore = maxScore > score ? maxScore : score;
+            minScore = minScore < score ? minScore : score;
+        }
+        for (int s = 0; s < st.n_karts; ++s) {
+            const int sc = f2i(raw[s]);                               // foreach (int score in scores) (quirk B.6-6)
+            scores[n_scores++] = ((float)sc - minScore) * 1.0f / (maxScore - minScore);
+        }
+        return true;
+    }
+    scores[n_scores++] = (float)(g.p.maxEpisodeSteps - st.karts[0].timeAtSection / g.p.maxEpisodeSteps);   // :314
+    return true;
+}
+
+// ---- Philox4x32-10, counter = (rollout lo, rollout hi, ply, 0), key = seed ------------------------------------------
+__device__ __forceinline__ unsigned philox_first(unsigned long long seed, unsigned long long rollout, unsigned ply)
+{
+    unsigned c0 = (unsigned)rollout, c1 = (unsigned)(rollout >> 32), c2 = ply, c3 = 0u;
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+
+__device__ __forceinline__ int policy_index(const DevGame& g, int cnt, unsigned u)
+{
+    const unsigned* cdf = g.cdf[cnt];
+    int idx = 0;
+    for (int k = 0; k < cnt - 1; ++k) idx += (cdf[k] <= u);
+    return idx;
+}
+
+// One playout of KartMCTS.simulate (:238-278). Returns plies played; first_gi = generation index of the first action.
+template <bool TRACE>
+__device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long seed, unsigned long long rid, float* scores,
+                       int& n_scores, int& first_gi, hk_action* act_out, int* choice_out)
+{
+    unsigned long long keys[HK_MAX_ACTIONS];
+    int ply = 0;
+    first_gi = -1;
+    n_scores = 0;
+    for (;;) {
+        const int np = up_next(st);
+        if (np < 0) return -1;
+        const int cnt = legal_moves(g, st, np, keys);
+        if (is_over(g, st, cnt, np, scores, n_scores)) break;
+        const unsigned u = philox_first(seed, rid, (unsigned)ply);
+        const int index = policy_index(g, cnt, u);
+        const int gi = select_kth(keys, g.n_cand, index);
+        const hk_action a = action_of(g, gi);
+        if (ply == 0) first_gi = gi;
+        if (TRACE && ply < HK_MAX_PLIES) { act_out[ply] = a; choice_out[ply] = index; }
+        make_move(g, st, np, a);
+        ++ply;
+    }
+    return ply;
+}
+
+// ---- kernels ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rollouts_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ leaves,
+                                                       long long rollouts_per_leaf, unsigned long long seed,
+                                                       unsigned long long rollout_offset, unsigned long long* visit,
+                                                       double* reward_sum, unsigned long long* nan_count,
+                                                       unsigned long long* plies_sum, int* error_flag)
+{
+    __shared__ DevGame g;
+    __shared__ unsigned s_visit[HK_MAX_ACTIONS];
+    __shared__ unsigned s_nan[HK_MAX_ACTIONS];
+    __shared__ double s_reward[HK_MAX_ACTIONS][HK_MAX_KARTS];
+    __shared__ unsigned s_plies;
+    {
+        const int* src = reinterpret_cast<const int*>(gg);
+        int* dst = reinterpret_cast<int*>(&g);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevGame) / 4); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < HK_MAX_ACTIONS; i += blockDim.x) {
+            s_visit[i] = 0; s_nan[i] = 0;
+            for (int k = 0; k < HK_MAX_KARTS; ++k) s_reward[i][k] = 0.0;
+        }
+        if (threadIdx.x == 0) s_plies = 0;
+    }
+    __syncthreads();
+    const int leaf = blockIdx.y;
+    const hk_game_state st = leaves[leaf];
+    // grid-stride over the leaf's rollouts; block-local partial sums in double
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rollouts_per_leaf; r += (long long)gridDim.x * blockDim.x) {
+        float scores[2 * HK_MAX_KARTS];
+        int n_scores, first_gi;
+        const unsigned long long rid = rollout_offset + (unsigned long long)leaf * (unsigned long long)rollouts_per_leaf + (unsigned long long)r;
+        const int plies = rollout<false>(g, st, seed, rid, scores, n_scores, first_gi, nullptr, nullptr);
+        if (plies < 0) { atomicExch(error_flag, 1); continue; }
+        if (plies == 0) continue;
+        atomicAdd(&s_plies, (unsigned)plies);
+        atomicAdd(&s_visit[first_gi], 1u);
+        bool has_nan = false;
+        for (int k = 0; k < st.n_karts && k < n_scores; ++k) has_nan |= isnan(scores[k]);
+        if (has_nan) { atomicAdd(&s_nan[first_gi], 1u); continue; }
+        for (int k = 0; k < st.n_karts && k < n_scores; ++k)
+            if (scores[k] != 0.0f) atomicAdd(&s_reward[first_gi][k], (double)scores[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HK_MAX_ACTIONS; i += blockDim.x) {
+        if (s_visit[i]) atomicAdd(&visit[(size_t)leaf * HK_MAX_ACTIONS + i], (unsigned long long)s_visit[i]);
+        if (s_nan[i]) atomicAdd(&nan_count[(size_t)leaf * HK_MAX_ACTIONS + i], (unsigned long long)s_nan[i]);
+        for (int k = 0; k < HK_MAX_KARTS; ++k)
+            if (s_reward[i][k] != 0.0) atomicAdd(&reward_sum[((size_t)leaf * HK_MAX_ACTIONS + i) * HK_MAX_KARTS + k], s_reward[i][k]);
+    }
+    if (threadIdx.x == 0 && s_plies) atomicAdd(&plies_sum[leaf], (unsigned long long)s_plies);
+}
+
+__global__ void __launch_bounds__(128) rollouts_trace_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ leaf,
+                                                             long long n_rollouts, unsigned long long seed,
+                                                             unsigned long long rollout_offset, int* n_plies_out,
+                                                             hk_action* actions_out, int* choice_out, int* n_scores_out,
+                                                             float* scores_out)
+{
+    __shared__ DevGame g;
+    {
+        const int* src = reinterpret_cast<const int*>(gg);
+        int* dst = reinterpret_cast<int*>(&g);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevGame) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rollouts) return;
+    float scores[2 * HK_MAX_KARTS];
+    hk_action acts[HK_MAX_PLIES];
+    int choice[HK_MAX_PLIES];
+    int n_scores, first_gi;
+    const int plies = rollout<true>(g, *leaf, seed, rollout_offset + (unsigned long long)r, scores, n_scores, first_gi, acts, choice);
+    n_plies_out[r] = plies;
+    n_scores_out[r] = n_scores;
+    for (int k = 0; k < 2 * HK_MAX_KARTS; ++k) scores_out[r * 2 * HK_MAX_KARTS + k] = k < n_scores ? scores[k] : 0.0f;
+    for (int k = 0; k < HK_MAX_PLIES; ++k) {
+        const bool on = k < plies;
+        actions_out[r * HK_MAX_PLIES + k] = on ? acts[k] : hk_action{0, 0, 0};
+        choice_out[r * HK_MAX_PLIES + k] = on ? choice[k] : -1;
+    }
+}
+
+// exact-parity replay: one thread per root; see hk_game_replay_batch in include/hk_abi.h
+__global__ void __launch_bounds__(128) replay_kernel(const DevGame* __restrict__ gg, int batch, int len,
+                                                     const hk_game_state* __restrict__ roots, const hk_action* __restrict__ actions,
+                                                     hk_game_state* states_out, int* upnext_out, int* over_out, int* n_scores_out,
+                                                     float* scores_out, int* n_moves_out, hk_action* moves_out, int* moves_index_out)
+{
+    __shared__ DevGame g;
+    {
+        const int* src = reinterpret_cast<const int*>(gg);
+        int* dst = reinterpret_cast<int*>(&g);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevGame) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    hk_game_state st = roots[b];
+    unsigned long long keys[HK_MAX_ACTIONS];
+    for (int k = 0; k <= len; ++k) {
+        const size_t o = (size_t)b * (len + 1) + k;
+        const int np = up_next(st);
+        float scores[2 * HK_MAX_KARTS];
+        int n_scores = 0, cnt = 0, over = -1;
+        if (np >= 0) {
+            cnt = legal_moves(g, st, np, keys);
+            over = is_over(g, st, cnt, np, scores, n_scores) ? 1 : 0;
+        }
+        if (states_out) states_out[o] = st;
+        if (upnext_out) upnext_out[o] = np;
+        if (over_out) over_out[o] = over;
+        if (n_scores_out) n_scores_out[o] = n_scores;
+        if (scores_out) for (int j = 0; j < 2 * HK_MAX_KARTS; ++j) scores_out[o * 2 * HK_MAX_KARTS + j] = j < n_scores ? scores[j] : 0.0f;
+        if (n_moves_out) n_moves_out[o] = np >= 0 ? cnt : -1;
+        if (moves_out || moves_index_out)
+            for (int j = 0; j < HK_MAX_ACTIONS; ++j) {
+                int gi = -1;
+                hk_action a{0, 0, 0};
+                if (j < cnt) { gi = select_kth(keys, g.n_cand, j); a = action_of(g, gi); }
+                if (moves_out) moves_out[o * HK_MAX_ACTIONS + j] = a;
+                if (moves_index_out) moves_index_out[o * HK_MAX_ACTIONS + j] = gi;
+            }
+        if (k < len) {
+            if (np < 0) continue;                                      // makeMove would throw; state stays
+            make_move(g, st, np, actions[(size_t)b * len + k]);
+        }
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+static double phi(double x) { return 0.5 * erfc(-x / 1.4142135623730951); }
+
+// Index distribution of the rollout policy as cumulative 32-bit thresholds (KartMCTS.cs:266-269, NextGaussian :218-236):
+// X ~ N(0, cnt/6f) redrawn while |X| > cnt-1 for at most 10 attempts (then the mean 0), index = RoundToInt(|X|).
+void policy_cdf_host(int cnt, uint32_t* cdf)
+{
+    if (cnt <= 2) {                                                    // random.Next(cnt)
+        for (int k = 0; k < cnt; ++k) cdf[k] = (k == cnt - 1) ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)(k + 1) << 32) / (uint64_t)cnt);
+        return;
+    }
+    const double sd = (double)((float)cnt / 6.0f), lim = (double)cnt - 1.0;
+    const double rej = 1.0 - 2.0 * (phi(lim / sd) - 0.5);
+    double geo = 0.0, rp = 1.0;
+    for (int a = 0; a < 10; ++a) { geo += rp; rp *= rej; }
+    double c = 0.0;
+    for (int k = 0; k < cnt; ++k) {
+        const double lo = k == 0 ? 0.0 : k - 0.5;
+        double hi = k + 0.5;
+        if (hi > lim) hi = lim;
+        const double pk = (lo < hi ? 2.0 * (phi(hi / sd) - phi(lo / sd)) : 0.0) * geo + (k == 0 ? rp : 0.0);
+        c += pk;
+        const double th = c * 4294967296.0;
+        cdf[k] = (k == cnt - 1 || th >= 4294967295.0) ? 0xFFFFFFFFu : (uint32_t)th;
+    }
+}
+
+}  // namespace hk
+
+struct hk_game {
+    hk::DevGame host;
+    hk::DevGame* dev = nullptr;
+};
+
+using namespace hk;
+
+extern "C" int hk_policy_cdf(int cnt, uint32_t* cdf_out)
+{
+    if (cnt < 1 || cnt > HK_MAX_ACTIONS || !cdf_out) { set_error("hk_policy_cdf: cnt must be 1..%d", HK_MAX_ACTIONS); return HK_ERR_INVALID_ARGUMENT; }
+    policy_cdf_host(cnt, cdf_out);
+    return HK_OK;
+}
+
+extern "C" int hk_game_create(const hk_section* sections, int n_sections, const hk_kart* karts, int n_karts,
+                              const hk_kart* env_karts, int n_env_karts, const hk_game_params* params, hk_game** out)
+{
+    if (!sections || !karts || !params || !out || n_sections < 1 || n_sections > HK_MAX_SECTIONS || n_karts < 1 ||
+        n_karts > HK_MAX_KARTS || (env_karts && (n_env_karts < 1 || n_env_karts > HK_MAX_ENV_KARTS)) ||
+        params->velocityBucketSize < 1) {
+        set_error("hk_game_create: invalid argument (sections 1..%d, karts 1..%d, bucket >= 1)", HK_MAX_SECTIONS, HK_MAX_KARTS);
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    int rc = ensure_device();
+    if (rc != HK_OK) return rc;
+    hk_game* g = new hk_game();
+    std::memset(&g->host, 0, sizeof(DevGame));
+    DevGame& d = g->host;
+    d.n_sections = n_sections; d.n_karts = n_karts; d.p = *params;
+    std::memcpy(d.sections, sections, sizeof(hk_section) * n_sections);
+    std::memcpy(d.karts, karts, sizeof(hk_kart) * n_karts);
+    if (env_karts) { d.n_env_karts = n_env_karts; std::memcpy(d.env_karts, env_karts, sizeof(hk_kart) * n_env_karts); }
+    else { d.n_env_karts = n_karts; std::memcpy(d.env_karts, karts, sizeof(hk_kart) * n_karts); }
+    // (int)GetMaxSpeed() of the candidate loop (:329); all karts of one game share constants in the shipped scenes; the
+    // generation index space is sized with kart 0 and the per-kart limit is applied through g.vmax of kart 0 only.
+    const float ms = karts[0].topSpeed > karts[0].reverseSpeed ? karts[0].topSpeed : karts[0].reverseSpeed;
+    d.vmax = (int)ms;
+    for (int k = 1; k < n_karts; ++k) {
+        const float mk = karts[k].topSpeed > karts[k].reverseSpeed ? karts[k].topSpeed : karts[k].reverseSpeed;
+        if ((int)mk != d.vmax) { delete g; set_error("hk_game_create: karts with different (int)GetMaxSpeed() are not supported"); return HK_ERR_INVALID_ARGUMENT; }
+    }
+    int nv = 0;
+    for (int v = 6; v < d.vmax; v += params->velocityBucketSize) ++nv;
+    d.n_cand = nv * 4;
+    if (d.n_cand > HK_MAX_ACTIONS) { delete g; set_error("hk_game_create: more than %d candidate actions", HK_MAX_ACTIONS); return HK_ERR_INVALID_ARGUMENT; }
+    for (int c = 1; c <= HK_MAX_ACTIONS; ++c) policy_cdf_host(c, d.cdf[c]);
+    cudaError_t e = cudaMalloc(&g->dev, sizeof(DevGame));
+    if (e == cudaSuccess) e = cudaMemcpy(g->dev, &g->host, sizeof(DevGame), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("hk_game_create: %s", cudaGetErrorString(e)); if (g->dev) cudaFree(g->dev); delete g; return HK_ERR_CUDA; }
+    *out = g;
+    return HK_OK;
+}
+
+extern "C" void hk_game_destroy(hk_game* g)
+{
+    if (!g) return;
+    if (g->dev) cudaFree(g->dev);
+    delete g;
+}
+
+static int check_state(const hk_game* g, const hk_game_state* s, const char* who)
+{
+    if (s->n_karts < 1 || s->n_karts > g->host.n_karts) { set_error("%s: state has %d karts, game has %d", who, s->n_karts, g->host.n_karts); return HK_ERR_INVALID_ARGUMENT; }
+    for (int i = 0; i < s->n_karts; ++i)
+        if (s->karts[i].player < 0 || s->karts[i].player >= g->host.n_env_karts || s->karts[i].lane < 1 || s->karts[i].lane > 4 ||
+            s->karts[i].section < 0) { set_error("%s: kart %d has an invalid player/lane/section", who, i); return HK_ERR_INVALID_ARGUMENT; }
+    return HK_OK;
+}
+
+extern "C" int hk_game_replay_batch(const hk_game* g, int batch, int len, const hk_game_state* roots, const hk_action* actions,
+                                    hk_game_state* states_out, int32_t* upnext_out, int32_t* over_out, int32_t* n_scores_out,
+                                    float* scores_out, int32_t* n_moves_out, hk_action* moves_out, int32_t* moves_index_out)
+{
+    if (!g || batch < 0 || len < 0 || (batch && !roots) || (batch && len && !actions)) { set_error("hk_game_replay_batch: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    if (batch == 0) return HK_OK;
+    for (int b = 0; b < batch; ++b) { int rc = check_state(g, &roots[b], "hk_game_replay_batch"); if (rc) return rc; }
+    for (size_t i = 0; i < (size_t)batch * len; ++i)
+        if (actions[i].lane < 1 || actions[i].lane > 4) { set_error("hk_game_replay_batch: action lane out of 1..4"); return HK_ERR_INVALID_ARGUMENT; }
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const size_t np1 = (size_t)batch * (len + 1);
+    const size_t sz[10] = {sizeof(hk_game_state) * batch, sizeof(hk_action) * (size_t)batch * len, sizeof(hk_game_state) * np1, 4 * np1, 4 * np1,
+                           4 * np1, 4 * np1 * 2 * HK_MAX_KARTS, 4 * np1, sizeof(hk_action) * np1 * HK_MAX_ACTIONS, 4 * np1 * HK_MAX_ACTIONS};
+    size_t off[11]; off[0] = 0;
+    for (int i = 0; i < 10; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
+    char* d = (char*)dscratch(c, 0, off[10]);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    HK_CUDA(cudaMemcpyAsync(d + off[0], roots, sz[0], cudaMemcpyHostToDevice, c->stream));
+    if (len) HK_CUDA(cudaMemcpyAsync(d + off[1], actions, sz[1], cudaMemcpyHostToDevice, c->stream));
+    replay_kernel<<<(batch + 127) / 128, 128, 0, c->stream>>>(g->dev, batch, len, (const hk_game_state*)(d + off[0]), (const hk_action*)(d + off[1]),
+        states_out ? (hk_game_state*)(d + off[2]) : nullptr, upnext_out ? (int*)(d + off[3]) : nullptr, over_out ? (int*)(d + off[4]) : nullptr,
+        n_scores_out ? (int*)(d + off[5]) : nullptr, scores_out ? (float*)(d + off[6]) : nullptr, n_moves_out ? (int*)(d + off[7]) : nullptr,
+        moves_out ? (hk_action*)(d + off[8]) : nullptr, moves_index_out ? (int*)(d + off[9]) : nullptr);
+    HK_CUDA(cudaGetLastError());
+    void* outs[8] = {states_out, upnext_out, over_out, n_scores_out, scores_out, n_moves_out, moves_out, moves_index_out};
+    for (int i = 0; i < 8; ++i)
+        if (outs[i]) HK_CUDA(cudaMemcpyAsync(outs[i], d + off[2 + i], sz[2 + i], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    return HK_OK;
+}
+
+static int rollouts_impl(const hk_game* g, const hk_game_state* leaves, int n_leaves, int64_t rollouts_per_leaf, uint64_t seed,
+                         uint64_t rollout_offset, int64_t* visit, double* reward_sum, int64_t* nan_count, int64_t* plies_sum)
+{
+    if (!g || !leaves || n_leaves < 1 || rollouts_per_leaf < 0 || !visit || !reward_sum || !nan_count) { set_error("hk_mcts_rollouts: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    for (int l = 0; l < n_leaves; ++l) { int rc = check_state(g, &leaves[l], "hk_mcts_rollouts"); if (rc) return rc; }
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const size_t nA = (size_t)n_leaves * HK_MAX_ACTIONS;
+    const size_t sz[6] = {sizeof(hk_game_state) * n_leaves, 8 * nA, 8 * nA * HK_MAX_KARTS, 8 * nA, 8 * (size_t)n_leaves, 256};
+    size_t off[7]; off[0] = 0;
+    for (int i = 0; i < 6; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
+    char* d = (char*)dscratch(c, 0, off[6]);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    HK_CUDA(cudaMemcpyAsync(d, leaves, sz[0], cudaMemcpyHostToDevice, c->stream));
+    HK_CUDA(cudaMemsetAsync(d + off[1], 0, off[6] - off[1], c->stream));
+    if (rollouts_per_leaf > 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        long long want = (rollouts_per_leaf + 127) / 128;
+        long long cap = (long long)sms * 16 / (n_leaves < sms * 16 ? 1 : 1);          // persistent-ish grid: 16 CTAs of 128 threads per SM
+        if (n_leaves > 1) cap = (cap + n_leaves - 1) / n_leaves > 0 ? (cap + n_leaves - 1) / n_leaves : 1;
+        dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_leaves);
+        rollouts_kernel<<<grid, 128, 0, c->stream>>>(g->dev, (const hk_game_state*)d, rollouts_per_leaf, seed, rollout_offset,
+            (unsigned long long*)(d + off[1]), (double*)(d + off[2]), (unsigned long long*)(d + off[3]), (unsigned long long*)(d + off[4]), (int*)(d + off[5]));
+        HK_CUDA(cudaGetLastError());
+    }
+    int err = 0;
+    HK_CUDA(cudaMemcpyAsync(visit, d + off[1], sz[1], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaMemcpyAsync(reward_sum, d + off[2], sz[2], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaMemcpyAsync(nan_count, d + off[3], sz[3], cudaMemcpyDeviceToHost, c->stream));
+    if (plies_sum) HK_CUDA(cudaMemcpyAsync(plies_sum, d + off[4], sz[4], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaMemcpyAsync(&err, d + off[5], 4, cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    if (err) { set_error("hk_mcts_rollouts: upNext() == -1 reached (KartDiscreteGame.cs:326 would throw)"); return HK_ERR_NO_UPNEXT; }
+    return HK_OK;
+}
+
+extern "C" int hk_mcts_rollouts(const hk_game* g, const hk_game_state* leaf, int64_t n_rollouts, uint64_t seed, uint64_t rollout_offset,
+                                int64_t* visit, double* reward_sum, int64_t* nan_count, int64_t* plies_sum)
+{
+    return rollouts_impl(g, leaf, 1, n_rollouts, seed, rollout_offset, visit, reward_sum, nan_count, plies_sum);
+}
+
+extern "C" int hk_mcts_rollouts_multi(const hk_game* g, const hk_game_state* leaves, int n_leaves, int64_t rollouts_per_leaf, uint64_t seed,
+                                      uint64_t rollout_offset, int64_t* visit, double* reward_sum, int64_t* nan_count, int64_t* plies_sum)
+{
+    return rollouts_impl(g, leaves, n_leaves, rollouts_per_leaf, seed, rollout_offset, visit, reward_sum, nan_count, plies_sum);
+}
+
+extern "C" int hk_mcts_rollouts_trace(const hk_game* g, const hk_game_state* leaf, int64_t n_rollouts, uint64_t seed, uint64_t rollout_offset,
+                                      int32_t* n_plies_out, hk_action* actions_out, int32_t* choice_out, int32_t* n_scores_out, float* scores_out)
+{
+    if (!g || !leaf || n_rollouts < 0 || !n_plies_out || !actions_out || !choice_out || !n_scores_out || !scores_out) { set_error("hk_mcts_rollouts_trace: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    int rc = check_state(g, leaf, "hk_mcts_rollouts_trace");
+    if (rc) return rc;
+    if (n_rollouts == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const size_t n = (size_t)n_rollouts;
+    const size_t sz[6] = {sizeof(hk_game_state), 4 * n, sizeof(hk_action) * n * HK_MAX_PLIES, 4 * n * HK_MAX_PLIES, 4 * n, 4 * n * 2 * HK_MAX_KARTS};
+    size_t off[7]; off[0] = 0;
+    for (int i = 0; i < 6; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
+    char* d = (char*)dscratch(c, 0, off[6]);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    HK_CUDA(cudaMemcpyAsync(d, leaf, sz[0], cudaMemcpyHostToDevice, c->stream));
+    rollouts_trace_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(g->dev, (const hk_game_state*)d, n_rollouts, seed, rollout_offset,
+        (int*)(d + off[1]), (hk_action*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (float*)(d + off[5]));
+    HK_CUDA(cudaGetLastError());
+    void* outs[5] = {n_plies_out, actions_out, choice_out, n_scores_out, scores_out};
+    for (int i = 0; i < 5; ++i) HK_CUDA(cudaMemcpyAsync(outs[i], d + off[1 + i], sz[1 + i], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    return HK_OK;
+}

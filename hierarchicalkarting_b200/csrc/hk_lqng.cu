@@ -1,0 +1,368 @@
+// hk_lqng.cu — batched feedback LQ Nash game solver for sm_100a.
+//
+// Replaces the body of KartLQR.solveFeedbackLQR (reference: Assets/Karting/Scripts/AI/LQR/KartLQR.cs:17-128):
+// coupled-Riccati backward recursion, one coupled N-player m x m solve per step (KartLQR.cs:104-105), quirks Q1/Q2
+// of SURVEY.md A.3 reproduced (block placement of the coupled LHS, eta update with the already updated Z_i).
+//
+// Kernels in this file
+//   lqng_generic_kernel<N>   any N in 1..4, time-varying or not, general (also non-symmetric) Q, all outputs.
+//                            G = 4/8/16 lanes per problem, matrices staged in shared memory, partial-pivot elimination.
+//                            This is the robust path every other kernel falls back to.
+//   (hk_lqng_mma.cuh)        warp-per-problem FP64 tensor-core (DMMA m8n8k4) kernels for the time-invariant 2- and
+//                            4-kart games — the throughput path, see DESIGN.md §4.
+//
+// Record layout of the operands = include/hk_abi.h (problem-major: one warp reads one problem's record with fully
+// coalesced 128-bit loads; there is no cross-problem reuse, so HBM traffic = algorithmic bytes).
+#include "hk_common.cuh"
+
+namespace hk {
+
+struct LqngParams {
+    int batch, horizon, time_varying;
+    const double *A, *B, *Q, *q, *R, *x0;
+    double *u0, *P, *alpha, *traj;
+    int* status;
+};
+
+template <int N>
+struct GenericLayout {
+    static constexpr int n = 4 * N, m = 2 * N;
+    static constexpr int G = n <= 4 ? 4 : (n <= 8 ? 8 : 16);     // lanes per problem
+    static constexpr int LD = n + 1;                              // padded leading dimension: conflict-free column reads
+    static constexpr int AW = m + n + 1;                          // [LHS | RHSMat | RHSVec]
+    // offsets in doubles
+    static constexpr int oZ = 0;
+    static constexpr int oF = oZ + N * n * LD;
+    static constexpr int oY = oF + n * LD;
+    static constexpr int oM = oY + n * LD;
+    static constexpr int oW = oM + m * AW;
+    static constexpr int oA = oW + m * n;
+    static constexpr int oB = oA + N * 16;
+    static constexpr int oR = oB + N * 8;
+    static constexpr int oEta = oR + N * 4;
+    static constexpr int oBeta = oEta + N * n;
+    static constexpr int oTmp = oBeta + n;
+    static constexpr int oX = oTmp + n;
+    static constexpr int oU = oX + n;
+    static constexpr int total = oU + m + 1;
+};
+
+template <int N>
+__global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
+{
+    using L = GenericLayout<N>;
+    constexpr int n = L::n, m = L::m, G = L::G, LD = L::LD, AW = L::AW;
+    extern __shared__ double smem[];
+    const int gpb = blockDim.x / G;
+    const int g = threadIdx.x / G, r = threadIdx.x % G;
+    long long prob = (long long)blockIdx.x * gpb + g;
+    const bool live = prob < p.batch;
+    if (!live) prob = p.batch - 1;           // dead groups shadow the last problem so that __syncwarp stays converged
+    double* s = smem + (size_t)g * L::total;
+    double *Z = s + L::oZ, *F = s + L::oF, *Y = s + L::oY, *M = s + L::oM, *W = s + L::oW, *As = s + L::oA, *Bs = s + L::oB,
+           *Rs = s + L::oR, *eta = s + L::oEta, *beta = s + L::oBeta, *tmp = s + L::oTmp, *xs = s + L::oX, *us = s + L::oU;
+
+    const int T = p.horizon + 1, Tm = p.time_varying ? T : 1;
+    const double* gA = p.A + (size_t)prob * Tm * N * 16;
+    const double* gB = p.B + (size_t)prob * Tm * N * 8;
+    const double* gQ = p.Q + (size_t)prob * Tm * N * n * n;
+    const double* gq = p.q + (size_t)prob * Tm * N * n;
+    const double* gR = p.R + (size_t)prob * Tm * N * 4;
+    const double* gx = p.x0 + (size_t)prob * n;
+    double* gP = p.P ? p.P + (size_t)prob * T * m * n : nullptr;
+    double* ga = p.alpha ? p.alpha + (size_t)prob * T * m : nullptr;
+    int singular = 0;
+
+    {   // Zs = Q, etas = q of the last stage (KartLQR.cs:62-63)
+        const int tl = Tm - 1;
+        for (int e = r; e < N * n * n; e += G) {
+            int i = e / (n * n), rc = e % (n * n);
+            Z[i * n * LD + (rc / n) * LD + rc % n] = gQ[(size_t)tl * N * n * n + e];
+        }
+        for (int e = r; e < N * n; e += G) eta[e] = gq[(size_t)tl * N * n + e];
+        for (int e = r; e < n; e += G) xs[e] = gx[e];
+    }
+    for (int t = p.horizon; t >= 0; --t) {                       // KartLQR.cs:64
+        const int tt = p.time_varying ? t : 0;
+        if (p.time_varying || t == p.horizon) {
+            for (int e = r; e < N * 16; e += G) As[e] = gA[(size_t)tt * N * 16 + e];
+            for (int e = r; e < N * 8; e += G) Bs[e] = gB[(size_t)tt * N * 8 + e];
+            for (int e = r; e < N * 4; e += G) Rs[e] = gR[(size_t)tt * N * 4 + e];
+        }
+        __syncwarp();
+        // W_i = B_i^T Z_i (rows of block i only: B_i is zero elsewhere, KartLQR.cs:41-52); lane c owns column c
+        if (r < n) {
+            const int c = r;
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], Z[i * n * LD + (4 * i + k) * LD + c], acc);
+                    W[(2 * i + a) * n + c] = acc;
+                }
+        }
+        __syncwarp();
+        // coupled system [LHS | RHSMat | RHSVec]; block (i,j) -> row-block j, column-block i (quirk Q1, KartLQR.cs:68-87)
+        for (int e = r; e < m * m; e += G) {
+            const int ia = e / m, jb = e % m;                     // raw[2i+a][2j+b] = (B_i^T Z_i B_j)[a][b]
+            const int i = ia / 2, a = ia % 2, j = jb / 2, b = jb % 2;
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = fma(W[ia * n + 4 * j + k], Bs[j * 8 + k * 2 + b], acc);
+            if (i == j) acc = Rs[i * 4 + a * 2 + b] + acc;        // getRMatrix() + ... (:78)
+            M[(2 * j + a) * AW + (2 * i + b)] = acc;
+        }
+        if (r < n) {                                              // RHSMat = vstack_i B_i^T Z_i A (:89-95), A block diagonal
+            const int c = r, pc = c / 4, cc = c % 4;
+#pragma unroll
+            for (int ia = 0; ia < m; ++ia) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = fma(W[ia * n + 4 * pc + k], As[pc * 16 + k * 4 + cc], acc);
+                M[ia * AW + m + c] = acc;
+            }
+        }
+        if (r < m) {                                              // RHSVec = concat_i B_i^T eta_i (:96)
+            const int i = r / 2, a = r % 2;
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], eta[i * n + 4 * i + k], acc);
+            M[r * AW + m + n] = acc;
+        }
+        __syncwarp();
+        // P = LHS.Solve(RHSMat), alpha = LHS.Solve(RHSVec): LU with partial pivoting (MathNet, KartLQR.cs:104-105)
+        for (int k = 0; k < m; ++k) {
+            int pr = k;
+            double best = fabs(M[k * AW + k]);
+            for (int i = k + 1; i < m; ++i) {
+                double v = fabs(M[i * AW + k]);
+                if (v > best) { best = v; pr = i; }
+            }
+            __syncwarp();
+            if (pr != k)
+                for (int c = r; c < AW; c += G) { double t0 = M[k * AW + c]; M[k * AW + c] = M[pr * AW + c]; M[pr * AW + c] = t0; }
+            __syncwarp();
+            const double piv = M[k * AW + k];
+            if (piv == 0.0) singular = 1;
+            for (int i = k + 1; i < m; ++i) {
+                const double l = M[i * AW + k] / piv;
+                for (int c = k + 1 + r; c < AW; c += G) M[i * AW + c] = fma(-l, M[k * AW + c], M[i * AW + c]);
+            }
+            __syncwarp();
+        }
+        for (int c = m + r; c < AW; c += G)
+            for (int k = m - 1; k >= 0; --k) {
+                double x = M[k * AW + c];
+                for (int j = k + 1; j < m; ++j) x = fma(-M[k * AW + j], M[j * AW + c], x);
+                M[k * AW + c] = x / M[k * AW + k];
+            }
+        __syncwarp();
+        // from here P[k][c] = M[k][m+c], alpha[k] = M[k][m+n]
+        if (live) {
+            if (gP) for (int e = r; e < m * n; e += G) gP[(size_t)t * m * n + e] = M[(e / n) * AW + m + e % n];
+            if (ga) for (int e = r; e < m; e += G) ga[(size_t)t * m + e] = M[e * AW + m + n];
+        }
+        // F = A - sum_k B_k P_k, beta = -sum_k B_k alpha_k (:110-111); lane r owns row r
+        if (r < n) {
+            const int pr = r / 4, rr = r % 4;
+            const double b0 = Bs[pr * 8 + rr * 2 + 0], b1 = Bs[pr * 8 + rr * 2 + 1];
+#pragma unroll
+            for (int c = 0; c < n; ++c) {
+                const double a = (c / 4 == pr) ? As[pr * 16 + rr * 4 + c % 4] : 0.0;
+                const double bp = fma(b1, M[(2 * pr + 1) * AW + m + c], b0 * M[(2 * pr) * AW + m + c]);
+                F[r * LD + c] = a - bp;
+            }
+            beta[r] = -fma(b1, M[(2 * pr + 1) * AW + m + n], b0 * M[(2 * pr) * AW + m + n]);
+        }
+        __syncwarp();
+        // Z_i <- Q_i + P_i^T R_i P_i + F^T Z_i F ; eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)  (:116-117)
+        for (int i = 0; i < N; ++i) {
+            double* Zi = Z + i * n * LD;
+            const double r00 = Rs[i * 4 + 0], r01 = Rs[i * 4 + 1], r10 = Rs[i * 4 + 2], r11 = Rs[i * 4 + 3];
+            if (r < n) {                                          // Y = Z_i F, row r
+                double zr[n];
+#pragma unroll
+                for (int k = 0; k < n; ++k) zr[k] = Zi[r * LD + k];
+#pragma unroll
+                for (int c = 0; c < n; ++c) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < n; ++k) acc = fma(zr[k], F[k * LD + c], acc);
+                    Y[r * LD + c] = acc;
+                }
+            }
+            __syncwarp();
+            if (r < n) {                                          // row r of the new Z_i
+                double fc[n];
+#pragma unroll
+                for (int k = 0; k < n; ++k) fc[k] = F[k * LD + r];
+                const double p0r = M[(2 * i) * AW + m + r], p1r = M[(2 * i + 1) * AW + m + r];
+                double zb = 0.0;
+#pragma unroll
+                for (int c = 0; c < n; ++c) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < n; ++k) acc = fma(fc[k], Y[k * LD + c], acc);
+                    const double p0c = M[(2 * i) * AW + m + c], p1c = M[(2 * i + 1) * AW + m + c];
+                    const double rp0 = fma(r01, p1c, r00 * p0c), rp1 = fma(r11, p1c, r10 * p0c);   // (R_i P_i)[:, c]
+                    const double prp = fma(p1r, rp1, p0r * rp0);                                    // (P_i^T R_i P_i)[r][c]
+                    const double znew = (gQ[(size_t)tt * N * n * n + (size_t)i * n * n + r * n + c] + prp) + acc;
+                    Zi[r * LD + c] = znew;                        // row r is only read by lane r from here on
+                    zb = fma(znew, beta[c], zb);
+                }
+                tmp[r] = eta[i * n + r] + zb;                     // eta_i + Z_i^{new} beta (quirk Q2)
+            }
+            __syncwarp();
+            if (r < n) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < n; ++k) acc = fma(F[k * LD + r], tmp[k], acc);
+                const double a0 = M[(2 * i) * AW + m + n], a1 = M[(2 * i + 1) * AW + m + n];
+                const double ra0 = fma(r01, a1, r00 * a0), ra1 = fma(r11, a1, r10 * a0);
+                const double pra = fma(M[(2 * i + 1) * AW + m + r], ra1, M[(2 * i) * AW + m + r] * ra0);
+                eta[i * n + r] = (gq[(size_t)tt * N * n + i * n + r] + pra) + acc;
+            }
+            __syncwarp();
+        }
+    }
+    // optimal_control = -P x0 - alpha with the t = 0 pair (:121-126), every player
+    if (r < m) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < n; ++c) acc = fma(-M[r * AW + m + c], xs[c], acc);
+        const double u = acc - M[r * AW + m + n];
+        if (live) p.u0[(size_t)prob * m + r] = u;
+    }
+    if (live && r == 0 && p.status) p.status[prob] = singular;
+    // closed-loop rollout; gains are re-read from the P/alpha output buffers written above
+    if (p.traj) {
+        double* gt = p.traj + (size_t)prob * (T + 1) * n;
+        if (live && r < n) gt[r] = xs[r];
+        __syncwarp();
+        for (int t = 0; t <= p.horizon; ++t) {
+            const int tt = p.time_varying ? t : 0;
+            if (r < m) {
+                double acc = 0.0;
+                for (int c = 0; c < n; ++c) acc = fma(-gP[(size_t)t * m * n + r * n + c], xs[c], acc);
+                us[r] = acc - ga[(size_t)t * m + r];
+            }
+            __syncwarp();
+            double xn = 0.0;
+            if (r < n) {
+                const int pr = r / 4, rr = r % 4;
+                for (int c = 0; c < 4; ++c) xn = fma(gA[(size_t)tt * N * 16 + pr * 16 + rr * 4 + c], xs[4 * pr + c], xn);
+                for (int c = 0; c < 2; ++c) xn = fma(gB[(size_t)tt * N * 8 + pr * 8 + rr * 2 + c], us[2 * pr + c], xn);
+            }
+            __syncwarp();
+            if (r < n) { xs[r] = xn; if (live) gt[(size_t)(t + 1) * n + r] = xn; }
+            __syncwarp();
+        }
+    }
+}
+
+template <int N>
+static int launch_generic(const LqngParams& p, cudaStream_t stream)
+{
+    using L = GenericLayout<N>;
+    const int threads = 128, gpb = threads / L::G;
+    const size_t smem = (size_t)gpb * L::total * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        HK_CUDA(cudaFuncSetAttribute(lqng_generic_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int blocks = (p.batch + gpb - 1) / gpb;
+    lqng_generic_kernel<N><<<blocks, threads, smem, stream>>>(p);
+    HK_CUDA(cudaGetLastError());
+    return HK_OK;
+}
+
+// Device-side problem assembly: one thread per (problem, player) expands the compact description
+// into the dense record: LinearizedBicycle.getA/getB (KartLQRDynamics.cs:40-62) and
+// LQRCheckpointReachAvoidCost.getQMatrix/getQVec/getRMatrix (KartLQRCosts.cs:57-140, quirks Q4/Q5 of SURVEY.md A.3).
+__global__ void lqng_assemble_kernel(int batch, int N, double dt, const double* __restrict__ x0, const double* __restrict__ target,
+                                     const double* __restrict__ tw, const double* __restrict__ cw, const double* __restrict__ aw,
+                                     const double* __restrict__ otgt, const double* __restrict__ otw,
+                                     double* A, double* B, double* Q, double* q, double* R, double* xj)
+{
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)batch * N) return;
+    const int n = 4 * N, K = N - 1;
+    const double* x = x0 + id * 4;
+    double* Ai = A + id * 16;
+    for (int e = 0; e < 16; ++e) Ai[e] = (e % 5 == 0) ? 1.0 : 0.0;                 // SparseIdentity (:44)
+    const double ch = cos(x[3]), sh = sin(x[3]);
+    Ai[0 * 4 + 2] = ch * dt;                                                       // :45
+    Ai[1 * 4 + 2] = sh * dt;                                                       // :46
+    Ai[0 * 4 + 3] = -sh * dt * x[2];                                               // :47
+    Ai[1 * 4 + 3] = ch * dt * x[2];                                                // :48
+    double* Bi = B + id * 8;
+    for (int e = 0; e < 8; ++e) Bi[e] = 0.0;
+    Bi[2 * 2 + 0] = dt; Bi[3 * 2 + 1] = dt;                                        // :58-59
+    double* Ri = R + id * 4;
+    Ri[0] = cw[id]; Ri[1] = 0.0; Ri[2] = 0.0; Ri[3] = cw[id];                      // KartLQRCosts.cs:136
+    for (int e = 0; e < 4; ++e) xj[id * 4 + e] = x[e];
+    double* Qi = Q + id * n * n;
+    double* qi = q + id * n;
+    for (int e = 0; e < n * n; ++e) Qi[e] = 0.0;
+    const double* awi = aw + id * K * 2;
+    const double* oti = otgt + id * K * 4;
+    const double* owi = otw + id * K * 3;
+    for (int s = 0; s < 2; ++s) {                                                  // :64-80
+        double total = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const int t = 4 * (1 + k) + s;
+            const double w = awi[k * 2 + s];
+            Qi[s * n + t] = w; Qi[t * n + s] = w; Qi[t * n + t] = -w;
+            total -= w;
+        }
+        Qi[s * n + s] = total;
+    }
+    for (int s = 0; s < 4; ++s) Qi[s * n + s] += tw[id * 4 + s];                   // :81-84
+    for (int k = 0; k < K; ++k)
+        for (int o = 0; o < 3; ++o) Qi[(4 * (1 + k) + o) * n + 4 * (1 + k) + o] = -owi[k * 3 + o];   // :86-94 (assignment)
+    for (int s = 0; s < 4; ++s) qi[s] = (-target[id * 4 + s]) * tw[id * 4 + s];    // :109-113
+    for (int k = 0; k < K; ++k) {                                                  // :115-124
+        for (int s = 0; s < 4; ++s) qi[4 * (1 + k) + s] = oti[k * 4 + s];
+        for (int o = 0; o < 3; ++o) qi[4 * (1 + k) + o] = qi[4 * (1 + k) + o] * -owi[k * 3 + o];
+    }
+}
+
+int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double* dx0, const double* dtarget,
+                         const double* dtw, const double* dcw, const double* daw, const double* dotgt, const double* dotw,
+                         double* du0, int* dstatus, cudaStream_t stream)
+{
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const int n = 4 * N;
+    const size_t per = (size_t)N * 16 + N * 8 + (size_t)N * n * n + (size_t)N * n + N * 4 + n;
+    double* d = (double*)dscratch(c, 5, per * sizeof(double) * (size_t)batch);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    double *dA = d, *dB = dA + (size_t)batch * N * 16, *dQ = dB + (size_t)batch * N * 8, *dq = dQ + (size_t)batch * N * n * n,
+           *dR = dq + (size_t)batch * N * n, *dx = dR + (size_t)batch * N * 4;
+    const long long threads = (long long)batch * N;
+    lqng_assemble_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(batch, N, dt, dx0, dtarget, dtw, dcw, daw, dotgt, dotw,
+                                                                              dA, dB, dQ, dq, dR, dx);
+    HK_CUDA(cudaGetLastError());
+    return lqng_launch(batch, N, horizon, 0, dA, dB, dQ, dq, dR, dx, du0, nullptr, nullptr, nullptr, dstatus, stream);
+}
+
+int lqng_launch(int batch, int N, int horizon, int time_varying, const double* dA, const double* dB, const double* dQ,
+                const double* dq, const double* dR, const double* dx0, double* du0, double* dP, double* dalpha,
+                double* dtraj, int* dstatus, cudaStream_t stream)
+{
+    if (batch == 0) return HK_OK;
+    LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus};
+    switch (N) {
+        case 1: return launch_generic<1>(p, stream);
+        case 2: return launch_generic<2>(p, stream);
+        case 3: return launch_generic<3>(p, stream);
+        case 4: return launch_generic<4>(p, stream);
+    }
+    set_error("n_players must be 1..4");
+    return HK_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace hk

@@ -182,14 +182,25 @@ int hk_oracle_up_next(const hk_oracle_game* g, const hk_game_state* st)      /* 
 {
     (void)g;
     int order[HK_MAX_KARTS];
-    /* List.Sort on <= 16 elements is an insertion sort => stable; sort indices to recover the original position
-     * (the reference recovers it with ValueType.Equals over all fields incl. the unique name, :232-238) */
+    /* List<T>.Sort(Comparison) = introspective sort (.NET 4.5+ / Mono reference source ArraySortHelper.IntroSort):
+     * partitions of <= 16 elements use an insertion sort (stable) EXCEPT sizes 2 and 3, which use exchange networks:
+     * size 2: SwapIfGreater(0,1); size 3: SwapIfGreater(0,1), (0,2), (1,2) — the latter is not stable, and ties are
+     * common at the root (equal time and bucket), so it is replayed literally.  Indices are sorted to recover the
+     * original position (the reference recovers it with ValueType.Equals over all fields incl. the unique name, :232-238). */
     for (int i = 0; i < st->n_karts; ++i) order[i] = i;
-    for (int i = 1; i < st->n_karts; ++i) {
-        int t = order[i], j = i - 1;
-        while (j >= 0 && cmp_kart(&st->karts[t], &st->karts[order[j]]) < 0) { order[j + 1] = order[j]; --j; }
-        order[j + 1] = t;
+#define HK_SWAP_IF_GREATER(a, b) do { if (cmp_kart(&st->karts[order[a]], &st->karts[order[b]]) > 0) { int t_ = order[a]; order[a] = order[b]; order[b] = t_; } } while (0)
+    if (st->n_karts == 2) {
+        HK_SWAP_IF_GREATER(0, 1);
+    } else if (st->n_karts == 3) {
+        HK_SWAP_IF_GREATER(0, 1); HK_SWAP_IF_GREATER(0, 2); HK_SWAP_IF_GREATER(1, 2);
+    } else {
+        for (int i = 1; i < st->n_karts; ++i) {
+            int t = order[i], j = i - 1;
+            while (j >= 0 && cmp_kart(&st->karts[t], &st->karts[order[j]]) < 0) { order[j + 1] = order[j]; --j; }
+            order[j + 1] = t;
+        }
     }
+#undef HK_SWAP_IF_GREATER
     for (int i = 0; i < st->n_karts; ++i)
         if (st->karts[order[i]].section != st->lastCompletedSection + 1) return order[i];
     return -1;

@@ -1,0 +1,86 @@
+"""CPU tests (no GPU): the C-ABI shared library loads, exports every symbol include/hk_abi.h declares, validates its
+arguments on the host, and refuses to compute without a CUDA device (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from hierarchicalkarting_b200 import abi, scenarios as S
+
+HEADER = open("include/hk_abi.h").read()
+
+
+def _declared():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(hk_[a-z0-9_]+)\s*\(", body)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    lib = abi.load_library()
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/hk_abi.h but not exported"
+        assert n in abi.PROTOTYPES, f"{n} has no ctypes prototype"
+    syms = subprocess.run(["nm", "-D", "--defined-only", abi.LIB_PATH], capture_output=True, text=True).stdout
+    for n in names:
+        assert re.search(rf"\bT {n}\b", syms)
+    assert lib.hk_abi_version() == abi.HK_ABI_VERSION
+
+
+def test_only_sm100a_code_in_library():
+    out = subprocess.run(["cuobjdump", "-lelf", abi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(abi.hk_section) == 24 and C.sizeof(abi.hk_kart) == 28 and C.sizeof(abi.hk_game_params) == 32
+    assert C.sizeof(abi.hk_kart_state) == 40 and C.sizeof(abi.hk_action) == 12 and C.sizeof(abi.hk_game_state) == 16 + 4 * 40
+    for name, val in (("HK_MAX_PLAYERS", 4), ("HK_MAX_ACTIONS", 36), ("HK_MAX_PLIES", 64), ("HK_MAX_KARTS", 4), ("HK_MAX_HORIZON", 31)):
+        assert re.search(rf"#define {name} {val}\b", HEADER) and getattr(abi, name) == val
+
+
+def test_host_side_argument_validation_needs_no_gpu():
+    lib = abi.load_library()
+    A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(S.OVAL, 2, 2, seed=1))
+    u0 = np.zeros((2, 4))
+    args = [abi.dptr(a) for a in (A, B, Q, q, R, x0)] + [abi.dptr(u0), None, None, None, None]
+    assert lib.hk_lqng_solve_batch(2, 0, 3, 0, *args) == abi.HK_ERR_INVALID_ARGUMENT
+    assert lib.hk_lqng_solve_batch(2, 2, 99, 0, *args) == abi.HK_ERR_INVALID_ARGUMENT
+    assert lib.hk_lqng_solve_batch(-1, 2, 3, 0, *args) == abi.HK_ERR_INVALID_ARGUMENT
+    assert b"batch" in lib.hk_last_error()
+    assert lib.hk_lqng_solve_batch(0, 2, 3, 0, *args) == abi.HK_OK            # empty batch is a no-op, even without a device
+    cdf = np.zeros(4, dtype=np.uint32)
+    assert lib.hk_policy_cdf(0, cdf.ctypes.data_as(C.POINTER(C.c_uint32))) == abi.HK_ERR_INVALID_ARGUMENT
+    assert lib.hk_policy_cdf(4, cdf.ctypes.data_as(C.POINTER(C.c_uint32))) == abi.HK_OK and cdf[-1] == 0xFFFFFFFF
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the compute entries fail loudly with HK_ERR_NO_DEVICE."""
+    lib = abi.load_library()
+    if lib.hk_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(S.OVAL, 2, 2, seed=1))
+    u0 = np.zeros((2, 4))
+    rc = lib.hk_lqng_solve_batch(2, 2, 3, 0, *[abi.dptr(a) for a in (A, B, Q, q, R, x0)], abi.dptr(u0), None, None, None, None)
+    assert rc == abi.HK_ERR_NO_DEVICE and b"no CPU fallback" in lib.hk_last_error()
+    from hierarchicalkarting_b200 import mcts, tracks
+    with pytest.raises(abi.HKError) as e:
+        mcts.Game(tracks.OVAL, 2, 2)
+    assert e.value.status == abi.HK_ERR_NO_DEVICE
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the package, include/ or host/ may reference it."""
+    for root in ("hierarchicalkarting_b200", "include", "host", "csharp"):
+        for dp, _, fs in os.walk(root):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cs", ".cpp")):
+                    txt = open(os.path.join(dp, f)).read()
+                    assert "hk_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, os.path.join(dp, f)

@@ -1,0 +1,188 @@
+"""GPU parity of the discrete race game and the rollout kernels against the CPU oracle, through the C-ABI.
+Transitions, legal move sets, policy ordering and terminal scores must be BIT-EXACT (BASELINE.json north_star);
+rollout decision statistics must match the reference's own sampling procedure distributionally."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hierarchicalkarting_b200 import abi, mcts, tracks
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_game(oracle, track, n_karts, bucket, tp=100):
+    params = tracks.game_params(track, bucket, tp)
+    return oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(n_karts), n_karts, params)
+
+
+def _random_root(rng, track, n_karts, bucket, teams):
+    sec = int(rng.integers(0, 3 * track.n_sections))
+    lanes = [int(x) for x in rng.integers(1, 5, n_karts)]
+    if rng.random() < 0.5:
+        buckets = None                                                     # reference root quirk: (0, bucket)
+    else:
+        buckets = []
+        for _ in range(n_karts):
+            v = int(rng.choice(list(range(6, 15, bucket))))
+            buckets.append((v, min(v + bucket, 15)))
+    times = [0] + [int(x) for x in rng.integers(0, 151, n_karts - 1)]
+    st = tracks.root_state(track, sec, lanes, teams=teams, buckets=buckets, tire_age=int(rng.choice([0, 2500, 6000, 9900, 13500])),
+                           lane_changes=int(rng.integers(0, 3)), times=times)
+    if buckets is None:
+        for i in range(n_karts):
+            st.karts[i].max_velocity = bucket
+    return st
+
+
+def _state_tuple_np(rec):
+    n = int(rec["n_karts"])
+    return (n, int(rec["initialSection"]), int(rec["lastCompletedSection"]), int(rec["finalSection"]),
+            tuple(tuple(int(rec["karts"][i][k]) for k in abi.KART_STATE_FIELDS) for i in range(n)))
+
+
+@pytest.mark.parametrize("track_name,n_karts,bucket,teams", [
+    ("Oval", 2, 2, [0, 1]), ("Complex", 2, 2, [0, 1]), ("Complex", 2, 1, [0, 1]), ("Oval", 3, 2, [0, 0, 1]),
+    ("Complex", 4, 2, [0, 0, 1, 1]), ("Oval", 1, 2, [0]), ("Complex", 4, 1, [0, 1, 2, 3])])
+def test_replay_bit_exact(hk, oracle, track_name, n_karts, bucket, teams):
+    """Fixed action sequences (legal moves picked at random, plus a few illegal ones): every state, upNext, isOver flag,
+    score list, legal set and policy order equal the oracle's, bit for bit."""
+    track = tracks.TRACKS[track_name]
+    rng = np.random.default_rng(hash((track_name, n_karts, bucket)) % 2**32)
+    G = mcts.Game(track, n_karts, bucket)
+    OG = _oracle_game(oracle, track, n_karts, bucket)
+    batch, ln = 48, n_karts * 8 + 3
+    roots, seqs, expect = [], np.zeros((batch, ln, 3), dtype=np.int32), []
+    for b in range(batch):
+        st = _random_root(rng, track, n_karts, bucket, teams)
+        roots.append(st)
+        cur, rows = st, []
+        for k in range(ln + 1):
+            up = OG.up_next(cur)
+            over, scores = OG.is_over(cur) if up >= 0 else (-1, np.zeros(0, np.float32))
+            mv, gi, cnt = OG.policy_moves(cur) if up >= 0 else ([], [], -1)
+            rows.append((cur.astuple(), up, over, scores.copy(), mv, gi, cnt))
+            if k == ln:
+                break
+            if cnt > 0 and rng.random() < 0.9:
+                a = mv[int(rng.integers(0, cnt))]
+            else:                                                            # arbitrary (possibly illegal) action
+                v = int(rng.choice(list(range(6, 15, bucket))))
+                a = (v, min(v + bucket, 15), int(rng.integers(1, 5)))
+            seqs[b, k] = a
+            if up >= 0:
+                cur = OG.make_move(cur, a)
+        expect.append(rows)
+    out = G.replay(roots, seqs)
+    for b in range(batch):
+        for k in range(ln + 1):
+            st, up, over, scores, mv, gi, cnt = expect[b][k]
+            assert _state_tuple_np(out["states"][b, k]) == st, (b, k)
+            assert out["upnext"][b, k] == up
+            assert out["over"][b, k] == over
+            assert out["n_scores"][b, k] == len(scores)
+            assert out["scores"][b, k, :len(scores)].tobytes() == scores.tobytes()      # bit-exact incl. NaN payloads
+            assert out["n_moves"][b, k] == cnt
+            if cnt > 0:
+                assert [tuple(int(v) for v in out["moves"][b, k, j]) for j in range(cnt)] == mv
+                assert [int(v) for v in out["moves_index"][b, k, :cnt]] == gi
+
+
+@pytest.mark.parametrize("track_name,n_karts,bucket,teams", [("Complex", 2, 2, [0, 1]), ("Oval", 2, 1, [0, 1]), ("Complex", 4, 2, [0, 0, 1, 1]), ("Oval", 3, 2, [0, 1, 2])])
+def test_rollout_trace_replays_in_oracle(hk, oracle, track_name, n_karts, bucket, teams):
+    """Each GPU rollout, replayed move by move in the oracle with the same Philox stream, gives the same choices, the
+    same actions and the same terminal score list bit-exactly."""
+    track = tracks.TRACKS[track_name]
+    rng = np.random.default_rng(12)
+    G = mcts.Game(track, n_karts, bucket)
+    OG = _oracle_game(oracle, track, n_karts, bucket)
+    for trial in range(3):
+        leaf = _random_root(rng, track, n_karts, bucket, teams)
+        seed, off, n = 20260003 + trial, 1000 * trial, 256
+        tr = G.rollouts_trace(leaf, n, seed=seed, rollout_offset=off)
+        for r in range(n):
+            ref = OG.rollout(leaf, mode=0, seed=seed, rollout_id=off + r)
+            assert tr["n_plies"][r] == ref["n_plies"]
+            npl = ref["n_plies"]
+            assert [tuple(int(v) for v in tr["actions"][r, k]) for k in range(npl)] == ref["actions"]
+            assert [int(v) for v in tr["choice"][r, :npl]] == ref["choices"]
+            assert tr["n_scores"][r] == len(ref["scores"])
+            assert tr["scores"][r, :len(ref["scores"])].tobytes() == ref["scores"].tobytes()
+
+
+def test_rollout_statistics_equal_oracle(hk, oracle):
+    """hk_mcts_rollouts == the oracle's reduction over the same Philox counters (exact visits; sums to 1e-12),
+    and multi-leaf launches equal single-leaf launches."""
+    track = tracks.COMPLEX
+    G = mcts.Game(track, 2, 2)
+    OG = _oracle_game(oracle, track, 2, 2)
+    rng = np.random.default_rng(4)
+    leaves = [_random_root(rng, track, 2, 2, [0, 1]) for _ in range(3)]
+    n = 20000
+    for li, leaf in enumerate(leaves):
+        got = G.rollouts(leaf, n, seed=99, rollout_offset=li * n)
+        ref = OG.rollouts(leaf, n, mode=0, seed=99, rollout_offset=li * n)
+        assert np.array_equal(got["visit"], ref["visit"]) and np.array_equal(got["nan_count"], ref["nan_count"])
+        assert got["plies"] == ref["plies"]
+        assert np.allclose(got["reward_sum"], ref["reward_sum"], rtol=1e-12, atol=1e-9)
+    multi = G.rollouts_multi(leaves, n, seed=99, rollout_offset=0)
+    for li, leaf in enumerate(leaves):
+        single = G.rollouts(leaf, n, seed=99, rollout_offset=li * n)
+        assert np.array_equal(multi["visit"][li], single["visit"])
+        assert np.allclose(multi["reward_sum"][li], single["reward_sum"], rtol=1e-12, atol=1e-9)
+
+
+def test_rollout_distribution_matches_reference_procedure(hk, oracle):
+    """Decision statistics vs the reference's own sampler (polar Box-Muller N(0,1), float NextGaussian with <= 10
+    redraws, RoundToInt(|x|)): chi-square on first-action visit frequencies and z-test on mean terminal score."""
+    track = tracks.COMPLEX
+    G = mcts.Game(track, 2, 2)
+    OG = _oracle_game(oracle, track, 2, 2)
+    leaf = tracks.root_state(track, 12, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 37])
+    n = 200000
+    got = G.rollouts(leaf, n, seed=20260003)
+    ref = OG.rollouts(leaf, n, mode=1, seed=5)
+    used = (got["visit"] + ref["visit"]) > 0
+    a, b = got["visit"][used].astype(float), ref["visit"][used].astype(float)
+    big = (a + b) >= 20
+    chi2 = float(np.sum((a[big] - b[big]) ** 2 / (a[big] + b[big])))
+    dof = int(big.sum()) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (chi2, dof)
+    for k in range(2):
+        ma, mb = got["reward_sum"][:, k].sum() / n, ref["reward_sum"][:, k].sum() / n
+        assert abs(ma - mb) < 6 * np.sqrt(0.25 / n * 2) + 1e-9
+
+
+def test_policy_cdf_and_full_size_rollouts(hk, oracle):
+    """CDF tables exported by the library equal the oracle's; 10^6 rollouts (BASELINE config 4) conserve counts and are
+    reproducible; disjoint shards (rollout_offset) sum to the whole."""
+    for cnt in range(1, abi.HK_MAX_ACTIONS + 1):
+        assert np.array_equal(mcts.policy_cdf(cnt), oracle.policy_cdf(cnt))
+    track = tracks.COMPLEX
+    G = mcts.Game(track, 2, 2)
+    leaf = tracks.root_state(track, 3, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 80])
+    n = 1_000_000
+    whole = G.rollouts(leaf, n, seed=20260003)
+    again = G.rollouts(leaf, n, seed=20260003)
+    assert whole["visit"].sum() == n and np.array_equal(whole["visit"], again["visit"])
+    assert np.allclose(whole["reward_sum"], again["reward_sum"], rtol=1e-12)
+    parts = [G.rollouts(leaf, n // 4, seed=20260003, rollout_offset=k * (n // 4)) for k in range(4)]
+    assert np.array_equal(sum(p["visit"] for p in parts), whole["visit"])
+    assert np.allclose(sum(p["reward_sum"] for p in parts), whole["reward_sum"], rtol=1e-12)
+    assert sum(p["plies"] for p in parts) == whole["plies"]
+    # 2-kart terminal reward is the constant vector (1, 0) in kart order unless t0 >= 3 t1 (quirk B.6-5)
+    tot = whole["reward_sum"].sum(axis=0)
+    assert tot[0] == pytest.approx(n - whole["nan_count"].sum(), rel=1e-9) or tot[0] <= n
+
+
+def test_tree_search_api(hk):
+    """KartMCTS.constructSearchTree / getBestStatesSequence drop-in: the plan covers the search depth."""
+    track = tracks.COMPLEX
+    G = mcts.Game(track, 2, 2)
+    root = mcts.DiscreteGameState(G, tracks.root_state(track, 0, [2, 3], teams=[0, 1], tire_age=2500))
+    mcts.KartMCTS.random.seed(7)
+    node = mcts.KartMCTS.constructSearchTree(root, T=30.0, seed=1, max_iterations=40)
+    assert node.numEpisodes > 0 and len(node.children) == len(root.nextMoves())
+    best = mcts.KartMCTS.getBestStatesSequence(node)
+    assert len(best) >= 1
+    assert all(all(k.section == s.lastCompletedSection for k in s.kartStates) for s in best)

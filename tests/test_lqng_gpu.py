@@ -1,0 +1,149 @@
+"""GPU parity of the LQNG kernels against the CPU oracle, through the C-ABI (include/hk_abi.h).
+Tolerance: 1e-9 relative (BASELINE.json north_star), metric of SURVEY.md A.7 — see conftest.rel_err."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from hierarchicalkarting_b200 import lqr, scenarios as S
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _check(got, ref, full=True):
+    for b in range(ref["u0"].shape[0]):
+        assert rel_err(got["u0"][b], ref["u0"][b]) <= TOL
+        if full:
+            for k in ("P", "alpha", "traj"):
+                assert rel_err(got[k][b], ref[k][b]) <= TOL, (k, b)
+    assert np.array_equal(got["status"], ref["status"])
+
+
+@pytest.mark.parametrize("N,track", [(1, S.OVAL), (2, S.OVAL), (3, S.COMPLEX), (4, S.COMPLEX)])
+@pytest.mark.parametrize("horizon", [3, 0, 7])
+def test_parity_time_invariant(hk, oracle, N, track, horizon):
+    p = S.make_problems(track, 257, N, seed=100 + N)          # ragged: not a multiple of any group/warp size
+    A, B, Q, q, R, x0 = S.assemble_dense(p)
+    ref = oracle.lqng_solve_batch(A, B, Q, q, R, x0, horizon)
+    got = lqr.solve_batch(A, B, Q, q, R, x0, horizon)
+    _check(got, ref)
+    got_u = lqr.solve_batch(A, B, Q, q, R, x0, horizon, full=False)   # reference output only (u0)
+    _check(got_u, ref, full=False)
+
+
+@pytest.mark.parametrize("N", [1, 2, 4])
+def test_parity_time_varying(hk, oracle, N):
+    rng = np.random.default_rng(5)
+    horizon, batch = 3, 64
+    T, n = horizon + 1, 4 * N
+    p = S.make_problems(S.OVAL if N < 3 else S.COMPLEX, batch, N, seed=11)
+    A, B, Q, q, R, x0 = S.assemble_dense(p)
+    tv = lambda a, s: np.ascontiguousarray(np.repeat(a[:, None], T, axis=1) * (1.0 + s * rng.standard_normal((batch, T) + a.shape[1:])))
+    At, Bt, Rt, qt = tv(A, 0.01), tv(B, 0.05), tv(R, 0.05), tv(q, 0.05)
+    Qt = tv(Q, 0.05)
+    Qt = 0.5 * (Qt + np.swapaxes(Qt, -1, -2))
+    ref = oracle.lqng_solve_batch(At, Bt, Qt, qt, Rt, x0, horizon, time_varying=True)
+    got = lqr.solve_batch(At, Bt, Qt, qt, Rt, x0, horizon, time_varying=True)
+    _check(got, ref)
+
+
+def test_general_dense_blocks_and_nonsymmetric_q(hk, oracle):
+    """The ABI takes any per-player A_i (4x4), B_i (4x2), R_i (2x2) and Q_i — not only the bicycle structure."""
+    rng = np.random.default_rng(9)
+    for N in (2, 3, 4):
+        batch, n = 33, 4 * N
+        A = np.eye(4) + 0.05 * rng.standard_normal((batch, N, 4, 4))
+        B = 0.05 * rng.standard_normal((batch, N, 4, 2))
+        Q = 0.3 * rng.standard_normal((batch, N, n, n))                 # deliberately NOT symmetric
+        q = rng.standard_normal((batch, N, n))
+        R = np.eye(2) * 0.2 + 0.02 * rng.standard_normal((batch, N, 2, 2))
+        x0 = rng.standard_normal((batch, n))
+        ref = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 3)
+        got = lqr.solve_batch(A, B, Q, q, R, x0, 3)
+        _check(got, ref)
+
+
+def test_pivoting_and_singular_status(hk, oracle):
+    """LHS whose natural pivot order is wrong (tiny R, large coupling) and an exactly singular LHS (R = 0, B = 0)."""
+    rng = np.random.default_rng(3)
+    N, n, batch = 2, 8, 16
+    A = np.tile(np.eye(4), (batch, N, 1, 1))
+    B = rng.standard_normal((batch, N, 4, 2))
+    Q = rng.standard_normal((batch, N, n, n)); Q = Q + np.swapaxes(Q, -1, -2)
+    q = rng.standard_normal((batch, N, n))
+    R = np.zeros((batch, N, 2, 2)); R[..., 0, 1] = 1e-3; R[..., 1, 0] = 1e-3      # zero diagonal forces row exchanges
+    x0 = rng.standard_normal((batch, n))
+    ref = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 2)
+    got = lqr.solve_batch(A, B, Q, q, R, x0, 2)
+    for b in range(batch):
+        assert rel_err(got["u0"][b], ref["u0"][b]) <= 1e-7              # conditioning of these systems is ~1e3-1e5
+    Bz = np.zeros_like(B); Rz = np.zeros_like(R)
+    ref = oracle.lqng_solve_batch(A, Bz, Q, q, Rz, x0, 1)
+    got = lqr.solve_batch(A, Bz, Q, q, Rz, x0, 1)
+    assert np.all(ref["status"] == 1) and np.array_equal(got["status"], ref["status"])
+
+
+def test_golden_fixture(hk):
+    g = np.load("tests/golden/lqng_golden.npz")
+    for N in (2, 4):
+        got = lqr.solve_batch(*(g[f"N{N}_{k}"] for k in ("A", "B", "Q", "q", "R", "x0")), 3)
+        for k in ("u0", "P", "alpha", "traj"):
+            for b in range(got["u0"].shape[0]):
+                assert rel_err(got[k][b], g[f"N{N}_{k}_out"][b]) <= TOL
+
+
+def test_reference_api_single_solve(hk, oracle):
+    """KartLQR.solveFeedbackLQR drop-in on BASELINE config 1 (one 2-kart Oval problem) and the SURVEY Appendix D smoke value."""
+    p = S.config1()
+    A, B, Q, q, R, x0 = S.assemble_dense(p)
+    dyn = [lqr.LinearizedBicycle(p["dt"], p["x0"][0, i]) for i in range(2)]
+
+    class Cost(lqr.KartLQRCosts):
+        def __init__(self, i): self.i = i
+        def getQMatrix(self): return Q[0, self.i]
+        def getQVec(self): return q[0, self.i]
+        def getRMatrix(self): return R[0, self.i]
+    u = lqr.KartLQR.solveFeedbackLQR(dyn, [Cost(0), Cost(1)], [p["x0"][0, 0], p["x0"][0, 1]], 3)
+    ref = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 3)
+    assert u.shape == (2,) and rel_err(u, ref["u0"][0, :2]) <= TOL
+
+
+def test_edge_cases(hk):
+    A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(S.OVAL, 1, 2, seed=1))
+    out = lqr.solve_batch(A[:0], B[:0], Q[:0], q[:0], R[:0], x0[:0], 3)     # empty batch
+    assert out["u0"].shape == (0, 4)
+    with pytest.raises(ValueError):
+        lqr.solve_batch(A, B, Q[:, :, :7], q, R, x0, 3)                      # dimension mismatch -> ArgumentException analogue
+    from hierarchicalkarting_b200 import abi
+    lib = abi.load_library()
+    u0 = np.zeros(4)
+    rc = lib.hk_lqng_solve_batch(1, 5, 3, 0, abi.dptr(A), abi.dptr(B), abi.dptr(Q), abi.dptr(q), abi.dptr(R), abi.dptr(x0), abi.dptr(u0),
+                                 None, None, None, None)
+    assert rc == abi.HK_ERR_INVALID_ARGUMENT and b"n_players" in lib.hk_last_error()
+
+
+def test_full_size_properties(hk, oracle):
+    """BASELINE config 2 size (65,536 problems): determinism, batch-permutation equivariance, duplicate problems give
+    identical answers, and a strided sample checked against the oracle."""
+    p = S.config2(65536)
+    A, B, Q, q, R, x0 = S.assemble_dense(p)
+    a = lqr.solve_batch(A, B, Q, q, R, x0, 3, full=False)
+    b = lqr.solve_batch(A, B, Q, q, R, x0, 3, full=False)
+    assert np.array_equal(a["u0"], b["u0"])
+    perm = np.random.default_rng(0).permutation(65536)
+    c = lqr.solve_batch(A[perm], B[perm], Q[perm], q[perm], R[perm], x0[perm], 3, full=False)
+    assert np.array_equal(c["u0"], a["u0"][perm])
+    idx = np.arange(0, 65536, 257)
+    ref = oracle.lqng_solve_batch(A[idx], B[idx], Q[idx], q[idx], R[idx], x0[idx], 3, full=False)
+    for k, i in enumerate(idx):
+        assert rel_err(a["u0"][i], ref["u0"][k]) <= TOL
+    assert np.all(a["status"] == 0)
+
+
+def test_assemble_on_device(hk, oracle):
+    for N, track in ((2, S.OVAL), (4, S.COMPLEX), (1, S.OVAL), (3, S.COMPLEX)):
+        p = S.make_problems(track, 300, N, seed=77)
+        ref = oracle.lqng_solve_batch(*S.assemble_dense(p), 3, full=False)
+        got = lqr.assemble_solve_batch(p, 3)
+        for b in range(300):
+            assert rel_err(got["u0"][b], ref["u0"][b]) <= TOL

@@ -1,0 +1,206 @@
+"""CPU tests (no GPU): the oracle against everything that pins it — the surveyor's independently computed known answers
+(SURVEY.md Appendix D -> tests/golden/game_kat.json), Random123 Philox vectors, the closed-form policy distribution
+(SURVEY.md B.7), an independent numpy restatement of the solver, and the committed golden fixture."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from hierarchicalkarting_b200 import abi, lqr, scenarios as S, tracks
+from oracle import np_lqng
+
+KAT = json.load(open("tests/golden/game_kat.json"))
+
+
+def test_max_speed_kat(oracle):
+    k = abi.hk_kart(*tracks.KART_COMPETE)
+    f = oracle.lib().hk_oracle_max_speed_for_radius_and_wear
+    for r, w, want in KAT["max_speed_for_radius_and_wear"]:
+        assert np.float32(f(C.byref(k), r, w)) == np.float32(want)
+
+
+def test_apply_action_kat(oracle):
+    L = oracle.lib()
+    k = abi.hk_kart(*tracks.KART_COMPETE)
+    for c in KAT["apply_action"]:
+        insideR, length, width, deg, left = c["section"]
+        secs = (abi.hk_section * 2)(abi.hk_section(insideR, length, width, deg, left, 1), abi.hk_section(insideR, length, width, deg, left, 1))
+        g = oracle.Game(secs, 2, tracks.kart_array(2), 2, tracks.game_params(tracks.OVAL))
+        lane, mn, mx, tire, t = c["from"]
+        ks = abi.hk_kart_state(0, 0, 0, t, mn, mx, lane, tire, 0, 0)
+        a = abi.hk_action(*c["action"])
+        ns = g.apply_action(ks, a)
+        d = L.hk_oracle_distance_to_travel(C.byref(secs[0]), lane, a.lane)
+        r = L.hk_oracle_radius_of_lane(C.byref(secs[0]), lane, a.lane)
+        toc = L.hk_oracle_compute_toc(C.byref(k), d, r, 0.0, (mn + mx) / 2, (a.min_velocity + a.max_velocity) / 2)
+        # the survey prints 7-8 significant digits: allow the last printed digit (< 1 ulp); the derived ints below are exact
+        close = lambda x, y: abs(float(np.float32(x)) - y) <= 1.2e-7 * max(1.0, abs(y))
+        assert close(d, c["dist"]) and np.float32(r) == np.float32(c["radius"])
+        assert close(toc, c["toc"])
+        assert ns.timeAtSection == c["time"] and ns.infeasible == c["infeasible"]
+        if not c["infeasible"]:
+            assert close(L.hk_oracle_tire_load(C.byref(secs[0]), float(a.max_velocity), lane, a.lane), c["tireLoad"])
+            assert ns.tireAge == c["tireAge"]
+        assert ns.section == 1 and ns.lane == a.lane
+
+
+def test_philox_kat(oracle):
+    for c in KAT["philox4x32_10"]:
+        assert [int(x) for x in oracle.philox(c["seed"], *c["ctr"])] == c["out"]
+
+
+def test_policy_cdf_closed_form(oracle):
+    for cnt, pmf in KAT["policy_pmf"].items():
+        cdf = oracle.policy_cdf(int(cnt)).astype(np.float64) / 2**32
+        got = np.diff(np.concatenate([[0.0], cdf]))
+        assert np.allclose(got[:len(pmf)], pmf, atol=6e-5), (cnt, got[:len(pmf)])
+    for cnt in (1, 2):
+        cdf = oracle.policy_cdf(cnt)
+        assert cdf[-1] == 0xFFFFFFFF and (cnt == 1 or cdf[0] == 2**31)
+
+
+def test_reference_sampler_matches_cdf(oracle):
+    """The reference's own procedure (Box-Muller, float NextGaussian, <=10 redraws, RoundToInt(|x|)) vs the CDF tables."""
+    L = oracle.lib()
+    for cnt in (3, 5, 8, 20, 36):
+        st = C.c_uint64(12345 + cnt)
+        n = 200000
+        hist = np.zeros(cnt)
+        for _ in range(n):
+            hist[L.hk_oracle_reference_policy_index(cnt, C.byref(st))] += 1
+        cdf = oracle.policy_cdf(cnt).astype(np.float64)
+        cdf[-1] = 2.0**32
+        p = np.diff(np.concatenate([[0.0], cdf])) / 2**32
+        big = p * n >= 10
+        chi2 = float(np.sum((hist[big] - p[big] * n) ** 2 / (p[big] * n)))
+        dof = int(big.sum()) - 1
+        assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (cnt, chi2, dof)
+
+
+def test_upnext_orders(oracle):
+    """2 and 4 karts: stable; 3 karts: IntroSort's 3-exchange network is not stable — [a, a', b] with b smaller yields
+    [b, a', a], so when b already moved the next kart is a' (index 1), not a (index 0)."""
+    track = tracks.OVAL
+    g = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(3), 3, tracks.game_params(track))
+    st = tracks.root_state(track, 5, [1, 2, 3], teams=[0, 1, 2])
+    assert g.up_next(st) == 0                        # all tied: (0,1) no swap, (0,2) no swap, (1,2) no swap
+    st.karts[2].section = 6; st.karts[2].timeAtSection = -5   # moved already; sorts last by section
+    assert g.up_next(st) == 0
+    st.karts[2].section = 5; st.karts[2].timeAtSection = -5   # same section, earlier time -> b smaller than a, a'
+    assert g.up_next(st) == 2
+    st.karts[2].section = 4                                  # smaller section: first in order but also != last+1
+    assert g.up_next(st) == 2
+    # network instability: order becomes [2, 1, 0]; make kart 2 ineligible (section == last+1) and smaller by time
+    st2 = tracks.root_state(track, 5, [1, 2, 3], teams=[0, 1, 2])
+    st2.lastCompletedSection = 5
+    st2.karts[0].section = 7; st2.karts[1].section = 7; st2.karts[2].section = 6
+    assert g.up_next(st2) == 1
+    g4 = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(4), 4, tracks.game_params(track))
+    st4 = tracks.root_state(track, 5, [1, 2, 3, 4], teams=[0, 0, 1, 1])
+    st4.lastCompletedSection = 5
+    for i, s in enumerate((7, 7, 6, 7)):
+        st4.karts[i].section = s
+    assert g4.up_next(st4) == 0                       # insertion sort keeps ties in index order
+
+
+def test_is_over_quirks(oracle):
+    track = tracks.OVAL
+    g = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, tracks.game_params(track))
+    st = tracks.root_state(track, 0, [2, 3], teams=[0, 1], buckets=[(8, 10), (8, 10)])
+    st.finalSection = 0
+    st.karts[0].timeAtSection, st.karts[1].timeAtSection = 500, 400
+    over, sc = g.is_over(st)                          # accumulators never reset: (t1 - t0, -(t0 + t1)/2...) -> normalised (1, 0)
+    assert over == 1 and list(sc) == [1.0, 0.0]
+    st.karts[0].timeAtSection, st.karts[1].timeAtSection = 1300, 400    # t0 >= 3 t1 flips it
+    over, sc = g.is_over(st)
+    assert over == 1 and list(sc) == [0.0, 1.0]
+    st.finalSection = 8
+    assert g.is_over(st)[0] == 0
+    # no legal move: lateral-g limit with huge wear on a tight corner cannot happen on the Oval; force it through lane rule
+    st.karts[0].laneChanges = 99
+    st.karts[0].timeAtSection = 0
+    p = tracks.game_params(track); p.maxLaneChanges = -1
+    g2 = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, p)
+    over, sc = g2.is_over(st)                         # upNext = kart 1 (time 400 > 0? no: kart 0 has time 0) -> kart 0
+    assert over == 1 and list(sc) == [0.0, 0.5, 0.5]  # missing `else`: list longer than N
+
+
+def test_lqng_oracle_vs_numpy_and_smoke(oracle):
+    dt = S.DT
+    me, opp = np.array([10, 2, 12, 0.3]), np.array([13, 3.5, 11, 0.25])
+    dyn = [lqr.LinearizedBicycle(dt, me), lqr.LinearizedBicycle(dt, opp)]
+
+    def mk(i, x, tgt, otgt, mult):
+        o = opp if i == 0 else me
+        d = np.float32(np.linalg.norm((o[:2] - x[:2]).astype(np.float32)))
+        w = float(np.float32(1) / (np.float32(np.power(d, np.float32(1.5))) * np.float32(mult)))
+        v = x[2]
+        tw = {0: 0.3 * 3.1 / max(1, v), 1: 0.3 * 3.1 / max(1, v), 2: 5e-4, 3: 3.5}
+        return lqr.LQRCheckpointReachAvoidCost(tgt, tw, 0.115, dyn[i], [np.array([otgt[0], otgt[1], otgt[2], 0.0])],
+                                               [{0: 0.2 / max(1, v), 1: 0.2 / max(1, v), 2: 0.08}], {0: [w], 1: [w]}, {0: [0], 1: [1]}, [dyn[1 - i]])
+    t0, t1 = np.array([20, 5, 15, 0.35]), np.array([20, 7.5, 15, 0.3])
+    A, B, Q, q, R, x0 = lqr.flatten(dyn, [mk(0, me, t0, t1, 1.0), mk(1, opp, t1, t0, 1.3)], [me, opp])
+    r = oracle.lqng_solve_batch(A[None], B[None], Q[None], q[None], R[None], x0[None], 3)
+    assert np.allclose(r["u0"][0, :2], KAT["lqng_smoke_u0"], atol=5e-6)           # surveyor's independent numpy value
+    # provider classes == oracle cost restatement, entry for entry
+    for N, track in ((2, S.OVAL), (3, S.COMPLEX), (4, S.COMPLEX)):
+        p = S.make_problems(track, 40, N, seed=3)
+        A, B, Q, q, R, x0 = S.assemble_dense(p)
+        for b in range(0, 40, 7):
+            for i in range(N):
+                Qo, qo, Ro = oracle.cost(p["target"][b, i], p["tw"][b, i], p["cw"][b, i], p["aw"][b, i], p["otgt"][b, i], p["otw"][b, i])
+                assert np.array_equal(Qo, Q[b, i]) and np.array_equal(qo, q[b, i]) and np.array_equal(Ro, R[b, i])
+                assert np.array_equal(oracle.bicycle_A(p["dt"], p["x0"][b, i]), A[b, i]) and np.array_equal(oracle.bicycle_B(p["dt"]), B[b, i])
+        r = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 3)
+        for b in range(0, 40, 5):
+            u, Ps, als, uall = np_lqng.solve_feedback_lqr(list(A[b]), list(B[b]), list(Q[b]), list(q[b]), list(R[b]), list(x0[b].reshape(N, 4)), 3)
+            assert rel_err(r["P"][b], Ps) < 1e-11 and rel_err(r["alpha"][b], als) < 1e-11 and rel_err(r["u0"][b], uall) < 1e-11
+    assert np.all(r["status"] == 0)
+
+
+def test_quirks_matter(oracle):
+    """Q1 (block placement) and Q2 (eta uses the updated Z) move u0 far above the 1e-9 tolerance: the restatement
+    must keep them."""
+    p = S.make_problems(S.OVAL, 16, 2, seed=8)
+    A, B, Q, q, R, x0 = S.assemble_dense(p)
+    r = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 3)
+    # a "textbook" variant: transpose the block placement by swapping the two players' roles in LHS only is not expressible
+    # through the API, so check sensitivity instead: u0 of player 0 differs from a single-player solve of the same cost
+    A1, B1, Q1, q1, R1, x1 = A[:, :1], B[:, :1], Q[:, :1, :4, :4].copy(), q[:, :1, :4].copy(), R[:, :1], x0[:, :4].copy()
+    r1 = oracle.lqng_solve_batch(A1, B1, Q1, q1, R1, x1, 3)
+    assert np.max(np.abs(r1["u0"][:, :2] - r["u0"][:, :2])) > 1e-6
+
+
+def test_golden_fixture_matches_oracle(oracle):
+    g = np.load("tests/golden/lqng_golden.npz")
+    for N in (2, 4):
+        r = oracle.lqng_solve_batch(*(g[f"N{N}_{k}"] for k in ("A", "B", "Q", "q", "R", "x0")), 3)
+        for k in ("u0", "P", "alpha", "traj"):
+            assert np.array_equal(r[k], g[f"N{N}_{k}_out"])
+
+
+def test_time_varying_reduces_to_invariant(oracle):
+    p = S.make_problems(S.OVAL, 8, 2, seed=2)
+    A, B, Q, q, R, x0 = S.assemble_dense(p)
+    T = 4
+    rep = lambda a: np.ascontiguousarray(np.repeat(a[:, None], T, axis=1))
+    a = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 3)
+    b = oracle.lqng_solve_batch(rep(A), rep(B), rep(Q), rep(q), rep(R), x0, 3, time_varying=True)
+    for k in ("u0", "P", "alpha", "traj"):
+        assert np.array_equal(a[k], b[k])
+
+
+def test_rollout_oracle_modes_agree_distributionally(oracle):
+    track = tracks.COMPLEX
+    g = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, tracks.game_params(track))
+    leaf = tracks.root_state(track, 12, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 37])
+    n = 20000
+    a, b = g.rollouts(leaf, n, mode=0, seed=1), g.rollouts(leaf, n, mode=1, seed=2)
+    assert a["visit"].sum() == n and b["visit"].sum() == n
+    big = (a["visit"] + b["visit"]) >= 20
+    x, y = a["visit"][big].astype(float), b["visit"][big].astype(float)
+    chi2, dof = float(np.sum((x - y) ** 2 / (x + y))), int(big.sum()) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10
+    assert 2 <= a["plies"] / n <= 16
