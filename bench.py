@@ -182,7 +182,12 @@ def main():
     u0_h = torch.empty((batch, m), dtype=torch.float64).pin_memory()
     st_h = torch.empty((batch,), dtype=torch.int32).pin_memory()
     d2h_bytes = int(u0_h.numel() * 8 + st_h.numel() * 4)
-    stream = torch.cuda.current_stream()
+    # a real (non-NULL) stream: the ABI treats a NULL stream as "the calling thread's own stream", and torch's events
+    # only see the stream they are recorded on, so kernel launches and events must share this one
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    torch.cuda.synchronize()                       # input copies above ran on the default stream
     launches = 0
 
     def step_device(k):

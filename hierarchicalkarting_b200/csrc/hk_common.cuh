@@ -21,6 +21,7 @@ struct ThreadCtx {
     void* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};      // pinned
     size_t hcap[4] = {0, 0, 0, 0};
     bool ready = false;
+    unsigned launch_id = 0;                                   // alternates the redo counters of the LQNG fast path
     ~ThreadCtx();
 };
 

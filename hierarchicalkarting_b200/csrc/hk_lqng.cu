@@ -14,6 +14,7 @@
 // Record layout of the operands = include/hk_abi.h (problem-major: one warp reads one problem's record with fully
 // coalesced 128-bit loads; there is no cross-problem reuse, so HBM traffic = algorithmic bytes).
 #include "hk_common.cuh"
+#include <cstdlib>
 
 namespace hk {
 
@@ -22,6 +23,9 @@ struct LqngParams {
     const double *A, *B, *Q, *q, *R, *x0;
     double *u0, *P, *alpha, *traj;
     int* status;
+    const int* redo_list;      // non-null: solve only problems redo_list[0 .. *redo_count) (queued by a fast kernel)
+    const int* redo_count;
+    int* reset_count;          // counter of the NEXT launch, cleared here (stream order makes that safe)
 };
 
 template <int N>
@@ -56,8 +60,15 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
     const int gpb = blockDim.x / G;
     const int g = threadIdx.x / G, r = threadIdx.x % G;
     long long prob = (long long)blockIdx.x * gpb + g;
-    const bool live = prob < p.batch;
-    if (!live) prob = p.batch - 1;           // dead groups shadow the last problem so that __syncwarp stays converged
+    long long count = p.batch;
+    if (p.redo_list) {
+        count = *p.redo_count;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && p.reset_count) *p.reset_count = 0;
+        if ((long long)blockIdx.x * gpb >= count) return;          // block-uniform: nothing queued for this block
+    }
+    const bool live = prob < count;
+    if (!live) prob = count - 1;             // dead groups shadow the last problem so that __syncwarp stays converged
+    if (p.redo_list) prob = p.redo_list[prob];
     double* s = smem + (size_t)g * L::total;
     double *Z = s + L::oZ, *F = s + L::oF, *Y = s + L::oY, *M = s + L::oM, *W = s + L::oW, *As = s + L::oA, *Bs = s + L::oB,
            *Rs = s + L::oR, *eta = s + L::oEta, *beta = s + L::oBeta, *tmp = s + L::oTmp, *xs = s + L::oX, *us = s + L::oU;
@@ -262,6 +273,10 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
     }
 }
 
+}  // namespace hk
+#include "hk_lqng_mma.cuh"
+namespace hk {
+
 template <int N>
 static int launch_generic(const LqngParams& p, cudaStream_t stream)
 {
@@ -354,7 +369,27 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
                 double* dtraj, int* dstatus, cudaStream_t stream)
 {
     if (batch == 0) return HK_OK;
-    LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus};
+    LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr};
+    static const bool force_generic = getenv("HK_LQNG_FORCE_GENERIC") != nullptr;
+    if (N == 2 && !time_varying && !dP && !dalpha && !dtraj && !force_generic) {
+        // throughput path: DMMA kernel, then the generic kernel over whatever it queued (normally nothing)
+        ThreadCtx* c = ctx();
+        if (!c) return HK_ERR_NO_DEVICE;
+        const size_t need = sizeof(int) * (4 + (size_t)batch);
+        const bool fresh = need > c->dcap[6];
+        int* scratch = (int*)dscratch(c, 6, need);
+        if (!scratch) return HK_ERR_OUT_OF_MEMORY;
+        if (fresh) { HK_CUDA(cudaMemsetAsync(scratch, 0, 16, stream)); c->launch_id = 0; }
+        int* counter = scratch + (c->launch_id & 1);
+        int* next_counter = scratch + ((c->launch_id + 1) & 1);
+        c->launch_id++;
+        int* list = scratch + 4;
+        const int wpb = MMA2_THREADS / 32;
+        lqng_mma2_kernel<<<(batch + wpb - 1) / wpb, MMA2_THREADS, 0, stream>>>(p, list, counter);
+        HK_CUDA(cudaGetLastError());
+        p.redo_list = list; p.redo_count = counter; p.reset_count = next_counter;
+        return launch_generic<2>(p, stream);
+    }
     switch (N) {
         case 1: return launch_generic<1>(p, stream);
         case 2: return launch_generic<2>(p, stream);

@@ -1,0 +1,213 @@
+// hk_lqng_mma.cuh — warp-per-problem FP64 tensor-core (DMMA m8n8k4) kernel for the time-invariant 2-kart LQNG
+// (n = 8, m = 4), the BASELINE headline configuration.  Same algorithm as KartLQR.solveFeedbackLQR
+// (reference: Assets/Karting/Scripts/AI/LQR/KartLQR.cs:64-127), re-associated so that every 8x8 product is a pair of
+// mma.sync.m8n8k4.f64 and no matrix ever leaves the register file.
+//
+// Why DMMA (measured on B200, profiles/fp64_microbench_r01.md): DFMA and DMMA share the FP64 pipe and reach the same
+// flop rate (33.5 vs 37.0 TFLOP/s sustained), but one DMMA replaces 8 DFMA warp-instructions AND does the operand
+// broadcast that a lane-per-row DFMA kernel pays for with shuffles (1.28 SHFL/clk/SM) or shared-memory loads.
+//
+// Register forms of an 8x8 matrix M, lane L = 4g + t (g = L>>2 in 0..7, t = L&3):
+//   R-form (m0,m1) = (M[g][2t],  M[g][2t+1])   = the DMMA C/D fragment; directly usable as an A operand whose four k-slots
+//                                                  are k = 2t (first DMMA) and k = 2t+1 (second DMMA);
+//   T-form (m0,m1) = (M[2t][g],  M[2t+1][g])   = R-form of M^T; directly usable as a B operand with the same k permutation.
+// so  D(R-form) = X(R-form) * Y(T-form)  costs two DMMAs and zero data movement, and the R-form registers of M double as
+// the T-form of M^T.  The recursion is arranged so that every product finds its operands already in the right form:
+//   Y_i^T = F^T Z_i^T            X = F T-form (= F^T R-form),   Y = Z_i R-form (= Z_i^T T-form)   -> Y_i in T-form
+//   Z_i  <- Q_i + P_i^T(R_i P_i) + F^T Y_i                       (accumulated in the C fragment)
+//   W     = sum_i [B_i^T ; beta^T] Z_i      rows 0..3 = stacked B_i^T Z_i, row 4+i = (Z_i beta)^T  (needs Z_i symmetric)
+//   L     = W B,  RM^T = A^T W^T,  P = LHS^-1 RM (as RM^T Lambda^T),  alpha = LHS^-1 rv,  u^T = (eta + Z beta)^T F
+// Vectors (eta_i, q_i, beta, Z_i beta) ride in rows 4 and 5 of these products, lane (4+i, t) holding entries (2t, 2t+1).
+// The 4x4 coupled system is inverted in place by Gauss-Jordan over 8 lanes; the kernel verifies at every pivot that
+// partial pivoting (MathNet LU, KartLQR.cs:104-105) would not have exchanged rows — otherwise, or if Q_i / R_i are not
+// symmetric, the problem is queued for the generic kernel, which pivots.
+#pragma once
+
+namespace hk {
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// D += X(R-form) * Y(T-form)
+__device__ __forceinline__ void mm(double& c0, double& c1, double x0, double x1, double y0, double y1)
+{
+    dmma(c0, c1, x0, y0);
+    dmma(c0, c1, x1, y1);
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+constexpr int MMA2_THREADS = 128;
+
+__global__ void __launch_bounds__(MMA2_THREADS) lqng_mma2_kernel(LqngParams p, int* __restrict__ redo_list, int* __restrict__ redo_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const long long prob = (long long)blockIdx.x * (MMA2_THREADS / 32) + (threadIdx.x >> 5);
+    if (prob >= p.batch) return;                                   // whole warps only: no divergence inside a warp
+    const double* gA = p.A + (size_t)prob * 32;
+    const double* gB = p.B + (size_t)prob * 16;
+    const double* gQ = p.Q + (size_t)prob * 128;
+    const double* gq = p.q + (size_t)prob * 16;
+    const double* gR = p.R + (size_t)prob * 8;
+    const double* gx = p.x0 + (size_t)prob * 8;
+
+    // ---- per-lane constants --------------------------------------------------------------------------------------
+    const int pl = t >> 1;                                          // player owning joint rows 2t, 2t+1 (and control row t)
+    const int lr = (2 * t) & 3;                                     // local row of joint row 2t inside A_pl / B_pl
+    // joint A in T-form: (A[2t][g], A[2t+1][g]); block diagonal (KartLQR.cs:33-37)
+    const bool a_on = pl == (g >> 2);
+    const double aT0 = a_on ? gA[pl * 16 + lr * 4 + (g & 3)] : 0.0;
+    const double aT1 = a_on ? gA[pl * 16 + (lr + 1) * 4 + (g & 3)] : 0.0;
+    // joint B (8x4, column c belongs to player c>>1; KartLQR.cs:41-52) in T-form, padded to 8 columns
+    const bool b_on = g < 4 && pl == (g >> 1);
+    const double bT0 = b_on ? gB[pl * 8 + lr * 2 + (g & 1)] : 0.0;
+    const double bT1 = b_on ? gB[pl * 8 + (lr + 1) * 2 + (g & 1)] : 0.0;
+    // B rows 2t, 2t+1 against their own player's two controls (F = A - B P, beta = -B alpha; KartLQR.cs:110-111)
+    const double bF00 = gB[pl * 8 + lr * 2 + 0], bF01 = gB[pl * 8 + lr * 2 + 1];
+    const double bF10 = gB[pl * 8 + (lr + 1) * 2 + 0], bF11 = gB[pl * 8 + (lr + 1) * 2 + 1];
+    // R of player t>>1, row t&1 (for R P and R alpha), and the diagonal-block entries of the coupled LHS
+    const double rr0 = gR[pl * 4 + (t & 1) * 2 + 0], rr1 = gR[pl * 4 + (t & 1) * 2 + 1];
+    const bool lhs_lane = g < 4 && t < 2;                           // natural LHS distribution, see below
+    const bool l_diag = lhs_lane && t == (g >> 1);
+    const double rl0 = l_diag ? gR[(g >> 1) * 4 + (g & 1) * 2 + 0] : 0.0;
+    const double rl1 = l_diag ? gR[(g >> 1) * 4 + (g & 1) * 2 + 1] : 0.0;
+    const double xg = gx[g];
+    const bool vec_lane = (g >> 1) == 2;                            // quads 4 and 5 carry the vectors of player g-4
+    const int vp = g & 1;
+    double2 qv = make_double2(0.0, 0.0);
+    if (vec_lane) qv = *reinterpret_cast<const double2*>(gq + vp * 8 + 2 * t);
+    // Q_i in R-form (coalesced 128-bit loads: lane L reads doubles 2L, 2L+1 of the 8x8 block)
+    const double2 q0 = *reinterpret_cast<const double2*>(gQ + 2 * lane);
+    const double2 q1 = *reinterpret_cast<const double2*>(gQ + 64 + 2 * lane);
+    // symmetry of Q_i and R_i is what lets Z_i's R-form stand in for its T-form in the W product
+    bool redo = (gQ[(2 * t) * 8 + g] != q0.x) | (gQ[(2 * t + 1) * 8 + g] != q0.y) | (gQ[64 + (2 * t) * 8 + g] != q1.x) |
+                (gQ[64 + (2 * t + 1) * 8 + g] != q1.y) | (gR[1] != gR[2]) | (gR[5] != gR[6]);
+    int singular = 0;
+
+    // shuffle sources of the Gauss-Jordan inversion. Natural LHS distribution: lane (g<4, t<2) holds
+    // LHS[rho][2*kap], LHS[rho][2*kap+1] with rho = 2t + (g&1), kap = g>>1 — exactly where the D fragment of L = W B leaves
+    // them once the reference's block placement is applied (block (i,j) of B_i^T Z_i B_j goes to row-block j,
+    // column-block i: quirk Q1, KartLQR.cs:68-87).
+    const int rho = 2 * t + (g & 1), kap = g >> 1;
+    // Lambda rows re-dealt as the B operand of the P product: column map s(col) = (0,1,0,1,2,3,2,3)
+    const int s_of_g = ((g >> 2) << 1) | (g & 1);
+    const int srcLam = 4 * ((s_of_g & 1) + 2 * (t & 1)) + (s_of_g >> 1);
+    const int srcRv = 4 * (4 + (t & 1)) + (t & 1);
+
+    // ---- state ------------------------------------------------------------------------------------------------------
+    double z00 = q0.x, z01 = q0.y, z10 = q1.x, z11 = q1.y;         // Z_i = Q_i (KartLQR.cs:62)
+    double e0 = qv.x, e1 = qv.y;                                    // eta_i = q_i (:63), lanes (4+i, t)
+    double w0 = 0.0, w1 = 0.0;                                      // W (rows 0..3) and Z_i beta (rows 4, 5)
+    {
+        const bool m0 = g < 2, m1 = g == 2 || g == 3;
+        mm(w0, w1, m0 ? bT0 : 0.0, m0 ? bT1 : 0.0, z00, z01);
+        mm(w0, w1, m1 ? bT0 : 0.0, m1 ? bT1 : 0.0, z10, z11);
+    }
+    double pe = 0.0, po = 0.0, ae = 0.0, ao = 0.0;
+
+    for (int step = p.horizon; step >= 0; --step) {                 // KartLQR.cs:64
+        // L = W B with eta^T B in rows 4, 5 (RHSVec, :96)
+        double l0 = 0.0, l1 = 0.0;
+        {
+            const double x0 = g < 4 ? w0 : (vec_lane ? e0 : 0.0), x1 = g < 4 ? w1 : (vec_lane ? e1 : 0.0);
+            mm(l0, l1, x0, x1, bT0, bT1);
+        }
+        // RM^T = A^T W^T (RHSMat, :89-95)
+        double m0 = 0.0, m1 = 0.0;
+        mm(m0, m1, aT0, aT1, g < 4 ? w0 : 0.0, g < 4 ? w1 : 0.0);
+        // coupled LHS in the natural distribution (+ R_i on the diagonal blocks, :78), inverted in place by Gauss-Jordan
+        double M0 = l0 + rl0, M1 = l1 + rl1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int kk = k >> 1, bk = k & 1;
+            const double mine = bk ? M1 : M0;
+            const double c = shfl_d(mine, 4 * ((g & 1) + 2 * kk) + t);                    // LHS[rho][k]
+            const int srcR = 4 * ((k & 1) + 2 * (g >> 1)) + (k >> 1);
+            const double r0 = shfl_d(M0, srcR), r1 = shfl_d(M1, srcR);                    // LHS[k][2 kap], LHS[k][2 kap + 1]
+            const double pv = shfl_d(c, 4 * (k & 1) + (k >> 1));                          // LHS[k][k]
+            redo |= lhs_lane && rho > k && fabs(c) > fabs(pv);                            // partial pivoting would swap rows
+            if (pv == 0.0) singular = 1;
+            const double pinv = 1.0 / pv;
+            const double f = c * pinv;
+            const bool prow = rho == k;
+            const double n0 = prow ? r0 * pinv : fma(-f, r0, M0);
+            const double n1 = prow ? r1 * pinv : fma(-f, r1, M1);
+            const double dk = prow ? pinv : -f;                                           // column k of the in-place inverse
+            M0 = (kap == kk && bk == 0) ? dk : n0;
+            M1 = (kap == kk && bk == 1) ? dk : n1;
+        }
+        // Lambda = LHS^-1 as B operand: Y[k][col] = Lambda[s(col)][k]
+        const bool ylane = t < 2;
+        double y0 = shfl_d(M0, srcLam), y1 = shfl_d(M1, srcLam);
+        y0 = ylane ? y0 : 0.0; y1 = ylane ? y1 : 0.0;
+        // P (both rows of player t>>1 for column g): (pe, po) = (P[2(t>>1)][g], P[2(t>>1)+1][g])   (:104)
+        pe = 0.0; po = 0.0;
+        mm(pe, po, m0, m1, y0, y1);
+        // alpha = Lambda rv: rows 4, 5 of the A operand both carry rv^T   (:105)
+        {
+            double v0 = shfl_d(l0, srcRv), v1 = shfl_d(l1, srcRv);
+            const bool on = vec_lane && t < 2;
+            v0 = on ? v0 : 0.0; v1 = on ? v1 : 0.0;
+            ae = 0.0; ao = 0.0;
+            mm(ae, ao, v0, v1, y0, y1);                              // lanes (4+i, t): alpha of player t>>1
+        }
+        const double pc = (t & 1) ? po : pe;                        // compact P: P[t][g]
+        if (step == 0) break;                                       // the last update of Z, eta is never used (:121-126)
+
+        // F = A - B P (T-form), beta = -B alpha (rows 2t, 2t+1 at lanes (4+i, t))   (:110-111)
+        const double f0 = aT0 - fma(bF01, po, bF00 * pe);
+        const double f1 = aT1 - fma(bF11, po, bF10 * pe);
+        const double be0 = vec_lane ? -fma(bF01, ao, bF00 * ae) : 0.0;
+        const double be1 = vec_lane ? -fma(bF11, ao, bF10 * ae) : 0.0;
+        const double rpc = fma(rr1, po, rr0 * pe);                  // (R_p P_p)[t&1][g]
+        // Z_i <- Q_i + P_i^T R_i P_i + F^T (Z_i F)   (:116)
+        {
+            double yt0 = 0.0, yt1 = 0.0;
+            mm(yt0, yt1, f0, f1, z00, z01);
+            z00 = q0.x; z01 = q0.y;
+            dmma(z00, z01, pl == 0 ? pc : 0.0, rpc);
+            mm(z00, z01, f0, f1, yt0, yt1);
+        }
+        {
+            double yt0 = 0.0, yt1 = 0.0;
+            mm(yt0, yt1, f0, f1, z10, z11);
+            z10 = q1.x; z11 = q1.y;
+            dmma(z10, z11, pl == 1 ? pc : 0.0, rpc);
+            mm(z10, z11, f0, f1, yt0, yt1);
+        }
+        // W for the next step, with beta^T in row 4+i so that row 4+i of the result is (Z_i^{new} beta)^T   (quirk Q2)
+        w0 = 0.0; w1 = 0.0;
+        {
+            const bool m0b = g < 2, m1b = g == 2 || g == 3;
+            mm(w0, w1, m0b ? bT0 : (g == 4 ? be0 : 0.0), m0b ? bT1 : (g == 4 ? be1 : 0.0), z00, z01);
+            mm(w0, w1, m1b ? bT0 : (g == 5 ? be0 : 0.0), m1b ? bT1 : (g == 5 ? be1 : 0.0), z10, z11);
+        }
+        // eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)   (:117)
+        {
+            const double ra = fma(rr1, ao, rr0 * ae);               // (R_i alpha_i)[t&1] at lanes (4+i, 2i + (t&1))
+            double n0 = qv.x, n1 = qv.y;
+            dmma(n0, n1, (vec_lane && pl == vp) ? ra : 0.0, pc);
+            mm(n0, n1, vec_lane ? e0 + w0 : 0.0, vec_lane ? e1 + w1 : 0.0, f0, f1);
+            e0 = n0; e1 = n1;
+        }
+    }
+    // optimal_control = -P x0 - alpha with the t = 0 gains (:121-126): reduce P[t][g] x0[g] over g
+    double acc;
+    {
+        const double pc = (t & 1) ? po : pe;
+        acc = -pc * xg;
+        acc += shfl_d(acc, lane ^ 4);
+        acc += shfl_d(acc, lane ^ 8);
+        acc += shfl_d(acc, lane ^ 16);
+    }
+    const unsigned any_redo = __ballot_sync(0xffffffffu, redo || singular);
+    if (any_redo) {
+        if (lane == 0) redo_list[atomicAdd(redo_count, 1)] = (int)prob;
+        return;
+    }
+    if (g == 4) p.u0[(size_t)prob * 4 + t] = acc - ((t & 1) ? ao : ae);
+    if (lane == 0 && p.status) p.status[prob] = 0;
+}
+
+}  // namespace hk
