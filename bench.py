@@ -217,6 +217,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     launches = 0
+    k0 = lib.hk_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(args.steps):
@@ -225,7 +226,7 @@ def main():
     e1.synchronize()
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    gpu_launches = launches
+    gpu_launches = int(lib.hk_kernel_launch_count() - k0)      # counted inside the library at every <<<>>> site
     # per-launch kernel duration for the roofline (events around single launches, rotating inputs)
     per = []
     for k in range(min(args.steps, 20)):

@@ -1,0 +1,61 @@
+// HkNative.cs — P/Invoke bindings of libhk_b200 (include/hk_abi.h). Drop next to the shims in Assets/Karting/Scripts/AI/.
+// Blittable structs mirror the C structs field for field ([StructLayout(LayoutKind.Sequential)]); every call returns an
+// hk_status (0 = OK) and HkNative.Check turns failures into exceptions carrying hk_last_error().
+using System;
+using System.Runtime.InteropServices;
+
+namespace KartGame.AI.Native
+{
+    [StructLayout(LayoutKind.Sequential)] public struct HkSection { public float insideR, length, width, turnDeg; public int leftTurn, optimalLane; }
+    [StructLayout(LayoutKind.Sequential)] public struct HkKart { public float accel, braking, topSpeed, reverseSpeed, maxGs, minGs, tireWearFactor; }
+    [StructLayout(LayoutKind.Sequential)] public struct HkGameParams
+    {
+        public int velocityBucketSize, timePrecision, sectionWindow, treeSearchDepth, maxLaneChanges;
+        public float collisionWindow, teamScoreRewardMultiplier; public int maxEpisodeSteps;
+    }
+    [StructLayout(LayoutKind.Sequential)] public struct HkKartState
+    {
+        public int player, team, section, timeAtSection, min_velocity, max_velocity, lane, tireAge, laneChanges, infeasible;
+    }
+    [StructLayout(LayoutKind.Sequential)] public struct HkAction { public int min_velocity, max_velocity, lane; }
+    [StructLayout(LayoutKind.Sequential)] public struct HkGameState
+    {
+        public int n_karts, initialSection, lastCompletedSection, finalSection;
+        public HkKartState k0, k1, k2, k3;                      // karts[HK_MAX_KARTS]
+        public void Set(int i, HkKartState s) { if (i == 0) k0 = s; else if (i == 1) k1 = s; else if (i == 2) k2 = s; else k3 = s; }
+    }
+
+    public static class HkNative
+    {
+        const string Lib = "hk_b200";                            // libhk_b200.so / hk_b200.dll on the plugin search path
+        public const int MaxActions = 36, MaxKarts = 4;
+
+        [DllImport(Lib)] public static extern int hk_abi_version();
+        [DllImport(Lib)] public static extern int hk_init(int device);
+        [DllImport(Lib)] public static extern void hk_shutdown();
+        [DllImport(Lib)] static extern IntPtr hk_last_error();
+        [DllImport(Lib)] public static extern int hk_lqng_solve_one(int nPlayers, int horizon, double[] A, double[] B, double[] Q, double[] q,
+                                                                    double[] R, double[] x0, [Out] double[] u0);
+        [DllImport(Lib)] public static extern int hk_lqng_solve_batch(int batch, int nPlayers, int horizon, int timeVarying, double[] A, double[] B,
+                                                                      double[] Q, double[] q, double[] R, double[] x0, [Out] double[] u0,
+                                                                      [Out] double[] P, [Out] double[] alpha, [Out] double[] traj, [Out] int[] status);
+        [DllImport(Lib)] public static extern int hk_lqng_assemble_solve_batch(int batch, int nPlayers, int horizon, double dt, double[] x0, double[] target,
+                                                                               double[] tw, double[] cw, double[] aw, double[] otgt, double[] otw,
+                                                                               [Out] double[] u0, [Out] int[] status);
+        [DllImport(Lib)] public static extern int hk_game_create(HkSection[] sections, int nSections, HkKart[] karts, int nKarts, HkKart[] envKarts,
+                                                                 int nEnvKarts, ref HkGameParams p, out IntPtr game);
+        [DllImport(Lib)] public static extern void hk_game_destroy(IntPtr game);
+        [DllImport(Lib)] public static extern int hk_mcts_rollouts_multi(IntPtr game, HkGameState[] leaves, int nLeaves, long rolloutsPerLeaf, ulong seed,
+                                                                         ulong rolloutOffset, [Out] long[] visit, [Out] double[] rewardSum,
+                                                                         [Out] long[] nanCount, [Out] long[] pliesSum);
+
+        public static void Check(int status)
+        {
+            if (status == 0) return;
+            string msg = Marshal.PtrToStringAnsi(hk_last_error());
+            if (status == -1) throw new ArgumentException(msg);           // what MathNet throws on a dimension mismatch
+            if (status == -5) throw new ArgumentOutOfRangeException(msg); // upNext() == -1, KartDiscreteGame.cs:326
+            throw new InvalidOperationException("hk_b200 status " + status + ": " + msg);
+        }
+    }
+}

@@ -11,6 +11,9 @@ static thread_local char g_err[512] = "";
 static std::mutex g_mu;
 static std::atomic<int> g_device{-1};          // -1 = not initialised
 static std::atomic<int> g_device_state{0};     // 0 unknown, 1 ok, -1 no usable device
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...)
 {
@@ -109,6 +112,8 @@ using namespace hk;
 
 extern "C" int hk_abi_version(void) { return HK_ABI_VERSION; }
 extern "C" const char* hk_last_error(void) { return g_err; }
+
+extern "C" long long hk_kernel_launch_count(void) { return g_launches.load(); }
 
 extern "C" int hk_device_count(void)
 {

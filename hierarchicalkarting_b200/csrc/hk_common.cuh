@@ -9,6 +9,7 @@
 namespace hk {
 
 void set_error(const char* fmt, ...);
+void count_launch();                       // every kernel launch of this library (hk_kernel_launch_count)
 
 // Per host-thread context: the reference calls the planners from several C# threads (HierarchicalKartAgent.cs:246-283),
 // so every thread owns a stream and grow-only scratch buffers; nothing is shared but the immutable hk_game objects.

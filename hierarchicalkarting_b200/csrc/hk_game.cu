@@ -566,7 +566,7 @@ extern "C" int hk_game_replay_batch(const hk_game* g, int batch, int len, const 
     if (!d) return HK_ERR_OUT_OF_MEMORY;
     HK_CUDA(cudaMemcpyAsync(d + off[0], roots, sz[0], cudaMemcpyHostToDevice, c->stream));
     if (len) HK_CUDA(cudaMemcpyAsync(d + off[1], actions, sz[1], cudaMemcpyHostToDevice, c->stream));
-    replay_kernel<<<(batch + 127) / 128, 128, 0, c->stream>>>(g->dev, batch, len, (const hk_game_state*)(d + off[0]), (const hk_action*)(d + off[1]),
+    count_launch(); replay_kernel<<<(batch + 127) / 128, 128, 0, c->stream>>>(g->dev, batch, len, (const hk_game_state*)(d + off[0]), (const hk_action*)(d + off[1]),
         states_out ? (hk_game_state*)(d + off[2]) : nullptr, upnext_out ? (int*)(d + off[3]) : nullptr, over_out ? (int*)(d + off[4]) : nullptr,
         n_scores_out ? (int*)(d + off[5]) : nullptr, scores_out ? (float*)(d + off[6]) : nullptr, n_moves_out ? (int*)(d + off[7]) : nullptr,
         moves_out ? (hk_action*)(d + off[8]) : nullptr, moves_index_out ? (int*)(d + off[9]) : nullptr);
@@ -600,7 +600,7 @@ static int rollouts_impl(const hk_game* g, const hk_game_state* leaves, int n_le
         long long cap = (long long)sms * 16 / (n_leaves < sms * 16 ? 1 : 1);          // persistent-ish grid: 16 CTAs of 128 threads per SM
         if (n_leaves > 1) cap = (cap + n_leaves - 1) / n_leaves > 0 ? (cap + n_leaves - 1) / n_leaves : 1;
         dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_leaves);
-        rollouts_kernel<<<grid, 128, 0, c->stream>>>(g->dev, (const hk_game_state*)d, rollouts_per_leaf, seed, rollout_offset,
+        count_launch(); rollouts_kernel<<<grid, 128, 0, c->stream>>>(g->dev, (const hk_game_state*)d, rollouts_per_leaf, seed, rollout_offset,
             (unsigned long long*)(d + off[1]), (double*)(d + off[2]), (unsigned long long*)(d + off[3]), (unsigned long long*)(d + off[4]), (int*)(d + off[5]));
         HK_CUDA(cudaGetLastError());
     }
@@ -643,7 +643,7 @@ extern "C" int hk_mcts_rollouts_trace(const hk_game* g, const hk_game_state* lea
     char* d = (char*)dscratch(c, 0, off[6]);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
     HK_CUDA(cudaMemcpyAsync(d, leaf, sz[0], cudaMemcpyHostToDevice, c->stream));
-    rollouts_trace_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(g->dev, (const hk_game_state*)d, n_rollouts, seed, rollout_offset,
+    count_launch(); rollouts_trace_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(g->dev, (const hk_game_state*)d, n_rollouts, seed, rollout_offset,
         (int*)(d + off[1]), (hk_action*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (float*)(d + off[5]));
     HK_CUDA(cudaGetLastError());
     void* outs[5] = {n_plies_out, actions_out, choice_out, n_scores_out, scores_out};

@@ -52,24 +52,10 @@ struct GenericLayout {
 };
 
 template <int N>
-__global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
+__device__ __noinline__ void lqng_generic_body(const LqngParams& p, long long prob, const bool live, double* s, const int r, const unsigned mask)
 {
     using L = GenericLayout<N>;
     constexpr int n = L::n, m = L::m, G = L::G, LD = L::LD, AW = L::AW;
-    extern __shared__ double smem[];
-    const int gpb = blockDim.x / G;
-    const int g = threadIdx.x / G, r = threadIdx.x % G;
-    long long prob = (long long)blockIdx.x * gpb + g;
-    long long count = p.batch;
-    if (p.redo_list) {
-        count = *p.redo_count;
-        if (blockIdx.x == 0 && threadIdx.x == 0 && p.reset_count) *p.reset_count = 0;
-        if ((long long)blockIdx.x * gpb >= count) return;          // block-uniform: nothing queued for this block
-    }
-    const bool live = prob < count;
-    if (!live) prob = count - 1;             // dead groups shadow the last problem so that __syncwarp stays converged
-    if (p.redo_list) prob = p.redo_list[prob];
-    double* s = smem + (size_t)g * L::total;
     double *Z = s + L::oZ, *F = s + L::oF, *Y = s + L::oY, *M = s + L::oM, *W = s + L::oW, *As = s + L::oA, *Bs = s + L::oB,
            *Rs = s + L::oR, *eta = s + L::oEta, *beta = s + L::oBeta, *tmp = s + L::oTmp, *xs = s + L::oX, *us = s + L::oU;
 
@@ -100,7 +86,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
             for (int e = r; e < N * 8; e += G) Bs[e] = gB[(size_t)tt * N * 8 + e];
             for (int e = r; e < N * 4; e += G) Rs[e] = gR[(size_t)tt * N * 4 + e];
         }
-        __syncwarp();
+        __syncwarp(mask);
         // W_i = B_i^T Z_i (rows of block i only: B_i is zero elsewhere, KartLQR.cs:41-52); lane c owns column c
         if (r < n) {
             const int c = r;
@@ -114,7 +100,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
                     W[(2 * i + a) * n + c] = acc;
                 }
         }
-        __syncwarp();
+        __syncwarp(mask);
         // coupled system [LHS | RHSMat | RHSVec]; block (i,j) -> row-block j, column-block i (quirk Q1, KartLQR.cs:68-87)
         for (int e = r; e < m * m; e += G) {
             const int ia = e / m, jb = e % m;                     // raw[2i+a][2j+b] = (B_i^T Z_i B_j)[a][b]
@@ -142,7 +128,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
             for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], eta[i * n + 4 * i + k], acc);
             M[r * AW + m + n] = acc;
         }
-        __syncwarp();
+        __syncwarp(mask);
         // P = LHS.Solve(RHSMat), alpha = LHS.Solve(RHSVec): LU with partial pivoting (MathNet, KartLQR.cs:104-105)
         for (int k = 0; k < m; ++k) {
             int pr = k;
@@ -151,17 +137,17 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
                 double v = fabs(M[i * AW + k]);
                 if (v > best) { best = v; pr = i; }
             }
-            __syncwarp();
+            __syncwarp(mask);
             if (pr != k)
                 for (int c = r; c < AW; c += G) { double t0 = M[k * AW + c]; M[k * AW + c] = M[pr * AW + c]; M[pr * AW + c] = t0; }
-            __syncwarp();
+            __syncwarp(mask);
             const double piv = M[k * AW + k];
             if (piv == 0.0) singular = 1;
             for (int i = k + 1; i < m; ++i) {
                 const double l = M[i * AW + k] / piv;
                 for (int c = k + 1 + r; c < AW; c += G) M[i * AW + c] = fma(-l, M[k * AW + c], M[i * AW + c]);
             }
-            __syncwarp();
+            __syncwarp(mask);
         }
         for (int c = m + r; c < AW; c += G)
             for (int k = m - 1; k >= 0; --k) {
@@ -169,7 +155,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
                 for (int j = k + 1; j < m; ++j) x = fma(-M[k * AW + j], M[j * AW + c], x);
                 M[k * AW + c] = x / M[k * AW + k];
             }
-        __syncwarp();
+        __syncwarp(mask);
         // from here P[k][c] = M[k][m+c], alpha[k] = M[k][m+n]
         if (live) {
             if (gP) for (int e = r; e < m * n; e += G) gP[(size_t)t * m * n + e] = M[(e / n) * AW + m + e % n];
@@ -187,7 +173,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
             }
             beta[r] = -fma(b1, M[(2 * pr + 1) * AW + m + n], b0 * M[(2 * pr) * AW + m + n]);
         }
-        __syncwarp();
+        __syncwarp(mask);
         // Z_i <- Q_i + P_i^T R_i P_i + F^T Z_i F ; eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)  (:116-117)
         for (int i = 0; i < N; ++i) {
             double* Zi = Z + i * n * LD;
@@ -204,7 +190,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
                     Y[r * LD + c] = acc;
                 }
             }
-            __syncwarp();
+            __syncwarp(mask);
             if (r < n) {                                          // row r of the new Z_i
                 double fc[n];
 #pragma unroll
@@ -225,7 +211,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
                 }
                 tmp[r] = eta[i * n + r] + zb;                     // eta_i + Z_i^{new} beta (quirk Q2)
             }
-            __syncwarp();
+            __syncwarp(mask);
             if (r < n) {
                 double acc = 0.0;
 #pragma unroll
@@ -235,7 +221,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
                 const double pra = fma(M[(2 * i + 1) * AW + m + r], ra1, M[(2 * i) * AW + m + r] * ra0);
                 eta[i * n + r] = (gq[(size_t)tt * N * n + i * n + r] + pra) + acc;
             }
-            __syncwarp();
+            __syncwarp(mask);
         }
     }
     // optimal_control = -P x0 - alpha with the t = 0 pair (:121-126), every player
@@ -251,7 +237,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
     if (p.traj) {
         double* gt = p.traj + (size_t)prob * (T + 1) * n;
         if (live && r < n) gt[r] = xs[r];
-        __syncwarp();
+        __syncwarp(mask);
         for (int t = 0; t <= p.horizon; ++t) {
             const int tt = p.time_varying ? t : 0;
             if (r < m) {
@@ -259,17 +245,42 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
                 for (int c = 0; c < n; ++c) acc = fma(-gP[(size_t)t * m * n + r * n + c], xs[c], acc);
                 us[r] = acc - ga[(size_t)t * m + r];
             }
-            __syncwarp();
+            __syncwarp(mask);
             double xn = 0.0;
             if (r < n) {
                 const int pr = r / 4, rr = r % 4;
                 for (int c = 0; c < 4; ++c) xn = fma(gA[(size_t)tt * N * 16 + pr * 16 + rr * 4 + c], xs[4 * pr + c], xn);
                 for (int c = 0; c < 2; ++c) xn = fma(gB[(size_t)tt * N * 8 + pr * 8 + rr * 2 + c], us[2 * pr + c], xn);
             }
-            __syncwarp();
+            __syncwarp(mask);
             if (r < n) { xs[r] = xn; if (live) gt[(size_t)(t + 1) * n + r] = xn; }
-            __syncwarp();
+            __syncwarp(mask);
         }
+    }
+}
+
+
+template <int N>
+__global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
+{
+    using L = GenericLayout<N>;
+    constexpr int G = L::G;
+    extern __shared__ double smem[];
+    const int gpb = blockDim.x / G;
+    const int g = threadIdx.x / G, r = threadIdx.x % G;
+    long long count = p.batch;
+    if (p.redo_list) {
+        count = *p.redo_count;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && p.reset_count) *p.reset_count = 0;
+    }
+    // direct mode: one pass; redo mode: a small grid strides over whatever the fast kernel queued (normally nothing)
+    for (long long base = (long long)blockIdx.x * gpb; base < count; base += (long long)gridDim.x * gpb) {
+        long long slot = base + g;
+        const bool live = slot < count;
+        if (!live) slot = count - 1;         // dead groups shadow the last problem so that __syncwarp stays converged
+        const long long prob = p.redo_list ? p.redo_list[slot] : slot;
+        lqng_generic_body<N>(p, prob, live, smem + (size_t)g * L::total, r, 0xffffffffu);
+        __syncwarp();
     }
 }
 
@@ -288,8 +299,9 @@ static int launch_generic(const LqngParams& p, cudaStream_t stream)
         HK_CUDA(cudaFuncSetAttribute(lqng_generic_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const int blocks = (p.batch + gpb - 1) / gpb;
-    lqng_generic_kernel<N><<<blocks, threads, smem, stream>>>(p);
+    int blocks = (p.batch + gpb - 1) / gpb;
+    if (p.redo_list && blocks > 148) blocks = 148;     // redo mode: grid-stride over the (normally empty) queue
+    count_launch(); lqng_generic_kernel<N><<<blocks, threads, smem, stream>>>(p);
     HK_CUDA(cudaGetLastError());
     return HK_OK;
 }
@@ -358,7 +370,7 @@ int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double*
     double *dA = d, *dB = dA + (size_t)batch * N * 16, *dQ = dB + (size_t)batch * N * 8, *dq = dQ + (size_t)batch * N * n * n,
            *dR = dq + (size_t)batch * N * n, *dx = dR + (size_t)batch * N * 4;
     const long long threads = (long long)batch * N;
-    lqng_assemble_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(batch, N, dt, dx0, dtarget, dtw, dcw, daw, dotgt, dotw,
+    count_launch(); lqng_assemble_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(batch, N, dt, dx0, dtarget, dtw, dcw, daw, dotgt, dotw,
                                                                               dA, dB, dQ, dq, dR, dx);
     HK_CUDA(cudaGetLastError());
     return lqng_launch(batch, N, horizon, 0, dA, dB, dQ, dq, dR, dx, du0, nullptr, nullptr, nullptr, dstatus, stream);
@@ -372,23 +384,17 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
     LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr};
     static const bool force_generic = getenv("HK_LQNG_FORCE_GENERIC") != nullptr;
     if (N == 2 && !time_varying && !dP && !dalpha && !dtraj && !force_generic) {
-        // throughput path: DMMA kernel, then the generic kernel over whatever it queued (normally nothing)
-        ThreadCtx* c = ctx();
-        if (!c) return HK_ERR_NO_DEVICE;
-        const size_t need = sizeof(int) * (4 + (size_t)batch);
-        const bool fresh = need > c->dcap[6];
-        int* scratch = (int*)dscratch(c, 6, need);
-        if (!scratch) return HK_ERR_OUT_OF_MEMORY;
-        if (fresh) { HK_CUDA(cudaMemsetAsync(scratch, 0, 16, stream)); c->launch_id = 0; }
-        int* counter = scratch + (c->launch_id & 1);
-        int* next_counter = scratch + ((c->launch_id + 1) & 1);
-        c->launch_id++;
-        int* list = scratch + 4;
+        // throughput path: one launch of the DMMA kernel (problems it cannot take fall back inside the kernel)
+        static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : 5;   // tuning knob, see DESIGN.md §4
         const int wpb = MMA2_THREADS / 32;
-        lqng_mma2_kernel<<<(batch + wpb - 1) / wpb, MMA2_THREADS, 0, stream>>>(p, list, counter);
+        const unsigned grid = (unsigned)((batch + wpb - 1) / wpb);
+        count_launch();
+        if (minb >= 8) lqng_mma2_kernel<8><<<grid, MMA2_THREADS, 0, stream>>>(p);
+        else if (minb >= 6) lqng_mma2_kernel<6><<<grid, MMA2_THREADS, 0, stream>>>(p);
+        else if (minb == 5) lqng_mma2_kernel<5><<<grid, MMA2_THREADS, 0, stream>>>(p);
+        else lqng_mma2_kernel<4><<<grid, MMA2_THREADS, 0, stream>>>(p);
         HK_CUDA(cudaGetLastError());
-        p.redo_list = list; p.redo_count = counter; p.reset_count = next_counter;
-        return launch_generic<2>(p, stream);
+        return HK_OK;
     }
     switch (N) {
         case 1: return launch_generic<1>(p, stream);

@@ -55,6 +55,7 @@ int         hk_init(int device);                 /* binds the calling process to
 void        hk_shutdown(void);
 const char* hk_last_error(void);                 /* thread-local */
 int         hk_device_count(void);
+long long   hk_kernel_launch_count(void);        /* kernels launched by this library so far (all threads); for benchmarks */
 
 /* ---- LQNG: batched feedback linear-quadratic Nash game ------------------------------------------------------ */
 /*
