@@ -249,21 +249,34 @@ extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizo
     const double* src[7] = {x0, target, tw, cw, aw, otgt, otw};
     size_t per = 0;
     for (int i = 0; i < 7; ++i) per += e[i];
-    double* d = (double*)dscratch(c, 4, ((per + m) * sizeof(double) + sizeof(int)) * (size_t)batch + 64);
-    if (!d) return HK_ERR_OUT_OF_MEMORY;
-    double* dp[7];
-    double* cur = d;
-    for (int i = 0; i < 7; ++i) {
-        dp[i] = cur;
-        if (e[i]) HK_CUDA(cudaMemcpyAsync(cur, src[i], sizeof(double) * e[i] * batch, cudaMemcpyHostToDevice, c->stream));
-        cur += e[i] * batch;
+    // chunked two-stream pipeline: H2D of chunk k+1 overlaps assembly + solve of chunk k and D2H of chunk k-1
+    const int nchunks = batch >= 8192 ? 4 : 1;
+    const int chunk = (batch + nchunks - 1) / nchunks;
+    cudaStream_t streams[2] = {c->stream, c->stream2};
+    double* dbufs[2] = {nullptr, nullptr};
+    for (int k = 0; k < (nchunks > 1 ? 2 : 1); ++k) {
+        dbufs[k] = (double*)dscratch(c, k == 0 ? 4 : 6, ((per + m) * sizeof(double) + sizeof(int)) * (size_t)chunk + 64);
+        if (!dbufs[k]) return HK_ERR_OUT_OF_MEMORY;
     }
-    double* du = cur;
-    int* dst = (int*)(du + (size_t)m * batch);
-    int rc = lqng_assemble_launch(batch, N, horizon, dt, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], du, dst, c->stream);
-    if (rc) return rc;
-    HK_CUDA(cudaMemcpyAsync(u0, du, sizeof(double) * m * batch, cudaMemcpyDeviceToHost, c->stream));
-    if (status) HK_CUDA(cudaMemcpyAsync(status, dst, sizeof(int) * batch, cudaMemcpyDeviceToHost, c->stream));
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int b0 = ci * chunk, nb = (b0 + chunk <= batch) ? chunk : batch - b0;
+        if (nb <= 0) break;
+        cudaStream_t s = streams[ci & 1];
+        double* dp[7];
+        double* cur = dbufs[ci & 1];
+        for (int i = 0; i < 7; ++i) {
+            dp[i] = cur;
+            if (e[i]) HK_CUDA(cudaMemcpyAsync(cur, src[i] + e[i] * b0, sizeof(double) * e[i] * nb, cudaMemcpyHostToDevice, s));
+            cur += e[i] * nb;
+        }
+        double* du = cur;
+        int* dst = (int*)(du + (size_t)m * nb);
+        int rc = lqng_assemble_launch(nb, N, horizon, dt, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], du, dst, s, (ci & 1) ? 7 : 5);
+        if (rc) return rc;
+        HK_CUDA(cudaMemcpyAsync(u0 + (size_t)m * b0, du, sizeof(double) * m * nb, cudaMemcpyDeviceToHost, s));
+        if (status) HK_CUDA(cudaMemcpyAsync(status + b0, dst, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+    }
     HK_CUDA(cudaStreamSynchronize(c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream2));
     return HK_OK;
 }

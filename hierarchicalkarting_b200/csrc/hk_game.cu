@@ -294,27 +294,149 @@ __device__ __forceinline__ int policy_index(const DevGame& g, int cnt, unsigned 
     return idx;
 }
 
+// ---- table-driven ply (same results as legal_moves + select_kth + make_move, see DevGame) ---------------------------------
+struct Tables {
+    const int* dt; const unsigned char* order; const float* load; const float* radius;
+    int nv, nc;
+    __device__ Tables(const DevGame& g)
+        : dt(reinterpret_cast<const int*>(g.tables + g.off_dt)), order(g.tables + g.off_order),
+          load(reinterpret_cast<const float*>(g.tables + g.off_load)), radius(reinterpret_cast<const float*>(g.tables + g.off_radius)),
+          nv(g.nv), nc(g.n_cand) {}
+};
+
+// velocity level of a kart's bucket if it is one of the action buckets (KartDiscreteGame.cs:329-340), else -1 (e.g. the root's (0, b))
+__device__ __forceinline__ int velocity_level(const DevGame& g, int mn, int mx)
+{
+    const int b = g.p.velocityBucketSize, j = (mn - 6) / b;
+    return (mn >= 6 && mn < g.vmax && (mn - 6) == j * b && mx == min(mn + b, g.vmax)) ? j : -1;
+}
+
+// Legal moves of kart np as a bit mask over the RANKS of the pre-sorted candidate list; returns the count.
+__device__ __forceinline__ int fast_legal(const DevGame& g, const Tables& tb, const hk_game_state& st, int np, int lvl,
+                                          unsigned long long& mask, const unsigned char*& ord)
+{
+    const hk_kart_state& cs = st.karts[np];
+    const int sidx = cs.section % g.n_sections, type = g.type_of[sidx], l0 = cs.lane - 1;
+    const int os = (g.sec_flags[st.lastCompletedSection % g.n_sections] >> 2) & 3;                   // KartMCTS.cs:252
+    const float wear = (float)cs.tireAge / 10000.0f;
+    float ms[4];
+#pragma unroll
+    for (int l1 = 0; l1 < 4; ++l1) ms[l1] = max_speed_radius_wear(g.karts[np], __ldg(&tb.radius[type * 16 + l0 * 4 + l1]), wear);   // :357
+    const int maxdl = (g.sec_flags[sidx] & 1) ? g.p.maxLaneChanges - cs.laneChanges : 99;             // :346
+    ord = tb.order + ((((size_t)type * 4 + l0) * tb.nv + lvl) * 3 + os) * tb.nc;
+    mask = 0ull;
+    int cnt = 0;
+    for (int r = 0; r < tb.nc; ++r) {
+        const int gi = __ldg(&ord[r]);
+        if (gi == 255) break;                                                                         // statically infeasible from here on (:368)
+        const int l1 = gi & 3, v = 6 + (gi >> 2) * g.p.velocityBucketSize;
+        const bool ok = abs(l1 - l0) <= maxdl && !(ms[l1] < (float)v);
+        mask |= (unsigned long long)ok << r;
+        cnt += ok;
+    }
+    return cnt;
+}
+
+__device__ __forceinline__ int nth_set_bit(unsigned long long mask, int n)
+{
+    const unsigned lo = (unsigned)mask, hi = (unsigned)(mask >> 32);
+    const int clo = __popc(lo);
+    return n < clo ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - clo + 1);
+}
+
+// applyAction + makeMove bookkeeping from the tables (:127-171, :420-446)
+__device__ __forceinline__ void fast_move(const DevGame& g, const Tables& tb, hk_game_state& st, int np, int lvl, int gi)
+{
+    hk_kart_state& cs = st.karts[np];
+    const int sidx = cs.section % g.n_sections, type = g.type_of[sidx], l0 = cs.lane - 1, l1 = gi & 3, j = gi >> 2;
+    const int b = g.p.velocityBucketSize, v = 6 + j * b;
+    const int dtv = __ldg(&tb.dt[(((size_t)type * 4 + l0) * tb.nv + lvl) * tb.nc + gi]);
+    const float load = __ldg(&tb.load[((size_t)type * 16 + l0 * 4 + l1) * tb.nv + j]);
+    const int last = st.lastCompletedSection;
+    if (g.sec_flags[sidx] & 2) cs.laneChanges = 0; else cs.laneChanges += abs(l1 - l0);
+    cs.tireAge = f2i(((float)cs.tireAge / 10000.0f + load * g.env_karts[0].tireWearFactor) * (float)10000);
+    cs.timeAtSection = (int)((unsigned)cs.timeAtSection + (unsigned)dtv);
+    cs.section += 1; cs.min_velocity = v; cs.max_velocity = min(v + b, g.vmax); cs.lane = l1 + 1; cs.infeasible = 0;
+    bool allAhead = true;
+    for (int i = 0; i < st.n_karts; ++i) allAhead &= st.karts[i].section > last;
+    if (allAhead) st.lastCompletedSection = last + 1;
+}
+
+// One thread per (type, lane, velocity level): time updates of all candidates, then the policy's static sort order for the
+// three possible optimal-lane signs; threads with lvl == 0 also fill the load / radius tables of their (type, lane).
+__global__ void build_tables_kernel(const DevGame* __restrict__ gg, unsigned char* blob)
+{
+    const DevGame& g = *gg;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= g.n_types * 4 * g.nv) return;
+    const int lvl = id % g.nv, l0 = (id / g.nv) % 4, type = id / (g.nv * 4);
+    int* dt = reinterpret_cast<int*>(blob + g.off_dt) + (size_t)id * g.n_cand;
+    unsigned char* order = blob + g.off_order + (size_t)id * 3 * g.n_cand;
+    const int b = g.p.velocityBucketSize, sec0 = g.rep_section[type];
+    hk_kart_state cs{};
+    cs.player = 0; cs.section = sec0; cs.lane = l0 + 1; cs.tireAge = 0;
+    cs.min_velocity = 6 + lvl * b; cs.max_velocity = min(cs.min_velocity + b, g.vmax);
+    unsigned long long keys[3][HK_MAX_ACTIONS];
+    for (int gi = 0; gi < g.n_cand; ++gi) {
+        const hk_action a = hk_action{6 + (gi >> 2) * b, min(6 + (gi >> 2) * b + b, g.vmax), (gi & 3) + 1};
+        const hk_kart_state ap = apply_action(g, cs, a);
+        const int dtv = ap.timeAtSection - cs.timeAtSection;
+        dt[gi] = ap.infeasible ? -1 : dtv;
+        const int dl = abs(a.lane - cs.lane);
+        for (int os = 0; os < 3; ++os)
+            keys[os][gi] = ap.infeasible ? ~0ull
+                : ((unsigned long long)(unsigned)dtv << 22) | ((unsigned long long)(1023 - a.max_velocity) << 12) |
+                  ((unsigned long long)dl << 10) | ((unsigned long long)((os - 1) * a.lane + 4) << 6) | (unsigned long long)gi;
+    }
+    for (int os = 0; os < 3; ++os) {
+        int n_ok = 0;
+        for (int gi = 0; gi < g.n_cand; ++gi) n_ok += keys[os][gi] != ~0ull;
+        for (int r = 0; r < g.n_cand; ++r) order[os * g.n_cand + r] = r < n_ok ? (unsigned char)select_kth(keys[os], g.n_cand, r) : 255;
+    }
+    if (lvl == 0) {
+        float* load = reinterpret_cast<float*>(blob + g.off_load);
+        float* radius = reinterpret_cast<float*>(blob + g.off_radius);
+        const hk_section& cur = g.sections[sec0];
+        for (int l1 = 0; l1 < 4; ++l1) {
+            radius[type * 16 + l0 * 4 + l1] = radius_of_lane(cur, l0 + 1, l1 + 1);
+            for (int j = 0; j < g.nv; ++j)
+                load[((size_t)type * 16 + l0 * 4 + l1) * g.nv + j] = tire_load(cur, (float)min(6 + j * b + b, g.vmax), l0 + 1, l1 + 1);
+        }
+    }
+}
+
 // One playout of KartMCTS.simulate (:238-278). Returns plies played; first_gi = generation index of the first action.
 template <bool TRACE>
 __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long seed, unsigned long long rid, float* scores,
                        int& n_scores, int& first_gi, hk_action* act_out, int* choice_out)
 {
-    unsigned long long keys[HK_MAX_ACTIONS];
+    const Tables tb(g);
     int ply = 0;
     first_gi = -1;
     n_scores = 0;
     for (;;) {
         const int np = up_next(st);
         if (np < 0) return -1;
-        const int cnt = legal_moves(g, st, np, keys);
-        if (is_over(g, st, cnt, np, scores, n_scores)) break;
-        const unsigned u = philox_first(seed, rid, (unsigned)ply);
-        const int index = policy_index(g, cnt, u);
-        const int gi = select_kth(keys, g.n_cand, index);
-        const hk_action a = action_of(g, gi);
+        const int lvl = (g.tables_ok && st.karts[np].player == 0) ? velocity_level(g, st.karts[np].min_velocity, st.karts[np].max_velocity) : -1;
+        int gi, index;
+        if (lvl >= 0) {                                  // table-driven ply
+            unsigned long long mask;
+            const unsigned char* ord;
+            const int cnt = fast_legal(g, tb, st, np, lvl, mask, ord);
+            if (is_over(g, st, cnt, np, scores, n_scores)) break;
+            index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
+            gi = __ldg(&ord[nth_set_bit(mask, index)]);
+            fast_move(g, tb, st, np, lvl, gi);
+        } else {                                         // direct evaluation (e.g. the root's (0, bucket) velocity bucket)
+            unsigned long long keys[HK_MAX_ACTIONS];
+            const int cnt = legal_moves(g, st, np, keys);
+            if (is_over(g, st, cnt, np, scores, n_scores)) break;
+            index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
+            gi = select_kth(keys, g.n_cand, index);
+            make_move(g, st, np, action_of(g, gi));
+        }
         if (ply == 0) first_gi = gi;
-        if (TRACE && ply < HK_MAX_PLIES) { act_out[ply] = a; choice_out[ply] = index; }
-        make_move(g, st, np, a);
+        if (TRACE && ply < HK_MAX_PLIES) { act_out[ply] = action_of(g, gi); choice_out[ply] = index; }
         ++ply;
     }
     return ply;
@@ -523,9 +645,41 @@ extern "C" int hk_game_create(const hk_section* sections, int n_sections, const 
     d.n_cand = nv * 4;
     if (d.n_cand > HK_MAX_ACTIONS) { delete g; set_error("hk_game_create: more than %d candidate actions", HK_MAX_ACTIONS); return HK_ERR_INVALID_ARGUMENT; }
     for (int c = 1; c <= HK_MAX_ACTIONS; ++c) policy_cdf_host(c, d.cdf[c]);
+    // geometry types, per-section flags and the table layout; the tables themselves are filled on the device
+    d.nv = nv; d.n_types = 0; d.tables_ok = 1;
+    for (int s = 0; s < n_sections; ++s) {
+        int t = -1;
+        for (int k = 0; k < d.n_types && t < 0; ++k) {
+            const hk_section& r = sections[d.rep_section[k]];
+            if (r.insideR == sections[s].insideR && r.length == sections[s].length && r.width == sections[s].width &&
+                r.turnDeg == sections[s].turnDeg && (r.leftTurn != 0) == (sections[s].leftTurn != 0)) t = k;
+        }
+        if (t < 0) {
+            if (d.n_types == HK_MAX_TYPES) { d.tables_ok = 0; t = 0; }
+            else { t = d.n_types; d.rep_section[d.n_types++] = (unsigned char)s; }
+        }
+        d.type_of[s] = (unsigned char)t;
+        const bool st0 = sections[s].insideR == 0.0f, st1 = sections[(s + 1) % n_sections].insideR == 0.0f;
+        const int sign = sections[s].optimalLane == 1 ? 1 : (sections[s].optimalLane == 4 ? -1 : 0);
+        d.sec_flags[s] = (unsigned char)((st0 ? 1 : 0) | ((st0 != st1) ? 2 : 0) | ((sign + 1) << 2));
+    }
+    const size_t cells = (size_t)d.n_types * 4 * nv;
+    d.off_dt = 0;
+    d.off_order = (int)(cells * d.n_cand * 4);
+    d.off_load = (int)((d.off_order + cells * 3 * d.n_cand + 15) & ~(size_t)15);
+    d.off_radius = d.off_load + (int)((size_t)d.n_types * 16 * nv * 4);
+    d.table_bytes = d.off_radius + d.n_types * 16 * 4;
+    unsigned char* blob = nullptr;
     cudaError_t e = cudaMalloc(&g->dev, sizeof(DevGame));
+    if (e == cudaSuccess) e = cudaMalloc(&blob, d.table_bytes);
+    d.tables = blob;
     if (e == cudaSuccess) e = cudaMemcpy(g->dev, &g->host, sizeof(DevGame), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { set_error("hk_game_create: %s", cudaGetErrorString(e)); if (g->dev) cudaFree(g->dev); delete g; return HK_ERR_CUDA; }
+    if (e == cudaSuccess && d.tables_ok) {
+        count_launch(); build_tables_kernel<<<(unsigned)((cells + 63) / 64), 64>>>(g->dev, blob);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) { set_error("hk_game_create: %s", cudaGetErrorString(e)); if (g->dev) cudaFree(g->dev); if (blob) cudaFree(blob); delete g; return HK_ERR_CUDA; }
     *out = g;
     return HK_OK;
 }
@@ -534,6 +688,7 @@ extern "C" void hk_game_destroy(hk_game* g)
 {
     if (!g) return;
     if (g->dev) cudaFree(g->dev);
+    if (g->host.tables) cudaFree(const_cast<unsigned char*>(g->host.tables));
     delete g;
 }
 

@@ -4,6 +4,7 @@
 
 #define HK_MAX_SECTIONS 64
 #define HK_MAX_ENV_KARTS 16
+#define HK_MAX_TYPES 24
 
 namespace hk {
 
@@ -17,6 +18,17 @@ struct DevGame {
     hk_kart env_karts[HK_MAX_ENV_KARTS];        // envController.Agents[player].m_Kart constants
     hk_section sections[HK_MAX_SECTIONS];
     uint32_t cdf[HK_MAX_ACTIONS + 1][HK_MAX_ACTIONS];   // rollout-policy index distribution per legal-move count
+    // ---- transition tables (built on the device by build_tables_kernel at hk_game_create) -------------------------------
+    // The time update of applyAction is a pure function of (section geometry, lane, velocity bucket, action) because the
+    // reference evaluates computeTOC with tyre wear 0 (quirk B.6-3), so it — and with it the static part of the rollout
+    // policy's sort order — is tabulated per geometry TYPE; tyre load per (type, lane pair, max_velocity) likewise.
+    int tables_ok;                              // 0: more than HK_MAX_TYPES geometries -> kernels use the direct path only
+    int n_types, nv;                            // geometry types; velocity levels (n_cand = 4 nv)
+    int off_dt, off_order, off_load, off_radius, table_bytes;   // byte offsets into `tables`
+    unsigned char type_of[HK_MAX_SECTIONS];     // section -> type
+    unsigned char rep_section[HK_MAX_TYPES];    // a section of that type
+    unsigned char sec_flags[HK_MAX_SECTIONS];   // bit0 straight(s), bit1 straight(s) != straight(s+1), bits 2-3 optimalLaneSign + 1
+    const unsigned char* tables;                // device blob: dt int32[T][4][nv][nc] | order u8[T][4][nv][3][nc] | load f32[T][16][nv] | radius f32[T][16]
 };
 static_assert(sizeof(DevGame) % 4 == 0, "DevGame is copied word-wise");
 

@@ -359,13 +359,13 @@ __global__ void lqng_assemble_kernel(int batch, int N, double dt, const double* 
 
 int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double* dx0, const double* dtarget,
                          const double* dtw, const double* dcw, const double* daw, const double* dotgt, const double* dotw,
-                         double* du0, int* dstatus, cudaStream_t stream)
+                         double* du0, int* dstatus, cudaStream_t stream, int scratch_slot)
 {
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
     const int n = 4 * N;
     const size_t per = (size_t)N * 16 + N * 8 + (size_t)N * n * n + (size_t)N * n + N * 4 + n;
-    double* d = (double*)dscratch(c, 5, per * sizeof(double) * (size_t)batch);
+    double* d = (double*)dscratch(c, scratch_slot, per * sizeof(double) * (size_t)batch);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
     double *dA = d, *dB = dA + (size_t)batch * N * 16, *dQ = dB + (size_t)batch * N * 8, *dq = dQ + (size_t)batch * N * n * n,
            *dR = dq + (size_t)batch * N * n, *dx = dR + (size_t)batch * N * 4;

@@ -58,6 +58,7 @@ __device__ __forceinline__ bool bad_pivot(double a)                 // zero, den
 }
 
 constexpr int MMA2_THREADS = 128;
+constexpr int MMA2_PREFETCH_DISTANCE = 4096;                       // problems; > resident warps per GPU (148 SMs x 20)
 
 template <int MINB>                                             // resident CTAs per SM the register allocation is sized for
 __global__ void __launch_bounds__(MMA2_THREADS, MINB) lqng_mma2_kernel(LqngParams p)
@@ -73,6 +74,17 @@ __global__ void __launch_bounds__(MMA2_THREADS, MINB) lqng_mma2_kernel(LqngParam
     const double* gq = p.q + (size_t)prob * 16;
     const double* gR = p.R + (size_t)prob * 8;
     const double* gx = p.x0 + (size_t)prob * 8;
+    {   // L2 prefetch of the record a later warp will need (14 lines of 128 B): turns its HBM latency into L2 latency
+        const long long pf = prob + MMA2_PREFETCH_DISTANCE;
+        if (pf < p.batch && lane < 14) {
+            const double* a = lane < 8 ? p.Q + (size_t)pf * 128 + lane * 16
+                            : lane < 10 ? p.A + (size_t)pf * 32 + (lane - 8) * 16
+                            : lane == 10 ? p.B + (size_t)pf * 16
+                            : lane == 11 ? p.q + (size_t)pf * 16
+                            : lane == 12 ? p.R + (size_t)pf * 8 : p.x0 + (size_t)pf * 8;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+    }
 
     // ---- per-lane constants --------------------------------------------------------------------------------------
     const int pl = t >> 1;                                          // player owning joint rows 2t, 2t+1 (and control row t)
@@ -162,7 +174,7 @@ __global__ void __launch_bounds__(MMA2_THREADS, MINB) lqng_mma2_kernel(LqngParam
             const double c = shfl_d(mine, 4 * ((g & 1) + 2 * kk) + rowhi);                // LHS[rho][k] of this lane's row
             const int srcR = aug_lane ? 4 * k + 2 : 4 * ((k & 1) + 2 * (g >> 1)) + (k >> 1);
             const double r0 = shfl_d(M0, srcR), r1 = shfl_d(M1, srcR);                    // pivot row k, this lane's column(s)
-            const double pv = shfl_d(c, 4 * (k & 1) + (k >> 1));                          // LHS[k][k]
+            const double pv = shfl_d(mine, 4 * ((k & 1) + 2 * kk) + (k >> 1));            // LHS[k][k], straight from its owner
             redo |= (below[k] & abs_gt(c, pv)) | bad_pivot(pv);                           // partial pivoting would swap rows
             const double pinv = rcp_fast(pv);
             const bool prow = rho == k;
@@ -210,8 +222,9 @@ __global__ void __launch_bounds__(MMA2_THREADS, MINB) lqng_mma2_kernel(LqngParam
             dmma(z10, z11, pl == 1 ? pc : 0.0, rpc);
             mm(z10, z11, f0, f1, yt0, yt1);
         }
-        // W for the next step, with beta^T in row 4+i so that row 4+i of the result is (Z_i^{new} beta)^T   (quirk Q2)
-        w0 = 0.0; w1 = 0.0;
+        // W for the next step, with beta^T in row 4+i so that row 4+i of the result is (Z_i^{new} beta)^T (quirk Q2);
+        // rows 4, 5 start from eta_i, so they come out as eta_i + Z_i^{new} beta, the vector F^T is applied to below
+        w0 = vec_lane ? e0 : 0.0; w1 = vec_lane ? e1 : 0.0;
         mm(w0, w1, g == 4 ? be0 : xb00, g == 4 ? be1 : xb01, z00, z01);
         mm(w0, w1, g == 5 ? be0 : xb10, g == 5 ? be1 : xb11, z10, z11);
         // eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)   (:117)
@@ -219,7 +232,7 @@ __global__ void __launch_bounds__(MMA2_THREADS, MINB) lqng_mma2_kernel(LqngParam
             const double ra = fma(rr1, ao, rr0 * ae);               // (R_i alpha_i)[t&1] at lanes (4+i, 2i + (t&1))
             double n0 = qv.x, n1 = qv.y;
             dmma(n0, n1, (vec_lane && pl == vp) ? ra : 0.0, pc);
-            mm(n0, n1, vec_lane ? e0 + w0 : 0.0, vec_lane ? e1 + w1 : 0.0, f0, f1);
+            mm(n0, n1, vec_lane ? w0 : 0.0, vec_lane ? w1 : 0.0, f0, f1);
             e0 = n0; e1 = n1;
         }
     }
