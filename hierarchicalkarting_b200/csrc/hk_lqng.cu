@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
 
 }  // namespace hk
 #include "hk_lqng_mma.cuh"
+#include "hk_lqng_mma2p.cuh"
 namespace hk {
 
 template <int N>
@@ -384,7 +385,29 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
     LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr};
     static const bool force_generic = getenv("HK_LQNG_FORCE_GENERIC") != nullptr;
     if (N == 2 && !time_varying && !dP && !dalpha && !dtraj && !force_generic) {
-        // throughput path: one launch of the DMMA kernel (problems it cannot take fall back inside the kernel)
+        // throughput path: one launch of a DMMA kernel (problems it cannot take fall back inside the kernel)
+        static const int variant = getenv("HK_MMA2_VARIANT") ? atoi(getenv("HK_MMA2_VARIANT")) : 1;   // 0: one CTA per 4 problems, 1: persistent + TMA
+        const bool aligned = ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dQ) |
+                               reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dR) | reinterpret_cast<uintptr_t>(dx0)) & 15) == 0;
+        if (variant == 1 && aligned) {                                 // cp.async.bulk needs 16-byte aligned sources
+            static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : 5;
+            auto kern = minb >= 8 ? lqng_mma2p_kernel<8> : minb == 7 ? lqng_mma2p_kernel<7> : minb == 6 ? lqng_mma2p_kernel<6>
+                        : minb == 5 ? lqng_mma2p_kernel<5> : lqng_mma2p_kernel<4>;
+            static int resident = 0;                                   // persistent grid: SMs x resident CTAs
+            if (!resident) {
+                int dev = 0, sms = 0, occ = 0;
+                HK_CUDA(cudaGetDevice(&dev));
+                HK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                HK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P2_THREADS, 0));
+                resident = sms * (occ > 0 ? occ : 1);
+            }
+            const long long want = ((long long)batch + P2_WARPS - 1) / P2_WARPS;
+            const unsigned grid = (unsigned)(want < resident ? want : resident);
+            count_launch();
+            kern<<<grid, P2_THREADS, 0, stream>>>(p);
+            HK_CUDA(cudaGetLastError());
+            return HK_OK;
+        }
         static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : 5;   // tuning knob, see DESIGN.md §4
         const int wpb = MMA2_THREADS / 32;
         const unsigned grid = (unsigned)((batch + wpb - 1) / wpb);

@@ -1,0 +1,262 @@
+// hk_lqng_mma2p.cuh — persistent, TMA-staged version of the warp-per-problem FP64 tensor-core kernel for the
+// time-invariant 2-kart LQNG (n = 8, m = 4): the BASELINE headline configuration.
+// Same algorithm as KartLQR.solveFeedbackLQR (reference: Assets/Karting/Scripts/AI/LQR/KartLQR.cs:64-127) and the same
+// DMMA fragment algebra as hk_lqng_mma.cuh (read its header first).  What changes:
+//   * persistent warps: grid = SMs x resident CTAs, every warp strides over the batch, so the ~25 per-lane layout
+//     constants (fragment ownership, shuffle sources, operand offsets) are computed once per warp, not once per problem;
+//   * TMA staging: one elected lane issues six cp.async.bulk copies (Q 1024 B, A 256 B, B 128 B, q 128 B, R 64 B,
+//     x0 64 B = the problem's whole 1,664 B record) into a per-warp, double-buffered shared-memory record that completes
+//     on an mbarrier, one problem ahead of the one being solved: HBM latency is off the critical path and every operand
+//     read is a conflict-free LDS.  Zero-padding of fragment operands is done by pointing a lane at a constant tail
+//     ([0 0 0 0 0 1 1 0]) instead of select instructions; Q_i / q_i are re-read from the record each step instead of
+//     being pinned in registers;
+//   * the coupled 4x4 system [LHS | I | RHSVec] is reduced by fraction-free Gauss-Jordan (rows are rescaled by the pivot
+//     instead of divided by it): the identity block lives in the otherwise unused rows 6,7 of the L fragment, there is
+//     no placement select and no reciprocal on the pivot chain — one reciprocal per row, all rows in parallel, at the
+//     end.  All rows carry the same cumulative scale, so the test "partial pivoting (MathNet LU, KartLQR.cs:104-105)
+//     would not exchange rows" stays a plain magnitude comparison, done on the high words in the integer pipe.
+// Problems that need row exchanges, have non-symmetric Q_i/R_i or an out-of-range pivot are solved by the pivoting
+// algorithm (lqng_generic_body) in the same launch.
+#pragma once
+
+namespace hk {
+
+constexpr int P2_WARPS = 4;
+constexpr int P2_THREADS = 32 * P2_WARPS;
+constexpr int P2_oQ = 0, P2_oA = 128, P2_oB = 160, P2_oq = 176, P2_oR = 192, P2_ox = 200, P2_oC = 208;   // doubles
+constexpr int P2_STRIDE = 216;                  // record + constant tail, 1,728 B
+constexpr unsigned P2_TX_BYTES = 1664;
+
+struct P2Smem {
+    double rec[P2_WARPS][2][P2_STRIDE];
+    double fallback[GenericLayout<2>::total];    // one pivoting scratch per CTA, serialised by `lock` (rare path)
+    unsigned long long bar[P2_WARPS][2];
+    int lock;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tHK_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra HK_DONE;\n\tbra HK_WAIT;\n\tHK_DONE:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ unsigned abs_hi(double a) { return (unsigned)__double2hiint(a) & 0x7fffffffu; }
+__device__ __forceinline__ bool bits_differ(double a, double b)
+{
+    return ((__double2hiint(a) ^ __double2hiint(b)) | (__double2loint(a) ^ __double2loint(b))) != 0;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(P2_THREADS, MINB) lqng_mma2p_kernel(LqngParams p)
+{
+    __shared__ __align__(128) P2Smem sm;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long long nwarps = (long long)gridDim.x * P2_WARPS;
+    const long long first = (long long)wib * gridDim.x + blockIdx.x;      // leftovers of the last round spread over all SMs
+    const unsigned bar_u32 = smem_u32(&sm.bar[wib][0]);
+    const unsigned rec_u32 = smem_u32(&sm.rec[wib][0][0]);
+    if (threadIdx.x == 0) sm.lock = 0;
+    if (lane < 16) sm.rec[wib][lane >> 3][P2_oC + (lane & 7)] = ((lane & 7) == 5 || (lane & 7) == 6) ? 1.0 : 0.0;
+    if (lane == 0) {
+        mbar_init(bar_u32, 1);
+        mbar_init(bar_u32 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (first >= p.batch) return;                                    // whole warps only; no block-wide sync below
+
+    auto issue = [&](long long prob, int b) {                         // lane 0 only
+        const unsigned bar = bar_u32 + 8u * b, dst = rec_u32 + (unsigned)(b * P2_STRIDE * 8);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of this buffer come first
+        mbar_expect_tx(bar, P2_TX_BYTES);
+        bulk_g2s(dst + P2_oQ * 8, p.Q + (size_t)prob * 128, 1024, bar);
+        bulk_g2s(dst + P2_oA * 8, p.A + (size_t)prob * 32, 256, bar);
+        bulk_g2s(dst + P2_oB * 8, p.B + (size_t)prob * 16, 128, bar);
+        bulk_g2s(dst + P2_oq * 8, p.q + (size_t)prob * 16, 128, bar);
+        bulk_g2s(dst + P2_oR * 8, p.R + (size_t)prob * 8, 64, bar);
+        bulk_g2s(dst + P2_ox * 8, p.x0 + (size_t)prob * 8, 64, bar);
+    };
+    if (lane == 0) issue(first, 0);
+
+    // ---- per-lane layout constants (once per warp) ------------------------------------------------------------------------
+    const int pl = t >> 1;                                          // player owning joint rows 2t, 2t+1 (and control row t)
+    const int lr = (2 * t) & 3;                                     // local row of joint row 2t inside A_pl / B_pl
+    const bool a_on = pl == (g >> 2);
+    const int offA = a_on ? P2_oA + pl * 16 + lr * 4 + (g & 3) : P2_oC;          // joint A, T-form: A[2t][g]; A[2t+1][g] at +4
+    const bool b_on = g < 4 && pl == (g >> 1);
+    const int offB = b_on ? P2_oB + pl * 8 + lr * 2 + (g & 1) : P2_oC;           // joint B (8x4), T-form; next row at +2
+    const int offXb0 = (b_on && g < 2) ? offB : P2_oC;                           // rows 0,1 of the W operand: B_0^T
+    const int offXb1 = (b_on && g >= 2) ? offB : P2_oC;                          // rows 2,3: B_1^T
+    const int offBF = P2_oB + pl * 8 + lr * 2;                                   // B rows 2t, 2t+1 x own player's controls
+    const int offAx = P2_oA + pl * 16 + lr * 4;
+    const int offRr = P2_oR + pl * 4 + (t & 1) * 2;                              // R_pl row t&1
+    const bool isL = g < 4 && t < 2, isI = g >= 6, isAug = g < 4 && t == 2;
+    // coupled system, lane ownership: L lanes hold LHS[rho][2kap..2kap+1] exactly where the D fragment of L = W B leaves
+    // them under the reference's block placement (quirk Q1, KartLQR.cs:68-87); I lanes (rows 6,7 of the same fragment)
+    // hold the identity block; Aug lanes hold RHSVec[rho].
+    const int rho = isL ? 2 * t + (g & 1) : isI ? 2 * (t & 1) + (g & 1) : isAug ? g : 0;
+    const int kap = isL ? (g >> 1) : isI ? (t >> 1) : 0;
+    const int offRl = (isL && t == (g >> 1)) ? P2_oR + (g >> 1) * 4 + (g & 1) * 2
+                      : isI ? (rho == 2 * kap ? P2_oC + 6 : rho == 2 * kap + 1 ? P2_oC + 4 : P2_oC) : P2_oC;
+    const bool vec = (g >> 1) == 2;                                 // quads 4 and 5 carry the vectors of player g-4
+    const int vp = g & 1;
+    const int offQv = vec ? P2_oq + vp * 8 + 2 * t : P2_oC;
+    const int rho_chk = isL ? rho : -1;
+    const int csrc = 4 * (rho & 1) + (rho >> 1);                    // + 8 (k>>1): L lane holding LHS[rho][k]
+    const int rb = isL ? 8 * kap : isI ? 24 + 2 * kap : 2;          // row k, this lane's columns: rb + 4 (k&1) + (k>>1) [+ 7 (k>>1) on Aug lanes]
+    const int rb2 = rb + 1 + (isAug ? 7 : 0);
+    const int dsrc = csrc + 8 * (rho >> 1);                         // L lane holding the diagonal of row rho
+    const int srcRv = 4 * (4 + ((g >> 1) & 1)) + ((g >> 1) & 1);    // RHSVec of player g>>1 sits in lane (4 + (g>>1), t = g>>1)
+    const int s_of_g = ((g >> 2) << 1) | (g & 1);
+    const int srcLam = 4 * (6 + (s_of_g & 1)) + (s_of_g >> 1) + 2 * (t & 1);   // I lane holding Lambda[s(g)][2t..2t+1]
+    const int srcAe = 8 * pl + 2, srcAo = 8 * pl + 6;
+    const bool ylane = t < 2, podd = t & 1, godd = g & 1, rodd = rho & 1;
+
+    int it = 0;
+    for (long long prob = first; prob < p.batch; prob += nwarps, ++it) {
+        const int buf = it & 1;
+        const double* rec = &sm.rec[wib][buf][0];
+        __syncwarp();                                               // every lane is done with the other buffer
+        if (lane == 0 && prob + nwarps < p.batch) issue(prob + nwarps, buf ^ 1);
+        mbar_wait(bar_u32 + 8u * buf, (unsigned)(it >> 1) & 1u);
+
+        // ---- operands of this problem -----------------------------------------------------------------------------------
+        const double aT0 = rec[offA], aT1 = rec[offA + 4];
+        const double xb00 = rec[offXb0], xb01 = rec[offXb0 + 2], xb10 = rec[offXb1], xb11 = rec[offXb1 + 2];
+        const double2 bFa = *reinterpret_cast<const double2*>(rec + offBF), bFb = *reinterpret_cast<const double2*>(rec + offBF + 2);
+        const double2 rr = *reinterpret_cast<const double2*>(rec + offRr);
+        const double2 rl = *reinterpret_cast<const double2*>(rec + offRl);
+        double yL0, yL1;                                            // [B | A x0 | 0 0 0] in T-form
+        {
+            const double2 a0 = *reinterpret_cast<const double2*>(rec + offAx), a1 = *reinterpret_cast<const double2*>(rec + offAx + 2);
+            const double2 a2 = *reinterpret_cast<const double2*>(rec + offAx + 4), a3 = *reinterpret_cast<const double2*>(rec + offAx + 6);
+            const double2 xa = *reinterpret_cast<const double2*>(rec + P2_ox + 4 * pl), xc = *reinterpret_cast<const double2*>(rec + P2_ox + 4 * pl + 2);
+            const double ax0 = fma(a1.y, xc.y, fma(a1.x, xc.x, fma(a0.y, xa.y, a0.x * xa.x)));
+            const double ax1 = fma(a3.y, xc.y, fma(a3.x, xc.x, fma(a2.y, xa.y, a2.x * xa.x)));
+            yL0 = g == 4 ? ax0 : rec[offB];
+            yL1 = g == 4 ? ax1 : rec[offB + 2];
+        }
+        double z00, z01, z10, z11, e0, e1;
+        bool redo;
+        {
+            const double2 q0 = *reinterpret_cast<const double2*>(rec + P2_oQ + 2 * lane);          // Z_i = Q_i (KartLQR.cs:62), R-form
+            const double2 q1 = *reinterpret_cast<const double2*>(rec + P2_oQ + 64 + 2 * lane);
+            const double2 qv = *reinterpret_cast<const double2*>(rec + offQv);                      // eta_i = q_i (:63), lanes (4+i, t)
+            z00 = q0.x; z01 = q0.y; z10 = q1.x; z11 = q1.y; e0 = qv.x; e1 = qv.y;
+            // symmetry of Q_i and R_i is what lets Z_i's R-form stand in for its T-form
+            redo = bits_differ(rec[(2 * t) * 8 + g], q0.x) | bits_differ(rec[(2 * t + 1) * 8 + g], q0.y) |
+                   bits_differ(rec[64 + (2 * t) * 8 + g], q1.x) | bits_differ(rec[64 + (2 * t + 1) * 8 + g], q1.y) |
+                   bits_differ(rec[P2_oR + 1], rec[P2_oR + 2]) | bits_differ(rec[P2_oR + 5], rec[P2_oR + 6]);
+        }
+        // W: rows 0..3 = stacked B_i^T Z_i, rows 4+i = eta_i (+ Z_i beta from the second step on)
+        double w0 = e0, w1 = e1;
+        mm(w0, w1, xb00, xb01, z00, z01);
+        mm(w0, w1, xb10, xb11, z10, z11);
+        double u_out = 0.0;
+
+        for (int step = p.horizon; step >= 0; --step) {             // KartLQR.cs:64
+            const bool last = step == 0;
+            // L = W [B | A x0] with eta^T B in rows 4, 5 (RHSVec, :96), + R_i on the diagonal blocks (:78), identity in rows 6, 7
+            double l0 = rl.x, l1 = rl.y;
+            mm(l0, l1, g < 4 ? w0 : e0, g < 4 ? w1 : e1, yL0, yL1);
+            // RM^T = A^T W^T (RHSMat, :89-95); not needed at t = 0, where only u0 = -LHS^-1 (RM x0 + rv) is
+            double m0 = 0.0, m1 = 0.0;
+            if (!last) mm(m0, m1, aT0, aT1, w0, w1);
+            double M0 = l0, M1 = l1;
+            {
+                const double v0 = shfl_d(l0, srcRv), v1 = shfl_d(l1, srcRv);
+                double rv = godd ? v1 : v0;
+                if (last) rv += l0;                                 // l0 of an Aug lane = (RM x0)[rho]
+                if (isAug) M0 = rv;
+            }
+            // fraction-free Gauss-Jordan: row_i <- pv row_i - LHS[i][k] row_k (the pivot row is only rescaled)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double mine = (k & 1) ? M1 : M0;
+                const double c = shfl_d(mine, csrc + 8 * (k >> 1));
+                const int rs = (k >> 1 ? rb2 : rb) + 4 * (k & 1);
+                const double r0 = shfl_d(M0, rs), r1 = shfl_d(M1, rs);
+                const double pv = shfl_d(mine, 8 * (k >> 1) + 4 * (k & 1) + (k >> 1));
+                const unsigned hp = abs_hi(pv);
+                redo |= ((rho_chk > k) & (abs_hi(c) > hp)) | ((hp - 0x33700000u) > 0x19000000u);   // |pv| outside 2^-200 .. 2^200
+                const double cz = rho == k ? 0.0 : c;
+                M0 = fma(pv, M0, -(cz * r0));
+                M1 = fma(pv, M1, -(cz * r1));
+            }
+            {
+                const double d = shfl_d(rodd ? M1 : M0, dsrc);
+                const double rinv = rcp_fast(d);
+                M0 *= rinv; M1 *= rinv;
+            }
+            if (last) {                                             // optimal_control = -P x0 - alpha with the t = 0 gains (:121-126)
+                u_out = -M0;
+                break;
+            }
+            const double ae = shfl_d(M0, srcAe), ao = shfl_d(M0, srcAo);           // alpha of player t>>1
+            double y0 = shfl_d(M0, srcLam), y1 = shfl_d(M1, srcLam);              // Lambda as B operand: Y[k][col] = Lambda[s(col)][k]
+            y0 = ylane ? y0 : 0.0; y1 = ylane ? y1 : 0.0;
+            double pe = 0.0, po = 0.0;                              // (P[2(t>>1)][g], P[2(t>>1)+1][g])   (:104-105)
+            mm(pe, po, m0, m1, y0, y1);
+            const double pc = podd ? po : pe;                       // compact P: P[t][g]
+            // F = A - B P (T-form), beta = -B alpha   (:110-111)
+            const double f0 = fma(-bFa.y, po, fma(-bFa.x, pe, aT0));
+            const double f1 = fma(-bFb.y, po, fma(-bFb.x, pe, aT1));
+            const double be0 = fma(-bFa.y, ao, -bFa.x * ae);
+            const double be1 = fma(-bFb.y, ao, -bFb.x * ae);
+            const double rpc = fma(rr.y, po, rr.x * pe);            // (R_p P_p)[t&1][g]
+            // Z_i <- Q_i + P_i^T R_i P_i + F^T (Z_i F)   (:116)
+            {
+                double ya0 = 0.0, ya1 = 0.0, yb0 = 0.0, yb1 = 0.0;
+                mm(ya0, ya1, f0, f1, z00, z01);
+                mm(yb0, yb1, f0, f1, z10, z11);
+                const double2 q0 = *reinterpret_cast<const double2*>(rec + P2_oQ + 2 * lane);
+                const double2 q1 = *reinterpret_cast<const double2*>(rec + P2_oQ + 64 + 2 * lane);
+                z00 = q0.x; z01 = q0.y; z10 = q1.x; z11 = q1.y;
+                dmma(z00, z01, pl == 0 ? pc : 0.0, rpc);
+                dmma(z10, z11, pl == 1 ? pc : 0.0, rpc);
+                mm(z00, z01, f0, f1, ya0, ya1);
+                mm(z10, z11, f0, f1, yb0, yb1);
+            }
+            // W for the next step, beta^T in row 4+i: row 4+i comes out as eta_i + Z_i^{new} beta (quirk Q2)
+            w0 = e0; w1 = e1;
+            mm(w0, w1, g == 4 ? be0 : xb00, g == 4 ? be1 : xb01, z00, z01);
+            mm(w0, w1, g == 5 ? be0 : xb10, g == 5 ? be1 : xb11, z10, z11);
+            // eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)   (:117)
+            {
+                const double ra = fma(rr.y, ao, rr.x * ae);         // (R_i alpha_i)[t&1]
+                const double2 qv = *reinterpret_cast<const double2*>(rec + offQv);
+                double n0 = qv.x, n1 = qv.y;
+                dmma(n0, n1, (vec && pl == vp) ? ra : 0.0, pc);
+                mm(n0, n1, vec ? w0 : 0.0, vec ? w1 : 0.0, f0, f1);
+                e0 = n0; e1 = n1;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, redo)) {
+            // Warp-uniform and rare: row exchanges needed, non-symmetric Q/R or an out-of-range pivot.
+            if (lane == 0) while (atomicCAS(&sm.lock, 0, 1) != 0) {}
+            __syncwarp();
+            if (lane < 8) lqng_generic_body<2>(p, prob, true, sm.fallback, lane, 0xffu);
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); atomicExch(&sm.lock, 0); }
+            continue;
+        }
+        if (isAug) p.u0[(size_t)prob * 4 + g] = u_out;
+        if (lane == 0 && p.status) p.status[prob] = 0;
+    }
+}
+
+}  // namespace hk
