@@ -386,25 +386,36 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
     static const bool force_generic = getenv("HK_LQNG_FORCE_GENERIC") != nullptr;
     if (N == 2 && !time_varying && !dP && !dalpha && !dtraj && !force_generic) {
         // throughput path: one launch of a DMMA kernel (problems it cannot take fall back inside the kernel)
-        static const int variant = getenv("HK_MMA2_VARIANT") ? atoi(getenv("HK_MMA2_VARIANT")) : 1;   // 0: one CTA per 4 problems, 1: persistent + TMA
+        static const int variant = getenv("HK_MMA2_VARIANT") ? atoi(getenv("HK_MMA2_VARIANT")) : 2;   // 0: one CTA per 4 problems; 1, 2: persistent + TMA
         const bool aligned = ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dQ) |
                                reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dR) | reinterpret_cast<uintptr_t>(dx0)) & 15) == 0;
-        if (variant == 1 && aligned) {                                 // cp.async.bulk needs 16-byte aligned sources
-            static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : 5;
-            auto kern = minb >= 8 ? lqng_mma2p_kernel<8> : minb == 7 ? lqng_mma2p_kernel<7> : minb == 6 ? lqng_mma2p_kernel<6>
-                        : minb == 5 ? lqng_mma2p_kernel<5> : lqng_mma2p_kernel<4>;
+        if (variant >= 1 && aligned) {                                 // cp.async.bulk needs 16-byte aligned sources
+            // variant 1: 4 warps per CTA, MINB resident CTAs per SM; variant 2 (default): one warp per CTA, MINB resident warps
+            // per SM.  16 warps x 128 registers is the measured optimum (profiles/lqng_mma2_tuning_r01.md).
+            static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : (variant == 2 ? 16 : 4);
+            static const int warps = variant == 2 ? 1 : 4;
+            void (*kern)(LqngParams) = nullptr;
+            if (variant == 2) {
+                kern = minb >= 32 ? lqng_mma2p_kernel<32, 1> : minb >= 24 ? lqng_mma2p_kernel<24, 1> : minb >= 20 ? lqng_mma2p_kernel<20, 1>
+                       : minb >= 16 ? lqng_mma2p_kernel<16, 1> : lqng_mma2p_kernel<12, 1>;
+            } else {
+                kern = minb >= 8 ? lqng_mma2p_kernel<8, 4> : minb >= 6 ? lqng_mma2p_kernel<6, 4> : minb == 5 ? lqng_mma2p_kernel<5, 4>
+                       : lqng_mma2p_kernel<4, 4>;
+            }
             static int resident = 0;                                   // persistent grid: SMs x resident CTAs
+            static const int pad = getenv("HK_MMA2_PAD_SMEM") ? atoi(getenv("HK_MMA2_PAD_SMEM")) : 0;   // occupancy experiments only
             if (!resident) {
                 int dev = 0, sms = 0, occ = 0;
                 HK_CUDA(cudaGetDevice(&dev));
                 HK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-                HK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P2_THREADS, 0));
+                if (pad) HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+                HK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * warps, pad));
                 resident = sms * (occ > 0 ? occ : 1);
             }
-            const long long want = ((long long)batch + P2_WARPS - 1) / P2_WARPS;
+            const long long want = ((long long)batch + warps - 1) / warps;
             const unsigned grid = (unsigned)(want < resident ? want : resident);
             count_launch();
-            kern<<<grid, P2_THREADS, 0, stream>>>(p);
+            kern<<<grid, 32 * warps, pad, stream>>>(p);
             HK_CUDA(cudaGetLastError());
             return HK_OK;
         }

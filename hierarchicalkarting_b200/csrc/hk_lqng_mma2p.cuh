@@ -15,22 +15,25 @@
 //     no placement select and no reciprocal on the pivot chain — one reciprocal per row, all rows in parallel, at the
 //     end.  All rows carry the same cumulative scale, so the test "partial pivoting (MathNet LU, KartLQR.cs:104-105)
 //     would not exchange rows" stays a plain magnitude comparison, done on the high words in the integer pipe.
-// Problems that need row exchanges, have non-symmetric Q_i/R_i or an out-of-range pivot are solved by the pivoting
-// algorithm (lqng_generic_body) in the same launch.
+// A problem whose coupled system needs row exchanges is solved a second time by the same warp with `pivot` set: the 4x4
+// system [LHS | I | RHSVec] is then dealt one column per lane and reduced by Gauss-Jordan with partial pivoting (same
+// pivot choice as MathNet's LU: first largest magnitude at or below the diagonal), everything else (all DMMA products)
+// is the same code.  That second pass costs one more solve (~7 us) instead of the ~40 us of the shared-memory
+// algorithm, which matters because a persistent launch ends with its slowest warp.  Only problems with non-symmetric
+// Q_i/R_i or a zero / out-of-range pivot go to lqng_generic_body (same launch).
 #pragma once
 
 namespace hk {
 
-constexpr int P2_WARPS = 4;
-constexpr int P2_THREADS = 32 * P2_WARPS;
 constexpr int P2_oQ = 0, P2_oA = 128, P2_oB = 160, P2_oq = 176, P2_oR = 192, P2_ox = 200, P2_oC = 208;   // doubles
 constexpr int P2_STRIDE = 216;                  // record + constant tail, 1,728 B
 constexpr unsigned P2_TX_BYTES = 1664;
 
+template <int WARPS>
 struct P2Smem {
-    double rec[P2_WARPS][2][P2_STRIDE];
+    double rec[WARPS][2][P2_STRIDE];
     double fallback[GenericLayout<2>::total];    // one pivoting scratch per CTA, serialised by `lock` (rare path)
-    unsigned long long bar[P2_WARPS][2];
+    unsigned long long bar[WARPS][2];
     int lock;
 };
 
@@ -59,13 +62,16 @@ __device__ __forceinline__ bool bits_differ(double a, double b)
     return ((__double2hiint(a) ^ __double2hiint(b)) | (__double2loint(a) ^ __double2loint(b))) != 0;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(P2_THREADS, MINB) lqng_mma2p_kernel(LqngParams p)
+// WARPS = warps per CTA.  WARPS == 1 makes every address of the TMA issue path a function of blockIdx.x only, i.e.
+// provably warp-uniform: the copies are issued from uniform registers without the elect/broadcast loops the compiler
+// otherwise wraps around each cp.async.bulk, and the loop state lives in uniform registers.
+template <int MINB, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams p)
 {
-    __shared__ __align__(128) P2Smem sm;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __shared__ __align__(128) P2Smem<WARPS> sm;
+    const int lane = threadIdx.x & 31, wib = WARPS == 1 ? 0 : threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const long long nwarps = (long long)gridDim.x * P2_WARPS;
+    const long long nwarps = (long long)gridDim.x * WARPS;
     const long long first = (long long)wib * gridDim.x + blockIdx.x;      // leftovers of the last round spread over all SMs
     const unsigned bar_u32 = smem_u32(&sm.bar[wib][0]);
     const unsigned rec_u32 = smem_u32(&sm.rec[wib][0][0]);
@@ -134,6 +140,9 @@ __global__ void __launch_bounds__(P2_THREADS, MINB) lqng_mma2p_kernel(LqngParams
         if (lane == 0 && prob + nwarps < p.batch) issue(prob + nwarps, buf ^ 1);
         mbar_wait(bar_u32 + 8u * buf, (unsigned)(it >> 1) & 1u);
 
+        bool pivot = false, hard = false;
+        double u_out = 0.0;
+        for (;;) {                                                  // pass 0: no row exchanges; pass 1 (rare): partial pivoting
         // ---- operands of this problem -----------------------------------------------------------------------------------
         const double aT0 = rec[offA], aT1 = rec[offA + 4];
         const double xb00 = rec[offXb0], xb01 = rec[offXb0 + 2], xb10 = rec[offXb1], xb11 = rec[offXb1 + 2];
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(P2_THREADS, MINB) lqng_mma2p_kernel(LqngParams
             yL1 = g == 4 ? ax1 : rec[offB + 2];
         }
         double z00, z01, z10, z11, e0, e1;
-        bool redo;
+        bool redo, redo_piv = false;                                // redo: the shared-memory algorithm must take this problem
         {
             const double2 q0 = *reinterpret_cast<const double2*>(rec + P2_oQ + 2 * lane);          // Z_i = Q_i (KartLQR.cs:62), R-form
             const double2 q1 = *reinterpret_cast<const double2*>(rec + P2_oQ + 64 + 2 * lane);
@@ -166,7 +175,6 @@ __global__ void __launch_bounds__(P2_THREADS, MINB) lqng_mma2p_kernel(LqngParams
         double w0 = e0, w1 = e1;
         mm(w0, w1, xb00, xb01, z00, z01);
         mm(w0, w1, xb10, xb11, z10, z11);
-        double u_out = 0.0;
 
         for (int step = p.horizon; step >= 0; --step) {             // KartLQR.cs:64
             const bool last = step == 0;
@@ -183,6 +191,7 @@ __global__ void __launch_bounds__(P2_THREADS, MINB) lqng_mma2p_kernel(LqngParams
                 if (last) rv += l0;                                 // l0 of an Aug lane = (RM x0)[rho]
                 if (isAug) M0 = rv;
             }
+            if (!pivot) {
             // fraction-free Gauss-Jordan: row_i <- pv row_i - LHS[i][k] row_k (the pivot row is only rescaled)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -192,7 +201,8 @@ __global__ void __launch_bounds__(P2_THREADS, MINB) lqng_mma2p_kernel(LqngParams
                 const double r0 = shfl_d(M0, rs), r1 = shfl_d(M1, rs);
                 const double pv = shfl_d(mine, 8 * (k >> 1) + 4 * (k & 1) + (k >> 1));
                 const unsigned hp = abs_hi(pv);
-                redo |= ((rho_chk > k) & (abs_hi(c) > hp)) | ((hp - 0x33700000u) > 0x19000000u);   // |pv| outside 2^-200 .. 2^200
+                redo_piv |= (rho_chk > k) & (abs_hi(c) > hp);                               // MathNet would exchange rows
+                redo |= (hp - 0x33700000u) > 0x19000000u;                                  // |pv| outside 2^-200 .. 2^200
                 const double cz = rho == k ? 0.0 : c;
                 M0 = fma(pv, M0, -(cz * r0));
                 M1 = fma(pv, M1, -(cz * r1));
@@ -201,6 +211,50 @@ __global__ void __launch_bounds__(P2_THREADS, MINB) lqng_mma2p_kernel(LqngParams
                 const double d = shfl_d(rodd ? M1 : M0, dsrc);
                 const double rinv = rcp_fast(d);
                 M0 *= rinv; M1 *= rinv;
+            }
+            } else {
+                // Gauss-Jordan with partial pivoting, lane j < 9 owning column j of [LHS | I | RHSVec] (KartLQR.cs:104-105)
+                double c0, c1, c2, c3;
+                {
+                    const int j = lane < 9 ? lane : 0, jq = j >> 1;            // LHS[i][j] sits in L lane (g = 2 jq + (i&1), t = i>>1)
+                    const double a0 = shfl_d(M0, 8 * jq), b0 = shfl_d(M1, 8 * jq);
+                    const double a1 = shfl_d(M0, 8 * jq + 4), b1 = shfl_d(M1, 8 * jq + 4);
+                    const double a2 = shfl_d(M0, 8 * jq + 1), b2 = shfl_d(M1, 8 * jq + 1);
+                    const double a3 = shfl_d(M0, 8 * jq + 5), b3 = shfl_d(M1, 8 * jq + 5);
+                    const double v0 = shfl_d(M0, 2), v1 = shfl_d(M0, 6), v2 = shfl_d(M0, 10), v3 = shfl_d(M0, 14);
+                    const bool od = j & 1;
+                    c0 = od ? b0 : a0; c1 = od ? b1 : a1; c2 = od ? b2 : a2; c3 = od ? b3 : a3;
+                    if (lane >= 4) { c0 = lane == 4 ? 1.0 : 0.0; c1 = lane == 5 ? 1.0 : 0.0; c2 = lane == 6 ? 1.0 : 0.0; c3 = lane == 7 ? 1.0 : 0.0; }
+                    if (lane == 8) { c0 = v0; c1 = v1; c2 = v2; c3 = v3; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double p0 = shfl_d(c0, k), p1 = shfl_d(c1, k), p2 = shfl_d(c2, k), p3 = shfl_d(c3, k);   // column k, every lane
+                    // pivot row: first largest |.| among rows k..3, brought to row k by an exchange
+                    int pr = k;
+                    double best = fabs(k == 0 ? p0 : k == 1 ? p1 : k == 2 ? p2 : p3);
+                    if (k < 1 && fabs(p1) > best) { best = fabs(p1); pr = 1; }
+                    if (k < 2 && fabs(p2) > best) { best = fabs(p2); pr = 2; }
+                    if (k < 3 && fabs(p3) > best) { best = fabs(p3); pr = 3; }
+                    double& ck = k == 0 ? c0 : k == 1 ? c1 : k == 2 ? c2 : c3;
+                    double& pk = k == 0 ? p0 : k == 1 ? p1 : k == 2 ? p2 : p3;
+                    if (k < 1 && pr == 1) { double tmp = ck; ck = c1; c1 = tmp; tmp = pk; pk = p1; p1 = tmp; }   // warp-uniform
+                    if (k < 2 && pr == 2) { double tmp = ck; ck = c2; c2 = tmp; tmp = pk; pk = p2; p2 = tmp; }
+                    if (k < 3 && pr == 3) { double tmp = ck; ck = c3; c3 = tmp; tmp = pk; pk = p3; p3 = tmp; }
+                    redo |= bad_pivot(pk);                          // zero, denormal, tiny, huge, inf or NaN: shared-memory algorithm
+                    const double rk = ck / pk;                      // row k of the reduced system, this lane's column
+                    if (k != 0) c0 = fma(-p0, rk, c0);
+                    if (k != 1) c1 = fma(-p1, rk, c1);
+                    if (k != 2) c2 = fma(-p2, rk, c2);
+                    if (k != 3) c3 = fma(-p3, rk, c3);
+                    ck = rk;
+                }
+                // back to the fragment distribution: I lanes take Lambda[rho][2kap..2kap+1], Aug lanes take (LHS^-1 rhs)[rho]
+                const int sa = isAug ? 8 : 4 + 2 * kap, sb = isAug ? 8 : 5 + 2 * kap;
+                const double a0 = shfl_d(c0, sa), a1 = shfl_d(c1, sa), a2 = shfl_d(c2, sa), a3 = shfl_d(c3, sa);
+                const double b0 = shfl_d(c0, sb), b1 = shfl_d(c1, sb), b2 = shfl_d(c2, sb), b3 = shfl_d(c3, sb);
+                M0 = rho == 0 ? a0 : rho == 1 ? a1 : rho == 2 ? a2 : a3;
+                M1 = rho == 0 ? b0 : rho == 1 ? b1 : rho == 2 ? b2 : b3;
             }
             if (last) {                                             // optimal_control = -P x0 - alpha with the t = 0 gains (:121-126)
                 u_out = -M0;
@@ -245,8 +299,12 @@ __global__ void __launch_bounds__(P2_THREADS, MINB) lqng_mma2p_kernel(LqngParams
                 e0 = n0; e1 = n1;
             }
         }
-        if (__ballot_sync(0xffffffffu, redo)) {
-            // Warp-uniform and rare: row exchanges needed, non-symmetric Q/R or an out-of-range pivot.
+        hard = __ballot_sync(0xffffffffu, redo) != 0;
+        if (hard || pivot || __ballot_sync(0xffffffffu, redo_piv) == 0) break;
+        pivot = true;
+        }
+        if (hard) {
+            // Warp-uniform and rare: non-symmetric Q/R or a zero / out-of-range pivot.
             if (lane == 0) while (atomicCAS(&sm.lock, 0, 1) != 0) {}
             __syncwarp();
             if (lane < 8) lqng_generic_body<2>(p, prob, true, sm.fallback, lane, 0xffu);

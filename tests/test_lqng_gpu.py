@@ -83,6 +83,34 @@ def test_pivoting_and_singular_status(hk, oracle):
     assert np.all(ref["status"] == 1) and np.array_equal(got["status"], ref["status"])
 
 
+def test_pivot_pass_of_the_throughput_kernel(hk, oracle):
+    """u0-only 2-kart batches take the DMMA kernel; problems whose coupled system needs row exchanges are re-solved by the
+    same warp with partial pivoting (hk_lqng_mma2p.cuh), zero pivots go to the shared-memory algorithm.  Mixed batch."""
+    rng = np.random.default_rng(21)
+    batch = 301
+    A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(S.OVAL, batch, 2, seed=5))
+    kind = np.arange(batch) % 7
+    for b in np.nonzero(kind == 3)[0]:                   # R_i with a dominant off-diagonal: every step exchanges rows
+        c = 0.2 + 0.1 * rng.random()
+        R[b] = np.array([[0.05 * c, c], [c, 0.03 * c]])
+    for b in np.nonzero(kind == 5)[0]:                   # coupling larger than R: exchanges across the two players' rows
+        B[b] = 3.0 * rng.standard_normal((2, 4, 2))
+        Qb = rng.standard_normal((2, 8, 8))
+        Q[b] = Qb + np.swapaxes(Qb, -1, -2)
+        R[b] = np.eye(2) * 1e-2
+    sing = np.nonzero(kind == 6)[0][:5]                  # exactly singular: status 1 like the oracle
+    B[sing] = 0.0
+    R[sing] = 0.0
+    ref = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 3, full=False)
+    got = lqr.solve_batch(A, B, Q, q, R, x0, 3, full=False)
+    assert np.array_equal(got["status"], ref["status"]) and ref["status"].sum() == 5
+    for b in range(batch):
+        if ref["status"][b]:
+            continue
+        tol = 1e-7 if kind[b] == 5 else TOL               # kind 5: condition numbers up to ~1e5
+        assert rel_err(got["u0"][b], ref["u0"][b]) <= tol, (b, kind[b])
+
+
 def test_golden_fixture(hk):
     g = np.load("tests/golden/lqng_golden.npz")
     for N in (2, 4):
