@@ -32,6 +32,8 @@ IN_BYTES_PER_SOLVE = 1664          # A,B per player + Q,q,R,x0 (SURVEY.md §8(d)
 OUT_BYTES_PER_SOLVE = 32 + 4       # u0 for both players + status
 N_INPUT_SETS = 4                   # rotated so that consecutive steps never hit the same 109 MB in the 126 MB L2
 MCTS_ROLLOUTS = 1_000_000          # BASELINE config 4
+RACES = 16384                      # BASELINE config 5
+RACE_STEPS = 200
 
 
 def _peaks():
@@ -148,6 +150,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mcts", action="store_true")
+    ap.add_argument("--no-race", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -289,6 +292,27 @@ def main():
                     "config": "BASELINE config 4: Complex, 2 karts, depth 8, bucket 2, Philox4x32-10; host call incl. result D2H",
                     "gpu_launches": reps}
 
+    # ---- closed loop without PhysX (BASELINE config 5: 16,384 2-kart Oval races; Fixed high level, LQNG every step) -----------
+    race_obj = None
+    if not args.no_race:
+        from hierarchicalkarting_b200 import race as RC
+        RS = RC.Races(S.OVAL, RC.race_params(S.OVAL))
+        karts, plans = RC.start_grid(S.OVAL, RACES, seed=20260004 + rank)
+        RS.run(karts, plans, 0, 100)                                        # warm-up: the standing start
+        barrier()
+        k0r = lib.hk_kernel_launch_count()
+        t0 = time.perf_counter()
+        _, bad = RS.run(karts, plans, 100, RACE_STEPS)
+        el = max_over_ranks(time.perf_counter() - t0)
+        race_obj = {"metric": "race_agent_steps_per_s", "value": world * 2 * RACES * RACE_STEPS / el, "unit": "agent-steps/s",
+                    "races_per_gpu": RACES, "steps": RACE_STEPS, "ms_per_step": 1e3 * el / RACE_STEPS,
+                    "realtime_factor": (RACE_STEPS * 0.02) / el * world * RACES,
+                    "lqng_status_nonzero": int(bad), "gpu_launches": int(lib.hk_kernel_launch_count() - k0r),
+                    "sections_mean": float(karts["section"].mean()),
+                    "config": "BASELINE config 5: 2-kart Oval races, kinematic plant, planFixed every 100 steps, one LQNG solve per "
+                              "agent and step (recipe + assembly + solve + plant + bookkeeping on the GPU); host call incl. the "
+                              "upload and download of the race states"}
+
     clocks = sampler.finish()
 
     # ---- final gather of per-rank summaries (the only communication) ------------------------------------------------------
@@ -338,6 +362,8 @@ def main():
     }
     if mcts_obj:
         line["mcts"] = mcts_obj
+    if race_obj:
+        line["race"] = race_obj
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)

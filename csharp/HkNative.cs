@@ -25,6 +25,21 @@ namespace KartGame.AI.Native
         public void Set(int i, HkKartState s) { if (i == 0) k0 = s; else if (i == 1) k1 = s; else if (i == 2) k2 = s; else k3 = s; }
     }
 
+    [StructLayout(LayoutKind.Sequential)] public struct HkRaceKart
+    {
+        public double x, z, v, h; public float steer;
+        public int section, lane, laneChanges, illegalLaneChanges, sectionStep, active, pad_;
+    }
+    [StructLayout(LayoutKind.Sequential)] public unsafe struct HkRacePlan
+    {
+        public fixed sbyte lane[64]; public fixed float vel[64]; public fixed sbyte oppLane[64]; public fixed float oppVel[64];
+    }
+    [StructLayout(LayoutKind.Sequential)] public struct HkRaceParams
+    {
+        public double dt; public float accel, braking, coastingDrag, topSpeed, gateHalfWidth;
+        public int maxLaneChanges, goalSection, highModeMcts, velocityBucketSize, treeSearchDepth, planEvery, horizon;
+    }
+
     public static class HkNative
     {
         const string Lib = "hk_b200";                            // libhk_b200.so / hk_b200.dll on the plugin search path
@@ -48,6 +63,20 @@ namespace KartGame.AI.Native
         [DllImport(Lib)] public static extern int hk_mcts_rollouts_multi(IntPtr game, HkGameState[] leaves, int nLeaves, long rolloutsPerLeaf, ulong seed,
                                                                          ulong rolloutOffset, [Out] long[] visit, [Out] double[] rewardSum,
                                                                          [Out] long[] nanCount, [Out] long[] pliesSum);
+
+        // headless batch races (kinematic plant instead of PhysX)
+        [DllImport(Lib)] public static extern int hk_track_create(HkSection[] sections, double[] triggerXz, double[] forwardXz, double[] laneXz,
+                                                                  int nSections, out IntPtr track);
+        [DllImport(Lib)] public static extern void hk_track_destroy(IntPtr track);
+        [DllImport(Lib)] public static extern int hk_race_recipe(IntPtr track, ref HkRaceParams p, int nRaces, HkRaceKart[] karts, HkRacePlan[] plans,
+                                                                 [Out] double[] x0, [Out] double[] target, [Out] double[] tw, [Out] double[] cw,
+                                                                 [Out] double[] aw, [Out] double[] otgt, [Out] double[] otw);
+        [DllImport(Lib)] public static extern int hk_race_plan_fixed(IntPtr track, ref HkRaceParams p, int nKarts, HkRaceKart[] karts, [In, Out] HkRacePlan[] plans);
+        [DllImport(Lib)] public static extern int hk_race_step(IntPtr track, ref HkRaceParams p, int nKarts, int episodeStep, double[] u,
+                                                               [In, Out] HkRaceKart[] karts, [In, Out] HkRacePlan[] plans);
+        [DllImport(Lib)] public static extern int hk_race_run(IntPtr track, ref HkRaceParams p, int nRaces, int firstStep, int nSteps,
+                                                              [In, Out] HkRaceKart[] karts, [In, Out] HkRacePlan[] plans, [Out] double[] uLast,
+                                                              out long lqngStatusNonzero);
 
         public static void Check(int status)
         {

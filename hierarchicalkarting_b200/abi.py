@@ -17,6 +17,7 @@ HK_MAX_HORIZON = 31
 HK_MAX_KARTS = 4
 HK_MAX_ACTIONS = 36
 HK_MAX_PLIES = 64
+HK_MAX_SECTIONS = 64
 
 HK_OK = 0
 HK_ERR_INVALID_ARGUMENT = -1
@@ -68,7 +69,32 @@ class hk_game_state(C.Structure):
                 tuple(self.karts[i].astuple() for i in range(self.n_karts)))
 
 
+class hk_race_kart(C.Structure):
+    _fields_ = [("x", C.c_double), ("z", C.c_double), ("v", C.c_double), ("h", C.c_double), ("steer", C.c_float),
+                ("section", C.c_int32), ("lane", C.c_int32), ("laneChanges", C.c_int32), ("illegalLaneChanges", C.c_int32),
+                ("sectionStep", C.c_int32), ("active", C.c_int32), ("pad_", C.c_int32)]
+
+
+class hk_race_plan(C.Structure):
+    _fields_ = [("lane", C.c_int8 * HK_MAX_SECTIONS), ("vel", C.c_float * HK_MAX_SECTIONS),
+                ("oppLane", C.c_int8 * HK_MAX_SECTIONS), ("oppVel", C.c_float * HK_MAX_SECTIONS)]
+
+
+class hk_race_params(C.Structure):
+    _fields_ = [("dt", C.c_double), ("accel", C.c_float), ("braking", C.c_float), ("coastingDrag", C.c_float),
+                ("topSpeed", C.c_float), ("gateHalfWidth", C.c_float), ("maxLaneChanges", C.c_int32),
+                ("goalSection", C.c_int32), ("highModeMcts", C.c_int32), ("velocityBucketSize", C.c_int32),
+                ("treeSearchDepth", C.c_int32), ("planEvery", C.c_int32), ("horizon", C.c_int32)]
+
+
 # numpy views of the same layouts (for batched buffers)
+RACE_KART_DTYPE = np.dtype([("x", np.float64), ("z", np.float64), ("v", np.float64), ("h", np.float64), ("steer", np.float32),
+                            ("section", np.int32), ("lane", np.int32), ("laneChanges", np.int32),
+                            ("illegalLaneChanges", np.int32), ("sectionStep", np.int32), ("active", np.int32), ("pad_", np.int32)])
+RACE_PLAN_DTYPE = np.dtype([("lane", np.int8, (HK_MAX_SECTIONS,)), ("vel", np.float32, (HK_MAX_SECTIONS,)),
+                            ("oppLane", np.int8, (HK_MAX_SECTIONS,)), ("oppVel", np.float32, (HK_MAX_SECTIONS,))])
+assert RACE_KART_DTYPE.itemsize == C.sizeof(hk_race_kart) == 64
+assert RACE_PLAN_DTYPE.itemsize == C.sizeof(hk_race_plan) == 640
 KART_STATE_DTYPE = np.dtype([(k, np.int32) for k in KART_STATE_FIELDS])
 ACTION_DTYPE = np.dtype([("min_velocity", np.int32), ("max_velocity", np.int32), ("lane", np.int32)])
 GAME_STATE_DTYPE = np.dtype([("n_karts", np.int32), ("initialSection", np.int32), ("lastCompletedSection", np.int32),
@@ -102,6 +128,12 @@ PROTOTYPES = {
     "hk_mcts_rollouts_trace": (C.c_int, [C.c_void_p, C.POINTER(hk_game_state), C.c_int64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 5),
     "hk_mcts_rollouts_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 4),
     "hk_policy_cdf": (C.c_int, [C.c_int, _up]),
+    "hk_track_create": (C.c_int, [C.POINTER(hk_section), _dp, _dp, _dp, C.c_int, C.POINTER(C.c_void_p)]),
+    "hk_track_destroy": (None, [C.c_void_p]),
+    "hk_race_recipe": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_void_p, C.c_void_p] + [_dp] * 7),
+    "hk_race_step": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_int, _dp, C.c_void_p, C.c_void_p]),
+    "hk_race_plan_fixed": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_void_p, C.c_void_p]),
+    "hk_race_run": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, _dp, _lp]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libhk_b200.so")

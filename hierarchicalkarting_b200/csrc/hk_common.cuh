@@ -17,8 +17,8 @@ struct ThreadCtx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    void* dbuf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t dcap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* dbuf[12] = {};
+    size_t dcap[12] = {};
     void* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};      // pinned
     size_t hcap[4] = {0, 0, 0, 0};
     bool ready = false;

@@ -1,0 +1,401 @@
+// hk_race.cu — the closed loop without PhysX for many independent 2-kart races, sm_100a.
+//
+// Per step and per agent: the LQNG problem recipe of HierarchicalKartAgent.SolveLQR, raycast-free branches
+// (reference: Assets/Karting/Scripts/AI/HierarchicalKartAgent.cs:699-1197), device-side assembly + solve (hk_lqng.cu),
+// the actuator map (:1206-1224) on the kinematic model the planners assume (MPC/KartMPCDynamics.cs:55-70) and the
+// checkpoint bookkeeping of OnTriggerEnter (:611-662; lane by DiscretePositionTracker.CalculateLane :116-148); planFixed
+// (:145-166) as the high level.  One thread per agent; kart records are 64-byte AoS (a warp reads 2 KB contiguous), plans are
+// touched at two keys per agent and step.  Compiled with -fmad=false: the float32 expressions of the recipe (distances,
+// Mathf.Atan2, Mathf.Pow weights) must round exactly like the reference's scalar code, an FMA would move avoid weights by
+// one float ulp (6e-8), far above the 1e-9 parity bar.  Unity's Mathf.X(float) is (float)Math.X(double).
+#include "hk_common.cuh"
+#include <cmath>
+
+namespace hk {
+
+struct DevTrack {
+    int n;
+    hk_section sec[HK_MAX_SECTIONS];
+    double trig[HK_MAX_SECTIONS][2];
+    double fwd[HK_MAX_SECTIONS][2];
+    double lane[HK_MAX_SECTIONS][4][2];
+};
+
+}  // namespace hk
+
+struct hk_track {
+    hk::DevTrack* dev;
+    int n;
+};
+
+namespace hk {
+
+__device__ __forceinline__ float mathf_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
+__device__ __forceinline__ float magnitude2(float dx, float dz) { return (float)sqrt((double)(dx * dx + dz * dz)); }
+__device__ __forceinline__ float wrap2pi_f(float a) { return a < 0 ? a + 2 * 3.14159274f : a; }
+__device__ __forceinline__ double angle_difference(double a1, double a2) { return atan2(sin(a2 - a1), cos(a2 - a1)); }   // HKA:1341-1344
+__device__ __forceinline__ bool is_straight(const DevTrack* t, int section) { return t->sec[section % t->n].insideR == 0.0f; }
+
+__device__ __forceinline__ void plan_target(const DevTrack* t, const hk_race_params& p, const int8_t* lanes, const float* vels, int idx,
+                                            double& x, double& z, double& vel)
+{
+    const double max_speed = (double)p.topSpeed;                    // GetMaxSpeed(), ArcadeKart.cs:210
+    const int ln = lanes[idx];
+    if (ln != 0) {
+        x = t->lane[idx][ln - 1][0];
+        z = t->lane[idx][ln - 1][1];
+        const double v = (double)vels[idx] + (p.highModeMcts ? p.velocityBucketSize * 2 : 0);
+        vel = max_speed < v ? max_speed : v;
+    } else {
+        x = t->trig[idx][0];
+        z = t->trig[idx][1];
+        vel = max_speed;
+    }
+}
+
+// One thread per problem b = 2 race + ego; player 0 = ego, player 1 = the other kart (HKA:702).
+__global__ void race_recipe_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_problems, const hk_race_kart* __restrict__ karts,
+                                   const hk_race_plan* __restrict__ plans, double* x0, double* target, double* tw, double* cw, double* aw,
+                                   double* otgt, double* otw)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_problems) return;
+    const int e = b & 1;
+    const hk_race_kart* pair = karts + (b - e);
+    const hk_race_plan* plan = plans + b;
+    double tlx[2], tlz[2], vel[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const hk_race_kart k = pair[i == 0 ? e : 1 - e];
+        const int8_t* lanes = i == 0 ? plan->lane : plan->oppLane;   // own plan / belief about the other (:745-817)
+        const float* vels = i == 0 ? plan->vel : plan->oppVel;
+        double* x = x0 + (size_t)b * 8 + i * 4;
+        x[0] = k.x; x[1] = k.z; x[2] = k.v; x[3] = k.h;              // :730-736
+        const int s = k.section + 1;                                 // :745
+        const int idx = s % t->n, idx2 = (s + 1) % t->n;
+        double nlx, nlz, nvel;
+        plan_target(t, p, lanes, vels, idx, tlx[i], tlz[i], vel[i]);
+        plan_target(t, p, lanes, vels, idx2, nlx, nlz, nvel);
+        const bool stopped = (float)k.v <= 5.0f;                     // :808
+        double tx = tlx[i], tz = tlz[i], tv = stopped ? 0.0 : vel[i];
+        const float d_t = magnitude2((float)(tlx[i] - k.x), (float)(tlz[i] - k.z));
+        const bool near = d_t <= (is_straight(t, k.section) ? 10.5f : 7.5f);           // :823
+        const float d_c = magnitude2((float)(t->trig[idx][0] - k.x), (float)(t->trig[idx][1] - k.z));
+        const bool follow = near && (d_c <= 4.0f);                   // :877-890, centre-line distance stand-in
+        const double h0 = k.h;
+        double th;
+        if (follow) {
+            const double f6w = (double)wrap2pi_f(mathf_atan2((float)(nlz - k.z), (float)(nlx - k.x)));
+            th = h0 - angle_difference(h0, f6w);                     // :887
+            tx = nlx; tz = nlz;
+            if (!stopped) tv = nvel;
+        } else {
+            const double f1w = (double)wrap2pi_f(mathf_atan2((float)(tlz[i] - k.z), (float)(tlx[i] - k.x)));
+            if (near) {
+                const double f2w = (double)wrap2pi_f(mathf_atan2((float)(nlz - tlz[i]), (float)(nlx - tlx[i])));
+                double blend = f1w - angle_difference(f2w, f1w) * (double)0.4f;         // :896
+                if (blend < 0) blend += 2 * (double)3.14159274f;
+                th = h0 - angle_difference(h0, blend);               // :898
+            } else {
+                th = h0 - angle_difference(h0, f1w);                 // :921
+            }
+        }
+        double* tg = target + (size_t)b * 8 + i * 4;
+        tg[0] = tx; tg[1] = tz; tg[2] = tv; tg[3] = th;
+        const double vmax1 = k.v > 1.0 ? k.v : 1.0;                  // own target weights, 2-agent branch (:930-962)
+        const double w_xz = stopped ? 0.3 * 3.1 : 0.3 * 3.1 / vmax1;
+        double* w = tw + (size_t)b * 8 + i * 4;
+        w[0] = w_xz; w[1] = w_xz; w[2] = stopped ? -2.0 : 5e-4; w[3] = p.highModeMcts ? 3.5 : 1.9;
+        cw[(size_t)b * 2 + i] = 0.115;                               // :1192-1196
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                                    // avoid + opponent-target weights (:964-1190)
+        const int o = 1 - i;
+        const hk_race_kart ki = pair[i == 0 ? e : 1 - e];
+        const hk_race_kart ko = pair[o == 0 ? e : 1 - e];
+        const float mult = i == 0 ? 1.0f : 1.3f;                     // :999-1002
+        const float dist = magnitude2((float)(ko.x - ki.x), (float)(ko.z - ki.z));
+        const bool far = dist > 8;
+        const float w32 = 1.0f / ((float)pow((double)dist, (double)1.5f) * mult);      // 1f/(Mathf.Pow(d,1.5f)*mult), :1019
+        const double w = far ? 0.0 : (double)w32;
+        aw[(size_t)b * 4 + i * 2 + 0] = w;
+        aw[(size_t)b * 4 + i * 2 + 1] = w;
+        double* og = otgt + (size_t)b * 8 + i * 4;
+        og[0] = tlx[o]; og[1] = tlz[o]; og[2] = vel[o]; og[3] = 0.0;
+        const double vmax1 = ki.v > 1.0 ? ki.v : 1.0;
+        const double wxz = (p.highModeMcts ? 0.2 : 0.1) / vmax1;     // :1089-1091
+        double* ow = otw + (size_t)b * 6 + i * 3;
+        ow[0] = far ? 0.0 : wxz; ow[1] = far ? 0.0 : wxz; ow[2] = far ? 0.0 : 0.08;
+    }
+}
+
+// planFixed (:145-166), one thread per agent
+__global__ void race_plan_fixed_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_karts, const hk_race_kart* __restrict__ karts,
+                                       hk_race_plan* plans)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_karts || !karts[k].active) return;
+    const int s = karts[k].section;
+    const int hi = s + p.treeSearchDepth < 1000 ? s + p.treeSearchDepth : 1000;
+    for (int i = s + 1; i < hi + 1; ++i) {
+        const int key = i % t->n;
+        if (plans[k].lane[key] == 0) {
+            plans[k].lane[key] = (int8_t)t->sec[(i - 1) % t->n].optimalLane;   // getOptimalNextLane
+            plans[k].vel[key] = p.topSpeed;                                     // GetMaxSpeed()
+        }
+    }
+}
+
+// actuator map (:1206-1224) + kinematic plant (KartMPCDynamics.cs:55-70) + OnTriggerEnter bookkeeping (:611-662).
+// u has `u_stride` doubles per kart (2: plain controls; 4: the LQNG u0 record of problem = kart, ego first).
+__global__ void race_step_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_karts, int episode_step, const double* __restrict__ u,
+                                 int u_stride, const int* __restrict__ lqng_status, unsigned long long* status_count, hk_race_kart* karts,
+                                 hk_race_plan* plans)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_karts) return;
+    if (lqng_status && lqng_status[i] != 0) atomicAdd(status_count, 1ull);
+    hk_race_kart k = karts[i];
+    if (!k.active) return;
+    const double u0 = u[(size_t)i * u_stride], u1 = u[(size_t)i * u_stride + 1];
+    const float max_ang = k.steer * 0.4f;                            // getMaxAngularVelocity, ArcadeKart.cs:505-510
+    float ang = (float)u1;
+    ang = ang < -max_ang ? -max_ang : (ang > max_ang ? max_ang : ang);              // Mathf.Clamp :1206
+    bool accel = false, brake = false;
+    if (u0 < 0) brake = true;
+    else if (u0 > 0) accel = true;
+    else ang = 0.0f;
+    const float steering = ang / (0.4f * k.steer);                   // m_Steering :1224
+    const float turning_power = steering * k.steer * (fabsf((float)k.v) > 0.5f ? 1.0f : 0.0f);   // ArcadeKart.cs:406
+    const double omega = (double)(turning_power * 0.4f);
+    const double x_old = k.x, z_old = k.z;
+    k.x = x_old + p.dt * k.v * cos(k.h);
+    k.z = z_old + p.dt * k.v * sin(k.h);
+    // Unity's yaw is left-handed: a positive TurnInput turns the kart clockwise seen from above, i.e. the solver's heading
+    // atan2(forward.z, forward.x) DEcreases.  SolveLQR compensates by mirroring the target heading about the current one
+    // (h0 - AngleDifference(h0, target) = 2 h0 - target, :887,:898,:921), so the stand-in must turn like Unity does.
+    double h = k.h - p.dt * omega;
+    const double TWO_PI = 6.283185307179586;
+    if (h < 0) h += TWO_PI;
+    if (h >= TWO_PI) h -= TWO_PI;
+    double v = k.v;
+    if (accel) { v += p.dt * (double)p.accel; if (v > (double)p.topSpeed) v = (double)p.topSpeed; }
+    else if (brake) { v -= p.dt * (double)p.braking; if (v < 0) v = 0; }
+    else { v -= p.dt * (double)p.coastingDrag; if (v < 0) v = 0; }  // MoveTowards(v, 0, dt CoastingDrag), ArcadeKart.cs:431
+    k.h = h; k.v = v;
+    // did the kart enter the trigger of checkpoint section+1 during this step?
+    const int index = k.section + 1, c = index % t->n;
+    const double fx = t->fwd[c][0], fz = t->fwd[c][1];
+    const double s_old = (x_old - t->trig[c][0]) * fx + (z_old - t->trig[c][1]) * fz;
+    const double s_new = (k.x - t->trig[c][0]) * fx + (k.z - t->trig[c][1]) * fz;
+    const double lat = -(k.x - t->trig[c][0]) * fz + (k.z - t->trig[c][1]) * fx;
+    if (s_old < 0 && s_new >= 0 && fabs(lat) <= (double)p.gateHalfWidth) {
+        int lane_new = 1;                                            // CalculateLane: first minimum
+        float best = 0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const float d = magnitude2((float)(k.x - t->lane[c][l][0]), (float)(k.z - t->lane[c][l][1]));
+            if (l == 0 || d < best) { best = d; lane_new = l + 1; }
+        }
+        plans[i].lane[c] = 0;                                        // m_UpcomingLanes.Remove (:631-632)
+        plans[i].vel[c] = 0.0f;
+        const int dl = abs(k.lane - lane_new);
+        const bool st_old = is_straight(t, k.section), st_new = is_straight(t, index);
+        if (k.laneChanges + dl > p.maxLaneChanges && st_old) k.illegalLaneChanges += 1;   // :638-642
+        if (st_old != st_new) k.laneChanges = 0;                     // :643-646
+        else if (k.lane != lane_new) k.laneChanges += dl;            // :647-650
+        k.section = index;
+        k.lane = lane_new;
+        k.sectionStep = episode_step;
+        if (k.section == p.goalSection) k.active = 0;                // ReachGoalSection (:652-655)
+    }
+    karts[i] = k;
+}
+
+static int check_track(const hk_track* t, const hk_race_params* p, const char* who)
+{
+    if (!t || !t->dev || !p) { set_error("%s: null track / params", who); return HK_ERR_INVALID_ARGUMENT; }
+    if (p->planEvery <= 0 || p->horizon < 0 || p->horizon > HK_MAX_HORIZON || p->treeSearchDepth < 0) {
+        set_error("%s: invalid parameters", who);
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    return HK_OK;
+}
+
+}  // namespace hk
+
+using namespace hk;
+
+extern "C" int hk_track_create(const hk_section* sections, const double* trigger_xz, const double* forward_xz, const double* lane_xz,
+                               int n_sections, hk_track** out)
+{
+    if (!sections || !trigger_xz || !forward_xz || !lane_xz || !out || n_sections < 1 || n_sections > HK_MAX_SECTIONS) {
+        set_error("hk_track_create: invalid argument (1..%d sections)", HK_MAX_SECTIONS);
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    DevTrack* h = new DevTrack();
+    h->n = n_sections;
+    for (int i = 0; i < n_sections; ++i) {
+        h->sec[i] = sections[i];
+        for (int a = 0; a < 2; ++a) { h->trig[i][a] = trigger_xz[i * 2 + a]; h->fwd[i][a] = forward_xz[i * 2 + a]; }
+        for (int l = 0; l < 4; ++l)
+            for (int a = 0; a < 2; ++a) h->lane[i][l][a] = lane_xz[(i * 4 + l) * 2 + a];
+    }
+    DevTrack* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(DevTrack));
+    if (e == cudaSuccess) e = cudaMemcpy(d, h, sizeof(DevTrack), cudaMemcpyHostToDevice);
+    delete h;
+    if (e != cudaSuccess) { set_error("hk_track_create: %s", cudaGetErrorString(e)); if (d) cudaFree(d); return HK_ERR_CUDA; }
+    *out = new hk_track{d, n_sections};
+    return HK_OK;
+}
+
+extern "C" void hk_track_destroy(hk_track* t)
+{
+    if (!t) return;
+    if (t->dev) cudaFree(t->dev);
+    delete t;
+}
+
+extern "C" int hk_race_recipe(const hk_track* t, const hk_race_params* p, int n_races, const hk_race_kart* karts, const hk_race_plan* plans,
+                              double* x0, double* target, double* tw, double* cw, double* aw, double* otgt, double* otw)
+{
+    int rc = check_track(t, p, "hk_race_recipe");
+    if (rc) return rc;
+    if (n_races < 0 || (n_races > 0 && (!karts || !plans || !x0 || !target || !tw || !cw || !aw || !otgt || !otw))) {
+        set_error("hk_race_recipe: invalid argument");
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    if (n_races == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const size_t nb = (size_t)2 * n_races;
+    const size_t out_elems = nb * (8 + 8 + 8 + 2 + 4 + 8 + 6);
+    char* d = (char*)dscratch(c, 8, nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan)) + out_elems * sizeof(double));
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    hk_race_kart* dk = (hk_race_kart*)d;
+    hk_race_plan* dp = (hk_race_plan*)(dk + nb);
+    double* o = (double*)(dp + nb);
+    double *dx0 = o, *dtg = dx0 + nb * 8, *dtw = dtg + nb * 8, *dcw = dtw + nb * 8, *daw = dcw + nb * 2, *dot = daw + nb * 4, *dow = dot + nb * 8;
+    HK_CUDA(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, c->stream));
+    HK_CUDA(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, c->stream));
+    count_launch();
+    race_recipe_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(t->dev, *p, (int)nb, dk, dp, dx0, dtg, dtw, dcw, daw, dot, dow);
+    HK_CUDA(cudaGetLastError());
+    double* dst[7] = {x0, target, tw, cw, aw, otgt, otw};
+    double* src[7] = {dx0, dtg, dtw, dcw, daw, dot, dow};
+    const size_t per[7] = {8, 8, 8, 2, 4, 8, 6};
+    for (int i = 0; i < 7; ++i) HK_CUDA(cudaMemcpyAsync(dst[i], src[i], nb * per[i] * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    return HK_OK;
+}
+
+extern "C" int hk_race_plan_fixed(const hk_track* t, const hk_race_params* p, int n_karts, const hk_race_kart* karts, hk_race_plan* plans)
+{
+    int rc = check_track(t, p, "hk_race_plan_fixed");
+    if (rc) return rc;
+    if (n_karts < 0 || (n_karts > 0 && (!karts || !plans))) { set_error("hk_race_plan_fixed: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    if (n_karts == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    char* d = (char*)dscratch(c, 8, (size_t)n_karts * (sizeof(hk_race_kart) + sizeof(hk_race_plan)));
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    hk_race_kart* dk = (hk_race_kart*)d;
+    hk_race_plan* dp = (hk_race_plan*)(dk + n_karts);
+    HK_CUDA(cudaMemcpyAsync(dk, karts, (size_t)n_karts * sizeof(hk_race_kart), cudaMemcpyHostToDevice, c->stream));
+    HK_CUDA(cudaMemcpyAsync(dp, plans, (size_t)n_karts * sizeof(hk_race_plan), cudaMemcpyHostToDevice, c->stream));
+    count_launch();
+    race_plan_fixed_kernel<<<(n_karts + 127) / 128, 128, 0, c->stream>>>(t->dev, *p, n_karts, dk, dp);
+    HK_CUDA(cudaGetLastError());
+    HK_CUDA(cudaMemcpyAsync(plans, dp, (size_t)n_karts * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    return HK_OK;
+}
+
+extern "C" int hk_race_step(const hk_track* t, const hk_race_params* p, int n_karts, int episode_step, const double* u, hk_race_kart* karts,
+                            hk_race_plan* plans)
+{
+    int rc = check_track(t, p, "hk_race_step");
+    if (rc) return rc;
+    if (n_karts < 0 || (n_karts > 0 && (!karts || !plans || !u))) { set_error("hk_race_step: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    if (n_karts == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    char* d = (char*)dscratch(c, 8, (size_t)n_karts * (sizeof(hk_race_kart) + sizeof(hk_race_plan) + 2 * sizeof(double)));
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    hk_race_kart* dk = (hk_race_kart*)d;
+    hk_race_plan* dp = (hk_race_plan*)(dk + n_karts);
+    double* du = (double*)(dp + n_karts);
+    HK_CUDA(cudaMemcpyAsync(dk, karts, (size_t)n_karts * sizeof(hk_race_kart), cudaMemcpyHostToDevice, c->stream));
+    HK_CUDA(cudaMemcpyAsync(dp, plans, (size_t)n_karts * sizeof(hk_race_plan), cudaMemcpyHostToDevice, c->stream));
+    HK_CUDA(cudaMemcpyAsync(du, u, (size_t)n_karts * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    count_launch();
+    race_step_kernel<<<(n_karts + 127) / 128, 128, 0, c->stream>>>(t->dev, *p, n_karts, episode_step, du, 2, nullptr, nullptr, dk, dp);
+    HK_CUDA(cudaGetLastError());
+    HK_CUDA(cudaMemcpyAsync(karts, dk, (size_t)n_karts * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaMemcpyAsync(plans, dp, (size_t)n_karts * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    return HK_OK;
+}
+
+extern "C" int hk_race_run(const hk_track* t, const hk_race_params* p, int n_races, int first_step, int n_steps, hk_race_kart* karts,
+                           hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero)
+{
+    int rc = check_track(t, p, "hk_race_run");
+    if (rc) return rc;
+    if (n_races < 0 || n_steps < 0 || first_step < 0 || (n_races > 0 && (!karts || !plans))) {
+        set_error("hk_race_run: invalid argument");
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    if (lqng_status_nonzero) *lqng_status_nonzero = 0;
+    if (n_races == 0 || n_steps == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const size_t nb = (size_t)2 * n_races;                           // agents = problems per step
+    const size_t compact = nb * (8 + 8 + 8 + 2 + 4 + 8 + 6);
+    char* d = (char*)dscratch(c, 8, nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan) + sizeof(int)) + (compact + nb * 4) * sizeof(double) + 64);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    hk_race_kart* dk = (hk_race_kart*)d;
+    hk_race_plan* dp = (hk_race_plan*)(dk + nb);
+    double* o = (double*)(dp + nb);
+    double *dx0 = o, *dtg = dx0 + nb * 8, *dtw = dtg + nb * 8, *dcw = dtw + nb * 8, *daw = dcw + nb * 2, *dot = daw + nb * 4, *dow = dot + nb * 8;
+    double* du = dow + nb * 6;
+    unsigned long long* dcount = (unsigned long long*)(du + nb * 4);
+    int* dst = (int*)(dcount + 1);
+    cudaStream_t s = c->stream;
+    HK_CUDA(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
+    HK_CUDA(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
+    HK_CUDA(cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), s));
+    const unsigned blocks = (unsigned)((nb + 127) / 128);
+    for (int step = first_step; step < first_step + n_steps; ++step) {
+        if (step > 0 && step % p->planEvery == 0) {                  // HKA:334 (0.5 Hz)
+            count_launch();
+            race_plan_fixed_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp);
+        }
+        count_launch();
+        race_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp, dx0, dtg, dtw, dcw, daw, dot, dow);
+        HK_CUDA(cudaGetLastError());
+        rc = lqng_assemble_launch((int)nb, 2, p->horizon, p->dt, dx0, dtg, dtw, dcw, daw, dot, dow, du, dst, s, 9);
+        if (rc) return rc;
+        count_launch();
+        race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp);
+        HK_CUDA(cudaGetLastError());
+    }
+    HK_CUDA(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
+    HK_CUDA(cudaMemcpyAsync(plans, dp, nb * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, s));
+    unsigned long long count = 0;
+    HK_CUDA(cudaMemcpyAsync(&count, dcount, sizeof(count), cudaMemcpyDeviceToHost, s));
+    if (u_last) {
+        // u0 records are [problem][4] (ego controls first): compact to [race][2 agents][2] on the host side of the copy
+        double* hu = (double*)hscratch(c, 2, nb * 4 * sizeof(double));
+        if (!hu) return HK_ERR_OUT_OF_MEMORY;
+        HK_CUDA(cudaMemcpyAsync(hu, du, nb * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        HK_CUDA(cudaStreamSynchronize(s));
+        for (size_t b = 0; b < nb; ++b) { u_last[b * 2] = hu[b * 4]; u_last[b * 2 + 1] = hu[b * 4 + 1]; }
+    }
+    HK_CUDA(cudaStreamSynchronize(s));
+    if (lqng_status_nonzero) *lqng_status_nonzero = (int64_t)count;
+    return HK_OK;
+}

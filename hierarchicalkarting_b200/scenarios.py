@@ -18,6 +18,16 @@ DT = float(np.float32(0.02))            # (double)Time.fixedDeltaTime, HKA:707; 
 F32 = np.float32
 
 
+def _mathf_atan2(y, x):
+    """Mathf.Atan2(float, float) = (float)Math.Atan2((double)y, (double)x)."""
+    return np.arctan2(np.asarray(y, dtype=np.float32).astype(np.float64), np.asarray(x, dtype=np.float32).astype(np.float64)).astype(np.float32)
+
+
+def _mathf_pow(x, p):
+    """Mathf.Pow(float, float) = (float)Math.Pow((double)x, (double)p)."""
+    return np.power(np.asarray(x, dtype=np.float32).astype(np.float64), float(F32(p))).astype(np.float32)
+
+
 def _wrap2pi(a):
     return np.where(a < 0, a + F32(2) * F32(np.pi), a)
 
@@ -92,9 +102,9 @@ def make_problems(track: Track, batch: int, n_players: int, seed: int, slow_frac
     near = d_t <= np.where(straight[s0], F32(10.5), F32(7.5))             # HKA:823
     d_c = np.linalg.norm((trig[s1] - pos).astype(np.float32), axis=-1)     # stand-in for centerLine.ClosestPoint distance
     follow = near & (d_c <= 4.0)                                           # HKA:877-890: target the following checkpoint
-    f1 = np.arctan2((tl[..., 1] - pos[..., 1]).astype(np.float32), (tl[..., 0] - pos[..., 0]).astype(np.float32))
-    f2 = np.arctan2((nl[..., 1] - tl[..., 1]).astype(np.float32), (nl[..., 0] - tl[..., 0]).astype(np.float32))
-    f6 = np.arctan2((nl[..., 1] - pos[..., 1]).astype(np.float32), (nl[..., 0] - pos[..., 0]).astype(np.float32))
+    f1 = _mathf_atan2(tl[..., 1] - pos[..., 1], tl[..., 0] - pos[..., 0])
+    f2 = _mathf_atan2(nl[..., 1] - tl[..., 1], nl[..., 0] - tl[..., 0])
+    f6 = _mathf_atan2(nl[..., 1] - pos[..., 1], nl[..., 0] - pos[..., 0])
     f1w, f2w, f6w = _wrap2pi(f1).astype(np.float64), _wrap2pi(f2).astype(np.float64), _wrap2pi(f6).astype(np.float64)
     h0 = heading
     blend = f1w - _angle_difference(f2w, f1w) * float(F32(0.4))            # HKA:896
@@ -137,7 +147,7 @@ def make_problems(track: Track, batch: int, n_players: int, seed: int, slow_frac
             dist32 = np.linalg.norm((pos[:, o] - pos[:, i]).astype(np.float32), axis=-1).astype(np.float32)
             far = dist32 > 8
             m_eff = (mult / F32(2.0)) if is_mate else mult                 # multiplier2, HKA:1113
-            w32 = F32(1.0) / (np.power(dist32, F32(1.5)).astype(np.float32) * m_eff)   # 1f/(Mathf.Pow(d,1.5f)*mult), HKA:1019
+            w32 = F32(1.0) / (_mathf_pow(dist32, 1.5) * m_eff)              # 1f/(Mathf.Pow(d,1.5f)*mult), HKA:1019
             w = np.where(far, 0.0, w32.astype(np.float64))
             aw[:, i, k, 0] = w
             aw[:, i, k, 1] = w
@@ -167,7 +177,8 @@ def make_problems(track: Track, batch: int, n_players: int, seed: int, slow_frac
                 otw[:, i, k, 1] = np.where(far, 0.0, wxz)
                 otw[:, i, k, 2] = np.where(far, 0.0, wv)
     return dict(x0=x0, target=target, tw=tw, cw=cw, aw=aw, otgt=otgt, otw=otw, dt=DT, teams=teams, order=order,
-                track=track.name, seed=seed)
+                track=track.name, seed=seed,
+                sampled=dict(section=sec, tgt_lane=tgt_lane, nxt_lane=nxt_lane, bucket_max=bucket_max, nbucket_max=nbucket_max))
 
 
 def assemble_dense(prob: dict):
@@ -230,7 +241,7 @@ def _refresh_fixed(track, p):
     lanes_xy = track.lane_table()
     for i, ln in enumerate((3, 2)):
         tl = lanes_xy[1, ln - 1]
-        th = float(_wrap2pi(np.arctan2(F32(tl[1] - x0[0, i, 1]), F32(tl[0] - x0[0, i, 0]))))
+        th = float(_wrap2pi(_mathf_atan2(tl[1] - x0[0, i, 1], tl[0] - x0[0, i, 0])))
         h0 = x0[0, i, 3]
         p["target"][0, i] = [tl[0], tl[1], 15.0, h0 - _angle_difference(h0, th)]
         v = x0[0, i, 2]
@@ -239,7 +250,7 @@ def _refresh_fixed(track, p):
         o = 1 - i
         d = F32(np.linalg.norm((x0[0, o, :2] - x0[0, i, :2]).astype(np.float32)))
         mult = F32(1.0 if i == 0 else 1.3)
-        w = float(F32(1.0) / (F32(np.power(d, F32(1.5))) * mult)) if d <= 8 else 0.0
+        w = float(F32(1.0) / (_mathf_pow(d, 1.5) * mult)) if d <= 8 else 0.0
         p["aw"][0, i, 0] = [w, w]
         p["otgt"][0, i, 0] = [p["target"][0, o, 0], p["target"][0, o, 1], 15.0, 0.0]
         p["otw"][0, i, 0] = [0.2 / max(1.0, x0[0, i, 2]), 0.2 / max(1.0, x0[0, i, 2]), 0.08]

@@ -208,6 +208,82 @@ int hk_mcts_rollouts_multi(const hk_game* g, const hk_game_state* leaves, int n_
  * cdf_out[k] = P(index <= k) as a 32-bit threshold, exactly what the kernels sample from. cnt in 1..HK_MAX_ACTIONS. */
 int hk_policy_cdf(int cnt, uint32_t* cdf_out /* [cnt] */);
 
+/* ---- closed loop without PhysX: problem recipe + kinematic plant + checkpoint bookkeeping ---- */
+/*
+ * The reference closes its loop through Unity's PhysX ArcadeKart, which is out of scope; the planners themselves assume
+ * the kinematic model x += dt v cos h, z += dt v sin h, h += dt w, v += dt a (MPC/KartMPCDynamics.cs:55-70, the model
+ * LinearizedBicycle linearises, LQR/KartLQRDynamics.cs:40-62).  These entry points run that model for many independent
+ * 2-kart races entirely on the GPU: per step and per agent the LQNG problem recipe of HierarchicalKartAgent.SolveLQR
+ * (HierarchicalKartAgent.cs:699-1197, raycast-free branches), the solve, the actuator map (:1206-1224), the plant and
+ * the checkpoint bookkeeping of OnTriggerEnter (:611-662, lane by DiscretePositionTracker.CalculateLane :116-148).
+ */
+#define HK_MAX_SECTIONS 64       /* Oval has 24, Complex 41 */
+
+typedef struct hk_race_kart {    /* one kart of one race; 64 bytes */
+    double  x, z, v, h;          /* LQR state order (MPC/KartMPC.cs:13-20); h in [0, 2 pi) (HierarchicalKartAgent.cs:734-736) */
+    float   steer;               /* m_FinalStats.Steer (ArcadeKart.cs:300); max yaw rate = 0.4 steer (:505-510) */
+    int32_t section;             /* m_SectionIndex: grows without bound, used % n_sections (RacingEnvController.cs:758-784) */
+    int32_t lane;                /* m_Lane, 1..4 */
+    int32_t laneChanges;         /* m_LaneChanges */
+    int32_t illegalLaneChanges;  /* m_IllegalLaneChanges */
+    int32_t sectionStep;         /* sectionTimes[m_SectionIndex]: episodeSteps at the last crossing (:650) */
+    int32_t active;              /* 0 once the kart has reached goalSection (:651-654) */
+    int32_t pad_;
+} hk_race_kart;
+
+typedef struct hk_race_plan {    /* m_UpcomingLanes / m_UpcomingVelocities of one agent, keyed by section % n_sections */
+    int8_t lane[HK_MAX_SECTIONS];      /* 0 = key absent */
+    float  vel[HK_MAX_SECTIONS];
+    int8_t oppLane[HK_MAX_SECTIONS];   /* opponentUpcomingLanes[other] (filled from MCTS bestStates, HierarchicalKartAgent.cs:396-400) */
+    float  oppVel[HK_MAX_SECTIONS];
+} hk_race_plan;
+
+typedef struct hk_race_params {
+    double  dt;                  /* (double)Time.fixedDeltaTime = (double)0.02f */
+    float   accel, braking, coastingDrag, topSpeed;   /* ArcadeKart.Stats (7, 16, 5, 15) */
+    float   gateHalfWidth;       /* lateral half extent of a checkpoint trigger */
+    int32_t maxLaneChanges;      /* RacingEnvController.MaxLaneChanges */
+    int32_t goalSection;         /* RacingEnvController.goalSection = laps * n_sections */
+    int32_t highModeMcts;        /* HighLevelMode.MCTS (1) or Fixed (0): selects weights and the +2*bucket velocity margin */
+    int32_t velocityBucketSize, treeSearchDepth;      /* DiscreteGameParams */
+    int32_t planEvery;           /* the high level replans when episodeSteps % planEvery == 0 (100, :334) */
+    int32_t horizon;             /* LQNG horizon (3, :1201) */
+} hk_race_params;
+
+typedef struct hk_track hk_track;   /* immutable device-resident geometry */
+/* sections[n] as for hk_game_create; trigger_xz [n][2], forward_xz [n][2] (unit vector of the checkpoint's transform.forward
+ * in (x, z)), lane_xz [n][4][2] lane collider centres. */
+int  hk_track_create(const hk_section* sections, const double* trigger_xz, const double* forward_xz, const double* lane_xz,
+                     int n_sections, hk_track** out);
+void hk_track_destroy(hk_track* t);
+
+/*
+ * Problem recipe only (device-side K5 of SURVEY.md §7): for each of n_races races and each of its 2 agents builds the compact
+ * description hk_lqng_assemble_solve_batch takes.  Problem index = 2 race + ego; player 0 = ego, player 1 = the other kart.
+ * Host pointers.  Outputs [2 n_races][...] as documented at hk_lqng_assemble_solve_batch with N = 2.
+ */
+int hk_race_recipe(const hk_track* t, const hk_race_params* p, int n_races, const hk_race_kart* karts /* [n_races][2] */,
+                   const hk_race_plan* plans /* [n_races][2] */,
+                   double* x0, double* target, double* tw, double* cw, double* aw, double* otgt, double* otw);
+
+/* One plant + bookkeeping step for n_karts karts with the given controls u [n_karts][2] = (KartLQR output: acceleration
+ * command, angular velocity); karts and plans are updated in place (host pointers). */
+int hk_race_step(const hk_track* t, const hk_race_params* p, int n_karts, int episode_step, const double* u,
+                 hk_race_kart* karts, hk_race_plan* plans);
+
+/* planFixed (HierarchicalKartAgent.cs:145-166) for n_karts agents, in place. */
+int hk_race_plan_fixed(const hk_track* t, const hk_race_params* p, int n_karts, const hk_race_kart* karts, hk_race_plan* plans);
+
+/*
+ * The loop: n_steps steps (episodeSteps = first_step .. first_step + n_steps - 1) of n_races independent 2-kart races,
+ * device-resident between the initial upload and the final download of karts/plans: replan (Fixed high level) when
+ * episodeSteps % planEvery == 0 and > 0, recipe, assemble, LQNG solve, plant + bookkeeping.
+ * u_last [n_races][2][2] (may be NULL) receives the controls of the last step; lqng_status_nonzero (may be NULL) the number
+ * of solves that reported a zero pivot.
+ */
+int hk_race_run(const hk_track* t, const hk_race_params* p, int n_races, int first_step, int n_steps,
+                hk_race_kart* karts, hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero);
+
 #ifdef __cplusplus
 }
 #endif

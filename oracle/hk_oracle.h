@@ -39,6 +39,21 @@ int  hk_oracle_rollout(const hk_oracle_game* g, const hk_game_state* leaf, int m
                        hk_game_state* terminal);
 int  hk_oracle_rollouts(const hk_oracle_game* g, const hk_game_state* leaf, int64_t n_rollouts, int mode, uint64_t seed,
                         uint64_t rollout_offset, int64_t* visit, double* reward_sum, int64_t* nan_count, int64_t* plies_sum);
+/* closed loop without PhysX (hk_oracle_race.c): recipe, planFixed, plant + bookkeeping, the loop */
+void hk_oracle_race_recipe_one(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                               const hk_race_params* p, const hk_race_kart* karts, const hk_race_plan* plans, int e,
+                               double* x0, double* target, double* tw, double* cw, double* aw, double* otgt, double* otw);
+void hk_oracle_race_recipe(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                           const hk_race_params* p, int n_races, const hk_race_kart* karts, const hk_race_plan* plans,
+                           double* x0, double* target, double* tw, double* cw, double* aw, double* otgt, double* otw);
+void hk_oracle_race_plan_fixed(const hk_section* sections, int n_sections, const hk_race_params* p, int n_karts,
+                               const hk_race_kart* karts, hk_race_plan* plans);
+void hk_oracle_race_step(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                         const hk_race_params* p, int n_karts, int episode_step, const double* u, hk_race_kart* karts,
+                         hk_race_plan* plans);
+long long hk_oracle_race_run(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                             const hk_race_params* p, int n_races, int first_step, int n_steps, hk_race_kart* karts,
+                             hk_race_plan* plans, double* u_last);
 /* helpers for the KAT tests (track formulas) */
 float hk_oracle_distance_to_travel(const hk_section* s, int a, int b);
 float hk_oracle_radius_of_lane(const hk_section* s, int a, int b);

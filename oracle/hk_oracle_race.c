@@ -1,0 +1,238 @@
+/*
+ * hk_oracle_race.c — CPU ORACLE (test infrastructure, NOT the product) for the closed loop without PhysX
+ * (SURVEY.md §8f ranks 1-2, §3.3).  Plain C restatement of
+ *   - the LQNG problem recipe of HierarchicalKartAgent.SolveLQR, raycast-free branches
+ *     (Assets/Karting/Scripts/AI/HierarchicalKartAgent.cs:699-1197; initial states :730-736, targets :745-817, target-heading
+ *     rules :821-823, :877-890, :896-898, :919-923, own weights :930-962, avoid weights :999-1023, opponent target
+ *     weights :1089-1091, control weight :1192-1196),
+ *   - planFixed (:145-166),
+ *   - the actuator map (:1206-1224) on the kinematic model the planners assume (MPC/KartMPCDynamics.cs:55-70),
+ *   - the checkpoint bookkeeping of OnTriggerEnter (:611-662) with DiscretePositionTracker.CalculateLane (:116-148).
+ * Unity's Mathf.X(float...) is (float)Math.X(double...): float32-typed expressions are evaluated in double on the
+ * float32 inputs and rounded once.  PARITY UNPINNED by the reference (no tests, no .NET here): pinned instead by the
+ * independently written numpy recipe of hierarchicalkarting_b200/scenarios.py (tests/test_oracle_cpu.py).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "hk_oracle.h"
+
+static const float PI_F = 3.14159274f;                     /* Mathf.PI */
+
+static double angle_difference(double a1, double a2)       /* HierarchicalKartAgent.cs:1341-1344 */
+{
+    return atan2(sin(a2 - a1), cos(a2 - a1));
+}
+static float mathf_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
+static float magnitude2(float dx, float dz) { return (float)sqrt((double)(dx * dx + dz * dz)); }   /* Vector3.magnitude, dy = 0 */
+static float wrap2pi_f(float a) { return a < 0 ? a + 2 * PI_F : a; }
+
+typedef struct {
+    int n;
+    const hk_section* sec;
+    const double *trig, *fwd, *lane;
+} track_view;
+
+static int is_straight(const track_view* t, int section) { return t->sec[section % t->n].insideR == 0.0f; }
+
+/* target point / velocity of kart k for checkpoint index idx, from a lane plan (0 = key absent => Trigger, max speed) */
+static void plan_target(const track_view* t, const hk_race_params* p, const int8_t* lanes, const float* vels, int idx,
+                        double* xz, double* vel)
+{
+    const double max_speed = (double)p->topSpeed;          /* GetMaxSpeed(), ArcadeKart.cs:210 (TopSpeed > ReverseSpeed) */
+    if (lanes[idx] != 0) {
+        xz[0] = t->lane[(idx * 4 + lanes[idx] - 1) * 2];
+        xz[1] = t->lane[(idx * 4 + lanes[idx] - 1) * 2 + 1];
+        const double v = (double)vels[idx] + (p->highModeMcts ? p->velocityBucketSize * 2 : 0);
+        *vel = max_speed < v ? max_speed : v;
+    } else {
+        xz[0] = t->trig[idx * 2];
+        xz[1] = t->trig[idx * 2 + 1];
+        *vel = max_speed;
+    }
+}
+
+/* One problem: ego = karts[e], other = karts[1 - e].  Outputs: x0[2][4], target[2][4], tw[2][4], cw[2], aw[2][1][2],
+ * otgt[2][1][4], otw[2][1][3]. */
+void hk_oracle_race_recipe_one(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                               const hk_race_params* p, const hk_race_kart* karts, const hk_race_plan* plans, int e,
+                               double* x0, double* target, double* tw, double* cw, double* aw, double* otgt, double* otw)
+{
+    const track_view t = {n_sections, sections, trig, fwd, lane};
+    double tl[2][2], vel[2];
+    for (int i = 0; i < 2; ++i) {
+        const hk_race_kart* k = &karts[i == 0 ? e : 1 - e];
+        const int8_t* lanes = i == 0 ? plans[e].lane : plans[e].oppLane;      /* own plan / belief about the other (:745-817) */
+        const float* vels = i == 0 ? plans[e].vel : plans[e].oppVel;
+        x0[i * 4 + 0] = k->x; x0[i * 4 + 1] = k->z; x0[i * 4 + 2] = k->v; x0[i * 4 + 3] = k->h;     /* :730-736 */
+        const int s = k->section + 1;                                           /* :745 */
+        const int idx = s % t.n, idx2 = (s + 1) % t.n;
+        double nl[2], nvel;
+        plan_target(&t, p, lanes, vels, idx, tl[i], &vel[i]);
+        plan_target(&t, p, lanes, vels, idx2, nl, &nvel);
+        const int stopped = (float)k->v <= 5.0f;                                /* :808 */
+        double tx = tl[i][0], tz = tl[i][1], tv = stopped ? 0.0 : vel[i];
+        const float d_t = magnitude2((float)(tl[i][0] - k->x), (float)(tl[i][1] - k->z));
+        const int near = d_t <= (is_straight(&t, k->section) ? 10.5f : 7.5f);   /* :823 */
+        const float d_c = magnitude2((float)(t.trig[idx * 2] - k->x), (float)(t.trig[idx * 2 + 1] - k->z));
+        const int follow = near && (d_c <= 4.0f);                               /* :877-890, centre-line distance stand-in */
+        const double f1w = (double)wrap2pi_f(mathf_atan2((float)(tl[i][1] - k->z), (float)(tl[i][0] - k->x)));
+        const double f2w = (double)wrap2pi_f(mathf_atan2((float)(nl[1] - tl[i][1]), (float)(nl[0] - tl[i][0])));
+        const double f6w = (double)wrap2pi_f(mathf_atan2((float)(nl[1] - k->z), (float)(nl[0] - k->x)));
+        const double h0 = k->h;
+        double blend = f1w - angle_difference(f2w, f1w) * (double)0.4f;         /* :896 */
+        if (blend < 0) blend += 2 * (double)PI_F;
+        double th;
+        if (follow) th = h0 - angle_difference(h0, f6w);                        /* :887 */
+        else if (near) th = h0 - angle_difference(h0, blend);                   /* :898 */
+        else th = h0 - angle_difference(h0, f1w);                               /* :921 */
+        if (follow) { tx = nl[0]; tz = nl[1]; if (!stopped) tv = nvel; }
+        target[i * 4 + 0] = tx; target[i * 4 + 1] = tz; target[i * 4 + 2] = tv; target[i * 4 + 3] = th;
+        /* own target weights, 2-agent branch (:930-962) */
+        const double vmax1 = k->v > 1.0 ? k->v : 1.0;
+        const double w_xz = stopped ? 0.3 * 3.1 : 0.3 * 3.1 / vmax1;
+        tw[i * 4 + 0] = w_xz; tw[i * 4 + 1] = w_xz;
+        tw[i * 4 + 2] = stopped ? -2.0 : 5e-4;
+        tw[i * 4 + 3] = p->highModeMcts ? 3.5 : 1.9;
+        cw[i] = 0.115;                                                          /* :1192-1196 */
+    }
+    for (int i = 0; i < 2; ++i) {                                               /* avoid + opponent-target weights (:964-1190) */
+        const int o = 1 - i;
+        const hk_race_kart* ki = &karts[i == 0 ? e : 1 - e];
+        const hk_race_kart* ko = &karts[o == 0 ? e : 1 - e];
+        const float mult = i == 0 ? 1.0f : 1.3f;                                /* :999-1002 */
+        const float dist = magnitude2((float)(ko->x - ki->x), (float)(ko->z - ki->z));
+        const int far = dist > 8;
+        const float w32 = 1.0f / ((float)pow((double)dist, (double)1.5f) * mult);   /* 1f/(Mathf.Pow(d,1.5f)*mult), :1019 */
+        const double w = far ? 0.0 : (double)w32;
+        aw[i * 2 + 0] = w; aw[i * 2 + 1] = w;
+        otgt[i * 4 + 0] = tl[o][0]; otgt[i * 4 + 1] = tl[o][1]; otgt[i * 4 + 2] = vel[o]; otgt[i * 4 + 3] = 0.0;
+        const double vmax1 = ki->v > 1.0 ? ki->v : 1.0;
+        const double wxz = (p->highModeMcts ? 0.2 : 0.1) / vmax1;               /* :1089-1091 */
+        otw[i * 3 + 0] = far ? 0.0 : wxz; otw[i * 3 + 1] = far ? 0.0 : wxz; otw[i * 3 + 2] = far ? 0.0 : 0.08;
+    }
+}
+
+void hk_oracle_race_recipe(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                           const hk_race_params* p, int n_races, const hk_race_kart* karts, const hk_race_plan* plans,
+                           double* x0, double* target, double* tw, double* cw, double* aw, double* otgt, double* otw)
+{
+    for (int r = 0; r < n_races; ++r)
+        for (int e = 0; e < 2; ++e) {
+            const size_t b = (size_t)2 * r + e;
+            hk_oracle_race_recipe_one(sections, trig, fwd, lane, n_sections, p, karts + 2 * r, plans + 2 * r, e, x0 + b * 8,
+                                      target + b * 8, tw + b * 8, cw + b * 2, aw + b * 4, otgt + b * 8, otw + b * 6);
+        }
+}
+
+/* planFixed (:145-166) */
+void hk_oracle_race_plan_fixed(const hk_section* sections, int n_sections, const hk_race_params* p, int n_karts,
+                               const hk_race_kart* karts, hk_race_plan* plans)
+{
+    for (int k = 0; k < n_karts; ++k) {
+        if (!karts[k].active) continue;
+        const int s = karts[k].section;
+        const int hi = s + p->treeSearchDepth < 1000 ? s + p->treeSearchDepth : 1000;
+        for (int i = s + 1; i < hi + 1; ++i) {
+            const int key = i % n_sections;
+            if (plans[k].lane[key] == 0) {
+                plans[k].lane[key] = (int8_t)sections[(i - 1) % n_sections].optimalLane;      /* getOptimalNextLane */
+                plans[k].vel[key] = p->topSpeed;                                               /* GetMaxSpeed() */
+            }
+        }
+    }
+}
+
+/* actuator map (:1206-1224) + kinematic plant (KartMPCDynamics.cs:55-70) + OnTriggerEnter bookkeeping (:611-662) */
+void hk_oracle_race_step(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                         const hk_race_params* p, int n_karts, int episode_step, const double* u, hk_race_kart* karts,
+                         hk_race_plan* plans)
+{
+    const track_view t = {n_sections, sections, trig, fwd, lane};
+    const double TWO_PI = 6.283185307179586;
+    for (int i = 0; i < n_karts; ++i) {
+        hk_race_kart* k = &karts[i];
+        if (!k->active) continue;
+        const float max_ang = k->steer * 0.4f;                                  /* getMaxAngularVelocity, ArcadeKart.cs:505-510 */
+        float ang = (float)u[i * 2 + 1];
+        ang = ang < -max_ang ? -max_ang : (ang > max_ang ? max_ang : ang);      /* Mathf.Clamp :1206 */
+        int accel = 0, brake = 0;
+        if (u[i * 2] < 0) brake = 1;
+        else if (u[i * 2] > 0) accel = 1;
+        else ang = 0.0f;
+        const float steering = ang / (0.4f * k->steer);                         /* m_Steering :1224 */
+        const float turning_power = steering * k->steer * (fabsf((float)k->v) > 0.5f ? 1.0f : 0.0f);   /* ArcadeKart.cs:406 */
+        const double omega = (double)(turning_power * 0.4f);
+        const double x_old = k->x, z_old = k->z;
+        k->x = x_old + p->dt * k->v * cos(k->h);
+        k->z = z_old + p->dt * k->v * sin(k->h);
+        /* Unity's yaw is left-handed: a positive TurnInput turns the kart clockwise seen from above, i.e. the solver's heading
+         * atan2(forward.z, forward.x) DEcreases.  SolveLQR compensates by mirroring the target heading about the current one
+         * (h0 - AngleDifference(h0, target) = 2 h0 - target, :887,:898,:921), so the stand-in must turn like Unity does. */
+        double h = k->h - p->dt * omega;
+        if (h < 0) h += TWO_PI;
+        if (h >= TWO_PI) h -= TWO_PI;
+        double v = k->v;
+        if (accel) { v += p->dt * (double)p->accel; if (v > (double)p->topSpeed) v = (double)p->topSpeed; }
+        else if (brake) { v -= p->dt * (double)p->braking; if (v < 0) v = 0; }
+        else { v -= p->dt * (double)p->coastingDrag; if (v < 0) v = 0; }       /* MoveTowards(v, 0, dt CoastingDrag), ArcadeKart.cs:431 */
+        k->h = h; k->v = v;
+        /* did the kart enter the trigger of checkpoint section+1 during this step? */
+        const int index = k->section + 1, c = index % t.n;
+        const double fx = t.fwd[c * 2], fz = t.fwd[c * 2 + 1];
+        const double s_old = (x_old - t.trig[c * 2]) * fx + (z_old - t.trig[c * 2 + 1]) * fz;
+        const double s_new = (k->x - t.trig[c * 2]) * fx + (k->z - t.trig[c * 2 + 1]) * fz;
+        const double lat = -(k->x - t.trig[c * 2]) * fz + (k->z - t.trig[c * 2 + 1]) * fx;
+        if (s_old < 0 && s_new >= 0 && fabs(lat) <= (double)p->gateHalfWidth) {
+            int lane_new = 1;                                                   /* CalculateLane: first minimum */
+            float best = 0;
+            for (int l = 0; l < 4; ++l) {
+                const float d = magnitude2((float)(k->x - t.lane[(c * 4 + l) * 2]), (float)(k->z - t.lane[(c * 4 + l) * 2 + 1]));
+                if (l == 0 || d < best) { best = d; lane_new = l + 1; }
+            }
+            hk_race_plan* pl = &plans[i];
+            pl->lane[c] = 0;                                                    /* m_UpcomingLanes.Remove (:631-632) */
+            pl->vel[c] = 0.0f;
+            const int dl = abs(k->lane - lane_new);
+            if (k->laneChanges + dl > p->maxLaneChanges && is_straight(&t, k->section)) k->illegalLaneChanges += 1;   /* :638-642 */
+            if (is_straight(&t, k->section) != is_straight(&t, index)) k->laneChanges = 0;                           /* :643-646 */
+            else if (k->lane != lane_new) k->laneChanges += dl;                                                        /* :647-650 */
+            k->section = index;
+            k->lane = lane_new;
+            k->sectionStep = episode_step;
+            if (k->section == p->goalSection) k->active = 0;                    /* ReachGoalSection (:652-655) */
+        }
+    }
+}
+
+/* the loop of hk_race_run; returns the number of solves with non-zero status */
+long long hk_oracle_race_run(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                             const hk_race_params* p, int n_races, int first_step, int n_steps, hk_race_kart* karts,
+                             hk_race_plan* plans, double* u_last)
+{
+    long long bad = 0;
+    for (int step = first_step; step < first_step + n_steps; ++step) {
+        if (step > 0 && step % p->planEvery == 0) hk_oracle_race_plan_fixed(sections, n_sections, p, 2 * n_races, karts, plans);
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+        for (int r = 0; r < n_races; ++r) {
+            double u[4];
+            for (int e = 0; e < 2; ++e) {
+                double x0[8], target[8], tw[8], cw[2], aw[4], otgt[8], otw[6];
+                hk_oracle_race_recipe_one(sections, trig, fwd, lane, n_sections, p, karts + 2 * r, plans + 2 * r, e, x0, target, tw,
+                                          cw, aw, otgt, otw);
+                double A[2 * 16], B[2 * 8], Q[2 * 64], q[2 * 8], R[2 * 4], u0[4];
+                for (int i = 0; i < 2; ++i) {
+                    hk_oracle_bicycle_A(p->dt, x0 + 4 * i, A + 16 * i);
+                    hk_oracle_bicycle_B(p->dt, B + 8 * i);
+                    hk_oracle_cost(1, target + 4 * i, tw + 4 * i, cw[i], aw + 2 * i, otgt + 4 * i, otw + 3 * i, Q + 64 * i, q + 8 * i,
+                                   R + 4 * i);
+                }
+                bad += hk_oracle_lqng_solve(2, p->horizon, 0, A, B, Q, q, R, x0, u0, NULL, NULL, NULL) != 0;
+                u[2 * e] = u0[0]; u[2 * e + 1] = u0[1];
+            }
+            if (u_last) memcpy(u_last + 4 * (size_t)r, u, sizeof(u));
+            hk_oracle_race_step(sections, trig, fwd, lane, n_sections, p, 2, step, u, karts + 2 * r, plans + 2 * r);
+        }
+    }
+    return bad;
+}

@@ -19,7 +19,7 @@ _dp, _ip, _lp, _fp, _up = (C.POINTER(t) for t in (C.c_double, C.c_int32, C.c_int
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("hk_oracle_lqng.c", "hk_oracle_game.c", "hk_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("hk_oracle_lqng.c", "hk_oracle_game.c", "hk_oracle_race.c", "hk_oracle.h", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -191,3 +191,45 @@ def philox(seed, c0, c1, c2, c3) -> np.ndarray:
     out = np.zeros(4, dtype=np.uint32)
     lib().hk_oracle_philox4x32_10(seed, c0, c1, c2, c3, out.ctypes.data_as(_up))
     return out
+
+
+# ---- closed loop without PhysX (hk_oracle_race.c) ---------------------------------------------------------------
+class Races:
+    """Oracle twin of hierarchicalkarting_b200.race.Races (same array layouts)."""
+
+    def __init__(self, sections, trig, fwd, lane, n_sections, params):
+        self.sections, self.n = sections, n_sections
+        self.trig, self.fwd, self.lane = (np.ascontiguousarray(a, dtype=np.float64) for a in (trig, fwd, lane))
+        self.params = params
+        L = lib()
+        vp = C.c_void_p
+        geo = [C.POINTER(abi.hk_section), _dp, _dp, _dp, C.c_int, C.POINTER(abi.hk_race_params)]
+        L.hk_oracle_race_recipe.argtypes = geo + [C.c_int, vp, vp] + [_dp] * 7
+        L.hk_oracle_race_plan_fixed.argtypes = [C.POINTER(abi.hk_section), C.c_int, C.POINTER(abi.hk_race_params), C.c_int, vp, vp]
+        L.hk_oracle_race_step.argtypes = geo + [C.c_int, C.c_int, _dp, vp, vp]
+        L.hk_oracle_race_run.argtypes = geo + [C.c_int, C.c_int, C.c_int, vp, vp, _dp]
+        L.hk_oracle_race_run.restype = C.c_longlong
+
+    def _geo(self):
+        return [self.sections, _p(self.trig), _p(self.fwd), _p(self.lane), self.n, C.byref(self.params)]
+
+    def recipe(self, karts, plans):
+        nb = 2 * karts.shape[0]
+        out = dict(x0=np.zeros((nb, 2, 4)), target=np.zeros((nb, 2, 4)), tw=np.zeros((nb, 2, 4)), cw=np.zeros((nb, 2)),
+                   aw=np.zeros((nb, 2, 1, 2)), otgt=np.zeros((nb, 2, 1, 4)), otw=np.zeros((nb, 2, 1, 3)))
+        lib().hk_oracle_race_recipe(*self._geo(), karts.shape[0], abi.vptr(karts), abi.vptr(plans),
+                                    *(_p(out[k]) for k in ("x0", "target", "tw", "cw", "aw", "otgt", "otw")))
+        out["dt"] = self.params.dt
+        return out
+
+    def plan_fixed(self, karts, plans):
+        lib().hk_oracle_race_plan_fixed(self.sections, self.n, C.byref(self.params), karts.size, abi.vptr(karts), abi.vptr(plans))
+
+    def step(self, karts, plans, u, episode_step):
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(karts.size, 2)
+        lib().hk_oracle_race_step(*self._geo(), karts.size, episode_step, _p(u), abi.vptr(karts), abi.vptr(plans))
+
+    def run(self, karts, plans, first_step, n_steps):
+        u = np.zeros((karts.shape[0], 2, 2))
+        bad = lib().hk_oracle_race_run(*self._geo(), karts.shape[0], first_step, n_steps, abi.vptr(karts), abi.vptr(plans), _p(u))
+        return u, int(bad)

@@ -1,0 +1,108 @@
+"""CPU tests of the closed-loop ORACLE (oracle/hk_oracle_race.c): the C restatement of the SolveLQR problem recipe is pinned
+by the independently written numpy recipe of scenarios.make_problems; planFixed / plant / checkpoint bookkeeping are checked on
+hand-built cases; the loop is checked through size-independent properties (monotone sections, finish, freeze)."""
+import numpy as np
+import pytest
+
+from hierarchicalkarting_b200 import abi, race as R, scenarios as S
+
+
+def _oracle_races(oracle, track, **kw):
+    prm = R.race_params(track, **kw)
+    sec, trig, fwd, lane = R.geometry(track)
+    return oracle.Races(sec, trig, fwd, lane, track.n_sections, prm), prm
+
+
+def karts_from_problems(p, track):
+    """Race state whose (race, ego 0) recipe must reproduce make_problems: same states, the sampled lanes / velocities as the
+    ego's own plan and as its belief about the other kart."""
+    sm, batch, L = p["sampled"], p["x0"].shape[0], track.n_sections
+    karts = np.zeros((batch, 2), dtype=abi.RACE_KART_DTYPE)
+    plans = np.zeros((batch, 2), dtype=abi.RACE_PLAN_DTYPE)
+    for i in range(2):
+        for c, k in enumerate(("x", "z", "v", "h")):
+            karts[k][:, i] = p["x0"][:, i, c]
+        karts["section"][:, i] = sm["section"]
+    karts["active"], karts["steer"], karts["lane"] = 1, 3.25, 2
+    s1, s2, rows = (sm["section"] + 1) % L, (sm["section"] + 2) % L, np.arange(batch)
+    for own, lk, vk in ((0, "lane", "vel"), (1, "oppLane", "oppVel")):
+        plans[lk][rows, 0, s1] = sm["tgt_lane"][:, own]; plans[vk][rows, 0, s1] = sm["bucket_max"][:, own]
+        plans[lk][rows, 0, s2] = sm["nxt_lane"][:, own]; plans[vk][rows, 0, s2] = sm["nbucket_max"][:, own]
+    return karts, plans
+
+
+@pytest.mark.parametrize("track", [S.OVAL, S.COMPLEX])
+@pytest.mark.parametrize("mcts", [True, False])
+def test_oracle_recipe_equals_numpy_recipe(oracle, track, mcts):
+    p = S.make_problems(track, 3000, 2, seed=7, high_mode_mcts=mcts)
+    karts, plans = karts_from_problems(p, track)
+    OR, _ = _oracle_races(oracle, track, high_mode_mcts=mcts)
+    out = OR.recipe(karts, plans)
+    for k in ("x0", "tw", "cw", "aw", "otgt", "otw"):
+        assert np.array_equal(out[k][0::2], p[k]), k
+    assert np.max(np.abs(out["target"][0::2] - p["target"])) <= 1e-14      # libm vs numpy sin/cos in AngleDifference
+    # all three target-heading branches and the stopped branch are exercised
+    d_t = np.linalg.norm((p["target"][:, 0, :2] - p["x0"][:, 0, :2]), axis=-1)
+    assert (p["x0"][:, :, 2] <= 5).any() and (d_t > 10.5).any() and (d_t < 7.5).any()
+
+
+def test_plan_fixed_and_absent_plan_targets(oracle):
+    track = S.OVAL
+    OR, prm = _oracle_races(oracle, track)
+    karts, plans = R.start_grid(track, 4, seed=1)
+    out = OR.recipe(karts, plans)
+    assert np.allclose(out["target"][:, 0, :2], track.trigger_table()[1])          # no plan: Trigger of section+1 (HKA:762-766)
+    assert np.all(out["target"][:, 0, 2] == 0.0)                                   # v <= 5: target speed 0 (HKA:808)
+    karts["section"][0, 0] = 20
+    plans["lane"][0, 0, 22] = 1                                                    # an existing key is kept
+    OR.plan_fixed(karts, plans)
+    want = [track.rows[(i - 1) % 24][6] for i in range(21, 29)]
+    got = [int(plans["lane"][0, 0, i % 24]) for i in range(21, 29)]
+    want[1] = 1
+    assert got == want and np.all(plans["vel"][0, 0, [i % 24 for i in range(21, 29) if i != 22]] == 15.0)
+    assert plans["lane"][0, 0, 5] == 0 and plans["lane"][0, 0, 20] == 0
+    assert [int(plans["lane"][1, 1, i]) for i in range(1, 9)] == [track.rows[i - 1][6] for i in range(1, 9)]
+
+
+def test_step_bookkeeping_hand_cases(oracle):
+    track = S.OVAL
+    OR, prm = _oracle_races(oracle, track)
+    karts, plans = R.start_grid(track, 1, seed=1)
+    k = karts[0]
+    # kart 0: 0.1 m before gate 1 (z = 7.9) near lane 4, driving up at 10 m/s; kart 1: stays far from any gate
+    k["x"][0], k["z"][0], k["v"][0], k["h"][0], k["lane"][0], k["laneChanges"][0] = 19.3, 7.8, 10.0, np.pi / 2, 2, 2
+    plans["lane"][0, 0, 1], plans["vel"][0, 0, 1] = 4, 12.0
+    before1 = karts[0, 1].copy()
+    OR.step(karts, plans, np.array([[1.0, 0.0], [0.0, 0.0]]), 77)
+    assert k["section"][0] == 1 and k["lane"][0] == 4 and k["sectionStep"][0] == 77
+    assert k["illegalLaneChanges"][0] == 1 and k["laneChanges"][0] == 4            # 2 + |2-4| > 3 on a straight (HKA:638-650)
+    assert plans["lane"][0, 0, 1] == 0                                              # key consumed (HKA:631-632)
+    assert abs(k["v"][0] - (10.0 + prm.dt * 7.0)) < 1e-12 and abs(k["z"][0] - (7.8 + prm.dt * 10.0)) < 1e-12
+    # u0 == 0: coasting and no steering (HKA:1216-1221); kart 1 only coasts
+    assert karts[0, 1]["section"] == 0 and karts[0, 1]["h"] == before1["h"]
+    assert abs(karts[0, 1]["v"] - max(0.0, before1["v"] - prm.dt * 5.0)) < 1e-12
+    # steering: positive angular-velocity command turns clockwise (Unity yaw), clamped to 0.4 steer
+    h0 = float(k["h"][0])
+    OR.step(karts, plans, np.array([[-1.0, 9.0], [0.0, 0.0]]), 78)
+    assert abs(k["h"][0] - (h0 - prm.dt * float(np.float32(0.4) * np.float32(3.25)))) < 1e-7 and k["v"][0] < 10.14
+    # straight -> curve resets the counter (HKA:643-646): gate 4 of the Oval starts the first curve
+    k["section"][0], k["lane"][0], k["laneChanges"][0] = 3, 3, 3
+    k["x"][0], k["z"][0], k["h"][0] = 17.1, 38.1, np.pi / 2
+    OR.step(karts, plans, np.array([[1.0, 0.0], [0.0, 0.0]]), 79)
+    assert k["section"][0] == 4 and k["laneChanges"][0] == 0
+
+
+@pytest.mark.parametrize("track", [S.OVAL, S.COMPLEX])
+def test_loop_properties(oracle, track):
+    OR, prm = _oracle_races(oracle, track, laps=1)
+    karts, plans = R.start_grid(track, 32, seed=11)
+    last = karts["section"].copy()
+    for blk in range(16):
+        _, bad = OR.run(karts, plans, blk * 200, 200)
+        assert bad == 0 and np.all(karts["section"] >= last) and np.all(np.isfinite(karts["x"]))
+        assert np.all((karts["v"] >= 0) & (karts["v"] <= 15.0)) and np.all((karts["h"] >= 0) & (karts["h"] < 2 * np.pi))
+        last = karts["section"].copy()
+    assert np.all(karts["active"] == 0) and np.all(karts["section"] == prm.goalSection)    # everybody finished one lap
+    frozen = karts.copy()
+    OR.run(karts, plans, 3200, 50)
+    assert np.array_equal(frozen, karts)                                                   # finished karts do not move

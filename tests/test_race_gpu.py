@@ -1,0 +1,116 @@
+"""GPU parity of the closed loop without PhysX (hk_race.cu) against the CPU oracle (oracle/hk_oracle_race.c), through the
+C-ABI.  Integers (section, lane, counters, plan keys) bit-exact; doubles within 1e-9 (BASELINE.json north_star tolerance),
+in practice ~1e-15 (device vs host libm)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from hierarchicalkarting_b200 import abi, race as R, scenarios as S
+from test_race_cpu import _oracle_races, karts_from_problems
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+INT_FIELDS = ("section", "lane", "laneChanges", "illegalLaneChanges", "sectionStep", "active")
+DBL_FIELDS = ("x", "z", "v", "h")
+
+
+def _same(gk, gp, ok, op, tol=TOL):
+    for f in INT_FIELDS:
+        assert np.array_equal(gk[f], ok[f]), f
+    for f in DBL_FIELDS:
+        assert np.max(np.abs(gk[f] - ok[f])) <= tol * max(1.0, float(np.max(np.abs(ok[f])))), f
+    for f in ("lane", "vel", "oppLane", "oppVel"):
+        assert np.array_equal(gp[f], op[f]), f
+
+
+@pytest.mark.parametrize("track", [S.OVAL, S.COMPLEX])
+@pytest.mark.parametrize("mcts", [True, False])
+def test_recipe_parity(hk, oracle, track, mcts):
+    p = S.make_problems(track, 2001, 2, seed=17, high_mode_mcts=mcts)          # ragged size
+    karts, plans = karts_from_problems(p, track)
+    plans[:, 1] = plans[:, 0]                                                   # give the second agent a plan too
+    OR, prm = _oracle_races(oracle, track, high_mode_mcts=mcts)
+    G = R.Races(track, prm)
+    ref, got = OR.recipe(karts, plans), G.recipe(karts, plans)
+    for k in ("x0", "tw", "cw", "aw", "otgt", "otw"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.max(np.abs(got["target"] - ref["target"])) <= 1e-13
+    # and the assembled problems solve to the same controls
+    from hierarchicalkarting_b200 import lqr
+    u_g = lqr.assemble_solve_batch(got, 3)["u0"]
+    u_o = oracle.lqng_solve_batch(*S.assemble_dense(ref), 3, full=False)["u0"]
+    for b in range(0, u_o.shape[0], 7):
+        assert rel_err(u_g[b], u_o[b]) <= TOL
+
+
+def test_plan_fixed_and_step_parity(hk, oracle):
+    rng = np.random.default_rng(5)
+    for track in (S.OVAL, S.COMPLEX):
+        OR, prm = _oracle_races(oracle, track)
+        G = R.Races(track, prm)
+        n = 4097
+        karts, plans = R.start_grid(track, n, seed=9)
+        L = track.n_sections
+        # scatter the karts just before / after / far from their next gate, with every kind of control
+        sec = rng.integers(0, 3 * L, size=(n, 2))
+        c = (sec + 1) % L
+        trig, head = track.trigger_table(), track.heading_table()
+        fwd = np.stack([np.cos(head), np.sin(head)], axis=-1)
+        along = rng.choice([-0.05, -0.15, -0.4, 0.1, -3.0], size=(n, 2))
+        lat = rng.uniform(-12.0, 12.0, size=(n, 2))
+        karts["x"] = trig[c, 0] + fwd[c, 0] * along - fwd[c, 1] * lat
+        karts["z"] = trig[c, 1] + fwd[c, 1] * along + fwd[c, 0] * lat
+        karts["v"] = rng.uniform(0.0, 15.0, size=(n, 2))
+        karts["h"] = np.mod(head[c] + rng.normal(0, 0.3, size=(n, 2)), 2 * np.pi)
+        karts["section"], karts["lane"] = sec, rng.integers(1, 5, size=(n, 2))
+        karts["laneChanges"] = rng.integers(0, 5, size=(n, 2))
+        karts["active"] = rng.random((n, 2)) < 0.95
+        karts["section"][0, 0] = prm.goalSection - 1                            # one kart finishes
+        plans["lane"] = rng.integers(0, 5, size=plans["lane"].shape)
+        plans["vel"] = rng.integers(6, 16, size=plans["vel"].shape)
+        u = rng.normal(0, 3, size=(n, 2, 2))
+        u[rng.random((n, 2)) < 0.2, 0] = 0.0                                    # coasting branch
+        gk, gp, ok, op = karts.copy(), plans.copy(), karts.copy(), plans.copy()
+        G.plan_fixed(gk, gp); OR.plan_fixed(ok, op)
+        _same(gk, gp, ok, op)
+        assert not np.array_equal(gp["lane"], plans["lane"])
+        G.step(gk, gp, u, 123); OR.step(ok, op, u, 123)
+        _same(gk, gp, ok, op, tol=1e-13)
+        assert (ok["section"] != karts["section"]).mean() > 0.1                 # many crossings happened
+        assert (ok["illegalLaneChanges"] > 0).any() and (ok["laneChanges"] != karts["laneChanges"]).any()
+
+
+@pytest.mark.parametrize("track", [S.OVAL, S.COMPLEX])
+def test_run_parity(hk, oracle, track):
+    """The whole loop (replan, recipe, assemble, solve, actuator, plant, bookkeeping) for 96 races x 600 steps, re-synchronised
+    with the oracle every 100 steps so that rounding differences cannot move a checkpoint crossing to another step."""
+    OR, prm = _oracle_races(oracle, track)
+    G = R.Races(track, prm)
+    karts, plans = R.start_grid(track, 96, seed=23)
+    for blk in range(6):
+        gk, gp = karts.copy(), plans.copy()
+        u_g, bad_g = G.run(gk, gp, blk * 100, 100)
+        u_o, bad_o = OR.run(karts, plans, blk * 100, 100)
+        assert bad_g == bad_o == 0
+        _same(gk, gp, karts, plans, tol=1e-9)
+        assert np.max(np.abs(u_g - u_o)) <= 1e-8 * max(1.0, float(np.max(np.abs(u_o))))
+    assert karts["section"].min() >= 8
+
+
+def test_full_size_properties(hk):
+    """BASELINE config 5 size (16,384 Oval races): determinism, monotone progress, bounded states, every solve regular."""
+    track = S.OVAL
+    G = R.Races(track, R.race_params(track))
+    karts, plans = R.start_grid(track, 16384, seed=20260004)
+    a_k, a_p = karts.copy(), plans.copy()
+    _, bad = G.run(a_k, a_p, 0, 300)
+    b_k, b_p = karts.copy(), plans.copy()
+    G.run(b_k, b_p, 0, 150)
+    G.run(b_k, b_p, 150, 150)                                                   # split runs give the same races
+    assert bad == 0 and np.array_equal(a_k, b_k) and np.array_equal(a_p, b_p)
+    assert np.all(a_k["section"] >= 3) and np.all(a_k["section"] <= 8)
+    assert np.all(np.isfinite(a_k["x"])) and np.all((a_k["v"] >= 0) & (a_k["v"] <= 15)) and np.all((a_k["h"] >= 0) & (a_k["h"] < 2 * np.pi))
+    perm = np.random.default_rng(0).permutation(16384)
+    c_k, c_p = np.ascontiguousarray(karts[perm]), np.ascontiguousarray(plans[perm])
+    G.run(c_k, c_p, 0, 300)
+    assert np.array_equal(c_k, a_k[perm])                                       # races are independent
