@@ -33,6 +33,7 @@ namespace KartGame.AI.Native
     [StructLayout(LayoutKind.Sequential)] public unsafe struct HkRacePlan
     {
         public fixed sbyte lane[64]; public fixed float vel[64]; public fixed sbyte oppLane[64]; public fixed float oppVel[64];
+        public fixed int sectionTimes[64]; public fixed int lapStep[8]; public float avgLaneDiff, avgVelDiff;
     }
     [StructLayout(LayoutKind.Sequential)] public struct HkRaceParams
     {

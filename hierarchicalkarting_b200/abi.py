@@ -18,6 +18,7 @@ HK_MAX_KARTS = 4
 HK_MAX_ACTIONS = 36
 HK_MAX_PLIES = 64
 HK_MAX_SECTIONS = 64
+HK_MAX_LAPS = 8
 
 HK_OK = 0
 HK_ERR_INVALID_ARGUMENT = -1
@@ -77,7 +78,9 @@ class hk_race_kart(C.Structure):
 
 class hk_race_plan(C.Structure):
     _fields_ = [("lane", C.c_int8 * HK_MAX_SECTIONS), ("vel", C.c_float * HK_MAX_SECTIONS),
-                ("oppLane", C.c_int8 * HK_MAX_SECTIONS), ("oppVel", C.c_float * HK_MAX_SECTIONS)]
+                ("oppLane", C.c_int8 * HK_MAX_SECTIONS), ("oppVel", C.c_float * HK_MAX_SECTIONS),
+                ("sectionTimes", C.c_int32 * HK_MAX_SECTIONS), ("lapStep", C.c_int32 * HK_MAX_LAPS),
+                ("avgLaneDiff", C.c_float), ("avgVelDiff", C.c_float)]
 
 
 class hk_race_params(C.Structure):
@@ -92,9 +95,11 @@ RACE_KART_DTYPE = np.dtype([("x", np.float64), ("z", np.float64), ("v", np.float
                             ("section", np.int32), ("lane", np.int32), ("laneChanges", np.int32),
                             ("illegalLaneChanges", np.int32), ("sectionStep", np.int32), ("active", np.int32), ("pad_", np.int32)])
 RACE_PLAN_DTYPE = np.dtype([("lane", np.int8, (HK_MAX_SECTIONS,)), ("vel", np.float32, (HK_MAX_SECTIONS,)),
-                            ("oppLane", np.int8, (HK_MAX_SECTIONS,)), ("oppVel", np.float32, (HK_MAX_SECTIONS,))])
+                            ("oppLane", np.int8, (HK_MAX_SECTIONS,)), ("oppVel", np.float32, (HK_MAX_SECTIONS,)),
+                            ("sectionTimes", np.int32, (HK_MAX_SECTIONS,)), ("lapStep", np.int32, (HK_MAX_LAPS,)),
+                            ("avgLaneDiff", np.float32), ("avgVelDiff", np.float32)])
 assert RACE_KART_DTYPE.itemsize == C.sizeof(hk_race_kart) == 64
-assert RACE_PLAN_DTYPE.itemsize == C.sizeof(hk_race_plan) == 640
+assert RACE_PLAN_DTYPE.itemsize == C.sizeof(hk_race_plan) == 936
 KART_STATE_DTYPE = np.dtype([(k, np.int32) for k in KART_STATE_FIELDS])
 ACTION_DTYPE = np.dtype([("min_velocity", np.int32), ("max_velocity", np.int32), ("lane", np.int32)])
 GAME_STATE_DTYPE = np.dtype([("n_karts", np.int32), ("initialSection", np.int32), ("lastCompletedSection", np.int32),

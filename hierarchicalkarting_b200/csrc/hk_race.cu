@@ -197,8 +197,17 @@ __global__ void race_step_kernel(const DevTrack* __restrict__ t, hk_race_params 
             const float d = magnitude2((float)(k.x - t->lane[c][l][0]), (float)(k.z - t->lane[c][l][1]));
             if (l == 0 || d < best) { best = d; lane_new = l + 1; }
         }
-        plans[i].lane[c] = 0;                                        // m_UpcomingLanes.Remove (:631-632)
-        plans[i].vel[c] = 0.0f;
+        hk_race_plan* pl = plans + i;
+        const int pln = pl->lane[c];
+        if (pln != 0) {                                              // KartAgent.cs:226-239, InitCheckpointIndex = 0
+            const float d = magnitude2((float)(k.x - t->lane[c][pln - 1][0]), (float)(k.z - t->lane[c][pln - 1][1])) - 1.3f;
+            pl->avgLaneDiff = ((d > 0.0f ? d : 0.0f) + pl->avgLaneDiff * (float)(index - 1)) / (float)index;
+            pl->avgVelDiff = (((float)k.v - pl->vel[c]) + pl->avgVelDiff * (float)(index - 1)) / (float)index;
+        }
+        pl->lane[c] = 0;                                             // m_UpcomingLanes.Remove (:631-632)
+        pl->vel[c] = 0.0f;
+        pl->sectionTimes[c] = episode_step;                          // :650
+        if (c == 0 && index / t->n >= 1 && index / t->n <= HK_MAX_LAPS) pl->lapStep[index / t->n - 1] = episode_step;
         const int dl = abs(k.lane - lane_new);
         const bool st_old = is_straight(t, k.section), st_new = is_straight(t, index);
         if (k.laneChanges + dl > p.maxLaneChanges && st_old) k.illegalLaneChanges += 1;   // :638-642

@@ -114,3 +114,64 @@ class Races:
         abi.check(abi.load_library().hk_race_run(self._h, C.byref(self.params), n_races, first_step, n_steps, abi.vptr(karts),
                                                  abi.vptr(plans), abi.dptr(u), C.byref(bad)))
         return u, bad.value
+
+
+# ---- MCTS high level: root state and waypoint hand-off ----------------------------------------
+def mcts_root_state(track: Track, params: abi.hk_race_params, karts_race: np.ndarray, plans_race: np.ndarray, ego: int,
+                    section_window: int = 2, time_precision: int = 100):
+    """The root DiscreteGameState `planWithMCTS` builds for agent `ego` of one race (HierarchicalKartAgent.cs:180-245).
+    Returns (hk_game_state, nearby) where nearby[i] is the race-local index of game kart i."""
+    me = karts_race[ego]
+    nearby, initial, furthest = [], int(me["section"]), ego
+    for a in range(karts_race.shape[0]):                                    # foreach agent in m_envController.Agents (:182)
+        if abs(int(karts_race[a]["section"]) - int(me["section"])) < section_window:
+            nearby.append(a)
+            initial = max(initial, int(karts_race[a]["section"]))
+            if initial == int(karts_race[a]["section"]):
+                furthest = a
+    st = abi.hk_game_state()
+    st.n_karts = len(nearby)
+    st.initialSection = st.lastCompletedSection = initial
+    st.finalSection = initial + params.treeSearchDepth
+    L = track.n_sections
+    for i, a in enumerate(nearby):
+        k = karts_race[a]
+        t_at = 0
+        if int(k["section"]) != initial:                                    # :211-214, float32 product then (int)
+            d = int(plans_race[a]["sectionTimes"][int(k["section"]) % L]) - int(plans_race[furthest]["sectionTimes"][int(k["section"]) % L])
+            t_at = int(np.float32(np.float32(d) * np.float32(0.02)) * np.float32(time_precision))
+        wear = (np.float32(MAX_STEER) - np.float32(k["steer"])) / np.float32(MAX_STEER - MIN_STEER)
+        st.karts[i] = abi.hk_kart_state(player=0, team=a, section=initial, timeAtSection=t_at, min_velocity=0,     # quirks B.6-1, B.6-2
+                                        max_velocity=min(params.velocityBucketSize, int(params.topSpeed)), lane=int(k["lane"]),
+                                        tireAge=int(np.float32(wear * np.float32(10000))), laneChanges=int(k["laneChanges"]), infeasible=0)
+    return st, nearby
+
+
+def apply_best_states(track: Track, karts_race: np.ndarray, plans_race: np.ndarray, ego: int, nearby, best_states) -> None:
+    """The waypoint hand-off of FixedUpdate (HierarchicalKartAgent.cs:366-402): the ego's own lanes / velocities for sections
+    beyond the next checkpoint, and its belief about the other karts' (2-kart races: one opponent table)."""
+    L = track.n_sections
+    sec = int(karts_race[ego]["section"])
+    for gs in best_states:
+        s = gs.state
+        for i in range(s.n_karts):
+            ks = s.karts[i]
+            if nearby[i] == ego:
+                if ks.section > sec + (0 if sec == 0 else 1):
+                    plans_race[ego]["lane"][ks.section % L] = ks.lane
+                    plans_race[ego]["vel"][ks.section % L] = ks.max_velocity
+            else:
+                plans_race[ego]["oppLane"][ks.section % L] = ks.lane
+                plans_race[ego]["oppVel"][ks.section % L] = ks.max_velocity
+
+
+def plan_with_mcts(track: Track, params: abi.hk_race_params, game, karts_race: np.ndarray, plans_race: np.ndarray, ego: int,
+                   T: float = 0.9, max_iterations: int | None = None, seed: int | None = None):
+    """planWithMCTS + hand-off for one agent: root state, KartMCTS.constructSearchTree (GPU leaf-parallel rollouts),
+    getBestStatesSequence, apply.  `game` is a hierarchicalkarting_b200.mcts.Game for this track.  Returns the search root."""
+    from . import mcts as M
+    st, nearby = mcts_root_state(track, params, karts_race, plans_race, ego)
+    root = M.KartMCTS.constructSearchTree(M.DiscreteGameState(game, st), T=T, seed=seed, max_iterations=max_iterations)
+    best = M.KartMCTS.getBestStatesSequence(root)
+    apply_best_states(track, karts_race, plans_race, ego, nearby, best)
+    return root, best

@@ -231,11 +231,15 @@ typedef struct hk_race_kart {    /* one kart of one race; 64 bytes */
     int32_t pad_;
 } hk_race_kart;
 
-typedef struct hk_race_plan {    /* m_UpcomingLanes / m_UpcomingVelocities of one agent, keyed by section % n_sections */
-    int8_t lane[HK_MAX_SECTIONS];      /* 0 = key absent */
-    float  vel[HK_MAX_SECTIONS];
-    int8_t oppLane[HK_MAX_SECTIONS];   /* opponentUpcomingLanes[other] (filled from MCTS bestStates, HierarchicalKartAgent.cs:396-400) */
-    float  oppVel[HK_MAX_SECTIONS];
+#define HK_MAX_LAPS 8
+typedef struct hk_race_plan {    /* per-agent tables: m_UpcomingLanes / m_UpcomingVelocities keyed by section % n_sections, + metrics */
+    int8_t  lane[HK_MAX_SECTIONS];      /* 0 = key absent */
+    float   vel[HK_MAX_SECTIONS];
+    int8_t  oppLane[HK_MAX_SECTIONS];   /* opponentUpcomingLanes[other] (filled from MCTS bestStates, HierarchicalKartAgent.cs:396-400) */
+    float   oppVel[HK_MAX_SECTIONS];
+    int32_t sectionTimes[HK_MAX_SECTIONS];   /* sectionTimes[index] = episodeSteps (:650), keyed by index % n_sections; read by planWithMCTS :213 */
+    int32_t lapStep[HK_MAX_LAPS];       /* episodeSteps at which lap k+1 was completed (what TelemetryViewer.cs:60-72 derives) */
+    float   avgLaneDiff, avgVelDiff;    /* AverageLaneDifference / AverageVelDifference (KartAgent.cs:226-239) */
 } hk_race_plan;
 
 typedef struct hk_race_params {

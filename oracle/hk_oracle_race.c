@@ -191,8 +191,16 @@ void hk_oracle_race_step(const hk_section* sections, const double* trig, const d
                 if (l == 0 || d < best) { best = d; lane_new = l + 1; }
             }
             hk_race_plan* pl = &plans[i];
+            if (pl->lane[c] != 0) {                                             /* KartAgent.cs:226-239, InitCheckpointIndex = 0 */
+                const float d = magnitude2((float)(k->x - t.lane[(c * 4 + pl->lane[c] - 1) * 2]),
+                                           (float)(k->z - t.lane[(c * 4 + pl->lane[c] - 1) * 2 + 1])) - 1.3f;
+                pl->avgLaneDiff = ((d > 0.0f ? d : 0.0f) + pl->avgLaneDiff * (float)(index - 1)) / (float)index;
+                pl->avgVelDiff = (((float)k->v - pl->vel[c]) + pl->avgVelDiff * (float)(index - 1)) / (float)index;
+            }
             pl->lane[c] = 0;                                                    /* m_UpcomingLanes.Remove (:631-632) */
             pl->vel[c] = 0.0f;
+            pl->sectionTimes[c] = episode_step;                                 /* :650 */
+            if (c == 0 && index / t.n >= 1 && index / t.n <= HK_MAX_LAPS) pl->lapStep[index / t.n - 1] = episode_step;
             const int dl = abs(k->lane - lane_new);
             if (k->laneChanges + dl > p->maxLaneChanges && is_straight(&t, k->section)) k->illegalLaneChanges += 1;   /* :638-642 */
             if (is_straight(&t, k->section) != is_straight(&t, index)) k->laneChanges = 0;                           /* :643-646 */

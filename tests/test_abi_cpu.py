@@ -42,7 +42,7 @@ def test_only_sm100a_code_in_library():
 def test_struct_layouts_match_header():
     assert C.sizeof(abi.hk_section) == 24 and C.sizeof(abi.hk_kart) == 28 and C.sizeof(abi.hk_game_params) == 32
     assert C.sizeof(abi.hk_kart_state) == 40 and C.sizeof(abi.hk_action) == 12 and C.sizeof(abi.hk_game_state) == 16 + 4 * 40
-    assert C.sizeof(abi.hk_race_kart) == 64 and C.sizeof(abi.hk_race_plan) == 640 and C.sizeof(abi.hk_race_params) == 56
+    assert C.sizeof(abi.hk_race_kart) == 64 and C.sizeof(abi.hk_race_plan) == 936 and C.sizeof(abi.hk_race_params) == 56
     assert re.search(r"#define HK_MAX_SECTIONS 64\b", HEADER) and abi.HK_MAX_SECTIONS == 64
     for name, val in (("HK_MAX_PLAYERS", 4), ("HK_MAX_ACTIONS", 36), ("HK_MAX_PLIES", 64), ("HK_MAX_KARTS", 4), ("HK_MAX_HORIZON", 31)):
         assert re.search(rf"#define {name} {val}\b", HEADER) and getattr(abi, name) == val

@@ -106,3 +106,43 @@ def test_loop_properties(oracle, track):
     frozen = karts.copy()
     OR.run(karts, plans, 3200, 50)
     assert np.array_equal(frozen, karts)                                                   # finished karts do not move
+
+
+def test_telemetry_log_format_and_reference_parser(oracle, tmp_path, capsys):
+    """The experiment log of a headless batch has the reference's line format
+    (TelemetryViewer.cs:90-104); when the reference checkout is present (this container only) its own
+    experiment_log_parser.py must score it."""
+    import importlib.util
+    import os
+    from hierarchicalkarting_b200 import telemetry as T
+    track = S.OVAL
+    OR, prm = _oracle_races(oracle, track, laps=2)
+    karts, plans = R.start_grid(track, 6, seed=3)
+    OR.run(karts, plans, 0, 2400)
+    logs = tmp_path / "ExperimentLogs"
+    logs.mkdir()
+    names = ["Fixed-LQR(A)", "Fixed-LQR(B)"]
+    T.write_experiment_log(str(logs / "GPU_Fixed.txt"), names, karts, plans, track.n_sections, 2, 2400)
+    text = (logs / "GPU_Fixed.txt").read_text().splitlines()
+    assert text[0] == "Experiment 0" and text[1].startswith("Fixed-LQR(A) Speed: ") and text[5] == "Fixed-LQR(A) Laps Completed: 2/2"
+    assert text[19].startswith("Winner: Fixed-LQR(") and text[20] == "" and text[21] == "Experiment 1"
+    laps = [float(l.rsplit(" ", 1)[1]) for l in text if " Best Lap: " in l]
+    assert len(laps) == 12 and all(17.0 < t < 23.0 for t in laps)       # the reference's own Oval logs: 19.3 - 20.5 s per lap
+    parser = "/root/reference/experiment_log_parser.py"
+    if not os.path.exists(parser):
+        pytest.skip("reference checkout not present (GPU box)")
+    import ast
+    tree = ast.parse(open(parser).read())
+    keep = [n for n in tree.body if isinstance(n, (ast.Import, ast.FunctionDef))
+            or (isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") in ("logs_dir", "points_per_position"))]
+    src = ast.Module(body=keep, type_ignores=[])
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        exec(compile(src, parser, "exec"), ns)                              # defines the functions only
+        ns["summarize_experiment"]("GPU_Fixed")
+    finally:
+        os.chdir(cwd)
+    out = capsys.readouterr().out
+    assert "Wins {'Fixed-LQR': 6}" in out and "DNFs {}" in out and "Avg Collisions {'Fixed-LQR': 0.0}" in out

@@ -19,8 +19,10 @@ def _same(gk, gp, ok, op, tol=TOL):
         assert np.array_equal(gk[f], ok[f]), f
     for f in DBL_FIELDS:
         assert np.max(np.abs(gk[f] - ok[f])) <= tol * max(1.0, float(np.max(np.abs(ok[f])))), f
-    for f in ("lane", "vel", "oppLane", "oppVel"):
+    for f in ("lane", "vel", "oppLane", "oppVel", "sectionTimes", "lapStep"):
         assert np.array_equal(gp[f], op[f]), f
+    for f in ("avgLaneDiff", "avgVelDiff"):
+        assert np.max(np.abs(gp[f] - op[f])) <= 1e-6 * max(1.0, float(np.max(np.abs(op[f])))), f
 
 
 @pytest.mark.parametrize("track", [S.OVAL, S.COMPLEX])
@@ -114,3 +116,39 @@ def test_full_size_properties(hk):
     c_k, c_p = np.ascontiguousarray(karts[perm]), np.ascontiguousarray(plans[perm])
     G.run(c_k, c_p, 0, 300)
     assert np.array_equal(c_k, a_k[perm])                                       # races are independent
+
+
+def test_mcts_root_and_waypoint_handoff(hk):
+    """planWithMCTS's root state (HKA:180-245), the host tree policy over GPU leaf statistics and the
+    hand-off of getBestStatesSequence to the LQNG targets (HKA:366-402), closing the MCTS -> LQNG loop."""
+    from hierarchicalkarting_b200 import mcts as M
+    track = S.OVAL
+    prm = R.race_params(track, high_mode_mcts=True)
+    G = R.Races(track, prm)
+    game = M.Game(track, 2, prm.velocityBucketSize)
+    karts, plans = R.start_grid(track, 2, seed=31)
+    G.run(karts, plans, 0, 99)                                      # no plan yet: both karts steer for the Trigger centres
+    assert np.all(plans["lane"] == 0) and karts["section"].min() >= 1
+    # root state of race 0, ego 0
+    st, nearby = R.mcts_root_state(track, prm, karts[0], plans[0], 0)
+    assert nearby == [0, 1] and st.n_karts == 2 and st.initialSection == int(karts[0]["section"].max())
+    assert st.finalSection == st.initialSection + 8 and st.karts[0].tireAge == 2500 and st.karts[0].max_velocity == 2
+    lead, trail = int(np.argmax(karts[0]["section"])), int(np.argmin(karts[0]["section"]))
+    if karts[0]["section"][lead] != karts[0]["section"][trail]:
+        d = int(plans[0]["sectionTimes"][trail][karts[0]["section"][trail] % 24]) - int(plans[0]["sectionTimes"][lead][karts[0]["section"][trail] % 24])
+        assert st.karts[trail].timeAtSection == int(np.float32(np.float32(d) * np.float32(0.02)) * np.float32(100)) > 0
+    M.KartMCTS.rollouts_per_leaf = 256
+    for r in range(2):
+        for ego in range(2):
+            root, best = R.plan_with_mcts(track, prm, game, karts[r], plans[r], ego, max_iterations=60, seed=100 + 2 * r + ego)
+            assert root.numEpisodes > 0 and len(best) >= 1
+            sec = int(karts[r]["section"][ego])
+            keys = [int(b.state.karts[0].section) for b in best]
+            mine = [k for k in keys if k > sec + (0 if sec == 0 else 1)]
+            for k in mine:
+                assert 1 <= plans[r]["lane"][ego][k % 24] <= 4 and plans[r]["vel"][ego][k % 24] in (8, 10, 12, 14, 15)
+            assert (plans[r]["oppLane"][ego] != 0).sum() >= len(best) - 1
+            assert plans[r]["lane"][ego][(sec + 1) % 24] == 0           # the next checkpoint keeps its Trigger target (:369)
+    before = karts["section"].copy()
+    _, bad = G.run(karts, plans, 99, 300)                           # LQNG now tracks the MCTS waypoints (+2 buckets of speed, :757)
+    assert bad == 0 and np.all(karts["section"] >= before + 4)
