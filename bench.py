@@ -138,10 +138,29 @@ def run_reference(args):
                              "sample": f"{sample} problems per step x {args.steps} steps; C oracle port of KartLQR.solveFeedbackLQR "
                                        "(reference C# not compilable: no .NET in image), OpenMP over all host threads"},
             "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_STDOUT_FD = None
+
+
+def _only_json_on_stdout():
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; emit() writes the one JSON line."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, data)
 
 
 def main():
+    _only_json_on_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -366,7 +385,7 @@ def main():
         line["race"] = race_obj
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
