@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(128) lqng_generic_kernel(LqngParams p)
 }  // namespace hk
 #include "hk_lqng_mma.cuh"
 #include "hk_lqng_mma2p.cuh"
+#include "hk_lqng_mma4.cuh"
 namespace hk {
 
 template <int N>
@@ -427,6 +428,17 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
         else if (minb >= 6) lqng_mma2_kernel<6><<<grid, MMA2_THREADS, 0, stream>>>(p);
         else if (minb == 5) lqng_mma2_kernel<5><<<grid, MMA2_THREADS, 0, stream>>>(p);
         else lqng_mma2_kernel<4><<<grid, MMA2_THREADS, 0, stream>>>(p);
+        HK_CUDA(cudaGetLastError());
+        return HK_OK;
+    }
+    static const bool mma4 = !(getenv("HK_LQNG_MMA4") && atoi(getenv("HK_LQNG_MMA4")) == 0);
+    if (N == 4 && mma4 && !force_generic) {
+        // 4-kart game: warp per problem, DMMA for the 16 x 16 products (hk_lqng_mma4.cuh); takes every operand form
+        const size_t smem = (size_t)MMA4_WARPS * Mma4Layout::total * sizeof(double);
+        const long long want = ((long long)batch + MMA4_WARPS - 1) / MMA4_WARPS;
+        const unsigned grid = (unsigned)(want < 148 * 40 ? want : 148 * 40);
+        count_launch();
+        lqng_mma4_kernel<<<grid, 32 * MMA4_WARPS, smem, stream>>>(p);
         HK_CUDA(cudaGetLastError());
         return HK_OK;
     }

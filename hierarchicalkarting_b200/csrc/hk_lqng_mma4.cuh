@@ -1,0 +1,290 @@
+// hk_lqng_mma4.cuh — warp-per-problem kernel for the 4-kart LQNG (n = 16, m = 8; BASELINE config 3), any operands the ABI
+// accepts (time-varying, non-symmetric Q, all outputs).  Same algorithm as KartLQR.solveFeedbackLQR
+// (reference: Assets/Karting/Scripts/AI/LQR/KartLQR.cs:17-128) with quirks Q1/Q2 of SURVEY.md A.3.
+//
+// Where the flops are: Z_i <- Q_i + P_i^T R_i P_i + F^T Z_i F for four players is 2 x 4 x 16^3 x 2 = 65 k of the 139 k flops
+// of a backward step.  Those products run on the FP64 tensor pipe as DMMA m8n8k4 over 2 x 2 tiles of 8 x 8 with operand
+// fragments read straight from shared memory (row-major, leading dimension 20 doubles: every fragment load is the minimal two
+// wavefronts).  F and Y = Z_i F are kept TRANSPOSED (Ft, Yt) so that both their uses — as the k x n operand of one product and
+// the m x k operand of the next — are row reads.  The coupled 8 x 8 system [LHS | RHSMat | RHSVec] (25 columns) is dealt one
+// column per lane and reduced in registers by Gauss-Jordan with partial pivoting (the pivot MathNet's LU would take: first
+// largest magnitude at or below the diagonal, KartLQR.cs:104-105), the pivot column broadcast by shuffles.  Everything else
+// (W = B_i^T Z_i, F = A - B P, eta, the rollout) is lane-per-row / lane-per-column scalar code on the same shared arrays.
+#pragma once
+
+namespace hk {
+
+struct Mma4Layout {
+    static constexpr int LD = 20;
+    static constexpr int oZ = 0;                     // Z[4][16][LD]
+    static constexpr int oFt = oZ + 4 * 16 * LD;     // Ft[c][r] = F[r][c]
+    static constexpr int oYt = oFt + 16 * LD;        // Yt[c][k] = (Z_i F)[k][c]
+    static constexpr int oP = oYt + 16 * LD;         // P[8][16]
+    static constexpr int oRP = oP + 128;             // (R_i P_i)[i][a][c]
+    static constexpr int oW = oRP + 128;             // W[8][16] = stacked B_i^T Z_i
+    static constexpr int oA = oW + 128;              // A_i[4][4][4]
+    static constexpr int oB = oA + 64;               // B_i[4][4][2]
+    static constexpr int oR = oB + 32;               // R_i[4][2][2]
+    static constexpr int oEta = oR + 16;             // eta[4][16]
+    static constexpr int oTmp = oEta + 64;           // eta_i + Z_i beta, per player
+    static constexpr int oBeta = oTmp + 64;
+    static constexpr int oAlpha = oBeta + 16;
+    static constexpr int oX = oAlpha + 8;
+    static constexpr int oU = oX + 16;
+    static constexpr int total = oU + 8;
+};
+
+constexpr int MMA4_WARPS = 2;
+
+__global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p)
+{
+    using L = Mma4Layout;
+    constexpr int N = 4, n = 16, m = 8, LD = L::LD;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3, lo = lane & 15, hf = lane >> 4;
+    double* s = smem + (size_t)wib * L::total;
+    double *Z = s + L::oZ, *Ft = s + L::oFt, *Yt = s + L::oYt, *Pm = s + L::oP, *RP = s + L::oRP, *W = s + L::oW, *As = s + L::oA,
+           *Bs = s + L::oB, *Rs = s + L::oR, *eta = s + L::oEta, *tmp = s + L::oTmp, *beta = s + L::oBeta, *alpha = s + L::oAlpha,
+           *xs = s + L::oX, *us = s + L::oU;
+    const long long nwarps = (long long)gridDim.x * MMA4_WARPS;
+
+    for (long long prob = (long long)blockIdx.x * MMA4_WARPS + wib; prob < p.batch; prob += nwarps) {
+        const int T = p.horizon + 1, Tm = p.time_varying ? T : 1;
+        const double* gA = p.A + (size_t)prob * Tm * N * 16;
+        const double* gB = p.B + (size_t)prob * Tm * N * 8;
+        const double* gQ = p.Q + (size_t)prob * Tm * N * n * n;
+        const double* gq = p.q + (size_t)prob * Tm * N * n;
+        const double* gR = p.R + (size_t)prob * Tm * N * 4;
+        const double* gx = p.x0 + (size_t)prob * n;
+        double* gP = p.P ? p.P + (size_t)prob * T * m * n : nullptr;
+        double* ga = p.alpha ? p.alpha + (size_t)prob * T * m : nullptr;
+        int singular = 0;
+        __syncwarp();
+        {   // Zs = Q, etas = q of the last stage (KartLQR.cs:62-63): 1,024 doubles, 128-bit coalesced loads
+            const double* q0 = gQ + (size_t)(Tm - 1) * N * n * n;
+            for (int e = lane; e < N * n * n / 2; e += 32) {
+                const double2 v = *reinterpret_cast<const double2*>(q0 + 2 * e);
+                const int i = e >> 7, r = (e >> 3) & 15, c = (e & 7) * 2;
+                *reinterpret_cast<double2*>(Z + (i * 16 + r) * LD + c) = v;
+            }
+            for (int e = lane; e < N * n; e += 32) eta[e] = gq[(size_t)(Tm - 1) * N * n + e];
+            if (lane < n) xs[lane] = gx[lane];
+        }
+        for (int st = p.horizon; st >= 0; --st) {                   // KartLQR.cs:64
+            const int tt = p.time_varying ? st : 0;
+            const double* Qt = gQ + (size_t)tt * N * n * n;
+            if (p.time_varying || st == p.horizon) {
+                for (int e = lane; e < N * 16; e += 32) As[e] = gA[(size_t)tt * N * 16 + e];
+                Bs[lane] = gB[(size_t)tt * N * 8 + lane];
+                if (lane < N * 4) Rs[lane] = gR[(size_t)tt * N * 4 + lane];
+            }
+            __syncwarp();
+            // W_i = B_i^T Z_i (rows of block i only: B_i is zero elsewhere, KartLQR.cs:41-52); lane owns column lo of two players
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                const int i = 2 * hf + ii;
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], Z[(i * 16 + 4 * i + k) * LD + lo], acc);
+                    W[(2 * i + a) * n + lo] = acc;
+                }
+            }
+            __syncwarp();
+            // coupled system, one column per lane: LHS (8, quirk Q1 placement :68-87), RHSMat (16, :89-95), RHSVec (1, :96)
+            double col[8];
+            if (lane < 8) {
+                const int i = lane >> 1, b = lane & 1;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int j = r >> 1, a = r & 1;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc = fma(W[(2 * i + a) * n + 4 * j + k], Bs[j * 8 + k * 2 + b], acc);
+                    if (i == j) acc = Rs[i * 4 + a * 2 + b] + acc;  // getRMatrix() + ... (:78)
+                    col[r] = acc;
+                }
+            } else if (lane < 24) {
+                const int c = lane - 8, pc = c >> 2, cc = c & 3;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc = fma(W[r * n + 4 * pc + k], As[pc * 16 + k * 4 + cc], acc);
+                    col[r] = acc;
+                }
+            } else if (lane == 24) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i = r >> 1, a = r & 1;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], eta[i * n + 4 * i + k], acc);
+                    col[r] = acc;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) col[r] = 0.0;
+            }
+            // P = LHS.Solve(RHSMat), alpha = LHS.Solve(RHSVec): Gauss-Jordan with partial pivoting (KartLQR.cs:104-105)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                double pc[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) pc[r] = shfl_d(col[r], k);
+                int pr = k;
+                double best = fabs(pc[k]);
+#pragma unroll
+                for (int r = k + 1; r < 8; ++r)
+                    if (fabs(pc[r]) > best) { best = fabs(pc[r]); pr = r; }
+#pragma unroll
+                for (int r = k + 1; r < 8; ++r)
+                    if (pr == r) {                                  // warp-uniform row exchange
+                        double tv = col[k]; col[k] = col[r]; col[r] = tv;
+                        tv = pc[k]; pc[k] = pc[r]; pc[r] = tv;
+                    }
+                if (pc[k] == 0.0) singular = 1;
+                const double rk = col[k] / pc[k];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r != k) col[r] = fma(-pc[r], rk, col[r]);
+                col[k] = rk;
+            }
+            if (lane >= 8 && lane < 24) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) Pm[r * n + lane - 8] = col[r];
+                if (gP)
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) gP[(size_t)st * m * n + r * n + lane - 8] = col[r];
+            } else if (lane == 24) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) alpha[r] = col[r];
+                if (ga)
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) ga[(size_t)st * m + r] = col[r];
+            }
+            __syncwarp();
+            // F = A - sum_k B_k P_k (stored transposed), beta = -sum_k B_k alpha_k (:110-111), R_i P_i
+            {
+                const int r = lo, pr = r >> 2, rr = r & 3;
+                const double b0 = Bs[pr * 8 + rr * 2 + 0], b1 = Bs[pr * 8 + rr * 2 + 1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = hf * 8 + j;
+                    const double a = (c >> 2) == pr ? As[pr * 16 + rr * 4 + (c & 3)] : 0.0;
+                    Ft[c * LD + r] = a - fma(b1, Pm[(2 * pr + 1) * n + c], b0 * Pm[(2 * pr) * n + c]);
+                }
+                if (hf == 0) beta[r] = -fma(b1, alpha[2 * pr + 1], b0 * alpha[2 * pr]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = lane + 32 * j, i = e >> 5, a = (e >> 4) & 1, c = e & 15;
+                    RP[e] = fma(Rs[i * 4 + a * 2 + 1], Pm[(2 * i + 1) * n + c], Rs[i * 4 + a * 2 + 0] * Pm[(2 * i) * n + c]);
+                }
+            }
+            __syncwarp();
+            // Z_i <- Q_i + P_i^T R_i P_i + F^T Z_i F ; eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)  (:116-117)
+            for (int i = 0; i < N; ++i) {
+                double* Zi = Z + i * 16 * LD;
+                {   // Y = Z_i F, stored transposed
+                    double c00a = 0, c00b = 0, c01a = 0, c01b = 0, c10a = 0, c10b = 0, c11a = 0, c11b = 0;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const double a0 = Zi[g * LD + 4 * ks + t], a1 = Zi[(8 + g) * LD + 4 * ks + t];
+                        const double b0 = Ft[g * LD + 4 * ks + t], b1 = Ft[(8 + g) * LD + 4 * ks + t];
+                        dmma(c00a, c00b, a0, b0); dmma(c01a, c01b, a0, b1);
+                        dmma(c10a, c10b, a1, b0); dmma(c11a, c11b, a1, b1);
+                    }
+                    __syncwarp();
+                    Yt[(2 * t) * LD + g] = c00a;          Yt[(2 * t + 1) * LD + g] = c00b;
+                    Yt[(8 + 2 * t) * LD + g] = c01a;      Yt[(8 + 2 * t + 1) * LD + g] = c01b;
+                    Yt[(2 * t) * LD + 8 + g] = c10a;      Yt[(2 * t + 1) * LD + 8 + g] = c10b;
+                    Yt[(8 + 2 * t) * LD + 8 + g] = c11a;  Yt[(8 + 2 * t + 1) * LD + 8 + g] = c11b;
+                }
+                __syncwarp();
+                {
+                    const double* Qi = Qt + (size_t)i * n * n;
+                    const double2 q00 = *reinterpret_cast<const double2*>(Qi + g * n + 2 * t);
+                    const double2 q01 = *reinterpret_cast<const double2*>(Qi + g * n + 8 + 2 * t);
+                    const double2 q10 = *reinterpret_cast<const double2*>(Qi + (8 + g) * n + 2 * t);
+                    const double2 q11 = *reinterpret_cast<const double2*>(Qi + (8 + g) * n + 8 + 2 * t);
+                    double c00a = q00.x, c00b = q00.y, c01a = q01.x, c01b = q01.y, c10a = q10.x, c10b = q10.y, c11a = q11.x, c11b = q11.y;
+                    {   // + P_i^T (R_i P_i): k = 2
+                        const double a0 = t < 2 ? Pm[(2 * i + t) * n + g] : 0.0, a1 = t < 2 ? Pm[(2 * i + t) * n + 8 + g] : 0.0;
+                        const double b0 = t < 2 ? RP[(i * 2 + t) * n + g] : 0.0, b1 = t < 2 ? RP[(i * 2 + t) * n + 8 + g] : 0.0;
+                        dmma(c00a, c00b, a0, b0); dmma(c01a, c01b, a0, b1);
+                        dmma(c10a, c10b, a1, b0); dmma(c11a, c11b, a1, b1);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {              // + F^T Y
+                        const double a0 = Ft[g * LD + 4 * ks + t], a1 = Ft[(8 + g) * LD + 4 * ks + t];
+                        const double b0 = Yt[g * LD + 4 * ks + t], b1 = Yt[(8 + g) * LD + 4 * ks + t];
+                        dmma(c00a, c00b, a0, b0); dmma(c01a, c01b, a0, b1);
+                        dmma(c10a, c10b, a1, b0); dmma(c11a, c11b, a1, b1);
+                    }
+                    *reinterpret_cast<double2*>(Zi + g * LD + 2 * t) = make_double2(c00a, c00b);
+                    *reinterpret_cast<double2*>(Zi + g * LD + 8 + 2 * t) = make_double2(c01a, c01b);
+                    *reinterpret_cast<double2*>(Zi + (8 + g) * LD + 2 * t) = make_double2(c10a, c10b);
+                    *reinterpret_cast<double2*>(Zi + (8 + g) * LD + 8 + 2 * t) = make_double2(c11a, c11b);
+                }
+                __syncwarp();
+                {   // eta_i + Z_i^{new} beta (quirk Q2): row lo, the two half-warps take 8 columns each
+                    double zb = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) zb = fma(Zi[lo * LD + hf * 8 + j], beta[hf * 8 + j], zb);
+                    zb += __shfl_xor_sync(0xffffffffu, zb, 16);
+                    if (hf == 0) tmp[i * n + lo] = eta[i * n + lo] + zb;
+                }
+                __syncwarp();
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc = fma(Ft[lo * LD + hf * 8 + j], tmp[i * n + hf * 8 + j], acc);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                    const double a0 = alpha[2 * i], a1 = alpha[2 * i + 1];
+                    const double ra0 = fma(Rs[i * 4 + 1], a1, Rs[i * 4 + 0] * a0), ra1 = fma(Rs[i * 4 + 3], a1, Rs[i * 4 + 2] * a0);
+                    const double pra = fma(Pm[(2 * i + 1) * n + lo], ra1, Pm[(2 * i) * n + lo] * ra0);
+                    const double e_new = (gq[(size_t)tt * N * n + i * n + lo] + pra) + acc;
+                    __syncwarp();
+                    if (hf == 0) eta[i * n + lo] = e_new;
+                }
+                __syncwarp();
+            }
+        }
+        // optimal_control = -P x0 - alpha with the t = 0 pair (:121-126), every player
+        if (lane < m) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < n; ++c) acc = fma(-Pm[lane * n + c], xs[c], acc);
+            p.u0[(size_t)prob * m + lane] = acc - alpha[lane];
+        }
+        if (lane == 0 && p.status) p.status[prob] = singular;
+        // closed-loop rollout; gains are re-read from the P/alpha output buffers written above
+        if (p.traj) {
+            double* gt = p.traj + (size_t)prob * (T + 1) * n;
+            if (lane < n) gt[lane] = xs[lane];
+            __syncwarp();
+            for (int st = 0; st <= p.horizon; ++st) {
+                const int tt = p.time_varying ? st : 0;
+                if (lane < m) {
+                    double acc = 0.0;
+                    for (int c = 0; c < n; ++c) acc = fma(-gP[(size_t)st * m * n + lane * n + c], xs[c], acc);
+                    us[lane] = acc - ga[(size_t)st * m + lane];
+                }
+                __syncwarp();
+                double xn = 0.0;
+                if (lane < n) {
+                    const int pr = lane >> 2, rr = lane & 3;
+                    for (int c = 0; c < 4; ++c) xn = fma(gA[(size_t)tt * N * 16 + pr * 16 + rr * 4 + c], xs[4 * pr + c], xn);
+                    for (int c = 0; c < 2; ++c) xn = fma(gB[(size_t)tt * N * 8 + pr * 8 + rr * 2 + c], us[2 * pr + c], xn);
+                }
+                __syncwarp();
+                if (lane < n) { xs[lane] = xn; gt[(size_t)(st + 1) * n + lane] = xn; }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+}  // namespace hk
