@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 BATCH = 65536
 HORIZON = 3
 FLOPS_PER_SOLVE = 41805            # dense count, SURVEY.md §8(d), 2-kart horizon 3
+FLOPS_PER_SOLVE_4 = 556823         # same count for the 4-kart game
 IN_BYTES_PER_SOLVE = 1664          # A,B per player + Q,q,R,x0 (per-player A/B form)
 OUT_BYTES_PER_SOLVE = 32 + 4       # u0 for both players + status
 N_INPUT_SETS = 4                   # rotated so that consecutive steps never hit the same 109 MB in the 126 MB L2
@@ -170,6 +171,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mcts", action="store_true")
     ap.add_argument("--no-race", action="store_true")
+    ap.add_argument("--no-lqng4", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -311,6 +313,42 @@ def main():
                     "config": "BASELINE config 4: Complex, 2 karts, depth 8, bucket 2, Philox4x32-10; host call incl. result D2H",
                     "gpu_launches": reps}
 
+    # ---- 4-kart LQNG (BASELINE config 3: 1,048,576 Complex 2v2 problems per GPU, HBM-resident) --------------------------------
+    lqng4_obj = None
+    if not args.no_lqng4:
+        uniq, rep = 65536, 16
+        h4 = S.assemble_dense(S.make_problems(S.COMPLEX, uniq, 4, seed=20260002 + rank))
+        d4 = [torch.from_numpy(a).to(dev).repeat((rep,) + (1,) * (a.ndim - 1)).contiguous() for a in h4]
+        b4 = uniq * rep
+        u4 = torch.empty((b4, 8), dtype=torch.float64, device=dev)
+        s4 = torch.empty((b4,), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+
+        def step4():
+            abi.check(lib.hk_lqng_solve_batch_device(b4, 4, HORIZON, 0, *[t.data_ptr() for t in d4], u4.data_ptr(), None, None, None,
+                                                     s4.data_ptr(), stream.cuda_stream))
+        step4()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps4 = 3
+        f0.record(stream)
+        for _ in range(reps4):
+            step4()
+        f1.record(stream)
+        f1.synchronize()
+        ms4 = max_over_ranks(f0.elapsed_time(f1)) / reps4
+        bad4 = int(s4.sum().item())
+        _, _, fp64_pk, _ = _peaks()
+        lqng4_obj = {"metric": "lqng4_solves_per_s", "value": world * b4 / (ms4 * 1e-3), "unit": "solves/s", "ms_per_launch": ms4,
+                     "batch_per_gpu": b4, "status_nonzero": bad4,
+                     "roofline": {"bound": "tensor", "achieved": b4 * FLOPS_PER_SOLVE_4 / (ms4 * 1e-3) / 1e12, "peak": fp64_pk, "unit": "TFLOP/s",
+                                  "frac": b4 * FLOPS_PER_SOLVE_4 / (ms4 * 1e-3) / 1e12 / fp64_pk,
+                                  "note": f"dense count {FLOPS_PER_SOLVE_4} flops per 4-kart solve (SURVEY.md 8d); kernel lqng_mma4_kernel"},
+                     "config": f"BASELINE config 3: 4-kart 2v2 Complex problems, horizon 3; {uniq} distinct seeded problems tiled x{rep} in HBM "
+                               f"({sum(t.numel() for t in d4) * 8 / 1e9:.1f} GB of operands per launch, u0 + status out)"}
+        del d4, u4, s4
+        torch.cuda.empty_cache()
+
     # ---- closed loop without PhysX (BASELINE config 5: 16,384 2-kart Oval races; Fixed high level, LQNG every step) -----------
     race_obj = None
     if not args.no_race:
@@ -383,6 +421,8 @@ def main():
         line["mcts"] = mcts_obj
     if race_obj:
         line["race"] = race_obj
+    if lqng4_obj:
+        line["lqng4"] = lqng4_obj
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     emit(line)

@@ -135,10 +135,10 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
 #pragma unroll
                 for (int r = 0; r < 8; ++r) pc[r] = shfl_d(col[r], k);
                 int pr = k;
-                double best = fabs(pc[k]);
+                double best = pc[k];
 #pragma unroll
                 for (int r = k + 1; r < 8; ++r)
-                    if (fabs(pc[r]) > best) { best = fabs(pc[r]); pr = r; }
+                    if (abs_gt(pc[r], best)) { best = pc[r]; pr = r; }  // |.| compared on the integer pipes (exact)
 #pragma unroll
                 for (int r = k + 1; r < 8; ++r)
                     if (pr == r) {                                  // warp-uniform row exchange
@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
                         tv = pc[k]; pc[k] = pc[r]; pc[r] = tv;
                     }
                 if (pc[k] == 0.0) singular = 1;
-                const double rk = col[k] / pc[k];
+                // 1 / pivot: MUFU seed + one cubic step (2^-60) unless the pivot is zero, denormal or huge (warp-uniform)
+                const double rinv = bad_pivot(pc[k]) ? 1.0 / pc[k] : rcp_fast(pc[k]);
+                const double rk = col[k] * rinv;
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
                     if (r != k) col[r] = fma(-pc[r], rk, col[r]);
@@ -187,6 +189,12 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
             // Z_i <- Q_i + P_i^T R_i P_i + F^T Z_i F ; eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)  (:116-117)
             for (int i = 0; i < N; ++i) {
                 double* Zi = Z + i * 16 * LD;
+                // C fragments of the new Z_i start from Q_i: issue the loads before the first product to hide their L2 latency
+                const double* Qi = Qt + (size_t)i * n * n;
+                const double2 q00 = *reinterpret_cast<const double2*>(Qi + g * n + 2 * t);
+                const double2 q01 = *reinterpret_cast<const double2*>(Qi + g * n + 8 + 2 * t);
+                const double2 q10 = *reinterpret_cast<const double2*>(Qi + (8 + g) * n + 2 * t);
+                const double2 q11 = *reinterpret_cast<const double2*>(Qi + (8 + g) * n + 8 + 2 * t);
                 {   // Y = Z_i F, stored transposed
                     double c00a = 0, c00b = 0, c01a = 0, c01b = 0, c10a = 0, c10b = 0, c11a = 0, c11b = 0;
 #pragma unroll
@@ -204,11 +212,6 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
                 }
                 __syncwarp();
                 {
-                    const double* Qi = Qt + (size_t)i * n * n;
-                    const double2 q00 = *reinterpret_cast<const double2*>(Qi + g * n + 2 * t);
-                    const double2 q01 = *reinterpret_cast<const double2*>(Qi + g * n + 8 + 2 * t);
-                    const double2 q10 = *reinterpret_cast<const double2*>(Qi + (8 + g) * n + 2 * t);
-                    const double2 q11 = *reinterpret_cast<const double2*>(Qi + (8 + g) * n + 8 + 2 * t);
                     double c00a = q00.x, c00b = q00.y, c01a = q01.x, c01b = q01.y, c10a = q10.x, c10b = q10.y, c11a = q11.x, c11b = q11.y;
                     {   // + P_i^T (R_i P_i): k = 2
                         const double a0 = t < 2 ? Pm[(2 * i + t) * n + g] : 0.0, a1 = t < 2 ? Pm[(2 * i + t) * n + 8 + g] : 0.0;
