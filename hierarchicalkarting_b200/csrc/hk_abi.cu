@@ -2,6 +2,7 @@
 // points.  The discrete-game entry points live next to their kernels in hk_game.cu.
 #include "hk_common.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <atomic>
 
@@ -250,7 +251,8 @@ extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizo
     size_t per = 0;
     for (int i = 0; i < 7; ++i) per += e[i];
     // chunked two-stream pipeline: H2D of chunk k+1 overlaps assembly + solve of chunk k and D2H of chunk k-1
-    const int nchunks = batch >= 8192 ? 4 : 1;
+    static const int chunks_env = getenv("HK_E2E_CHUNKS") ? atoi(getenv("HK_E2E_CHUNKS")) : 0;    // tuning knob
+    const int nchunks = batch >= 8192 ? (chunks_env > 0 ? chunks_env : 4) : 1;
     const int chunk = (batch + nchunks - 1) / nchunks;
     cudaStream_t streams[2] = {c->stream, c->stream2};
     double* dbufs[2] = {nullptr, nullptr};

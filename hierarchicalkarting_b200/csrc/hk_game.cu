@@ -406,12 +406,23 @@ __global__ void build_tables_kernel(const DevGame* __restrict__ gg, unsigned cha
 }
 
 // One playout of KartMCTS.simulate (:238-278). Returns plies played; first_gi = generation index of the first action.
+// Legal moves of the leaf's own karts in policy order.  A kart that has not moved yet in a rollout still has its leaf state, and
+// its legal set depends on nothing else (the collision filter is disabled, KartDiscreteGame.cs:398; the optimal-lane sign is
+// that of lastCompletedSection, which only advances once every kart has moved): the sorted list of the slow, directly
+// evaluated plies — the root's (0, bucket) velocity bucket is not an action bucket, quirk B.6-1 — is the same for every
+// rollout of a leaf, so it is built once per block.
+struct RootMoves {
+    int cnt[HK_MAX_KARTS];                               // -1: not prepared (table-driven kart)
+    unsigned char order[HK_MAX_KARTS][HK_MAX_ACTIONS];   // generation indices in policy order
+};
+
 template <bool TRACE>
 __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long seed, unsigned long long rid, float* scores,
-                       int& n_scores, int& first_gi, hk_action* act_out, int* choice_out)
+                       int& n_scores, int& first_gi, hk_action* act_out, int* choice_out, const RootMoves* root = nullptr)
 {
     const Tables tb(g);
     int ply = 0;
+    unsigned moved = 0;
     first_gi = -1;
     n_scores = 0;
     for (;;) {
@@ -419,7 +430,13 @@ __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long se
         if (np < 0) return -1;
         const int lvl = (g.tables_ok && st.karts[np].player == 0) ? velocity_level(g, st.karts[np].min_velocity, st.karts[np].max_velocity) : -1;
         int gi, index;
-        if (lvl >= 0) {                                  // table-driven ply
+        if (lvl < 0 && root && !((moved >> np) & 1u) && root->cnt[np] >= 0) {     // leaf kart, list prepared by the block
+            const int cnt = root->cnt[np];
+            if (is_over(g, st, cnt, np, scores, n_scores)) break;
+            index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
+            gi = root->order[np][index];
+            make_move(g, st, np, action_of(g, gi));
+        } else if (lvl >= 0) {                           // table-driven ply
             unsigned long long mask;
             const unsigned char* ord;
             const int cnt = fast_legal(g, tb, st, np, lvl, mask, ord);
@@ -435,6 +452,7 @@ __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long se
             gi = select_kth(keys, g.n_cand, index);
             make_move(g, st, np, action_of(g, gi));
         }
+        moved |= 1u << np;
         if (ply == 0) first_gi = gi;
         if (TRACE && ply < HK_MAX_PLIES) { act_out[ply] = action_of(g, gi); choice_out[ply] = index; }
         ++ply;
@@ -467,12 +485,33 @@ __global__ void __launch_bounds__(128) rollouts_kernel(const DevGame* __restrict
     __syncthreads();
     const int leaf = blockIdx.y;
     const hk_game_state st = leaves[leaf];
+    __shared__ RootMoves s_root;
+    __shared__ unsigned long long s_keys[HK_MAX_KARTS][HK_MAX_ACTIONS];
+    if (threadIdx.x < HK_MAX_KARTS) {
+        const int k = threadIdx.x;
+        int cnt = -1;
+        if (k < st.n_karts) {
+            const int lvl = (g.tables_ok && st.karts[k].player == 0) ? velocity_level(g, st.karts[k].min_velocity, st.karts[k].max_velocity) : -1;
+            if (lvl < 0) cnt = legal_moves(g, st, k, s_keys[k]);
+        }
+        s_root.cnt[k] = cnt;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < HK_MAX_KARTS * HK_MAX_ACTIONS; e += blockDim.x) {
+        const int k = e / HK_MAX_ACTIONS, c = e % HK_MAX_ACTIONS;
+        if (s_root.cnt[k] > 0 && c < g.n_cand && s_keys[k][c] != ~0ull) {       // keys are distinct: rank = number of smaller keys
+            int rank = 0;
+            for (int j = 0; j < g.n_cand; ++j) rank += s_keys[k][j] < s_keys[k][c];
+            s_root.order[k][rank] = (unsigned char)c;
+        }
+    }
+    __syncthreads();
     // grid-stride over the leaf's rollouts; block-local partial sums in double
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rollouts_per_leaf; r += (long long)gridDim.x * blockDim.x) {
         float scores[2 * HK_MAX_KARTS];
         int n_scores, first_gi;
         const unsigned long long rid = rollout_offset + (unsigned long long)leaf * (unsigned long long)rollouts_per_leaf + (unsigned long long)r;
-        const int plies = rollout<false>(g, st, seed, rid, scores, n_scores, first_gi, nullptr, nullptr);
+        const int plies = rollout<false>(g, st, seed, rid, scores, n_scores, first_gi, nullptr, nullptr, &s_root);
         if (plies < 0) { atomicExch(error_flag, 1); continue; }
         if (plies == 0) continue;
         atomicAdd(&s_plies, (unsigned)plies);
