@@ -461,7 +461,7 @@ __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long se
 }
 
 // ---- kernels ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) rollouts_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ leaves,
+__global__ void __launch_bounds__(128, 8) rollouts_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ leaves,
                                                        long long rollouts_per_leaf, unsigned long long seed,
                                                        unsigned long long rollout_offset, unsigned long long* visit,
                                                        double* reward_sum, unsigned long long* nan_count,
