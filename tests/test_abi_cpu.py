@@ -58,6 +58,18 @@ def test_host_side_argument_validation_needs_no_gpu():
     assert lib.hk_lqng_solve_batch(-1, 2, 3, 0, *args) == abi.HK_ERR_INVALID_ARGUMENT
     assert b"batch" in lib.hk_last_error()
     assert lib.hk_lqng_solve_batch(0, 2, 3, 0, *args) == abi.HK_OK            # empty batch is a no-op, even without a device
+    # closed-loop entries: NULL handles / bad sizes are rejected before any device work; empty batches are no-ops
+    from hierarchicalkarting_b200 import race as R
+    prm = R.race_params(S.OVAL)
+    karts, plans = R.start_grid(S.OVAL, 2, seed=1)
+    u = np.zeros((2, 2, 2))
+    assert lib.hk_race_run(None, C.byref(prm), 2, 0, 10, abi.vptr(karts), abi.vptr(plans), abi.dptr(u), None) == abi.HK_ERR_INVALID_ARGUMENT
+    assert b"hk_race_run" in lib.hk_last_error()
+    assert lib.hk_race_step(None, C.byref(prm), 4, 0, abi.dptr(u), abi.vptr(karts), abi.vptr(plans)) == abi.HK_ERR_INVALID_ARGUMENT
+    sec, trig, fwd, lane = R.geometry(S.OVAL)
+    h = C.c_void_p()
+    assert lib.hk_track_create(sec, abi.dptr(trig), abi.dptr(fwd), abi.dptr(lane), 65, C.byref(h)) == abi.HK_ERR_INVALID_ARGUMENT
+    assert lib.hk_track_create(sec, None, abi.dptr(fwd), abi.dptr(lane), 24, C.byref(h)) == abi.HK_ERR_INVALID_ARGUMENT
     cdf = np.zeros(4, dtype=np.uint32)
     assert lib.hk_policy_cdf(0, cdf.ctypes.data_as(C.POINTER(C.c_uint32))) == abi.HK_ERR_INVALID_ARGUMENT
     assert lib.hk_policy_cdf(4, cdf.ctypes.data_as(C.POINTER(C.c_uint32))) == abi.HK_OK and cdf[-1] == 0xFFFFFFFF
@@ -75,6 +87,10 @@ def test_no_cpu_fallback():
     from hierarchicalkarting_b200 import mcts, tracks
     with pytest.raises(abi.HKError) as e:
         mcts.Game(tracks.OVAL, 2, 2)
+    assert e.value.status == abi.HK_ERR_NO_DEVICE
+    from hierarchicalkarting_b200 import race
+    with pytest.raises(abi.HKError) as e:
+        race.Races(tracks.OVAL)                                              # the headless race loop has no CPU path either
     assert e.value.status == abi.HK_ERR_NO_DEVICE
 
 
