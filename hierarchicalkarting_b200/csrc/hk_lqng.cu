@@ -15,6 +15,8 @@
 // coalesced 128-bit loads; there is no cross-problem reuse, so HBM traffic = algorithmic bytes).
 #include "hk_common.cuh"
 #include <cstdlib>
+#include <atomic>
+#include <mutex>
 
 namespace hk {
 
@@ -26,6 +28,7 @@ struct LqngParams {
     const int* redo_list;      // non-null: solve only problems redo_list[0 .. *redo_count) (queued by a fast kernel)
     const int* redo_count;
     int* reset_count;          // counter of the NEXT launch, cleared here (stream order makes that safe)
+    int* work;                 // persistent 2-kart kernel: {next problem - resident warps, warps done}; zero between launches
 };
 
 template <int N>
@@ -383,7 +386,7 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
                 double* dtraj, int* dstatus, cudaStream_t stream)
 {
     if (batch == 0) return HK_OK;
-    LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr};
+    LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr, nullptr};
     static const bool force_generic = getenv("HK_LQNG_FORCE_GENERIC") != nullptr;
     if (N == 2 && !time_varying && !dP && !dalpha && !dtraj && !force_generic) {
         // throughput path: one launch of a DMMA kernel (problems it cannot take fall back inside the kernel)
@@ -415,8 +418,34 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
             }
             const long long want = ((long long)batch + warps - 1) / warps;
             const unsigned grid = (unsigned)(want < resident ? want : resident);
+            // dynamic work distribution: a pool of zero-initialised counter pairs, one per launch in flight (the kernel's
+            // last warp clears its pair); launches on one stream serialise, 64 pairs cover concurrent host threads
+            static const bool dyn = !(getenv("HK_MMA2_DYNAMIC") && atoi(getenv("HK_MMA2_DYNAMIC")) == 0);
+            static int* pool = nullptr;
+            static std::atomic<unsigned> next_slot{0};
+            static std::mutex pool_mu;
+            if (dyn && !pool) {
+                std::lock_guard<std::mutex> lk(pool_mu);
+                if (!pool) {
+                    int* d = nullptr;
+                    HK_CUDA(cudaMalloc(&d, 64 * 2 * sizeof(int)));
+                    HK_CUDA(cudaMemset(d, 0, 64 * 2 * sizeof(int)));
+                    pool = d;
+                }
+            }
+            if (dyn && (long long)grid * warps < batch) p.work = pool + 2 * (next_slot.fetch_add(1) % 64);
             count_launch();
-            kern<<<grid, 32 * warps, pad, stream>>>(p);
+            // Launched with programmatic stream serialization: if the previous kernel on this stream is this same kernel (the
+            // only one here that triggers early), the new grid's ramp-up overlaps its tail; after any other kernel or copy the
+            // attribute changes nothing.  The kernel waits for the previous grid before its first global store.
+            static const bool pdl = !(getenv("HK_MMA2_PDL") && atoi(getenv("HK_MMA2_PDL")) == 0);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * warps); cfg.dynamicSmemBytes = (size_t)pad; cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+            HK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
             HK_CUDA(cudaGetLastError());
             return HK_OK;
         }

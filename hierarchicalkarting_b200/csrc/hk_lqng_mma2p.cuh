@@ -83,7 +83,24 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (first >= p.batch) return;                                    // whole warps only; no block-wide sync below
+    // Work distribution: the first problem of a warp is static, the following ones come from a device-wide counter when the
+    // launcher provides one (p.work) — SMs differ by a few per cent in how fast they get through their problems, and a
+    // persistent launch ends with its slowest SM.  p.work[0] = next index - gridDim.x * WARPS, p.work[1] = warps that are done;
+    // the last warp to finish clears both for the next launch (every fetch of a warp precedes its own done-increment).
+    const bool dynamic = p.work != nullptr;
+    auto fetch = [&]() -> long long {                                // all lanes; returns the next problem of this warp
+        int v = 0;
+        if (lane == 0) v = atomicAdd(p.work, 1);
+        return nwarps + (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
+    auto finish = [&]() {
+        if (dynamic && lane == 0 && atomicAdd(p.work + 1, 1) == (int)nwarps - 1) { p.work[0] = 0; p.work[1] = 0; }
+    };
+    // Programmatic dependent launch: a following launch of this kernel on the same stream may start filling SMs as this one's
+    // warps exit (its ramp-up overlaps this launch's tail).  Such a dependent reads only its own inputs before
+    // griddepcontrol.wait, which it executes before its first global store (see below) — by then this grid has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (first >= p.batch) { asm volatile("griddepcontrol.wait;" ::: "memory"); finish(); return; }   // whole warps only; no block-wide sync below
 
     auto issue = [&](long long prob, int b) {                         // lane 0 only
         const unsigned bar = bar_u32 + 8u * b, dst = rec_u32 + (unsigned)(b * P2_STRIDE * 8);
@@ -133,11 +150,14 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
     const bool ylane = t < 2, podd = t & 1, godd = g & 1, rodd = rho & 1;
 
     int it = 0;
-    for (long long prob = first; prob < p.batch; prob += nwarps, ++it) {
+    long long nxt = dynamic ? fetch() : first + nwarps;
+    for (long long prob = first; prob < p.batch; ++it) {
         const int buf = it & 1;
         const double* rec = &sm.rec[wib][buf][0];
         __syncwarp();                                               // every lane is done with the other buffer
-        if (lane == 0 && prob + nwarps < p.batch) issue(prob + nwarps, buf ^ 1);
+        if (lane == 0 && nxt < p.batch) issue(nxt, buf ^ 1);
+        int after = 0;                                              // the problem after the next: fetched now, needed at the end
+        if (dynamic && lane == 0 && nxt < p.batch) after = atomicAdd(p.work, 1);
         mbar_wait(bar_u32 + 8u * buf, (unsigned)(it >> 1) & 1u);
 
         bool pivot = false, hard = false;
@@ -303,6 +323,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
         if (hard || pivot || __ballot_sync(0xffffffffu, redo_piv) == 0) break;
         pivot = true;
         }
+        if (it == 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // outputs of the previous launch are complete from here on
         if (hard) {
             // Warp-uniform and rare: non-symmetric Q/R or a zero / out-of-range pivot.
             if (lane == 0) while (atomicCAS(&sm.lock, 0, 1) != 0) {}
@@ -310,11 +331,15 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             if (lane < 8) lqng_generic_body<2>(p, prob, true, sm.fallback, lane, 0xffu);
             __syncwarp();
             if (lane == 0) { __threadfence_block(); atomicExch(&sm.lock, 0); }
-            continue;
+        } else {
+            if (isAug) p.u0[(size_t)prob * 4 + g] = u_out;
+            if (lane == 0 && p.status) p.status[prob] = 0;
         }
-        if (isAug) p.u0[(size_t)prob * 4 + g] = u_out;
-        if (lane == 0 && p.status) p.status[prob] = 0;
+        prob = nxt;
+        if (dynamic) nxt = nxt < p.batch ? nwarps + (long long)__shfl_sync(0xffffffffu, after, 0) : nxt;
+        else nxt += nwarps;
     }
+    finish();
 }
 
 }  // namespace hk
