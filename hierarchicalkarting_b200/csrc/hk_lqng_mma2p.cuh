@@ -220,15 +220,16 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
                 const int rs = (k >> 1 ? rb2 : rb) + 4 * (k & 1);
                 const double r0 = shfl_d(M0, rs), r1 = shfl_d(M1, rs);
                 const double pv = shfl_d(mine, 8 * (k >> 1) + 4 * (k & 1) + (k >> 1));
-                const unsigned hp = abs_hi(pv);
-                redo_piv |= (rho_chk > k) & (abs_hi(c) > hp);                               // MathNet would exchange rows
-                redo |= (hp - 0x33700000u) > 0x19000000u;                                  // |pv| outside 2^-200 .. 2^200
+                redo_piv |= (rho_chk > k) & (abs_hi(c) > abs_hi(pv));                       // MathNet would exchange rows
                 const double cz = rho == k ? 0.0 : c;
                 M0 = fma(pv, M0, -(cz * r0));
                 M1 = fma(pv, M1, -(cz * r1));
             }
             {
                 const double d = shfl_d(rodd ? M1 : M0, dsrc);
+                // One range test per sweep instead of one per pivot: the rows carry the product of the pivots, so a zero pivot
+                // leaves d = 0 and an overflow leaves inf / NaN; |d| in 2^-900 .. 2^900 keeps rcp_fast exact to 2^-60.
+                redo |= (abs_hi(d) - 0x07b00000u) > 0x70800000u;
                 const double rinv = rcp_fast(d);
                 M0 *= rinv; M1 *= rinv;
             }
