@@ -317,6 +317,16 @@ def main():
                     "config": "BASELINE config 4: Complex, 2 karts, depth 8, bucket 2, Philox4x32-10; host call incl. result D2H",
                     "gpu_launches": reps}
 
+    # ---- one solve at a time (BASELINE config 1: what HierarchicalKartAgent does at 50 Hz): latency of hk_lqng_solve_one ------------
+    one = [np.ascontiguousarray(a[:1]) for a in hp]
+    u1 = np.zeros(4)
+    for _ in range(20):
+        abi.check(lib.hk_lqng_solve_one(N, HORIZON, *[abi.dptr(a) for a in one], abi.dptr(u1)))
+    t0 = time.perf_counter()
+    for _ in range(200):
+        abi.check(lib.hk_lqng_solve_one(N, HORIZON, *[abi.dptr(a) for a in one], abi.dptr(u1)))
+    single_us = 1e6 * (time.perf_counter() - t0) / 200
+
     # ---- 4-kart LQNG (BASELINE config 3: 1,048,576 Complex 2v2 problems per GPU, HBM-resident) --------------------------------
     lqng4_obj = None
     if not args.no_lqng4:
@@ -420,6 +430,7 @@ def main():
                 "dense": {"value": world * batch * args.steps / e2e_dense_s, "unit": "solves/s", "h2d_bytes_per_step": h2d_bytes,
                           "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * e2e_dense_s / args.steps,
                           "api": "hk_lqng_solve_batch: dense A,B,Q,q,R,x0 records from pinned host buffers (PCIe-bound)"}},
+        "single_solve_latency_us": single_us,        # BASELINE config 1 through hk_lqng_solve_one (pageable host pointers, H2D + kernel + D2H + sync)
         "gpu_launches": gpu_launches, "clocks": clocks,
         "summary": {"status_nonzero": summary[0].item(), "u0_checksum": summary[1].item(), "problems": summary[2].item()},
     }

@@ -296,12 +296,12 @@ __device__ __forceinline__ int policy_index(const DevGame& g, int cnt, unsigned 
 
 // ---- table-driven ply (same results as legal_moves + select_kth + make_move, see DevGame) ---------------------------------
 struct Tables {
-    const int* dt; const unsigned char* order; const float* load; const float* radius;
+    const int* dt; const unsigned char* order; const float* load; const float* radius; const unsigned long long* lmask;
     int nv, nc;
     __device__ Tables(const DevGame& g)
         : dt(reinterpret_cast<const int*>(g.tables + g.off_dt)), order(g.tables + g.off_order),
           load(reinterpret_cast<const float*>(g.tables + g.off_load)), radius(reinterpret_cast<const float*>(g.tables + g.off_radius)),
-          nv(g.nv), nc(g.n_cand) {}
+          lmask(reinterpret_cast<const unsigned long long*>(g.tables + g.off_lmask)), nv(g.nv), nc(g.n_cand) {}
 };
 
 // velocity level of a kart's bucket if it is one of the action buckets (KartDiscreteGame.cs:329-340), else -1 (e.g. the root's (0, b))
@@ -319,22 +319,25 @@ __device__ __forceinline__ int fast_legal(const DevGame& g, const Tables& tb, co
     const int sidx = cs.section % g.n_sections, type = g.type_of[sidx], l0 = cs.lane - 1;
     const int os = (g.sec_flags[st.lastCompletedSection % g.n_sections] >> 2) & 3;                   // KartMCTS.cs:252
     const float wear = (float)cs.tireAge / 10000.0f;
-    float ms[4];
-#pragma unroll
-    for (int l1 = 0; l1 < 4; ++l1) ms[l1] = max_speed_radius_wear(g.karts[np], __ldg(&tb.radius[type * 16 + l0 * 4 + l1]), wear);   // :357
     const int maxdl = (g.sec_flags[sidx] & 1) ? g.p.maxLaneChanges - cs.laneChanges : 99;             // :346
-    ord = tb.order + ((((size_t)type * 4 + l0) * tb.nv + lvl) * 3 + os) * tb.nc;
+    const size_t cell = (((size_t)type * 4 + l0) * tb.nv + lvl) * 3 + os;
+    ord = tb.order + cell * tb.nc;
+    const unsigned long long* lm = tb.lmask + cell * 4 * tb.nv;
+    const int b = g.p.velocityBucketSize;
     mask = 0ull;
-    int cnt = 0;
-    for (int r = 0; r < tb.nc; ++r) {
-        const int gi = __ldg(&ord[r]);
-        if (gi == 255) break;                                                                         // statically infeasible from here on (:368)
-        const int l1 = gi & 3, v = 6 + (gi >> 2) * g.p.velocityBucketSize;
-        const bool ok = abs(l1 - l0) <= maxdl && !(ms[l1] < (float)v);
-        mask |= (unsigned long long)ok << r;
-        cnt += ok;
+    // Per target lane the speed filter !(maxSpeed < v) (:357) passes the velocity levels up to floor(maxSpeed) (v is an integer;
+    // a NaN limit passes all of them), and the statically feasible moves into that lane up to a level are one precomputed mask
+    // over the policy's rank order — no scan over the 4 nv candidates.
+#pragma unroll
+    for (int l1 = 0; l1 < 4; ++l1) {
+        if (abs(l1 - l0) > maxdl) continue;
+        const float ms = max_speed_radius_wear(g.karts[np], __ldg(&tb.radius[type * 16 + l0 * 4 + l1]), wear);
+        const int mi = (int)fminf(ms, 1000.0f);                                                         // fminf(NaN, x) = x
+        if (mi < 6) continue;
+        const int jm = min((mi - 6) / b, tb.nv - 1);
+        mask |= __ldg(&lm[l1 * tb.nv + jm]);
     }
-    return cnt;
+    return __popcll(mask);
 }
 
 __device__ __forceinline__ int nth_set_bit(unsigned long long mask, int n)
@@ -392,6 +395,19 @@ __global__ void build_tables_kernel(const DevGame* __restrict__ gg, unsigned cha
         int n_ok = 0;
         for (int gi = 0; gi < g.n_cand; ++gi) n_ok += keys[os][gi] != ~0ull;
         for (int r = 0; r < g.n_cand; ++r) order[os * g.n_cand + r] = r < n_ok ? (unsigned char)select_kth(keys[os], g.n_cand, r) : 255;
+    }
+    {   // masks over the rank order: moves into lane l1 with velocity level <= j, per optimal-lane sign
+        unsigned long long* lm = reinterpret_cast<unsigned long long*>(blob + g.off_lmask) + (size_t)id * 3 * 4 * g.nv;
+        for (int os = 0; os < 3; ++os)
+            for (int l1 = 0; l1 < 4; ++l1)
+                for (int j = 0; j < g.nv; ++j) {
+                    unsigned long long m = 0;
+                    for (int r = 0; r < g.n_cand; ++r) {
+                        const int gi = order[os * g.n_cand + r];
+                        if (gi != 255 && (gi & 3) == l1 && (gi >> 2) <= j) m |= 1ull << r;
+                    }
+                    lm[(os * 4 + l1) * g.nv + j] = m;
+                }
     }
     if (lvl == 0) {
         float* load = reinterpret_cast<float*>(blob + g.off_load);
@@ -707,7 +723,8 @@ extern "C" int hk_game_create(const hk_section* sections, int n_sections, const 
     d.off_order = (int)(cells * d.n_cand * 4);
     d.off_load = (int)((d.off_order + cells * 3 * d.n_cand + 15) & ~(size_t)15);
     d.off_radius = d.off_load + (int)((size_t)d.n_types * 16 * nv * 4);
-    d.table_bytes = d.off_radius + d.n_types * 16 * 4;
+    d.off_lmask = (d.off_radius + d.n_types * 16 * 4 + 15) & ~15;
+    d.table_bytes = d.off_lmask + (int)(cells * 3 * 4 * nv * 8);
     unsigned char* blob = nullptr;
     cudaError_t e = cudaMalloc(&g->dev, sizeof(DevGame));
     if (e == cudaSuccess) e = cudaMalloc(&blob, d.table_bytes);

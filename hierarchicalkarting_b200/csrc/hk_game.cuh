@@ -12,7 +12,7 @@ struct DevGame {
     int n_sections, n_karts, n_env_karts;
     int vmax;                                   // (int)GetMaxSpeed()  KartDiscreteGame.cs:329
     int n_cand;                                 // velocity levels x 4 lanes (generation-order index space)
-    int pad_[3];
+    int pad_[2];
     hk_game_params p;
     hk_kart karts[HK_MAX_KARTS];                // DiscreteGameState.kartAgents[i].m_Kart constants
     hk_kart env_karts[HK_MAX_ENV_KARTS];        // envController.Agents[player].m_Kart constants
@@ -24,11 +24,12 @@ struct DevGame {
     // policy's sort order — is tabulated per geometry TYPE; tyre load per (type, lane pair, max_velocity) likewise.
     int tables_ok;                              // 0: more than HK_MAX_TYPES geometries -> kernels use the direct path only
     int n_types, nv;                            // geometry types; velocity levels (n_cand = 4 nv)
-    int off_dt, off_order, off_load, off_radius, table_bytes;   // byte offsets into `tables`
+    int off_dt, off_order, off_load, off_radius, off_lmask, table_bytes;   // byte offsets into `tables`
     unsigned char type_of[HK_MAX_SECTIONS];     // section -> type
     unsigned char rep_section[HK_MAX_TYPES];    // a section of that type
     unsigned char sec_flags[HK_MAX_SECTIONS];   // bit0 straight(s), bit1 straight(s) != straight(s+1), bits 2-3 optimalLaneSign + 1
     const unsigned char* tables;                // device blob: dt int32[T][4][nv][nc] | order u8[T][4][nv][3][nc] | load f32[T][16][nv] | radius f32[T][16]
+                                                //              | lmask u64[T][4][nv][3][4][nv]: ranks of the moves into lane l1 with velocity level <= j
 };
 static_assert(sizeof(DevGame) % 4 == 0, "DevGame is copied word-wise");
 

@@ -168,6 +168,26 @@ def test_full_size_properties(hk, oracle):
     assert np.all(a["status"] == 0)
 
 
+def test_full_size_properties_4kart(hk, oracle):
+    """BASELINE config 3 shape (4-kart 2v2 Complex), 131,072 problems through the DMMA kernel: determinism, batch-permutation
+    equivariance, and a strided sample against the oracle; all outputs on a smaller slice."""
+    n = 131072
+    p = S.make_problems(S.COMPLEX, n, 4, seed=20260002)
+    A, B, Q, q, R, x0 = S.assemble_dense(p)
+    a = lqr.solve_batch(A, B, Q, q, R, x0, 3, full=False)
+    b = lqr.solve_batch(A, B, Q, q, R, x0, 3, full=False)
+    assert np.array_equal(a["u0"], b["u0"]) and np.all(a["status"] == 0)
+    perm = np.random.default_rng(1).permutation(n)[:32768]
+    c = lqr.solve_batch(A[perm], B[perm], Q[perm], q[perm], R[perm], x0[perm], 3, full=False)
+    assert np.array_equal(c["u0"], a["u0"][perm])
+    idx = np.arange(0, n, 509)
+    ref = oracle.lqng_solve_batch(A[idx], B[idx], Q[idx], q[idx], R[idx], x0[idx], 3)
+    for k, i in enumerate(idx):
+        assert rel_err(a["u0"][i], ref["u0"][k]) <= TOL
+    full = lqr.solve_batch(A[idx], B[idx], Q[idx], q[idx], R[idx], x0[idx], 3)
+    _check(full, ref)
+
+
 def test_assemble_on_device(hk, oracle):
     for N, track in ((2, S.OVAL), (4, S.COMPLEX), (1, S.OVAL), (3, S.COMPLEX)):
         p = S.make_problems(track, 300, N, seed=77)
