@@ -316,6 +316,15 @@ def main():
                     "plies_per_s": world * plies / el, "ms_per_decision": 1e3 * el / reps, "rollouts_per_decision": MCTS_ROLLOUTS,
                     "config": "BASELINE config 4: Complex, 2 karts, depth 8, bucket 2, Philox4x32-10; host call incl. result D2H",
                     "gpu_launches": reps}
+        try:                                             # the rollouts are bound by the SM issue rate, not by DRAM
+            with open(os.path.join(ROOT, "profiles", "mcts_issue.json")) as f:
+                wi = float(json.load(f)["warp_instr_per_rollout"])
+            peak_issue = 148 * 4 * 1.965e9                # one warp-instruction per cycle and SM sub-partition at the max SM clock
+            ach = mcts_obj["value"] / world * wi
+            mcts_obj["roofline"] = {"bound": "issue", "achieved": ach, "peak": peak_issue, "unit": "warp-instr/s", "frac": ach / peak_issue,
+                                    "note": f"{wi:.1f} executed warp-instructions per rollout (ncu, profiles/mcts_issue.json) x rollouts/s per GPU"}
+        except Exception:
+            pass
 
     # ---- one solve at a time (BASELINE config 1: what HierarchicalKartAgent does at 50 Hz): latency of hk_lqng_solve_one ------------
     one = [np.ascontiguousarray(a[:1]) for a in hp]

@@ -1,6 +1,8 @@
 import time, numpy as np, torch, sys
 sys.path.insert(0,'/root/repo')
+import os
 from hierarchicalkarting_b200 import abi, scenarios as S
+if os.environ.get("HK_LIB_PATH"): abi.LIB_PATH = os.environ["HK_LIB_PATH"]
 lib=abi.load_library(); abi.check(lib.hk_init(0))
 dev=torch.device('cuda',0)
 for N,track,batch in ((4,S.COMPLEX,65536),(3,S.COMPLEX,65536),(1,S.OVAL,262144),(2,S.OVAL,65536)):
