@@ -29,6 +29,9 @@ struct LqngParams {
     const int* redo_count;
     int* reset_count;          // counter of the NEXT launch, cleared here (stream order makes that safe)
     int* work;                 // persistent 2-kart kernel: {next problem - resident warps, warps done}; zero between launches
+    // compact (fused assembly) mode of the 2-kart kernel: hk_lqng_assemble_solve_batch's arrays + (cos h, sin h) per player
+    const double *c_x0, *c_target, *c_tw, *c_cw, *c_aw, *c_otgt, *c_otw, *c_cs;
+    double dt;
 };
 
 template <int N>
@@ -362,12 +365,105 @@ __global__ void lqng_assemble_kernel(int batch, int N, double dt, const double* 
     }
 }
 
+// Persistent TMA-staged 2-kart kernel (hk_lqng_mma2p.cuh): dense records (p.A .. p.x0) or, with `compact`, the description of
+// hk_lqng_assemble_solve_batch (p.c_*), assembled by the warp in shared memory.
+static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact)
+{
+    const int batch = p.batch;
+    static const int variant_env = getenv("HK_MMA2_VARIANT") ? atoi(getenv("HK_MMA2_VARIANT")) : 2;
+    const int variant = variant_env >= 1 ? variant_env : 2;
+    // variant 1: 4 warps per CTA, MINB resident CTAs per SM; variant 2 (default): one warp per CTA, MINB resident warps
+    // per SM.  16 warps x 128 registers is the measured optimum (profiles/lqng_mma2_tuning_r01.md).
+    static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : (variant == 2 ? 16 : 4);
+    const int warps = (compact || variant == 2) ? 1 : 4;
+    void (*kern)(LqngParams) = nullptr;
+    if (compact) {
+        kern = lqng_mma2p_kernel<16, 1, true>;
+    } else if (variant == 2) {
+        kern = minb >= 32 ? lqng_mma2p_kernel<32, 1> : minb >= 24 ? lqng_mma2p_kernel<24, 1> : minb >= 20 ? lqng_mma2p_kernel<20, 1>
+               : minb >= 16 ? lqng_mma2p_kernel<16, 1> : lqng_mma2p_kernel<12, 1>;
+    } else {
+        kern = minb >= 8 ? lqng_mma2p_kernel<8, 4> : minb >= 6 ? lqng_mma2p_kernel<6, 4> : minb == 5 ? lqng_mma2p_kernel<5, 4>
+               : lqng_mma2p_kernel<4, 4>;
+    }
+    static int resident_of[2] = {0, 0};                        // persistent grid: SMs x resident CTAs (dense, compact)
+    int& resident = resident_of[compact ? 1 : 0];
+    static const int pad = getenv("HK_MMA2_PAD_SMEM") ? atoi(getenv("HK_MMA2_PAD_SMEM")) : 0;   // occupancy experiments only
+    if (!resident) {
+        int dev = 0, sms = 0, occ = 0;
+        HK_CUDA(cudaGetDevice(&dev));
+        HK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (pad) HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+        HK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * warps, pad));
+        resident = sms * (occ > 0 ? occ : 1);
+    }
+    const long long want = ((long long)batch + warps - 1) / warps;
+    const unsigned grid = (unsigned)(want < resident ? want : resident);
+    // dynamic work distribution: a pool of zero-initialised counter pairs, one per launch in flight (the kernel's
+    // last warp clears its pair); launches on one stream serialise, 64 pairs cover concurrent host threads
+    static const bool dyn = !(getenv("HK_MMA2_DYNAMIC") && atoi(getenv("HK_MMA2_DYNAMIC")) == 0);
+    static int* pool = nullptr;
+    static std::atomic<unsigned> next_slot{0};
+    static std::mutex pool_mu;
+    if (dyn && !pool) {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        if (!pool) {
+            int* d = nullptr;
+            HK_CUDA(cudaMalloc(&d, 64 * 2 * sizeof(int)));
+            HK_CUDA(cudaMemset(d, 0, 64 * 2 * sizeof(int)));
+            pool = d;
+        }
+    }
+    if (dyn && (long long)grid * warps < batch) p.work = pool + 2 * (next_slot.fetch_add(1) % 64);
+    count_launch();
+    // Launched with programmatic stream serialization: if the previous kernel on this stream is this same kernel (the
+    // only one here that triggers early), the new grid's ramp-up overlaps its tail; after any other kernel or copy the
+    // attribute changes nothing.  The kernel waits for the previous grid before its first global store.
+    static const bool pdl = !(getenv("HK_MMA2_PDL") && atoi(getenv("HK_MMA2_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * warps); cfg.dynamicSmemBytes = (size_t)pad; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    HK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    HK_CUDA(cudaGetLastError());
+    return HK_OK;
+}
+
+// (cos h, sin h) of every player: the one transcendental of the assembly, evaluated one thread per player (a warp of the
+// solve kernel would spend a whole sincos instruction sequence on two useful lanes)
+__global__ void lqng_trig_kernel(long long n_players_total, const double* __restrict__ x0, double* __restrict__ cs)
+{
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_players_total) return;
+    const double h = x0[id * 4 + 3];
+    cs[id * 2] = cos(h);
+    cs[id * 2 + 1] = sin(h);
+}
+
 int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double* dx0, const double* dtarget,
                          const double* dtw, const double* dcw, const double* daw, const double* dotgt, const double* dotw,
                          double* du0, int* dstatus, cudaStream_t stream, int scratch_slot)
 {
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
+    static const bool fused = !(getenv("HK_LQNG_FUSED_ASSEMBLY") && atoi(getenv("HK_LQNG_FUSED_ASSEMBLY")) == 0);
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(dx0) | reinterpret_cast<uintptr_t>(dtarget) | reinterpret_cast<uintptr_t>(dtw) |
+                             reinterpret_cast<uintptr_t>(dcw) | reinterpret_cast<uintptr_t>(daw) | reinterpret_cast<uintptr_t>(dotgt) |
+                             reinterpret_cast<uintptr_t>(dotw)) & 15) == 0;
+    if (N == 2 && fused && aligned16 && batch > 0) {
+        // 2-kart game: no dense records in HBM at all — the solve kernel stages the 352-byte description by TMA and assembles
+        // A, B, Q, q, R in shared memory (hk_lqng_mma2p.cuh, COMPACT)
+        double* dcs = (double*)dscratch(c, scratch_slot, sizeof(double) * 4 * (size_t)batch);
+        if (!dcs) return HK_ERR_OUT_OF_MEMORY;
+        const long long np = (long long)batch * 2;
+        count_launch(); lqng_trig_kernel<<<(unsigned)((np + 255) / 256), 256, 0, stream>>>(np, dx0, dcs);
+        HK_CUDA(cudaGetLastError());
+        LqngParams p{batch, horizon, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, du0, nullptr, nullptr, nullptr, dstatus,
+                     nullptr, nullptr, nullptr, nullptr, dx0, dtarget, dtw, dcw, daw, dotgt, dotw, dcs, dt};
+        return launch_mma2p(p, stream, true);
+    }
     const int n = 4 * N;
     const size_t per = (size_t)N * 16 + N * 8 + (size_t)N * n * n + (size_t)N * n + N * 4 + n;
     double* d = (double*)dscratch(c, scratch_slot, per * sizeof(double) * (size_t)batch);
@@ -386,69 +482,15 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
                 double* dtraj, int* dstatus, cudaStream_t stream)
 {
     if (batch == 0) return HK_OK;
-    LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr, nullptr};
+    LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr, nullptr,
+                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0};
     static const bool force_generic = getenv("HK_LQNG_FORCE_GENERIC") != nullptr;
     if (N == 2 && !time_varying && !dP && !dalpha && !dtraj && !force_generic) {
         // throughput path: one launch of a DMMA kernel (problems it cannot take fall back inside the kernel)
         static const int variant = getenv("HK_MMA2_VARIANT") ? atoi(getenv("HK_MMA2_VARIANT")) : 2;   // 0: one CTA per 4 problems; 1, 2: persistent + TMA
         const bool aligned = ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dQ) |
                                reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dR) | reinterpret_cast<uintptr_t>(dx0)) & 15) == 0;
-        if (variant >= 1 && aligned) {                                 // cp.async.bulk needs 16-byte aligned sources
-            // variant 1: 4 warps per CTA, MINB resident CTAs per SM; variant 2 (default): one warp per CTA, MINB resident warps
-            // per SM.  16 warps x 128 registers is the measured optimum (profiles/lqng_mma2_tuning_r01.md).
-            static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : (variant == 2 ? 16 : 4);
-            static const int warps = variant == 2 ? 1 : 4;
-            void (*kern)(LqngParams) = nullptr;
-            if (variant == 2) {
-                kern = minb >= 32 ? lqng_mma2p_kernel<32, 1> : minb >= 24 ? lqng_mma2p_kernel<24, 1> : minb >= 20 ? lqng_mma2p_kernel<20, 1>
-                       : minb >= 16 ? lqng_mma2p_kernel<16, 1> : lqng_mma2p_kernel<12, 1>;
-            } else {
-                kern = minb >= 8 ? lqng_mma2p_kernel<8, 4> : minb >= 6 ? lqng_mma2p_kernel<6, 4> : minb == 5 ? lqng_mma2p_kernel<5, 4>
-                       : lqng_mma2p_kernel<4, 4>;
-            }
-            static int resident = 0;                                   // persistent grid: SMs x resident CTAs
-            static const int pad = getenv("HK_MMA2_PAD_SMEM") ? atoi(getenv("HK_MMA2_PAD_SMEM")) : 0;   // occupancy experiments only
-            if (!resident) {
-                int dev = 0, sms = 0, occ = 0;
-                HK_CUDA(cudaGetDevice(&dev));
-                HK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-                if (pad) HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
-                HK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * warps, pad));
-                resident = sms * (occ > 0 ? occ : 1);
-            }
-            const long long want = ((long long)batch + warps - 1) / warps;
-            const unsigned grid = (unsigned)(want < resident ? want : resident);
-            // dynamic work distribution: a pool of zero-initialised counter pairs, one per launch in flight (the kernel's
-            // last warp clears its pair); launches on one stream serialise, 64 pairs cover concurrent host threads
-            static const bool dyn = !(getenv("HK_MMA2_DYNAMIC") && atoi(getenv("HK_MMA2_DYNAMIC")) == 0);
-            static int* pool = nullptr;
-            static std::atomic<unsigned> next_slot{0};
-            static std::mutex pool_mu;
-            if (dyn && !pool) {
-                std::lock_guard<std::mutex> lk(pool_mu);
-                if (!pool) {
-                    int* d = nullptr;
-                    HK_CUDA(cudaMalloc(&d, 64 * 2 * sizeof(int)));
-                    HK_CUDA(cudaMemset(d, 0, 64 * 2 * sizeof(int)));
-                    pool = d;
-                }
-            }
-            if (dyn && (long long)grid * warps < batch) p.work = pool + 2 * (next_slot.fetch_add(1) % 64);
-            count_launch();
-            // Launched with programmatic stream serialization: if the previous kernel on this stream is this same kernel (the
-            // only one here that triggers early), the new grid's ramp-up overlaps its tail; after any other kernel or copy the
-            // attribute changes nothing.  The kernel waits for the previous grid before its first global store.
-            static const bool pdl = !(getenv("HK_MMA2_PDL") && atoi(getenv("HK_MMA2_PDL")) == 0);
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * warps); cfg.dynamicSmemBytes = (size_t)pad; cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-            HK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
-            HK_CUDA(cudaGetLastError());
-            return HK_OK;
-        }
+        if (variant >= 1 && aligned) return launch_mma2p(p, stream, false);   // cp.async.bulk needs 16-byte aligned sources
         static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : 5;   // tuning knob, see DESIGN.md §4
         const int wpb = MMA2_THREADS / 32;
         const unsigned grid = (unsigned)((batch + wpb - 1) / wpb);

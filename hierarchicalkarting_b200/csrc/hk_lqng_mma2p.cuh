@@ -29,9 +29,15 @@ constexpr int P2_oQ = 0, P2_oA = 128, P2_oB = 160, P2_oq = 176, P2_oR = 192, P2_
 constexpr int P2_STRIDE = 216;                  // record + constant tail, 1,728 B
 constexpr unsigned P2_TX_BYTES = 1664;
 
+// compact (fused assembly) mode: the problem arrives as the constructor arguments of the reference's providers
+// (include/hk_abi.h, hk_lqng_assemble_solve_batch) plus (cos h, sin h) per player; staging offsets in doubles
+constexpr int C2_ox = 0, C2_otg = 8, C2_otw = 16, C2_ocw = 24, C2_oaw = 26, C2_oot = 30, C2_oow = 38, C2_ocs = 44, C2_STRIDE = 48;
+constexpr unsigned C2_TX_BYTES = 384;
+
 template <int WARPS>
 struct P2Smem {
     double rec[WARPS][2][P2_STRIDE];
+    double stage[WARPS][2][C2_STRIDE];           // compact mode only
     double fallback[GenericLayout<2>::total];    // one pivoting scratch per CTA, serialised by `lock` (rare path)
     unsigned long long bar[WARPS][2];
     int lock;
@@ -65,7 +71,10 @@ __device__ __forceinline__ bool bits_differ(double a, double b)
 // WARPS = warps per CTA.  WARPS == 1 makes every address of the TMA issue path a function of blockIdx.x only, i.e.
 // provably warp-uniform: the copies are issued from uniform registers without the elect/broadcast loops the compiler
 // otherwise wraps around each cp.async.bulk, and the loop state lives in uniform registers.
-template <int MINB, int WARPS>
+// COMPACT: the warp assembles its dense record in shared memory from the staged compact description — LinearizedBicycle.getA/getB
+// (KartLQRDynamics.cs:40-62) and LQRCheckpointReachAvoidCost.getQMatrix/getQVec/getRMatrix (KartLQRCosts.cs:57-140, quirks Q3-Q5 of
+// SURVEY.md A.3), same arithmetic as lqng_assemble_kernel — instead of reading a dense record another kernel wrote to HBM.
+template <int MINB, int WARPS, bool COMPACT = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams p)
 {
     __shared__ __align__(128) P2Smem<WARPS> sm;
@@ -102,9 +111,23 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (first >= p.batch) { asm volatile("griddepcontrol.wait;" ::: "memory"); finish(); return; }   // whole warps only; no block-wide sync below
 
+    const unsigned stage_u32 = smem_u32(&sm.stage[wib][0][0]);
     auto issue = [&](long long prob, int b) {                         // lane 0 only
         const unsigned bar = bar_u32 + 8u * b, dst = rec_u32 + (unsigned)(b * P2_STRIDE * 8);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of this buffer come first
+        if (COMPACT) {
+            const unsigned sd = stage_u32 + (unsigned)(b * C2_STRIDE * 8);
+            mbar_expect_tx(bar, C2_TX_BYTES);
+            bulk_g2s(sd + C2_ox * 8, p.c_x0 + (size_t)prob * 8, 64, bar);
+            bulk_g2s(sd + C2_otg * 8, p.c_target + (size_t)prob * 8, 64, bar);
+            bulk_g2s(sd + C2_otw * 8, p.c_tw + (size_t)prob * 8, 64, bar);
+            bulk_g2s(sd + C2_ocw * 8, p.c_cw + (size_t)prob * 2, 16, bar);
+            bulk_g2s(sd + C2_oaw * 8, p.c_aw + (size_t)prob * 4, 32, bar);
+            bulk_g2s(sd + C2_oot * 8, p.c_otgt + (size_t)prob * 8, 64, bar);
+            bulk_g2s(sd + C2_oow * 8, p.c_otw + (size_t)prob * 6, 48, bar);
+            bulk_g2s(sd + C2_ocs * 8, p.c_cs + (size_t)prob * 4, 32, bar);
+            return;
+        }
         mbar_expect_tx(bar, P2_TX_BYTES);
         bulk_g2s(dst + P2_oQ * 8, p.Q + (size_t)prob * 128, 1024, bar);
         bulk_g2s(dst + P2_oA * 8, p.A + (size_t)prob * 32, 256, bar);
@@ -153,12 +176,54 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
     long long nxt = dynamic ? fetch() : first + nwarps;
     for (long long prob = first; prob < p.batch; ++it) {
         const int buf = it & 1;
-        const double* rec = &sm.rec[wib][buf][0];
+        const double* rec = &sm.rec[wib][COMPACT ? 0 : buf][0];
         __syncwarp();                                               // every lane is done with the other buffer
         if (lane == 0 && nxt < p.batch) issue(nxt, buf ^ 1);
         int after = 0;                                              // the problem after the next: fetched now, needed at the end
         if (dynamic && lane == 0 && nxt < p.batch) after = atomicAdd(p.work, 1);
         mbar_wait(bar_u32 + 8u * buf, (unsigned)(it >> 1) & 1u);
+        if (COMPACT) {
+            // assemble the dense record (layout P2_o*) from the staged description; every lane writes a few entries
+            double* r = &sm.rec[wib][0][0];
+            const double* c = &sm.stage[wib][buf][0];
+            *reinterpret_cast<double2*>(r + P2_oQ + 4 * lane) = make_double2(0.0, 0.0);           // Q_0, Q_1 = 0 (128 doubles)
+            *reinterpret_cast<double2*>(r + P2_oQ + 4 * lane + 2) = make_double2(0.0, 0.0);
+            {   // A_i = I + dt [[0,0,cos h,-v sin h],[0,0,sin h,v cos h],0,0]  (KartLQRDynamics.cs:44-48), entry `lane` of A[2][4][4]
+                const int i = lane >> 4, rr_ = (lane >> 2) & 3, cc = lane & 3;
+                const double ch = c[C2_ocs + 2 * i], sh = c[C2_ocs + 2 * i + 1], v = c[C2_ox + 4 * i + 2];
+                double a = rr_ == cc ? 1.0 : 0.0;
+                if (rr_ == 0 && cc == 2) a = ch * p.dt;
+                if (rr_ == 1 && cc == 2) a = sh * p.dt;
+                if (rr_ == 0 && cc == 3) a = -sh * p.dt * v;
+                if (rr_ == 1 && cc == 3) a = ch * p.dt * v;
+                r[P2_oA + lane] = a;
+            }
+            if (lane < 16) {                                        // B_i (:57-59), q_i (KartLQRCosts.cs:109-124)
+                const int e = lane & 7, rr_ = e >> 1, cc = e & 1;
+                r[P2_oB + lane] = ((rr_ == 2 && cc == 0) || (rr_ == 3 && cc == 1)) ? p.dt : 0.0;
+                const int i = lane >> 3, s_ = lane & 7;
+                double qv;
+                if (s_ < 4) qv = (-c[C2_otg + 4 * i + s_]) * c[C2_otw + 4 * i + s_];
+                else { qv = c[C2_oot + 4 * i + s_ - 4]; if (s_ < 7) qv = qv * -c[C2_oow + 3 * i + s_ - 4]; }
+                r[P2_oq + lane] = qv;
+            } else if (lane < 24) {                                 // R_i = controlWeight I (:136), x0
+                const int e = lane - 16, i = e >> 2;
+                r[P2_oR + e] = ((e & 3) == 0 || (e & 3) == 3) ? c[C2_ocw + i] : 0.0;
+                r[P2_ox + e] = c[C2_ox + e];
+            }
+            __syncwarp();
+            if (lane < 24) {                                        // the 12 non-zeros of each Q_i (:64-94; diag 4,5 overwritten: quirk Q4)
+                const int i = lane / 12, j = lane % 12;
+                double* Qi = r + P2_oQ + 64 * i;
+                const double* aw = c + C2_oaw + 2 * i;
+                if (j < 4) Qi[j * 9] = (j < 2 ? (0.0 - aw[j]) : 0.0) + c[C2_otw + 4 * i + j];
+                else if (j < 7) Qi[j * 9] = -c[C2_oow + 3 * i + j - 4];
+                else if (j == 7) {}
+                else if (j < 10) Qi[(j - 8) * 8 + 4 + (j - 8)] = aw[j - 8];
+                else Qi[(4 + j - 10) * 8 + (j - 10)] = aw[j - 10];
+            }
+            __syncwarp();
+        }
 
         bool pivot = false, hard = false;
         double u_out = 0.0;
@@ -187,9 +252,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             const double2 qv = *reinterpret_cast<const double2*>(rec + offQv);                      // eta_i = q_i (:63), lanes (4+i, t)
             z00 = q0.x; z01 = q0.y; z10 = q1.x; z11 = q1.y; e0 = qv.x; e1 = qv.y;
             // symmetry of Q_i and R_i is what lets Z_i's R-form stand in for its T-form
-            redo = bits_differ(rec[(2 * t) * 8 + g], q0.x) | bits_differ(rec[(2 * t + 1) * 8 + g], q0.y) |
-                   bits_differ(rec[64 + (2 * t) * 8 + g], q1.x) | bits_differ(rec[64 + (2 * t + 1) * 8 + g], q1.y) |
-                   bits_differ(rec[P2_oR + 1], rec[P2_oR + 2]) | bits_differ(rec[P2_oR + 5], rec[P2_oR + 6]);
+            redo = false;                                           // assembled Q_i, R_i are symmetric by construction
+            if (!COMPACT)
+                redo = bits_differ(rec[(2 * t) * 8 + g], q0.x) | bits_differ(rec[(2 * t + 1) * 8 + g], q0.y) |
+                       bits_differ(rec[64 + (2 * t) * 8 + g], q1.x) | bits_differ(rec[64 + (2 * t + 1) * 8 + g], q1.y) |
+                       bits_differ(rec[P2_oR + 1], rec[P2_oR + 2]) | bits_differ(rec[P2_oR + 5], rec[P2_oR + 6]);
         }
         // W: rows 0..3 = stacked B_i^T Z_i, rows 4+i = eta_i (+ Z_i beta from the second step on)
         double w0 = e0, w1 = e1;
@@ -329,7 +396,13 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             // Warp-uniform and rare: non-symmetric Q/R or a zero / out-of-range pivot.
             if (lane == 0) while (atomicCAS(&sm.lock, 0, 1) != 0) {}
             __syncwarp();
-            if (lane < 8) lqng_generic_body<2>(p, prob, true, sm.fallback, lane, 0xffu);
+            if (COMPACT) {
+                LqngParams q = p;                                   // the assembled record is the only dense copy: solve it in place
+                double* r = &sm.rec[wib][0][0];
+                q.A = r + P2_oA; q.B = r + P2_oB; q.Q = r + P2_oQ; q.q = r + P2_oq; q.R = r + P2_oR; q.x0 = r + P2_ox;
+                q.u0 = p.u0 + (size_t)prob * 4; q.status = p.status ? p.status + prob : nullptr; q.time_varying = 0;
+                if (lane < 8) lqng_generic_body<2>(q, 0, true, sm.fallback, lane, 0xffu);
+            } else if (lane < 8) lqng_generic_body<2>(p, prob, true, sm.fallback, lane, 0xffu);
             __syncwarp();
             if (lane == 0) { __threadfence_block(); atomicExch(&sm.lock, 0); }
         } else {
