@@ -187,6 +187,53 @@ extern "C" int hk_lqng_solve_batch(int batch, int n_players, int horizon, int ti
     const size_t in_elems = eA + eB + eQ + eq + eR + n;
     const bool needPa = P || alpha || traj;
     const size_t out_elems = (size_t)m + (needPa ? (size_t)T * (m * n + m) : 0) + (traj ? (size_t)(T + 1) * n : 0);
+    if ((in_elems + out_elems) * sizeof(double) * (size_t)batch <= (256u << 10)) {
+        // Small calls — the reference's own pattern is ONE solve per agent and physics step (HierarchicalKartAgent.cs:319-325) —
+        // are latency-bound by the number of copies, not by bytes: gather the six operand arrays into one pinned staging
+        // buffer, one H2D copy, one launch, one D2H copy of every requested output.
+        const size_t in_b = in_elems * sizeof(double) * batch, out_b = out_elems * sizeof(double) * batch + sizeof(int) * batch;
+        char* h = (char*)hscratch(c, 0, in_b + out_b);
+        char* d = (char*)dscratch(c, 2, in_b + out_b + 64);
+        if (!h || !d) return HK_ERR_OUT_OF_MEMORY;
+        const double* src[6] = {A, B, Q, q, R, x0};
+        const size_t per[6] = {eA, eB, eQ, eq, eR, (size_t)n};
+        // A handful of problems: skip the copies altogether — pinned staging memory is device-accessible (UVA), the kernel reads
+        // its operands and writes its results over PCIe directly (one launch + one synchronise).
+        static const int zc_max = getenv("HK_ZEROCOPY_MAX") ? atoi(getenv("HK_ZEROCOPY_MAX")) : 4;
+        const bool zero_copy = batch <= zc_max;
+        if (zero_copy) d = h;
+        double* hp = (double*)h;
+        double* dp[6];
+        double* dcur = (double*)d;
+        for (int i = 0; i < 6; ++i) {
+            std::memcpy(hp, src[i], per[i] * sizeof(double) * batch);
+            dp[i] = dcur;
+            hp += per[i] * batch; dcur += per[i] * batch;
+        }
+        double* du = dcur;
+        double* dP = needPa ? du + (size_t)m * batch : nullptr;
+        double* da = needPa ? dP + (size_t)T * m * n * batch : nullptr;
+        double* dt = traj ? da + (size_t)T * m * batch : nullptr;
+        double* dend = traj ? dt + (size_t)(T + 1) * n * batch : (needPa ? da + (size_t)T * m * batch : du + (size_t)m * batch);
+        int* dst = (int*)dend;
+        cudaStream_t s = c->stream;
+        if (!zero_copy) HK_CUDA(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, s));
+        rc = lqng_launch(batch, N, horizon, time_varying ? 1 : 0, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], du, dP, da, dt, dst, s);
+        if (rc) return rc;
+        if (!zero_copy) HK_CUDA(cudaMemcpyAsync(h + in_b, du, out_b, cudaMemcpyDeviceToHost, s));
+        HK_CUDA(cudaStreamSynchronize(s));
+        const char* ho = h + in_b;
+        std::memcpy(u0, ho, sizeof(double) * m * batch); ho += sizeof(double) * m * batch;
+        if (needPa) {
+            if (P) std::memcpy(P, ho, sizeof(double) * T * m * n * batch);
+            ho += sizeof(double) * T * m * n * batch;
+            if (alpha) std::memcpy(alpha, ho, sizeof(double) * T * m * batch);
+            ho += sizeof(double) * T * m * batch;
+        }
+        if (traj) { std::memcpy(traj, ho, sizeof(double) * (T + 1) * n * batch); ho += sizeof(double) * (T + 1) * n * batch; }
+        if (status) std::memcpy(status, ho, sizeof(int) * batch);
+        return HK_OK;
+    }
     const int nchunks = batch >= 8192 ? 4 : 1;
     const int chunk = (batch + nchunks - 1) / nchunks;
     // two device buffers (double buffering) sized for one chunk each
