@@ -195,3 +195,48 @@ def test_assemble_on_device(hk, oracle):
         got = lqr.assemble_solve_batch(p, 3)
         for b in range(300):
             assert rel_err(got["u0"][b], ref["u0"][b]) <= TOL
+
+
+def test_reentrant_from_several_host_threads(hk, oracle):
+    """The reference calls the solver from the Unity main thread and the MCTS from one background thread per agent
+    (HierarchicalKartAgent.cs:246-283): concurrent host threads get their own stream / scratch and must not disturb each other
+    (large batches through the persistent kernel with its shared counter pool, small calls, rollouts)."""
+    import threading
+    from hierarchicalkarting_b200 import mcts as M, tracks
+    probs = [S.assemble_dense(S.make_problems(S.OVAL, 20000 + 37 * k, 2, seed=500 + k)) for k in range(4)]
+    want = [lqr.solve_batch(*p, 3, full=False)["u0"] for p in probs]
+    G = M.Game(tracks.COMPLEX, 2, 2)
+    leaf = tracks.root_state(tracks.COMPLEX, 5, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 40])
+    want_r = G.rollouts(leaf, 50000, seed=9)
+    errors = []
+
+    def lq_worker(k):
+        try:
+            for rep in range(6):
+                got = lqr.solve_batch(*probs[k], 3, full=False)["u0"]
+                if not np.array_equal(got, want[k]):
+                    errors.append(("lqng", k, rep))
+                one = lqr.solve_batch(*(a[:1] for a in probs[k]), 3, full=False)["u0"]
+                if not np.array_equal(one[0], want[k][0]):
+                    errors.append(("lqng-one", k, rep))
+        except Exception as e:                                   # noqa: BLE001
+            errors.append(("exc", k, repr(e)))
+
+    def mcts_worker():
+        try:
+            for rep in range(6):
+                got = G.rollouts(leaf, 50000, seed=9)
+                if not (np.array_equal(got["visit"], want_r["visit"]) and np.allclose(got["reward_sum"], want_r["reward_sum"], rtol=1e-12, atol=1e-9)):
+                    errors.append(("mcts", rep))
+        except Exception as e:                                   # noqa: BLE001
+            errors.append(("exc-mcts", repr(e)))
+
+    threads = [threading.Thread(target=lq_worker, args=(k,)) for k in range(4)] + [threading.Thread(target=mcts_worker)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
+    ref = oracle.lqng_solve_batch(*(a[:64] for a in probs[0]), 3, full=False)["u0"]
+    for b in range(64):
+        assert rel_err(want[0][b], ref[b]) <= TOL
