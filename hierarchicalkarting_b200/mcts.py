@@ -231,9 +231,19 @@ class KartMCTS:
         game = node.state.game
         moves = node.state.nextMoves()
         created = 0
-        for move in moves:                              # initials[j] = new KartMCTSNode(node.state.makeMove(action), node) (:142)
-            if move not in node.children:
-                node.children[move] = KartMCTSNode(node.state.makeMove(move), node)
+        new = [mv for mv in moves if mv not in node.children]   # initials[j] = new KartMCTSNode(node.state.makeMove(action), node) (:142)
+        if new:                                         # one batched replay call makes every missing child
+            out = game.replay([node.state.state] * len(new), np.array([[list(mv)] for mv in new], dtype=np.int32))
+            for j, mv in enumerate(new):
+                st = abi.hk_game_state()
+                C.memmove(C.byref(st), out["states"][j, 1:2].ctypes.data, C.sizeof(abi.hk_game_state))
+                child = DiscreteGameState(game, st)
+                nm, ns = int(out["n_moves"][j, 1]), int(out["n_scores"][j, 1])   # the same call already evaluated the child
+                child._info = dict(upnext=int(out["upnext"][j, 1]), over=int(out["over"][j, 1]),
+                                   scores=[float(x) for x in out["scores"][j, 1, :ns]],
+                                   moves=[tuple(int(v) for v in out["moves"][j, 1, k]) for k in range(max(nm, 0))],
+                                   moves_index=[int(v) for v in out["moves_index"][j, 1, :max(nm, 0)]])
+                node.children[mv] = KartMCTSNode(child, node)
                 created += 1
         kids = [node.children[mv] for mv in moves]
         R = KartMCTS.rollouts_per_leaf
