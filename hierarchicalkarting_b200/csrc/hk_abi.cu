@@ -65,6 +65,8 @@ ThreadCtx::~ThreadCtx()
     for (auto& b : dbuf) if (b) cudaFree(b);
     for (auto& b : hbuf) if (b) cudaFreeHost(b);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : pev) if (e) cudaEventDestroy(e);
+    for (auto& st : cstream) if (st) cudaStreamDestroy(st);
     if (stream) cudaStreamDestroy(stream);
     if (stream2) cudaStreamDestroy(stream2);
 }
@@ -80,6 +82,9 @@ ThreadCtx* ctx()
             return nullptr;
         }
         for (auto& e : c.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        for (auto& e : c.pev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        for (auto& st : c.cstream)
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return nullptr; }
         c.ready = true;
     }
     return &c;
@@ -282,6 +287,21 @@ extern "C" int hk_lqng_solve_one(int n_players, int horizon, const double* A, co
     return hk_lqng_solve_batch(1, n_players, horizon, 0, A, B, Q, q, R, x0, u0, nullptr, nullptr, nullptr, nullptr);
 }
 
+// Ingest kernel of the zero-copy mode (HK_E2E_COPY_MODE=2, an experiment kept behind its knob): the caller's pinned arrays are
+// device-accessible under UVA, so one kernel pulls a chunk of all seven over PCIe with 16-byte loads instead of seven copies.
+struct IngestArgs { const double2* src[7]; double2* dst[7]; long long n2[7]; };
+__global__ void lqng_ingest_kernel(IngestArgs a)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x, id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+        for (long long e = id; e < a.n2[i]; e += stride) a.dst[i][e] = a.src[i][e];
+}
+
+// Host-pointer entry of the compact description.  Pipeline over chunks of the batch: the seven H2D copies of a chunk go to
+// dedicated copy streams (round robin) and never queue behind a solve or a D2H; the assembly + solve of chunk k (compute
+// stream k & 1) waits on the chunk's "copied in" event, its results go back on the same compute stream.  Chunk buffers form a
+// ring of four, a copy into a ring slot waits for the slot's previous tenant to have drained.
 extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizon, double dt, const double* x0, const double* target,
                                             const double* tw, const double* cw, const double* aw, const double* otgt, const double* otw,
                                             double* u0, int* status)
@@ -297,33 +317,77 @@ extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizo
     const double* src[7] = {x0, target, tw, cw, aw, otgt, otw};
     size_t per = 0;
     for (int i = 0; i < 7; ++i) per += e[i];
-    // chunked two-stream pipeline: H2D of chunk k+1 overlaps assembly + solve of chunk k and D2H of chunk k-1
-    static const int chunks_env = getenv("HK_E2E_CHUNKS") ? atoi(getenv("HK_E2E_CHUNKS")) : 0;    // tuning knob
-    const int nchunks = batch >= 8192 ? (chunks_env > 0 ? chunks_env : 4) : 1;
-    const int chunk = (batch + nchunks - 1) / nchunks;
-    cudaStream_t streams[2] = {c->stream, c->stream2};
-    double* dbufs[2] = {nullptr, nullptr};
-    for (int k = 0; k < (nchunks > 1 ? 2 : 1); ++k) {
-        dbufs[k] = (double*)dscratch(c, k == 0 ? 4 : 6, ((per + m) * sizeof(double) + sizeof(int)) * (size_t)chunk + 64);
-        if (!dbufs[k]) return HK_ERR_OUT_OF_MEMORY;
+    static const int chunks_env = getenv("HK_E2E_CHUNKS") ? atoi(getenv("HK_E2E_CHUNKS")) : 0;    // tuning knobs
+    static const int ncs_env = getenv("HK_E2E_COPY_STREAMS") ? atoi(getenv("HK_E2E_COPY_STREAMS")) : 4;
+    // 0: seven cudaMemcpyAsync per chunk; 1 (default): one cudaMemcpyBatchAsync per chunk — the pipeline is bound by the host's
+    // issue rate (~3 us per call) before it is bound by PCIe; 2: ingest kernel (pinned sources only)
+    static const int mode_env = getenv("HK_E2E_COPY_MODE") ? atoi(getenv("HK_E2E_COPY_MODE")) : 1;
+    static std::atomic<int> batch_copy_ok{1};
+    const int mode = (mode_env == 1 && !batch_copy_ok.load()) ? 0 : mode_env;
+    constexpr int RING = 4;
+    const int ncs = ncs_env < 1 ? 1 : ncs_env > 4 ? 4 : ncs_env;
+    int nchunks = batch >= 16384 ? (chunks_env > 0 ? chunks_env : (batch >= 65536 ? 8 : batch / 8192)) : 1;
+    const int by_size = (int)(((long long)batch + 65535) / 65536);                                // chunks of at most 65,536 problems
+    if (nchunks < by_size) nchunks = by_size;
+    const int chunk = ((batch + nchunks - 1) / nchunks + 1) & ~1;                                 // even: keeps every sub-array 16-byte aligned
+    const size_t slot_bytes = (((per + m) * sizeof(double) + sizeof(int)) * (size_t)chunk + 255) & ~(size_t)255;
+    const int ring = nchunks < RING ? nchunks : RING;
+    char* dring = (char*)dscratch(c, 4, slot_bytes * ring);
+    if (!dring) return HK_ERR_OUT_OF_MEMORY;
+    static const int trig_slot[RING] = {5, 7, 10, 11};
+    {   // grow the per-slot scratch of lqng_assemble_launch before anything is in flight ((cos, sin) pairs, or dense records for N != 2)
+        const size_t n = 4 * (size_t)N, dense = (size_t)N * 16 + N * 8 + N * n * n + N * n + N * 4 + n;
+        for (int r = 0; r < ring; ++r)
+            if (!dscratch(c, trig_slot[r], sizeof(double) * (N == 2 ? 4 : dense) * (size_t)chunk)) return HK_ERR_OUT_OF_MEMORY;
     }
+    cudaStream_t compute[2] = {c->stream, c->stream2};
     for (int ci = 0; ci < nchunks; ++ci) {
         const int b0 = ci * chunk, nb = (b0 + chunk <= batch) ? chunk : batch - b0;
         if (nb <= 0) break;
-        cudaStream_t s = streams[ci & 1];
+        const int r = ci % ring;
+        cudaStream_t cs = nchunks > 1 ? c->cstream[ci % ncs] : compute[0];
+        cudaStream_t s = compute[ci & 1];
         double* dp[7];
-        double* cur = dbufs[ci & 1];
+        double* cur = (double*)(dring + slot_bytes * r);
+        if (ci >= ring) HK_CUDA(cudaStreamWaitEvent(cs, c->pev[8 + r], 0));                       // the slot's previous tenant has drained
+        void* dsts[7]; void* srcs[7]; size_t sizes[7]; size_t cnt = 0;
+        IngestArgs ia;
+        bool even = true;
+        for (int i = 0; i < 7; ++i) even = even && ((e[i] * nb) & 1) == 0;
+        const int md = (mode == 2 && !even) ? 0 : mode;
         for (int i = 0; i < 7; ++i) {
             dp[i] = cur;
-            if (e[i]) HK_CUDA(cudaMemcpyAsync(cur, src[i] + e[i] * b0, sizeof(double) * e[i] * nb, cudaMemcpyHostToDevice, s));
-            cur += e[i] * nb;
+            ia.src[i] = (const double2*)(src[i] + e[i] * b0); ia.dst[i] = (double2*)cur; ia.n2[i] = (long long)(e[i] * nb + 1) / 2;
+            if (e[i]) {
+                if (md == 0) HK_CUDA(cudaMemcpyAsync(cur, src[i] + e[i] * b0, sizeof(double) * e[i] * nb, cudaMemcpyHostToDevice, cs));
+                else { dsts[cnt] = cur; srcs[cnt] = (void*)(src[i] + e[i] * b0); sizes[cnt] = sizeof(double) * e[i] * nb; ++cnt; }
+            }
+            cur += e[i] * chunk;
+        }
+        if (md == 1 && cnt) {
+            cudaMemcpyAttributes at = {};
+            at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+            size_t idx = 0, fail = 0;
+            if (cudaMemcpyBatchAsync(dsts, srcs, sizes, cnt, &at, &idx, 1, &fail, cs) != cudaSuccess) {
+                cudaGetLastError();                                                               // driver without batched copies: plain copies from now on
+                batch_copy_ok.store(0);
+                for (size_t k = 0; k < cnt; ++k) HK_CUDA(cudaMemcpyAsync(dsts[k], srcs[k], sizes[k], cudaMemcpyHostToDevice, cs));
+            }
+        } else if (md == 2) {
+            count_launch(); lqng_ingest_kernel<<<296, 512, 0, cs>>>(ia);
+            HK_CUDA(cudaGetLastError());
         }
         double* du = cur;
-        int* dst = (int*)(du + (size_t)m * nb);
-        int rc = lqng_assemble_launch(nb, N, horizon, dt, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], du, dst, s, (ci & 1) ? 7 : 5);
+        int* dst = (int*)(du + (size_t)m * chunk);
+        if (nchunks > 1) {
+            HK_CUDA(cudaEventRecord(c->pev[r], cs));
+            HK_CUDA(cudaStreamWaitEvent(s, c->pev[r], 0));
+        }
+        int rc = lqng_assemble_launch(nb, N, horizon, dt, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], du, dst, s, trig_slot[r]);
         if (rc) return rc;
         HK_CUDA(cudaMemcpyAsync(u0 + (size_t)m * b0, du, sizeof(double) * m * nb, cudaMemcpyDeviceToHost, s));
         if (status) HK_CUDA(cudaMemcpyAsync(status + b0, dst, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+        if (ci + ring < nchunks) HK_CUDA(cudaEventRecord(c->pev[8 + r], s));
     }
     HK_CUDA(cudaStreamSynchronize(c->stream));
     HK_CUDA(cudaStreamSynchronize(c->stream2));

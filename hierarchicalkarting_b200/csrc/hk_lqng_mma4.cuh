@@ -4,8 +4,10 @@
 //
 // Where the flops are: Z_i <- Q_i + P_i^T R_i P_i + F^T Z_i F for four players is 2 x 4 x 16^3 x 2 = 65 k of the 139 k flops
 // of a backward step.  Those products run on the FP64 tensor pipe as DMMA m8n8k4 over 2 x 2 tiles of 8 x 8 with operand
-// fragments read straight from shared memory (row-major, leading dimension 20 doubles: every fragment load is the minimal two
-// wavefronts).  F and Y = Z_i F are kept TRANSPOSED (Ft, Yt) so that both their uses — as the k x n operand of one product and
+// fragments read straight from shared memory.  The 16 x 16 arrays are row-major with leading dimension 16 and the four 4-column
+// groups of row r XOR-swizzled by r & 3 (element (r, c) at r*16 + (c ^ 4 (r & 3))): fragment loads (lane (g, t) reads (g, 4 ks + t))
+// are the minimal two wavefronts, row reads stay contiguous, and a warp needs 17.3 KB instead of the 20.3 KB of a padded layout
+// (leading dimension 20) — 12 resident warps per SM instead of 10.  F and Y = Z_i F are kept TRANSPOSED (Ft, Yt) so that both their uses — as the k x n operand of one product and
 // the m x k operand of the next — are row reads.  The coupled 8 x 8 system [LHS | RHSMat | RHSVec] (25 columns) is dealt one
 // column per lane and reduced in registers by Gauss-Jordan with partial pivoting (the pivot MathNet's LU would take: first
 // largest magnitude at or below the diagonal, KartLQR.cs:104-105), the pivot column broadcast by shuffles.  Everything else
@@ -15,10 +17,10 @@
 namespace hk {
 
 struct Mma4Layout {
-    static constexpr int LD = 20;
-    static constexpr int oZ = 0;                     // Z[4][16][LD]
-    static constexpr int oFt = oZ + 4 * 16 * LD;     // Ft[c][r] = F[r][c]
-    static constexpr int oYt = oFt + 16 * LD;        // Yt[c][k] = (Z_i F)[k][c]
+    static constexpr int LD = 16;
+    static constexpr int oZ = 0;                     // Z[4][16][16], swizzled
+    static constexpr int oFt = oZ + 4 * 16 * LD;     // Ft[c][r] = F[r][c], swizzled
+    static constexpr int oYt = oFt + 16 * LD;        // Yt[c][k] = (Z_i F)[k][c], swizzled
     static constexpr int oP = oYt + 16 * LD;         // P[8][16]
     static constexpr int oRP = oP + 128;             // (R_i P_i)[i][a][c]
     static constexpr int oW = oRP + 128;             // W[8][16] = stacked B_i^T Z_i
@@ -32,6 +34,8 @@ struct Mma4Layout {
     static constexpr int oX = oAlpha + 8;
     static constexpr int oU = oX + 16;
     static constexpr int total = oU + 8;
+    // element (r, c) of a swizzled 16 x 16 array
+    __host__ __device__ static constexpr int at(int r, int c) { return r * 16 + (c ^ ((r & 3) << 2)); }
 };
 
 constexpr int MMA4_WARPS = 2;
@@ -48,6 +52,11 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
            *Bs = s + L::oB, *Rs = s + L::oR, *eta = s + L::oEta, *tmp = s + L::oTmp, *beta = s + L::oBeta, *alpha = s + L::oAlpha,
            *xs = s + L::oX, *us = s + L::oU;
     const long long nwarps = (long long)gridDim.x * MMA4_WARPS;
+    // fragment element (g, 4 ks + t) of a swizzled array sits at fb ^ (4 ks); rows 8 + g at + 128
+    const int fb = 16 * g + 4 * (g & 3) + t;
+    const int f0 = fb, f1 = fb ^ 4, f2 = fb ^ 8, f3 = fb ^ 12;
+    const int zo = L::at(g, 2 * t);                                 // C fragment (g, 2t..2t+1); columns 8 + 2t at ^ 8; rows 8 + g at + 128
+    const int yo0 = L::at(2 * t, g), yo1 = L::at(2 * t + 1, g);     // transposed store of a C fragment
 
     for (long long prob = (long long)blockIdx.x * MMA4_WARPS + wib; prob < p.batch; prob += nwarps) {
         const int T = p.horizon + 1, Tm = p.time_varying ? T : 1;
@@ -66,7 +75,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
             for (int e = lane; e < N * n * n / 2; e += 32) {
                 const double2 v = *reinterpret_cast<const double2*>(q0 + 2 * e);
                 const int i = e >> 7, r = (e >> 3) & 15, c = (e & 7) * 2;
-                *reinterpret_cast<double2*>(Z + (i * 16 + r) * LD + c) = v;
+                *reinterpret_cast<double2*>(Z + i * 256 + L::at(r, c)) = v;
             }
             for (int e = lane; e < N * n; e += 32) eta[e] = gq[(size_t)(Tm - 1) * N * n + e];
             if (lane < n) xs[lane] = gx[lane];
@@ -88,7 +97,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
                 for (int a = 0; a < 2; ++a) {
                     double acc = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], Z[(i * 16 + 4 * i + k) * LD + lo], acc);
+                    for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], Z[i * 256 + (4 * i + k) * 16 + (lo ^ (4 * k))], acc);
                     W[(2 * i + a) * n + lo] = acc;
                 }
             }
@@ -176,7 +185,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
                 for (int j = 0; j < 8; ++j) {
                     const int c = hf * 8 + j;
                     const double a = (c >> 2) == pr ? As[pr * 16 + rr * 4 + (c & 3)] : 0.0;
-                    Ft[c * LD + r] = a - fma(b1, Pm[(2 * pr + 1) * n + c], b0 * Pm[(2 * pr) * n + c]);
+                    Ft[c * 16 + (r ^ (4 * (j & 3)))] = a - fma(b1, Pm[(2 * pr + 1) * n + c], b0 * Pm[(2 * pr) * n + c]);
                 }
                 if (hf == 0) beta[r] = -fma(b1, alpha[2 * pr + 1], b0 * alpha[2 * pr]);
 #pragma unroll
@@ -187,8 +196,13 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
             }
             __syncwarp();
             // Z_i <- Q_i + P_i^T R_i P_i + F^T Z_i F ; eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)  (:116-117)
+            // F^T fragments (Ft[g][4 ks + t], Ft[8 + g][4 ks + t]) serve all four players: B operand of Y = Z_i F, A operand of F^T Y,
+            // and the F^T (eta_i + Z_i beta) product of the eta update
+            const double fa0 = Ft[f0], fa1 = Ft[f1], fa2 = Ft[f2], fa3 = Ft[f3];
+            const double fb0 = Ft[128 + f0], fb1 = Ft[128 + f1], fb2 = Ft[128 + f2], fb3 = Ft[128 + f3];
+            const double2 be0 = *reinterpret_cast<const double2*>(beta + 2 * t), be1 = *reinterpret_cast<const double2*>(beta + 8 + 2 * t);
             for (int i = 0; i < N; ++i) {
-                double* Zi = Z + i * 16 * LD;
+                double* Zi = Z + i * 256;
                 // C fragments of the new Z_i start from Q_i: issue the loads before the first product to hide their L2 latency
                 const double* Qi = Qt + (size_t)i * n * n;
                 const double2 q00 = *reinterpret_cast<const double2*>(Qi + g * n + 2 * t);
@@ -197,20 +211,22 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
                 const double2 q11 = *reinterpret_cast<const double2*>(Qi + (8 + g) * n + 8 + 2 * t);
                 {   // Y = Z_i F, stored transposed
                     double c00a = 0, c00b = 0, c01a = 0, c01b = 0, c10a = 0, c10b = 0, c11a = 0, c11b = 0;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const double a0 = Zi[g * LD + 4 * ks + t], a1 = Zi[(8 + g) * LD + 4 * ks + t];
-                        const double b0 = Ft[g * LD + 4 * ks + t], b1 = Ft[(8 + g) * LD + 4 * ks + t];
-                        dmma(c00a, c00b, a0, b0); dmma(c01a, c01b, a0, b1);
-                        dmma(c10a, c10b, a1, b0); dmma(c11a, c11b, a1, b1);
+#define HK_M4_Y(fk, bl, bh)                                                                       \
+                    {                                                                             \
+                        const double a0 = Zi[fk], a1 = Zi[128 + fk];                              \
+                        dmma(c00a, c00b, a0, bl); dmma(c01a, c01b, a0, bh);                       \
+                        dmma(c10a, c10b, a1, bl); dmma(c11a, c11b, a1, bh);                       \
                     }
+                    HK_M4_Y(f0, fa0, fb0) HK_M4_Y(f1, fa1, fb1) HK_M4_Y(f2, fa2, fb2) HK_M4_Y(f3, fa3, fb3)
+#undef HK_M4_Y
                     __syncwarp();
-                    Yt[(2 * t) * LD + g] = c00a;          Yt[(2 * t + 1) * LD + g] = c00b;
-                    Yt[(8 + 2 * t) * LD + g] = c01a;      Yt[(8 + 2 * t + 1) * LD + g] = c01b;
-                    Yt[(2 * t) * LD + 8 + g] = c10a;      Yt[(2 * t + 1) * LD + 8 + g] = c10b;
-                    Yt[(8 + 2 * t) * LD + 8 + g] = c11a;  Yt[(8 + 2 * t + 1) * LD + 8 + g] = c11b;
+                    Yt[yo0] = c00a;              Yt[yo1] = c00b;
+                    Yt[128 + yo0] = c01a;        Yt[128 + yo1] = c01b;
+                    Yt[yo0 ^ 8] = c10a;          Yt[yo1 ^ 8] = c10b;
+                    Yt[128 + (yo0 ^ 8)] = c11a;  Yt[128 + (yo1 ^ 8)] = c11b;
                 }
                 __syncwarp();
+                double zl, zh;                                      // (Z_i^{new} beta)[g], [8 + g] after the quad reduction
                 {
                     double c00a = q00.x, c00b = q00.y, c01a = q01.x, c01b = q01.y, c10a = q10.x, c10b = q10.y, c11a = q11.x, c11b = q11.y;
                     {   // + P_i^T (R_i P_i): k = 2
@@ -219,41 +235,42 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
                         dmma(c00a, c00b, a0, b0); dmma(c01a, c01b, a0, b1);
                         dmma(c10a, c10b, a1, b0); dmma(c11a, c11b, a1, b1);
                     }
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {              // + F^T Y
-                        const double a0 = Ft[g * LD + 4 * ks + t], a1 = Ft[(8 + g) * LD + 4 * ks + t];
-                        const double b0 = Yt[g * LD + 4 * ks + t], b1 = Yt[(8 + g) * LD + 4 * ks + t];
-                        dmma(c00a, c00b, a0, b0); dmma(c01a, c01b, a0, b1);
-                        dmma(c10a, c10b, a1, b0); dmma(c11a, c11b, a1, b1);
+#define HK_M4_Z(fk, al, ah)                                                                       \
+                    {                                                                             \
+                        const double b0 = Yt[fk], b1 = Yt[128 + fk];                              \
+                        dmma(c00a, c00b, al, b0); dmma(c01a, c01b, al, b1);                       \
+                        dmma(c10a, c10b, ah, b0); dmma(c11a, c11b, ah, b1);                       \
                     }
-                    *reinterpret_cast<double2*>(Zi + g * LD + 2 * t) = make_double2(c00a, c00b);
-                    *reinterpret_cast<double2*>(Zi + g * LD + 8 + 2 * t) = make_double2(c01a, c01b);
-                    *reinterpret_cast<double2*>(Zi + (8 + g) * LD + 2 * t) = make_double2(c10a, c10b);
-                    *reinterpret_cast<double2*>(Zi + (8 + g) * LD + 8 + 2 * t) = make_double2(c11a, c11b);
+                    HK_M4_Z(f0, fa0, fb0) HK_M4_Z(f1, fa1, fb1) HK_M4_Z(f2, fa2, fb2) HK_M4_Z(f3, fa3, fb3)      // + F^T Y
+#undef HK_M4_Z
+                    *reinterpret_cast<double2*>(Zi + zo) = make_double2(c00a, c00b);
+                    *reinterpret_cast<double2*>(Zi + (zo ^ 8)) = make_double2(c01a, c01b);
+                    *reinterpret_cast<double2*>(Zi + 128 + zo) = make_double2(c10a, c10b);
+                    *reinterpret_cast<double2*>(Zi + 128 + (zo ^ 8)) = make_double2(c11a, c11b);
+                    // Z_i^{new} beta (quirk Q2) straight from the C fragments: lane (g, t) holds columns 2t, 2t+1, 8+2t, 8+2t+1 of rows g, 8+g
+                    zl = fma(c01b, be1.y, fma(c01a, be1.x, fma(c00b, be0.y, c00a * be0.x)));
+                    zh = fma(c11b, be1.y, fma(c11a, be1.x, fma(c10b, be0.y, c10a * be0.x)));
+                    zl += __shfl_xor_sync(0xffffffffu, zl, 1); zh += __shfl_xor_sync(0xffffffffu, zh, 1);
+                    zl += __shfl_xor_sync(0xffffffffu, zl, 2); zh += __shfl_xor_sync(0xffffffffu, zh, 2);
                 }
+                if (t < 2) tmp[i * n + 8 * t + g] = eta[i * n + 8 * t + g] + (t ? zh : zl);       // eta_i + Z_i^{new} beta
                 __syncwarp();
-                {   // eta_i + Z_i^{new} beta (quirk Q2): row lo, the two half-warps take 8 columns each
-                    double zb = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) zb = fma(Zi[lo * LD + hf * 8 + j], beta[hf * 8 + j], zb);
-                    zb += __shfl_xor_sync(0xffffffffu, zb, 16);
-                    if (hf == 0) tmp[i * n + lo] = eta[i * n + lo] + zb;
+                {   // F^T (eta_i + Z_i beta): rows g and 8 + g of F^T from the fragments, reduced over the quad
+                    const double v0 = tmp[i * n + t], v1 = tmp[i * n + 4 + t], v2 = tmp[i * n + 8 + t], v3 = tmp[i * n + 12 + t];
+                    double al = fma(fa3, v3, fma(fa2, v2, fma(fa1, v1, fa0 * v0)));
+                    double ah = fma(fb3, v3, fma(fb2, v2, fma(fb1, v1, fb0 * v0)));
+                    al += __shfl_xor_sync(0xffffffffu, al, 1); ah += __shfl_xor_sync(0xffffffffu, ah, 1);
+                    al += __shfl_xor_sync(0xffffffffu, al, 2); ah += __shfl_xor_sync(0xffffffffu, ah, 2);
+                    if (t < 2) {
+                        const int c = 8 * t + g;
+                        const double a0 = alpha[2 * i], a1 = alpha[2 * i + 1];
+                        const double ra0 = fma(Rs[i * 4 + 1], a1, Rs[i * 4 + 0] * a0), ra1 = fma(Rs[i * 4 + 3], a1, Rs[i * 4 + 2] * a0);
+                        const double pra = fma(Pm[(2 * i + 1) * n + c], ra1, Pm[(2 * i) * n + c] * ra0);
+                        eta[i * n + c] = (gq[(size_t)tt * N * n + i * n + c] + pra) + (t ? ah : al);
+                    }
                 }
-                __syncwarp();
-                {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc = fma(Ft[lo * LD + hf * 8 + j], tmp[i * n + hf * 8 + j], acc);
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-                    const double a0 = alpha[2 * i], a1 = alpha[2 * i + 1];
-                    const double ra0 = fma(Rs[i * 4 + 1], a1, Rs[i * 4 + 0] * a0), ra1 = fma(Rs[i * 4 + 3], a1, Rs[i * 4 + 2] * a0);
-                    const double pra = fma(Pm[(2 * i + 1) * n + lo], ra1, Pm[(2 * i) * n + lo] * ra0);
-                    const double e_new = (gq[(size_t)tt * N * n + i * n + lo] + pra) + acc;
-                    __syncwarp();
-                    if (hf == 0) eta[i * n + lo] = e_new;
-                }
-                __syncwarp();
             }
+            __syncwarp();
         }
         // optimal_control = -P x0 - alpha with the t = 0 pair (:121-126), every player
         if (lane < m) {

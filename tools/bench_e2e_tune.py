@@ -23,10 +23,12 @@ big = torch.empty(23068672 // 8, dtype=torch.float64).pin_memory(); dbig = torch
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(20): dbig.copy_(big, non_blocking=True)
 torch.cuda.synchronize(); bw = 20 * big.numel() * 8 / (time.perf_counter() - t0) / 1e9
-print('%%.4f ms/step  %%.3e solves/s   (single 23 MB pinned H2D: %%.1f GB/s)' %% (best * 1e3, batch / best, bw))
+print('%%.4f ms/step  %%.3e solves/s   (single 23 MB pinned H2D: %%.1f GB/s)  u0 checksum %%.9f status!=0: %%d' %% (best * 1e3, batch / best, bw, float(u0.sum()), int((st != 0).sum())))
 """
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for ch in (sys.argv[1:] or ["1", "2", "4", "8", "16"]):
-    env = dict(os.environ, HK_E2E_CHUNKS=ch)
+# arguments: chunks[:copy_streams[:copy_mode]] ...   (HK_E2E_CHUNKS, HK_E2E_COPY_STREAMS, HK_E2E_COPY_MODE of hk_abi.cu)
+for spec in (sys.argv[1:] or ["1", "2", "4", "8", "16"]):
+    f = spec.split(":"); f += ["2", "0"][len(f) - 1:]
+    env = dict(os.environ, HK_E2E_CHUNKS=f[0], HK_E2E_COPY_STREAMS=f[1], HK_E2E_COPY_MODE=f[2])
     r = subprocess.run([sys.executable, "-c", CHILD % root], env=env, capture_output=True, text=True)
-    print("chunks", ch, "->", r.stdout.strip() or r.stderr.strip()[-300:], flush=True)
+    print("chunks %s copy-streams %s mode %s ->" % tuple(f), r.stdout.strip() or r.stderr.strip()[-300:], flush=True)
