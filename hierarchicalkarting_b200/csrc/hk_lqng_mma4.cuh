@@ -21,10 +21,9 @@ struct Mma4Layout {
     static constexpr int oZ = 0;                     // Z[4][16][16], swizzled
     static constexpr int oFt = oZ + 4 * 16 * LD;     // Ft[c][r] = F[r][c], swizzled
     static constexpr int oYt = oFt + 16 * LD;        // Yt[c][k] = (Z_i F)[k][c], swizzled
+    static constexpr int oW = oYt;                   // W[8][16] = stacked B_i^T Z_i: dead before the first Y of a step is stored
     static constexpr int oP = oYt + 16 * LD;         // P[8][16]
-    static constexpr int oRP = oP + 128;             // (R_i P_i)[i][a][c]
-    static constexpr int oW = oRP + 128;             // W[8][16] = stacked B_i^T Z_i
-    static constexpr int oA = oW + 128;              // A_i[4][4][4]
+    static constexpr int oA = oP + 128;              // A_i[4][4][4]
     static constexpr int oB = oA + 64;               // B_i[4][4][2]
     static constexpr int oR = oB + 32;               // R_i[4][2][2]
     static constexpr int oEta = oR + 16;             // eta[4][16]
@@ -40,7 +39,7 @@ struct Mma4Layout {
 
 constexpr int MMA4_WARPS = 2;
 
-__global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p)
+__global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParams p)
 {
     using L = Mma4Layout;
     constexpr int N = 4, n = 16, m = 8, LD = L::LD;
@@ -48,7 +47,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3, lo = lane & 15, hf = lane >> 4;
     double* s = smem + (size_t)wib * L::total;
-    double *Z = s + L::oZ, *Ft = s + L::oFt, *Yt = s + L::oYt, *Pm = s + L::oP, *RP = s + L::oRP, *W = s + L::oW, *As = s + L::oA,
+    double *Z = s + L::oZ, *Ft = s + L::oFt, *Yt = s + L::oYt, *Pm = s + L::oP, *W = s + L::oW, *As = s + L::oA,
            *Bs = s + L::oB, *Rs = s + L::oR, *eta = s + L::oEta, *tmp = s + L::oTmp, *beta = s + L::oBeta, *alpha = s + L::oAlpha,
            *xs = s + L::oX, *us = s + L::oU;
     const long long nwarps = (long long)gridDim.x * MMA4_WARPS;
@@ -177,7 +176,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
                     for (int r = 0; r < 8; ++r) ga[(size_t)st * m + r] = col[r];
             }
             __syncwarp();
-            // F = A - sum_k B_k P_k (stored transposed), beta = -sum_k B_k alpha_k (:110-111), R_i P_i
+            // F = A - sum_k B_k P_k (stored transposed), beta = -sum_k B_k alpha_k (:110-111)
             {
                 const int r = lo, pr = r >> 2, rr = r & 3;
                 const double b0 = Bs[pr * 8 + rr * 2 + 0], b1 = Bs[pr * 8 + rr * 2 + 1];
@@ -188,11 +187,6 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
                     Ft[c * 16 + (r ^ (4 * (j & 3)))] = a - fma(b1, Pm[(2 * pr + 1) * n + c], b0 * Pm[(2 * pr) * n + c]);
                 }
                 if (hf == 0) beta[r] = -fma(b1, alpha[2 * pr + 1], b0 * alpha[2 * pr]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int e = lane + 32 * j, i = e >> 5, a = (e >> 4) & 1, c = e & 15;
-                    RP[e] = fma(Rs[i * 4 + a * 2 + 1], Pm[(2 * i + 1) * n + c], Rs[i * 4 + a * 2 + 0] * Pm[(2 * i) * n + c]);
-                }
             }
             __syncwarp();
             // Z_i <- Q_i + P_i^T R_i P_i + F^T Z_i F ; eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)  (:116-117)
@@ -229,9 +223,11 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS) lqng_mma4_kernel(LqngParams p
                 double zl, zh;                                      // (Z_i^{new} beta)[g], [8 + g] after the quad reduction
                 {
                     double c00a = q00.x, c00b = q00.y, c01a = q01.x, c01b = q01.y, c10a = q10.x, c10b = q10.y, c11a = q11.x, c11b = q11.y;
-                    {   // + P_i^T (R_i P_i): k = 2
-                        const double a0 = t < 2 ? Pm[(2 * i + t) * n + g] : 0.0, a1 = t < 2 ? Pm[(2 * i + t) * n + 8 + g] : 0.0;
-                        const double b0 = t < 2 ? RP[(i * 2 + t) * n + g] : 0.0, b1 = t < 2 ? RP[(i * 2 + t) * n + 8 + g] : 0.0;
+                    {   // + P_i^T (R_i P_i): k = 2; lanes t < 2 hold row t of P_i and form row t of R_i P_i
+                        const double p0l = Pm[(2 * i) * n + g], p1l = Pm[(2 * i + 1) * n + g], p0h = Pm[(2 * i) * n + 8 + g], p1h = Pm[(2 * i + 1) * n + 8 + g];
+                        const double2 rt = *reinterpret_cast<const double2*>(Rs + i * 4 + 2 * (t & 1));
+                        const double a0 = t < 2 ? (t ? p1l : p0l) : 0.0, a1 = t < 2 ? (t ? p1h : p0h) : 0.0;
+                        const double b0 = t < 2 ? fma(rt.y, p1l, rt.x * p0l) : 0.0, b1 = t < 2 ? fma(rt.y, p1h, rt.x * p0h) : 0.0;
                         dmma(c00a, c00b, a0, b0); dmma(c01a, c01b, a0, b1);
                         dmma(c10a, c10b, a1, b0); dmma(c11a, c11b, a1, b1);
                     }

@@ -5,7 +5,9 @@ from hierarchicalkarting_b200 import abi, scenarios as S
 if os.environ.get("HK_LIB_PATH"): abi.LIB_PATH = os.environ["HK_LIB_PATH"]
 lib=abi.load_library(); abi.check(lib.hk_init(0))
 dev=torch.device('cuda',0)
+ONLY = [int(a) for a in sys.argv[1:]]
 for N,track,batch in ((4,S.COMPLEX,65536),(3,S.COMPLEX,65536),(1,S.OVAL,262144),(2,S.OVAL,65536)):
+    if ONLY and N not in ONLY: continue
     p=S.make_problems(track,batch,N,seed=1)
     host=S.assemble_dense(p)
     d=[torch.from_numpy(a).to(dev) for a in host]
