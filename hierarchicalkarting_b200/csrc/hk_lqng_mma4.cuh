@@ -33,6 +33,7 @@ struct Mma4Layout {
     static constexpr int oX = oAlpha + 8;
     static constexpr int oU = oX + 16;
     static constexpr int total = oU + 8;
+    static constexpr int LDS = 26;                   // coupled-system scratch [8][26] inside the Ft buffer
     // element (r, c) of a swizzled 16 x 16 array
     __host__ __device__ static constexpr int at(int r, int c) { return r * 16 + (c ^ ((r & 3) << 2)); }
 };
@@ -47,13 +48,14 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3, lo = lane & 15, hf = lane >> 4;
     double* s = smem + (size_t)wib * L::total;
-    double *Z = s + L::oZ, *Ft = s + L::oFt, *Yt = s + L::oYt, *Pm = s + L::oP, *W = s + L::oW, *As = s + L::oA,
+    double *Z = s + L::oZ, *Ft = s + L::oFt, *Yt = s + L::oYt, *Pm = s + L::oP, *W = s + L::oW, *Sy = s + L::oFt, *As = s + L::oA,
            *Bs = s + L::oB, *Rs = s + L::oR, *eta = s + L::oEta, *tmp = s + L::oTmp, *beta = s + L::oBeta, *alpha = s + L::oAlpha,
            *xs = s + L::oX, *us = s + L::oU;
     const long long nwarps = (long long)gridDim.x * MMA4_WARPS;
     // fragment element (g, 4 ks + t) of a swizzled array sits at fb ^ (4 ks); rows 8 + g at + 128
     const int fb = 16 * g + 4 * (g & 3) + t;
     const int f0 = fb, f1 = fb ^ 4, f2 = fb ^ 8, f3 = fb ^ 12;
+    const int bo = g < 4 ? 4 * t + g : 64 + 2 * t + (g - 4), bs = g < 4 ? 16 : 8;   // B operand [A_pc | B_pc | 0][t][g] relative to As (Bs follows As)
     const int zo = L::at(g, 2 * t);                                 // C fragment (g, 2t..2t+1); columns 8 + 2t at ^ 8; rows 8 + g at + 128
     const int yo0 = L::at(2 * t, g), yo1 = L::at(2 * t + 1, g);     // transposed store of a C fragment
 
@@ -97,62 +99,61 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
                     double acc = 0.0;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], Z[i * 256 + (4 * i + k) * 16 + (lo ^ (4 * k))], acc);
-                    W[(2 * i + a) * n + lo] = acc;
+                    W[(2 * i + a) * 16 + (lo ^ (4 * (2 * ii + a)))] = acc;              // swizzled like Z: fragment reads below
                 }
+            }
+            if (lane < 8) {                                         // RHSVec (:96): row r = (i, a) is B_i[:, a] . eta_i[4i..4i+3]
+                const int i = lane >> 1, a = lane & 1;
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], eta[i * n + 4 * i + k], acc);
+                Sy[lane * L::LDS + 24] = acc;
             }
             __syncwarp();
-            // coupled system, one column per lane: LHS (8, quirk Q1 placement :68-87), RHSMat (16, :89-95), RHSVec (1, :96)
-            double col[8];
-            if (lane < 8) {
-                const int i = lane >> 1, b = lane & 1;
+            // Coupled system [LHS | RHSMat | RHSVec] (:68-96): one DMMA per player block pc gives W[:, 4pc..4pc+3] [A_pc | B_pc] —
+            // columns 0..3 are RHSMat[:, 4pc..4pc+3], columns 4, 5 are M[(i, a)][(pc, b)] = LHS[(pc, a)][(i, b)] (quirk Q1 placement;
+            // + R_pc on the diagonal block, :78).  The D fragments go through a scratch array (the F^T buffer, dead here) to reach the
+            // column-per-lane distribution of the Gauss-Jordan sweep.
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int j = r >> 1, a = r & 1;
-                    double acc = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc = fma(W[(2 * i + a) * n + 4 * j + k], Bs[j * 8 + k * 2 + b], acc);
-                    if (i == j) acc = Rs[i * 4 + a * 2 + b] + acc;  // getRMatrix() + ... (:78)
-                    col[r] = acc;
+            for (int pc = 0; pc < 4; ++pc) {
+                const double wa = W[pc == 0 ? f0 : pc == 1 ? f1 : pc == 2 ? f2 : f3];
+                const double ab = g < 6 ? As[bo + pc * bs] : 0.0;
+                double d0 = 0.0, d1 = 0.0;
+                dmma(d0, d1, wa, ab);
+                if (t == 2 && (g >> 1) == pc) {
+                    const double2 r2 = *reinterpret_cast<const double2*>(Rs + pc * 4 + (g & 1) * 2);
+                    d0 = r2.x + d0; d1 = r2.y + d1;
                 }
-            } else if (lane < 24) {
-                const int c = lane - 8, pc = c >> 2, cc = c & 3;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc = fma(W[r * n + 4 * pc + k], As[pc * 16 + k * 4 + cc], acc);
-                    col[r] = acc;
-                }
-            } else if (lane == 24) {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int i = r >> 1, a = r & 1;
-                    double acc = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc = fma(Bs[i * 8 + k * 2 + a], eta[i * n + 4 * i + k], acc);
-                    col[r] = acc;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) col[r] = 0.0;
+                if (t < 2) *reinterpret_cast<double2*>(Sy + g * L::LDS + 8 + 4 * pc + 2 * t) = make_double2(d0, d1);
+                else if (t == 2) *reinterpret_cast<double2*>(Sy + (2 * pc + (g & 1)) * L::LDS + 2 * (g >> 1)) = make_double2(d0, d1);
             }
+            __syncwarp();
+            double col[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) col[r] = lane < 25 ? Sy[r * L::LDS + lane] : 0.0;
             // P = LHS.Solve(RHSMat), alpha = LHS.Solve(RHSVec): Gauss-Jordan with partial pivoting (KartLQR.cs:104-105)
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 double pc[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) pc[r] = shfl_d(col[r], k);
-                int pr = k;
-                double best = pc[k];
+                // common case (R dominates the LHS): the high word of |pc[k]| alone exceeds every candidate below it — no exchange
+                unsigned below = 0;
 #pragma unroll
-                for (int r = k + 1; r < 8; ++r)
-                    if (abs_gt(pc[r], best)) { best = pc[r]; pr = r; }  // |.| compared on the integer pipes (exact)
+                for (int r = k + 1; r < 8; ++r) below = max(below, (unsigned)__double2hiint(pc[r]) & 0x7fffffffu);
+                if (((unsigned)__double2hiint(pc[k]) & 0x7fffffffu) <= below) {              // warp-uniform (pc[] is a broadcast)
+                    int pr = k;
+                    double best = pc[k];
 #pragma unroll
-                for (int r = k + 1; r < 8; ++r)
-                    if (pr == r) {                                  // warp-uniform row exchange
-                        double tv = col[k]; col[k] = col[r]; col[r] = tv;
-                        tv = pc[k]; pc[k] = pc[r]; pc[r] = tv;
-                    }
+                    for (int r = k + 1; r < 8; ++r)
+                        if (abs_gt(pc[r], best)) { best = pc[r]; pr = r; }  // |.| compared on the integer pipes (exact)
+#pragma unroll
+                    for (int r = k + 1; r < 8; ++r)
+                        if (pr == r) {                              // warp-uniform row exchange
+                            double tv = col[k]; col[k] = col[r]; col[r] = tv;
+                            tv = pc[k]; pc[k] = pc[r]; pc[r] = tv;
+                        }
+                }
                 if (pc[k] == 0.0) singular = 1;
                 // 1 / pivot: MUFU seed + one cubic step (2^-60) unless the pivot is zero, denormal or huge (warp-uniform)
                 const double rinv = bad_pivot(pc[k]) ? 1.0 / pc[k] : rcp_fast(pc[k]);
