@@ -27,7 +27,7 @@ struct Mma4Layout {
     static constexpr int oB = oA + 64;               // B_i[4][4][2]
     static constexpr int oR = oB + 32;               // R_i[4][2][2]
     static constexpr int oEta = oR + 16;             // eta[4][16]
-    static constexpr int oTmp = oEta + 64;           // eta_i + Z_i beta, per player
+    static constexpr int oTmp = oEta + 64;           // q_i[4][16] of the current stage (the eta update reads it on its critical path)
     static constexpr int oBeta = oTmp + 64;
     static constexpr int oAlpha = oBeta + 16;
     static constexpr int oX = oAlpha + 8;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
     const int g = lane >> 2, t = lane & 3, lo = lane & 15, hf = lane >> 4;
     double* s = smem + (size_t)wib * L::total;
     double *Z = s + L::oZ, *Ft = s + L::oFt, *Yt = s + L::oYt, *Pm = s + L::oP, *W = s + L::oW, *Sy = s + L::oFt, *As = s + L::oA,
-           *Bs = s + L::oB, *Rs = s + L::oR, *eta = s + L::oEta, *tmp = s + L::oTmp, *beta = s + L::oBeta, *alpha = s + L::oAlpha,
+           *Bs = s + L::oB, *Rs = s + L::oR, *eta = s + L::oEta, *qs = s + L::oTmp, *beta = s + L::oBeta, *alpha = s + L::oAlpha,
            *xs = s + L::oX, *us = s + L::oU;
     const long long nwarps = (long long)gridDim.x * MMA4_WARPS;
     // fragment element (g, 4 ks + t) of a swizzled array sits at fb ^ (4 ks); rows 8 + g at + 128
@@ -70,6 +70,17 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
         double* gP = p.P ? p.P + (size_t)prob * T * m * n : nullptr;
         double* ga = p.alpha ? p.alpha + (size_t)prob * T * m : nullptr;
         int singular = 0;
+        if (prob + nwarps < p.batch) {                              // this warp's next record: 82 lines of 128 B into L2 while this one is solved
+            const size_t nx = (size_t)(prob + nwarps) * Tm;
+            const char* nq = reinterpret_cast<const char*>(p.Q + nx * N * n * n);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + 128 * lane));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + 128 * (32 + lane)));
+            const char* no = lane < 4 ? reinterpret_cast<const char*>(p.A + nx * N * 16) + 128 * lane
+                           : lane < 6 ? reinterpret_cast<const char*>(p.B + nx * N * 8) + 128 * (lane - 4)
+                           : lane < 10 ? reinterpret_cast<const char*>(p.q + nx * N * n) + 128 * (lane - 6)
+                           : lane == 10 ? reinterpret_cast<const char*>(p.R + nx * N * 4) : reinterpret_cast<const char*>(p.x0 + (size_t)(prob + nwarps) * n);
+            if (lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(no));
+        }
         __syncwarp();
         {   // Zs = Q, etas = q of the last stage (KartLQR.cs:62-63): 1,024 doubles, 128-bit coalesced loads
             const double* q0 = gQ + (size_t)(Tm - 1) * N * n * n;
@@ -78,13 +89,14 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
                 const int i = e >> 7, r = (e >> 3) & 15, c = (e & 7) * 2;
                 *reinterpret_cast<double2*>(Z + i * 256 + L::at(r, c)) = v;
             }
-            for (int e = lane; e < N * n; e += 32) eta[e] = gq[(size_t)(Tm - 1) * N * n + e];
+            for (int e = lane; e < N * n; e += 32) { const double v = gq[(size_t)(Tm - 1) * N * n + e]; eta[e] = v; qs[e] = v; }
             if (lane < n) xs[lane] = gx[lane];
         }
         for (int st = p.horizon; st >= 0; --st) {                   // KartLQR.cs:64
             const int tt = p.time_varying ? st : 0;
             const double* Qt = gQ + (size_t)tt * N * n * n;
             if (p.time_varying || st == p.horizon) {
+                if (st != p.horizon) { qs[lane] = gq[(size_t)tt * N * n + lane]; qs[32 + lane] = gq[(size_t)tt * N * n + 32 + lane]; }
                 for (int e = lane; e < N * 16; e += 32) As[e] = gA[(size_t)tt * N * 16 + e];
                 Bs[lane] = gB[(size_t)tt * N * 8 + lane];
                 if (lane < N * 4) Rs[lane] = gR[(size_t)tt * N * 4 + lane];
@@ -250,10 +262,11 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
                     zl += __shfl_xor_sync(0xffffffffu, zl, 1); zh += __shfl_xor_sync(0xffffffffu, zh, 1);
                     zl += __shfl_xor_sync(0xffffffffu, zl, 2); zh += __shfl_xor_sync(0xffffffffu, zh, 2);
                 }
-                if (t < 2) tmp[i * n + 8 * t + g] = eta[i * n + 8 * t + g] + (t ? zh : zl);       // eta_i + Z_i^{new} beta
+                if (t < 2) eta[i * n + 8 * t + g] += t ? zh : zl;                                // eta_i + Z_i^{new} beta, in place
                 __syncwarp();
-                {   // F^T (eta_i + Z_i beta): rows g and 8 + g of F^T from the fragments, reduced over the quad
-                    const double v0 = tmp[i * n + t], v1 = tmp[i * n + 4 + t], v2 = tmp[i * n + 8 + t], v3 = tmp[i * n + 12 + t];
+                {   // F^T (eta_i + Z_i beta): rows g and 8 + g of F^T from the fragments, reduced over the quad.  The new eta_i below
+                    // overwrites what these loads read: every lane's loads feed its shuffles, so they complete before any lane stores.
+                    const double v0 = eta[i * n + t], v1 = eta[i * n + 4 + t], v2 = eta[i * n + 8 + t], v3 = eta[i * n + 12 + t];
                     double al = fma(fa3, v3, fma(fa2, v2, fma(fa1, v1, fa0 * v0)));
                     double ah = fma(fb3, v3, fma(fb2, v2, fma(fb1, v1, fb0 * v0)));
                     al += __shfl_xor_sync(0xffffffffu, al, 1); ah += __shfl_xor_sync(0xffffffffu, ah, 1);
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
                         const double a0 = alpha[2 * i], a1 = alpha[2 * i + 1];
                         const double ra0 = fma(Rs[i * 4 + 1], a1, Rs[i * 4 + 0] * a0), ra1 = fma(Rs[i * 4 + 3], a1, Rs[i * 4 + 2] * a0);
                         const double pra = fma(Pm[(2 * i + 1) * n + c], ra1, Pm[(2 * i) * n + c] * ra0);
-                        eta[i * n + c] = (gq[(size_t)tt * N * n + i * n + c] + pra) + (t ? ah : al);
+                        eta[i * n + c] = (qs[i * n + c] + pra) + (t ? ah : al);
                     }
                 }
             }
