@@ -179,8 +179,12 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
         const double* rec = &sm.rec[wib][COMPACT ? 0 : buf][0];
         __syncwarp();                                               // every lane is done with the other buffer
         if (lane == 0 && nxt < p.batch) issue(nxt, buf ^ 1);
-        int after = 0;                                              // the problem after the next: fetched now, needed at the end
-        if (dynamic && lane == 0 && nxt < p.batch) after = atomicAdd(p.work, 1);
+        // The problem after the next: fetched now, needed at the end.  Inline PTX on purpose: nvcc turns a predicated atomicAdd() into
+        // a warp-aggregated one (leader election + SHFL of the result), and that SHFL waits for the atomic's round trip right here
+        // (4.6 % of the kernel's stall samples, ncu r01e) instead of ~5 us later where the value is consumed.
+        int after = 0;
+        if (dynamic && nxt < p.batch)                               // warp-uniform; the elected lane is lane 0
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p atom.global.add.u32 %0, [%1], 1;\n\t}" : "+r"(after) : "l"(p.work) : "memory");
         mbar_wait(bar_u32 + 8u * buf, (unsigned)(it >> 1) & 1u);
         if (COMPACT) {
             // assemble the dense record (layout P2_o*) from the staged description; every lane writes a few entries
