@@ -288,9 +288,15 @@ __device__ __forceinline__ unsigned philox_first(unsigned long long seed, unsign
 
 __device__ __forceinline__ int policy_index(const DevGame& g, int cnt, unsigned u)
 {
+    // number of thresholds <= u among the cnt - 1 ascending ones: branch-free binary search (6 probes instead of up to 35)
     const unsigned* cdf = g.cdf[cnt];
+    const int m = cnt - 1;
     int idx = 0;
-    for (int k = 0; k < cnt - 1; ++k) idx += (cdf[k] <= u);
+#pragma unroll
+    for (int s = 32; s; s >>= 1) {
+        const int k = idx + s;
+        if (k <= m && cdf[k - 1] <= u) idx = k;
+    }
     return idx;
 }
 
@@ -304,10 +310,13 @@ struct Tables {
           lmask(reinterpret_cast<const unsigned long long*>(g.tables + g.off_lmask)), nv(g.nv), nc(g.n_cand) {}
 };
 
+// x / velocityBucketSize for x >= 0 without the ~20-instruction integer division in the two bucket sizes the reference uses
+__device__ __forceinline__ int div_bucket(int x, int b) { return b == 1 ? x : b == 2 ? (x >> 1) : x / b; }
+
 // velocity level of a kart's bucket if it is one of the action buckets (KartDiscreteGame.cs:329-340), else -1 (e.g. the root's (0, b))
 __device__ __forceinline__ int velocity_level(const DevGame& g, int mn, int mx)
 {
-    const int b = g.p.velocityBucketSize, j = (mn - 6) / b;
+    const int b = g.p.velocityBucketSize, j = div_bucket(mn - 6, b);
     return (mn >= 6 && mn < g.vmax && (mn - 6) == j * b && mx == min(mn + b, g.vmax)) ? j : -1;
 }
 
@@ -334,7 +343,7 @@ __device__ __forceinline__ int fast_legal(const DevGame& g, const Tables& tb, co
         const float ms = max_speed_radius_wear(g.karts[np], __ldg(&tb.radius[type * 16 + l0 * 4 + l1]), wear);
         const int mi = (int)fminf(ms, 1000.0f);                                                         // fminf(NaN, x) = x
         if (mi < 6) continue;
-        const int jm = min((mi - 6) / b, tb.nv - 1);
+        const int jm = min(div_bucket(mi - 6, b), tb.nv - 1);
         mask |= __ldg(&lm[l1 * tb.nv + jm]);
     }
     return __popcll(mask);
