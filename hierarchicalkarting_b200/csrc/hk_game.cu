@@ -321,12 +321,15 @@ __device__ __forceinline__ int velocity_level(const DevGame& g, int mn, int mx)
 }
 
 // Legal moves of kart np as a bit mask over the RANKS of the pre-sorted candidate list; returns the count.
+// sidx (out) = the kart's section index on the track; lcs_idx = lastCompletedSection % n_sections, carried by the caller (an integer
+// modulo by a run-time divisor is ~15 instructions, and a ply used to take three)
 __device__ __forceinline__ int fast_legal(const DevGame& g, const Tables& tb, const hk_game_state& st, int np, int lvl,
-                                          unsigned long long& mask, const unsigned char*& ord)
+                                          unsigned long long& mask, const unsigned char*& ord, int& sidx, int lcs_idx)
 {
     const hk_kart_state& cs = st.karts[np];
-    const int sidx = cs.section % g.n_sections, type = g.type_of[sidx], l0 = cs.lane - 1;
-    const int os = (g.sec_flags[st.lastCompletedSection % g.n_sections] >> 2) & 3;                   // KartMCTS.cs:252
+    sidx = cs.section % g.n_sections;
+    const int type = g.type_of[sidx], l0 = cs.lane - 1;
+    const int os = (g.sec_flags[lcs_idx] >> 2) & 3;                                                  // KartMCTS.cs:252
     const float wear = (float)cs.tireAge / 10000.0f;
     const int maxdl = (g.sec_flags[sidx] & 1) ? g.p.maxLaneChanges - cs.laneChanges : 99;             // :346
     const size_t cell = (((size_t)type * 4 + l0) * tb.nv + lvl) * 3 + os;
@@ -351,16 +354,27 @@ __device__ __forceinline__ int fast_legal(const DevGame& g, const Tables& tb, co
 
 __device__ __forceinline__ int nth_set_bit(unsigned long long mask, int n)
 {
+    // position of the n-th (0-based) set bit: half selection, then a 5-step popcount descent (__fns is a ~50-instruction loop)
     const unsigned lo = (unsigned)mask, hi = (unsigned)(mask >> 32);
     const int clo = __popc(lo);
-    return n < clo ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - clo + 1);
+    const bool up = n >= clo;
+    unsigned w = up ? hi : lo;
+    int pos = up ? 32 : 0;
+    n -= up ? clo : 0;
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        const int c = __popc(w & ((1u << s) - 1u));
+        const bool u2 = n >= c;
+        n -= u2 ? c : 0; pos += u2 ? s : 0; w = u2 ? (w >> s) : w;
+    }
+    return pos;
 }
 
 // applyAction + makeMove bookkeeping from the tables (:127-171, :420-446)
-__device__ __forceinline__ void fast_move(const DevGame& g, const Tables& tb, hk_game_state& st, int np, int lvl, int gi)
+__device__ __forceinline__ void fast_move(const DevGame& g, const Tables& tb, hk_game_state& st, int np, int lvl, int gi, int sidx, int& lcs_idx)
 {
     hk_kart_state& cs = st.karts[np];
-    const int sidx = cs.section % g.n_sections, type = g.type_of[sidx], l0 = cs.lane - 1, l1 = gi & 3, j = gi >> 2;
+    const int type = g.type_of[sidx], l0 = cs.lane - 1, l1 = gi & 3, j = gi >> 2;
     const int b = g.p.velocityBucketSize, v = 6 + j * b;
     const int dtv = __ldg(&tb.dt[(((size_t)type * 4 + l0) * tb.nv + lvl) * tb.nc + gi]);
     const float load = __ldg(&tb.load[((size_t)type * 16 + l0 * 4 + l1) * tb.nv + j]);
@@ -371,7 +385,7 @@ __device__ __forceinline__ void fast_move(const DevGame& g, const Tables& tb, hk
     cs.section += 1; cs.min_velocity = v; cs.max_velocity = min(v + b, g.vmax); cs.lane = l1 + 1; cs.infeasible = 0;
     bool allAhead = true;
     for (int i = 0; i < st.n_karts; ++i) allAhead &= st.karts[i].section > last;
-    if (allAhead) st.lastCompletedSection = last + 1;
+    if (allAhead) { st.lastCompletedSection = last + 1; lcs_idx = lcs_idx + 1 == g.n_sections ? 0 : lcs_idx + 1; }
 }
 
 // One thread per (type, lane, velocity level): time updates of all candidates, then the policy's static sort order for the
@@ -450,6 +464,7 @@ __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long se
     unsigned moved = 0;
     first_gi = -1;
     n_scores = 0;
+    int lcs_idx = st.lastCompletedSection % g.n_sections;
     for (;;) {
         const int np = up_next(st);
         if (np < 0) return -1;
@@ -461,14 +476,16 @@ __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long se
             index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
             gi = root->order[np][index];
             make_move(g, st, np, action_of(g, gi));
+            lcs_idx = st.lastCompletedSection % g.n_sections;
         } else if (lvl >= 0) {                           // table-driven ply
             unsigned long long mask;
             const unsigned char* ord;
-            const int cnt = fast_legal(g, tb, st, np, lvl, mask, ord);
+            int sidx;
+            const int cnt = fast_legal(g, tb, st, np, lvl, mask, ord, sidx, lcs_idx);
             if (is_over(g, st, cnt, np, scores, n_scores)) break;
             index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
             gi = __ldg(&ord[nth_set_bit(mask, index)]);
-            fast_move(g, tb, st, np, lvl, gi);
+            fast_move(g, tb, st, np, lvl, gi, sidx, lcs_idx);
         } else {                                         // direct evaluation (e.g. the root's (0, bucket) velocity bucket)
             unsigned long long keys[HK_MAX_ACTIONS];
             const int cnt = legal_moves(g, st, np, keys);
@@ -476,6 +493,7 @@ __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long se
             index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
             gi = select_kth(keys, g.n_cand, index);
             make_move(g, st, np, action_of(g, gi));
+            lcs_idx = st.lastCompletedSection % g.n_sections;
         }
         moved |= 1u << np;
         if (ply == 0) first_gi = gi;
