@@ -62,6 +62,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.period = 0.005            # seconds between samples; raised for the host-timed legs (NVML queries contend for driver locks)
 
     def _nvml(self):
         """NVML in-process (nvidia_ml_py): a few microseconds per sample.  Spawning nvidia-smi every 100 ms instead re-initialises
@@ -78,7 +79,7 @@ class ClockSampler(threading.Thread):
             r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
             pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
             self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if r & b else "Not Active" for _, b in bits])
-            self._halt.wait(0.02)
+            self._halt.wait(self.period)
 
     def run(self):
         try:
@@ -286,6 +287,7 @@ def main():
         a0.record(stream); step_device(k); a1.record(stream); a1.synchronize()
         per.append(a0.elapsed_time(a1))
     isolated_ms = float(np.mean(per))
+    sampler.period = 0.25              # the legs below are timed on the host and are sensitive to driver-lock contention
 
     # ---- end to end through the host-pointer C-ABI call (`e2e`) ----------------------------------------------------------
     hp = [p.numpy() for p in pinned]

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
                     Yt[128 + (yo0 ^ 8)] = c11a;  Yt[128 + (yo1 ^ 8)] = c11b;
                 }
                 __syncwarp();
-                double zl, zh;                                      // (Z_i^{new} beta)[g], [8 + g] after the quad reduction
+                double zl, zh;                                      // partial sums of (Z_i^{new} beta)[g], [8 + g]; zl ends as [8 t + g] on lanes t < 2
                 {
                     double c00a = q00.x, c00b = q00.y, c01a = q01.x, c01b = q01.y, c10a = q10.x, c10b = q10.y, c11a = q11.x, c11b = q11.y;
                     {   // + P_i^T (R_i P_i): k = 2; lanes t < 2 hold row t of P_i and form row t of R_i P_i
@@ -259,24 +259,26 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
                     // Z_i^{new} beta (quirk Q2) straight from the C fragments: lane (g, t) holds columns 2t, 2t+1, 8+2t, 8+2t+1 of rows g, 8+g
                     zl = fma(c01b, be1.y, fma(c01a, be1.x, fma(c00b, be0.y, c00a * be0.x)));
                     zh = fma(c11b, be1.y, fma(c11a, be1.x, fma(c10b, be0.y, c10a * be0.x)));
-                    zl += __shfl_xor_sync(0xffffffffu, zl, 1); zh += __shfl_xor_sync(0xffffffffu, zh, 1);
-                    zl += __shfl_xor_sync(0xffffffffu, zl, 2); zh += __shfl_xor_sync(0xffffffffu, zh, 2);
+                    // quad reduction of both sums with two exchanges: odd lanes collect zh, even lanes zl; lane t = 0 ends with all of zl,
+                    // lane t = 1 with all of zh
+                    zl = (t & 1 ? zh : zl) + __shfl_xor_sync(0xffffffffu, t & 1 ? zl : zh, 1);
+                    zl += __shfl_xor_sync(0xffffffffu, zl, 2);
                 }
-                if (t < 2) eta[i * n + 8 * t + g] += t ? zh : zl;                                // eta_i + Z_i^{new} beta, in place
+                if (t < 2) eta[i * n + 8 * t + g] += zl;                                         // eta_i + Z_i^{new} beta, in place
                 __syncwarp();
                 {   // F^T (eta_i + Z_i beta): rows g and 8 + g of F^T from the fragments, reduced over the quad.  The new eta_i below
                     // overwrites what these loads read: every lane's loads feed its shuffles, so they complete before any lane stores.
                     const double v0 = eta[i * n + t], v1 = eta[i * n + 4 + t], v2 = eta[i * n + 8 + t], v3 = eta[i * n + 12 + t];
                     double al = fma(fa3, v3, fma(fa2, v2, fma(fa1, v1, fa0 * v0)));
                     double ah = fma(fb3, v3, fma(fb2, v2, fma(fb1, v1, fb0 * v0)));
-                    al += __shfl_xor_sync(0xffffffffu, al, 1); ah += __shfl_xor_sync(0xffffffffu, ah, 1);
-                    al += __shfl_xor_sync(0xffffffffu, al, 2); ah += __shfl_xor_sync(0xffffffffu, ah, 2);
+                    al = (t & 1 ? ah : al) + __shfl_xor_sync(0xffffffffu, t & 1 ? al : ah, 1);
+                    al += __shfl_xor_sync(0xffffffffu, al, 2);
                     if (t < 2) {
                         const int c = 8 * t + g;
                         const double a0 = alpha[2 * i], a1 = alpha[2 * i + 1];
                         const double ra0 = fma(Rs[i * 4 + 1], a1, Rs[i * 4 + 0] * a0), ra1 = fma(Rs[i * 4 + 3], a1, Rs[i * 4 + 2] * a0);
                         const double pra = fma(Pm[(2 * i + 1) * n + c], ra1, Pm[(2 * i) * n + c] * ra0);
-                        eta[i * n + c] = (qs[i * n + c] + pra) + (t ? ah : al);
+                        eta[i * n + c] = (qs[i * n + c] + pra) + al;
                     }
                 }
             }
