@@ -62,7 +62,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
-        self.period = 0.005            # seconds between samples; raised for the host-timed legs (NVML queries contend for driver locks)
+        self.period = 0.001            # seconds between samples; raised for the host-timed legs (NVML queries contend for driver locks)
 
     def _nvml(self):
         """NVML in-process (nvidia_ml_py): a few microseconds per sample.  Spawning nvidia-smi every 100 ms instead re-initialises
