@@ -367,7 +367,7 @@ __global__ void lqng_assemble_kernel(int batch, int N, double dt, const double* 
 
 // Persistent TMA-staged 2-kart kernel (hk_lqng_mma2p.cuh): dense records (p.A .. p.x0) or, with `compact`, the description of
 // hk_lqng_assemble_solve_batch (p.c_*), assembled by the warp in shared memory.
-static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact)
+static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact, bool full = false)
 {
     const int batch = p.batch;
     static const int variant_env = getenv("HK_MMA2_VARIANT") ? atoi(getenv("HK_MMA2_VARIANT")) : 2;
@@ -375,10 +375,12 @@ static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact)
     // variant 1: 4 warps per CTA, MINB resident CTAs per SM; variant 2 (default): one warp per CTA, MINB resident warps
     // per SM.  16 warps x 128 registers is the measured optimum (profiles/lqng_mma2_tuning_r01.md).
     static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : (variant == 2 ? 16 : 4);
-    const int warps = (compact || variant == 2) ? 1 : 4;
+    const int warps = (compact || full || variant == 2) ? 1 : 4;
     void (*kern)(LqngParams) = nullptr;
     if (compact) {
         kern = lqng_mma2p_kernel<16, 1, true>;
+    } else if (full) {
+        kern = lqng_mma2p_kernel<16, 1, false, true>;
     } else if (variant == 2) {
         kern = minb >= 32 ? lqng_mma2p_kernel<32, 1> : minb >= 24 ? lqng_mma2p_kernel<24, 1> : minb >= 20 ? lqng_mma2p_kernel<20, 1>
                : minb >= 16 ? lqng_mma2p_kernel<16, 1> : lqng_mma2p_kernel<12, 1>;
@@ -386,8 +388,8 @@ static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact)
         kern = minb >= 8 ? lqng_mma2p_kernel<8, 4> : minb >= 6 ? lqng_mma2p_kernel<6, 4> : minb == 5 ? lqng_mma2p_kernel<5, 4>
                : lqng_mma2p_kernel<4, 4>;
     }
-    static int resident_of[2] = {0, 0};                        // persistent grid: SMs x resident CTAs (dense, compact)
-    int& resident = resident_of[compact ? 1 : 0];
+    static int resident_of[3] = {0, 0, 0};                     // persistent grid: SMs x resident CTAs (dense, compact, full)
+    int& resident = resident_of[compact ? 1 : full ? 2 : 0];
     static const int pad = getenv("HK_MMA2_PAD_SMEM") ? atoi(getenv("HK_MMA2_PAD_SMEM")) : 0;   // occupancy experiments only
     if (!resident) {
         int dev = 0, sms = 0, occ = 0;
@@ -485,6 +487,23 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
     LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr, nullptr,
                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0};
     static const bool force_generic = getenv("HK_LQNG_FORCE_GENERIC") != nullptr;
+    static const bool full2 = !(getenv("HK_MMA2_FULL") && atoi(getenv("HK_MMA2_FULL")) == 0);
+    if (N == 2 && !time_varying && (dP || dalpha || dtraj) && !force_generic && full2 &&
+        ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dQ) |
+          reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dR) | reinterpret_cast<uintptr_t>(dx0)) & 15) == 0) {
+        // every output (gains, offsets, rollout) from the same persistent DMMA kernel; it re-reads the gains it has written, so it
+        // gets scratch for whichever of P / alpha the caller does not keep
+        if (!dP || !dalpha) {
+            ThreadCtx* c = ctx();
+            if (!c) return HK_ERR_NO_DEVICE;
+            const size_t T = (size_t)horizon + 1;
+            double* scratch = (double*)dscratch(c, 1, sizeof(double) * (size_t)batch * T * 36);
+            if (!scratch) return HK_ERR_OUT_OF_MEMORY;
+            if (!dP) p.P = scratch;
+            if (!dalpha) p.alpha = scratch + (size_t)batch * T * 32;
+        }
+        return launch_mma2p(p, stream, false, true);
+    }
     if (N == 2 && !time_varying && !dP && !dalpha && !dtraj && !force_generic) {
         // throughput path: one launch of a DMMA kernel (problems it cannot take fall back inside the kernel)
         static const int variant = getenv("HK_MMA2_VARIANT") ? atoi(getenv("HK_MMA2_VARIANT")) : 2;   // 0: one CTA per 4 problems; 1, 2: persistent + TMA

@@ -38,6 +38,7 @@ template <int WARPS>
 struct P2Smem {
     double rec[WARPS][2][P2_STRIDE];
     double stage[WARPS][2][C2_STRIDE];           // compact mode only
+    double roll[WARPS][16];                      // FULL mode: state (8) and controls (4) of the closed-loop rollout
     double fallback[GenericLayout<2>::total];    // one pivoting scratch per CTA, serialised by `lock` (rare path)
     unsigned long long bar[WARPS][2];
     int lock;
@@ -74,7 +75,10 @@ __device__ __forceinline__ bool bits_differ(double a, double b)
 // COMPACT: the warp assembles its dense record in shared memory from the staged compact description — LinearizedBicycle.getA/getB
 // (KartLQRDynamics.cs:40-62) and LQRCheckpointReachAvoidCost.getQMatrix/getQVec/getRMatrix (KartLQRCosts.cs:57-140, quirks Q3-Q5 of
 // SURVEY.md A.3), same arithmetic as lqng_assemble_kernel — instead of reading a dense record another kernel wrote to HBM.
-template <int MINB, int WARPS, bool COMPACT = false>
+// FULL: every output of the ABI — gains P_t, offsets alpha_t of every step (the reference computes them and keeps only t = 0,
+// KartLQR.cs:104-105, 121-126), u0 = -P_0 x0 - alpha_0 of every player, and the closed-loop rollout.  The last
+// backward step is then a full step (no u0 shortcut), gains go to global memory as they are produced and the rollout re-reads them.
+template <int MINB, int WARPS, bool COMPACT = false, bool FULL = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams p)
 {
     __shared__ __align__(128) P2Smem<WARPS> sm;
@@ -109,6 +113,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
     // warps exit (its ramp-up overlaps this launch's tail).  Such a dependent reads only its own inputs before
     // griddepcontrol.wait, which it executes before its first global store (see below) — by then this grid has completed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (FULL) asm volatile("griddepcontrol.wait;" ::: "memory");     // gains are stored from inside the recursion
     if (first >= p.batch) { asm volatile("griddepcontrol.wait;" ::: "memory"); finish(); return; }   // whole warps only; no block-wide sync below
 
     const unsigned stage_u32 = smem_u32(&sm.stage[wib][0][0]);
@@ -274,12 +279,12 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             mm(l0, l1, g < 4 ? w0 : e0, g < 4 ? w1 : e1, yL0, yL1);
             // RM^T = A^T W^T (RHSMat, :89-95); not needed at t = 0, where only u0 = -LHS^-1 (RM x0 + rv) is
             double m0 = 0.0, m1 = 0.0;
-            if (!last) mm(m0, m1, aT0, aT1, w0, w1);
+            if (FULL || !last) mm(m0, m1, aT0, aT1, w0, w1);
             double M0 = l0, M1 = l1;
             {
                 const double v0 = shfl_d(l0, srcRv), v1 = shfl_d(l1, srcRv);
                 double rv = godd ? v1 : v0;
-                if (last) rv += l0;                                 // l0 of an Aug lane = (RM x0)[rho]
+                if (last && !FULL) rv += l0;                        // l0 of an Aug lane = (RM x0)[rho]
                 if (isAug) M0 = rv;
             }
             if (!pivot) {
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
                 M0 = rho == 0 ? a0 : rho == 1 ? a1 : rho == 2 ? a2 : a3;
                 M1 = rho == 0 ? b0 : rho == 1 ? b1 : rho == 2 ? b2 : b3;
             }
-            if (last) {                                             // optimal_control = -P x0 - alpha with the t = 0 gains (:121-126)
+            if (!FULL && last) {                                    // optimal_control = -P x0 - alpha with the t = 0 gains (:121-126)
                 u_out = -M0;
                 break;
             }
@@ -358,6 +363,14 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             double pe = 0.0, po = 0.0;                              // (P[2(t>>1)][g], P[2(t>>1)+1][g])   (:104-105)
             mm(pe, po, m0, m1, y0, y1);
             const double pc = podd ? po : pe;                       // compact P: P[t][g]
+            if (FULL) {                                             // P_step [4][8] (one coalesced 256-byte store), alpha_step [4]
+                if (p.P) p.P[((size_t)prob * (p.horizon + 1) + step) * 32 + t * 8 + g] = pc;
+                if (p.alpha && g == 0 && !(t & 1)) {
+                    double* a = p.alpha + ((size_t)prob * (p.horizon + 1) + step) * 4 + t;
+                    a[0] = ae; a[1] = ao;
+                }
+                if (last) break;
+            }
             // F = A - B P (T-form), beta = -B alpha   (:110-111)
             const double f0 = fma(-bFa.y, po, fma(-bFa.x, pe, aT0));
             const double f1 = fma(-bFb.y, po, fma(-bFb.x, pe, aT1));
@@ -409,6 +422,39 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             } else if (lane < 8) lqng_generic_body<2>(p, prob, true, sm.fallback, lane, 0xffu);
             __syncwarp();
             if (lane == 0) { __threadfence_block(); atomicExch(&sm.lock, 0); }
+        } else if (FULL) {
+            // u_t = -P_t x_t - alpha_t, x_{t+1} = A x_t + B u_t in forward time order (t = 0 is the pair computed last); the gains
+            // are re-read from the output buffers this warp has just written (the launcher lends scratch when the caller keeps none)
+            const int T = p.horizon + 1;
+            const double* gP = p.P + (size_t)prob * T * 32;
+            const double* ga = p.alpha + (size_t)prob * T * 4;
+            double* gt = p.traj ? p.traj + (size_t)prob * (T + 1) * 8 : nullptr;
+            double* xs = &sm.roll[wib][0];
+            double* us = xs + 8;
+            if (lane < 8) { const double v = rec[P2_ox + lane]; xs[lane] = v; if (gt) gt[lane] = v; }
+            __syncwarp();
+            for (int st = 0; st < (gt ? T : 1); ++st) {
+                double sacc = gP[st * 32 + t * 8 + g] * xs[g];
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 8);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+                const double u = -sacc - ga[st * 4 + t];
+                if (g == 0) { us[t] = u; if (st == 0) p.u0[(size_t)prob * 4 + t] = u; }
+                if (!gt) break;
+                __syncwarp();
+                double xn = 0.0;
+                if (lane < 8) {
+                    const int pr = lane >> 2, rr_ = lane & 3;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) xn = fma(rec[P2_oA + pr * 16 + rr_ * 4 + c], xs[4 * pr + c], xn);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) xn = fma(rec[P2_oB + pr * 8 + rr_ * 2 + c], us[2 * pr + c], xn);
+                }
+                __syncwarp();
+                if (lane < 8) { xs[lane] = xn; gt[(size_t)(st + 1) * 8 + lane] = xn; }
+                __syncwarp();
+            }
+            if (lane == 0 && p.status) p.status[prob] = 0;
         } else {
             if (isAug) p.u0[(size_t)prob * 4 + g] = u_out;
             if (lane == 0 && p.status) p.status[prob] = 0;

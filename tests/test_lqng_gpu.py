@@ -111,6 +111,52 @@ def test_pivot_pass_of_the_throughput_kernel(hk, oracle):
         assert rel_err(got["u0"][b], ref["u0"][b]) <= tol, (b, kind[b])
 
 
+@pytest.mark.gpu
+def test_full_outputs_of_the_throughput_kernel(hk, oracle):
+    """Gains, offsets and the closed-loop rollout of a time-invariant 2-kart batch come from the same DMMA kernel (FULL mode of
+    hk_lqng_mma2p.cuh): mixed batch with row-exchange problems (pivot pass), non-symmetric Q (shared-memory fallback inside the
+    kernel), singular systems; with every subset of the optional outputs requested."""
+    rng = np.random.default_rng(22)
+    batch = 257
+    A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(S.OVAL, batch, 2, seed=6))
+    kind = np.arange(batch) % 7
+    for b in np.nonzero(kind == 3)[0]:
+        c = 0.2 + 0.1 * rng.random()
+        R[b] = np.array([[0.05 * c, c], [c, 0.03 * c]])
+    for b in np.nonzero(kind == 4)[0]:
+        Q[b] += 0.05 * rng.standard_normal((2, 8, 8))      # non-symmetric Q_i
+    sing = np.nonzero(kind == 6)[0][:4]
+    B[sing] = 0.0
+    R[sing] = 0.0
+    ref = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 3)
+    got = lqr.solve_batch(A, B, Q, q, R, x0, 3)
+    assert np.array_equal(got["status"], ref["status"]) and ref["status"].sum() == 4
+    ok = ref["status"] == 0
+    for k in ("u0", "P", "alpha", "traj"):
+        for b in np.nonzero(ok)[0]:
+            assert rel_err(got[k][b], ref[k][b]) <= TOL, (k, b, kind[b])
+    # subsets of the optional outputs through the device-pointer entry (the launcher lends scratch for what the rollout re-reads)
+    import torch
+    from hierarchicalkarting_b200 import abi
+    lib = hk
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (A, B, Q, q, R, x0)]
+    for want in (("P",), ("alpha",), ("traj",), ("P", "traj")):
+        u0 = torch.zeros((batch, 4), dtype=torch.float64, device=dev)
+        st = torch.zeros(batch, dtype=torch.int32, device=dev)
+        out = {"P": torch.zeros((batch, 4, 4, 8), dtype=torch.float64, device=dev), "alpha": torch.zeros((batch, 4, 4), dtype=torch.float64, device=dev),
+               "traj": torch.zeros((batch, 5, 8), dtype=torch.float64, device=dev)}
+        ptr = {k: (out[k].data_ptr() if k in want else None) for k in out}
+        abi.check(lib.hk_lqng_solve_batch_device(batch, 2, 3, 0, *[t.data_ptr() for t in d], u0.data_ptr(), ptr["P"], ptr["alpha"], ptr["traj"],
+                                                 st.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(st.cpu().numpy(), ref["status"])
+        for k in ("u0",) + want:
+            g = (u0 if k == "u0" else out[k]).cpu().numpy()
+            for b in np.nonzero(ok)[0]:
+                assert rel_err(g[b], ref[k][b]) <= TOL, (want, k, b)
+
+
 def test_golden_fixture(hk):
     g = np.load("tests/golden/lqng_golden.npz")
     for N in (2, 4):
