@@ -362,6 +362,34 @@ def main():
         abi.check(lib.hk_lqng_solve_one(N, HORIZON, *[abi.dptr(a) for a in one], abi.dptr(u1)))
     single_us = 1e6 * (time.perf_counter() - t0) / 200
 
+    # ---- 2-kart LQNG with every output (gains P_t, offsets alpha_t, closed-loop rollout: the north_star's wording; the reference
+    #      itself returns only u0, which is what `value` measures) -----------------------------------------------------------
+    T = HORIZON + 1
+    P_d = torch.empty((batch, T, m, n), dtype=torch.float64, device=dev)
+    al_d = torch.empty((batch, T, m), dtype=torch.float64, device=dev)
+    tr_d = torch.empty((batch, T + 1, n), dtype=torch.float64, device=dev)
+
+    def step_full(k):
+        a = sets[k % N_INPUT_SETS]
+        abi.check(lib.hk_lqng_solve_batch_device(batch, N, HORIZON, 0, *[t.data_ptr() for t in a], u0_d.data_ptr(), P_d.data_ptr(),
+                                                 al_d.data_ptr(), tr_d.data_ptr(), st_d.data_ptr(), stream.cuda_stream))
+    for k in range(args.warmup):
+        step_full(k)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    for k in range(args.steps):
+        step_full(k)
+    g1.record(stream)
+    g1.synchronize()
+    full_ms = max_over_ranks(g0.elapsed_time(g1)) / args.steps
+    out_bytes = (T * (m * n + m) + (T + 1) * n + m) * 8 + 4
+    full_obj = {"metric": "lqng_full_output_solves_per_s", "value": world * batch / (full_ms * 1e-3), "unit": "solves/s",
+                "ms_per_step": full_ms, "outputs": "u0 of every player, P_t [T][4][8], alpha_t [T][4], trajectory [T+1][8], status",
+                "hbm_bytes_per_solve": 1664 + out_bytes, "status_nonzero": int(st_d.sum().item()),
+                "kernel": "lqng_mma2p_kernel<16, 1, false, true> (FULL mode of the persistent DMMA kernel)"}
+    del P_d, al_d, tr_d
+
     # ---- 4-kart LQNG (BASELINE config 3: 1,048,576 Complex 2v2 problems per GPU, HBM-resident) --------------------------------
     lqng4_obj = None
     if not args.no_lqng4:
@@ -473,6 +501,7 @@ def main():
         line["mcts"] = mcts_obj
     if race_obj:
         line["race"] = race_obj
+    line["full_outputs"] = full_obj
     if lqng4_obj:
         line["lqng4"] = lqng4_obj
     if world == 1 and not args.no_cpu_baseline:

@@ -522,13 +522,15 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
         return HK_OK;
     }
     static const bool mma4 = !(getenv("HK_LQNG_MMA4") && atoi(getenv("HK_LQNG_MMA4")) == 0);
-    if (N == 4 && mma4 && !force_generic) {
-        // 4-kart game: warp per problem, DMMA for the 16 x 16 products (hk_lqng_mma4.cuh); takes every operand form
+    if ((N == 4 || N == 3) && mma4 && !force_generic && (reinterpret_cast<uintptr_t>(dQ) & 15) == 0) {
+        // 3- and 4-kart games: warp per problem, DMMA for the 16 x 16 products (hk_lqng_mma4.cuh); takes every operand form
+        // (Q_i is read with 128-bit loads: an 8-byte aligned Q goes to the general kernel)
         const size_t smem = (size_t)MMA4_WARPS * Mma4Layout::total * sizeof(double);
         const long long want = ((long long)batch + MMA4_WARPS - 1) / MMA4_WARPS;
         const unsigned grid = (unsigned)(want < 148 * 40 ? want : 148 * 40);
         count_launch();
-        lqng_mma4_kernel<<<grid, 32 * MMA4_WARPS, smem, stream>>>(p);
+        if (N == 4) lqng_mma4_kernel<4><<<grid, 32 * MMA4_WARPS, smem, stream>>>(p);
+        else lqng_mma4_kernel<3><<<grid, 32 * MMA4_WARPS, smem, stream>>>(p);
         HK_CUDA(cudaGetLastError());
         return HK_OK;
     }

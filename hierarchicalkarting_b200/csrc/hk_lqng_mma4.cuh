@@ -40,10 +40,15 @@ struct Mma4Layout {
 
 constexpr int MMA4_WARPS = 2;
 
+// NP = players of the game (3 or 4).  A 3-kart game runs in the same 16 x 16 / 8 x 8 frame with a decoupled dummy fourth player
+// (B_3 = 0, Q_3 = 0, q_3 = 0, A_3 = R_3 = I): its gains, its Z and its eta stay exactly zero, the coupled system is block diagonal
+// with an identity block (pivot choices of the real 6 x 6 system unchanged), and its pass through the player loop is skipped.
+template <int NP>
 __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParams p)
 {
     using L = Mma4Layout;
     constexpr int N = 4, n = 16, m = 8, LD = L::LD;
+    constexpr int rn = 4 * NP, rm = 2 * NP;                         // real joint state / control dimensions (record strides)
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3, lo = lane & 15, hf = lane >> 4;
@@ -61,45 +66,67 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
 
     for (long long prob = (long long)blockIdx.x * MMA4_WARPS + wib; prob < p.batch; prob += nwarps) {
         const int T = p.horizon + 1, Tm = p.time_varying ? T : 1;
-        const double* gA = p.A + (size_t)prob * Tm * N * 16;
-        const double* gB = p.B + (size_t)prob * Tm * N * 8;
-        const double* gQ = p.Q + (size_t)prob * Tm * N * n * n;
-        const double* gq = p.q + (size_t)prob * Tm * N * n;
-        const double* gR = p.R + (size_t)prob * Tm * N * 4;
-        const double* gx = p.x0 + (size_t)prob * n;
-        double* gP = p.P ? p.P + (size_t)prob * T * m * n : nullptr;
-        double* ga = p.alpha ? p.alpha + (size_t)prob * T * m : nullptr;
+        const double* gA = p.A + (size_t)prob * Tm * NP * 16;
+        const double* gB = p.B + (size_t)prob * Tm * NP * 8;
+        const double* gQ = p.Q + (size_t)prob * Tm * NP * rn * rn;
+        const double* gq = p.q + (size_t)prob * Tm * NP * rn;
+        const double* gR = p.R + (size_t)prob * Tm * NP * 4;
+        const double* gx = p.x0 + (size_t)prob * rn;
+        double* gP = p.P ? p.P + (size_t)prob * T * rm * rn : nullptr;
+        double* ga = p.alpha ? p.alpha + (size_t)prob * T * rm : nullptr;
         int singular = 0;
-        if (prob + nwarps < p.batch) {                              // this warp's next record: 82 lines of 128 B into L2 while this one is solved
+        if (prob + nwarps < p.batch) {                              // this warp's next record into L2 while this one is solved
             const size_t nx = (size_t)(prob + nwarps) * Tm;
-            const char* nq = reinterpret_cast<const char*>(p.Q + nx * N * n * n);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + 128 * lane));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + 128 * (32 + lane)));
-            const char* no = lane < 4 ? reinterpret_cast<const char*>(p.A + nx * N * 16) + 128 * lane
-                           : lane < 6 ? reinterpret_cast<const char*>(p.B + nx * N * 8) + 128 * (lane - 4)
-                           : lane < 10 ? reinterpret_cast<const char*>(p.q + nx * N * n) + 128 * (lane - 6)
-                           : lane == 10 ? reinterpret_cast<const char*>(p.R + nx * N * 4) : reinterpret_cast<const char*>(p.x0 + (size_t)(prob + nwarps) * n);
-            if (lane < 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(no));
+            const char* nq = reinterpret_cast<const char*>(p.Q + nx * NP * rn * rn);
+            constexpr int q_lines = (NP * rn * rn * 8 + 127) / 128;                      // 64 (4 karts) / 27 (3 karts)
+            if (lane < q_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + 128 * lane));
+            if (32 + lane < q_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + 128 * (32 + lane)));
+            const char* no = lane < 4 ? reinterpret_cast<const char*>(p.A + nx * NP * 16) + 128 * lane
+                           : lane < 6 ? reinterpret_cast<const char*>(p.B + nx * NP * 8) + 128 * (lane - 4)
+                           : lane < 10 ? reinterpret_cast<const char*>(p.q + nx * NP * rn) + 128 * (lane - 6)
+                           : lane == 10 ? reinterpret_cast<const char*>(p.R + nx * NP * 4) : reinterpret_cast<const char*>(p.x0 + (size_t)(prob + nwarps) * rn);
+            const bool in = lane < 4 ? 128 * lane < NP * 128 : lane < 6 ? 128 * (lane - 4) < NP * 64 : lane < 10 ? 128 * (lane - 6) < NP * rn * 8 : true;
+            if (lane < 12 && in) asm volatile("prefetch.global.L2 [%0];" ::"l"(no));
         }
         __syncwarp();
-        {   // Zs = Q, etas = q of the last stage (KartLQR.cs:62-63): 1,024 doubles, 128-bit coalesced loads
-            const double* q0 = gQ + (size_t)(Tm - 1) * N * n * n;
-            for (int e = lane; e < N * n * n / 2; e += 32) {
-                const double2 v = *reinterpret_cast<const double2*>(q0 + 2 * e);
-                const int i = e >> 7, r = (e >> 3) & 15, c = (e & 7) * 2;
-                *reinterpret_cast<double2*>(Z + i * 256 + L::at(r, c)) = v;
+        {   // Zs = Q, etas = q of the last stage (KartLQR.cs:62-63): 128-bit coalesced loads
+            const double* q0 = gQ + (size_t)(Tm - 1) * NP * rn * rn;
+            if (NP == 4) {
+                for (int e = lane; e < N * n * n / 2; e += 32) {
+                    const double2 v = *reinterpret_cast<const double2*>(q0 + 2 * e);
+                    const int i = e >> 7, r = (e >> 3) & 15, c = (e & 7) * 2;
+                    *reinterpret_cast<double2*>(Z + i * 256 + L::at(r, c)) = v;
+                }
+                for (int e = lane; e < N * n; e += 32) { const double v = gq[(size_t)(Tm - 1) * N * n + e]; eta[e] = v; qs[e] = v; }
+            } else {
+                for (int e = lane; e < N * n * n / 2; e += 32) *reinterpret_cast<double2*>(Z + 2 * e) = make_double2(0.0, 0.0);
+                eta[lane] = 0.0; eta[32 + lane] = 0.0; qs[lane] = 0.0; qs[32 + lane] = 0.0;
+                __syncwarp();
+                for (int e = lane; e < NP * rn * rn / 2; e += 32) {
+                    const double2 v = *reinterpret_cast<const double2*>(q0 + 2 * e);
+                    const int i = e / (rn * rn / 2), rem = e % (rn * rn / 2), r = rem / (rn / 2), c = (rem % (rn / 2)) * 2;
+                    *reinterpret_cast<double2*>(Z + i * 256 + L::at(r, c)) = v;
+                }
+                for (int e = lane; e < NP * rn; e += 32) {
+                    const double v = gq[(size_t)(Tm - 1) * NP * rn + e];
+                    eta[(e / rn) * n + e % rn] = v; qs[(e / rn) * n + e % rn] = v;
+                }
+                // the dummy player: A_3 = I, B_3 = 0, R_3 = I
+                if (lane < 16) As[NP * 16 + lane] = (lane >> 2) == (lane & 3) ? 1.0 : 0.0;
+                if (lane < 8) Bs[NP * 8 + lane] = 0.0;
+                if (lane < 4) Rs[NP * 4 + lane] = (lane == 0 || lane == 3) ? 1.0 : 0.0;
             }
-            for (int e = lane; e < N * n; e += 32) { const double v = gq[(size_t)(Tm - 1) * N * n + e]; eta[e] = v; qs[e] = v; }
-            if (lane < n) xs[lane] = gx[lane];
+            if (lane < n) xs[lane] = lane < rn ? gx[lane] : 0.0;
         }
         for (int st = p.horizon; st >= 0; --st) {                   // KartLQR.cs:64
             const int tt = p.time_varying ? st : 0;
-            const double* Qt = gQ + (size_t)tt * N * n * n;
+            const double* Qt = gQ + (size_t)tt * NP * rn * rn;
             if (p.time_varying || st == p.horizon) {
-                if (st != p.horizon) { qs[lane] = gq[(size_t)tt * N * n + lane]; qs[32 + lane] = gq[(size_t)tt * N * n + 32 + lane]; }
-                for (int e = lane; e < N * 16; e += 32) As[e] = gA[(size_t)tt * N * 16 + e];
-                Bs[lane] = gB[(size_t)tt * N * 8 + lane];
-                if (lane < N * 4) Rs[lane] = gR[(size_t)tt * N * 4 + lane];
+                if (st != p.horizon)
+                    for (int e = lane; e < NP * rn; e += 32) qs[(e / rn) * n + e % rn] = gq[(size_t)tt * NP * rn + e];
+                for (int e = lane; e < NP * 16; e += 32) As[e] = gA[(size_t)tt * NP * 16 + e];
+                if (lane < NP * 8) Bs[lane] = gB[(size_t)tt * NP * 8 + lane];
+                if (lane < NP * 4) Rs[lane] = gR[(size_t)tt * NP * 4 + lane];
             }
             __syncwarp();
             // W_i = B_i^T Z_i (rows of block i only: B_i is zero elsewhere, KartLQR.cs:41-52); lane owns column lo of two players
@@ -178,15 +205,15 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
             if (lane >= 8 && lane < 24) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) Pm[r * n + lane - 8] = col[r];
-                if (gP)
+                if (gP && lane - 8 < rn)
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) gP[(size_t)st * m * n + r * n + lane - 8] = col[r];
+                    for (int r = 0; r < rm; ++r) gP[(size_t)st * rm * rn + r * rn + lane - 8] = col[r];
             } else if (lane == 24) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) alpha[r] = col[r];
                 if (ga)
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) ga[(size_t)st * m + r] = col[r];
+                    for (int r = 0; r < rm; ++r) ga[(size_t)st * rm + r] = col[r];
             }
             __syncwarp();
             // F = A - sum_k B_k P_k (stored transposed), beta = -sum_k B_k alpha_k (:110-111)
@@ -208,14 +235,16 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
             const double fa0 = Ft[f0], fa1 = Ft[f1], fa2 = Ft[f2], fa3 = Ft[f3];
             const double fb0 = Ft[128 + f0], fb1 = Ft[128 + f1], fb2 = Ft[128 + f2], fb3 = Ft[128 + f3];
             const double2 be0 = *reinterpret_cast<const double2*>(beta + 2 * t), be1 = *reinterpret_cast<const double2*>(beta + 8 + 2 * t);
-            for (int i = 0; i < N; ++i) {
+            for (int i = 0; i < NP; ++i) {
                 double* Zi = Z + i * 256;
                 // C fragments of the new Z_i start from Q_i: issue the loads before the first product to hide their L2 latency
-                const double* Qi = Qt + (size_t)i * n * n;
-                const double2 q00 = *reinterpret_cast<const double2*>(Qi + g * n + 2 * t);
-                const double2 q01 = *reinterpret_cast<const double2*>(Qi + g * n + 8 + 2 * t);
-                const double2 q10 = *reinterpret_cast<const double2*>(Qi + (8 + g) * n + 2 * t);
-                const double2 q11 = *reinterpret_cast<const double2*>(Qi + (8 + g) * n + 8 + 2 * t);
+                const double* Qi = Qt + (size_t)i * rn * rn;
+                const double2 zero2 = make_double2(0.0, 0.0);
+                const bool cin = 8 + 2 * t < rn, rin = 8 + g < rn;   // rows / columns 12..15 of a 3-kart game are padding
+                const double2 q00 = *reinterpret_cast<const double2*>(Qi + g * rn + 2 * t);
+                const double2 q01 = cin ? *reinterpret_cast<const double2*>(Qi + g * rn + 8 + 2 * t) : zero2;
+                const double2 q10 = rin ? *reinterpret_cast<const double2*>(Qi + (8 + g) * rn + 2 * t) : zero2;
+                const double2 q11 = (cin && rin) ? *reinterpret_cast<const double2*>(Qi + (8 + g) * rn + 8 + 2 * t) : zero2;
                 {   // Y = Z_i F, stored transposed
                     double c00a = 0, c00b = 0, c01a = 0, c01b = 0, c10a = 0, c10b = 0, c11a = 0, c11b = 0;
 #define HK_M4_Y(fk, bl, bh)                                                                       \
@@ -285,34 +314,34 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
             __syncwarp();
         }
         // optimal_control = -P x0 - alpha with the t = 0 pair (:121-126), every player
-        if (lane < m) {
+        if (lane < rm) {
             double acc = 0.0;
 #pragma unroll
-            for (int c = 0; c < n; ++c) acc = fma(-Pm[lane * n + c], xs[c], acc);
-            p.u0[(size_t)prob * m + lane] = acc - alpha[lane];
+            for (int c = 0; c < rn; ++c) acc = fma(-Pm[lane * n + c], xs[c], acc);
+            p.u0[(size_t)prob * rm + lane] = acc - alpha[lane];
         }
         if (lane == 0 && p.status) p.status[prob] = singular;
         // closed-loop rollout; gains are re-read from the P/alpha output buffers written above
         if (p.traj) {
-            double* gt = p.traj + (size_t)prob * (T + 1) * n;
-            if (lane < n) gt[lane] = xs[lane];
+            double* gt = p.traj + (size_t)prob * (T + 1) * rn;
+            if (lane < rn) gt[lane] = xs[lane];
             __syncwarp();
             for (int st = 0; st <= p.horizon; ++st) {
                 const int tt = p.time_varying ? st : 0;
-                if (lane < m) {
+                if (lane < rm) {
                     double acc = 0.0;
-                    for (int c = 0; c < n; ++c) acc = fma(-gP[(size_t)st * m * n + lane * n + c], xs[c], acc);
-                    us[lane] = acc - ga[(size_t)st * m + lane];
+                    for (int c = 0; c < rn; ++c) acc = fma(-gP[(size_t)st * rm * rn + lane * rn + c], xs[c], acc);
+                    us[lane] = acc - ga[(size_t)st * rm + lane];
                 }
                 __syncwarp();
                 double xn = 0.0;
-                if (lane < n) {
+                if (lane < rn) {
                     const int pr = lane >> 2, rr = lane & 3;
-                    for (int c = 0; c < 4; ++c) xn = fma(gA[(size_t)tt * N * 16 + pr * 16 + rr * 4 + c], xs[4 * pr + c], xn);
-                    for (int c = 0; c < 2; ++c) xn = fma(gB[(size_t)tt * N * 8 + pr * 8 + rr * 2 + c], us[2 * pr + c], xn);
+                    for (int c = 0; c < 4; ++c) xn = fma(gA[(size_t)tt * NP * 16 + pr * 16 + rr * 4 + c], xs[4 * pr + c], xn);
+                    for (int c = 0; c < 2; ++c) xn = fma(gB[(size_t)tt * NP * 8 + pr * 8 + rr * 2 + c], us[2 * pr + c], xn);
                 }
                 __syncwarp();
-                if (lane < n) { xs[lane] = xn; gt[(size_t)(st + 1) * n + lane] = xn; }
+                if (lane < rn) { xs[lane] = xn; gt[(size_t)(st + 1) * rn + lane] = xn; }
                 __syncwarp();
             }
         }

@@ -31,7 +31,7 @@ def test_parity_time_invariant(hk, oracle, N, track, horizon):
     _check(got_u, ref, full=False)
 
 
-@pytest.mark.parametrize("N", [1, 2, 4])
+@pytest.mark.parametrize("N", [1, 2, 3, 4])
 def test_parity_time_varying(hk, oracle, N):
     rng = np.random.default_rng(5)
     horizon, batch = 3, 64
@@ -63,10 +63,12 @@ def test_general_dense_blocks_and_nonsymmetric_q(hk, oracle):
         _check(got, ref)
 
 
-def test_pivoting_and_singular_status(hk, oracle):
-    """LHS whose natural pivot order is wrong (tiny R, large coupling) and an exactly singular LHS (R = 0, B = 0)."""
+@pytest.mark.parametrize("N", [2, 3, 4])
+def test_pivoting_and_singular_status(hk, oracle, N):
+    """LHS whose natural pivot order is wrong (tiny R, large coupling) and an exactly singular LHS (R = 0, B = 0).
+    N = 3 runs in the 4-kart kernel's frame with a decoupled dummy player: its identity rows must never be taken as pivots."""
     rng = np.random.default_rng(3)
-    N, n, batch = 2, 8, 16
+    n, batch = 4 * N, 16
     A = np.tile(np.eye(4), (batch, N, 1, 1))
     B = rng.standard_normal((batch, N, 4, 2))
     Q = rng.standard_normal((batch, N, n, n)); Q = Q + np.swapaxes(Q, -1, -2)
@@ -75,8 +77,10 @@ def test_pivoting_and_singular_status(hk, oracle):
     x0 = rng.standard_normal((batch, n))
     ref = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 2)
     got = lqr.solve_batch(A, B, Q, q, R, x0, 2)
+    assert np.array_equal(got["status"], ref["status"])
     for b in range(batch):
-        assert rel_err(got["u0"][b], ref["u0"][b]) <= 1e-7              # conditioning of these systems is ~1e3-1e5
+        for k in ("u0", "P", "alpha"):
+            assert rel_err(got[k][b], ref[k][b]) <= (1e-7 if N == 2 else 1e-5), (k, b)   # conditioning of these systems is ~1e3-1e6
     Bz = np.zeros_like(B); Rz = np.zeros_like(R)
     ref = oracle.lqng_solve_batch(A, Bz, Q, q, Rz, x0, 1)
     got = lqr.solve_batch(A, Bz, Q, q, Rz, x0, 1)
