@@ -295,13 +295,14 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
                 }
                 if (t < 2) eta[i * n + 8 * t + g] += zl;                                         // eta_i + Z_i^{new} beta, in place
                 __syncwarp();
-                {   // F^T (eta_i + Z_i beta): rows g and 8 + g of F^T from the fragments, reduced over the quad.  The new eta_i below
-                    // overwrites what these loads read: every lane's loads feed its shuffles, so they complete before any lane stores.
+                {   // F^T (eta_i + Z_i beta): rows g and 8 + g of F^T from the fragments, reduced over the quad; the new eta_i below
+                    // overwrites what these loads read
                     const double v0 = eta[i * n + t], v1 = eta[i * n + 4 + t], v2 = eta[i * n + 8 + t], v3 = eta[i * n + 12 + t];
                     double al = fma(fa3, v3, fma(fa2, v2, fma(fa1, v1, fa0 * v0)));
                     double ah = fma(fb3, v3, fma(fb2, v2, fma(fb1, v1, fb0 * v0)));
                     al = (t & 1 ? ah : al) + __shfl_xor_sync(0xffffffffu, t & 1 ? al : ah, 1);
                     al += __shfl_xor_sync(0xffffffffu, al, 2);
+                    __syncwarp();                                   // every lane has read eta_i + Z_i beta before it is overwritten
                     if (t < 2) {
                         const int c = 8 * t + g;
                         const double a0 = alpha[2 * i], a1 = alpha[2 * i + 1];

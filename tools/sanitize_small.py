@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck): a few hundred LQNG problems
+of each size and output form, the compact entry, rollouts, one short race."""
+import sys
+sys.path.insert(0, '.')
+import numpy as np
+from hierarchicalkarting_b200 import abi, lqr, mcts as M, tracks, scenarios as S, race as RC
+lib = abi.load_library(); abi.check(lib.hk_init(0))
+for N, track in ((1, S.OVAL), (2, S.OVAL), (3, S.COMPLEX), (4, S.COMPLEX)):
+    A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(track, 130, N, seed=3))
+    for full in (False, True):
+        out = lqr.solve_batch(A, B, Q, q, R, x0, 3, full=full)
+        assert np.all(np.isfinite(out["u0"]))
+prob = S.make_problems(S.OVAL, 20000, 2, seed=4)
+keys = ("x0", "target", "tw", "cw", "aw", "otgt", "otw")
+arrs = [np.ascontiguousarray(prob[k], dtype=np.float64) for k in keys]
+u0 = np.zeros((20000, 4)); st = np.zeros(20000, dtype=np.int32)
+abi.check(lib.hk_lqng_assemble_solve_batch(20000, 2, 3, float(prob["dt"]), *[abi.dptr(a) for a in arrs], abi.dptr(u0), abi.iptr(st)))
+G = M.Game(tracks.COMPLEX, 2, 2)
+leaf = tracks.root_state(tracks.COMPLEX, 3, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 80])
+G.rollouts(leaf, 20000, seed=1)
+RS = RC.Races(S.OVAL, RC.race_params(S.OVAL))
+karts, plans = RC.start_grid(S.OVAL, 64, seed=1)
+RS.run(karts, plans, 0, 5)
+print("sanitize_small ok")
