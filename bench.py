@@ -342,6 +342,21 @@ def main():
                     "plies_per_s": world * plies / el, "ms_per_decision": 1e3 * el / reps, "rollouts_per_decision": MCTS_ROLLOUTS,
                     "config": "BASELINE config 4: Complex, 2 karts, depth 8, bucket 2, Philox4x32-10; host call incl. result D2H",
                     "gpu_launches": reps}
+        # the same decision through the reference's own entry points (KartMCTS.constructSearchTree + getBestStatesSequence): host tree
+        # policy, every iteration expands one leaf with a batch of GPU rollouts through each child (processLeaf, KartMCTS.cs:124-159)
+        try:
+            root_state = M.DiscreteGameState(G, leaf)
+            M.KartMCTS.rollouts_per_leaf = 4096
+            M.KartMCTS.constructSearchTree(root_state, T=1e9, seed=7, max_iterations=3)          # warm-up
+            t0 = time.perf_counter()
+            root = M.KartMCTS.constructSearchTree(root_state, T=1e9, seed=20260003, max_iterations=14)
+            seq = M.KartMCTS.getBestStatesSequence(root)
+            el_tree = time.perf_counter() - t0
+            mcts_obj["tree_search"] = {"ms_per_decision": 1e3 * el_tree, "iterations": 14, "episodes_at_root": int(root.numEpisodes),
+                                       "nodes": int(root.childrenAsRoot), "best_sequence_states": len(seq),
+                                       "api": "KartMCTS.constructSearchTree + getBestStatesSequence (Python mirror of the C# API over the C-ABI)"}
+        except Exception as exc:                         # reported, never fatal to the bench line
+            mcts_obj["tree_search"] = {"error": repr(exc)[:200]}
         try:                                             # the rollouts are bound by the SM issue rate, not by DRAM
             with open(os.path.join(ROOT, "profiles", "mcts_issue.json")) as f:
                 wi = float(json.load(f)["warp_instr_per_rollout"])
@@ -425,6 +440,28 @@ def main():
                                f"({sum(t.numel() for t in d4) * 8 / 1e9:.1f} GB of operands per launch, u0 + status out)"}
         del d4, u4, s4
         torch.cuda.empty_cache()
+        # the same game through the host-pointer entry: provider constructor arguments (1,280 B per problem) from pinned memory,
+        # A,B,Q,q,R assembled on the GPU (10.5 KB dense records stay in HBM), u0 + status back — PCIe-bound
+        p4 = S.make_problems(S.COMPLEX, uniq, 4, seed=20260002 + rank)
+        c4 = [torch.from_numpy(np.ascontiguousarray(p4[k], dtype=np.float64)).pin_memory() for k in ckeys]
+        c4n = [t.numpy() for t in c4]
+        u4h = torch.empty((uniq, 8), dtype=torch.float64).pin_memory().numpy()
+        s4h = torch.empty((uniq,), dtype=torch.int32).pin_memory().numpy()
+
+        def step4_e2e():
+            abi.check(lib.hk_lqng_assemble_solve_batch(uniq, 4, HORIZON, float(p4["dt"]), *[abi.dptr(a) for a in c4n], abi.dptr(u4h), abi.iptr(s4h)))
+        for _ in range(3):
+            step4_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            step4_e2e()
+        el4 = max_over_ranks(time.perf_counter() - t0)
+        lqng4_obj["e2e"] = {"value": world * uniq * 10 / el4, "unit": "solves/s", "ms_per_step": 1e2 * el4, "batch_per_gpu": uniq,
+                            "h2d_bytes_per_step": int(sum(a.nbytes for a in c4n)), "d2h_bytes_per_step": int(u4h.nbytes + s4h.nbytes),
+                            "status_nonzero": int((s4h != 0).sum()),
+                            "api": "hk_lqng_assemble_solve_batch, 4 players: pinned provider constructor arguments in, u0 + status out"}
+        del c4
 
     # ---- closed loop without PhysX (BASELINE config 5: 16,384 2-kart Oval races; Fixed high level, LQNG every step) -----------
     race_obj = None
