@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
     // warps exit (its ramp-up overlaps this launch's tail).  Such a dependent reads only its own inputs before
     // griddepcontrol.wait, which it executes before its first global store (see below) — by then this grid has completed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (FULL) asm volatile("griddepcontrol.wait;" ::: "memory");     // gains are stored from inside the recursion
+    bool waited = false;                                            // FULL: gains are stored from inside the recursion — wait before the first one
     if (first >= p.batch) { asm volatile("griddepcontrol.wait;" ::: "memory"); finish(); return; }   // whole warps only; no block-wide sync below
 
     const unsigned stage_u32 = smem_u32(&sm.stage[wib][0][0]);
@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             mm(pe, po, m0, m1, y0, y1);
             const double pc = podd ? po : pe;                       // compact P: P[t][g]
             if (FULL) {                                             // P_step [4][8] (one coalesced 256-byte store), alpha_step [4]
+                if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }   // warp-uniform
                 if (p.P) p.P[((size_t)prob * (p.horizon + 1) + step) * 32 + t * 8 + g] = pc;
                 if (p.alpha && g == 0 && !(t & 1)) {
                     double* a = p.alpha + ((size_t)prob * (p.horizon + 1) + step) * 4 + t;
