@@ -34,11 +34,13 @@ constexpr unsigned P2_TX_BYTES = 1664;
 constexpr int C2_ox = 0, C2_otg = 8, C2_otw = 16, C2_ocw = 24, C2_oaw = 26, C2_oot = 30, C2_oow = 38, C2_ocs = 44, C2_STRIDE = 48;
 constexpr unsigned C2_TX_BYTES = 384;
 
-template <int WARPS>
+constexpr int P2_ROLL_STEPS = 8;                // FULL mode keeps the gains of up to 8 steps in shared memory for its rollout
+
+template <int WARPS, int ROLL>
 struct P2Smem {
     double rec[WARPS][2][P2_STRIDE];
     double stage[WARPS][2][C2_STRIDE];           // compact mode only
-    double roll[WARPS][16];                      // FULL mode: state (8) and controls (4) of the closed-loop rollout
+    double roll[WARPS][ROLL];                    // FULL mode: state (8), controls (4) of the rollout; P_t (32) + alpha_t (4) per step
     double fallback[GenericLayout<2>::total];    // one pivoting scratch per CTA, serialised by `lock` (rare path)
     unsigned long long bar[WARPS][2];
     int lock;
@@ -81,7 +83,7 @@ __device__ __forceinline__ bool bits_differ(double a, double b)
 template <int MINB, int WARPS, bool COMPACT = false, bool FULL = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams p)
 {
-    __shared__ __align__(128) P2Smem<WARPS> sm;
+    __shared__ __align__(128) P2Smem<WARPS, FULL ? 16 + 36 * P2_ROLL_STEPS : 1> sm;
     const int lane = threadIdx.x & 31, wib = WARPS == 1 ? 0 : threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const long long nwarps = (long long)gridDim.x * WARPS;
@@ -365,6 +367,10 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             const double pc = podd ? po : pe;                       // compact P: P[t][g]
             if (FULL) {                                             // P_step [4][8] (one coalesced 256-byte store), alpha_step [4]
                 if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }   // warp-uniform
+                if (p.horizon < P2_ROLL_STEPS) {                    // the rollout below reads the gains from here
+                    sm.roll[wib][16 + step * 36 + t * 8 + g] = pc;
+                    if (g == 0 && !(t & 1)) { sm.roll[wib][16 + step * 36 + 32 + t] = ae; sm.roll[wib][16 + step * 36 + 33 + t] = ao; }
+                }
                 if (p.P) p.P[((size_t)prob * (p.horizon + 1) + step) * 32 + t * 8 + g] = pc;
                 if (p.alpha && g == 0 && !(t & 1)) {
                     double* a = p.alpha + ((size_t)prob * (p.horizon + 1) + step) * 4 + t;
@@ -424,9 +430,12 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             __syncwarp();
             if (lane == 0) { __threadfence_block(); atomicExch(&sm.lock, 0); }
         } else if (FULL) {
-            // u_t = -P_t x_t - alpha_t, x_{t+1} = A x_t + B u_t in forward time order (t = 0 is the pair computed last); the gains
-            // are re-read from the output buffers this warp has just written (the launcher lends scratch when the caller keeps none)
+            // u_t = -P_t x_t - alpha_t, x_{t+1} = A x_t + B u_t in forward time order (t = 0 is the pair computed last); gains from the
+            // warp's shared-memory copy (up to 8 steps), else re-read from the output buffers this warp has just written (the launcher
+            // lends scratch when the caller keeps none)
             const int T = p.horizon + 1;
+            const bool sg = T <= P2_ROLL_STEPS;
+            const double* gs = &sm.roll[wib][16];
             const double* gP = p.P + (size_t)prob * T * 32;
             const double* ga = p.alpha + (size_t)prob * T * 4;
             double* gt = p.traj ? p.traj + (size_t)prob * (T + 1) * 8 : nullptr;
@@ -435,11 +444,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             if (lane < 8) { const double v = rec[P2_ox + lane]; xs[lane] = v; if (gt) gt[lane] = v; }
             __syncwarp();
             for (int st = 0; st < (gt ? T : 1); ++st) {
-                double sacc = gP[st * 32 + t * 8 + g] * xs[g];
+                double sacc = (sg ? gs[st * 36 + t * 8 + g] : gP[st * 32 + t * 8 + g]) * xs[g];
                 sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
                 sacc += __shfl_xor_sync(0xffffffffu, sacc, 8);
                 sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
-                const double u = -sacc - ga[st * 4 + t];
+                const double u = -sacc - (sg ? gs[st * 36 + 32 + t] : ga[st * 4 + t]);
                 if (g == 0) { us[t] = u; if (st == 0) p.u0[(size_t)prob * 4 + t] = u; }
                 if (!gt) break;
                 __syncwarp();

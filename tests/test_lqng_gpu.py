@@ -139,6 +139,13 @@ def test_full_outputs_of_the_throughput_kernel(hk, oracle):
     for k in ("u0", "P", "alpha", "traj"):
         for b in np.nonzero(ok)[0]:
             assert rel_err(got[k][b], ref[k][b]) <= TOL, (k, b, kind[b])
+    # more than 8 steps: the rollout re-reads its gains from the output buffers instead of the warp's shared-memory copy
+    ref9 = oracle.lqng_solve_batch(A[:40], B[:40], Q[:40], q[:40], R[:40], x0[:40], 9)
+    got9 = lqr.solve_batch(A[:40], B[:40], Q[:40], q[:40], R[:40], x0[:40], 9)
+    assert np.array_equal(got9["status"], ref9["status"])
+    for k in ("u0", "P", "alpha", "traj"):
+        for b in np.nonzero(ref9["status"] == 0)[0]:
+            assert rel_err(got9[k][b], ref9[k][b]) <= TOL, (k, b)
     # subsets of the optional outputs through the device-pointer entry (the launcher lends scratch for what the rollout re-reads)
     import torch
     from hierarchicalkarting_b200 import abi
