@@ -367,7 +367,7 @@ __global__ void lqng_assemble_kernel(int batch, int N, double dt, const double* 
 
 // Persistent TMA-staged 2-kart kernel (hk_lqng_mma2p.cuh): dense records (p.A .. p.x0) or, with `compact`, the description of
 // hk_lqng_assemble_solve_batch (p.c_*), assembled by the warp in shared memory.
-static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact, bool full = false)
+static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact, bool full = false, bool tv = false)
 {
     const int batch = p.batch;
     static const int variant_env = getenv("HK_MMA2_VARIANT") ? atoi(getenv("HK_MMA2_VARIANT")) : 2;
@@ -375,10 +375,12 @@ static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact, bool fu
     // variant 1: 4 warps per CTA, MINB resident CTAs per SM; variant 2 (default): one warp per CTA, MINB resident warps
     // per SM.  16 warps x 128 registers is the measured optimum (profiles/lqng_mma2_tuning_r01.md).
     static const int minb = getenv("HK_MMA2_MINB") ? atoi(getenv("HK_MMA2_MINB")) : (variant == 2 ? 16 : 4);
-    const int warps = (compact || full || variant == 2) ? 1 : 4;
+    const int warps = (compact || full || tv || variant == 2) ? 1 : 4;
     void (*kern)(LqngParams) = nullptr;
     if (compact) {
         kern = lqng_mma2p_kernel<16, 1, true>;
+    } else if (tv) {
+        kern = full ? lqng_mma2p_kernel<12, 1, false, true, true> : lqng_mma2p_kernel<12, 1, false, false, true>;   // shared memory allows ~11 warps per SM at horizon 3
     } else if (full) {
         kern = lqng_mma2p_kernel<16, 1, false, true>;
     } else if (variant == 2) {
@@ -388,14 +390,17 @@ static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact, bool fu
         kern = minb >= 8 ? lqng_mma2p_kernel<8, 4> : minb >= 6 ? lqng_mma2p_kernel<6, 4> : minb == 5 ? lqng_mma2p_kernel<5, 4>
                : lqng_mma2p_kernel<4, 4>;
     }
-    static int resident_of[3] = {0, 0, 0};                     // persistent grid: SMs x resident CTAs (dense, compact, full)
-    int& resident = resident_of[compact ? 1 : full ? 2 : 0];
-    static const int pad = getenv("HK_MMA2_PAD_SMEM") ? atoi(getenv("HK_MMA2_PAD_SMEM")) : 0;   // occupancy experiments only
+    // persistent grid: SMs x resident CTAs (dense, compact, full; time-varying per number of stages and output form)
+    static int resident_of[3 + 2 * 8] = {};
+    int& resident = resident_of[tv ? 3 + 2 * p.horizon + (full ? 1 : 0) : compact ? 1 : full ? 2 : 0];
+    static const int pad_env = getenv("HK_MMA2_PAD_SMEM") ? atoi(getenv("HK_MMA2_PAD_SMEM")) : 0;   // occupancy experiments only
+    // time-varying: the whole horizon of a problem is staged, double-buffered: 2 x (horizon + 1) records of 1,728 B per warp
+    const int pad = tv ? 2 * (p.horizon + 1) * P2_STRIDE * (int)sizeof(double) : pad_env;
     if (!resident) {
         int dev = 0, sms = 0, occ = 0;
         HK_CUDA(cudaGetDevice(&dev));
         HK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        if (pad) HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+        if (pad) HK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pad > 48 * 1024 ? pad : 48 * 1024));
         HK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * warps, pad));
         resident = sms * (occ > 0 ? occ : 1);
     }
@@ -487,6 +492,14 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
     LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr, nullptr,
                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0};
     static const bool force_generic = getenv("HK_LQNG_FORCE_GENERIC") != nullptr;
+    static const bool tv2 = !(getenv("HK_MMA2_TV") && atoi(getenv("HK_MMA2_TV")) == 0);
+    if (N == 2 && time_varying && horizon <= 7 && !force_generic && tv2 &&
+        ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dQ) |
+          reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dR) | reinterpret_cast<uintptr_t>(dx0)) & 15) == 0) {
+        // time-varying operands: the same persistent DMMA kernel with the whole horizon of a problem staged by TMA
+        const bool full = dP || dalpha || dtraj;
+        return launch_mma2p(p, stream, false, full, true);
+    }
     static const bool full2 = !(getenv("HK_MMA2_FULL") && atoi(getenv("HK_MMA2_FULL")) == 0);
     if (N == 2 && !time_varying && (dP || dalpha || dtraj) && !force_generic && full2 &&
         ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dQ) |

@@ -36,9 +36,9 @@ constexpr unsigned C2_TX_BYTES = 384;
 
 constexpr int P2_ROLL_STEPS = 8;                // FULL mode keeps the gains of up to 8 steps in shared memory for its rollout
 
-template <int WARPS, int ROLL>
+template <int WARPS, int ROLL, int RECS>
 struct P2Smem {
-    double rec[WARPS][2][P2_STRIDE];
+    double rec[WARPS][2][RECS];                  // TV mode keeps its records (one per stage) in dynamic shared memory instead
     double stage[WARPS][2][C2_STRIDE];           // compact mode only
     double roll[WARPS][ROLL];                    // FULL mode: state (8), controls (4) of the rollout; P_t (32) + alpha_t (4) per step
     double fallback[GenericLayout<2>::total];    // one pivoting scratch per CTA, serialised by `lock` (rare path)
@@ -80,18 +80,25 @@ __device__ __forceinline__ bool bits_differ(double a, double b)
 // FULL: every output of the ABI — gains P_t, offsets alpha_t of every step (the reference computes them and keeps only t = 0,
 // KartLQR.cs:104-105, 121-126), u0 = -P_0 x0 - alpha_0 of every player, and the closed-loop rollout.  The last
 // backward step is then a full step (no u0 shortcut), gains go to global memory as they are produced and the rollout re-reads them.
-template <int MINB, int WARPS, bool COMPACT = false, bool FULL = false>
+// TV: time-varying operands A_t, B_t, Q_t, q_t, R_t (the reference's providers are constant over the horizon).  The
+// whole horizon of a problem is staged by TMA — stage t as one record of the time-invariant layout at rec + t * P2_STRIDE, x0 with
+// stage 0 — double-buffered across problems in dynamic shared memory; every per-lane offset then applies to the stage's record.
+template <int MINB, int WARPS, bool COMPACT = false, bool FULL = false, bool TV = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams p)
 {
-    __shared__ __align__(128) P2Smem<WARPS, FULL ? 16 + 36 * P2_ROLL_STEPS : 1> sm;
+    static_assert(!TV || (WARPS == 1 && !COMPACT), "TV: one warp per CTA, dense records");
+    __shared__ __align__(128) P2Smem<WARPS, FULL ? 16 + 36 * P2_ROLL_STEPS : 1, TV ? 2 : P2_STRIDE> sm;
+    extern __shared__ __align__(128) double tv_rec[];               // TV: [2][T][P2_STRIDE]
+    const int TS = TV ? p.horizon + 1 : 1;                          // stages per record
     const int lane = threadIdx.x & 31, wib = WARPS == 1 ? 0 : threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const long long nwarps = (long long)gridDim.x * WARPS;
     const long long first = (long long)wib * gridDim.x + blockIdx.x;      // leftovers of the last round spread over all SMs
     const unsigned bar_u32 = smem_u32(&sm.bar[wib][0]);
-    const unsigned rec_u32 = smem_u32(&sm.rec[wib][0][0]);
+    double* const rec_base = TV ? tv_rec : &sm.rec[wib][0][0];
+    const unsigned rec_u32 = smem_u32(rec_base);
     if (threadIdx.x == 0) sm.lock = 0;
-    if (lane < 16) sm.rec[wib][lane >> 3][P2_oC + (lane & 7)] = ((lane & 7) == 5 || (lane & 7) == 6) ? 1.0 : 0.0;
+    for (int i = lane; i < 16 * TS; i += 32) rec_base[(i >> 3) * P2_STRIDE + P2_oC + (i & 7)] = ((i & 7) == 5 || (i & 7) == 6) ? 1.0 : 0.0;
     if (lane == 0) {
         mbar_init(bar_u32, 1);
         mbar_init(bar_u32 + 8, 1);
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
 
     const unsigned stage_u32 = smem_u32(&sm.stage[wib][0][0]);
     auto issue = [&](long long prob, int b) {                         // lane 0 only
-        const unsigned bar = bar_u32 + 8u * b, dst = rec_u32 + (unsigned)(b * P2_STRIDE * 8);
+        const unsigned bar = bar_u32 + 8u * b, dst = rec_u32 + (unsigned)(b * TS * P2_STRIDE * 8);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of this buffer come first
         if (COMPACT) {
             const unsigned sd = stage_u32 + (unsigned)(b * C2_STRIDE * 8);
@@ -133,6 +140,20 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             bulk_g2s(sd + C2_oot * 8, p.c_otgt + (size_t)prob * 8, 64, bar);
             bulk_g2s(sd + C2_oow * 8, p.c_otw + (size_t)prob * 6, 48, bar);
             bulk_g2s(sd + C2_ocs * 8, p.c_cs + (size_t)prob * 4, 32, bar);
+            return;
+        }
+        if (TV) {
+            mbar_expect_tx(bar, (unsigned)TS * 1600u + 64u);
+            for (int st = 0; st < TS; ++st) {
+                const unsigned d = dst + (unsigned)(st * P2_STRIDE * 8);
+                const size_t ps = (size_t)prob * TS + st;
+                bulk_g2s(d + P2_oQ * 8, p.Q + ps * 128, 1024, bar);
+                bulk_g2s(d + P2_oA * 8, p.A + ps * 32, 256, bar);
+                bulk_g2s(d + P2_oB * 8, p.B + ps * 16, 128, bar);
+                bulk_g2s(d + P2_oq * 8, p.q + ps * 16, 128, bar);
+                bulk_g2s(d + P2_oR * 8, p.R + ps * 8, 64, bar);
+            }
+            bulk_g2s(dst + P2_ox * 8, p.x0 + (size_t)prob * 8, 64, bar);
             return;
         }
         mbar_expect_tx(bar, P2_TX_BYTES);
@@ -183,7 +204,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
     long long nxt = dynamic ? fetch() : first + nwarps;
     for (long long prob = first; prob < p.batch; ++it) {
         const int buf = it & 1;
-        const double* rec = &sm.rec[wib][COMPACT ? 0 : buf][0];
+        const double* rec = TV ? rec_base + (size_t)buf * TS * P2_STRIDE : &sm.rec[wib][COMPACT ? 0 : buf][0];   // TV: stage t at + t * P2_STRIDE
         __syncwarp();                                               // every lane is done with the other buffer
         if (lane == 0 && nxt < p.batch) issue(nxt, buf ^ 1);
         // The problem after the next: fetched now, needed at the end.  Inline PTX on purpose: nvcc turns a predicated atomicAdd() into
@@ -239,35 +260,44 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
         bool pivot = false, hard = false;
         double u_out = 0.0;
         for (;;) {                                                  // pass 0: no row exchanges; pass 1 (rare): partial pivoting
-        // ---- operands of this problem -----------------------------------------------------------------------------------
-        const double aT0 = rec[offA], aT1 = rec[offA + 4];
-        const double xb00 = rec[offXb0], xb01 = rec[offXb0 + 2], xb10 = rec[offXb1], xb11 = rec[offXb1 + 2];
-        const double2 bFa = *reinterpret_cast<const double2*>(rec + offBF), bFb = *reinterpret_cast<const double2*>(rec + offBF + 2);
-        const double2 rr = *reinterpret_cast<const double2*>(rec + offRr);
-        const double2 rl = *reinterpret_cast<const double2*>(rec + offRl);
-        double yL0, yL1;                                            // [B | A x0 | 0 0 0] in T-form
-        {
-            const double2 a0 = *reinterpret_cast<const double2*>(rec + offAx), a1 = *reinterpret_cast<const double2*>(rec + offAx + 2);
-            const double2 a2 = *reinterpret_cast<const double2*>(rec + offAx + 4), a3 = *reinterpret_cast<const double2*>(rec + offAx + 6);
-            const double2 xa = *reinterpret_cast<const double2*>(rec + P2_ox + 4 * pl), xc = *reinterpret_cast<const double2*>(rec + P2_ox + 4 * pl + 2);
-            const double ax0 = fma(a1.y, xc.y, fma(a1.x, xc.x, fma(a0.y, xa.y, a0.x * xa.x)));
-            const double ax1 = fma(a3.y, xc.y, fma(a3.x, xc.x, fma(a2.y, xa.y, a2.x * xa.x)));
-            yL0 = g == 4 ? ax0 : rec[offB];
-            yL1 = g == 4 ? ax1 : rec[offB + 2];
-        }
+        // ---- operands of this problem (TV: of the current stage, reloaded every step) --------------------------------------------
+        double aT0, aT1, xb00, xb01, xb10, xb11, yL0, yL1;          // yL: [B | A x0 | 0 0 0] in T-form
+        double2 bFa, bFb, rr, rl;
+        auto load_xb = [&](const double* r) { xb00 = r[offXb0]; xb01 = r[offXb0 + 2]; xb10 = r[offXb1]; xb11 = r[offXb1 + 2]; };
+        auto load_ops = [&](const double* r, bool with_ax) {        // with_ax: A x0 rides in column 4 of the L product (needed at t = 0)
+            aT0 = r[offA]; aT1 = r[offA + 4];
+            load_xb(r);
+            bFa = *reinterpret_cast<const double2*>(r + offBF); bFb = *reinterpret_cast<const double2*>(r + offBF + 2);
+            rr = *reinterpret_cast<const double2*>(r + offRr);
+            rl = *reinterpret_cast<const double2*>(r + offRl);
+            double ax0 = 0.0, ax1 = 0.0;
+            if (with_ax) {
+                const double2 a0 = *reinterpret_cast<const double2*>(r + offAx), a1 = *reinterpret_cast<const double2*>(r + offAx + 2);
+                const double2 a2 = *reinterpret_cast<const double2*>(r + offAx + 4), a3 = *reinterpret_cast<const double2*>(r + offAx + 6);
+                const double2 xa = *reinterpret_cast<const double2*>(r + P2_ox + 4 * pl), xc = *reinterpret_cast<const double2*>(r + P2_ox + 4 * pl + 2);
+                ax0 = fma(a1.y, xc.y, fma(a1.x, xc.x, fma(a0.y, xa.y, a0.x * xa.x)));
+                ax1 = fma(a3.y, xc.y, fma(a3.x, xc.x, fma(a2.y, xa.y, a2.x * xa.x)));
+            }
+            yL0 = g == 4 ? ax0 : r[offB];
+            yL1 = g == 4 ? ax1 : r[offB + 2];
+        };
+        // symmetry of Q_i and R_i is what lets Z_i's R-form stand in for its T-form
+        auto asym = [&](const double* r, const double2& q0, const double2& q1) -> bool {
+            return bits_differ(r[(2 * t) * 8 + g], q0.x) | bits_differ(r[(2 * t + 1) * 8 + g], q0.y) |
+                   bits_differ(r[64 + (2 * t) * 8 + g], q1.x) | bits_differ(r[64 + (2 * t + 1) * 8 + g], q1.y) |
+                   bits_differ(r[P2_oR + 1], r[P2_oR + 2]) | bits_differ(r[P2_oR + 5], r[P2_oR + 6]);
+        };
+        const double* rs = rec + (TV ? (size_t)p.horizon * P2_STRIDE : 0);      // record of the stage being processed
+        load_ops(rs, !TV || p.horizon == 0);
         double z00, z01, z10, z11, e0, e1;
         bool redo, redo_piv = false;                                // redo: the shared-memory algorithm must take this problem
         {
-            const double2 q0 = *reinterpret_cast<const double2*>(rec + P2_oQ + 2 * lane);          // Z_i = Q_i (KartLQR.cs:62), R-form
-            const double2 q1 = *reinterpret_cast<const double2*>(rec + P2_oQ + 64 + 2 * lane);
-            const double2 qv = *reinterpret_cast<const double2*>(rec + offQv);                      // eta_i = q_i (:63), lanes (4+i, t)
+            const double2 q0 = *reinterpret_cast<const double2*>(rs + P2_oQ + 2 * lane);           // Z_i = Q_i (KartLQR.cs:62), R-form
+            const double2 q1 = *reinterpret_cast<const double2*>(rs + P2_oQ + 64 + 2 * lane);
+            const double2 qv = *reinterpret_cast<const double2*>(rs + offQv);                       // eta_i = q_i (:63), lanes (4+i, t)
             z00 = q0.x; z01 = q0.y; z10 = q1.x; z11 = q1.y; e0 = qv.x; e1 = qv.y;
-            // symmetry of Q_i and R_i is what lets Z_i's R-form stand in for its T-form
             redo = false;                                           // assembled Q_i, R_i are symmetric by construction
-            if (!COMPACT)
-                redo = bits_differ(rec[(2 * t) * 8 + g], q0.x) | bits_differ(rec[(2 * t + 1) * 8 + g], q0.y) |
-                       bits_differ(rec[64 + (2 * t) * 8 + g], q1.x) | bits_differ(rec[64 + (2 * t + 1) * 8 + g], q1.y) |
-                       bits_differ(rec[P2_oR + 1], rec[P2_oR + 2]) | bits_differ(rec[P2_oR + 5], rec[P2_oR + 6]);
+            if (!COMPACT) redo = asym(rs, q0, q1);
         }
         // W: rows 0..3 = stacked B_i^T Z_i, rows 4+i = eta_i (+ Z_i beta from the second step on)
         double w0 = e0, w1 = e1;
@@ -276,6 +306,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
 
         for (int step = p.horizon; step >= 0; --step) {             // KartLQR.cs:64
             const bool last = step == 0;
+            if (TV && step != p.horizon) { rs = rec + (size_t)step * P2_STRIDE; load_ops(rs, last); }
             // L = W [B | A x0] with eta^T B in rows 4, 5 (RHSVec, :96), + R_i on the diagonal blocks (:78), identity in rows 6, 7
             double l0 = rl.x, l1 = rl.y;
             mm(l0, l1, g < 4 ? w0 : e0, g < 4 ? w1 : e1, yL0, yL1);
@@ -389,8 +420,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
                 double ya0 = 0.0, ya1 = 0.0, yb0 = 0.0, yb1 = 0.0;
                 mm(ya0, ya1, f0, f1, z00, z01);
                 mm(yb0, yb1, f0, f1, z10, z11);
-                const double2 q0 = *reinterpret_cast<const double2*>(rec + P2_oQ + 2 * lane);
-                const double2 q1 = *reinterpret_cast<const double2*>(rec + P2_oQ + 64 + 2 * lane);
+                const double2 q0 = *reinterpret_cast<const double2*>(rs + P2_oQ + 2 * lane);
+                const double2 q1 = *reinterpret_cast<const double2*>(rs + P2_oQ + 64 + 2 * lane);
+                if (TV && step != p.horizon) redo |= asym(rs, q0, q1);
                 z00 = q0.x; z01 = q0.y; z10 = q1.x; z11 = q1.y;
                 dmma(z00, z01, pl == 0 ? pc : 0.0, rpc);
                 dmma(z10, z11, pl == 1 ? pc : 0.0, rpc);
@@ -398,13 +430,14 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
                 mm(z10, z11, f0, f1, yb0, yb1);
             }
             // W for the next step, beta^T in row 4+i: row 4+i comes out as eta_i + Z_i^{new} beta (quirk Q2)
+            const double ra = fma(rr.y, ao, rr.x * ae);             // (R_i alpha_i)[t&1], this step's R_i
+            if (TV) load_xb(rec + (size_t)(step - 1) * P2_STRIDE);  // rows 0..3 of W are B_i^T Z_i with the NEXT step's B_i
             w0 = e0; w1 = e1;
             mm(w0, w1, g == 4 ? be0 : xb00, g == 4 ? be1 : xb01, z00, z01);
             mm(w0, w1, g == 5 ? be0 : xb10, g == 5 ? be1 : xb11, z10, z11);
             // eta_i <- q_i + P_i^T R_i alpha_i + F^T (eta_i + Z_i^{new} beta)   (:117)
             {
-                const double ra = fma(rr.y, ao, rr.x * ae);         // (R_i alpha_i)[t&1]
-                const double2 qv = *reinterpret_cast<const double2*>(rec + offQv);
+                const double2 qv = *reinterpret_cast<const double2*>(rs + offQv);
                 double n0 = qv.x, n1 = qv.y;
                 dmma(n0, n1, (vec && pl == vp) ? ra : 0.0, pc);
                 mm(n0, n1, vec ? w0 : 0.0, vec ? w1 : 0.0, f0, f1);
@@ -456,9 +489,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
                 if (lane < 8) {
                     const int pr = lane >> 2, rr_ = lane & 3;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) xn = fma(rec[P2_oA + pr * 16 + rr_ * 4 + c], xs[4 * pr + c], xn);
+                    const double* rt = rec + (TV ? (size_t)st * P2_STRIDE : 0);
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) xn = fma(rec[P2_oB + pr * 8 + rr_ * 2 + c], us[2 * pr + c], xn);
+                    for (int c = 0; c < 4; ++c) xn = fma(rt[P2_oA + pr * 16 + rr_ * 4 + c], xs[4 * pr + c], xn);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) xn = fma(rt[P2_oB + pr * 8 + rr_ * 2 + c], us[2 * pr + c], xn);
                 }
                 __syncwarp();
                 if (lane < 8) { xs[lane] = xn; gt[(size_t)(st + 1) * 8 + lane] = xn; }

@@ -45,6 +45,20 @@ def test_parity_time_varying(hk, oracle, N):
     ref = oracle.lqng_solve_batch(At, Bt, Qt, qt, Rt, x0, horizon, time_varying=True)
     got = lqr.solve_batch(At, Bt, Qt, qt, Rt, x0, horizon, time_varying=True)
     _check(got, ref)
+    got_u = lqr.solve_batch(At, Bt, Qt, qt, Rt, x0, horizon, time_varying=True, full=False)     # u0 only
+    _check(got_u, ref, full=False)
+    # stages that break the fast path of the 2-kart DMMA kernel (whole horizon staged by TMA): a non-symmetric Q_t at an inner
+    # stage (shared-memory fallback inside the kernel), an R_t that forces row exchanges at one stage (pivot pass)
+    for b in range(0, batch, 5):
+        Qt[b, 1, 0] += 0.05 * rng.standard_normal((n, n))
+    for b in range(1, batch, 5):
+        c = 0.2 + 0.1 * rng.random()
+        Rt[b, 2, :] = np.array([[0.05 * c, c], [c, 0.03 * c]])
+    ref = oracle.lqng_solve_batch(At, Bt, Qt, qt, Rt, x0, horizon, time_varying=True)
+    got = lqr.solve_batch(At, Bt, Qt, qt, Rt, x0, horizon, time_varying=True)
+    _check(got, ref)
+    got_u = lqr.solve_batch(At, Bt, Qt, qt, Rt, x0, horizon, time_varying=True, full=False)
+    _check(got_u, ref, full=False)
 
 
 def test_general_dense_blocks_and_nonsymmetric_q(hk, oracle):

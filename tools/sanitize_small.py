@@ -11,6 +11,14 @@ for N, track in ((1, S.OVAL), (2, S.OVAL), (3, S.COMPLEX), (4, S.COMPLEX)):
     for full in (False, True):
         out = lqr.solve_batch(A, B, Q, q, R, x0, 3, full=full)
         assert np.all(np.isfinite(out["u0"]))
+# time-varying operands (2-kart: whole horizon staged by TMA; 3/4-kart: DMMA kernel; 1-kart: general kernel)
+rng = np.random.default_rng(1)
+for N, track in ((1, S.OVAL), (2, S.OVAL), (3, S.COMPLEX), (4, S.COMPLEX)):
+    A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(track, 70, N, seed=5))
+    tv = lambda a, s_: np.ascontiguousarray(np.repeat(a[:, None], 4, axis=1) * (1.0 + s_ * rng.standard_normal((70, 4) + (1,) * (a.ndim - 1))))
+    for full in (False, True):
+        out = lqr.solve_batch(tv(A, 0.01), tv(B, 0.05), tv(Q, 0.05), tv(q, 0.05), tv(R, 0.05), x0, 3, time_varying=True, full=full)
+        assert np.all(np.isfinite(out["u0"]))
 prob = S.make_problems(S.OVAL, 20000, 2, seed=4)
 keys = ("x0", "target", "tw", "cw", "aw", "otgt", "otw")
 arrs = [np.ascontiguousarray(prob[k], dtype=np.float64) for k in keys]
