@@ -403,7 +403,35 @@ def main():
                 "ms_per_step": full_ms, "outputs": "u0 of every player, P_t [T][4][8], alpha_t [T][4], trajectory [T+1][8], status",
                 "hbm_bytes_per_solve": 1664 + out_bytes, "status_nonzero": int(st_d.sum().item()),
                 "kernel": "lqng_mma2p_kernel<16, 1, false, true> (FULL mode of the persistent DMMA kernel)"}
-    del P_d, al_d, tr_d
+    # time-varying operands (A_t, B_t, Q_t, q_t, R_t per stage: 6.5 KB per problem), u0 out — the TMA-staged whole-horizon mode
+    rng_tv = np.random.default_rng(20260005 + rank)
+    tvh = [np.ascontiguousarray(np.repeat(a[:, None], T, axis=1) * (1.0 + sc * rng_tv.standard_normal((batch, T) + (1,) * (a.ndim - 1))))
+           for a, sc in zip(host[:5], (0.01, 0.05, 0.05, 0.05, 0.05))]
+    tvd = [torch.from_numpy(a).to(dev) for a in tvh] + [sets[0][5]]
+    del tvh
+
+    def step_tv(with_outputs):
+        abi.check(lib.hk_lqng_solve_batch_device(batch, N, HORIZON, 1, *[t.data_ptr() for t in tvd], u0_d.data_ptr(),
+                                                 P_d.data_ptr() if with_outputs else None, al_d.data_ptr() if with_outputs else None,
+                                                 tr_d.data_ptr() if with_outputs else None, st_d.data_ptr(), stream.cuda_stream))
+    tv_ms = {}
+    for with_outputs in (False, True):
+        for _ in range(args.warmup):
+            step_tv(with_outputs)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        for _ in range(args.steps):
+            step_tv(with_outputs)
+        h1.record(stream)
+        h1.synchronize()
+        tv_ms[with_outputs] = max_over_ranks(h0.elapsed_time(h1)) / args.steps
+    tv_obj = {"metric": "lqng_time_varying_solves_per_s", "value": world * batch / (tv_ms[False] * 1e-3), "unit": "solves/s",
+              "ms_per_step": tv_ms[False], "with_all_outputs": {"value": world * batch / (tv_ms[True] * 1e-3), "ms_per_step": tv_ms[True]},
+              "hbm_bytes_per_solve": T * 1600 + 64 + 36, "status_nonzero": int(st_d.sum().item()),
+              "note": "the same 65,536 problems with every stage's operands perturbed (one input set of 428 MB > 126 MB L2)",
+              "kernel": "lqng_mma2p_kernel<12, 1, false, *, true> (TV mode: whole horizon staged by TMA)"}
+    del P_d, al_d, tr_d, tvd
 
     # ---- 4-kart LQNG (BASELINE config 3: 1,048,576 Complex 2v2 problems per GPU, HBM-resident) --------------------------------
     lqng4_obj = None
@@ -539,6 +567,7 @@ def main():
     if race_obj:
         line["race"] = race_obj
     line["full_outputs"] = full_obj
+    line["time_varying"] = tv_obj
     if lqng4_obj:
         line["lqng4"] = lqng4_obj
     if world == 1 and not args.no_cpu_baseline:
