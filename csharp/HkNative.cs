@@ -64,6 +64,9 @@ namespace KartGame.AI.Native
         [DllImport(Lib)] public static extern int hk_mcts_rollouts_multi(IntPtr game, HkGameState[] leaves, int nLeaves, long rolloutsPerLeaf, ulong seed,
                                                                          ulong rolloutOffset, [Out] long[] visit, [Out] double[] rewardSum,
                                                                          [Out] long[] nanCount, [Out] long[] pliesSum);
+        // batched tree search (constructSearchTree + getBestStatesSequence, one thread block per root); bestStates [nRoots][16]
+        [DllImport(Lib)] public static extern int hk_mcts_search_batch(IntPtr game, HkGameState[] roots, int nRoots, int iterations, int rolloutsPerLeaf,
+            ulong seed, [Out] HkGameState[] bestStates, [Out] int[] nBest, [Out] int[] rootEpisodes, [Out] double[] rootValues, [Out] int[] nNodes);
 
         // headless batch races (kinematic plant instead of PhysX)
         [DllImport(Lib)] public static extern int hk_track_create(HkSection[] sections, double[] triggerXz, double[] forwardXz, double[] laneXz,

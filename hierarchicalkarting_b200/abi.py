@@ -16,6 +16,7 @@ HK_MAX_PLAYERS = 4
 HK_MAX_HORIZON = 31
 HK_MAX_KARTS = 4
 HK_MAX_ACTIONS = 36
+HK_MCTS_MAX_SEQ = 16
 HK_MAX_PLIES = 64
 HK_MAX_SECTIONS = 64
 HK_MAX_LAPS = 8
@@ -132,6 +133,7 @@ PROTOTYPES = {
     "hk_mcts_rollouts": (C.c_int, [C.c_void_p, C.POINTER(hk_game_state), C.c_int64, C.c_uint64, C.c_uint64, _lp, _dp, _lp, _lp]),
     "hk_mcts_rollouts_trace": (C.c_int, [C.c_void_p, C.POINTER(hk_game_state), C.c_int64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 5),
     "hk_mcts_rollouts_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 4),
+    "hk_mcts_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64] + [C.c_void_p] * 5),
     "hk_policy_cdf": (C.c_int, [C.c_int, _up]),
     "hk_track_create": (C.c_int, [C.POINTER(hk_section), _dp, _dp, _dp, C.c_int, C.POINTER(C.c_void_p)]),
     "hk_track_destroy": (None, [C.c_void_p]),

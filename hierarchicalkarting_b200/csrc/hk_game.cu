@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace hk {
 
@@ -575,6 +576,204 @@ __global__ void __launch_bounds__(128, 8) rollouts_kernel(const DevGame* __restr
     if (threadIdx.x == 0 && s_plies) atomicAdd(&plies_sum[leaf], (unsigned long long)s_plies);
 }
 
+// ---- batched tree search: KartMCTS.constructSearchTree + getBestStatesSequence on the device, one CTA per root ------------------
+// The GPU form of the reference's own leaf-parallel variant (processLeaf, KartMCTS.cs:124-159), exactly as the host mirrors run it
+// (hierarchicalkarting_b200/mcts.py, host/KartMCTS.hpp): every iteration walks the tree with upperConfidenceStrategy (:167-192;
+// UCT = total/n + ln(parent.n / n) with the integer division of :164) to a node without children (findLeaf :194-201), creates
+// ALL its children (generation order of nextMoves :329-340), plays R rollouts of simulate (:238-278) through each child and
+// backpropagates the summed terminal scores (:280-289: every ancestor adds the entry of its own upNext()).  A whole tree lives in
+// a per-root slab of global memory; thread 0 does the tree policy, all threads the child creation and the rollouts.  The random
+// initial pick of upperConfidenceStrategy (it only matters for exact ties) comes from a Philox counter, so that a host mirror
+// given the same stream reproduces the search.
+struct TreeNode {
+    hk_game_state st;
+    double total;                                        // totalValue
+    int episodes;                                        // numEpisodes
+    int parent, first_child, n_children, upnext, pad_;
+};
+
+__device__ __forceinline__ float uct_weight(const TreeNode& parent, const TreeNode& c)                  // KartMCTS.cs:162-165
+{
+    const int ratio = parent.episodes / c.episodes;      // integer division (quirk B.6-7); the caller has checked c.episodes != 0
+    const float lg = ratio > 0 ? (float)log((double)ratio) : -INFINITY;
+    return (float)c.total / (float)c.episodes + lg;
+}
+
+// upperConfidenceStrategy: index of the chosen child, or -1 when a child without episodes makes UCTWeight divide by zero
+// (DivideByZeroException: swallowed by getBestStatesSequence :120)
+__device__ int ucs_pick(const TreeNode* nodes, int node, unsigned long long key, unsigned& ctr)
+{
+    const TreeNode& p = nodes[node];
+    const int n = p.n_children, first = p.first_child;
+    int best = (int)(philox_first(key, (unsigned long long)ctr++, 0u) % (unsigned)n);
+    if (nodes[first + best].episodes == 0) return -1;
+    float best_w = uct_weight(p, nodes[first + best]);
+    for (int j = 0; j < n; ++j) {
+        if (nodes[first + j].episodes == 0) return -1;
+        const float w = uct_weight(p, nodes[first + j]);
+        if (w > best_w) { best_w = w; best = j; }
+    }
+    return best;
+}
+
+constexpr int TREE_THREADS = 128;
+
+__global__ void __launch_bounds__(TREE_THREADS) tree_search_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ roots,
+                                                                   int iterations, int R, unsigned long long seed, int max_nodes,
+                                                                   TreeNode* __restrict__ slabs, hk_game_state* __restrict__ best_out,
+                                                                   int* __restrict__ n_best_out, int* __restrict__ root_episodes,
+                                                                   double* __restrict__ root_values, int* __restrict__ n_nodes_out,
+                                                                   int* __restrict__ status_out)
+{
+    __shared__ DevGame g;
+    __shared__ unsigned long long s_keys[HK_MAX_ACTIONS];
+    __shared__ unsigned s_vis[HK_MAX_ACTIONS], s_nan[HK_MAX_ACTIONS];
+    __shared__ double s_rsum[HK_MAX_ACTIONS][HK_MAX_KARTS];
+    __shared__ int s_leaf, s_cnt, s_first, s_nnodes, s_stop, s_err;
+    {
+        const int* src = reinterpret_cast<const int*>(gg);
+        int* dst = reinterpret_cast<int*>(&g);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevGame) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    const int root = blockIdx.x;
+    TreeNode* nodes = slabs + (size_t)root * max_nodes;
+    const unsigned long long rseed = seed + (unsigned long long)root;           // rollouts of root r: Philox key seed + r
+    const unsigned long long ukey = rseed ^ 0x9E3779B97F4A7C15ull;               // stream of the tie-breaking picks
+    unsigned ctr = 0;                                                            // thread 0 only
+    if (threadIdx.x == 0) {
+        TreeNode& r = nodes[0];
+        r.st = roots[root]; r.total = 0.0; r.episodes = 0; r.parent = -1; r.first_child = -1; r.n_children = 0;
+        r.upnext = up_next(r.st);
+        s_nnodes = 1; s_stop = 0; s_err = 0;
+    }
+    __syncthreads();
+    for (int it = 0; it < iterations; ++it) {
+        if (threadIdx.x == 0) {
+            // findLeaf (:194-201): a node either has all its children or none (processLeaf creates them together)
+            int node = 0;
+            while (nodes[node].n_children > 0) {
+                const int j = ucs_pick(nodes, node, ukey, ctr);
+                if (j < 0) { s_err = 2; break; }
+                node = nodes[node].first_child + j;
+            }
+            s_leaf = node;
+            s_cnt = 0;
+            const TreeNode& lf = nodes[node];
+            if (s_err == 0) {
+                if (lf.upnext < 0) s_err = 1;                                    // ArgumentOutOfRangeException at KartDiscreteGame.cs:326
+                else {
+                    float scores[2 * HK_MAX_KARTS];
+                    int ns;
+                    const int cnt = legal_moves(g, lf.st, lf.upnext, s_keys);
+                    if (is_over(g, lf.st, cnt, lf.upnext, scores, ns)) {         // terminal leaf: simulate() returns at once (:246-249)
+                        for (int n = node; n >= 0; n = nodes[n].parent) {
+                            const int up = nodes[n].upnext;
+                            if (up >= 0 && up < ns) nodes[n].total += (double)scores[up];
+                            nodes[n].episodes += 1;
+                        }
+                    } else if (s_nnodes + cnt <= max_nodes) {
+                        s_cnt = cnt; s_first = s_nnodes;
+                    } else s_stop = 1;                                           // slab full: the search ends here
+                }
+            }
+        }
+        for (int i = threadIdx.x; i < HK_MAX_ACTIONS; i += blockDim.x) {
+            s_vis[i] = 0; s_nan[i] = 0;
+            for (int k = 0; k < HK_MAX_KARTS; ++k) s_rsum[i][k] = 0.0;
+        }
+        __syncthreads();
+        if (s_err || s_stop) break;
+        const int cnt = s_cnt, first = s_first, leaf = s_leaf;
+        if (cnt == 0) { __syncthreads(); continue; }                             // terminal leaf handled above (uniform); s_* are rewritten next
+        // children in generation order (initials[j] = new KartMCTSNode(node.state.makeMove(action), node), :142)
+        if (threadIdx.x < g.n_cand && s_keys[threadIdx.x] != ~0ull) {
+            int rank = 0;
+            for (int j = 0; j < (int)threadIdx.x; ++j) rank += s_keys[j] != ~0ull;
+            TreeNode& c = nodes[first + rank];
+            c.st = nodes[leaf].st;
+            make_move(g, c.st, nodes[leaf].upnext, action_of(g, threadIdx.x));
+            c.total = 0.0; c.episodes = 0; c.parent = leaf; c.first_child = -1; c.n_children = 0;
+            c.upnext = up_next(c.st);
+        }
+        __syncthreads();
+        // R rollouts through every child; rollout r of child j is rollout id it * R * HK_MAX_ACTIONS + j * R + r of key rseed
+        const unsigned long long offset = (unsigned long long)it * (unsigned long long)R * HK_MAX_ACTIONS;
+        for (int idx = threadIdx.x; idx < cnt * R; idx += blockDim.x) {
+            const int j = idx / R, r = idx - j * R;
+            float scores[2 * HK_MAX_KARTS];
+            int ns, first_gi;
+            const int plies = rollout<false>(g, nodes[first + j].st, rseed, offset + (unsigned long long)j * R + r, scores, ns, first_gi,
+                                             nullptr, nullptr, nullptr);
+            if (plies < 0) { s_err = 1; continue; }
+            if (plies == 0) continue;                                            // the child is terminal: handled below
+            atomicAdd(&s_vis[j], 1u);
+            const int nk = nodes[first + j].st.n_karts;
+            bool has_nan = false;
+            for (int k = 0; k < nk && k < ns; ++k) has_nan |= isnan(scores[k]);
+            if (has_nan) { atomicAdd(&s_nan[j], 1u); continue; }
+            for (int k = 0; k < nk && k < ns; ++k)
+                if (scores[k] != 0.0f) atomicAdd(&s_rsum[j][k], (double)scores[k]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            nodes[leaf].first_child = first; nodes[leaf].n_children = cnt;
+            s_nnodes = first + cnt;
+            for (int j = 0; j < cnt; ++j) {                                      // backpropagate (:280-289)
+                const int child = first + j;
+                if (s_vis[j] == 0) {                                             // terminal child: its own scores, R times
+                    float scores[2 * HK_MAX_KARTS];
+                    int ns = 0;
+                    const TreeNode& cn = nodes[child];
+                    if (cn.upnext >= 0) {
+                        unsigned long long keys[HK_MAX_ACTIONS];
+                        const int cc = legal_moves(g, cn.st, cn.upnext, keys);
+                        is_over(g, cn.st, cc, cn.upnext, scores, ns);
+                    }
+                    for (int n = child; n >= 0; n = nodes[n].parent) {
+                        const int up = nodes[n].upnext;
+                        if (up >= 0 && up < ns) nodes[n].total += (double)scores[up] * R;
+                        nodes[n].episodes += R;
+                    }
+                    continue;
+                }
+                const int c = (int)(s_vis[j] - s_nan[j]);
+                for (int n = child; n >= 0; n = nodes[n].parent) {
+                    const int up = nodes[n].upnext;
+                    if (up >= 0 && up < HK_MAX_KARTS) nodes[n].total += s_rsum[j][up];
+                    nodes[n].episodes += c;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // getBestStatesSequence (:108-122): follow upperConfidenceStrategy down, keep the states in which every kart stands at
+        // lastCompletedSection
+        int nb = 0, node = 0;
+        if (s_err != 1) {
+            while (nodes[node].n_children > 0 && nb < HK_MCTS_MAX_SEQ) {
+                const int j = ucs_pick(nodes, node, ukey, ctr);
+                if (j < 0) break;
+                node = nodes[node].first_child + j;
+                const hk_game_state& st = nodes[node].st;
+                bool all = true;
+                for (int i = 0; i < st.n_karts; ++i) all &= st.karts[i].section == st.lastCompletedSection;
+                if (all) best_out[(size_t)root * HK_MCTS_MAX_SEQ + nb++] = st;
+            }
+        }
+        n_best_out[root] = nb;
+        if (n_nodes_out) n_nodes_out[root] = s_nnodes;
+        if (status_out) status_out[root] = s_err == 1 ? 1 : 0;
+        if (root_episodes)
+            for (int j = 0; j < HK_MAX_ACTIONS; ++j) {
+                const bool in = j < nodes[0].n_children;
+                root_episodes[(size_t)root * HK_MAX_ACTIONS + j] = in ? nodes[nodes[0].first_child + j].episodes : 0;
+                if (root_values) root_values[(size_t)root * HK_MAX_ACTIONS + j] = in ? nodes[nodes[0].first_child + j].total : 0.0;
+            }
+    }
+}
+
 __global__ void __launch_bounds__(128) rollouts_trace_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ leaf,
                                                              long long n_rollouts, unsigned long long seed,
                                                              unsigned long long rollout_offset, int* n_plies_out,
@@ -863,6 +1062,42 @@ extern "C" int hk_mcts_rollouts_multi(const hk_game* g, const hk_game_state* lea
                                       uint64_t rollout_offset, int64_t* visit, double* reward_sum, int64_t* nan_count, int64_t* plies_sum)
 {
     return rollouts_impl(g, leaves, n_leaves, rollouts_per_leaf, seed, rollout_offset, visit, reward_sum, nan_count, plies_sum);
+}
+
+extern "C" int hk_mcts_search_batch(const hk_game* g, const hk_game_state* roots, int n_roots, int iterations, int rollouts_per_leaf,
+                                    uint64_t seed, hk_game_state* best_states, int32_t* n_best, int32_t* root_episodes,
+                                    double* root_values, int32_t* n_nodes)
+{
+    if (!g || !roots || n_roots < 1 || iterations < 0 || rollouts_per_leaf < 1 || !best_states || !n_best) { set_error("hk_mcts_search_batch: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    for (int r = 0; r < n_roots; ++r) { int rc = check_state(g, &roots[r], "hk_mcts_search_batch"); if (rc) return rc; }
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const int max_nodes = 1 + iterations * HK_MAX_ACTIONS;
+    const size_t nA = (size_t)n_roots * HK_MAX_ACTIONS;
+    const size_t sz[8] = {sizeof(hk_game_state) * n_roots, sizeof(TreeNode) * (size_t)n_roots * max_nodes,
+                          sizeof(hk_game_state) * (size_t)n_roots * HK_MCTS_MAX_SEQ, 4 * (size_t)n_roots, 4 * nA, 8 * nA, 4 * (size_t)n_roots,
+                          4 * (size_t)n_roots};
+    size_t off[9]; off[0] = 0;
+    for (int i = 0; i < 8; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
+    char* d = (char*)dscratch(c, 0, off[8]);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    HK_CUDA(cudaMemcpyAsync(d, roots, sz[0], cudaMemcpyHostToDevice, c->stream));
+    count_launch();
+    tree_search_kernel<<<(unsigned)n_roots, TREE_THREADS, 0, c->stream>>>(g->dev, (const hk_game_state*)d, iterations, rollouts_per_leaf, seed, max_nodes,
+        (TreeNode*)(d + off[1]), (hk_game_state*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (double*)(d + off[5]),
+        (int*)(d + off[6]), (int*)(d + off[7]));
+    HK_CUDA(cudaGetLastError());
+    std::vector<int> st((size_t)n_roots);
+    HK_CUDA(cudaMemcpyAsync(best_states, d + off[2], sz[2], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaMemcpyAsync(n_best, d + off[3], sz[3], cudaMemcpyDeviceToHost, c->stream));
+    if (root_episodes) HK_CUDA(cudaMemcpyAsync(root_episodes, d + off[4], sz[4], cudaMemcpyDeviceToHost, c->stream));
+    if (root_values) HK_CUDA(cudaMemcpyAsync(root_values, d + off[5], sz[5], cudaMemcpyDeviceToHost, c->stream));
+    if (n_nodes) HK_CUDA(cudaMemcpyAsync(n_nodes, d + off[6], sz[6], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaMemcpyAsync(st.data(), d + off[7], sz[7], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < n_roots; ++r)
+        if (st[r]) { set_error("hk_mcts_search_batch: upNext() == -1 reached in the tree of root %d (KartDiscreteGame.cs:326 would throw)", r); return HK_ERR_NO_UPNEXT; }
+    return HK_OK;
 }
 
 extern "C" int hk_mcts_rollouts_trace(const hk_game* g, const hk_game_state* leaf, int64_t n_rollouts, uint64_t seed, uint64_t rollout_offset,

@@ -96,6 +96,23 @@ class Game:
                                              abi.vptr(visit), abi.vptr(rsum), abi.vptr(nanc), abi.vptr(plies)))
         return dict(visit=visit, reward_sum=rsum, nan_count=nanc, plies=plies)
 
+    def search_batch(self, roots, iterations: int, rollouts_per_leaf: int, seed: int = 0):
+        """hk_mcts_search_batch: constructSearchTree + getBestStatesSequence for every root in one launch (one thread block per
+        tree).  Returns best (list of lists of hk_game_state), root_episodes / root_values of the root's children in nextMoves()
+        order, n_nodes."""
+        n = len(roots)
+        arr = (abi.hk_game_state * n)(*roots)
+        best = (abi.hk_game_state * (n * abi.HK_MCTS_MAX_SEQ))()
+        n_best = np.zeros(n, dtype=np.int32)
+        eps = np.zeros((n, abi.HK_MAX_ACTIONS), dtype=np.int32)
+        vals = np.zeros((n, abi.HK_MAX_ACTIONS))
+        nodes = np.zeros(n, dtype=np.int32)
+        lib = abi.load_library()
+        abi.check(lib.hk_mcts_search_batch(self._h, C.cast(arr, C.c_void_p), n, iterations, rollouts_per_leaf, seed,
+                                           C.cast(best, C.c_void_p), abi.vptr(n_best), abi.vptr(eps), abi.vptr(vals), abi.vptr(nodes)))
+        seqs = [[best[r * abi.HK_MCTS_MAX_SEQ + k] for k in range(int(n_best[r]))] for r in range(n)]
+        return dict(best=seqs, n_best=n_best, root_episodes=eps, root_values=vals, n_nodes=nodes)
+
     def rollouts_trace(self, leaf: abi.hk_game_state, n_rollouts: int, seed: int = 0, rollout_offset: int = 0):
         n = n_rollouts
         out = dict(n_plies=np.zeros(n, dtype=np.int32), actions=np.zeros((n, abi.HK_MAX_PLIES, 3), dtype=np.int32),
@@ -176,6 +193,35 @@ class DiscreteGameState:
     @property
     def lastCompletedSection(self):
         return self.state.lastCompletedSection
+
+
+def philox_first(key: int, counter: int, ply: int) -> int:
+    """First word of Philox4x32-10 with counter (counter lo, counter hi, ply, 0) and key `key` — the generator of the rollouts
+    (csrc/hk_game.cu) and of the tie-breaking picks of hk_mcts_search_batch."""
+    M = 0xFFFFFFFF
+    c0, c1, c2, c3 = counter & M, (counter >> 32) & M, ply & M, 0
+    k0, k1 = key & M, (key >> 32) & M
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & M, p1 & M, ((p0 >> 32) ^ c3 ^ k1) & M, p0 & M
+        k0, k1 = (k0 + 0x9E3779B9) & M, (k1 + 0xBB67AE85) & M
+    return c0
+
+
+class PhiloxPicks:
+    """Stand-in for KartMCTS.random that replays the pick stream of hk_mcts_search_batch for root seed `rseed` (= seed + root
+    index): upperConfidenceStrategy's random initial child (it only matters for exact ties)."""
+
+    def __init__(self, rseed: int):
+        self.key, self.ctr = (rseed ^ 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF, 0
+
+    def randrange(self, n: int) -> int:
+        v = philox_first(self.key, self.ctr, 0) % n
+        self.ctr += 1
+        return v
+
+    def getrandbits(self, k: int) -> int:
+        return 0
 
 
 class KartMCTSNode:                                     # KartMCTS.cs:18-38

@@ -204,6 +204,24 @@ int hk_mcts_rollouts_multi(const hk_game* g, const hk_game_state* leaves, int n_
                            uint64_t seed, uint64_t rollout_offset, int64_t* visit, double* reward_sum,
                            int64_t* nan_count, int64_t* plies_sum);
 
+/*
+ * Batched tree search: KartMCTS.constructSearchTree (KartMCTS.cs:50-106) followed by getBestStatesSequence (:108-122) for
+ * n_roots independent root states in one launch, one thread block per tree — what planWithMCTS (HierarchicalKartAgent.cs:
+ * 194-283) does per agent on a background thread, for every agent of many races at once.  Each of `iterations` iterations
+ * walks the tree with upperConfidenceStrategy (:167-192) to a node without children (findLeaf :194-201), creates all its
+ * children and plays rollouts_per_leaf rollouts through each (the reference's own leaf-parallel variant, processLeaf
+ * :124-159), then backpropagates (:280-289).  Root r uses Philox key seed + r for its rollouts (ids it * R * HK_MAX_ACTIONS +
+ * child * R + k, as hk_mcts_rollouts_multi numbers them) and counter stream (seed + r) ^ 0x9E3779B97F4A7C15 for the random
+ * initial pick of upperConfidenceStrategy, so a host mirror driven by the same streams builds the same tree.
+ *   best_states   [n_roots][HK_MCTS_MAX_SEQ]  the states of getBestStatesSequence, n_best [n_roots] of them
+ *   root_episodes [n_roots][HK_MAX_ACTIONS]   numEpisodes of the root's children in nextMoves() order (may be NULL)
+ *   root_values   [n_roots][HK_MAX_ACTIONS]   their totalValue (may be NULL);  n_nodes [n_roots] tree sizes (may be NULL)
+ */
+#define HK_MCTS_MAX_SEQ 16
+int hk_mcts_search_batch(const hk_game* g, const hk_game_state* roots, int n_roots, int iterations, int rollouts_per_leaf,
+                         uint64_t seed, hk_game_state* best_states, int32_t* n_best, int32_t* root_episodes,
+                         double* root_values, int32_t* n_nodes);
+
 /* The rollout policy's index distribution for `cnt` legal moves (KartMCTS.cs:266-269 via NextGaussian :218-236):
  * cdf_out[k] = P(index <= k) as a 32-bit threshold, exactly what the kernels sample from. cnt in 1..HK_MAX_ACTIONS. */
 int hk_policy_cdf(int cnt, uint32_t* cdf_out /* [cnt] */);

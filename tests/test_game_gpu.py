@@ -186,3 +186,33 @@ def test_tree_search_api(hk):
     best = mcts.KartMCTS.getBestStatesSequence(node)
     assert len(best) >= 1
     assert all(all(k.section == s.lastCompletedSection for k in s.kartStates) for s in best)
+
+
+@pytest.mark.parametrize("track_name,n_karts,bucket,teams", [("Complex", 2, 2, [0, 1]), ("Oval", 2, 1, [0, 1]), ("Complex", 4, 2, [0, 0, 1, 1])])
+def test_device_tree_search_equals_host_mirror(hk, track_name, n_karts, bucket, teams):
+    """hk_mcts_search_batch (one thread block per tree) builds the tree the host mirror of KartMCTS.constructSearchTree builds when
+    it is driven by the same Philox streams: same children statistics at the root, same tree size, same getBestStatesSequence."""
+    import ctypes as C
+    from hierarchicalkarting_b200 import abi, mcts as M, tracks
+    track = tracks.COMPLEX if track_name == "Complex" else tracks.OVAL
+    G = M.Game(track, n_karts, bucket)
+    lanes = [2, 3, 1, 4][:n_karts]
+    roots = [tracks.root_state(track, s0, lanes, teams=teams, tire_age=2500, times=[0, 40, 20, 60][:n_karts]) for s0 in (0, 3, 7, 11, 17)]
+    K, R, seed = 6, 64, 20260007
+    dev = G.search_batch(roots, K, R, seed)
+    old_random, old_R = M.KartMCTS.random, M.KartMCTS.rollouts_per_leaf
+    try:
+        M.KartMCTS.rollouts_per_leaf = R
+        for r, root in enumerate(roots):
+            M.KartMCTS.random = M.PhiloxPicks(seed + r)
+            tree = M.KartMCTS.constructSearchTree(M.DiscreteGameState(G, root), T=1e9, seed=seed + r, max_iterations=K)
+            seq = M.KartMCTS.getBestStatesSequence(tree)
+            kids = [tree.children[mv] for mv in tree.state.nextMoves()]
+            assert int(dev["n_nodes"][r]) == 1 + tree.childrenAsRoot
+            assert [int(x) for x in dev["root_episodes"][r][:len(kids)]] == [k.numEpisodes for k in kids]
+            assert np.allclose(dev["root_values"][r][:len(kids)], [k.totalValue for k in kids], rtol=1e-9, atol=1e-9)
+            assert int(dev["n_best"][r]) == len(seq)
+            for a, b in zip(dev["best"][r], seq):
+                assert bytes(a) == bytes(b.state)
+    finally:
+        M.KartMCTS.random, M.KartMCTS.rollouts_per_leaf = old_random, old_R
