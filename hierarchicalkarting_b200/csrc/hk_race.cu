@@ -379,7 +379,8 @@ extern "C" int hk_race_run(const hk_track* t, const hk_race_params* p, int n_rac
     HK_CUDA(cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), s));
     const unsigned blocks = (unsigned)((nb + 127) / 128);
     for (int step = first_step; step < first_step + n_steps; ++step) {
-        if (step > 0 && step % p->planEvery == 0) {                  // HKA:334 (0.5 Hz)
+        if (step > 0 && step % p->planEvery == 0 && !p->highModeMcts) {   // HKA:331-353 (0.5 Hz): planFixed, or planWithMCTS — the caller's
+                                                                         // (Races.plan_mcts_batch over hk_mcts_search_batch) between two runs
             count_launch();
             race_plan_fixed_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp);
         }

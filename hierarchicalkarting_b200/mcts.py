@@ -113,6 +113,19 @@ class Game:
         seqs = [[best[r * abi.HK_MCTS_MAX_SEQ + k] for k in range(int(n_best[r]))] for r in range(n)]
         return dict(best=seqs, n_best=n_best, root_episodes=eps, root_values=vals, n_nodes=nodes)
 
+    def search_batch_array(self, roots: np.ndarray, iterations: int, rollouts_per_leaf: int, seed: int = 0):
+        """search_batch over a numpy array of abi.GAME_STATE_DTYPE; `best` comes back as an array [n][HK_MCTS_MAX_SEQ] of that dtype."""
+        roots = np.ascontiguousarray(roots, dtype=abi.GAME_STATE_DTYPE)
+        n = roots.shape[0]
+        best = np.zeros((n, abi.HK_MCTS_MAX_SEQ), dtype=abi.GAME_STATE_DTYPE)
+        n_best = np.zeros(n, dtype=np.int32)
+        eps = np.zeros((n, abi.HK_MAX_ACTIONS), dtype=np.int32)
+        vals = np.zeros((n, abi.HK_MAX_ACTIONS))
+        nodes = np.zeros(n, dtype=np.int32)
+        abi.check(abi.load_library().hk_mcts_search_batch(self._h, abi.vptr(roots), n, iterations, rollouts_per_leaf, seed, abi.vptr(best),
+                                                          abi.vptr(n_best), abi.vptr(eps), abi.vptr(vals), abi.vptr(nodes)))
+        return dict(best=best, n_best=n_best, root_episodes=eps, root_values=vals, n_nodes=nodes)
+
     def rollouts_trace(self, leaf: abi.hk_game_state, n_rollouts: int, seed: int = 0, rollout_offset: int = 0):
         n = n_rollouts
         out = dict(n_plies=np.zeros(n, dtype=np.int32), actions=np.zeros((n, abi.HK_MAX_PLIES, 3), dtype=np.int32),

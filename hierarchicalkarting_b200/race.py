@@ -165,6 +165,80 @@ def apply_best_states(track: Track, karts_race: np.ndarray, plans_race: np.ndarr
                 plans_race[ego]["oppVel"][ks.section % L] = ks.max_velocity
 
 
+def mcts_root_states_batch(track: Track, params: abi.hk_race_params, karts: np.ndarray, plans: np.ndarray, section_window: int = 2,
+                           time_precision: int = 100):
+    """`mcts_root_state` for every agent of every 2-kart race at once (vectorised; same arithmetic, float32 where the reference is
+    float32).  Returns (roots [n_races][2] of abi.GAME_STATE_DTYPE, nearby [n_races][2][2]: race-local agent of game kart i, -1 = none)."""
+    n_races, L = karts.shape[0], track.n_sections
+    ar = np.arange(n_races)
+    sec = karts["section"].astype(np.int64)
+    stimes = plans["sectionTimes"]
+    roots = np.zeros((n_races, 2), dtype=abi.GAME_STATE_DTYPE)
+    nearby = np.full((n_races, 2, 2), -1, dtype=np.int32)
+    wear = (np.float32(MAX_STEER) - karts["steer"].astype(np.float32)) / np.float32(MAX_STEER - MIN_STEER)
+    tire = (wear * np.float32(10000)).astype(np.float32).astype(np.int32)
+    for e in (0, 1):
+        o = 1 - e
+        near = np.abs(sec[:, o] - sec[:, e]) < section_window                   # foreach agent in m_envController.Agents (:182)
+        initial = np.where(near, np.maximum(sec[:, 0], sec[:, 1]), sec[:, e])
+        furthest = np.where(near, np.where(sec[:, 1] >= sec[:, 0], 1, 0), e)
+        g = roots[:, e]
+        g["n_karts"] = np.where(near, 2, 1)
+        g["initialSection"] = initial
+        g["lastCompletedSection"] = initial
+        g["finalSection"] = initial + params.treeSearchDepth
+        for slot in (0, 1):
+            a = np.where(near, slot, e)
+            valid = near | (slot == 0)
+            sa = sec[ar, a]
+            d = stimes[ar, a, sa % L].astype(np.int64) - stimes[ar, furthest, sa % L].astype(np.int64)
+            t_at = ((d.astype(np.float32) * np.float32(0.02)).astype(np.float32) * np.float32(time_precision)).astype(np.float32).astype(np.int32)
+            ks = g["karts"][:, slot]
+            ks["team"] = np.where(valid, a, 0)
+            ks["section"] = np.where(valid, initial, 0)
+            ks["timeAtSection"] = np.where(valid & (sa != initial), t_at, 0)              # :211-214
+            ks["max_velocity"] = np.where(valid, min(params.velocityBucketSize, int(params.topSpeed)), 0)   # quirks B.6-1, B.6-2
+            ks["lane"] = np.where(valid, karts["lane"][ar, a], 0)
+            ks["tireAge"] = np.where(valid, tire[ar, a], 0)
+            ks["laneChanges"] = np.where(valid, karts["laneChanges"][ar, a], 0)
+            nearby[:, e, slot] = np.where(valid, a, -1)
+    return roots, nearby
+
+
+def apply_best_states_batch(track: Track, karts: np.ndarray, plans: np.ndarray, nearby: np.ndarray, best: np.ndarray, n_best: np.ndarray) -> None:
+    """`apply_best_states` for every agent at once: best [n_races][2][HK_MCTS_MAX_SEQ] of abi.GAME_STATE_DTYPE, n_best [n_races][2]."""
+    n_races, L = karts.shape[0], track.n_sections
+    ar = np.arange(n_races)
+    for e in (0, 1):
+        sec = karts["section"][:, e].astype(np.int64)
+        bound = sec + np.where(sec == 0, 0, 1)
+        pl = plans[:, e]
+        for k in range(int(n_best[:, e].max()) if n_races else 0):
+            gs = best[:, e, k]
+            for slot in (0, 1):
+                ks = gs["karts"][:, slot]
+                live = (k < n_best[:, e]) & (slot < gs["n_karts"])
+                who = nearby[:, e, slot]
+                key = ks["section"].astype(np.int64) % L
+                m = live & (who == e) & (ks["section"] > bound)
+                pl["lane"][ar[m], key[m]] = ks["lane"][m]
+                pl["vel"][ar[m], key[m]] = ks["max_velocity"][m]
+                m = live & (who != e) & (who >= 0)
+                pl["oppLane"][ar[m], key[m]] = ks["lane"][m]
+                pl["oppVel"][ar[m], key[m]] = ks["max_velocity"][m]
+
+
+def plan_mcts_batch(track: Track, params: abi.hk_race_params, game, karts: np.ndarray, plans: np.ndarray, iterations: int,
+                    rollouts_per_leaf: int, seed: int = 0):
+    """planWithMCTS + the waypoint hand-off for EVERY agent of every race in one GPU tree-search launch (hk_mcts_search_batch: one
+    thread block per agent's tree).  Root of agent (race r, ego e) is root index 2 r + e.  Returns the search result dict."""
+    n_races = karts.shape[0]
+    roots, nearby = mcts_root_states_batch(track, params, karts, plans)
+    out = game.search_batch_array(np.ascontiguousarray(roots.reshape(-1)), iterations, rollouts_per_leaf, seed)
+    apply_best_states_batch(track, karts, plans, nearby, out["best"].reshape(n_races, 2, abi.HK_MCTS_MAX_SEQ), out["n_best"].reshape(n_races, 2))
+    return out
+
+
 def plan_with_mcts(track: Track, params: abi.hk_race_params, game, karts_race: np.ndarray, plans_race: np.ndarray, ego: int,
                    T: float = 0.9, max_iterations: int | None = None, seed: int | None = None):
     """planWithMCTS + hand-off for one agent: root state, KartMCTS.constructSearchTree (GPU leaf-parallel rollouts),

@@ -220,7 +220,8 @@ long long hk_oracle_race_run(const hk_section* sections, const double* trig, con
 {
     long long bad = 0;
     for (int step = first_step; step < first_step + n_steps; ++step) {
-        if (step > 0 && step % p->planEvery == 0) hk_oracle_race_plan_fixed(sections, n_sections, p, 2 * n_races, karts, plans);
+        if (step > 0 && step % p->planEvery == 0 && !p->highModeMcts)       /* HierarchicalKartAgent.cs:331-353: planFixed only in Fixed mode */
+            hk_oracle_race_plan_fixed(sections, n_sections, p, 2 * n_races, karts, plans);
 #pragma omp parallel for reduction(+ : bad) schedule(static)
         for (int r = 0; r < n_races; ++r) {
             double u[4];

@@ -146,3 +146,49 @@ def test_telemetry_log_format_and_reference_parser(oracle, tmp_path, capsys):
         os.chdir(cwd)
     out = capsys.readouterr().out
     assert "Wins {'Fixed-LQR': 6}" in out and "DNFs {}" in out and "Avg Collisions {'Fixed-LQR': 0.0}" in out
+
+
+def test_batched_mcts_root_states_and_handoff_equal_per_agent_versions():
+    """race.mcts_root_states_batch / apply_best_states_batch (what plan_mcts_batch feeds hk_mcts_search_batch with and applies) are the
+    vectorised forms of mcts_root_state / apply_best_states (HierarchicalKartAgent.cs:180-245, 366-402)."""
+    import ctypes as C
+    from hierarchicalkarting_b200 import abi, race as R, tracks
+    rng = np.random.default_rng(11)
+    track = tracks.COMPLEX
+    prm = R.race_params(S.COMPLEX, high_mode_mcts=True)
+    n = 300
+    karts = np.zeros((n, 2), dtype=abi.RACE_KART_DTYPE)
+    plans = np.zeros((n, 2), dtype=abi.RACE_PLAN_DTYPE)
+    karts["section"] = rng.integers(0, 90, size=(n, 1)) + rng.integers(-3, 4, size=(n, 2)).clip(0)
+    karts["section"][:20] = 0
+    karts["lane"] = rng.integers(1, 5, size=(n, 2))
+    karts["laneChanges"] = rng.integers(0, 4, size=(n, 2))
+    karts["steer"] = rng.uniform(1.0, 4.0, size=(n, 2)).astype(np.float32)
+    plans["sectionTimes"] = rng.integers(0, 5000, size=(n, 2, abi.HK_MAX_SECTIONS))
+    roots, nearby = R.mcts_root_states_batch(track, prm, karts, plans)
+    for r in range(n):
+        for e in (0, 1):
+            st, nb = R.mcts_root_state(track, prm, karts[r], plans[r], e)
+            assert bytes(st) == roots[r, e].tobytes(), (r, e)
+            assert list(nearby[r, e, :len(nb)]) == nb and all(v == -1 for v in nearby[r, e, len(nb):])
+    # hand-off: synthetic best sequences (sections ahead of the karts, random lanes / buckets)
+    best = np.zeros((n, 2, abi.HK_MCTS_MAX_SEQ), dtype=abi.GAME_STATE_DTYPE)
+    n_best = rng.integers(0, 9, size=(n, 2)).astype(np.int32)
+    for k in range(abi.HK_MCTS_MAX_SEQ):
+        best[:, :, k] = roots
+        for slot in (0, 1):
+            best["karts"][:, :, k, slot]["section"] = roots["initialSection"] + k + rng.integers(0, 2, size=(n, 2))
+            best["karts"][:, :, k, slot]["lane"] = rng.integers(1, 5, size=(n, 2))
+            best["karts"][:, :, k, slot]["max_velocity"] = rng.integers(8, 16, size=(n, 2))
+    pa, pb = plans.copy(), plans.copy()
+    R.apply_best_states_batch(track, karts, pa, nearby, best, n_best)
+
+    class _GS:
+        def __init__(self, rec):
+            self.state = abi.hk_game_state.from_buffer_copy(rec.tobytes())
+    for r in range(n):
+        for e in (0, 1):
+            nb = [int(v) for v in nearby[r, e] if v >= 0]
+            R.apply_best_states(track, karts[r], pb[r], e, nb, [_GS(best[r, e, k]) for k in range(int(n_best[r, e]))])
+    for f in ("lane", "vel", "oppLane", "oppVel"):
+        assert np.array_equal(pa[f], pb[f]), f

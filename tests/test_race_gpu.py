@@ -152,3 +152,35 @@ def test_mcts_root_and_waypoint_handoff(hk):
     before = karts["section"].copy()
     _, bad = G.run(karts, plans, 99, 300)                           # LQNG now tracks the MCTS waypoints (+2 buckets of speed, :757)
     assert bad == 0 and np.all(karts["section"] >= before + 4)
+
+
+def test_batched_mcts_planning_equals_per_agent_host_search(hk):
+    """BASELINE config 5's high level at scale: race.plan_mcts_batch (every agent's tree in one hk_mcts_search_batch launch, one thread
+    block per tree) leaves the plan tables the per-agent host flow (planWithMCTS over the KartMCTS mirror) leaves when both are
+    driven by the same Philox streams; the races then run on those waypoints."""
+    from hierarchicalkarting_b200 import mcts as M
+    track = S.OVAL
+    prm = R.race_params(track, high_mode_mcts=True)
+    G = R.Races(track, prm)
+    game = M.Game(track, 2, prm.velocityBucketSize)
+    n_races, K, RPL, seed = 6, 24, 32, 777
+    karts, plans = R.start_grid(track, n_races, seed=41)
+    G.run(karts, plans, 0, 100)
+    pa, pb = plans.copy(), plans.copy()
+    out = R.plan_mcts_batch(track, prm, game, karts, pa, K, RPL, seed)
+    assert out["n_best"].max() >= 1
+    old_random, old_R = M.KartMCTS.random, M.KartMCTS.rollouts_per_leaf
+    try:
+        M.KartMCTS.rollouts_per_leaf = RPL
+        for r in range(n_races):
+            for ego in range(2):
+                M.KartMCTS.random = M.PhiloxPicks(seed + 2 * r + ego)
+                root, best = R.plan_with_mcts(track, prm, game, karts[r], pb[r], ego, T=1e9, max_iterations=K, seed=seed + 2 * r + ego)
+                assert len(best) == int(out["n_best"][2 * r + ego])
+    finally:
+        M.KartMCTS.random, M.KartMCTS.rollouts_per_leaf = old_random, old_R
+    for f in ("lane", "vel", "oppLane", "oppVel"):
+        assert np.array_equal(pa[f], pb[f]), f
+    before = karts["section"].copy()
+    _, bad = G.run(karts, pa, 100, 300)                             # MCTS mode: hk_race_run does not replan with planFixed
+    assert bad == 0 and np.all(karts["section"] >= before + 4)
