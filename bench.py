@@ -512,6 +512,45 @@ def main():
                               "agent and step (recipe + assembly + solve + plant + bookkeeping on the GPU); host call incl. the "
                               "upload and download of the race states"}
 
+    # ---- the same loop with the MCTS high level (BASELINE config 5 as written: MCTS waypoints -> batched LQNG -> dynamics rollout):
+    #      every 100 steps every agent's tree search runs on the GPU (hk_mcts_search_batch, one thread block per tree) --------------
+    race_mcts_obj = None
+    if not args.no_race and not args.no_mcts:
+        try:
+            from hierarchicalkarting_b200 import mcts as M2
+            prm_m = RC.race_params(S.OVAL, high_mode_mcts=True)
+            RM = RC.Races(S.OVAL, prm_m)
+            game_m = M2.Game(S.OVAL, 2, prm_m.velocityBucketSize)
+            km, pm = RC.start_grid(S.OVAL, RACES, seed=20260004 + rank)
+            RM.run(km, pm, 0, 100)                                              # standing start, no plan yet
+            MCTS_K, MCTS_R, blocks_m = 24, 16, 2
+            RC.plan_mcts_batch(S.OVAL, prm_m, game_m, km[:64].copy(), pm[:64].copy(), MCTS_K, MCTS_R, 1)   # warm-up
+            barrier()
+            k0m = lib.hk_kernel_launch_count()
+            t_plan = t_run = 0.0
+            n_best_mean = 0.0
+            for b in range(blocks_m):
+                t0 = time.perf_counter()
+                outm = RC.plan_mcts_batch(S.OVAL, prm_m, game_m, km, pm, MCTS_K, MCTS_R, 20260006 + 1000 * rank + b)
+                t1 = time.perf_counter()
+                _, badm = RM.run(km, pm, 100 + 100 * b, 100)
+                t2 = time.perf_counter()
+                t_plan += t1 - t0; t_run += t2 - t1
+                n_best_mean = float(outm["n_best"].mean())
+            el_m = max_over_ranks(t_plan + t_run)
+            race_mcts_obj = {"metric": "race_agent_steps_per_s", "value": world * 2 * RACES * 100 * blocks_m / el_m, "unit": "agent-steps/s",
+                             "races_per_gpu": RACES, "steps": 100 * blocks_m, "plans_per_s": world * 2 * RACES * blocks_m / max_over_ranks(t_plan),
+                             "ms_per_planning_event": 1e3 * t_plan / blocks_m, "ms_per_step_between_plans": 1e3 * t_run / (100 * blocks_m),
+                             "tree_search": {"iterations": MCTS_K, "rollouts_per_leaf": MCTS_R, "episodes_per_plan": float(outm["root_episodes"].sum(axis=1).mean()),
+                                             "nodes_per_tree": float(outm["n_nodes"].mean()), "best_states_per_plan": n_best_mean},
+                             "lqng_status_nonzero": int(badm), "gpu_launches": int(lib.hk_kernel_launch_count() - k0m),
+                             "sections_mean": float(km["section"].mean()),
+                             "config": "BASELINE config 5 with the MCTS high level: 2-kart Oval races, every agent replans every 100 steps by "
+                                       "KartMCTS.constructSearchTree + getBestStatesSequence on the GPU (one thread block per tree), root "
+                                       "states and waypoint hand-off vectorised on the host, LQNG every step"}
+        except Exception as exc:
+            race_mcts_obj = {"error": repr(exc)[:300]}
+
     clocks = sampler.finish()
 
     # ---- final gather of per-rank summaries (the only communication) ------------------------------------------------------
@@ -566,6 +605,8 @@ def main():
         line["mcts"] = mcts_obj
     if race_obj:
         line["race"] = race_obj
+    if race_mcts_obj:
+        line["race_mcts"] = race_mcts_obj
     line["full_outputs"] = full_obj
     line["time_varying"] = tv_obj
     if lqng4_obj:
