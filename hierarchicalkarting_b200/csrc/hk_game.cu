@@ -1082,6 +1082,7 @@ extern "C" int hk_mcts_search_batch(const hk_game* g, const hk_game_state* roots
     char* d = (char*)dscratch(c, 0, off[8]);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
     HK_CUDA(cudaMemcpyAsync(d, roots, sz[0], cudaMemcpyHostToDevice, c->stream));
+    HK_CUDA(cudaMemsetAsync(d + off[2], 0, sz[2], c->stream));                 // entries past n_best stay zero
     count_launch();
     tree_search_kernel<<<(unsigned)n_roots, TREE_THREADS, 0, c->stream>>>(g->dev, (const hk_game_state*)d, iterations, rollouts_per_leaf, seed, max_nodes,
         (TreeNode*)(d + off[1]), (hk_game_state*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (double*)(d + off[5]),

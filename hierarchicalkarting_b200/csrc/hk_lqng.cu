@@ -246,10 +246,13 @@ __device__ __noinline__ void lqng_generic_body(const LqngParams& p, long long pr
         __syncwarp(mask);
         for (int t = 0; t <= p.horizon; ++t) {
             const int tt = p.time_varying ? t : 0;
-            if (r < m) {
+            if (r < m) {                                            // groups past the end of the batch (live == false) only keep step
                 double acc = 0.0;
-                for (int c = 0; c < n; ++c) acc = fma(-gP[(size_t)t * m * n + r * n + c], xs[c], acc);
-                us[r] = acc - ga[(size_t)t * m + r];
+                if (live) {
+                    for (int c = 0; c < n; ++c) acc = fma(-gP[(size_t)t * m * n + r * n + c], xs[c], acc);
+                    acc -= ga[(size_t)t * m + r];
+                }
+                us[r] = acc;
             }
             __syncwarp(mask);
             double xn = 0.0;

@@ -27,6 +27,9 @@ abi.check(lib.hk_lqng_assemble_solve_batch(20000, 2, 3, float(prob["dt"]), *[abi
 G = M.Game(tracks.COMPLEX, 2, 2)
 leaf = tracks.root_state(tracks.COMPLEX, 3, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 80])
 G.rollouts(leaf, 20000, seed=1)
+roots = [tracks.root_state(tracks.COMPLEX, s0, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 40]) for s0 in (0, 5, 9, 30)]
+out = G.search_batch(roots, 5, 8, seed=3)
+assert out["n_nodes"].min() > 1
 RS = RC.Races(S.OVAL, RC.race_params(S.OVAL))
 karts, plans = RC.start_grid(S.OVAL, 64, seed=1)
 RS.run(karts, plans, 0, 5)
