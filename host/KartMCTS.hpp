@@ -132,6 +132,22 @@ public:
         return root;
     }
 
+    // constructSearchTree + getBestStatesSequence for many roots in one GPU launch (hk_mcts_search_batch, one thread block per
+    // tree): what planWithMCTS (HierarchicalKartAgent.cs:194-283) does per agent, for every agent of many races at once
+    static std::vector<std::vector<DiscreteGameState>> searchBatch(const std::shared_ptr<GameTables>& tables, const std::vector<hk_game_state>& roots,
+                                                                   int iterations, int rolloutsPerLeaf, unsigned long long seed)
+    {
+        const int n = (int)roots.size();
+        std::vector<hk_game_state> best((size_t)n * HK_MCTS_MAX_SEQ);
+        std::vector<int32_t> nBest(n);
+        hk_check(hk_mcts_search_batch(tables->handle(), roots.data(), n, iterations, rolloutsPerLeaf, seed, best.data(), nBest.data(), nullptr,
+                                      nullptr, nullptr));
+        std::vector<std::vector<DiscreteGameState>> out(n);
+        for (int r = 0; r < n; ++r)
+            for (int k = 0; k < nBest[r]; ++k) out[r].push_back(DiscreteGameState(tables, best[(size_t)r * HK_MCTS_MAX_SEQ + k]));
+        return out;
+    }
+
     static std::vector<DiscreteGameState> getBestStatesSequence(KartMCTSNode* node)                          // :108-122
     {
         std::vector<DiscreteGameState> best;

@@ -59,6 +59,14 @@ int main(int argc, char** argv)
     MCTS::KartMCTS::constructSearchTree(&node, 0.2);
     auto best = MCTS::KartMCTS::getBestStatesSequence(&node);
     if (node.numEpisodes <= 0 || node.children.empty() || best.empty()) { std::printf("MCTS produced no plan\n"); return 1; }
+    {   // the same search for several roots at once on the device
+        std::vector<hk_game_state> roots(5, root);
+        for (int r = 0; r < 5; ++r) { roots[r].initialSection = roots[r].lastCompletedSection = r; roots[r].finalSection = r + 8; for (int i = 0; i < 2; ++i) roots[r].karts[i].section = r; }
+        auto plans = MCTS::KartMCTS::searchBatch(tables, roots, 40, 64, 12345ull);
+        int withPlan = 0;
+        for (auto& p : plans) withPlan += !p.empty();
+        if (plans.size() != 5 || withPlan == 0) { std::printf("batched tree search produced no plan\n"); return 1; }
+    }
     // headless races on a square ring: 4 straights of 20 m joined by 90-degree corners, 8 checkpoints, 3 races x 2 karts
     {
         std::vector<Race::Checkpoint> ring;
