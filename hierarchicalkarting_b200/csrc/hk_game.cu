@@ -618,7 +618,7 @@ __device__ int ucs_pick(const TreeNode* nodes, int node, unsigned long long key,
 
 constexpr int TREE_THREADS = 128;
 
-__global__ void __launch_bounds__(TREE_THREADS) tree_search_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ roots,
+__global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ roots,
                                                                    int iterations, int R, unsigned long long seed, int max_nodes,
                                                                    TreeNode* __restrict__ slabs, hk_game_state* __restrict__ best_out,
                                                                    int* __restrict__ n_best_out, int* __restrict__ root_episodes,
