@@ -195,6 +195,25 @@ __device__ int legal_moves(const DevGame& g, const hk_game_state& st, int np, un
     return cnt;
 }
 
+// One candidate of legal_moves (same filters, same key): lets a thread block evaluate the candidates of a node in parallel.
+__device__ unsigned long long legal_move_key(const DevGame& g, const hk_game_state& st, int np, int gi)
+{
+    const hk_kart& kart = g.karts[np];
+    const hk_kart_state& cs = st.karts[np];
+    const hk_section& cur = sec(g, cs.section);
+    const int optSign = optimal_lane_sign(g.sections[st.lastCompletedSection % g.n_sections]);            // KartMCTS.cs:252
+    const float wear = (float)cs.tireAge / 10000.0f;
+    const int v = 6 + (gi >> 2) * g.p.velocityBucketSize, vmx = min(v + g.p.velocityBucketSize, g.vmax), lane = (gi & 3) + 1;
+    const int dl = abs(lane - cs.lane);
+    if (is_straight(cur) && cs.laneChanges + dl > g.p.maxLaneChanges) return ~0ull;                        // :346
+    if (max_speed_radius_wear(kart, radius_of_lane(cur, cs.lane, lane), wear) < (float)v) return ~0ull;    // :357 (real wear)
+    const hk_kart_state ap = apply_action(g, cs, hk_action{v, vmx, lane});                                 // :368
+    if (ap.infeasible) return ~0ull;
+    const unsigned dt = (unsigned)(ap.timeAtSection - cs.timeAtSection);
+    return ((unsigned long long)dt << 22) | ((unsigned long long)(1023 - vmx) << 12) | ((unsigned long long)dl << 10) |
+           ((unsigned long long)(optSign * lane + 4) << 6) | (unsigned long long)gi;
+}
+
 // k-th smallest key (k < cnt): k+1 passes of "smallest key greater than the previous one" — keys are distinct.
 __device__ int select_kth(const unsigned long long* keys, int n_cand, int k)
 {
@@ -629,6 +648,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
     __shared__ unsigned long long s_keys[HK_MAX_ACTIONS];
     __shared__ unsigned s_vis[HK_MAX_ACTIONS], s_nan[HK_MAX_ACTIONS];
     __shared__ double s_rsum[HK_MAX_ACTIONS][HK_MAX_KARTS];
+    __shared__ float s_w[HK_MAX_ACTIONS];
     __shared__ int s_leaf, s_cnt, s_first, s_nnodes, s_stop, s_err;
     {
         const int* src = reinterpret_cast<const int*>(gg);
@@ -644,29 +664,51 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
         TreeNode& r = nodes[0];
         r.st = roots[root]; r.total = 0.0; r.episodes = 0; r.parent = -1; r.first_child = -1; r.n_children = 0;
         r.upnext = up_next(r.st);
-        s_nnodes = 1; s_stop = 0; s_err = 0;
+        s_nnodes = 1; s_stop = 0; s_err = 0; s_leaf = 0;
     }
     __syncthreads();
     for (int it = 0; it < iterations; ++it) {
-        if (threadIdx.x == 0) {
-            // findLeaf (:194-201): a node either has all its children or none (processLeaf creates them together)
-            int node = 0;
-            while (nodes[node].n_children > 0) {
-                const int j = ucs_pick(nodes, node, ukey, ctr);
-                if (j < 0) { s_err = 2; break; }
-                node = nodes[node].first_child + j;
+        // findLeaf (:194-201): a node either has all its children or none (processLeaf creates them together).  One level per round:
+        // the threads evaluate UCTWeight of the children in parallel (a double-precision log each), thread 0 makes the pick.
+        for (;;) {
+            const int node = s_leaf;
+            const int n = nodes[node].n_children;
+            if (n == 0) break;                                                   // uniform: s_leaf and the node are block-wide state
+            if ((int)threadIdx.x < n) {
+                const TreeNode& c = nodes[nodes[node].first_child + threadIdx.x];
+                s_w[threadIdx.x] = c.episodes == 0 ? 0.0f : uct_weight(nodes[node], c);
+                if (c.episodes == 0) s_err = 2;                                  // UCTWeight would divide by zero
             }
-            s_leaf = node;
+            __syncthreads();
+            if (threadIdx.x == 0 && s_err == 0) {
+                int best = (int)(philox_first(ukey, (unsigned long long)ctr++, 0u) % (unsigned)n);
+                float best_w = s_w[best];
+                for (int j = 0; j < n; ++j)
+                    if (s_w[j] > best_w) { best_w = s_w[j]; best = j; }
+                s_leaf = nodes[node].first_child + best;
+            }
+            __syncthreads();
+            if (s_err) break;
+        }
+        const int leaf = s_leaf;
+        const int np = nodes[leaf].upnext;
+        if (s_err == 0 && np >= 0 && (int)threadIdx.x < g.n_cand) s_keys[threadIdx.x] = legal_move_key(g, nodes[leaf].st, np, threadIdx.x);
+        for (int i = threadIdx.x; i < HK_MAX_ACTIONS; i += blockDim.x) {
+            s_vis[i] = 0; s_nan[i] = 0;
+            for (int k = 0; k < HK_MAX_KARTS; ++k) s_rsum[i][k] = 0.0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
             s_cnt = 0;
-            const TreeNode& lf = nodes[node];
+            const TreeNode& lf = nodes[leaf];
             if (s_err == 0) {
-                if (lf.upnext < 0) s_err = 1;                                    // ArgumentOutOfRangeException at KartDiscreteGame.cs:326
+                if (np < 0) s_err = 1;                                           // ArgumentOutOfRangeException at KartDiscreteGame.cs:326
                 else {
                     float scores[2 * HK_MAX_KARTS];
-                    int ns;
-                    const int cnt = legal_moves(g, lf.st, lf.upnext, s_keys);
-                    if (is_over(g, lf.st, cnt, lf.upnext, scores, ns)) {         // terminal leaf: simulate() returns at once (:246-249)
-                        for (int n = node; n >= 0; n = nodes[n].parent) {
+                    int ns, cnt = 0;
+                    for (int gi = 0; gi < g.n_cand; ++gi) cnt += s_keys[gi] != ~0ull;
+                    if (is_over(g, lf.st, cnt, np, scores, ns)) {                // terminal leaf: simulate() returns at once (:246-249)
+                        for (int n = leaf; n >= 0; n = nodes[n].parent) {
                             const int up = nodes[n].upnext;
                             if (up >= 0 && up < ns) nodes[n].total += (double)scores[up];
                             nodes[n].episodes += 1;
@@ -676,14 +718,11 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
                     } else s_stop = 1;                                           // slab full: the search ends here
                 }
             }
-        }
-        for (int i = threadIdx.x; i < HK_MAX_ACTIONS; i += blockDim.x) {
-            s_vis[i] = 0; s_nan[i] = 0;
-            for (int k = 0; k < HK_MAX_KARTS; ++k) s_rsum[i][k] = 0.0;
+            s_leaf = 0;                                                          // the next walk starts at the root
         }
         __syncthreads();
         if (s_err || s_stop) break;
-        const int cnt = s_cnt, first = s_first, leaf = s_leaf;
+        const int cnt = s_cnt, first = s_first;
         if (cnt == 0) { __syncthreads(); continue; }                             // terminal leaf handled above (uniform); s_* are rewritten next
         // children in generation order (initials[j] = new KartMCTSNode(node.state.makeMove(action), node), :142)
         if (threadIdx.x < g.n_cand && s_keys[threadIdx.x] != ~0ull) {
@@ -691,7 +730,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
             for (int j = 0; j < (int)threadIdx.x; ++j) rank += s_keys[j] != ~0ull;
             TreeNode& c = nodes[first + rank];
             c.st = nodes[leaf].st;
-            make_move(g, c.st, nodes[leaf].upnext, action_of(g, threadIdx.x));
+            make_move(g, c.st, np, action_of(g, threadIdx.x));
             c.total = 0.0; c.episodes = 0; c.parent = leaf; c.first_child = -1; c.n_children = 0;
             c.upnext = up_next(c.st);
         }
@@ -715,33 +754,43 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
                 if (scores[k] != 0.0f) atomicAdd(&s_rsum[j][k], (double)scores[k]);
         }
         __syncthreads();
+        // backpropagate (:280-289).  What child j adds to every node of its chain — entry upNext() of its reward sums and its
+        // episode count; a terminal child its own scores, R times — is formed by thread j, which also settles the child itself;
+        // thread 0 then updates the shared ancestors once each, adding the children's contributions in order j (the order of the
+        // reference's loop, so every node sees the same sequence of additions).
+        if ((int)threadIdx.x < cnt) {
+            const int j = threadIdx.x;
+            TreeNode& cn = nodes[first + j];
+            int count;
+            if (s_vis[j] == 0) {                                                 // terminal child: its own scores, R times
+                float scores[2 * HK_MAX_KARTS];
+                int ns = 0;
+                if (cn.upnext >= 0) {
+                    int cc = 0;
+                    for (int gi = 0; gi < g.n_cand; ++gi) cc += legal_move_key(g, cn.st, cn.upnext, gi) != ~0ull;
+                    is_over(g, cn.st, cc, cn.upnext, scores, ns);
+                }
+                for (int k = 0; k < HK_MAX_KARTS; ++k) s_rsum[j][k] = k < ns ? (double)scores[k] * R : 0.0;
+                count = R;
+            } else count = (int)(s_vis[j] - s_nan[j]);
+            s_vis[j] = (unsigned)count;
+            const int up = cn.upnext;
+            if (up >= 0 && up < HK_MAX_KARTS) cn.total += s_rsum[j][up];
+            cn.episodes += count;
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
             nodes[leaf].first_child = first; nodes[leaf].n_children = cnt;
             s_nnodes = first + cnt;
-            for (int j = 0; j < cnt; ++j) {                                      // backpropagate (:280-289)
-                const int child = first + j;
-                if (s_vis[j] == 0) {                                             // terminal child: its own scores, R times
-                    float scores[2 * HK_MAX_KARTS];
-                    int ns = 0;
-                    const TreeNode& cn = nodes[child];
-                    if (cn.upnext >= 0) {
-                        unsigned long long keys[HK_MAX_ACTIONS];
-                        const int cc = legal_moves(g, cn.st, cn.upnext, keys);
-                        is_over(g, cn.st, cc, cn.upnext, scores, ns);
-                    }
-                    for (int n = child; n >= 0; n = nodes[n].parent) {
-                        const int up = nodes[n].upnext;
-                        if (up >= 0 && up < ns) nodes[n].total += (double)scores[up] * R;
-                        nodes[n].episodes += R;
-                    }
-                    continue;
+            for (int n = leaf; n >= 0; n = nodes[n].parent) {
+                const int up = nodes[n].upnext;
+                double t = nodes[n].total;
+                int e = nodes[n].episodes;
+                for (int j = 0; j < cnt; ++j) {
+                    if (up >= 0 && up < HK_MAX_KARTS) t += s_rsum[j][up];
+                    e += (int)s_vis[j];
                 }
-                const int c = (int)(s_vis[j] - s_nan[j]);
-                for (int n = child; n >= 0; n = nodes[n].parent) {
-                    const int up = nodes[n].upnext;
-                    if (up >= 0 && up < HK_MAX_KARTS) nodes[n].total += s_rsum[j][up];
-                    nodes[n].episodes += c;
-                }
+                nodes[n].total = t; nodes[n].episodes = e;
             }
         }
         __syncthreads();
