@@ -113,6 +113,27 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (what `numactl --cpunodebind` per rank does): the pinned
+    staging buffers of the e2e leg are then first-touched on the GPU's own NUMA node.  Returns (cpus bound to, all cpus allowed)."""
+    allowed = os.sched_getaffinity(0)
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis else index
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        words = (max(allowed) + 64) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        local = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1} & allowed
+        if local and local != allowed:
+            os.sched_setaffinity(0, local)
+            return sorted(local), sorted(allowed)
+    except Exception:
+        pass
+    return sorted(allowed), sorted(allowed)
+
+
 def cpu_baseline(seconds: float = 12.0, threads: int | None = None):
     """The oracle port of the reference solver on the host cores, bounded sample of the same workload."""
     from hierarchicalkarting_b200 import scenarios as S
@@ -209,6 +230,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    bound_cpus, all_cpus = bind_to_gpu_numa(local)                          # before any pinned allocation
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -599,6 +621,8 @@ def main():
                           "api": "hk_lqng_solve_batch: dense A,B,Q,q,R,x0 records from pinned host buffers (PCIe-bound)"}},
         "single_solve_latency_us": single_us,        # BASELINE config 1 through hk_lqng_solve_one (pageable host pointers, H2D + kernel + D2H + sync)
         "gpu_launches": gpu_launches, "clocks": clocks,
+        "cpu_affinity": {"bound": len(bound_cpus), "allowed": len(all_cpus),
+                         "note": "process pinned to the CPUs NVML reports local to its GPU (numactl-style) for every leg but cpu_baseline"},
         "summary": {"status_nonzero": summary[0].item(), "u0_checksum": summary[1].item(), "problems": summary[2].item()},
     }
     if mcts_obj:
@@ -612,6 +636,7 @@ def main():
     if lqng4_obj:
         line["lqng4"] = lqng4_obj
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)                                      # the CPU baseline gets every core of the box
         line["cpu_baseline"] = cpu_baseline()
     emit(line)
     if world > 1:
