@@ -638,7 +638,7 @@ __device__ int ucs_pick(const TreeNode* nodes, int node, unsigned long long key,
 constexpr int TREE_THREADS = 128;
 
 __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ roots,
-                                                                   int iterations, int R, unsigned long long seed, int max_nodes,
+                                                                   int iterations, int R, unsigned long long seed, int root_base, int max_nodes,
                                                                    TreeNode* __restrict__ slabs, hk_game_state* __restrict__ best_out,
                                                                    int* __restrict__ n_best_out, int* __restrict__ root_episodes,
                                                                    double* __restrict__ root_values, int* __restrict__ n_nodes_out,
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
     }
     const int root = blockIdx.x;
     TreeNode* nodes = slabs + (size_t)root * max_nodes;
-    const unsigned long long rseed = seed + (unsigned long long)root;           // rollouts of root r: Philox key seed + r
+    const unsigned long long rseed = seed + (unsigned long long)(root_base + root);   // rollouts of root r: Philox key seed + r
     const unsigned long long ukey = rseed ^ 0x9E3779B97F4A7C15ull;               // stream of the tie-breaking picks
     unsigned ctr = 0;                                                            // thread 0 only
     if (threadIdx.x == 0) {
@@ -1122,28 +1122,35 @@ extern "C" int hk_mcts_search_batch(const hk_game* g, const hk_game_state* roots
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
     const int max_nodes = 1 + iterations * HK_MAX_ACTIONS;
-    const size_t nA = (size_t)n_roots * HK_MAX_ACTIONS;
-    const size_t sz[8] = {sizeof(hk_game_state) * n_roots, sizeof(TreeNode) * (size_t)n_roots * max_nodes,
-                          sizeof(hk_game_state) * (size_t)n_roots * HK_MCTS_MAX_SEQ, 4 * (size_t)n_roots, 4 * nA, 8 * nA, 4 * (size_t)n_roots,
-                          4 * (size_t)n_roots};
+    // chunks of roots: the tree slabs of one chunk stay below ~2 GB whatever the batch (1,184 thread blocks are resident at a time)
+    long long per_chunk = (long long)(2.0e9 / ((double)sizeof(TreeNode) * max_nodes));
+    if (per_chunk < 2368) per_chunk = 2368;
+    const int chunk = (int)(per_chunk < n_roots ? per_chunk : n_roots);
+    const size_t nA = (size_t)chunk * HK_MAX_ACTIONS;
+    const size_t sz[8] = {sizeof(hk_game_state) * chunk, sizeof(TreeNode) * (size_t)chunk * max_nodes,
+                          sizeof(hk_game_state) * (size_t)chunk * HK_MCTS_MAX_SEQ, 4 * (size_t)chunk, 4 * nA, 8 * nA, 4 * (size_t)chunk,
+                          4 * (size_t)chunk};
     size_t off[9]; off[0] = 0;
     for (int i = 0; i < 8; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
     char* d = (char*)dscratch(c, 0, off[8]);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
-    HK_CUDA(cudaMemcpyAsync(d, roots, sz[0], cudaMemcpyHostToDevice, c->stream));
-    HK_CUDA(cudaMemsetAsync(d + off[2], 0, sz[2], c->stream));                 // entries past n_best stay zero
-    count_launch();
-    tree_search_kernel<<<(unsigned)n_roots, TREE_THREADS, 0, c->stream>>>(g->dev, (const hk_game_state*)d, iterations, rollouts_per_leaf, seed, max_nodes,
-        (TreeNode*)(d + off[1]), (hk_game_state*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (double*)(d + off[5]),
-        (int*)(d + off[6]), (int*)(d + off[7]));
-    HK_CUDA(cudaGetLastError());
     std::vector<int> st((size_t)n_roots);
-    HK_CUDA(cudaMemcpyAsync(best_states, d + off[2], sz[2], cudaMemcpyDeviceToHost, c->stream));
-    HK_CUDA(cudaMemcpyAsync(n_best, d + off[3], sz[3], cudaMemcpyDeviceToHost, c->stream));
-    if (root_episodes) HK_CUDA(cudaMemcpyAsync(root_episodes, d + off[4], sz[4], cudaMemcpyDeviceToHost, c->stream));
-    if (root_values) HK_CUDA(cudaMemcpyAsync(root_values, d + off[5], sz[5], cudaMemcpyDeviceToHost, c->stream));
-    if (n_nodes) HK_CUDA(cudaMemcpyAsync(n_nodes, d + off[6], sz[6], cudaMemcpyDeviceToHost, c->stream));
-    HK_CUDA(cudaMemcpyAsync(st.data(), d + off[7], sz[7], cudaMemcpyDeviceToHost, c->stream));
+    for (int base = 0; base < n_roots; base += chunk) {
+        const int nr = base + chunk <= n_roots ? chunk : n_roots - base;
+        HK_CUDA(cudaMemcpyAsync(d, roots + base, sizeof(hk_game_state) * nr, cudaMemcpyHostToDevice, c->stream));
+        HK_CUDA(cudaMemsetAsync(d + off[2], 0, sz[2], c->stream));             // entries past n_best stay zero
+        count_launch();
+        tree_search_kernel<<<(unsigned)nr, TREE_THREADS, 0, c->stream>>>(g->dev, (const hk_game_state*)d, iterations, rollouts_per_leaf, seed, base,
+            max_nodes, (TreeNode*)(d + off[1]), (hk_game_state*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (double*)(d + off[5]),
+            (int*)(d + off[6]), (int*)(d + off[7]));
+        HK_CUDA(cudaGetLastError());
+        HK_CUDA(cudaMemcpyAsync(best_states + (size_t)base * HK_MCTS_MAX_SEQ, d + off[2], sizeof(hk_game_state) * (size_t)nr * HK_MCTS_MAX_SEQ, cudaMemcpyDeviceToHost, c->stream));
+        HK_CUDA(cudaMemcpyAsync(n_best + base, d + off[3], 4 * (size_t)nr, cudaMemcpyDeviceToHost, c->stream));
+        if (root_episodes) HK_CUDA(cudaMemcpyAsync(root_episodes + (size_t)base * HK_MAX_ACTIONS, d + off[4], 4 * (size_t)nr * HK_MAX_ACTIONS, cudaMemcpyDeviceToHost, c->stream));
+        if (root_values) HK_CUDA(cudaMemcpyAsync(root_values + (size_t)base * HK_MAX_ACTIONS, d + off[5], 8 * (size_t)nr * HK_MAX_ACTIONS, cudaMemcpyDeviceToHost, c->stream));
+        if (n_nodes) HK_CUDA(cudaMemcpyAsync(n_nodes + base, d + off[6], 4 * (size_t)nr, cudaMemcpyDeviceToHost, c->stream));
+        HK_CUDA(cudaMemcpyAsync(st.data() + base, d + off[7], 4 * (size_t)nr, cudaMemcpyDeviceToHost, c->stream));
+    }
     HK_CUDA(cudaStreamSynchronize(c->stream));
     for (int r = 0; r < n_roots; ++r)
         if (st[r]) { set_error("hk_mcts_search_batch: upNext() == -1 reached in the tree of root %d (KartDiscreteGame.cs:326 would throw)", r); return HK_ERR_NO_UPNEXT; }

@@ -216,3 +216,23 @@ def test_device_tree_search_equals_host_mirror(hk, track_name, n_karts, bucket, 
                 assert bytes(a) == bytes(b.state)
     finally:
         M.KartMCTS.random, M.KartMCTS.rollouts_per_leaf = old_random, old_R
+
+
+def test_device_tree_search_chunks(hk):
+    """hk_mcts_search_batch works through large batches in chunks of roots (bounded tree slabs); root r keeps Philox key seed + r, so
+    the tail of a two-chunk batch equals the same roots searched on their own with the seed shifted."""
+    from hierarchicalkarting_b200 import mcts as M, tracks
+    track = tracks.OVAL
+    G = M.Game(track, 2, 2)
+    base = [tracks.root_state(track, s0 % 24, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 10 * (s0 % 7)]) for s0 in range(40)]
+    n = 3000
+    roots = np.zeros(n, dtype=abi.GAME_STATE_DTYPE)
+    for r in range(n):
+        roots[r] = np.frombuffer(bytes(base[r % 40]), dtype=abi.GAME_STATE_DTYPE)[0]
+    K, R, seed = 80, 4, 99                                  # 2,881 nodes per tree: 2,992 roots per chunk
+    big = G.search_batch_array(roots, K, R, seed)
+    tail = G.search_batch_array(roots[2990:], K, R, seed + 2990)
+    for k in ("n_best", "root_episodes", "n_nodes"):
+        assert np.array_equal(big[k][2990:], tail[k]), k
+    assert np.allclose(big["root_values"][2990:], tail["root_values"], rtol=1e-12, atol=1e-12)   # double sums through shared-memory atomics
+    assert big["best"][2990:].tobytes() == tail["best"].tobytes()
