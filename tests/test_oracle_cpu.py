@@ -51,6 +51,20 @@ def test_philox_kat(oracle):
         assert [int(x) for x in oracle.philox(c["seed"], *c["ctr"])] == c["out"]
 
 
+def test_host_philox_matches_the_kat_and_the_oracle(oracle):
+    """mcts.philox_first (the stream behind PhiloxPicks, the host stand-in for the device tree search's tie-breaking picks) is the
+    first word of the same Philox4x32-10: Random123's published vectors where the counter layout allows, the C oracle elsewhere."""
+    from hierarchicalkarting_b200 import mcts as M
+    for c in KAT["philox4x32_10"]:
+        ctr = c["ctr"]
+        if ctr[3] == 0 and len(ctr) == 4:
+            assert M.philox_first(c["seed"], ctr[0] | (ctr[1] << 32), ctr[2]) == c["out"][0]
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        key, cnt, ply = int(rng.integers(0, 2**63)), int(rng.integers(0, 2**63)), int(rng.integers(0, 64))
+        assert M.philox_first(key, cnt, ply) == int(oracle.philox(key, cnt & 0xFFFFFFFF, cnt >> 32, ply, 0)[0])
+
+
 def test_policy_cdf_closed_form(oracle):
     for cnt, pmf in KAT["policy_pmf"].items():
         cdf = oracle.policy_cdf(int(cnt)).astype(np.float64) / 2**32
