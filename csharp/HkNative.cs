@@ -68,6 +68,9 @@ namespace KartGame.AI.Native
         [DllImport(Lib)] public static extern int hk_mcts_search_batch(IntPtr game, HkGameState[] roots, int nRoots, int iterations, int rolloutsPerLeaf,
             ulong seed, [Out] HkGameState[] bestStates, [Out] int[] nBest, [Out] int[] rootEpisodes, [Out] double[] rootValues, [Out] int[] nNodes);
 
+        // the headless loop with the MCTS high level on the device (root states, tree search, waypoint hand-off between two steps)
+        [DllImport(Lib)] public static extern int hk_race_run_mcts(IntPtr track, ref HkRaceParams p, IntPtr game, int iterations, int rolloutsPerLeaf, ulong seed,
+            int nRaces, int firstStep, int nSteps, [In, Out] HkRaceKart[] karts, [In, Out] HkRacePlan[] plans, [Out] double[] uLast, out long lqngStatusNonzero);
         // headless batch races (kinematic plant instead of PhysX)
         [DllImport(Lib)] public static extern int hk_track_create(HkSection[] sections, double[] triggerXz, double[] forwardXz, double[] laneXz,
                                                                   int nSections, out IntPtr track);

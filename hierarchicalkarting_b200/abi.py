@@ -141,6 +141,8 @@ PROTOTYPES = {
     "hk_race_step": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_int, _dp, C.c_void_p, C.c_void_p]),
     "hk_race_plan_fixed": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_void_p, C.c_void_p]),
     "hk_race_run": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, _dp, _lp]),
+    "hk_race_run_mcts": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, _dp, _lp]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libhk_b200.so")

@@ -19,8 +19,8 @@ struct ThreadCtx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t cstream[4] = {nullptr, nullptr, nullptr, nullptr};   // host-to-device copy streams of the chunk pipelines
     cudaEvent_t pev[16] = {};                                 // ring events of the chunk pipelines: [slot] copied in, [8 + slot] drained
-    void* dbuf[12] = {};
-    size_t dcap[12] = {};
+    void* dbuf[16] = {};
+    size_t dcap[16] = {};
     void* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};      // pinned
     size_t hcap[4] = {0, 0, 0, 0};
     bool ready = false;

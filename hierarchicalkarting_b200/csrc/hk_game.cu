@@ -1113,6 +1113,34 @@ extern "C" int hk_mcts_rollouts_multi(const hk_game* g, const hk_game_state* lea
     return rollouts_impl(g, leaves, n_leaves, rollouts_per_leaf, seed, rollout_offset, visit, reward_sum, nan_count, plies_sum);
 }
 
+namespace hk {
+const hk_game_params& game_params_of(const hk_game* g) { return g->host.p; }
+int game_karts_of(const hk_game* g) { return g->host.n_karts; }
+
+int mcts_search_device(const hk_game* g, const hk_game_state* d_roots, int n_roots, int iterations, int rollouts_per_leaf, uint64_t seed,
+                       hk_game_state* d_best, int* d_nbest, int* d_eps, double* d_vals, int* d_nnodes, int* d_status, ThreadCtx* c,
+                       cudaStream_t s)
+{
+    const int max_nodes = 1 + iterations * HK_MAX_ACTIONS;
+    // chunks of roots: the tree slabs of one chunk stay below ~2 GB whatever the batch (1,184 thread blocks are resident at a time)
+    long long per_chunk = (long long)(2.0e9 / ((double)sizeof(TreeNode) * max_nodes));
+    if (per_chunk < 2368) per_chunk = 2368;
+    const int chunk = (int)(per_chunk < n_roots ? per_chunk : n_roots);
+    TreeNode* slabs = (TreeNode*)dscratch(c, 12, sizeof(TreeNode) * (size_t)chunk * max_nodes);
+    if (!slabs) return HK_ERR_OUT_OF_MEMORY;
+    HK_CUDA(cudaMemsetAsync(d_best, 0, sizeof(hk_game_state) * (size_t)n_roots * HK_MCTS_MAX_SEQ, s));   // entries past n_best stay zero
+    for (int base = 0; base < n_roots; base += chunk) {
+        const int nr = base + chunk <= n_roots ? chunk : n_roots - base;
+        count_launch();
+        tree_search_kernel<<<(unsigned)nr, TREE_THREADS, 0, s>>>(g->dev, d_roots + base, iterations, rollouts_per_leaf, seed, base, max_nodes, slabs,
+            d_best + (size_t)base * HK_MCTS_MAX_SEQ, d_nbest + base, d_eps ? d_eps + (size_t)base * HK_MAX_ACTIONS : nullptr,
+            d_vals ? d_vals + (size_t)base * HK_MAX_ACTIONS : nullptr, d_nnodes ? d_nnodes + base : nullptr, d_status + base);
+        HK_CUDA(cudaGetLastError());
+    }
+    return HK_OK;
+}
+}  // namespace hk
+
 extern "C" int hk_mcts_search_batch(const hk_game* g, const hk_game_state* roots, int n_roots, int iterations, int rollouts_per_leaf,
                                     uint64_t seed, hk_game_state* best_states, int32_t* n_best, int32_t* root_episodes,
                                     double* root_values, int32_t* n_nodes)
@@ -1121,36 +1149,24 @@ extern "C" int hk_mcts_search_batch(const hk_game* g, const hk_game_state* roots
     for (int r = 0; r < n_roots; ++r) { int rc = check_state(g, &roots[r], "hk_mcts_search_batch"); if (rc) return rc; }
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
-    const int max_nodes = 1 + iterations * HK_MAX_ACTIONS;
-    // chunks of roots: the tree slabs of one chunk stay below ~2 GB whatever the batch (1,184 thread blocks are resident at a time)
-    long long per_chunk = (long long)(2.0e9 / ((double)sizeof(TreeNode) * max_nodes));
-    if (per_chunk < 2368) per_chunk = 2368;
-    const int chunk = (int)(per_chunk < n_roots ? per_chunk : n_roots);
-    const size_t nA = (size_t)chunk * HK_MAX_ACTIONS;
-    const size_t sz[8] = {sizeof(hk_game_state) * chunk, sizeof(TreeNode) * (size_t)chunk * max_nodes,
-                          sizeof(hk_game_state) * (size_t)chunk * HK_MCTS_MAX_SEQ, 4 * (size_t)chunk, 4 * nA, 8 * nA, 4 * (size_t)chunk,
-                          4 * (size_t)chunk};
-    size_t off[9]; off[0] = 0;
-    for (int i = 0; i < 8; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
-    char* d = (char*)dscratch(c, 0, off[8]);
+    const size_t nA = (size_t)n_roots * HK_MAX_ACTIONS;
+    const size_t sz[7] = {sizeof(hk_game_state) * n_roots, sizeof(hk_game_state) * (size_t)n_roots * HK_MCTS_MAX_SEQ, 4 * (size_t)n_roots, 4 * nA, 8 * nA,
+                          4 * (size_t)n_roots, 4 * (size_t)n_roots};
+    size_t off[8]; off[0] = 0;
+    for (int i = 0; i < 7; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
+    char* d = (char*)dscratch(c, 0, off[7]);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
+    HK_CUDA(cudaMemcpyAsync(d, roots, sz[0], cudaMemcpyHostToDevice, c->stream));
+    int rc = mcts_search_device(g, (const hk_game_state*)d, n_roots, iterations, rollouts_per_leaf, seed, (hk_game_state*)(d + off[1]), (int*)(d + off[2]),
+                                (int*)(d + off[3]), (double*)(d + off[4]), (int*)(d + off[5]), (int*)(d + off[6]), c, c->stream);
+    if (rc) return rc;
     std::vector<int> st((size_t)n_roots);
-    for (int base = 0; base < n_roots; base += chunk) {
-        const int nr = base + chunk <= n_roots ? chunk : n_roots - base;
-        HK_CUDA(cudaMemcpyAsync(d, roots + base, sizeof(hk_game_state) * nr, cudaMemcpyHostToDevice, c->stream));
-        HK_CUDA(cudaMemsetAsync(d + off[2], 0, sz[2], c->stream));             // entries past n_best stay zero
-        count_launch();
-        tree_search_kernel<<<(unsigned)nr, TREE_THREADS, 0, c->stream>>>(g->dev, (const hk_game_state*)d, iterations, rollouts_per_leaf, seed, base,
-            max_nodes, (TreeNode*)(d + off[1]), (hk_game_state*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (double*)(d + off[5]),
-            (int*)(d + off[6]), (int*)(d + off[7]));
-        HK_CUDA(cudaGetLastError());
-        HK_CUDA(cudaMemcpyAsync(best_states + (size_t)base * HK_MCTS_MAX_SEQ, d + off[2], sizeof(hk_game_state) * (size_t)nr * HK_MCTS_MAX_SEQ, cudaMemcpyDeviceToHost, c->stream));
-        HK_CUDA(cudaMemcpyAsync(n_best + base, d + off[3], 4 * (size_t)nr, cudaMemcpyDeviceToHost, c->stream));
-        if (root_episodes) HK_CUDA(cudaMemcpyAsync(root_episodes + (size_t)base * HK_MAX_ACTIONS, d + off[4], 4 * (size_t)nr * HK_MAX_ACTIONS, cudaMemcpyDeviceToHost, c->stream));
-        if (root_values) HK_CUDA(cudaMemcpyAsync(root_values + (size_t)base * HK_MAX_ACTIONS, d + off[5], 8 * (size_t)nr * HK_MAX_ACTIONS, cudaMemcpyDeviceToHost, c->stream));
-        if (n_nodes) HK_CUDA(cudaMemcpyAsync(n_nodes + base, d + off[6], 4 * (size_t)nr, cudaMemcpyDeviceToHost, c->stream));
-        HK_CUDA(cudaMemcpyAsync(st.data() + base, d + off[7], 4 * (size_t)nr, cudaMemcpyDeviceToHost, c->stream));
-    }
+    HK_CUDA(cudaMemcpyAsync(best_states, d + off[1], sz[1], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaMemcpyAsync(n_best, d + off[2], sz[2], cudaMemcpyDeviceToHost, c->stream));
+    if (root_episodes) HK_CUDA(cudaMemcpyAsync(root_episodes, d + off[3], sz[3], cudaMemcpyDeviceToHost, c->stream));
+    if (root_values) HK_CUDA(cudaMemcpyAsync(root_values, d + off[4], sz[4], cudaMemcpyDeviceToHost, c->stream));
+    if (n_nodes) HK_CUDA(cudaMemcpyAsync(n_nodes, d + off[5], sz[5], cudaMemcpyDeviceToHost, c->stream));
+    HK_CUDA(cudaMemcpyAsync(st.data(), d + off[6], sz[6], cudaMemcpyDeviceToHost, c->stream));
     HK_CUDA(cudaStreamSynchronize(c->stream));
     for (int r = 0; r < n_roots; ++r)
         if (st[r]) { set_error("hk_mcts_search_batch: upNext() == -1 reached in the tree of root %d (KartDiscreteGame.cs:326 would throw)", r); return HK_ERR_NO_UPNEXT; }

@@ -1,5 +1,6 @@
 // hk_game.cuh — device-resident immutable description of one discrete race game (track + karts + parameters).
 #pragma once
+#include <cuda_runtime.h>
 #include "../../include/hk_abi.h"
 
 #define HK_MAX_SECTIONS 64
@@ -34,5 +35,14 @@ struct DevGame {
 static_assert(sizeof(DevGame) % 4 == 0, "DevGame is copied word-wise");
 
 void policy_cdf_host(int cnt, uint32_t* cdf);
+
+struct ThreadCtx;
+// hk_mcts_search_batch on device pointers (all of them for n_roots roots; d_eps / d_vals / d_nnodes may be null): chunks of roots, tree
+// slabs in the calling thread's scratch slot 12, everything enqueued on `s`.  d_status[r] = 1 where upNext() == -1 was reached.
+int mcts_search_device(const hk_game* g, const hk_game_state* d_roots, int n_roots, int iterations, int rollouts_per_leaf, uint64_t seed,
+                       hk_game_state* d_best, int* d_nbest, int* d_eps, double* d_vals, int* d_nnodes, int* d_status, ThreadCtx* c,
+                       cudaStream_t s);
+const hk_game_params& game_params_of(const hk_game* g);
+int game_karts_of(const hk_game* g);
 
 }  // namespace hk

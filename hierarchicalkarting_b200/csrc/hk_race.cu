@@ -9,7 +9,9 @@
 // Mathf.Atan2, Mathf.Pow weights) must round exactly like the reference's scalar code, an FMA would move avoid weights by
 // one float ulp (6e-8), far above the 1e-9 parity bar.  Unity's Mathf.X(float) is (float)Math.X(double).
 #include "hk_common.cuh"
+#include "hk_game.cuh"
 #include <cmath>
+#include <vector>
 
 namespace hk {
 
@@ -349,8 +351,75 @@ extern "C" int hk_race_step(const hk_track* t, const hk_race_params* p, int n_ka
     return HK_OK;
 }
 
-extern "C" int hk_race_run(const hk_track* t, const hk_race_params* p, int n_races, int first_step, int n_steps, hk_race_kart* karts,
-                           hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero)
+namespace hk {
+
+// planWithMCTS's root state for every agent (HierarchicalKartAgent.cs:180-245): agent id = 2 race + ego; the karts within
+// sectionWindow sections of the ego, all placed at the furthest one's section with the time they trail it by (float32 product, :211-214),
+// velocity bucket (0, bucket) (quirk B.6-1), player 0 (B.6-2), tyre age from the steering stat.  nearby[id][i] = race-local agent of
+// game kart i, -1 = none.  Same arithmetic as race.mcts_root_state / mcts_root_states_batch.
+__global__ void race_mcts_root_kernel(const DevTrack* __restrict__ tr, hk_race_params p, int section_window, int time_precision, int n_agents,
+                                      const hk_race_kart* __restrict__ karts, const hk_race_plan* __restrict__ plans,
+                                      hk_game_state* __restrict__ roots, int* __restrict__ nearby)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_agents) return;
+    const int r2 = id & ~1, e = id & 1, L = tr->n;
+    const int sec0 = karts[r2].section, sec1 = karts[r2 + 1].section, sec_e = e ? sec1 : sec0, sec_o = e ? sec0 : sec1;
+    const bool near = abs(sec_o - sec_e) < section_window;
+    const int initial = near ? max(sec0, sec1) : sec_e;
+    const int furthest = near ? (sec1 >= sec0 ? 1 : 0) : e;
+    hk_game_state st;
+    st.n_karts = near ? 2 : 1;
+    st.initialSection = initial; st.lastCompletedSection = initial; st.finalSection = initial + p.treeSearchDepth;
+    for (int slot = 0; slot < HK_MAX_KARTS; ++slot) {
+        hk_kart_state ks = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const bool valid = slot < 2 && (near || slot == 0);
+        if (valid) {
+            const int a = near ? slot : e;
+            const hk_race_kart& k = karts[r2 + a];
+            int t_at = 0;
+            if (k.section != initial) {
+                const int d = plans[r2 + a].sectionTimes[k.section % L] - plans[r2 + furthest].sectionTimes[k.section % L];
+                t_at = (int)(((float)d * 0.02f) * (float)time_precision);
+            }
+            const float wear = (4.0f - k.steer) / 3.0f;                          // (maxSteer - steer) / (maxSteer - minSteer), ArcadeKart.cs:300-306
+            ks.player = 0; ks.team = a; ks.section = initial; ks.timeAtSection = t_at; ks.min_velocity = 0;
+            ks.max_velocity = min(p.velocityBucketSize, (int)p.topSpeed); ks.lane = k.lane; ks.tireAge = (int)(wear * 10000.0f);
+            ks.laneChanges = k.laneChanges; ks.infeasible = 0;
+            nearby[id * 2 + slot] = a;
+        } else if (slot < 2) nearby[id * 2 + slot] = -1;
+        st.karts[slot] = ks;
+    }
+    roots[id] = st;
+}
+
+// The waypoint hand-off of FixedUpdate (HierarchicalKartAgent.cs:366-402) from getBestStatesSequence: the ego's own lanes / velocities
+// for sections beyond the next checkpoint, and its belief about the other kart's.  Same as race.apply_best_states(_batch).
+__global__ void race_mcts_apply_kernel(const DevTrack* __restrict__ tr, int n_agents, const hk_race_kart* __restrict__ karts,
+                                       const int* __restrict__ nearby, const hk_game_state* __restrict__ best, const int* __restrict__ n_best,
+                                       hk_race_plan* __restrict__ plans)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_agents) return;
+    const int e = id & 1, L = tr->n, sec = karts[id].section, bound = sec + (sec == 0 ? 0 : 1);
+    hk_race_plan& pl = plans[id];
+    for (int k = 0; k < n_best[id]; ++k) {
+        const hk_game_state& gs = best[(size_t)id * HK_MCTS_MAX_SEQ + k];
+        for (int slot = 0; slot < gs.n_karts && slot < 2; ++slot) {
+            const hk_kart_state& ks = gs.karts[slot];
+            const int who = nearby[id * 2 + slot], key = ks.section % L;
+            if (who == e) {
+                if (ks.section > bound) { pl.lane[key] = (int8_t)ks.lane; pl.vel[key] = (float)ks.max_velocity; }
+            } else if (who >= 0) { pl.oppLane[key] = (int8_t)ks.lane; pl.oppVel[key] = (float)ks.max_velocity; }
+        }
+    }
+}
+
+}  // namespace hk
+
+static int race_run_impl(const hk_track* t, const hk_race_params* p, const hk_game* game, int mcts_iterations, int mcts_rollouts, uint64_t mcts_seed,
+                         int n_races, int first_step, int n_steps, hk_race_kart* karts, hk_race_plan* plans, double* u_last,
+                         int64_t* lqng_status_nonzero)
 {
     int rc = check_track(t, p, "hk_race_run");
     if (rc) return rc;
@@ -378,11 +447,37 @@ extern "C" int hk_race_run(const hk_track* t, const hk_race_params* p, int n_rac
     HK_CUDA(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
     HK_CUDA(cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), s));
     const unsigned blocks = (unsigned)((nb + 127) / 128);
+    // MCTS high level on the device (hk_race_run_mcts): root states, tree search, waypoint hand-off — nothing crosses PCIe
+    hk_game_state *mroots = nullptr, *mbest = nullptr;
+    int *mnear = nullptr, *mnbest = nullptr, *mstatus = nullptr;
+    if (game && p->highModeMcts) {
+        const size_t sz[5] = {sizeof(hk_game_state) * nb, sizeof(hk_game_state) * nb * HK_MCTS_MAX_SEQ, 8 * nb, 4 * nb, 4 * nb};
+        size_t off[6]; off[0] = 0;
+        for (int i = 0; i < 5; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
+        char* m = (char*)dscratch(c, 13, off[5]);
+        if (!m) return HK_ERR_OUT_OF_MEMORY;
+        mroots = (hk_game_state*)m; mbest = (hk_game_state*)(m + off[1]); mnear = (int*)(m + off[2]); mnbest = (int*)(m + off[3]); mstatus = (int*)(m + off[4]);
+        HK_CUDA(cudaMemsetAsync(mstatus, 0, sz[4], s));
+    }
+    int plan_events = 0;
     for (int step = first_step; step < first_step + n_steps; ++step) {
-        if (step > 0 && step % p->planEvery == 0 && !p->highModeMcts) {   // HKA:331-353 (0.5 Hz): planFixed, or planWithMCTS — the caller's
-                                                                         // (Races.plan_mcts_batch over hk_mcts_search_batch) between two runs
-            count_launch();
-            race_plan_fixed_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp);
+        if (step > 0 && step % p->planEvery == 0) {                      // HKA:331-353 (0.5 Hz): planFixed or planWithMCTS by mode
+            if (!p->highModeMcts) {
+                count_launch();
+                race_plan_fixed_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp);
+            } else if (game) {
+                const hk_game_params& gp = game_params_of(game);
+                count_launch();
+                race_mcts_root_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, gp.sectionWindow, gp.timePrecision, (int)nb, dk, dp, mroots, mnear);
+                HK_CUDA(cudaGetLastError());
+                rc = mcts_search_device(game, mroots, (int)nb, mcts_iterations, mcts_rollouts, mcts_seed + (uint64_t)plan_events * (uint64_t)nb, mbest,
+                                        mnbest, nullptr, nullptr, nullptr, mstatus, c, s);
+                if (rc) return rc;
+                count_launch();
+                race_mcts_apply_kernel<<<blocks, 128, 0, s>>>(t->dev, (int)nb, dk, mnear, mbest, mnbest, dp);
+                HK_CUDA(cudaGetLastError());
+                ++plan_events;
+            }                                                            // MCTS mode without a game: the caller plans between two runs
         }
         count_launch();
         race_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp, dx0, dtg, dtw, dcw, daw, dot, dow);
@@ -405,7 +500,26 @@ extern "C" int hk_race_run(const hk_track* t, const hk_race_params* p, int n_rac
         HK_CUDA(cudaStreamSynchronize(s));
         for (size_t b = 0; b < nb; ++b) { u_last[b * 2] = hu[b * 4]; u_last[b * 2 + 1] = hu[b * 4 + 1]; }
     }
+    std::vector<int> mst;
+    if (mstatus && plan_events) { mst.resize(nb); HK_CUDA(cudaMemcpyAsync(mst.data(), mstatus, 4 * nb, cudaMemcpyDeviceToHost, s)); }
     HK_CUDA(cudaStreamSynchronize(s));
     if (lqng_status_nonzero) *lqng_status_nonzero = (int64_t)count;
+    for (size_t a = 0; a < mst.size(); ++a)
+        if (mst[a]) { set_error("hk_race_run_mcts: upNext() == -1 reached in the tree of agent %zu (KartDiscreteGame.cs:326 would throw)", a); return HK_ERR_NO_UPNEXT; }
     return HK_OK;
+}
+
+extern "C" int hk_race_run(const hk_track* t, const hk_race_params* p, int n_races, int first_step, int n_steps, hk_race_kart* karts,
+                           hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero)
+{
+    return race_run_impl(t, p, nullptr, 0, 0, 0, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
+}
+
+extern "C" int hk_race_run_mcts(const hk_track* t, const hk_race_params* p, const hk_game* game, int iterations, int rollouts_per_leaf,
+                                uint64_t seed, int n_races, int first_step, int n_steps, hk_race_kart* karts, hk_race_plan* plans,
+                                double* u_last, int64_t* lqng_status_nonzero)
+{
+    if (!game || iterations < 0 || rollouts_per_leaf < 1 || !p || !p->highModeMcts) { set_error("hk_race_run_mcts: needs a game, highModeMcts = 1, rollouts_per_leaf >= 1"); return HK_ERR_INVALID_ARGUMENT; }
+    if (game_karts_of(game) < 2) { set_error("hk_race_run_mcts: the game must have at least 2 karts"); return HK_ERR_INVALID_ARGUMENT; }
+    return race_run_impl(t, p, game, iterations, rollouts_per_leaf, seed, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
 }

@@ -116,6 +116,18 @@ class Races:
         return u, bad.value
 
 
+    def run_mcts(self, karts: np.ndarray, plans: np.ndarray, game, iterations: int, rollouts_per_leaf: int, seed: int, first_step: int,
+                 n_steps: int):
+        """hk_race_run_mcts: the loop with the MCTS high level entirely on the GPU (root states, tree search, waypoint hand-off between
+        two steps whenever episodeSteps % planEvery == 0).  `game` is a hierarchicalkarting_b200.mcts.Game for this track."""
+        n_races = karts.shape[0]
+        u = np.zeros((n_races, 2, 2))
+        bad = C.c_int64(0)
+        abi.check(abi.load_library().hk_race_run_mcts(self._h, C.byref(self.params), game._h, iterations, rollouts_per_leaf, seed, n_races,
+                                                      first_step, n_steps, abi.vptr(karts), abi.vptr(plans), abi.dptr(u), C.byref(bad)))
+        return u, bad.value
+
+
 # ---- MCTS high level: root state and waypoint hand-off (SURVEY.md §8f rank 3) ----------------------------------------
 def mcts_root_state(track: Track, params: abi.hk_race_params, karts_race: np.ndarray, plans_race: np.ndarray, ego: int,
                     section_window: int = 2, time_precision: int = 100):

@@ -306,6 +306,17 @@ int hk_race_plan_fixed(const hk_track* t, const hk_race_params* p, int n_karts, 
 int hk_race_run(const hk_track* t, const hk_race_params* p, int n_races, int first_step, int n_steps,
                 hk_race_kart* karts, hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero);
 
+/*
+ * The same loop with the MCTS high level (HighLevelMode.MCTS, HierarchicalKartAgent.cs:331-353; p->highModeMcts must be 1): when
+ * episodeSteps % planEvery == 0 and > 0 every agent replans by planWithMCTS (:180-283) + the waypoint hand-off (:366-402) ON THE
+ * DEVICE — root states, hk_mcts_search_batch's tree search (`iterations` x `rollouts_per_leaf`, one thread block per agent's tree)
+ * and the hand-off are kernels between two steps; karts / plans cross PCIe only at the start and the end of the call.  The k-th
+ * planning event of the call searches agent a (= 2 race + ego) as root index k * 2 n_races + a of `seed` (hk_mcts_search_batch).
+ */
+int hk_race_run_mcts(const hk_track* t, const hk_race_params* p, const hk_game* game, int iterations, int rollouts_per_leaf,
+                     uint64_t seed, int n_races, int first_step, int n_steps, hk_race_kart* karts, hk_race_plan* plans,
+                     double* u_last, int64_t* lqng_status_nonzero);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,3 +184,27 @@ def test_batched_mcts_planning_equals_per_agent_host_search(hk):
     before = karts["section"].copy()
     _, bad = G.run(karts, pa, 100, 300)                             # MCTS mode: hk_race_run does not replan with planFixed
     assert bad == 0 and np.all(karts["section"] >= before + 4)
+
+
+def test_device_resident_mcts_loop_equals_host_composition(hk):
+    """hk_race_run_mcts (root states, tree search and waypoint hand-off as kernels between two steps) leaves exactly the karts and plan
+    tables of the host composition run / plan_mcts_batch / run / ... with the seeds shifted per planning event."""
+    from hierarchicalkarting_b200 import mcts as M
+    track = S.OVAL
+    prm = R.race_params(track, high_mode_mcts=True)
+    G = R.Races(track, prm)
+    game = M.Game(track, 2, prm.velocityBucketSize)
+    n_races, K, RPL, seed = 50, 24, 16, 4242
+    ka, pa = R.start_grid(track, n_races, seed=43)
+    kb, pb = ka.copy(), pa.copy()
+    _, bad = G.run_mcts(ka, pa, game, K, RPL, seed, 0, 300)
+    assert bad == 0
+    for ev in range(3):
+        G.run(kb, pb, 100 * ev, 100)
+        if ev < 2:
+            R.plan_mcts_batch(track, prm, game, kb, pb, K, RPL, seed + ev * 2 * n_races)
+    for f in ka.dtype.names:
+        assert np.array_equal(ka[f], kb[f]), f
+    for f in pa.dtype.names:
+        assert np.array_equal(pa[f], pb[f]), f
+    assert ((pa["lane"] != 0) | (pa["oppLane"] != 0)).any() and ka["section"].min() >= 4     # waypoints were handed off, the karts drove on
