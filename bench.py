@@ -344,6 +344,40 @@ def main():
     e2e_s = timed(step_e2e)
     e2e_dense_s = timed(step_e2e_dense)
 
+    # what this box's host link gives (the compact e2e call varies 0.57 - 1.4 ms between boxes of the pool at identical code, the 109 MB
+    # dense call does not): one 23 MB pinned H2D copy, and the round trip of a small one
+    def _probe():
+        big_h = torch.empty(compact_bytes // 8, dtype=torch.float64).pin_memory()
+        big_d = torch.empty_like(big_h, device=dev)
+        small_h = torch.empty(1024, dtype=torch.float64).pin_memory()
+        small_d = torch.empty_like(small_h, device=dev)
+        for _ in range(3):
+            big_d.copy_(big_h, non_blocking=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            big_d.copy_(big_h, non_blocking=True)
+        torch.cuda.synchronize()
+        gbs = 10 * compact_bytes / (time.perf_counter() - t0) / 1e9
+        t0 = time.perf_counter()
+        for _ in range(200):
+            small_d.copy_(small_h, non_blocking=True)
+            torch.cuda.synchronize()
+        us = 1e6 * (time.perf_counter() - t0) / 200
+        drv = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            drv = nv.nvmlSystemGetDriverVersion()
+            drv = drv.decode() if isinstance(drv, bytes) else drv
+        except Exception:
+            pass
+        return {"h2d_23mb_gbs": gbs, "h2d_8kb_roundtrip_us": us, "driver": drv}
+    try:
+        box_probe = _probe()
+    except Exception as exc:
+        box_probe = {"error": repr(exc)[:200]}
+
     # ---- MCTS rollouts/s (BASELINE config 4: Complex, 2 karts, 10^6 leaf-parallel rollouts per decision) ------------------
     mcts_obj = None
     if not args.no_mcts:
@@ -546,30 +580,24 @@ def main():
             km, pm = RC.start_grid(S.OVAL, RACES, seed=20260004 + rank)
             RM.run(km, pm, 0, 100)                                              # standing start, no plan yet
             MCTS_K, MCTS_R, blocks_m = 24, 16, 2
-            RC.plan_mcts_batch(S.OVAL, prm_m, game_m, km[:64].copy(), pm[:64].copy(), MCTS_K, MCTS_R, 1)   # warm-up
+            RM.run_mcts(km[:64].copy(), pm[:64].copy(), game_m, MCTS_K, MCTS_R, 1, 100, 101)      # warm-up (one planning event)
             barrier()
             k0m = lib.hk_kernel_launch_count()
-            t_plan = t_run = 0.0
-            n_best_mean = 0.0
-            for b in range(blocks_m):
-                t0 = time.perf_counter()
-                outm = RC.plan_mcts_batch(S.OVAL, prm_m, game_m, km, pm, MCTS_K, MCTS_R, 20260006 + 1000 * rank + b)
-                t1 = time.perf_counter()
-                _, badm = RM.run(km, pm, 100 + 100 * b, 100)
-                t2 = time.perf_counter()
-                t_plan += t1 - t0; t_run += t2 - t1
-                n_best_mean = float(outm["n_best"].mean())
-            el_m = max_over_ranks(t_plan + t_run)
+            t0 = time.perf_counter()
+            _, badm = RM.run_mcts(km, pm, game_m, MCTS_K, MCTS_R, 20260006 + 1000 * rank, 100, 100 * blocks_m)   # plans at steps 100, 200
+            el_m = max_over_ranks(time.perf_counter() - t0)
+            step_ms = race_obj["ms_per_step"] if race_obj else 0.0
             race_mcts_obj = {"metric": "race_agent_steps_per_s", "value": world * 2 * RACES * 100 * blocks_m / el_m, "unit": "agent-steps/s",
-                             "races_per_gpu": RACES, "steps": 100 * blocks_m, "plans_per_s": world * 2 * RACES * blocks_m / max_over_ranks(t_plan),
-                             "ms_per_planning_event": 1e3 * t_plan / blocks_m, "ms_per_step_between_plans": 1e3 * t_run / (100 * blocks_m),
-                             "tree_search": {"iterations": MCTS_K, "rollouts_per_leaf": MCTS_R, "episodes_per_plan": float(outm["root_episodes"].sum(axis=1).mean()),
-                                             "nodes_per_tree": float(outm["n_nodes"].mean()), "best_states_per_plan": n_best_mean},
+                             "races_per_gpu": RACES, "steps": 100 * blocks_m, "planning_events": blocks_m, "ms_total": 1e3 * el_m,
+                             "ms_per_planning_event_derived": (1e3 * el_m - 100 * blocks_m * step_ms) / blocks_m,
+                             "plans_per_s_derived": world * 2 * RACES * blocks_m / max(1e-9, el_m - 1e-3 * 100 * blocks_m * step_ms),
+                             "tree_search": {"iterations": MCTS_K, "rollouts_per_leaf": MCTS_R},
                              "lqng_status_nonzero": int(badm), "gpu_launches": int(lib.hk_kernel_launch_count() - k0m),
-                             "sections_mean": float(km["section"].mean()),
-                             "config": "BASELINE config 5 with the MCTS high level: 2-kart Oval races, every agent replans every 100 steps by "
-                                       "KartMCTS.constructSearchTree + getBestStatesSequence on the GPU (one thread block per tree), root "
-                                       "states and waypoint hand-off vectorised on the host, LQNG every step"}
+                             "sections_mean": float(km["section"].mean()), "waypoints_set": int(((pm["lane"] != 0) | (pm["oppLane"] != 0)).sum()),
+                             "config": "BASELINE config 5 with the MCTS high level, GPU-resident (hk_race_run_mcts): 2-kart Oval races, every agent "
+                                       "replans every 100 steps by KartMCTS.constructSearchTree + getBestStatesSequence (one thread block per "
+                                       "tree), root states and waypoint hand-off as kernels, LQNG every step; one host call incl. the upload "
+                                       "and download of the race states; the planning time is derived from the Fixed-mode step time"}
         except Exception as exc:
             race_mcts_obj = {"error": repr(exc)[:300]}
 
@@ -613,7 +641,7 @@ def main():
                      "hbm": {"achieved": ach_gb, "peak": hbm, "unit": "GB/s", "frac": ach_gb / hbm, "peak_source": hbm_src,
                              "bytes_per_solve": IN_BYTES_PER_SOLVE + OUT_BYTES_PER_SOLVE}},
         "e2e": {"value": world * batch * args.steps / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": compact_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "host_link": box_probe,
                 "api": "hk_lqng_assemble_solve_batch: pinned host buffers holding the reference's provider constructor arguments "
                        "(LinearizedBicycle / LQRCheckpointReachAvoidCost), A,B,Q,q,R assembled on the GPU, u0 + status copied back",
                 "dense": {"value": world * batch * args.steps / e2e_dense_s, "unit": "solves/s", "h2d_bytes_per_step": h2d_bytes,
