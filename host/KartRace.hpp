@@ -53,6 +53,17 @@ public:
         hk_check(hk_race_run(track_, &params_, n_races, first_step, n_steps, karts.data(), plans.data(), u_last ? u_last->data() : nullptr, &bad));
         return bad;
     }
+    // the same loop in HighLevelMode.MCTS (params.highModeMcts = 1): every planEvery steps every agent replans by planWithMCTS + the
+    // waypoint hand-off on the GPU (HierarchicalKartAgent.cs:180-283, 331-353, 366-402); `game` is the hk_game of this track
+    long long runMcts(const hk_game* game, int iterations, int rolloutsPerLeaf, unsigned long long seed, std::vector<hk_race_kart>& karts,
+                      std::vector<hk_race_plan>& plans, int first_step, int n_steps)
+    {
+        if (karts.size() != plans.size() || karts.size() % 2) throw std::invalid_argument("karts / plans must hold 2 entries per race");
+        int64_t bad = 0;
+        hk_check(hk_race_run_mcts(track_, &params_, game, iterations, rolloutsPerLeaf, seed, (int)karts.size() / 2, first_step, n_steps, karts.data(),
+                                  plans.data(), nullptr, &bad));
+        return bad;
+    }
     void planFixed(const std::vector<hk_race_kart>& karts, std::vector<hk_race_plan>& plans)       // HierarchicalKartAgent.cs:145-166
     {
         hk_check(hk_race_plan_fixed(track_, &params_, (int)karts.size(), karts.data(), plans.data()));

@@ -101,6 +101,38 @@ int main(int argc, char** argv)
                 return 1;
             }
     }
+    {   // the MCTS-mode loop on the same ring (8 sections), GPU-resident planning every 100 steps
+        std::vector<Race::Checkpoint> ring;
+        const double cx[8] = {10, 10, 5, -5, -10, -10, -5, 5}, cz[8] = {-5, 5, 10, 10, 5, -5, -10, -10};
+        const double fx[8] = {0, 0, -1, -1, 0, 0, 1, 1}, fz[8] = {1, 1, 0, 0, -1, -1, 0, 0};
+        std::vector<hk_section> gsecs;
+        for (int i = 0; i < 8; ++i) {
+            Race::Checkpoint c{};
+            c.section = hk_section{0, 10, 10, 0, 0, 3};
+            gsecs.push_back(c.section);
+            c.trigger[0] = cx[i]; c.trigger[1] = cz[i]; c.forward[0] = fx[i]; c.forward[1] = fz[i];
+            const double off[4] = {-3.5, -1.25, 1.25, 3.5};
+            for (int l = 0; l < 4; ++l) { c.lane[l][0] = cx[i] + off[l] * fz[i]; c.lane[l][1] = cz[i] - off[l] * fx[i]; }
+            ring.push_back(c);
+        }
+        hk_race_params rp{};
+        rp.dt = (double)0.02f; rp.accel = 7; rp.braking = 16; rp.coastingDrag = 5; rp.topSpeed = 15; rp.gateHalfWidth = 10;
+        rp.maxLaneChanges = 3; rp.goalSection = 64; rp.highModeMcts = 1; rp.velocityBucketSize = 2; rp.treeSearchDepth = 8;
+        rp.planEvery = 100; rp.horizon = 3;
+        Race::HeadlessRaces races(ring, rp);
+        auto gtables = std::make_shared<MCTS::GameTables>(gsecs, karts, std::vector<hk_kart>{}, gp);
+        std::vector<hk_race_kart> rk(4);
+        std::vector<hk_race_plan> pl(4);
+        for (int i = 0; i < 4; ++i) {
+            rk[i] = hk_race_kart{};
+            rk[i].x = 10 + (i % 2 ? 1.25 : -1.25); rk[i].z = -4.0 + 0.3 * (i / 2); rk[i].v = 1.0; rk[i].h = 1.5707963267948966;
+            rk[i].steer = 3.25f; rk[i].section = 0; rk[i].lane = 2 + i % 2; rk[i].active = 1;
+            pl[i] = hk_race_plan{};
+        }
+        const long long bad = races.runMcts(gtables->handle(), 24, 16, 7ull, rk, pl, 0, 250);
+        for (int i = 0; i < 4; ++i)
+            if (bad != 0 || rk[i].section < 2 || !std::isfinite(rk[i].x)) { std::printf("mcts race: kart %d section %d bad %lld\n", i, rk[i].section, bad); return 1; }
+    }
     std::printf("HOST_OK u0=(%.12g, %.12g) episodes=%d plan=%zu\n", u[0], u[1], node.numEpisodes, best.size());
     return 0;
 }
