@@ -33,4 +33,9 @@ assert out["n_nodes"].min() > 1
 RS = RC.Races(S.OVAL, RC.race_params(S.OVAL))
 karts, plans = RC.start_grid(S.OVAL, 64, seed=1)
 RS.run(karts, plans, 0, 5)
+prm_m = RC.race_params(S.OVAL, high_mode_mcts=True)
+RM = RC.Races(S.OVAL, prm_m)
+gm = M.Game(S.OVAL, 2, prm_m.velocityBucketSize)
+km, pm = RC.start_grid(S.OVAL, 16, seed=2)
+RM.run_mcts(km, pm, gm, 6, 4, 5, 0, 102)
 print("sanitize_small ok")
