@@ -236,3 +236,38 @@ def test_device_tree_search_chunks(hk):
         assert np.array_equal(big[k][2990:], tail[k]), k
     assert np.allclose(big["root_values"][2990:], tail["root_values"], rtol=1e-12, atol=1e-12)   # double sums through shared-memory atomics
     assert big["best"][2990:].tobytes() == tail["best"].tobytes()
+
+
+def test_device_tree_search_full_size_properties(hk):
+    """BASELINE config 5's planning event at full size (32,768 agents' trees, 24 iterations x 16 rollouts per leaf) through
+    size-independent properties: tree sizes and episode counts within their bounds, every returned state has all its karts at
+    lastCompletedSection and lies ahead of its root, and the search is reproducible (same seed -> same plans)."""
+    from hierarchicalkarting_b200 import mcts as M, race as R, scenarios as S
+    track = S.OVAL
+    prm = R.race_params(track, high_mode_mcts=True)
+    G = R.Races(track, prm)
+    game = M.Game(track, 2, prm.velocityBucketSize)
+    karts, plans = R.start_grid(track, 16384, seed=20260004)
+    G.run(karts, plans, 0, 100)
+    roots, _ = R.mcts_root_states_batch(track, prm, karts, plans)
+    flat = np.ascontiguousarray(roots.reshape(-1))
+    K, RPL = 24, 16
+    a = game.search_batch_array(flat, K, RPL, 5)
+    b = game.search_batch_array(flat, K, RPL, 5)
+    n = flat.shape[0]
+    assert n == 32768
+    assert a["n_nodes"].min() > 1 and a["n_nodes"].max() <= 1 + K * abi.HK_MAX_ACTIONS
+    eps = a["root_episodes"].sum(axis=1)
+    assert eps.min() > 0 and eps.max() <= K * abi.HK_MAX_ACTIONS * RPL
+    assert a["n_best"].max() <= abi.HK_MCTS_MAX_SEQ and (a["n_best"] >= 1).mean() > 0.9
+    for k in range(int(a["n_best"].max())):
+        live = a["n_best"] > k
+        st = a["best"][live, k]
+        for i in range(2):
+            on = st["n_karts"] > i
+            assert np.all(st["karts"][on, i]["section"] == st["lastCompletedSection"][on])
+        assert np.all(st["lastCompletedSection"] > flat["lastCompletedSection"][live])
+        assert np.all(st["finalSection"] == flat["finalSection"][live])
+    for key in ("n_best", "root_episodes", "n_nodes"):
+        assert np.array_equal(a[key], b[key]), key
+    assert a["best"].tobytes() == b["best"].tobytes()
