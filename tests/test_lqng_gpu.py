@@ -268,6 +268,33 @@ def test_assemble_on_device(hk, oracle):
             assert rel_err(got["u0"][b], ref["u0"][b]) <= TOL
 
 
+def test_assemble_pipeline_chunks_and_ring(hk, oracle):
+    """hk_lqng_assemble_solve_batch at sizes that exercise its chunk pipeline: 2 chunks (20,001 problems, odd), 8 chunks over a ring of
+    4 chunk buffers with reuse waits (70,001 problems), pageable and pinned caller buffers; every problem against the dense DMMA path
+    (itself checked against the oracle), a sample against the oracle directly."""
+    import torch
+    for batch in (20001, 70001):
+        p = S.make_problems(S.OVAL, batch, 2, seed=78)
+        dense = lqr.solve_batch(*S.assemble_dense(p), 3, full=False)
+        got = lqr.assemble_solve_batch(p, 3)                                     # pageable numpy buffers
+        assert np.array_equal(got["status"], dense["status"])
+        scale = np.maximum(np.abs(dense["u0"]), np.abs(dense["u0"]).max(axis=1, keepdims=True))
+        assert np.max(np.abs(got["u0"] - dense["u0"]) / scale) <= TOL
+        idx = np.linspace(0, batch - 1, 257).astype(int)
+        ref = oracle.lqng_solve_batch(*[a[idx] for a in S.assemble_dense(p)], 3, full=False)
+        for j, b in enumerate(idx):
+            assert rel_err(got["u0"][b], ref["u0"][j]) <= TOL
+        keys = ("x0", "target", "tw", "cw", "aw", "otgt", "otw")                 # pinned caller buffers (the batched-copy path)
+        pin = [torch.from_numpy(np.ascontiguousarray(p[k], dtype=np.float64)).pin_memory().numpy() for k in keys]
+        u0 = torch.empty((batch, 4), dtype=torch.float64).pin_memory().numpy()
+        st = torch.empty(batch, dtype=torch.int32).pin_memory().numpy()
+        from hierarchicalkarting_b200 import abi
+        for rep in range(2):
+            u0[:] = 0
+            abi.check(hk.hk_lqng_assemble_solve_batch(batch, 2, 3, float(p["dt"]), *[abi.dptr(a) for a in pin], abi.dptr(u0), abi.iptr(st)))
+            assert np.array_equal(u0, got["u0"]) and np.array_equal(st, got["status"])
+
+
 def test_reentrant_from_several_host_threads(hk, oracle):
     """The reference calls the solver from the Unity main thread and the MCTS from one background thread per agent
     (HierarchicalKartAgent.cs:246-283): concurrent host threads get their own stream / scratch and must not disturb each other
