@@ -188,7 +188,8 @@ def test_tree_search_api(hk):
     assert all(all(k.section == s.lastCompletedSection for k in s.kartStates) for s in best)
 
 
-@pytest.mark.parametrize("track_name,n_karts,bucket,teams", [("Complex", 2, 2, [0, 1]), ("Oval", 2, 1, [0, 1]), ("Complex", 4, 2, [0, 0, 1, 1])])
+@pytest.mark.parametrize("track_name,n_karts,bucket,teams", [("Complex", 2, 2, [0, 1]), ("Oval", 2, 1, [0, 1]), ("Complex", 4, 2, [0, 0, 1, 1]),
+                                                             ("Oval", 1, 2, [0]), ("Complex", 3, 2, [0, 1, 2])])
 def test_device_tree_search_equals_host_mirror(hk, track_name, n_karts, bucket, teams):
     """hk_mcts_search_batch (one thread block per tree) builds the tree the host mirror of KartMCTS.constructSearchTree builds when
     it is driven by the same Philox streams: same children statistics at the root, same tree size, same getBestStatesSequence."""
