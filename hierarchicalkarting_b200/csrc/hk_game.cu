@@ -475,6 +475,88 @@ struct RootMoves {
     unsigned char order[HK_MAX_KARTS][HK_MAX_ACTIONS];   // generation indices in policy order
 };
 
+// ---- packed two-kart playout ---------------------------------------------------------------------------------------------------
+// Once both karts of a 2-kart game hold action velocity buckets every remaining ply is table-driven, and the state fits in registers:
+// per kart (section, timeAtSection, tireAge, misc) with misc = lane-1 | section index on the track << 2 | velocity level << 8 |
+// laneChanges << 12.  No local-memory state, no modulo per ply (the section index is carried), upNext() is two compares (at action
+// buckets the average velocity is monotone in the level).  Same transitions, draws and terminal scores as the struct-based loop: it
+// unpacks into the hk_game_state and lets is_over() score the end.
+struct K2 { int sec, time, tire, misc; };
+
+__device__ __forceinline__ bool pack_k2(const DevGame& g, const hk_kart_state& k, K2& o)
+{
+    const int lvl = k.player == 0 ? velocity_level(g, k.min_velocity, k.max_velocity) : -1;
+    if (lvl < 0 || (unsigned)k.laneChanges >= (1u << 19) || (unsigned)(k.lane - 1) > 3u) return false;
+    o.sec = k.section; o.time = k.timeAtSection; o.tire = k.tireAge;
+    o.misc = (k.lane - 1) | ((k.section % g.n_sections) << 2) | (lvl << 8) | (k.laneChanges << 12);
+    return true;
+}
+
+__device__ __forceinline__ void unpack_k2(const DevGame& g, const K2& k, hk_kart_state& o)
+{
+    const int b = g.p.velocityBucketSize, lvl = (k.misc >> 8) & 15, v = 6 + lvl * b;
+    o.section = k.sec; o.timeAtSection = k.time; o.tireAge = k.tire; o.lane = (k.misc & 3) + 1; o.laneChanges = k.misc >> 12;
+    o.min_velocity = v; o.max_velocity = min(v + b, g.vmax); o.infeasible = 0;
+}
+
+// continues a playout from `ply` with both karts packed; returns the total number of plies (or -1: upNext() == -1)
+__device__ int rollout_packed2(const DevGame& g, const Tables& tb, hk_game_state& st, K2 k0, K2 k1, unsigned long long seed, unsigned long long rid,
+                               float* scores, int& n_scores, int& first_gi, int ply)
+{
+    int last = st.lastCompletedSection, lcs_idx = last % g.n_sections;
+    const int fin = st.finalSection, b = g.p.velocityBucketSize;
+    for (;;) {
+        // upNext (:188-243): karts not yet at last + 1, minimum (section, time, -avgVelocity), lowest index on ties
+        const bool e0 = k0.sec != last + 1, e1 = k1.sec != last + 1;
+        if (!e0 && !e1) return -1;
+        const bool one_first = k1.sec < k0.sec || (k1.sec == k0.sec && (k1.time < k0.time || (k1.time == k0.time && ((k1.misc >> 8) & 15) > ((k0.misc >> 8) & 15))));
+        const int np = (e0 && e1) ? (one_first ? 1 : 0) : (e0 ? 0 : 1);
+        const K2 k = np ? k1 : k0;
+        const int l0 = k.misc & 3, sidx = (k.misc >> 2) & 63, lvl = (k.misc >> 8) & 15, lc = k.misc >> 12;
+        const int type = g.type_of[sidx], flags = g.sec_flags[sidx];
+        const int os = (g.sec_flags[lcs_idx] >> 2) & 3;                                                   // KartMCTS.cs:252
+        const float wear = (float)k.tire / 10000.0f;
+        const int maxdl = (flags & 1) ? g.p.maxLaneChanges - lc : 99;                                     // :346
+        const size_t cell = (((size_t)type * 4 + l0) * tb.nv + lvl) * 3 + os;
+        const unsigned char* ord = tb.order + cell * tb.nc;
+        const unsigned long long* lm = tb.lmask + cell * 4 * tb.nv;
+        unsigned long long mask = 0ull;
+#pragma unroll
+        for (int l1 = 0; l1 < 4; ++l1) {
+            if (abs(l1 - l0) > maxdl) continue;
+            const float ms = max_speed_radius_wear(g.karts[np], __ldg(&tb.radius[type * 16 + l0 * 4 + l1]), wear);
+            const int mi = (int)fminf(ms, 1000.0f);                                                     // fminf(NaN, x) = x
+            if (mi < 6) continue;
+            const int jm = min(div_bucket(mi - 6, b), tb.nv - 1);
+            mask |= __ldg(&lm[l1 * tb.nv + jm]);
+        }
+        const int cnt = __popcll(mask);
+        if (cnt == 0 || last == fin) {                                                                   // isOver (:251-317) on the struct
+            unpack_k2(g, k0, st.karts[0]); unpack_k2(g, k1, st.karts[1]);
+            st.lastCompletedSection = last;
+            if (is_over(g, st, cnt, np, scores, n_scores)) break;
+        }
+        const int index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
+        const int gi = __ldg(&ord[nth_set_bit(mask, index)]);
+        // applyAction + makeMove from the tables (:127-171, :420-446)
+        const int l1 = gi & 3, j = gi >> 2;
+        const int dtv = __ldg(&tb.dt[(((size_t)type * 4 + l0) * tb.nv + lvl) * tb.nc + gi]);
+        const float load = __ldg(&tb.load[((size_t)type * 16 + l0 * 4 + l1) * tb.nv + j]);
+        K2 nk;
+        const int nlc = (flags & 2) ? 0 : lc + abs(l1 - l0);
+        const int nsidx = sidx + 1 == g.n_sections ? 0 : sidx + 1;
+        nk.tire = f2i(((float)k.tire / 10000.0f + load * g.env_karts[0].tireWearFactor) * (float)10000);
+        nk.time = (int)((unsigned)k.time + (unsigned)dtv);
+        nk.sec = k.sec + 1;
+        nk.misc = l1 | (nsidx << 2) | (j << 8) | (nlc << 12);
+        if (np) k1 = nk; else k0 = nk;
+        if (k0.sec > last && k1.sec > last) { last += 1; lcs_idx = lcs_idx + 1 == g.n_sections ? 0 : lcs_idx + 1; }
+        if (ply == 0) first_gi = gi;
+        ++ply;
+    }
+    return ply;
+}
+
 template <bool TRACE>
 __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long seed, unsigned long long rid, float* scores,
                        int& n_scores, int& first_gi, hk_action* act_out, int* choice_out, const RootMoves* root = nullptr)
@@ -486,6 +568,11 @@ __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long se
     n_scores = 0;
     int lcs_idx = st.lastCompletedSection % g.n_sections;
     for (;;) {
+        if (!TRACE && st.n_karts == 2 && g.tables_ok) {                  // both karts at action buckets: the rest runs packed in registers
+            K2 k0, k1;
+            if (pack_k2(g, st.karts[0], k0) && pack_k2(g, st.karts[1], k1))
+                return rollout_packed2(g, tb, st, k0, k1, seed, rid, scores, n_scores, first_gi, ply);
+        }
         const int np = up_next(st);
         if (np < 0) return -1;
         const int lvl = (g.tables_ok && st.karts[np].player == 0) ? velocity_level(g, st.karts[np].min_velocity, st.karts[np].max_velocity) : -1;
