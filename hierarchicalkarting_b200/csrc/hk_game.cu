@@ -363,7 +363,7 @@ __device__ __forceinline__ int fast_legal(const DevGame& g, const Tables& tb, co
 #pragma unroll
     for (int l1 = 0; l1 < 4; ++l1) {
         if (abs(l1 - l0) > maxdl) continue;
-        const float ms = max_speed_radius_wear(g.karts[np], __ldg(&tb.radius[type * 16 + l0 * 4 + l1]), wear);
+        const float ms = max_speed_radius_wear(g.karts[np], g.radius_tab[type * 16 + l0 * 4 + l1], wear);
         const int mi = (int)fminf(ms, 1000.0f);                                                         // fminf(NaN, x) = x
         if (mi < 6) continue;
         const int jm = min(div_bucket(mi - 6, b), tb.nv - 1);
@@ -410,7 +410,7 @@ __device__ __forceinline__ void fast_move(const DevGame& g, const Tables& tb, hk
 
 // One thread per (type, lane, velocity level): time updates of all candidates, then the policy's static sort order for the
 // three possible optimal-lane signs; threads with lvl == 0 also fill the load / radius tables of their (type, lane).
-__global__ void build_tables_kernel(const DevGame* __restrict__ gg, unsigned char* blob)
+__global__ void build_tables_kernel(DevGame* __restrict__ gg, unsigned char* blob)
 {
     const DevGame& g = *gg;
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -458,6 +458,7 @@ __global__ void build_tables_kernel(const DevGame* __restrict__ gg, unsigned cha
         const hk_section& cur = g.sections[sec0];
         for (int l1 = 0; l1 < 4; ++l1) {
             radius[type * 16 + l0 * 4 + l1] = radius_of_lane(cur, l0 + 1, l1 + 1);
+            gg->radius_tab[type * 16 + l0 * 4 + l1] = radius[type * 16 + l0 * 4 + l1];
             for (int j = 0; j < g.nv; ++j)
                 load[((size_t)type * 16 + l0 * 4 + l1) * g.nv + j] = tire_load(cur, (float)min(6 + j * b + b, g.vmax), l0 + 1, l1 + 1);
         }
@@ -524,7 +525,7 @@ __device__ int rollout_packed2(const DevGame& g, const Tables& tb, hk_game_state
 #pragma unroll
         for (int l1 = 0; l1 < 4; ++l1) {
             if (abs(l1 - l0) > maxdl) continue;
-            const float ms = max_speed_radius_wear(g.karts[np], __ldg(&tb.radius[type * 16 + l0 * 4 + l1]), wear);
+            const float ms = max_speed_radius_wear(g.karts[np], g.radius_tab[type * 16 + l0 * 4 + l1], wear);
             const int mi = (int)fminf(ms, 1000.0f);                                                     // fminf(NaN, x) = x
             if (mi < 6) continue;
             const int jm = min(div_bucket(mi - 6, b), tb.nv - 1);

@@ -29,6 +29,8 @@ struct DevGame {
     unsigned char type_of[HK_MAX_SECTIONS];     // section -> type
     unsigned char rep_section[HK_MAX_TYPES];    // a section of that type
     unsigned char sec_flags[HK_MAX_SECTIONS];   // bit0 straight(s), bit1 straight(s) != straight(s+1), bits 2-3 optimalLaneSign + 1
+    float radius_tab[HK_MAX_TYPES * 16];        // radiusOfLane per (type, lane, target lane): read four times per ply, so it travels with this
+                                                // struct into shared memory (filled by build_tables_kernel)
     const unsigned char* tables;                // device blob: dt int32[T][4][nv][nc] | order u8[T][4][nv][3][nc] | load f32[T][16][nv] | radius f32[T][16]
                                                 //              | lmask u64[T][4][nv][3][4][nv]: ranks of the moves into lane l1 with velocity level <= j
 };
