@@ -521,16 +521,20 @@ __device__ int rollout_packed2(const DevGame& g, const Tables& tb, hk_game_state
         const size_t cell = (((size_t)type * 4 + l0) * tb.nv + lvl) * 3 + os;
         const unsigned char* ord = tb.order + cell * tb.nc;
         const unsigned long long* lm = tb.lmask + cell * 4 * tb.nv;
-        unsigned long long mask = 0ull;
+        // the four target lanes without branches: the mask loads are issued together (always at a valid index) and selected afterwards
+        unsigned long long mv[4];
+        bool okl[4];
 #pragma unroll
         for (int l1 = 0; l1 < 4; ++l1) {
-            if (abs(l1 - l0) > maxdl) continue;
             const float ms = max_speed_radius_wear(g.karts[np], g.radius_tab[type * 16 + l0 * 4 + l1], wear);
             const int mi = (int)fminf(ms, 1000.0f);                                                     // fminf(NaN, x) = x
-            if (mi < 6) continue;
-            const int jm = min(div_bucket(mi - 6, b), tb.nv - 1);
-            mask |= __ldg(&lm[l1 * tb.nv + jm]);
+            okl[l1] = abs(l1 - l0) <= maxdl && mi >= 6;
+            const int jm = min(div_bucket(max(mi, 6) - 6, b), tb.nv - 1);
+            mv[l1] = __ldg(&lm[l1 * tb.nv + jm]);
         }
+        unsigned long long mask = 0ull;
+#pragma unroll
+        for (int l1 = 0; l1 < 4; ++l1) mask |= okl[l1] ? mv[l1] : 0ull;
         const int cnt = __popcll(mask);
         if (cnt == 0 || last == fin) {                                                                   // isOver (:251-317) on the struct
             unpack_k2(g, k0, st.karts[0]); unpack_k2(g, k1, st.karts[1]);
