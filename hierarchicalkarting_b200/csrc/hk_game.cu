@@ -356,19 +356,22 @@ __device__ __forceinline__ int fast_legal(const DevGame& g, const Tables& tb, co
     ord = tb.order + cell * tb.nc;
     const unsigned long long* lm = tb.lmask + cell * 4 * tb.nv;
     const int b = g.p.velocityBucketSize;
-    mask = 0ull;
     // Per target lane the speed filter !(maxSpeed < v) (:357) passes the velocity levels up to floor(maxSpeed) (v is an integer;
     // a NaN limit passes all of them), and the statically feasible moves into that lane up to a level are one precomputed mask
-    // over the policy's rank order — no scan over the 4 nv candidates.
+    // over the policy's rank order — no scan over the 4 nv candidates.  Branch-free: the four mask loads are issued together.
+    unsigned long long mv[4];
+    bool okl[4];
 #pragma unroll
     for (int l1 = 0; l1 < 4; ++l1) {
-        if (abs(l1 - l0) > maxdl) continue;
         const float ms = max_speed_radius_wear(g.karts[np], g.radius_tab[type * 16 + l0 * 4 + l1], wear);
         const int mi = (int)fminf(ms, 1000.0f);                                                         // fminf(NaN, x) = x
-        if (mi < 6) continue;
-        const int jm = min(div_bucket(mi - 6, b), tb.nv - 1);
-        mask |= __ldg(&lm[l1 * tb.nv + jm]);
+        okl[l1] = abs(l1 - l0) <= maxdl && mi >= 6;
+        const int jm = min(div_bucket(max(mi, 6) - 6, b), tb.nv - 1);
+        mv[l1] = __ldg(&lm[l1 * tb.nv + jm]);
     }
+    mask = 0ull;
+#pragma unroll
+    for (int l1 = 0; l1 < 4; ++l1) mask |= okl[l1] ? mv[l1] : 0ull;
     return __popcll(mask);
 }
 
