@@ -323,11 +323,13 @@ __device__ __forceinline__ int policy_index(const DevGame& g, int cnt, unsigned 
 // ---- table-driven ply (same results as legal_moves + select_kth + make_move, see DevGame) ---------------------------------
 struct Tables {
     const int* dt; const unsigned char* order; const float* load; const float* radius; const unsigned long long* lmask;
+    const unsigned long long* od;
     int nv, nc;
     __device__ Tables(const DevGame& g)
         : dt(reinterpret_cast<const int*>(g.tables + g.off_dt)), order(g.tables + g.off_order),
           load(reinterpret_cast<const float*>(g.tables + g.off_load)), radius(reinterpret_cast<const float*>(g.tables + g.off_radius)),
-          lmask(reinterpret_cast<const unsigned long long*>(g.tables + g.off_lmask)), nv(g.nv), nc(g.n_cand) {}
+          lmask(reinterpret_cast<const unsigned long long*>(g.tables + g.off_lmask)),
+          od(reinterpret_cast<const unsigned long long*>(g.tables + g.off_od)), nv(g.nv), nc(g.n_cand) {}
 };
 
 // x / velocityBucketSize for x >= 0 without the ~20-instruction integer division in the two bucket sizes the reference uses
@@ -441,6 +443,12 @@ __global__ void build_tables_kernel(DevGame* __restrict__ gg, unsigned char* blo
         int n_ok = 0;
         for (int gi = 0; gi < g.n_cand; ++gi) n_ok += keys[os][gi] != ~0ull;
         for (int r = 0; r < g.n_cand; ++r) order[os * g.n_cand + r] = r < n_ok ? (unsigned char)select_kth(keys[os], g.n_cand, r) : 255;
+        // rank -> (time update, generation index) in one 8-byte entry: the packed playout's move costs one dependent load, not two
+        unsigned long long* od = reinterpret_cast<unsigned long long*>(blob + g.off_od) + ((size_t)id * 3 + os) * g.n_cand;
+        for (int r = 0; r < g.n_cand; ++r) {
+            const int gi = order[os * g.n_cand + r];
+            od[r] = gi == 255 ? 0xFFull : (((unsigned long long)(unsigned)dt[gi]) << 8) | (unsigned long long)gi;
+        }
     }
     {   // masks over the rank order: moves into lane l1 with velocity level <= j, per optimal-lane sign
         unsigned long long* lm = reinterpret_cast<unsigned long long*>(blob + g.off_lmask) + (size_t)id * 3 * 4 * g.nv;
@@ -522,7 +530,7 @@ __device__ int rollout_packed2(const DevGame& g, const Tables& tb, hk_game_state
         const float wear = (float)k.tire / 10000.0f;
         const int maxdl = (flags & 1) ? g.p.maxLaneChanges - lc : 99;                                     // :346
         const size_t cell = (((size_t)type * 4 + l0) * tb.nv + lvl) * 3 + os;
-        const unsigned char* ord = tb.order + cell * tb.nc;
+        const unsigned long long* od = tb.od + cell * tb.nc;
         const unsigned long long* lm = tb.lmask + cell * 4 * tb.nv;
         // the four target lanes without branches: the mask loads are issued together (always at a valid index) and selected afterwards
         unsigned long long mv[4];
@@ -545,10 +553,11 @@ __device__ int rollout_packed2(const DevGame& g, const Tables& tb, hk_game_state
             if (is_over(g, st, cnt, np, scores, n_scores)) break;
         }
         const int index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
-        const int gi = __ldg(&ord[nth_set_bit(mask, index)]);
+        const unsigned long long mvrec = __ldg(&od[nth_set_bit(mask, index)]);
+        const int gi = (int)(mvrec & 0xFFull);
         // applyAction + makeMove from the tables (:127-171, :420-446)
         const int l1 = gi & 3, j = gi >> 2;
-        const int dtv = __ldg(&tb.dt[(((size_t)type * 4 + l0) * tb.nv + lvl) * tb.nc + gi]);
+        const int dtv = (int)(unsigned)(mvrec >> 8);
         const float load = __ldg(&tb.load[((size_t)type * 16 + l0 * 4 + l1) * tb.nv + j]);
         K2 nk;
         const int nlc = (flags & 2) ? 0 : lc + abs(l1 - l0);
@@ -1094,7 +1103,8 @@ extern "C" int hk_game_create(const hk_section* sections, int n_sections, const 
     d.off_load = (int)((d.off_order + cells * 3 * d.n_cand + 15) & ~(size_t)15);
     d.off_radius = d.off_load + (int)((size_t)d.n_types * 16 * nv * 4);
     d.off_lmask = (d.off_radius + d.n_types * 16 * 4 + 15) & ~15;
-    d.table_bytes = d.off_lmask + (int)(cells * 3 * 4 * nv * 8);
+    d.off_od = d.off_lmask + (int)(cells * 3 * 4 * nv * 8);
+    d.table_bytes = d.off_od + (int)(cells * 3 * d.n_cand * 8);
     unsigned char* blob = nullptr;
     cudaError_t e = cudaMalloc(&g->dev, sizeof(DevGame));
     if (e == cudaSuccess) e = cudaMalloc(&blob, d.table_bytes);

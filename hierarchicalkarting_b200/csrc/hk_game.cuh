@@ -26,6 +26,7 @@ struct DevGame {
     int tables_ok;                              // 0: more than HK_MAX_TYPES geometries -> kernels use the direct path only
     int n_types, nv;                            // geometry types; velocity levels (n_cand = 4 nv)
     int off_dt, off_order, off_load, off_radius, off_lmask, table_bytes;   // byte offsets into `tables`
+    int off_od, pad2_;                          // u64[T][4][nv][3][nc]: per rank of the policy order (time update << 8 | generation index)
     unsigned char type_of[HK_MAX_SECTIONS];     // section -> type
     unsigned char rep_section[HK_MAX_TYPES];    // a section of that type
     unsigned char sec_flags[HK_MAX_SECTIONS];   // bit0 straight(s), bit1 straight(s) != straight(s+1), bits 2-3 optimalLaneSign + 1
