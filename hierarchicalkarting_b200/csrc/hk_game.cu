@@ -1190,7 +1190,14 @@ static int rollouts_impl(const hk_game* g, const hk_game_state* leaves, int n_le
         long long want = (rollouts_per_leaf + 127) / 128;
         long long cap = (long long)sms * 16 / (n_leaves < sms * 16 ? 1 : 1);          // persistent-ish grid: 16 CTAs of 128 threads per SM
         if (n_leaves > 1) cap = (cap + n_leaves - 1) / n_leaves > 0 ? (cap + n_leaves - 1) / n_leaves : 1;
-        dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_leaves);
+        long long gx = want < cap ? want : cap;
+        if (n_leaves == 1 && want > (long long)sms * 8) {
+            // one leaf: a single wave of resident thread blocks (8 per SM) with the same number of rollouts per thread — the grid-stride
+            // loop otherwise ends in a partly filled round and a second, partly filled wave of blocks (ncu: `barrier` 1.2 warps per issue cycle)
+            const long long resident = (long long)sms * 8, rounds = (want + resident - 1) / resident;
+            gx = (want + rounds - 1) / rounds;
+        }
+        dim3 grid((unsigned)gx, (unsigned)n_leaves);
         count_launch(); rollouts_kernel<<<grid, 128, 0, c->stream>>>(g->dev, (const hk_game_state*)d, rollouts_per_leaf, seed, rollout_offset,
             (unsigned long long*)(d + off[1]), (double*)(d + off[2]), (unsigned long long*)(d + off[3]), (unsigned long long*)(d + off[4]), (int*)(d + off[5]));
         HK_CUDA(cudaGetLastError());
