@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(128, 8) rollouts_kernel(const DevGame* __restr
                                                        long long rollouts_per_leaf, unsigned long long seed,
                                                        unsigned long long rollout_offset, unsigned long long* visit,
                                                        double* reward_sum, unsigned long long* nan_count,
-                                                       unsigned long long* plies_sum, int* error_flag)
+                                                       unsigned long long* plies_sum, int* error_flag, unsigned long long* next)
 {
     __shared__ DevGame g;
     __shared__ unsigned s_visit[HK_MAX_ACTIONS];
@@ -673,8 +673,15 @@ __global__ void __launch_bounds__(128, 8) rollouts_kernel(const DevGame* __restr
         }
     }
     __syncthreads();
-    // grid-stride over the leaf's rollouts; block-local partial sums in double
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rollouts_per_leaf; r += (long long)gridDim.x * blockDim.x) {
+    // Warps take the leaf's rollouts 32 at a time from a device counter (SMs differ by a few per cent in speed and a launch ends with
+    // its slowest warp); which thread plays a rollout does not matter, its Philox counter is its id.  Block-local partial sums in double.
+    for (;;) {
+        unsigned long long base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(&next[leaf], 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned long long)rollouts_per_leaf) break;
+        const long long r = (long long)base + (threadIdx.x & 31);
+        if (r >= rollouts_per_leaf) continue;
         float scores[2 * HK_MAX_KARTS];
         int n_scores, first_gi;
         const unsigned long long rid = rollout_offset + (unsigned long long)leaf * (unsigned long long)rollouts_per_leaf + (unsigned long long)r;
@@ -1177,7 +1184,7 @@ static int rollouts_impl(const hk_game* g, const hk_game_state* leaves, int n_le
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
     const size_t nA = (size_t)n_leaves * HK_MAX_ACTIONS;
-    const size_t sz[6] = {sizeof(hk_game_state) * n_leaves, 8 * nA, 8 * nA * HK_MAX_KARTS, 8 * nA, 8 * (size_t)n_leaves, 256};
+    const size_t sz[6] = {sizeof(hk_game_state) * n_leaves, 8 * nA, 8 * nA * HK_MAX_KARTS, 8 * nA, 8 * (size_t)n_leaves, 256 + 8 * (size_t)n_leaves};
     size_t off[7]; off[0] = 0;
     for (int i = 0; i < 6; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
     char* d = (char*)dscratch(c, 0, off[6]);
@@ -1199,7 +1206,8 @@ static int rollouts_impl(const hk_game* g, const hk_game_state* leaves, int n_le
         }
         dim3 grid((unsigned)gx, (unsigned)n_leaves);
         count_launch(); rollouts_kernel<<<grid, 128, 0, c->stream>>>(g->dev, (const hk_game_state*)d, rollouts_per_leaf, seed, rollout_offset,
-            (unsigned long long*)(d + off[1]), (double*)(d + off[2]), (unsigned long long*)(d + off[3]), (unsigned long long*)(d + off[4]), (int*)(d + off[5]));
+            (unsigned long long*)(d + off[1]), (double*)(d + off[2]), (unsigned long long*)(d + off[3]), (unsigned long long*)(d + off[4]), (int*)(d + off[5]),
+            (unsigned long long*)(d + off[5] + 256));
         HK_CUDA(cudaGetLastError());
     }
     int err = 0;
