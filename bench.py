@@ -580,7 +580,7 @@ def main():
             km, pm = RC.start_grid(S.OVAL, RACES, seed=20260004 + rank)
             RM.run(km, pm, 0, 100)                                              # standing start, no plan yet
             MCTS_K, MCTS_R, blocks_m = 24, 16, 2
-            RM.run_mcts(km[:64].copy(), pm[:64].copy(), game_m, MCTS_K, MCTS_R, 1, 100, 101)      # warm-up (one planning event)
+            RM.run_mcts(km.copy(), pm.copy(), game_m, MCTS_K, MCTS_R, 1, 100, 101)                # warm-up at full size (one planning event; scratch allocated)
             barrier()
             k0m = lib.hk_kernel_launch_count()
             t0 = time.perf_counter()
