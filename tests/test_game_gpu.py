@@ -272,3 +272,25 @@ def test_device_tree_search_full_size_properties(hk):
     for key in ("n_best", "root_episodes", "n_nodes"):
         assert np.array_equal(a[key], b[key]), key
     assert a["best"].tobytes() == b["best"].tobytes()
+
+
+@pytest.mark.parametrize("track_name,n_karts,bucket,teams", [("Complex", 2, 2, [0, 1]), ("Oval", 2, 1, [0, 1]), ("Complex", 4, 2, [0, 0, 1, 1])])
+def test_device_tree_search_equals_cpu_oracle_tree_search(hk, oracle, track_name, n_karts, bucket, teams):
+    """hk_mcts_search_batch against a tree search in which NOTHING comes from the CUDA library: oracle/np_mcts.py restates the tree policy
+    of KartMCTS.cs over the C oracle's game primitives and playouts, driven by the Philox streams the ABI documents."""
+    from oracle import np_mcts
+    track = tracks.COMPLEX if track_name == "Complex" else tracks.OVAL
+    G = mcts.Game(track, n_karts, bucket)
+    OG = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(n_karts), n_karts, tracks.game_params(track, bucket=bucket))
+    lanes = [2, 3, 1, 4][:n_karts]
+    roots = [tracks.root_state(track, s0, lanes, teams=teams, tire_age=2500, times=[0, 40, 20, 60][:n_karts]) for s0 in (1, 6, 13)]
+    K, R, seed = 5, 32, 20260008
+    dev = G.search_batch(roots, K, R, seed)
+    for r, root in enumerate(roots):
+        tree, best, n_nodes = np_mcts.TreeSearch(OG, seed + r).search(root, K, R)
+        assert int(dev["n_nodes"][r]) == n_nodes
+        assert [int(x) for x in dev["root_episodes"][r][:len(tree.children)]] == [c.numEpisodes for c in tree.children]
+        assert np.allclose(dev["root_values"][r][:len(tree.children)], [c.totalValue for c in tree.children], rtol=1e-9, atol=1e-9)
+        assert int(dev["n_best"][r]) == len(best)
+        for a, b in zip(dev["best"][r], best):
+            assert bytes(a) == bytes(b)

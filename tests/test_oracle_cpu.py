@@ -218,3 +218,36 @@ def test_rollout_oracle_modes_agree_distributionally(oracle):
     chi2, dof = float(np.sum((x - y) ** 2 / (x + y))), int(big.sum()) - 1
     assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10
     assert 2 <= a["plies"] / n <= 16
+
+
+def test_oracle_tree_search_properties(oracle):
+    """oracle/np_mcts.py (the CPU tree search the device search is compared with): episode bookkeeping of backpropagate
+    (KartMCTS.cs:280-289) — a node's episodes are the sum of its children's plus nothing else, every expanded leaf contributes R
+    episodes per child — reproducibility under the documented Philox streams, and the shape of getBestStatesSequence."""
+    from oracle import np_mcts
+    track = tracks.OVAL
+    g = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, tracks.game_params(track))
+    root = tracks.root_state(track, 4, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 30])
+    K, R = 6, 16
+    t1, b1, n1 = np_mcts.TreeSearch(g, 11).search(root, K, R)
+    t2, b2, n2 = np_mcts.TreeSearch(g, 11).search(root, K, R)
+    assert n1 == n2 and [c.numEpisodes for c in t1.children] == [c.numEpisodes for c in t2.children]
+    assert [bytes(s) for s in b1] == [bytes(s) for s in b2]
+
+    def check(node):                                     # a node's own R episodes (as somebody's child) + everything played below it
+        if node.children:
+            own = 0 if node.parent is None else R
+            assert node.numEpisodes == own + sum(c.numEpisodes for c in node.children)
+            for c in node.children:
+                check(c)
+    check(t1)
+    expanded = sum(1 for nd in _walk(t1) if nd.children)
+    assert t1.numEpisodes == sum(len(nd.children) * R for nd in _walk(t1) if nd.children) and expanded == K
+    for s in b1:
+        assert all(s.karts[i].section == s.lastCompletedSection for i in range(s.n_karts))
+
+
+def _walk(node):
+    yield node
+    for c in node.children:
+        yield from _walk(c)
