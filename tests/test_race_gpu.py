@@ -208,3 +208,39 @@ def test_device_resident_mcts_loop_equals_host_composition(hk):
     for f in pa.dtype.names:
         assert np.array_equal(pa[f], pb[f]), f
     assert ((pa["lane"] != 0) | (pa["oppLane"] != 0)).any() and ka["section"].min() >= 4     # waypoints were handed off, the karts drove on
+
+
+def test_mcts_loop_parity_against_cpu_oracle(hk, oracle):
+    """BASELINE config 5 as written — MCTS waypoints -> LQNG -> dynamics — against a loop in which nothing comes from the CUDA library:
+    the C oracle's race loop (recipe, LQNG, plant, bookkeeping), planWithMCTS's root state and hand-off (race.mcts_root_state /
+    apply_best_states, host logic) and oracle/np_mcts.py's tree search over the C oracle's game.  Re-synchronised every 100 steps like
+    test_run_parity, so that rounding differences cannot move a checkpoint crossing to another step."""
+    from hierarchicalkarting_b200 import mcts as M, tracks
+    from oracle import np_mcts
+    track = S.OVAL
+    OR, prm = _oracle_races(oracle, track, high_mode_mcts=True)
+    G = R.Races(track, prm)
+    game = M.Game(track, 2, prm.velocityBucketSize)
+    OG = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, tracks.game_params(track, bucket=prm.velocityBucketSize))
+    n_races, K, RPL, seed = 5, 24, 16, 9001
+    karts, plans = R.start_grid(track, n_races, seed=29)
+    waypoints = 0
+    for blk in range(4):
+        gk, gp = karts.copy(), plans.copy()
+        _, bad_g = G.run_mcts(gk, gp, game, K, RPL, seed + 1000 * blk, blk * 100, 100)       # plans at its first step when blk > 0
+        if blk > 0:
+            for r in range(n_races):
+                snapshot = karts[r].copy()                                                   # both agents plan from the same race state
+                for ego in range(2):
+                    st, nearby = R.mcts_root_state(track, prm, snapshot, plans[r], ego)
+                    _, best, _ = np_mcts.TreeSearch(OG, seed + 1000 * blk + 2 * r + ego).search(st, K, RPL)
+
+                    class _GS:
+                        def __init__(self, s_):
+                            self.state = s_
+                    R.apply_best_states(track, snapshot, plans[r], ego, nearby, [_GS(b) for b in best])
+                    waypoints += len(best)
+        _, bad_o = OR.run(karts, plans, blk * 100, 100)
+        assert bad_g == bad_o == 0
+        _same(gk, gp, karts, plans, tol=1e-9)
+    assert waypoints > 0 and karts["section"].min() >= 5
