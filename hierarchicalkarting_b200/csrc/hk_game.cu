@@ -628,7 +628,7 @@ __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long se
 }
 
 // ---- kernels ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 8) rollouts_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ leaves,
+__global__ void __launch_bounds__(128, 6) rollouts_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ leaves,
                                                        long long rollouts_per_leaf, unsigned long long seed,
                                                        unsigned long long rollout_offset, unsigned long long* visit,
                                                        double* reward_sum, unsigned long long* nan_count,
@@ -1198,10 +1198,10 @@ static int rollouts_impl(const hk_game* g, const hk_game_state* leaves, int n_le
         long long cap = (long long)sms * 16 / (n_leaves < sms * 16 ? 1 : 1);          // persistent-ish grid: 16 CTAs of 128 threads per SM
         if (n_leaves > 1) cap = (cap + n_leaves - 1) / n_leaves > 0 ? (cap + n_leaves - 1) / n_leaves : 1;
         long long gx = want < cap ? want : cap;
-        if (n_leaves == 1 && want > (long long)sms * 8) {
-            // one leaf: a single wave of resident thread blocks (8 per SM) with the same number of rollouts per thread — the grid-stride
+        if (n_leaves == 1 && want > (long long)sms * 6) {
+            // one leaf: a single wave of resident thread blocks (6 per SM at 80 registers) with the same number of rollouts per thread — the grid-stride
             // loop otherwise ends in a partly filled round and a second, partly filled wave of blocks (ncu: `barrier` 1.2 warps per issue cycle)
-            const long long resident = (long long)sms * 8, rounds = (want + resident - 1) / resident;
+            const long long resident = (long long)sms * 6, rounds = (want + resident - 1) / resident;
             gx = (want + rounds - 1) / rounds;
         }
         dim3 grid((unsigned)gx, (unsigned)n_leaves);
