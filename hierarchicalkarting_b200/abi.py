@@ -106,6 +106,10 @@ ACTION_DTYPE = np.dtype([("min_velocity", np.int32), ("max_velocity", np.int32),
 GAME_STATE_DTYPE = np.dtype([("n_karts", np.int32), ("initialSection", np.int32), ("lastCompletedSection", np.int32),
                              ("finalSection", np.int32), ("karts", KART_STATE_DTYPE, (HK_MAX_KARTS,))])
 assert GAME_STATE_DTYPE.itemsize == C.sizeof(hk_game_state)
+MCTS_NODE_DTYPE = np.dtype([("child_mask", np.uint64), ("totalValue", np.float32), ("numEpisodes", np.int32), ("first_child", np.int32),
+                            ("last_child", np.int32), ("next_sibling", np.int32), ("gen", np.uint8), ("n_legal", np.uint8),
+                            ("upnext", np.int8), ("pad_", np.uint8)])
+assert MCTS_NODE_DTYPE.itemsize == 32
 assert ACTION_DTYPE.itemsize == C.sizeof(hk_action)
 
 _dp = C.POINTER(C.c_double)
@@ -134,6 +138,11 @@ PROTOTYPES = {
     "hk_mcts_rollouts_trace": (C.c_int, [C.c_void_p, C.POINTER(hk_game_state), C.c_int64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 5),
     "hk_mcts_rollouts_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 4),
     "hk_mcts_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64] + [C.c_void_p] * 5),
+    "hk_mcts_forest_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "hk_mcts_forest_destroy": (None, [C.c_void_p]),
+    "hk_mcts_forest_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64] + [C.c_void_p] * 4),
+    "hk_mcts_forest_nodes": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, _ip]),
+    "hk_mcts_search_seq_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64] + [C.c_void_p] * 6),
     "hk_policy_cdf": (C.c_int, [C.c_int, _up]),
     "hk_track_create": (C.c_int, [C.POINTER(hk_section), _dp, _dp, _dp, C.c_int, C.POINTER(C.c_void_p)]),
     "hk_track_destroy": (None, [C.c_void_p]),

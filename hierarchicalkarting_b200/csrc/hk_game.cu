@@ -934,6 +934,8 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
     }
 }
 
+#include "hk_mcts_seq.cuh"
+
 __global__ void __launch_bounds__(128) rollouts_trace_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ leaf,
                                                              long long n_rollouts, unsigned long long seed,
                                                              unsigned long long rollout_offset, int* n_plies_out,
@@ -1291,6 +1293,177 @@ extern "C" int hk_mcts_search_batch(const hk_game* g, const hk_game_state* roots
     for (int r = 0; r < n_roots; ++r)
         if (st[r]) { set_error("hk_mcts_search_batch: upNext() == -1 reached in the tree of root %d (KartDiscreteGame.cs:326 would throw)", r); return HK_ERR_NO_UPNEXT; }
     return HK_OK;
+}
+
+// ---- sequential (faithful) tree search: forest of device-resident trees -----------------------------------------------------------
+struct hk_mcts_forest {
+    const hk_game* g = nullptr;
+    int n_trees = 0, max_nodes = 0;
+    hk::SeqTree* trees = nullptr;
+    hk_mcts_node* slabs = nullptr;
+};
+
+namespace hk {
+// (float)Math.Log((double)(float)k) of UCTWeight (KartMCTS.cs:164) for the integer ratios a search can produce, computed by the host's
+// libm (the same function the oracle calls) so that device trees are bit-equal to the oracle's; one table per process.
+constexpr int SEQ_LOG_TABLE = 1 << 16;
+static float* g_logtab = nullptr;
+static std::mutex g_logtab_mu;
+static const float* seq_log_table()
+{
+    std::lock_guard<std::mutex> lk(g_logtab_mu);
+    if (g_logtab) return g_logtab;
+    std::vector<float> h((size_t)SEQ_LOG_TABLE);
+    for (int k = 0; k < SEQ_LOG_TABLE; ++k) h[k] = k == 0 ? -INFINITY : (float)std::log((double)(float)k);
+    float* d = nullptr;
+    if (cudaMalloc(&d, sizeof(float) * SEQ_LOG_TABLE) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemcpy(d, h.data(), sizeof(float) * SEQ_LOG_TABLE, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); cudaGetLastError(); return nullptr; }
+    g_logtab = d;
+    return g_logtab;
+}
+
+int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, const int* d_fresh, int iterations, uint64_t seed,
+                           hk_game_state* d_best, int* d_nbest, int* d_nnodes, int* d_status, cudaStream_t s)
+{
+    const float* lt = seq_log_table();
+    if (!lt) { set_error("hk_mcts_forest_search: log table allocation failed"); return HK_ERR_OUT_OF_MEMORY; }
+    if (d_best) HK_CUDA(cudaMemsetAsync(d_best, 0, sizeof(hk_game_state) * (size_t)f->n_trees * HK_MCTS_MAX_SEQ, s));   // entries past n_best stay zero
+    constexpr int TPB = 32;                            // one warp per block: 32,768 trees spread over the 148 SMs as 1,024 blocks
+    count_launch();
+    seq_search_kernel<<<(unsigned)((f->n_trees + TPB - 1) / TPB), TPB, 0, s>>>(f->g->dev, f->trees, f->slabs, f->max_nodes, f->n_trees, iterations, seed, 0,
+                                                                              d_roots, d_fresh, lt, SEQ_LOG_TABLE, d_best, d_nbest, d_nnodes, d_status);
+    HK_CUDA(cudaGetLastError());
+    return HK_OK;
+}
+}  // namespace hk
+
+extern "C" int hk_mcts_forest_create(const hk_game* g, int n_trees, int max_nodes_per_tree, hk_mcts_forest** out)
+{
+    if (!g || n_trees < 1 || max_nodes_per_tree < 1 || !out) { set_error("hk_mcts_forest_create: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    int rc = ensure_device();
+    if (rc != HK_OK) return rc;
+    hk_mcts_forest* f = new hk_mcts_forest();
+    f->g = g; f->n_trees = n_trees; f->max_nodes = max_nodes_per_tree;
+    cudaError_t e = cudaMalloc(&f->trees, sizeof(SeqTree) * (size_t)n_trees);
+    if (e == cudaSuccess) e = cudaMalloc(&f->slabs, sizeof(hk_mcts_node) * (size_t)n_trees * max_nodes_per_tree);
+    if (e == cudaSuccess) e = cudaMemset(f->trees, 0, sizeof(SeqTree) * (size_t)n_trees);
+    if (e != cudaSuccess) {
+        set_error("hk_mcts_forest_create: %s (%d trees x %d nodes x 32 B)", cudaGetErrorString(e), n_trees, max_nodes_per_tree);
+        cudaGetLastError();
+        if (f->trees) cudaFree(f->trees);
+        if (f->slabs) cudaFree(f->slabs);
+        delete f;
+        return e == cudaErrorMemoryAllocation ? HK_ERR_OUT_OF_MEMORY : HK_ERR_CUDA;
+    }
+    *out = f;
+    return HK_OK;
+}
+
+extern "C" void hk_mcts_forest_destroy(hk_mcts_forest* f)
+{
+    if (!f) return;
+    if (f->trees) cudaFree(f->trees);
+    if (f->slabs) cudaFree(f->slabs);
+    delete f;
+}
+
+extern "C" int hk_mcts_forest_search(hk_mcts_forest* f, const hk_game_state* roots, const int32_t* fresh, int iterations, uint64_t seed,
+                                     hk_game_state* best_states, int32_t* n_best, int32_t* n_nodes, int32_t* status)
+{
+    if (!f || iterations < 0 || !best_states || !n_best) { set_error("hk_mcts_forest_search: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    const int n = f->n_trees;
+    bool any_fresh = false;
+    for (int r = 0; r < n; ++r) {
+        if (fresh && !fresh[r]) continue;
+        any_fresh = true;
+        if (!roots) { set_error("hk_mcts_forest_search: roots is NULL but tree %d is fresh", r); return HK_ERR_INVALID_ARGUMENT; }
+        int rc = check_state(f->g, &roots[r], "hk_mcts_forest_search");
+        if (rc) return rc;
+    }
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const size_t sz[6] = {sizeof(hk_game_state) * (size_t)n, 4 * (size_t)n, sizeof(hk_game_state) * (size_t)n * HK_MCTS_MAX_SEQ, 4 * (size_t)n, 4 * (size_t)n, 4 * (size_t)n};
+    size_t off[7]; off[0] = 0;
+    for (int i = 0; i < 6; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
+    char* d = (char*)dscratch(c, 0, off[6]);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    if (any_fresh) HK_CUDA(cudaMemcpyAsync(d, roots, sz[0], cudaMemcpyHostToDevice, c->stream));
+    if (fresh) HK_CUDA(cudaMemcpyAsync(d + off[1], fresh, sz[1], cudaMemcpyHostToDevice, c->stream));
+    int rc = mcts_seq_search_device(f, (const hk_game_state*)d, fresh ? (const int*)(d + off[1]) : nullptr, iterations, seed,
+                                    (hk_game_state*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (int*)(d + off[5]), c->stream);
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    std::vector<int> st((size_t)n);
+    cudaError_t e = cudaMemcpyAsync(best_states, d + off[2], sz[2], cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_best, d + off[3], sz[3], cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && n_nodes) e = cudaMemcpyAsync(n_nodes, d + off[4], sz[4], cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(st.data(), d + off[5], sz[5], cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e2 = cudaStreamSynchronize(c->stream);                 // also on the error path: nothing may stay in flight on the caller's buffers
+    if (e == cudaSuccess) e = e2;
+    if (e != cudaSuccess) { set_error("hk_mcts_forest_search: %s", cudaGetErrorString(e)); return HK_ERR_CUDA; }
+    if (status) std::memcpy(status, st.data(), sizeof(int) * (size_t)n);
+    for (int r = 0; r < n; ++r)
+        if (st[r] == 1) { set_error("hk_mcts_forest_search: upNext() == -1 reached in tree %d (KartDiscreteGame.cs:326 would throw)", r); return HK_ERR_NO_UPNEXT; }
+    return HK_OK;
+}
+
+extern "C" int hk_mcts_forest_nodes(const hk_mcts_forest* f, int tree, hk_mcts_node* nodes_out, int max_nodes, int32_t* n_nodes_out)
+{
+    if (!f || tree < 0 || tree >= f->n_trees || max_nodes < 0 || (max_nodes && !nodes_out)) { set_error("hk_mcts_forest_nodes: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    SeqTree hdr;
+    HK_CUDA(cudaMemcpy(&hdr, f->trees + tree, sizeof(SeqTree), cudaMemcpyDeviceToHost));
+    if (n_nodes_out) *n_nodes_out = hdr.n_nodes;
+    const int n = hdr.n_nodes < max_nodes ? hdr.n_nodes : max_nodes;
+    if (n > 0) HK_CUDA(cudaMemcpy(nodes_out, f->slabs + (size_t)tree * f->max_nodes, sizeof(hk_mcts_node) * (size_t)n, cudaMemcpyDeviceToHost));
+    return HK_OK;
+}
+
+extern "C" int hk_mcts_search_seq_batch(const hk_game* g, const hk_game_state* roots, int n_roots, int iterations, uint64_t seed,
+                                        hk_game_state* best_states, int32_t* n_best, int32_t* root_gen, int32_t* root_episodes,
+                                        float* root_values, int32_t* n_nodes)
+{
+    if (!g || !roots || n_roots < 1 || iterations < 0 || !best_states || !n_best) { set_error("hk_mcts_search_seq_batch: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    long long plies = 1;
+    for (int r = 0; r < n_roots; ++r) {
+        int rc = check_state(g, &roots[r], "hk_mcts_search_seq_batch");
+        if (rc) return rc;
+        long long p = 0;
+        for (int k = 0; k < roots[r].n_karts; ++k) { const long long dd = (long long)roots[r].finalSection - roots[r].karts[k].section; p += dd > 0 ? dd : 0; }
+        if (p > plies) plies = p;
+    }
+    if (plies > HK_MAX_PLIES) { set_error("hk_mcts_search_seq_batch: a playout could take %lld plies (> %d)", plies, HK_MAX_PLIES); return HK_ERR_INVALID_ARGUMENT; }
+    const long long max_nodes = 1 + (long long)iterations * plies;
+    if (max_nodes > (1ll << 30)) { set_error("hk_mcts_search_seq_batch: tree too large"); return HK_ERR_INVALID_ARGUMENT; }
+    hk_mcts_forest* f = nullptr;
+    int rc = hk_mcts_forest_create(g, n_roots, (int)max_nodes, &f);
+    if (rc) return rc;
+    rc = hk_mcts_forest_search(f, roots, nullptr, iterations, seed, best_states, n_best, n_nodes, nullptr);
+    if (rc == HK_OK && (root_gen || root_episodes || root_values)) {
+        // the root's children in insertion order: walk each tree's child list on the host from its first (at most HK_MAX_ACTIONS + 1) records' links
+        std::vector<hk_mcts_node> buf;
+        for (int r = 0; r < n_roots && rc == HK_OK; ++r) {
+            hk_mcts_node root;
+            cudaError_t e = cudaMemcpy(&root, f->slabs + (size_t)r * f->max_nodes, sizeof(root), cudaMemcpyDeviceToHost);
+            int j = 0;
+            for (int c = root.first_child; e == cudaSuccess && c >= 0 && j < HK_MAX_ACTIONS; ++j) {
+                hk_mcts_node ch;
+                e = cudaMemcpy(&ch, f->slabs + (size_t)r * f->max_nodes + c, sizeof(ch), cudaMemcpyDeviceToHost);
+                if (root_gen) root_gen[(size_t)r * HK_MAX_ACTIONS + j] = ch.gen;
+                if (root_episodes) root_episodes[(size_t)r * HK_MAX_ACTIONS + j] = ch.numEpisodes;
+                if (root_values) root_values[(size_t)r * HK_MAX_ACTIONS + j] = ch.totalValue;
+                c = ch.next_sibling;
+            }
+            for (; j < HK_MAX_ACTIONS; ++j) {
+                if (root_gen) root_gen[(size_t)r * HK_MAX_ACTIONS + j] = -1;
+                if (root_episodes) root_episodes[(size_t)r * HK_MAX_ACTIONS + j] = 0;
+                if (root_values) root_values[(size_t)r * HK_MAX_ACTIONS + j] = 0.0f;
+            }
+            if (e != cudaSuccess) { set_error("hk_mcts_search_seq_batch: %s", cudaGetErrorString(e)); rc = HK_ERR_CUDA; }
+        }
+    }
+    hk_mcts_forest_destroy(f);
+    return rc;
 }
 
 extern "C" int hk_mcts_rollouts_trace(const hk_game* g, const hk_game_state* leaf, int64_t n_rollouts, uint64_t seed, uint64_t rollout_offset,

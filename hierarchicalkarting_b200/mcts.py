@@ -126,6 +126,23 @@ class Game:
                                                           abi.vptr(n_best), abi.vptr(eps), abi.vptr(vals), abi.vptr(nodes)))
         return dict(best=best, n_best=n_best, root_episodes=eps, root_values=vals, n_nodes=nodes)
 
+    def search_seq_batch(self, roots, iterations: int, seed: int = 0):
+        """hk_mcts_search_seq_batch: the reference's sequential search (constructSearchTree with parallel == false: one playout per
+        iteration, every playout state a tree node) + getBestStatesSequence for every root, one GPU thread per tree.  `roots`: list
+        of hk_game_state or array of abi.GAME_STATE_DTYPE.  Returns best [n][HK_MCTS_MAX_SEQ] (GAME_STATE_DTYPE), n_best, and the
+        root's children in insertion order: root_gen (-1 past the end), root_episodes, root_values; n_nodes."""
+        roots = _states_array(roots)
+        n = roots.shape[0]
+        best = np.zeros((n, abi.HK_MCTS_MAX_SEQ), dtype=abi.GAME_STATE_DTYPE)
+        n_best = np.zeros(n, dtype=np.int32)
+        gen = np.zeros((n, abi.HK_MAX_ACTIONS), dtype=np.int32)
+        eps = np.zeros((n, abi.HK_MAX_ACTIONS), dtype=np.int32)
+        vals = np.zeros((n, abi.HK_MAX_ACTIONS), dtype=np.float32)
+        nodes = np.zeros(n, dtype=np.int32)
+        abi.check(abi.load_library().hk_mcts_search_seq_batch(self._h, abi.vptr(roots), n, iterations, seed, abi.vptr(best), abi.vptr(n_best),
+                                                              abi.vptr(gen), abi.vptr(eps), abi.vptr(vals), abi.vptr(nodes)))
+        return dict(best=best, n_best=n_best, root_gen=gen, root_episodes=eps, root_values=vals, n_nodes=nodes)
+
     def rollouts_trace(self, leaf: abi.hk_game_state, n_rollouts: int, seed: int = 0, rollout_offset: int = 0):
         n = n_rollouts
         out = dict(n_plies=np.zeros(n, dtype=np.int32), actions=np.zeros((n, abi.HK_MAX_PLIES, 3), dtype=np.int32),
@@ -145,6 +162,56 @@ class Game:
         b = self.params.velocityBucketSize
         v = 6 + (gi // 4) * b
         return (v, min(v + b, 15), gi % 4 + 1)
+
+
+def _states_array(roots) -> np.ndarray:
+    if isinstance(roots, np.ndarray):
+        return np.ascontiguousarray(roots, dtype=abi.GAME_STATE_DTYPE)
+    r = np.zeros(len(roots), dtype=abi.GAME_STATE_DTYPE)
+    for i, s in enumerate(roots):
+        C.memmove(r[i:i + 1].ctypes.data, C.byref(s), C.sizeof(abi.hk_game_state))
+    return r
+
+
+class Forest:
+    """hk_mcts_forest: device-resident trees of the reference's sequential search that survive between calls, like
+    HierarchicalKartAgent.currentRoot (HierarchicalKartAgent.cs:265-283)."""
+
+    def __init__(self, game: Game, n_trees: int, max_nodes_per_tree: int):
+        self.game, self.n_trees, self.max_nodes = game, n_trees, max_nodes_per_tree
+        self._h = C.c_void_p()
+        abi.check(abi.load_library().hk_mcts_forest_create(game._h, n_trees, max_nodes_per_tree, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            abi.load_library().hk_mcts_forest_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, roots, iterations: int, seed: int = 0, fresh=None):
+        """constructSearchTree(state) for trees with fresh[r] != 0 (None: all), constructSearchTree(root) for the others."""
+        n = self.n_trees
+        roots = _states_array(roots) if roots is not None else None
+        fr = None if fresh is None else np.ascontiguousarray(fresh, dtype=np.int32)
+        best = np.zeros((n, abi.HK_MCTS_MAX_SEQ), dtype=abi.GAME_STATE_DTYPE)
+        n_best, nodes, status = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        abi.check(abi.load_library().hk_mcts_forest_search(self._h, abi.vptr(roots), abi.vptr(fr), iterations, seed, abi.vptr(best),
+                                                           abi.vptr(n_best), abi.vptr(nodes), abi.vptr(status)))
+        return dict(best=best, n_best=n_best, n_nodes=nodes, status=status)
+
+    def nodes(self, tree: int) -> np.ndarray:
+        """Records of one tree in creation order (abi.MCTS_NODE_DTYPE)."""
+        n = C.c_int32(0)
+        lib = abi.load_library()
+        abi.check(lib.hk_mcts_forest_nodes(self._h, tree, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=abi.MCTS_NODE_DTYPE)
+        abi.check(lib.hk_mcts_forest_nodes(self._h, tree, abi.vptr(out), n.value, C.byref(n)))
+        return out
 
 
 def policy_cdf(cnt: int) -> np.ndarray:

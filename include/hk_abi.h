@@ -204,8 +204,9 @@ int hk_mcts_rollouts_multi(const hk_game* g, const hk_game_state* leaves, int n_
                            uint64_t seed, uint64_t rollout_offset, int64_t* visit, double* reward_sum,
                            int64_t* nan_count, int64_t* plies_sum);
 
+#define HK_MCTS_MAX_SEQ 16
 /*
- * Batched tree search: KartMCTS.constructSearchTree (KartMCTS.cs:50-106) followed by getBestStatesSequence (:108-122) for
+ * Batched tree search, LEAF-PARALLEL form: KartMCTS.constructSearchTree (KartMCTS.cs:50-106) followed by getBestStatesSequence (:108-122) for
  * n_roots independent root states in one launch, one thread block per tree — what planWithMCTS (HierarchicalKartAgent.cs:
  * 194-283) does per agent on a background thread, for every agent of many races at once.  Each of `iterations` iterations
  * walks the tree with upperConfidenceStrategy (:167-192) to a node without children (findLeaf :194-201), creates all its
@@ -217,10 +218,55 @@ int hk_mcts_rollouts_multi(const hk_game* g, const hk_game_state* leaves, int n_
  *   root_episodes [n_roots][HK_MAX_ACTIONS]   numEpisodes of the root's children in nextMoves() order (may be NULL)
  *   root_values   [n_roots][HK_MAX_ACTIONS]   their totalValue (may be NULL);  n_nodes [n_roots] tree sizes (may be NULL)
  */
-#define HK_MCTS_MAX_SEQ 16
 int hk_mcts_search_batch(const hk_game* g, const hk_game_state* roots, int n_roots, int iterations, int rollouts_per_leaf,
                          uint64_t seed, hk_game_state* best_states, int32_t* n_best, int32_t* root_episodes,
                          double* root_values, int32_t* n_nodes);
+
+/*
+ * The tree search AS THE REFERENCE'S CALLERS RUN IT: KartMCTS.constructSearchTree with parallel == false (KartMCTS.cs:50-78 / :80-106 —
+ * HierarchicalKartAgent.cs:250,271 never pass `parallel`): per iteration findLeaf (:194-201), ONE playout of simulate (:238-278) in which
+ * every state becomes a tree node (:271-276), backpropagate from the playout's terminal node (:280-289); then getBestStatesSequence
+ * (:108-122).  The reference's wall-clock budget T (:55) becomes an iteration count.  One GPU thread owns one tree, so the call pays
+ * off for many trees at once (every agent of many races); a single tree runs at the latency of one thread.
+ * Trees live in a device-resident forest and survive between calls, as HierarchicalKartAgent.currentRoot does (:265-283): tree r is
+ * (re)started from roots[r] where fresh[r] != 0 (constructSearchTree(state), fresh == NULL: all), and continued otherwise
+ * (constructSearchTree(root); roots[r] is ignored).  Random sources: tree r started by a call with `seed` has key = seed + r for life;
+ * policy index of iteration `it` (counted over the life of the tree), ply p of its playout = word 0 of Philox4x32-10(key, counter
+ * (it, 0, p, 0)) through hk_policy_cdf; the random initial pick of upperConfidenceStrategy (:169) = word 0 of
+ * Philox4x32-10(key ^ 0x9E3779B97F4A7C15, counter (picks so far, 0, 0, 0)) modulo the child count.  totalValue is float32, updated in
+ * the reference's order.
+ *   best_states [n_trees][HK_MCTS_MAX_SEQ], n_best [n_trees]   getBestStatesSequence of every tree after this call
+ *   n_nodes     [n_trees]  tree sizes (may be NULL)
+ *   status      [n_trees]  (may be NULL) 0 ok; 1 upNext() == -1 was reached (ArgumentOutOfRangeException, KartDiscreteGame.cs:326);
+ *                          2 UCTWeight divided by zero inside findLeaf (DivideByZeroException, KartMCTS.cs:164); 3 max_nodes_per_tree
+ *                          reached (the search of that tree stopped early).  Status 1 makes the call return HK_ERR_NO_UPNEXT.
+ * max_nodes_per_tree must cover 1 + (iterations over the life of a tree) x (plies of a playout <= sum over karts of finalSection - section).
+ */
+typedef struct hk_mcts_node {    /* one KartMCTSNode (KartMCTS.cs:18-38) of a device-resident tree; the state is not stored (replay the path) */
+    uint64_t child_mask;         /* generation indices (vi*4 + lane-1) of the actions in `children` */
+    float    totalValue;         /* :23 */
+    int32_t  numEpisodes;        /* :24 */
+    int32_t  first_child, last_child, next_sibling;   /* children in insertion order = the Dictionary's enumeration order; -1 = none */
+    uint8_t  gen;                /* generation index of the action that created this node (255: the root) */
+    uint8_t  n_legal;            /* state.nextMoves().Count (255: never evaluated, i.e. a terminal node) */
+    int8_t   upnext;             /* state.upNext() */
+    uint8_t  pad_;
+} hk_mcts_node;
+
+typedef struct hk_mcts_forest hk_mcts_forest;
+int  hk_mcts_forest_create(const hk_game* g, int n_trees, int max_nodes_per_tree, hk_mcts_forest** out);
+void hk_mcts_forest_destroy(hk_mcts_forest* f);
+int  hk_mcts_forest_search(hk_mcts_forest* f, const hk_game_state* roots, const int32_t* fresh, int iterations, uint64_t seed,
+                           hk_game_state* best_states, int32_t* n_best, int32_t* n_nodes, int32_t* status);
+/* Nodes of one tree in creation order (node 0 = root; a node's parent is the node whose child list holds it): at most max_nodes
+ * records are written, *n_nodes_out receives the tree size. */
+int  hk_mcts_forest_nodes(const hk_mcts_forest* f, int tree, hk_mcts_node* nodes_out, int max_nodes, int32_t* n_nodes_out);
+/* One-shot form: forest of n_roots fresh trees sized for `iterations`, searched, destroyed.  root_gen / root_episodes / root_values
+ * [n_roots][HK_MAX_ACTIONS] (each may be NULL): generation index (-1 past the end), numEpisodes and totalValue of the root's children
+ * in insertion order. */
+int  hk_mcts_search_seq_batch(const hk_game* g, const hk_game_state* roots, int n_roots, int iterations, uint64_t seed,
+                              hk_game_state* best_states, int32_t* n_best, int32_t* root_gen, int32_t* root_episodes,
+                              float* root_values, int32_t* n_nodes);
 
 /* The rollout policy's index distribution for `cnt` legal moves (KartMCTS.cs:266-269 via NextGaussian :218-236):
  * cdf_out[k] = P(index <= k) as a 32-bit threshold, exactly what the kernels sample from. cnt in 1..HK_MAX_ACTIONS. */

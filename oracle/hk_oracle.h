@@ -39,6 +39,19 @@ int  hk_oracle_rollout(const hk_oracle_game* g, const hk_game_state* leaf, int m
                        hk_game_state* terminal);
 int  hk_oracle_rollouts(const hk_oracle_game* g, const hk_game_state* leaf, int64_t n_rollouts, int mode, uint64_t seed,
                         uint64_t rollout_offset, int64_t* visit, double* reward_sum, int64_t* nan_count, int64_t* plies_sum);
+/* sequential tree search exactly as the reference's callers run it (hk_oracle_mcts.c): constructSearchTree with parallel == false */
+typedef struct hk_oracle_tree hk_oracle_tree;
+hk_oracle_tree* hk_oracle_tree_create(const hk_oracle_game* g, const hk_game_state* root);
+void hk_oracle_tree_destroy(hk_oracle_tree* t);
+int  hk_oracle_tree_search(hk_oracle_tree* t, int iterations, int mode, uint64_t key, uint64_t* rng_state);
+int  hk_oracle_tree_best_states(hk_oracle_tree* t, int mode, uint64_t key, uint64_t* rng_state, hk_game_state* out, int max_out);
+int  hk_oracle_tree_size(const hk_oracle_tree* t);
+long long hk_oracle_tree_children_as_root(const hk_oracle_tree* t);
+void hk_oracle_tree_dump(const hk_oracle_tree* t, int32_t* parent, int32_t* gen, float* totalValue, int32_t* numEpisodes,
+                         int32_t* n_children, int32_t* first_child, int32_t* next_sibling, hk_game_state* states);
+int  hk_oracle_tree_search_batch(const hk_oracle_game* g, const hk_game_state* roots, int n, int iterations, int mode, uint64_t seed,
+                                 const uint64_t* rng_states, hk_game_state* best, int32_t* n_best, int max_seq, int32_t* root_gen,
+                                 int32_t* root_episodes, float* root_values, int32_t* n_nodes, int threads);
 /* closed loop without PhysX (hk_oracle_race.c): recipe, planFixed, plant + bookkeeping, the loop */
 void hk_oracle_race_recipe_one(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
                                const hk_race_params* p, const hk_race_kart* karts, const hk_race_plan* plans, int e,

@@ -11,10 +11,10 @@ import math
 
 import numpy as np
 
-from hierarchicalkarting_b200 import abi
 from . import oracle as O
+from . import structs as S
 
-HK_MAX_ACTIONS = abi.HK_MAX_ACTIONS
+HK_MAX_ACTIONS = S.HK_MAX_ACTIONS
 
 
 class Node:                                              # KartMCTSNode, KartMCTS.cs:18-38
@@ -24,7 +24,7 @@ class Node:                                              # KartMCTSNode, KartMCT
 
 
 def _copy(st):
-    return abi.hk_game_state.from_buffer_copy(bytes(st))
+    return S.game_state(st)
 
 
 class TreeSearch:
@@ -84,7 +84,7 @@ class TreeSearch:
                 n = c
                 while n is not None:                     # backpropagate :280-289
                     u = self.g.up_next(n.state)
-                    if 0 <= u < min(len(contrib), abi.HK_MAX_KARTS):
+                    if 0 <= u < min(len(contrib), S.HK_MAX_KARTS):
                         n.totalValue += float(contrib[u])
                     n.numEpisodes += count
                     n = n.parent
