@@ -91,6 +91,11 @@ class hk_race_params(C.Structure):
                 ("treeSearchDepth", C.c_int32), ("planEvery", C.c_int32), ("horizon", C.c_int32)]
 
 
+class hk_race_mcts_params(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("iterations", C.c_int32), ("first_iterations", C.c_int32), ("rollouts_per_leaf", C.c_int32),
+                ("reuse_cycles", C.c_int32), ("apply_delay", C.c_int32), ("seed", C.c_uint64), ("max_tree_nodes", C.c_int32), ("pad_", C.c_int32)]
+
+
 # numpy views of the same layouts (for batched buffers)
 RACE_KART_DTYPE = np.dtype([("x", np.float64), ("z", np.float64), ("v", np.float64), ("h", np.float64), ("steer", np.float32),
                             ("section", np.int32), ("lane", np.int32), ("laneChanges", np.int32),
@@ -150,6 +155,10 @@ PROTOTYPES = {
     "hk_race_step": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_int, _dp, C.c_void_p, C.c_void_p]),
     "hk_race_plan_fixed": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_void_p, C.c_void_p]),
     "hk_race_run": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, _dp, _lp]),
+    "hk_race_planner_create": (C.c_int, [C.c_void_p, C.POINTER(hk_race_mcts_params), C.c_int, C.POINTER(C.c_void_p)]),
+    "hk_race_planner_destroy": (None, [C.c_void_p]),
+    "hk_race_planner_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hk_race_run_planned": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, _dp, _lp]),
     "hk_race_run_mcts": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, _dp, _lp]),
 }

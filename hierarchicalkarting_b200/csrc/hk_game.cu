@@ -1323,11 +1323,11 @@ static const float* seq_log_table()
 }
 
 int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, const int* d_fresh, int iterations, uint64_t seed,
-                           hk_game_state* d_best, int* d_nbest, int* d_nnodes, int* d_status, cudaStream_t s)
+                           hk_game_state* d_best, int* d_nbest, int* d_nnodes, int* d_status, cudaStream_t s, bool clear_best)
 {
     const float* lt = seq_log_table();
     if (!lt) { set_error("hk_mcts_forest_search: log table allocation failed"); return HK_ERR_OUT_OF_MEMORY; }
-    if (d_best) HK_CUDA(cudaMemsetAsync(d_best, 0, sizeof(hk_game_state) * (size_t)f->n_trees * HK_MCTS_MAX_SEQ, s));   // entries past n_best stay zero
+    if (d_best && clear_best) HK_CUDA(cudaMemsetAsync(d_best, 0, sizeof(hk_game_state) * (size_t)f->n_trees * HK_MCTS_MAX_SEQ, s));   // entries past n_best stay zero
     constexpr int TPB = 32;                            // one warp per block: 32,768 trees spread over the 148 SMs as 1,024 blocks
     count_launch();
     seq_search_kernel<<<(unsigned)((f->n_trees + TPB - 1) / TPB), TPB, 0, s>>>(f->g->dev, f->trees, f->slabs, f->max_nodes, f->n_trees, iterations, seed, 0,
@@ -1374,7 +1374,7 @@ extern "C" int hk_mcts_forest_search(hk_mcts_forest* f, const hk_game_state* roo
     const int n = f->n_trees;
     bool any_fresh = false;
     for (int r = 0; r < n; ++r) {
-        if (fresh && !fresh[r]) continue;
+        if (fresh && fresh[r] <= 0) continue;
         any_fresh = true;
         if (!roots) { set_error("hk_mcts_forest_search: roots is NULL but tree %d is fresh", r); return HK_ERR_INVALID_ARGUMENT; }
         int rc = check_state(f->g, &roots[r], "hk_mcts_forest_search");

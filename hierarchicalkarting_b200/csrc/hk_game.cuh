@@ -45,6 +45,9 @@ struct ThreadCtx;
 int mcts_search_device(const hk_game* g, const hk_game_state* d_roots, int n_roots, int iterations, int rollouts_per_leaf, uint64_t seed,
                        hk_game_state* d_best, int* d_nbest, int* d_eps, double* d_vals, int* d_nnodes, int* d_status, ThreadCtx* c,
                        cudaStream_t s);
+// hk_mcts_forest_search on device pointers (d_fresh may be null = all fresh; a negative entry skips that tree), enqueued on `s`.
+int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, const int* d_fresh, int iterations, uint64_t seed,
+                           hk_game_state* d_best, int* d_nbest, int* d_nnodes, int* d_status, cudaStream_t s, bool clear_best = true);
 const hk_game_params& game_params_of(const hk_game* g);
 int game_karts_of(const hk_game* g);
 

@@ -14,7 +14,7 @@
 // memory only for the nodes on its path.  A warp per tree was the first candidate; it leaves 31 lanes idle in every table-driven ply
 // and its issue rate, not memory latency, bounds the launch (DESIGN.md §5.2 has the arithmetic and the measurement).
 //
-// Random sources (the oracle, oracle/hk_oracle_mcts.c, documents the same): tree r has key = seed + r.  Policy index of iteration `it`
+// Random sources (as include/hk_abi.h documents them; the CPU checker in tests/ draws the same): tree r has key = seed + r.  Policy index of iteration `it`
 // (counted over the life of the tree), ply p of the playout: word 0 of Philox4x32-10(key, (it, 0, p, 0)) through the closed-form
 // distribution g.cdf; initial pick of upperConfidenceStrategy (:169): word 0 of Philox4x32-10(key ^ 0x9E3779B97F4A7C15, (picks, 0, 0, 0))
 // modulo the child count.  totalValue is float32 and is updated in the reference's order, so trees are BIT-EQUAL to the oracle's.
@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
     __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_trees) return;
+    if (fresh && fresh[t] < 0) {                                       // this tree does not search in this call (its outputs stay untouched)
+        if (status_out) status_out[t] = 0;
+        return;
+    }
     const Tables tb(g);
     SeqTree& tr = trees[t];
     hk_mcts_node* nodes = slabs + (size_t)t * max_nodes;

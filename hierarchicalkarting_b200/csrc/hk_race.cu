@@ -152,7 +152,7 @@ __global__ void race_plan_fixed_kernel(const DevTrack* __restrict__ t, hk_race_p
 // u has `u_stride` doubles per kart (2: plain controls; 4: the LQNG u0 record of problem = kart, ego first).
 __global__ void race_step_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_karts, int episode_step, const double* __restrict__ u,
                                  int u_stride, const int* __restrict__ lqng_status, unsigned long long* status_count, hk_race_kart* karts,
-                                 hk_race_plan* plans)
+                                 hk_race_plan* plans, int* __restrict__ root_valid = nullptr, int* __restrict__ cycles = nullptr)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_karts) return;
@@ -219,6 +219,7 @@ __global__ void race_step_kernel(const DevTrack* __restrict__ t, hk_race_params 
         k.lane = lane_new;
         k.sectionStep = episode_step;
         if (k.section == p.goalSection) k.active = 0;                // ReachGoalSection (:652-655)
+        if (root_valid) { root_valid[i] = 0; cycles[i] = 0; }        // currentRoot = null; CyclesRootProcessed = 0 (:660-661)
     }
     karts[i] = k;
 }
@@ -357,12 +358,24 @@ namespace hk {
 // sectionWindow sections of the ego, all placed at the furthest one's section with the time they trail it by (float32 product, :211-214),
 // velocity bucket (0, bucket) (quirk B.6-1), player 0 (B.6-2), tyre age from the steering stat.  nearby[id][i] = race-local agent of
 // game kart i, -1 = none.  Same arithmetic as race.mcts_root_state / mcts_root_states_batch.
+// With a planner (fresh != null) the kernel also takes planWithMCTS's decision (:175, :265): fresh[id] = 1 new tree (currentRoot == null),
+// 0 continue the tree (CyclesRootProcessed < reuse_cycles), -1 no search (inactive agent, or the root has been reused enough); a
+// continued tree keeps the root and the `nearby` map it was built with.
 __global__ void race_mcts_root_kernel(const DevTrack* __restrict__ tr, hk_race_params p, int section_window, int time_precision, int n_agents,
                                       const hk_race_kart* __restrict__ karts, const hk_race_plan* __restrict__ plans,
-                                      hk_game_state* __restrict__ roots, int* __restrict__ nearby)
+                                      hk_game_state* __restrict__ roots, int* __restrict__ nearby,
+                                      const int* __restrict__ root_valid = nullptr, const int* __restrict__ cycles = nullptr, int reuse_cycles = 0,
+                                      int* __restrict__ fresh = nullptr, bool build_all = false)
 {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n_agents) return;
+    if (fresh) {
+        int f = 1;
+        if (!karts[id].active) f = -1;                                       // !m_envController.inactiveAgents.Contains(this) (:331)
+        else if (reuse_cycles > 0 && root_valid[id]) f = cycles[id] < reuse_cycles ? 0 : -1;   // :265 (reuse_cycles == 0: always a new tree)
+        fresh[id] = f;
+        if (f != 1 && !build_all) return;                                    // the leaf-parallel search runs over every root of the batch
+    }
     const int r2 = id & ~1, e = id & 1, L = tr->n;
     const int sec0 = karts[r2].section, sec1 = karts[r2 + 1].section, sec_e = e ? sec1 : sec0, sec_o = e ? sec0 : sec1;
     const bool near = abs(sec_o - sec_e) < section_window;
@@ -395,12 +408,21 @@ __global__ void race_mcts_root_kernel(const DevTrack* __restrict__ tr, hk_race_p
 
 // The waypoint hand-off of FixedUpdate (HierarchicalKartAgent.cs:366-402) from getBestStatesSequence: the ego's own lanes / velocities
 // for sections beyond the next checkpoint, and its belief about the other kart's.  Same as race.apply_best_states(_batch).
+// With a planner the kernel is the moment the background thread's result lands (:250-253, :271-273): only agents whose search was
+// started (fresh >= 0) take part; bestStates is replaced, currentRoot is the searched tree, CyclesRootProcessed = 1 after a new tree
+// and += 1 after a continued one (read at landing time: a checkpoint crossing in between has reset it).
 __global__ void race_mcts_apply_kernel(const DevTrack* __restrict__ tr, int n_agents, const hk_race_kart* __restrict__ karts,
                                        const int* __restrict__ nearby, const hk_game_state* __restrict__ best, const int* __restrict__ n_best,
-                                       hk_race_plan* __restrict__ plans)
+                                       hk_race_plan* __restrict__ plans, const int* __restrict__ fresh = nullptr, int* __restrict__ root_valid = nullptr,
+                                       int* __restrict__ cycles = nullptr)
 {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n_agents) return;
+    if (fresh) {
+        if (fresh[id] < 0) return;
+        root_valid[id] = 1;
+        cycles[id] = fresh[id] ? 1 : cycles[id] + 1;
+    }
     const int e = id & 1, L = tr->n, sec = karts[id].section, bound = sec + (sec == 0 ? 0 : 1);
     hk_race_plan& pl = plans[id];
     for (int k = 0; k < n_best[id]; ++k) {
@@ -417,14 +439,89 @@ __global__ void race_mcts_apply_kernel(const DevTrack* __restrict__ tr, int n_ag
 
 }  // namespace hk
 
-static int race_run_impl(const hk_track* t, const hk_race_params* p, const hk_game* game, int mcts_iterations, int mcts_rollouts, uint64_t mcts_seed,
-                         int n_races, int first_step, int n_steps, hk_race_kart* karts, hk_race_plan* plans, double* u_last,
-                         int64_t* lqng_status_nonzero)
+// ---- the MCTS high level of many races: planner state that survives between hk_race_run_planned calls -------------------------------
+struct hk_race_planner {
+    const hk_game* game = nullptr;
+    hk_race_mcts_params mp{};
+    int n_agents = 0;
+    hk_mcts_forest* forest = nullptr;     // mode 0: every agent's currentRoot
+    char* dev = nullptr;                  // one allocation: roots | best | nearby | n_best | fresh | root_valid | cycles | status
+    hk_game_state *roots = nullptr, *best = nullptr;
+    int *nearby = nullptr, *n_best = nullptr, *fresh = nullptr, *root_valid = nullptr, *cycles = nullptr, *status = nullptr;
+    int pending_step = -1;                // step at which the result of the search in flight lands (-1: none)
+};
+
+extern "C" void hk_race_planner_destroy(hk_race_planner* pl)
+{
+    if (!pl) return;
+    if (pl->forest) hk_mcts_forest_destroy(pl->forest);
+    if (pl->dev) cudaFree(pl->dev);
+    delete pl;
+}
+
+extern "C" int hk_race_planner_create(const hk_game* game, const hk_race_mcts_params* mp, int n_races, hk_race_planner** out)
+{
+    if (!game || !mp || !out || n_races < 1 || mp->iterations < 0 || mp->first_iterations < 0 || mp->reuse_cycles < 0 || mp->apply_delay < 0 ||
+        (mp->mode != 0 && mp->mode != 1) || (mp->mode == 1 && mp->rollouts_per_leaf < 1)) {
+        set_error("hk_race_planner_create: invalid argument (mode 0 | 1, budgets >= 0, rollouts_per_leaf >= 1 in mode 1)");
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    if (game_karts_of(game) < 2) { set_error("hk_race_planner_create: the game must have at least 2 karts"); return HK_ERR_INVALID_ARGUMENT; }
+    int rc = ensure_device();
+    if (rc != HK_OK) return rc;
+    hk_race_planner* pl = new hk_race_planner();
+    pl->game = game; pl->mp = *mp; pl->n_agents = 2 * n_races;
+    const size_t nb = (size_t)pl->n_agents;
+    if (mp->mode == 0) {
+        // a tree lives for one new search plus (normally) reuse_cycles - 1 continued ones — one more is reserved, see hk_race_mcts_params;
+        // a playout of a 2-kart root takes <= 2 depth plies
+        const long long big = mp->first_iterations > mp->iterations ? mp->first_iterations : mp->iterations;
+        const long long life = big + (long long)mp->reuse_cycles * mp->iterations;
+        const long long max_nodes = mp->max_tree_nodes > 0 ? mp->max_tree_nodes : 1 + life * 2 * game_params_of(game).treeSearchDepth;
+        if (max_nodes > (1ll << 30) || 2 * game_params_of(game).treeSearchDepth > HK_MAX_PLIES) { delete pl; set_error("hk_race_planner_create: trees too large"); return HK_ERR_INVALID_ARGUMENT; }
+        rc = hk_mcts_forest_create(game, pl->n_agents, (int)max_nodes, &pl->forest);
+        if (rc) { delete pl; return rc; }
+    }
+    const size_t sz[8] = {sizeof(hk_game_state) * nb, sizeof(hk_game_state) * nb * HK_MCTS_MAX_SEQ, 4 * nb * 2, 4 * nb, 4 * nb, 4 * nb, 4 * nb, 4 * nb};
+    size_t off[9]; off[0] = 0;
+    for (int i = 0; i < 8; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
+    cudaError_t e = cudaMalloc(&pl->dev, off[8]);
+    if (e == cudaSuccess) e = cudaMemset(pl->dev, 0, off[8]);
+    if (e != cudaSuccess) { set_error("hk_race_planner_create: %s", cudaGetErrorString(e)); cudaGetLastError(); hk_race_planner_destroy(pl); return HK_ERR_OUT_OF_MEMORY; }
+    pl->roots = (hk_game_state*)pl->dev; pl->best = (hk_game_state*)(pl->dev + off[1]); pl->nearby = (int*)(pl->dev + off[2]);
+    pl->n_best = (int*)(pl->dev + off[3]); pl->fresh = (int*)(pl->dev + off[4]); pl->root_valid = (int*)(pl->dev + off[5]);
+    pl->cycles = (int*)(pl->dev + off[6]); pl->status = (int*)(pl->dev + off[7]);
+    *out = pl;
+    return HK_OK;
+}
+
+// Synchronises every stream the calling thread's context owns: an error return must not leave copies in flight on the caller's buffers.
+static void drain(ThreadCtx* c)
+{
+    cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2);
+    for (auto& st : c->cstream) if (st) cudaStreamSynchronize(st);
+}
+#define HK_CUDA_DRAIN(call)                                                                             \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            hk::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);  \
+            drain(c);                                                                                   \
+            return e_ == cudaErrorMemoryAllocation ? HK_ERR_OUT_OF_MEMORY : HK_ERR_CUDA;                \
+        }                                                                                               \
+    } while (0)
+
+static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_planner* pl, int n_races, int first_step, int n_steps,
+                         hk_race_kart* karts, hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero)
 {
     int rc = check_track(t, p, "hk_race_run");
     if (rc) return rc;
     if (n_races < 0 || n_steps < 0 || first_step < 0 || (n_races > 0 && (!karts || !plans))) {
         set_error("hk_race_run: invalid argument");
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    if (pl && (pl->n_agents != 2 * n_races || !p->highModeMcts || pl->mp.apply_delay >= p->planEvery)) {
+        set_error("hk_race_run_planned: planner made for %d races, highModeMcts must be 1, apply_delay < planEvery", pl->n_agents / 2);
         return HK_ERR_INVALID_ARGUMENT;
     }
     if (lqng_status_nonzero) *lqng_status_nonzero = 0;
@@ -443,83 +540,108 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, const hk_ga
     unsigned long long* dcount = (unsigned long long*)(du + nb * 4);
     int* dst = (int*)(dcount + 1);
     cudaStream_t s = c->stream;
-    HK_CUDA(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
-    HK_CUDA(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
-    HK_CUDA(cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
+    HK_CUDA_DRAIN(cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), s));
     const unsigned blocks = (unsigned)((nb + 127) / 128);
-    // MCTS high level on the device (hk_race_run_mcts): root states, tree search, waypoint hand-off — nothing crosses PCIe
-    hk_game_state *mroots = nullptr, *mbest = nullptr;
-    int *mnear = nullptr, *mnbest = nullptr, *mstatus = nullptr;
-    if (game && p->highModeMcts) {
-        const size_t sz[5] = {sizeof(hk_game_state) * nb, sizeof(hk_game_state) * nb * HK_MCTS_MAX_SEQ, 8 * nb, 4 * nb, 4 * nb};
-        size_t off[6]; off[0] = 0;
-        for (int i = 0; i < 5; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
-        char* m = (char*)dscratch(c, 13, off[5]);
-        if (!m) return HK_ERR_OUT_OF_MEMORY;
-        mroots = (hk_game_state*)m; mbest = (hk_game_state*)(m + off[1]); mnear = (int*)(m + off[2]); mnbest = (int*)(m + off[3]); mstatus = (int*)(m + off[4]);
-        HK_CUDA(cudaMemsetAsync(mstatus, 0, sz[4], s));
-    }
-    int plan_events = 0;
+    int searches = 0;
     for (int step = first_step; step < first_step + n_steps; ++step) {
-        if (step > 0 && step % p->planEvery == 0) {                      // HKA:331-353 (0.5 Hz): planFixed or planWithMCTS by mode
-            if (!p->highModeMcts) {
+        // HKA:331-353 (0.5 Hz): planFixed or planWithMCTS by mode; MCTS agents also plan when the episode begins (:85-93, T = 1.5)
+        const bool replan = step > 0 && step % p->planEvery == 0;
+        if (replan && !p->highModeMcts) {
+            count_launch();
+            race_plan_fixed_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp);
+        } else if (pl) {                                                 // MCTS mode without a planner: the caller plans between two runs
+            const hk_game_params& gp = game_params_of(pl->game);
+            const hk_race_mcts_params& mp = pl->mp;
+            const bool begin = step == 0 && mp.first_iterations > 0;
+            if ((replan && step < gp.maxEpisodeSteps) || begin) {        // episodeSteps < maxEpisodeSteps (:331)
+                const int budget = begin ? mp.first_iterations : mp.iterations;
+                // tree of agent a searched by the event of step s: key = seed + (s / planEvery) n_agents + a — a function of the absolute
+                // step, so that a loop advanced in blocks draws the streams of one long call
+                const uint64_t seed = mp.seed + (uint64_t)(step / p->planEvery) * (uint64_t)nb;
                 count_launch();
-                race_plan_fixed_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp);
-            } else if (game) {
-                const hk_game_params& gp = game_params_of(game);
+                race_mcts_root_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, gp.sectionWindow, gp.timePrecision, (int)nb, dk, dp, pl->roots, pl->nearby,
+                                                            pl->root_valid, pl->cycles, mp.mode == 0 ? mp.reuse_cycles : 0, pl->fresh, mp.mode == 1);
+                HK_CUDA_DRAIN(cudaGetLastError());
+                if (mp.mode == 0) rc = mcts_seq_search_device(pl->forest, pl->roots, pl->fresh, budget, seed, pl->best, pl->n_best, nullptr, pl->status, s, false);
+                else rc = mcts_search_device(pl->game, pl->roots, (int)nb, budget, mp.rollouts_per_leaf, seed, pl->best, pl->n_best, nullptr, nullptr, nullptr, pl->status, c, s);
+                if (rc) { drain(c); return rc; }
+                pl->pending_step = step + mp.apply_delay;
+                ++searches;
+            }
+            if (pl->pending_step == step) {                              // the background thread's result lands (:250-253, :271-273), then FixedUpdate hands it off (:366-402)
                 count_launch();
-                race_mcts_root_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, gp.sectionWindow, gp.timePrecision, (int)nb, dk, dp, mroots, mnear);
-                HK_CUDA(cudaGetLastError());
-                rc = mcts_search_device(game, mroots, (int)nb, mcts_iterations, mcts_rollouts, mcts_seed + (uint64_t)plan_events * (uint64_t)nb, mbest,
-                                        mnbest, nullptr, nullptr, nullptr, mstatus, c, s);
-                if (rc) return rc;
-                count_launch();
-                race_mcts_apply_kernel<<<blocks, 128, 0, s>>>(t->dev, (int)nb, dk, mnear, mbest, mnbest, dp);
-                HK_CUDA(cudaGetLastError());
-                ++plan_events;
-            }                                                            // MCTS mode without a game: the caller plans between two runs
+                race_mcts_apply_kernel<<<blocks, 128, 0, s>>>(t->dev, (int)nb, dk, pl->nearby, pl->best, pl->n_best, dp, pl->fresh, pl->root_valid, pl->cycles);
+                HK_CUDA_DRAIN(cudaGetLastError());
+                pl->pending_step = -1;
+            }
         }
         count_launch();
         race_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp, dx0, dtg, dtw, dcw, daw, dot, dow);
-        HK_CUDA(cudaGetLastError());
+        HK_CUDA_DRAIN(cudaGetLastError());
         rc = lqng_assemble_launch((int)nb, 2, p->horizon, p->dt, dx0, dtg, dtw, dcw, daw, dot, dow, du, dst, s, 9);
-        if (rc) return rc;
+        if (rc) { drain(c); return rc; }
         count_launch();
-        race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp);
-        HK_CUDA(cudaGetLastError());
+        race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp, pl ? pl->root_valid : nullptr, pl ? pl->cycles : nullptr);
+        HK_CUDA_DRAIN(cudaGetLastError());
     }
-    HK_CUDA(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
-    HK_CUDA(cudaMemcpyAsync(plans, dp, nb * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(plans, dp, nb * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, s));
     unsigned long long count = 0;
-    HK_CUDA(cudaMemcpyAsync(&count, dcount, sizeof(count), cudaMemcpyDeviceToHost, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(&count, dcount, sizeof(count), cudaMemcpyDeviceToHost, s));
     if (u_last) {
         // u0 records are [problem][4] (ego controls first): compact to [race][2 agents][2] on the host side of the copy
         double* hu = (double*)hscratch(c, 2, nb * 4 * sizeof(double));
-        if (!hu) return HK_ERR_OUT_OF_MEMORY;
-        HK_CUDA(cudaMemcpyAsync(hu, du, nb * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-        HK_CUDA(cudaStreamSynchronize(s));
+        if (!hu) { drain(c); return HK_ERR_OUT_OF_MEMORY; }
+        HK_CUDA_DRAIN(cudaMemcpyAsync(hu, du, nb * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        HK_CUDA_DRAIN(cudaStreamSynchronize(s));
         for (size_t b = 0; b < nb; ++b) { u_last[b * 2] = hu[b * 4]; u_last[b * 2 + 1] = hu[b * 4 + 1]; }
     }
     std::vector<int> mst;
-    if (mstatus && plan_events) { mst.resize(nb); HK_CUDA(cudaMemcpyAsync(mst.data(), mstatus, 4 * nb, cudaMemcpyDeviceToHost, s)); }
-    HK_CUDA(cudaStreamSynchronize(s));
+    if (pl && searches) { mst.resize(nb); HK_CUDA_DRAIN(cudaMemcpyAsync(mst.data(), pl->status, 4 * nb, cudaMemcpyDeviceToHost, s)); }
+    HK_CUDA_DRAIN(cudaStreamSynchronize(s));
     if (lqng_status_nonzero) *lqng_status_nonzero = (int64_t)count;
     for (size_t a = 0; a < mst.size(); ++a)
-        if (mst[a]) { set_error("hk_race_run_mcts: upNext() == -1 reached in the tree of agent %zu (KartDiscreteGame.cs:326 would throw)", a); return HK_ERR_NO_UPNEXT; }
+        if (mst[a] == 1) { set_error("hk_race_run_planned: upNext() == -1 reached in the tree of agent %zu (KartDiscreteGame.cs:326 would throw)", a); return HK_ERR_NO_UPNEXT; }
     return HK_OK;
 }
 
 extern "C" int hk_race_run(const hk_track* t, const hk_race_params* p, int n_races, int first_step, int n_steps, hk_race_kart* karts,
                            hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero)
 {
-    return race_run_impl(t, p, nullptr, 0, 0, 0, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
+    return race_run_impl(t, p, nullptr, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
+}
+
+extern "C" int hk_race_run_planned(const hk_track* t, const hk_race_params* p, hk_race_planner* planner, int n_races, int first_step, int n_steps,
+                                   hk_race_kart* karts, hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero)
+{
+    if (!planner) { set_error("hk_race_run_planned: planner is NULL"); return HK_ERR_INVALID_ARGUMENT; }
+    return race_run_impl(t, p, planner, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
+}
+
+extern "C" int hk_race_planner_state(const hk_race_planner* planner, int32_t* root_valid, int32_t* cycles, int32_t* tree_status)
+{
+    if (planner && tree_status) HK_CUDA(cudaMemcpy(tree_status, planner->status, 4 * (size_t)planner->n_agents, cudaMemcpyDeviceToHost));
+    if (!planner) { set_error("hk_race_planner_state: planner is NULL"); return HK_ERR_INVALID_ARGUMENT; }
+    if (root_valid) HK_CUDA(cudaMemcpy(root_valid, planner->root_valid, 4 * (size_t)planner->n_agents, cudaMemcpyDeviceToHost));
+    if (cycles) HK_CUDA(cudaMemcpy(cycles, planner->cycles, 4 * (size_t)planner->n_agents, cudaMemcpyDeviceToHost));
+    return HK_OK;
 }
 
 extern "C" int hk_race_run_mcts(const hk_track* t, const hk_race_params* p, const hk_game* game, int iterations, int rollouts_per_leaf,
                                 uint64_t seed, int n_races, int first_step, int n_steps, hk_race_kart* karts, hk_race_plan* plans,
                                 double* u_last, int64_t* lqng_status_nonzero)
 {
-    if (!game || iterations < 0 || rollouts_per_leaf < 1 || !p || !p->highModeMcts) { set_error("hk_race_run_mcts: needs a game, highModeMcts = 1, rollouts_per_leaf >= 1"); return HK_ERR_INVALID_ARGUMENT; }
-    if (game_karts_of(game) < 2) { set_error("hk_race_run_mcts: the game must have at least 2 karts"); return HK_ERR_INVALID_ARGUMENT; }
-    return race_run_impl(t, p, game, iterations, rollouts_per_leaf, seed, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
+    if (!game || iterations < 0 || rollouts_per_leaf < 0 || !p || !p->highModeMcts) { set_error("hk_race_run_mcts: needs a game, highModeMcts = 1, rollouts_per_leaf >= 0"); return HK_ERR_INVALID_ARGUMENT; }
+    if (n_races <= 0 || n_steps <= 0) return race_run_impl(t, p, nullptr, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
+    hk_race_mcts_params mp{};
+    mp.mode = rollouts_per_leaf > 0 ? 1 : 0; mp.iterations = iterations; mp.first_iterations = 0; mp.rollouts_per_leaf = rollouts_per_leaf;
+    mp.reuse_cycles = 0; mp.apply_delay = 0; mp.seed = seed; mp.max_tree_nodes = 0; mp.pad_ = 0;
+    hk_race_planner* pl = nullptr;
+    int rc = hk_race_planner_create(game, &mp, n_races, &pl);
+    if (rc) return rc;
+    rc = race_run_impl(t, p, pl, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
+    hk_race_planner_destroy(pl);
+    return rc;
 }

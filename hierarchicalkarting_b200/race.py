@@ -116,6 +116,15 @@ class Races:
         return u, bad.value
 
 
+    def run_planned(self, karts: np.ndarray, plans: np.ndarray, planner: "Planner", first_step: int, n_steps: int):
+        """hk_race_run_planned: the loop with the MCTS high level on the GPU and the planner's state carried between calls."""
+        n_races = karts.shape[0]
+        u = np.zeros((n_races, 2, 2))
+        bad = C.c_int64(0)
+        abi.check(abi.load_library().hk_race_run_planned(self._h, C.byref(self.params), planner._h, n_races, first_step, n_steps,
+                                                         abi.vptr(karts), abi.vptr(plans), abi.dptr(u), C.byref(bad)))
+        return u, bad.value
+
     def run_mcts(self, karts: np.ndarray, plans: np.ndarray, game, iterations: int, rollouts_per_leaf: int, seed: int, first_step: int,
                  n_steps: int):
         """hk_race_run_mcts: the loop with the MCTS high level entirely on the GPU (root states, tree search, waypoint hand-off between
@@ -126,6 +135,37 @@ class Races:
         abi.check(abi.load_library().hk_race_run_mcts(self._h, C.byref(self.params), game._h, iterations, rollouts_per_leaf, seed, n_races,
                                                       first_step, n_steps, abi.vptr(karts), abi.vptr(plans), abi.dptr(u), C.byref(bad)))
         return u, bad.value
+
+
+class Planner:
+    """hk_race_planner: the MCTS high level of a batch of races — per agent the device-resident tree (currentRoot), CyclesRootProcessed
+    and the pending result of a search (HierarchicalKartAgent.cs:172-283, 331-353, 660-661)."""
+
+    def __init__(self, game, n_races: int, iterations: int, seed: int = 0, mode: int = 0, first_iterations: int = 0,
+                 rollouts_per_leaf: int = 0, reuse_cycles: int = 3, apply_delay: int = 0, max_tree_nodes: int = 0):
+        self.params = abi.hk_race_mcts_params(mode=mode, iterations=iterations, first_iterations=first_iterations,
+                                              rollouts_per_leaf=rollouts_per_leaf, reuse_cycles=reuse_cycles, apply_delay=apply_delay, seed=seed,
+                                              max_tree_nodes=max_tree_nodes)
+        self.game, self.n_races = game, n_races
+        self._h = C.c_void_p()
+        abi.check(abi.load_library().hk_race_planner_create(game._h, C.byref(self.params), n_races, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            abi.load_library().hk_race_planner_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def state(self):
+        """(root_valid, cycles, tree_status), each [n_races][2]"""
+        rv, cy, ts = (np.zeros((self.n_races, 2), np.int32) for _ in range(3))
+        abi.check(abi.load_library().hk_race_planner_state(self._h, abi.vptr(rv), abi.vptr(cy), abi.vptr(ts)))
+        return rv, cy, ts
 
 
 # ---- MCTS high level: root state and waypoint hand-off (SURVEY.md §8f rank 3) ----------------------------------------

@@ -229,8 +229,8 @@ int hk_mcts_search_batch(const hk_game* g, const hk_game_state* roots, int n_roo
  * (:108-122).  The reference's wall-clock budget T (:55) becomes an iteration count.  One GPU thread owns one tree, so the call pays
  * off for many trees at once (every agent of many races); a single tree runs at the latency of one thread.
  * Trees live in a device-resident forest and survive between calls, as HierarchicalKartAgent.currentRoot does (:265-283): tree r is
- * (re)started from roots[r] where fresh[r] != 0 (constructSearchTree(state), fresh == NULL: all), and continued otherwise
- * (constructSearchTree(root); roots[r] is ignored).  Random sources: tree r started by a call with `seed` has key = seed + r for life;
+ * (re)started from roots[r] where fresh[r] > 0 (constructSearchTree(state), fresh == NULL: all), continued where fresh[r] == 0
+ * (constructSearchTree(root); roots[r] is ignored) and left alone where fresh[r] < 0 (its outputs are not written).  Random sources: tree r started by a call with `seed` has key = seed + r for life;
  * policy index of iteration `it` (counted over the life of the tree), ply p of its playout = word 0 of Philox4x32-10(key, counter
  * (it, 0, p, 0)) through hk_policy_cdf; the random initial pick of upperConfidenceStrategy (:169) = word 0 of
  * Philox4x32-10(key ^ 0x9E3779B97F4A7C15, counter (picks so far, 0, 0, 0)) modulo the child count.  totalValue is float32, updated in
@@ -353,12 +353,46 @@ int hk_race_run(const hk_track* t, const hk_race_params* p, int n_races, int fir
                 hk_race_kart* karts, hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero);
 
 /*
- * The same loop with the MCTS high level (HighLevelMode.MCTS, HierarchicalKartAgent.cs:331-353; p->highModeMcts must be 1): when
- * episodeSteps % planEvery == 0 and > 0 every agent replans by planWithMCTS (:180-283) + the waypoint hand-off (:366-402) ON THE
- * DEVICE — root states, hk_mcts_search_batch's tree search (`iterations` x `rollouts_per_leaf`, one thread block per agent's tree)
- * and the hand-off are kernels between two steps; karts / plans cross PCIe only at the start and the end of the call.  The k-th
- * planning event of the call searches agent a (= 2 race + ego) as root index k * 2 n_races + a of `seed` (hk_mcts_search_batch).
+ * The same loop with the MCTS high level (HighLevelMode.MCTS, HierarchicalKartAgent.cs:331-353; p->highModeMcts must be 1), entirely ON
+ * THE DEVICE: root states (planWithMCTS :180-245), tree search and the waypoint hand-off (:366-402) are kernels between two steps;
+ * karts / plans cross PCIe only at the start and the end of a call.  A planner holds what survives between planning events and between
+ * calls — per agent the tree (currentRoot), CyclesRootProcessed, and the result of a search whose background thread has not finished:
+ *   - a planning event happens when episodeSteps % planEvery == 0, 0 < episodeSteps < maxEpisodeSteps (:331), for active agents, and
+ *     (first_iterations > 0) when the episode begins (step 0: planWithMCTS(T: 1.5), :85-93);
+ *   - an agent without a tree starts a new one from its current root state (:175-262); an agent whose tree is still valid continues it
+ *     while CyclesRootProcessed < reuse_cycles (:265-283) and otherwise does not plan at all; crossing a checkpoint drops the tree
+ *     (currentRoot = null; CyclesRootProcessed = 0, :660-661);
+ *   - the result (bestStates, CyclesRootProcessed = 1 / += 1) lands apply_delay steps after the search started — the reference searches
+ *     on a background thread for T seconds of wall clock (:246-283), i.e. T / fixedDeltaTime physics steps; 0 = at once — and is handed
+ *     to the plan tables at that step.
+ * Tree of agent a (= 2 race + ego) searched by the event of step s: key = seed + (s / planEvery) * n_agents + a (hk_mcts_forest_search /
+ * hk_mcts_search_batch streams), a function of the absolute step, so a loop advanced in blocks equals one long call.
  */
+typedef struct hk_race_mcts_params {
+    int32_t  mode;               /* 0: the sequential search the reference runs (hk_mcts_forest_search); 1: leaf-parallel (hk_mcts_search_batch) */
+    int32_t  iterations;         /* budget of a replan (the reference: T = 0.9 s of wall clock, HierarchicalKartAgent.cs:172,271) */
+    int32_t  first_iterations;   /* budget of the plan at episode start (T = 1.5 s, :93); 0 = no plan at step 0 */
+    int32_t  rollouts_per_leaf;  /* mode 1 only */
+    int32_t  reuse_cycles;       /* mode 0: bound on CyclesRootProcessed (3, :265); 0 = every plan starts a new tree */
+    int32_t  apply_delay;        /* steps between the start of a search and the landing of its result; must be < planEvery */
+    uint64_t seed;
+    int32_t  max_tree_nodes;     /* mode 0: nodes reserved per agent's tree; 0 = 1 + (max(first_iterations, iterations) + reuse_cycles *
+                                    iterations) * 2 treeSearchDepth.  A checkpoint crossing while a continued search is in flight resets
+                                    CyclesRootProcessed, so a tree CAN be continued more often than reuse_cycles; a tree that runs out of
+                                    nodes stops growing (tree_status 3 in hk_race_planner_state) */
+    int32_t  pad_;
+} hk_race_mcts_params;
+
+typedef struct hk_race_planner hk_race_planner;
+int  hk_race_planner_create(const hk_game* game, const hk_race_mcts_params* mp, int n_races, hk_race_planner** out);
+void hk_race_planner_destroy(hk_race_planner* planner);
+/* per agent: currentRoot != null, CyclesRootProcessed, status of the tree's last search as in hk_mcts_forest_search (each may be NULL) */
+int  hk_race_planner_state(const hk_race_planner* planner, int32_t* root_valid, int32_t* cycles, int32_t* tree_status);
+int  hk_race_run_planned(const hk_track* t, const hk_race_params* p, hk_race_planner* planner, int n_races, int first_step, int n_steps,
+                         hk_race_kart* karts, hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero);
+
+/* One-call form without state between calls: a temporary planner with reuse_cycles = 0, apply_delay = 0, first_iterations = 0;
+ * rollouts_per_leaf == 0 selects mode 0 (the reference's sequential search), > 0 mode 1 (leaf-parallel). */
 int hk_race_run_mcts(const hk_track* t, const hk_race_params* p, const hk_game* game, int iterations, int rollouts_per_leaf,
                      uint64_t seed, int n_races, int first_step, int n_steps, hk_race_kart* karts, hk_race_plan* plans,
                      double* u_last, int64_t* lqng_status_nonzero);

@@ -49,6 +49,8 @@ int  hk_oracle_tree_size(const hk_oracle_tree* t);
 long long hk_oracle_tree_children_as_root(const hk_oracle_tree* t);
 void hk_oracle_tree_dump(const hk_oracle_tree* t, int32_t* parent, int32_t* gen, float* totalValue, int32_t* numEpisodes,
                          int32_t* n_children, int32_t* first_child, int32_t* next_sibling, hk_game_state* states);
+void hk_oracle_tree_set_key(hk_oracle_tree* t, uint64_t key);
+uint64_t hk_oracle_tree_key(const hk_oracle_tree* t);
 int  hk_oracle_tree_search_batch(const hk_oracle_game* g, const hk_game_state* roots, int n, int iterations, int mode, uint64_t seed,
                                  const uint64_t* rng_states, hk_game_state* best, int32_t* n_best, int max_seq, int32_t* root_gen,
                                  int32_t* root_episodes, float* root_values, int32_t* n_nodes, int threads);
@@ -67,6 +69,18 @@ void hk_oracle_race_step(const hk_section* sections, const double* trig, const d
 long long hk_oracle_race_run(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
                              const hk_race_params* p, int n_races, int first_step, int n_steps, hk_race_kart* karts,
                              hk_race_plan* plans, double* u_last);
+/* MCTS high level of the loop (hk_oracle_race.c): planWithMCTS's root state, the waypoint hand-off, the planner's schedule */
+int  hk_oracle_race_mcts_root(const hk_race_params* p, const hk_game_params* gp, int n_sections, const hk_race_kart* karts,
+                              const hk_race_plan* plans, int n_agents_in_race, int ego, hk_game_state* st, int* nearby);
+void hk_oracle_race_apply_best(int n_sections, const hk_race_kart* karts, hk_race_plan* plans, int ego, const int* nearby,
+                               const hk_game_state* best, int n_best);
+typedef struct hk_oracle_planner hk_oracle_planner;
+hk_oracle_planner* hk_oracle_planner_create(const hk_oracle_game* g, const hk_game_params* gp, const hk_race_mcts_params* mp, int n_races);
+void hk_oracle_planner_destroy(hk_oracle_planner* pl);
+void hk_oracle_planner_state(const hk_oracle_planner* pl, int32_t* root_valid, int32_t* cycles);
+long long hk_oracle_race_run_planned(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                                     const hk_race_params* p, hk_oracle_planner* pl, int n_races, int first_step, int n_steps,
+                                     hk_race_kart* karts, hk_race_plan* plans, double* u_last);
 /* helpers for the KAT tests (track formulas) */
 float hk_oracle_distance_to_travel(const hk_section* s, int a, int b);
 float hk_oracle_radius_of_lane(const hk_section* s, int a, int b);

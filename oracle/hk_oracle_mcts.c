@@ -43,6 +43,7 @@ struct hk_oracle_tree {
     const hk_oracle_game* g;
     onode* nodes;
     int n_nodes, cap_nodes;
+    uint64_t key;               /* optional: the Philox key the owner of the tree searches it with */
     uint64_t picks;             /* upperConfidenceStrategy calls so far */
     uint64_t iters;             /* search iterations so far */
     long long childrenAsRoot;   /* root.childrenAsRoot (:64) */
@@ -207,6 +208,9 @@ int hk_oracle_tree_best_states(hk_oracle_tree* t, int mode, uint64_t key, uint64
 }
 
 int hk_oracle_tree_size(const hk_oracle_tree* t) { return t->n_nodes; }
+/* a tree keeps the key it was started with (HierarchicalKartAgent.currentRoot continues its own random streams) */
+void hk_oracle_tree_set_key(hk_oracle_tree* t, uint64_t key) { t->key = key; }
+uint64_t hk_oracle_tree_key(const hk_oracle_tree* t) { return t->key; }
 long long hk_oracle_tree_children_as_root(const hk_oracle_tree* t) { return t->childrenAsRoot; }
 
 /* nodes in creation order; any output may be NULL.  first_child / next_sibling give the insertion-ordered child lists. */

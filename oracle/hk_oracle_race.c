@@ -245,3 +245,189 @@ long long hk_oracle_race_run(const hk_section* sections, const double* trig, con
     }
     return bad;
 }
+
+/* ---- MCTS high level of the loop: planWithMCTS's root state, the waypoint hand-off, and the planner's schedule --------------------------
+ * Restated from HierarchicalKartAgent.cs (not from the CUDA library or its host mirrors):
+ *   root state            :180-245  (nearby agents within sectionWindow sections, all placed at the furthest one's section; velocity bucket
+ *                                    (0, bucket) because the search loop breaks at i = 0, quirk B.6-1; player = 0, quirk B.6-2)
+ *   schedule              :85-93 (plan at episode start, T = 1.5), :331-353 (every planEvery steps), :175 / :265 (new tree / continue while
+ *                          CyclesRootProcessed < 3 / nothing), :250-253, :271-273 (what the background thread sets when it finishes),
+ *                          :660-661 (a checkpoint crossing drops the tree)
+ *   hand-off              :366-402
+ * 2-kart races; each kart is its own team (getTeamID of the head-to-head scenes). */
+int hk_oracle_race_mcts_root(const hk_race_params* p, const hk_game_params* gp, int n_sections, const hk_race_kart* karts,
+                             const hk_race_plan* plans, int n_agents_in_race, int ego, hk_game_state* st, int* nearby)
+{
+    const int me_sec = karts[ego].section;
+    int initial = me_sec, furthest = ego, n = 0;
+    for (int a = 0; a < n_agents_in_race; ++a) {                                        /* :182-193 */
+        if (abs(karts[a].section - me_sec) < gp->sectionWindow) {
+            nearby[n++] = a;
+            if (karts[a].section > initial) initial = karts[a].section;
+            if (initial == karts[a].section) furthest = a;
+        }
+    }
+    for (int i = n; i < HK_MAX_KARTS; ++i) nearby[i] = -1;
+    memset(st, 0, sizeof(*st));
+    st->n_karts = n;
+    st->initialSection = initial; st->lastCompletedSection = initial; st->finalSection = initial + gp->treeSearchDepth;   /* :194, :235-245 */
+    const int max_speed = (int)p->topSpeed;                                             /* (int)GetMaxSpeed() */
+    for (int i = 0; i < n; ++i) {
+        const hk_race_kart* k = &karts[nearby[i]];
+        hk_kart_state* ks = &st->karts[i];
+        ks->min_velocity = 0;                                                            /* the loop :200-208 breaks at i = 0: |v| >= 0 */
+        ks->max_velocity = gp->velocityBucketSize < max_speed ? gp->velocityBucketSize : max_speed;
+        int t_at = 0;
+        if (k->section != initial) {                                                     /* :211-214: int * float * int, then (int) */
+            const int d = plans[nearby[i]].sectionTimes[k->section % n_sections] - plans[furthest].sectionTimes[k->section % n_sections];
+            t_at = (int)(((float)d * 0.02f) * (float)gp->timePrecision);
+        }
+        ks->player = 0;                                                                  /* count is never incremented (:195, :221) */
+        ks->team = nearby[i];
+        ks->section = initial;
+        ks->timeAtSection = t_at;
+        ks->lane = k->lane;
+        ks->tireAge = (int)((4.0f - k->steer) / (4.0f - 1.0f) * 10000);                  /* (MaxSteer - Steer) / (MaxSteer - MinSteer) * 10000, :226 */
+        ks->laneChanges = k->laneChanges;
+        ks->infeasible = 0;
+    }
+    return n;
+}
+
+void hk_oracle_race_apply_best(int n_sections, const hk_race_kart* karts, hk_race_plan* plans, int ego, const int* nearby,
+                               const hk_game_state* best, int n_best)
+{
+    const int sec = karts[ego].section;
+    hk_race_plan* pl = &plans[ego];
+    for (int b = 0; b < n_best; ++b)                                                     /* foreach gameState in bestStates :366 */
+        for (int i = 0; i < best[b].n_karts; ++i) {                                      /* foreach kartState :368 */
+            const hk_kart_state* ks = &best[b].karts[i];
+            const int key = ks->section % n_sections;
+            if (nearby[i] == ego && ks->section > sec + (sec == 0 ? 0 : 1)) {            /* :371 */
+                pl->lane[key] = (int8_t)ks->lane;                                        /* :381-382 */
+                pl->vel[key] = (float)ks->max_velocity;
+            } else if (nearby[i] != ego && nearby[i] >= 0) {                             /* :395-400 */
+                pl->oppLane[key] = (int8_t)ks->lane;
+                pl->oppVel[key] = (float)ks->max_velocity;
+            }
+        }
+}
+
+typedef struct {
+    hk_oracle_tree* tree;       /* currentRoot */
+    int root_valid, cycles;     /* currentRoot != null, CyclesRootProcessed */
+    int pending;                /* a search result has not landed yet */
+    int pending_fresh;
+    int nearby[HK_MAX_KARTS];
+    hk_game_state best[HK_MCTS_MAX_SEQ];
+    int n_best;
+} oagent;
+
+struct hk_oracle_planner {
+    const hk_oracle_game* g;
+    hk_game_params gp;
+    hk_race_mcts_params mp;
+    int n_agents, pending_step;
+    oagent* a;
+};
+
+hk_oracle_planner* hk_oracle_planner_create(const hk_oracle_game* g, const hk_game_params* gp, const hk_race_mcts_params* mp, int n_races)
+{
+    hk_oracle_planner* pl = (hk_oracle_planner*)calloc(1, sizeof(*pl));
+    pl->g = g; pl->gp = *gp; pl->mp = *mp; pl->n_agents = 2 * n_races; pl->pending_step = -1;
+    pl->a = (oagent*)calloc((size_t)pl->n_agents, sizeof(oagent));
+    return pl;
+}
+
+void hk_oracle_planner_destroy(hk_oracle_planner* pl)
+{
+    if (!pl) return;
+    for (int i = 0; i < pl->n_agents; ++i) hk_oracle_tree_destroy(pl->a[i].tree);
+    free(pl->a); free(pl);
+}
+
+void hk_oracle_planner_state(const hk_oracle_planner* pl, int32_t* root_valid, int32_t* cycles)
+{
+    for (int i = 0; i < pl->n_agents; ++i) { if (root_valid) root_valid[i] = pl->a[i].root_valid; if (cycles) cycles[i] = pl->a[i].cycles; }
+}
+
+/* The loop of hk_oracle_race_run with the MCTS high level (sequential search only).  Returns the number of LQNG solves with a zero
+ * pivot, or -1 if a search failed. */
+long long hk_oracle_race_run_planned(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                                     const hk_race_params* p, hk_oracle_planner* pl, int n_races, int first_step, int n_steps,
+                                     hk_race_kart* karts, hk_race_plan* plans, double* u_last)
+{
+    long long bad = 0;
+    int failed = 0;
+    for (int step = first_step; step < first_step + n_steps; ++step) {
+        const int replan = step > 0 && step % p->planEvery == 0 && step < pl->gp.maxEpisodeSteps;     /* :331 */
+        const int begin = step == 0 && pl->mp.first_iterations > 0;                                  /* :85-93 */
+        if (replan || begin) {
+            const int budget = begin ? pl->mp.first_iterations : pl->mp.iterations;
+            const uint64_t seed = pl->mp.seed + (uint64_t)(step / p->planEvery) * (uint64_t)pl->n_agents;
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int id = 0; id < pl->n_agents; ++id) {
+                oagent* ag = &pl->a[id];
+                const int r2 = id & ~1, ego = id & 1;
+                ag->pending = 0;
+                if (!karts[id].active) continue;                                                      /* inactiveAgents.Contains(this) */
+                uint64_t rng = 1;
+                int fresh;
+                if (!(pl->mp.reuse_cycles > 0 && ag->root_valid)) {                                   /* currentRoot == null (:175) */
+                    hk_game_state root;
+                    hk_oracle_race_mcts_root(p, &pl->gp, n_sections, karts + r2, plans + r2, 2, ego, &root, ag->nearby);
+                    hk_oracle_tree_destroy(ag->tree);
+                    ag->tree = hk_oracle_tree_create(pl->g, &root);
+                    hk_oracle_tree_set_key(ag->tree, seed + (uint64_t)id);
+                    fresh = 1;
+                } else if (ag->cycles < pl->mp.reuse_cycles) {                                        /* :265 */
+                    fresh = 0;
+                } else continue;
+                const uint64_t key = hk_oracle_tree_key(ag->tree);
+                if (hk_oracle_tree_search(ag->tree, budget, 0, key, &rng) == -1) {
+#pragma omp atomic write
+                    failed = 1;
+                }
+                ag->n_best = hk_oracle_tree_best_states(ag->tree, 0, key, &rng, ag->best, HK_MCTS_MAX_SEQ);
+                ag->pending = 1; ag->pending_fresh = fresh;
+            }
+            pl->pending_step = step + pl->mp.apply_delay;
+        }
+        if (pl->pending_step == step) {                                                               /* the thread finishes; FixedUpdate hands off */
+            for (int id = 0; id < pl->n_agents; ++id) {
+                oagent* ag = &pl->a[id];
+                if (!ag->pending) continue;
+                const int r2 = id & ~1, ego = id & 1;
+                ag->root_valid = 1;                                                                   /* currentRoot = ... (:250, :271) */
+                ag->cycles = ag->pending_fresh ? 1 : ag->cycles + 1;                                  /* :253, :273 */
+                hk_oracle_race_apply_best(n_sections, karts + r2, plans + r2, ego, ag->nearby, ag->best, ag->n_best);
+                ag->pending = 0;
+            }
+            pl->pending_step = -1;
+        }
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+        for (int r = 0; r < n_races; ++r) {
+            double u[4];
+            int sec_before[2] = {karts[2 * r].section, karts[2 * r + 1].section};
+            for (int e = 0; e < 2; ++e) {
+                double x0[8], target[8], tw[8], cw[2], aw[4], otgt[8], otw[6];
+                hk_oracle_race_recipe_one(sections, trig, fwd, lane, n_sections, p, karts + 2 * r, plans + 2 * r, e, x0, target, tw,
+                                          cw, aw, otgt, otw);
+                double A[2 * 16], B[2 * 8], Q[2 * 64], q[2 * 8], R[2 * 4], u0[4];
+                for (int i = 0; i < 2; ++i) {
+                    hk_oracle_bicycle_A(p->dt, x0 + 4 * i, A + 16 * i);
+                    hk_oracle_bicycle_B(p->dt, B + 8 * i);
+                    hk_oracle_cost(1, target + 4 * i, tw + 4 * i, cw[i], aw + 2 * i, otgt + 4 * i, otw + 3 * i, Q + 64 * i, q + 8 * i,
+                                   R + 4 * i);
+                }
+                bad += hk_oracle_lqng_solve(2, p->horizon, 0, A, B, Q, q, R, x0, u0, NULL, NULL, NULL) != 0;
+                u[2 * e] = u0[0]; u[2 * e + 1] = u0[1];
+            }
+            if (u_last) memcpy(u_last + 4 * (size_t)r, u, sizeof(u));
+            hk_oracle_race_step(sections, trig, fwd, lane, n_sections, p, 2, step, u, karts + 2 * r, plans + 2 * r);
+            for (int e = 0; e < 2; ++e)
+                if (karts[2 * r + e].section != sec_before[e]) { pl->a[2 * r + e].root_valid = 0; pl->a[2 * r + e].cycles = 0; }   /* :660-661 */
+        }
+    }
+    return failed ? -1 : bad;
+}

@@ -302,7 +302,67 @@ class Races:
         u = np.ascontiguousarray(u, dtype=np.float64).reshape(karts.size, 2)
         lib().hk_oracle_race_step(*self._geo(), karts.size, episode_step, _p(u), S.ref(karts), S.ref(plans))
 
+    def mcts_root(self, game_params, karts_race, plans_race, ego):
+        """planWithMCTS's root state for agent `ego` of one race (hk_oracle_race_mcts_root). Returns (hk_game_state, nearby list)."""
+        L = lib()
+        L.hk_oracle_race_mcts_root.argtypes = [_vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _ip]
+        st = S.hk_game_state()
+        nearby = (C.c_int32 * S.HK_MAX_KARTS)()
+        n = L.hk_oracle_race_mcts_root(C.byref(self.params), C.byref(game_params), self.n, S.ref(karts_race), S.ref(plans_race),
+                                       karts_race.shape[0], ego, C.byref(st), nearby)
+        return st, [nearby[i] for i in range(n)]
+
+    def apply_best(self, karts_race, plans_race, ego, nearby, best_states):
+        """The waypoint hand-off (hk_oracle_race_apply_best); best_states: list of objects with hk_game_state's bytes."""
+        L = lib()
+        L.hk_oracle_race_apply_best.argtypes = [C.c_int, _vp, _vp, C.c_int, _ip, _vp, C.c_int]
+        nb = len(best_states)
+        arr = (S.hk_game_state * max(nb, 1))(*[S.game_state(b) for b in best_states])
+        near = (C.c_int32 * S.HK_MAX_KARTS)(*(list(nearby) + [-1] * (S.HK_MAX_KARTS - len(nearby))))
+        L.hk_oracle_race_apply_best(self.n, S.ref(karts_race), S.ref(plans_race), ego, near, arr, nb)
+
+    def planner(self, game: "Game", game_params, n_races: int, iterations: int, seed: int = 0, first_iterations: int = 0,
+                reuse_cycles: int = 3, apply_delay: int = 0):
+        return Planner(self, game, game_params, n_races, S.hk_race_mcts_params(mode=0, iterations=iterations, first_iterations=first_iterations,
+                                                                               rollouts_per_leaf=0, reuse_cycles=reuse_cycles,
+                                                                               apply_delay=apply_delay, seed=seed))
+
     def run(self, karts, plans, first_step, n_steps):
         u = np.zeros((karts.shape[0], 2, 2))
         bad = lib().hk_oracle_race_run(*self._geo(), karts.shape[0], first_step, n_steps, S.ref(karts), S.ref(plans), _p(u))
+        return u, int(bad)
+
+
+class Planner:
+    """hk_oracle_planner: the MCTS high level of the oracle's race loop (sequential search; schedule of HierarchicalKartAgent.cs:85-93,
+    172-283, 331-353, 660-661)."""
+
+    def __init__(self, races: Races, game: Game, game_params, n_races: int, mp):
+        L = lib()
+        L.hk_oracle_planner_create.argtypes = [_vp, _vp, _vp, C.c_int]
+        L.hk_oracle_planner_create.restype = C.c_void_p
+        L.hk_oracle_planner_destroy.argtypes = [_vp]
+        L.hk_oracle_planner_state.argtypes = [_vp, _vp, _vp]
+        L.hk_oracle_race_run_planned.argtypes = [_vp, _dp, _dp, _dp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _dp]
+        L.hk_oracle_race_run_planned.restype = C.c_longlong
+        self.races, self.game, self.n_races, self.mp = races, game, n_races, mp
+        self._h = C.c_void_p(L.hk_oracle_planner_create(game._h, C.byref(game_params), C.byref(mp), n_races))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().hk_oracle_planner_destroy(self._h)
+            self._h = None
+
+    def state(self):
+        rv, cy = np.zeros((self.n_races, 2), np.int32), np.zeros((self.n_races, 2), np.int32)
+        lib().hk_oracle_planner_state(self._h, S.ref(rv), S.ref(cy))
+        return rv, cy
+
+    def run(self, karts, plans, first_step, n_steps):
+        u = np.zeros((karts.shape[0], 2, 2))
+        R = self.races
+        bad = lib().hk_oracle_race_run_planned(R.sections, _p(R.trig), _p(R.fwd), _p(R.lane), R.n, C.byref(R.params), self._h,
+                                               karts.shape[0], first_step, n_steps, S.ref(karts), S.ref(plans), _p(u))
+        if bad < 0:
+            raise RuntimeError("oracle planned race loop: a tree search failed")
         return u, int(bad)

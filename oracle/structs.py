@@ -76,10 +76,20 @@ class hk_race_params(_S):
                 ("treeSearchDepth", i32), ("planEvery", i32), ("horizon", i32)]
 
 
-STRUCTS = {c.__name__: c for c in (hk_section, hk_kart, hk_game_params, hk_kart_state, hk_action, hk_game_state, hk_race_kart,
-                                   hk_race_plan, hk_race_params)}
+class hk_race_mcts_params(_S):
+    _fields_ = [("mode", i32), ("iterations", i32), ("first_iterations", i32), ("rollouts_per_leaf", i32), ("reuse_cycles", i32),
+                ("apply_delay", i32), ("seed", C.c_uint64), ("max_tree_nodes", i32), ("pad_", i32)]
 
-_NP = {i32: np.int32, f32: np.float32, f64: np.float64, i8: np.int8}
+
+class hk_mcts_node(_S):
+    _fields_ = [("child_mask", C.c_uint64), ("totalValue", f32), ("numEpisodes", i32), ("first_child", i32), ("last_child", i32),
+                ("next_sibling", i32), ("gen", C.c_uint8), ("n_legal", C.c_uint8), ("upnext", i8), ("pad_", C.c_uint8)]
+
+
+STRUCTS = {c.__name__: c for c in (hk_section, hk_kart, hk_game_params, hk_kart_state, hk_action, hk_game_state, hk_race_kart,
+                                   hk_race_plan, hk_race_params, hk_race_mcts_params, hk_mcts_node)}
+
+_NP = {i32: np.int32, f32: np.float32, f64: np.float64, i8: np.int8, C.c_uint64: np.uint64, C.c_uint8: np.uint8}
 
 
 def np_dtype(cls) -> np.dtype:

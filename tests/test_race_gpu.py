@@ -202,7 +202,7 @@ def test_device_resident_mcts_loop_equals_host_composition(hk):
     for ev in range(3):
         G.run(kb, pb, 100 * ev, 100)
         if ev < 2:
-            R.plan_mcts_batch(track, prm, game, kb, pb, K, RPL, seed + ev * 2 * n_races)
+            R.plan_mcts_batch(track, prm, game, kb, pb, K, RPL, seed + (ev + 1) * 2 * n_races)   # event of step 100 (ev + 1): key = seed + (step / planEvery) n_agents + agent
     for f in ka.dtype.names:
         assert np.array_equal(ka[f], kb[f]), f
     for f in pa.dtype.names:
@@ -211,36 +211,73 @@ def test_device_resident_mcts_loop_equals_host_composition(hk):
 
 
 def test_mcts_loop_parity_against_cpu_oracle(hk, oracle):
-    """BASELINE config 5 as written — MCTS waypoints -> LQNG -> dynamics — against a loop in which nothing comes from the CUDA library:
-    the C oracle's race loop (recipe, LQNG, plant, bookkeeping), planWithMCTS's root state and hand-off (race.mcts_root_state /
-    apply_best_states, host logic) and oracle/np_mcts.py's tree search over the C oracle's game.  Re-synchronised every 100 steps like
-    test_run_parity, so that rounding differences cannot move a checkpoint crossing to another step."""
+    """BASELINE config 5 with the LEAF-PARALLEL search — MCTS waypoints -> LQNG -> dynamics — against a loop in which nothing comes from
+    the CUDA library or its host mirrors: the C oracle's race loop (recipe, LQNG, plant, bookkeeping), the C oracle's restatement of
+    planWithMCTS's root state and of the hand-off (hk_oracle_race_mcts_root / _apply_best) and oracle/np_mcts.py's tree search over the
+    C oracle's game.  Re-synchronised every 100 steps like test_run_parity, so that rounding differences cannot move a checkpoint
+    crossing to another step."""
     from hierarchicalkarting_b200 import mcts as M, tracks
     from oracle import np_mcts
     track = S.OVAL
     OR, prm = _oracle_races(oracle, track, high_mode_mcts=True)
     G = R.Races(track, prm)
     game = M.Game(track, 2, prm.velocityBucketSize)
-    OG = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, tracks.game_params(track, bucket=prm.velocityBucketSize))
+    gparams = tracks.game_params(track, bucket=prm.velocityBucketSize)
+    OG = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, gparams)
     n_races, K, RPL, seed = 5, 24, 16, 9001
     karts, plans = R.start_grid(track, n_races, seed=29)
     waypoints = 0
     for blk in range(4):
         gk, gp = karts.copy(), plans.copy()
-        _, bad_g = G.run_mcts(gk, gp, game, K, RPL, seed + 1000 * blk, blk * 100, 100)       # plans at its first step when blk > 0
+        _, bad_g = G.run_mcts(gk, gp, game, K, RPL, seed, blk * 100, 100)                    # plans at its first step when blk > 0
         if blk > 0:
             for r in range(n_races):
                 snapshot = karts[r].copy()                                                   # both agents plan from the same race state
                 for ego in range(2):
-                    st, nearby = R.mcts_root_state(track, prm, snapshot, plans[r], ego)
-                    _, best, _ = np_mcts.TreeSearch(OG, seed + 1000 * blk + 2 * r + ego).search(st, K, RPL)
-
-                    class _GS:
-                        def __init__(self, s_):
-                            self.state = s_
-                    R.apply_best_states(track, snapshot, plans[r], ego, nearby, [_GS(b) for b in best])
+                    st, nearby = OR.mcts_root(gparams, snapshot, plans[r], ego)
+                    _, best, _ = np_mcts.TreeSearch(OG, seed + blk * 2 * n_races + 2 * r + ego).search(st, K, RPL)
+                    OR.apply_best(snapshot, plans[r], ego, nearby, best)
                     waypoints += len(best)
         _, bad_o = OR.run(karts, plans, blk * 100, 100)
         assert bad_g == bad_o == 0
         _same(gk, gp, karts, plans, tol=1e-9)
     assert waypoints > 0 and karts["section"].min() >= 5
+
+
+@pytest.mark.parametrize("plan_every,delay,first,reuse", [(100, 0, 40, 3), (100, 45, 40, 3), (20, 0, 0, 3), (20, 7, 30, 2), (25, 0, 16, 0)])
+def test_planned_loop_parity_against_cpu_oracle(hk, oracle, plan_every, delay, first, reuse):
+    """BASELINE config 5 as the reference runs it: the FAITHFUL sequential search with the planner's whole schedule — plan at episode
+    start (T = 1.5), a new tree or a continued one while CyclesRootProcessed < 3 or no plan at all, trees dropped at checkpoint crossings,
+    results landing `delay` steps after the search started (HierarchicalKartAgent.cs:85-93, 172-283, 331-353, 366-402, 660-661) — on the
+    device (hk_race_run_planned) against the C oracle's planned loop (hk_oracle_race_run_planned: its own root states, hand-off, schedule
+    and tree search).  Both sides keep their planners across the blocks; karts / plans are re-synchronised every block.  planEvery = 20
+    makes several planning events fall between two checkpoint crossings, so trees ARE continued and the 'reused enough' branch is taken."""
+    from hierarchicalkarting_b200 import mcts as M, tracks
+    track = S.OVAL
+    OR, prm = _oracle_races(oracle, track, high_mode_mcts=True)
+    prm.planEvery = plan_every
+    G = R.Races(track, prm)
+    game = M.Game(track, 2, prm.velocityBucketSize)
+    gparams = tracks.game_params(track, bucket=prm.velocityBucketSize)
+    OG = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, gparams)
+    n_races, iters, seed = 7, 24, 555
+    karts, plans = R.start_grid(track, n_races, seed=31)
+    karts["active"][3, 1] = 0                                                                # an inactive agent never plans (:331)
+    gpl = R.Planner(game, n_races, iters, seed, mode=0, first_iterations=first, reuse_cycles=reuse, apply_delay=delay,
+                    max_tree_nodes=1 + 16 * (first + 14 * iters))   # a crossing during a continued search resets CyclesRootProcessed: no bound short of every event
+    opl = OR.planner(OG, gparams, n_races, iters, seed, first_iterations=first, reuse_cycles=reuse, apply_delay=delay)
+    continued = stalled = 0
+    block = 50
+    for blk in range(6):
+        gk, gp = karts.copy(), plans.copy()
+        _, bad_g = G.run_planned(gk, gp, gpl, blk * block, block)
+        _, bad_o = opl.run(karts, plans, blk * block, block)
+        assert bad_g == bad_o == 0
+        _same(gk, gp, karts, plans, tol=1e-9)
+        (rv_g, cy_g, ts_g), (rv_o, cy_o) = gpl.state(), opl.state()
+        assert np.array_equal(rv_g, rv_o) and np.array_equal(cy_g, cy_o) and not ts_g.any()
+        continued += int((cy_o >= 2).sum())
+        stalled += int((cy_o >= max(reuse, 1)).sum())
+    assert ((plans["lane"] != 0) | (plans["oppLane"] != 0)).any() and karts["section"][karts["active"] == 1].min() >= 2
+    if plan_every == 20 and reuse > 0:
+        assert continued > 0                                                                 # constructSearchTree(currentRoot) was exercised
