@@ -44,7 +44,7 @@ namespace KartGame.AI.Native
     public static class HkNative
     {
         const string Lib = "hk_b200";                            // libhk_b200.so / hk_b200.dll on the plugin search path
-        public const int MaxActions = 36, MaxKarts = 4;
+        public const int MaxActions = 36, MaxKarts = 4, MaxSeq = 16;
 
         [DllImport(Lib)] public static extern int hk_abi_version();
         [DllImport(Lib)] public static extern int hk_init(int device);
@@ -67,6 +67,18 @@ namespace KartGame.AI.Native
         // batched tree search (constructSearchTree + getBestStatesSequence, one thread block per root); bestStates [nRoots][16]
         [DllImport(Lib)] public static extern int hk_mcts_search_batch(IntPtr game, HkGameState[] roots, int nRoots, int iterations, int rolloutsPerLeaf,
             ulong seed, [Out] HkGameState[] bestStates, [Out] int[] nBest, [Out] int[] rootEpisodes, [Out] double[] rootValues, [Out] int[] nNodes);
+
+        // The sequential search the reference's callers run (constructSearchTree with parallel == false), device-resident trees that
+        // survive between calls like HierarchicalKartAgent.currentRoot; one GPU thread per tree.
+        [StructLayout(LayoutKind.Sequential)] public struct HkMctsNode
+        { public ulong child_mask; public float totalValue; public int numEpisodes, first_child, last_child, next_sibling; public byte gen, n_legal; public sbyte upnext; public byte pad_; }
+        [DllImport(Lib)] public static extern int hk_mcts_forest_create(IntPtr game, int nTrees, int maxNodesPerTree, out IntPtr forest);
+        [DllImport(Lib)] public static extern void hk_mcts_forest_destroy(IntPtr forest);
+        [DllImport(Lib)] public static extern int hk_mcts_forest_search(IntPtr forest, HkGameState[] roots, int[] fresh, int iterations, ulong seed,
+            [Out] HkGameState[] bestStates, [Out] int[] nBest, [Out] int[] nNodes, [Out] int[] status);
+        [DllImport(Lib)] public static extern int hk_mcts_forest_nodes(IntPtr forest, int tree, [Out] HkMctsNode[] nodes, int maxNodes, out int nNodes);
+        [DllImport(Lib)] public static extern int hk_game_replay_batch(IntPtr game, int batch, int len, HkGameState[] roots, HkAction[] actions,
+            [Out] HkGameState[] statesOut, IntPtr upnext, IntPtr over, IntPtr nScores, IntPtr scores, IntPtr nMoves, IntPtr moves, IntPtr movesIndex);
 
         // the headless loop with the MCTS high level on the device (root states, tree search, waypoint hand-off between two steps)
         [DllImport(Lib)] public static extern int hk_race_run_mcts(IntPtr track, ref HkRaceParams p, IntPtr game, int iterations, int rolloutsPerLeaf, ulong seed,

@@ -1,9 +1,13 @@
 // KartMCTS.cs — drop-in replacement of Assets/Karting/Scripts/AI/MCTS/KartMCTS.cs.
 // Public surface kept verbatim (reference KartMCTS.cs:18-38, 50, 80, 108, 167, 204-236): KartMCTSNode, constructSearchTree (x2),
-// getBestStatesSequence, upperConfidenceStrategy, NextGaussian (x3).  The tree (findLeaf, UCT, backpropagate) stays in C#
-// exactly as in the reference and keeps using KartDiscreteGame.cs for the handful of tree-policy queries; what moves to
-// the GPU is the hot loop: instead of one `simulate` per iteration, every legal child of the selected leaf gets
-// `RolloutsPerChild` playouts in ONE launch (the reference's own leaf-parallel `processLeaf`, :124-159, with R > 1).
+// getBestStatesSequence, upperConfidenceStrategy, NextGaussian (x3).  `parallel` keeps the reference's meaning:
+//   parallel == false (what HierarchicalKartAgent passes, HierarchicalKartAgent.cs:250,271): the sequential search — findLeaf, ONE
+//     simulate() whose every state becomes a node (:271-276), backpropagate from its terminal node — runs on the GPU
+//     (hk_mcts_forest_search, a device-resident tree that constructSearchTree(root) continues, :80-106) and comes back as the same
+//     KartMCTSNode graph the reference would have built (children in insertion order, float totalValue, numEpisodes);
+//   parallel == true: the reference's leaf-parallel processLeaf (:124-159) with `RolloutsPerChild` playouts per child in ONE launch,
+//     tree in C#.
+// The wall-clock budget T becomes an iteration count: T * IterationsPerSecond (a calibration of how fast the C# simulate() was).
 using System;
 using System.Collections.Generic;
 using System.Diagnostics;
@@ -33,13 +37,55 @@ namespace KartGame.AI.MCTS
         static readonly Dictionary<RacingEnvController, IntPtr> games = new Dictionary<RacingEnvController, IntPtr>();
         static ulong seedCounter = (ulong)DateTime.Now.Ticks;
 
+        public static double IterationsPerSecond = 600.0;
+        public static int ReserveSearches = 3;                            // CyclesRootProcessed < 3 (HierarchicalKartAgent.cs:265)
+        sealed class DeviceTree { public IntPtr forest; ~DeviceTree() { if (forest != IntPtr.Zero) HkNative.hk_mcts_forest_destroy(forest); } }
+        static readonly System.Runtime.CompilerServices.ConditionalWeakTable<KartMCTSNode, DeviceTree> deviceTrees =
+            new System.Runtime.CompilerServices.ConditionalWeakTable<KartMCTSNode, DeviceTree>();
+
         public static KartMCTSNode constructSearchTree(DiscreteGameState state, double T = 0.09, bool parallel = false)
         {
             return constructSearchTree(new KartMCTSNode(state), T, parallel);
         }
 
+        // parallel == false: reference :61-66 / :91-96 on the device.  The graph under `root` is rebuilt from the device's node records.
+        static KartMCTSNode constructSequential(KartMCTSNode root, int iterations)
+        {
+            var game = GameOf(root.state); var rs = Pack(root.state);
+            int plies = Math.Max(1, root.state.kartStates.Sum(k => Math.Max(0, root.state.finalSection - k.section)));
+            int[] fresh = { 0 };
+            if (!deviceTrees.TryGetValue(root, out var tree))
+            {
+                tree = new DeviceTree();
+                HkNative.Check(HkNative.hk_mcts_forest_create(game, 1, 1 + ReserveSearches * iterations * plies, out tree.forest));
+                deviceTrees.Add(root, tree); fresh[0] = 1;
+            }
+            var best = new HkGameState[HkNative.MaxSeq]; var nBest = new int[1]; var nNodes = new int[1]; var status = new int[1];
+            ulong seed; lock (games) { seed = seedCounter++; }
+            HkNative.Check(HkNative.hk_mcts_forest_search(tree.forest, new[] { rs }, fresh, iterations, seed, best, nBest, nNodes, status));
+            if (status[0] == 2) throw new DivideByZeroException();
+            var rec = new HkNative.HkMctsNode[nNodes[0]];
+            HkNative.Check(HkNative.hk_mcts_forest_nodes(tree.forest, 0, rec, rec.Length, out int n));
+            var parent = new int[n]; var depth = new int[n]; parent[0] = -1; int maxDepth = 0;
+            for (int i = 0; i < n; i++)
+                for (int c = rec[i].first_child; c >= 0; c = rec[c].next_sibling) { parent[c] = i; depth[c] = depth[i] + 1; maxDepth = Math.Max(maxDepth, depth[c]); }
+            int b = root.state.gameParams.velocityBucketSize, vmax = (int)root.state.kartAgents[0].m_Kart.GetMaxSpeed();
+            Func<int, DiscreteKartAction> actionOf = gi => new DiscreteKartAction { min_velocity = 6 + (gi >> 2) * b, max_velocity = Math.Min(6 + (gi >> 2) * b + b, vmax), lane = (gi & 3) + 1 };
+            root.children.Clear(); root.totalValue = rec[0].totalValue; root.numEpisodes = rec[0].numEpisodes; root.childrenAsRoot = n - 1;
+            var node = new KartMCTSNode[n]; node[0] = root;
+            for (int i = 0; i < n; i++)                                   // creation order: a parent precedes its children; states by makeMove as in :273
+                for (int c = rec[i].first_child; c >= 0; c = rec[c].next_sibling)
+                {
+                    var a = actionOf(rec[c].gen);
+                    var ch = new KartMCTSNode(node[i].state.makeMove(a), node[i]) { totalValue = rec[c].totalValue, numEpisodes = rec[c].numEpisodes };
+                    node[i].children[a] = ch; node[c] = ch;               // insertion order = the reference Dictionary's enumeration order
+                }
+            return root;
+        }
+
         public static KartMCTSNode constructSearchTree(KartMCTSNode root, double T = 0.09, bool parallel = false)
         {
+            if (!parallel) return constructSequential(root, Math.Max(1, (int)(T * IterationsPerSecond)));
             var timer = new Stopwatch(); double total = 0.0f;
             while (total < T)
             {

@@ -91,6 +91,12 @@ class hk_race_params(C.Structure):
                 ("treeSearchDepth", C.c_int32), ("planEvery", C.c_int32), ("horizon", C.c_int32)]
 
 
+class hk_mcts_node(C.Structure):
+    _fields_ = [("child_mask", C.c_uint64), ("totalValue", C.c_float), ("numEpisodes", C.c_int32), ("first_child", C.c_int32),
+                ("last_child", C.c_int32), ("next_sibling", C.c_int32), ("gen", C.c_uint8), ("n_legal", C.c_uint8), ("upnext", C.c_int8),
+                ("pad_", C.c_uint8)]
+
+
 class hk_race_mcts_params(C.Structure):
     _fields_ = [("mode", C.c_int32), ("iterations", C.c_int32), ("first_iterations", C.c_int32), ("rollouts_per_leaf", C.c_int32),
                 ("reuse_cycles", C.c_int32), ("apply_delay", C.c_int32), ("seed", C.c_uint64), ("max_tree_nodes", C.c_int32), ("pad_", C.c_int32)]

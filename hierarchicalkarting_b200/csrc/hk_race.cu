@@ -115,9 +115,9 @@ __global__ void race_recipe_kernel(const DevTrack* __restrict__ t, hk_race_param
         const int o = 1 - i;
         const hk_race_kart ki = pair[i == 0 ? e : 1 - e];
         const hk_race_kart ko = pair[o == 0 ? e : 1 - e];
-        const float mult = i == 0 ? 1.0f : 1.3f;                     // :999-1002
+        const float mult = i == 0 ? (p.highModeMcts ? 1.0f : 0.45f) : 1.3f;   // k == this ? (Fixed ? 0.45f : 1.0f) : 1.3f, :999-1002
         const float dist = magnitude2((float)(ko.x - ki.x), (float)(ko.z - ki.z));
-        const bool far = dist > 8;
+        const bool far = dist > 8 || !ko.active;                      // ... .magnitude > 8 || !o.is_active, :1010
         const float w32 = 1.0f / ((float)pow((double)dist, (double)1.5f) * mult);      // 1f/(Mathf.Pow(d,1.5f)*mult), :1019
         const double w = far ? 0.0 : (double)w32;
         aw[(size_t)b * 4 + i * 2 + 0] = w;

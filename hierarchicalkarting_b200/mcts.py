@@ -4,9 +4,11 @@ flavour is host/KartMCTS.hpp, the C# shim csharp/KartMCTS.cs).
   DiscreteGameState.{upNext,isOver,nextMoves,makeMove}   Assets/Karting/Scripts/AI/MCTS/KartDiscreteGame.cs:188,251,322,420
   KartMCTSNode, KartMCTS.constructSearchTree / getBestStatesSequence / upperConfidenceStrategy / NextGaussian
                                                          Assets/Karting/Scripts/AI/MCTS/KartMCTS.cs:18-38,50-122,167-236
-Every game evaluation (transitions, legal moves, terminal scores, rollouts) runs in the CUDA library; the tree itself
-(a few hundred nodes) stays on the host like in the reference, and consumes leaf-parallel rollout statistics in the way
-`KartMCTS.processLeaf` (:124-159) + `backpropagate` (:280-289) would.
+Every game evaluation (transitions, legal moves, terminal scores, playouts) runs in the CUDA library.  constructSearchTree has the
+reference's two modes: `parallel=False` (what HierarchicalKartAgent calls, :250,271) is the sequential search — findLeaf, ONE playout
+whose every state becomes a node, backpropagate from its terminal node — run entirely on the device (hk_mcts_forest_search, one GPU
+thread per tree) and handed back as a KartMCTSNode graph; `parallel=True` is the reference's leaf-parallel `processLeaf` (:124-159)
+with R playouts per child: the tree stays on the host and consumes GPU rollout statistics.
 """
 from __future__ import annotations
 
@@ -315,6 +317,41 @@ class KartMCTSNode:                                     # KartMCTS.cs:18-38
         self.createdBy = createdBy
 
 
+class _DeviceNode(KartMCTSNode):
+    """A KartMCTSNode of a tree that lives on the device (hk_mcts_forest): links and statistics are copied from the node records,
+    the state — which the device does not store — is replayed from the root along the node's actions on first access."""
+
+    def __init__(self, game: Game, parent, action, rec):
+        self._game, self._action, self._state = game, action, None
+        self.parent = parent
+        self.children = {}
+        self.totalValue = float(rec["totalValue"])
+        self.numEpisodes = int(rec["numEpisodes"])
+        self.childrenAsRoot = 0
+        self.createdBy = ""
+
+    @property
+    def state(self) -> DiscreteGameState:
+        if self._state is None:
+            chain = []
+            n = self
+            while n._state is None:
+                chain.append(n)
+                n = n.parent
+            chain.reverse()
+            acts = np.array([[list(c._action) for c in chain]], dtype=np.int32)
+            out = self._game.replay([n._state.state], acts)
+            for k, c in enumerate(chain):
+                st = abi.hk_game_state()
+                C.memmove(C.byref(st), out["states"][0, k + 1:k + 2].ctypes.data, C.sizeof(abi.hk_game_state))
+                c._state = DiscreteGameState(self._game, st)
+        return self._state
+
+    @state.setter
+    def state(self, v):
+        self._state = v
+
+
 class KartMCTS:
     random = _random.Random()
     rollouts_per_leaf = 4096                            # GPU batch per expanded leaf (the reference plays 1 per iteration)
@@ -397,10 +434,68 @@ class KartMCTS:
             node.numEpisodes += count
             node = node.parent
 
+    iterations_per_second = 600.0                       # sequential mode: how a wall-clock budget T maps to an iteration count
+                                                        # (the reference's loop is budgeted in seconds of ITS C# simulate(), KartMCTS.cs:55;
+                                                        # ~1 ms per iteration is what LINQ-heavy simulate() manages — a calibration knob)
+
+    @staticmethod
+    def _graph_from_device(game: Game, forest: Forest, root_state: DiscreteGameState):
+        rec = forest.nodes(0)
+        nodes = [None] * len(rec)
+        root = _DeviceNode(game, None, None, rec[0])
+        root._state = root_state
+        nodes[0] = root
+        order = [0]
+        for i in order:                                 # parents are created before their children (creation order = index order)
+            c = int(rec[i]["first_child"])
+            while c >= 0:
+                act = game.action_of(int(rec[c]["gen"]))
+                nodes[c] = _DeviceNode(game, nodes[i], act, rec[c])
+                nodes[i].children[act] = nodes[c]       # insertion order = the Dictionary's enumeration order
+                order.append(c)
+                c = int(rec[c]["next_sibling"])
+        root.childrenAsRoot = len(rec) - 1
+        root._forest, root._forest_iterations = forest, int(rec[0]["numEpisodes"])
+        return root
+
+    @staticmethod
+    def _construct_sequential(state_or_root, T, seed, max_iterations, reserve_iterations=None):
+        """KartMCTS.cs:50-78 / :80-106 with parallel == false, on the device; the result is a KartMCTSNode graph."""
+        iterations = max_iterations if max_iterations is not None else max(1, int(T * KartMCTS.iterations_per_second))
+        if isinstance(state_or_root, KartMCTSNode):
+            root = state_or_root
+            forest = getattr(root, "_forest", None)
+            if forest is None and len(root.children) > 0:
+                raise ValueError("constructSearchTree(root): the root was not built by this library's sequential search")
+            state = root.state
+        else:
+            root, forest, state = None, None, state_or_root
+        game = state.game
+        seed = KartMCTS.random.getrandbits(63) if seed is None else seed
+        plies = max(1, sum(max(0, state.state.finalSection - state.state.karts[i].section) for i in range(state.state.n_karts)))
+        if forest is None:                              # constructSearchTree(state): a new tree
+            forest = Forest(game, 1, 1 + max(iterations, reserve_iterations or 0) * plies)
+            out = forest.search([state.state], iterations, seed)
+        else:                                           # constructSearchTree(root): continue the device-resident tree (root reuse, HKA:265-283)
+            done = root._forest_iterations
+            if 1 + (done + iterations) * plies > forest.max_nodes:
+                raise ValueError("constructSearchTree(root): the tree's node budget is exhausted; size the first call with reserve_iterations")
+            out = forest.search(None, iterations, 0, fresh=np.zeros(1, np.int32))
+        if int(out["status"][0]) == 2:
+            raise ZeroDivisionError("UCTWeight divided by zero inside findLeaf (KartMCTS.cs:164)")
+        new_root = KartMCTS._graph_from_device(game, forest, state)
+        new_root._device_best = [out["best"][0, k] for k in range(int(out["n_best"][0]))]
+        return new_root
+
     @staticmethod
     def constructSearchTree(state_or_root, T: float = 0.09, parallel: bool = False, seed: int | None = None,
-                            max_iterations: int | None = None):
-        """KartMCTS.cs:50-106 — wall-clock budgeted search; each iteration expands one leaf with a GPU rollout batch."""
+                            max_iterations: int | None = None, reserve_iterations: int | None = None):
+        """KartMCTS.cs:50-106.  parallel=False (the reference's callers): the sequential search on the device, `max_iterations`
+        iterations (default T * iterations_per_second); `reserve_iterations` sizes the device tree for later constructSearchTree(root)
+        calls on the result (root reuse, HierarchicalKartAgent.cs:265-283).  parallel=True: wall-clock budgeted, each iteration expands one leaf with a GPU
+        rollout batch (processLeaf with R playouts per child)."""
+        if not parallel:
+            return KartMCTS._construct_sequential(state_or_root, T, seed, max_iterations, reserve_iterations)
         root = state_or_root if isinstance(state_or_root, KartMCTSNode) else KartMCTSNode(state_or_root)
         seed = KartMCTS.random.getrandbits(63) if seed is None else seed
         total, it = 0.0, 0

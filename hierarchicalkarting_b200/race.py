@@ -292,12 +292,12 @@ def plan_mcts_batch(track: Track, params: abi.hk_race_params, game, karts: np.nd
 
 
 def plan_with_mcts(track: Track, params: abi.hk_race_params, game, karts_race: np.ndarray, plans_race: np.ndarray, ego: int,
-                   T: float = 0.9, max_iterations: int | None = None, seed: int | None = None):
+                   T: float = 0.9, max_iterations: int | None = None, seed: int | None = None, parallel: bool = False):
     """planWithMCTS + hand-off for one agent: root state, KartMCTS.constructSearchTree (GPU leaf-parallel rollouts),
     getBestStatesSequence, apply.  `game` is a hierarchicalkarting_b200.mcts.Game for this track.  Returns the search root."""
     from . import mcts as M
     st, nearby = mcts_root_state(track, params, karts_race, plans_race, ego)
-    root = M.KartMCTS.constructSearchTree(M.DiscreteGameState(game, st), T=T, seed=seed, max_iterations=max_iterations)
+    root = M.KartMCTS.constructSearchTree(M.DiscreteGameState(game, st), T=T, seed=seed, max_iterations=max_iterations, parallel=parallel)
     best = M.KartMCTS.getBestStatesSequence(root)
     apply_best_states(track, karts_race, plans_race, ego, nearby, best)
     return root, best

@@ -122,13 +122,13 @@ def make_problems(track: Track, batch: int, n_players: int, seed: int, slow_frac
     nb = max(N - 1, 1) if N > 2 else 1                                     # nearbyAgents (all within 8 m by construction)
     vmax1 = np.maximum(1.0, v)
     if N > 2:
-        w_h = np.full((batch, N), 3.5 * nb)
+        w_h = np.full((batch, N), (3.5 if high_mode_mcts else 2.5) * nb)   # HKA:932
     else:
         w_h = np.full((batch, N), 3.5 if high_mode_mcts else 1.9)
     w_xz = np.where(stopped, nb * 0.3 * 3.1, nb * 0.3 * 3.1 / vmax1)
     w_v = np.where(stopped, float(nb * -2), nb * 5e-4)
     tw = np.stack([w_xz, w_xz, w_v, w_h], axis=-1)
-    cw = np.full((batch, N), 0.25 if N > 2 else 0.115)                     # HKA:1192-1196
+    cw = np.full((batch, N), (0.25 if high_mode_mcts else 0.135) if N > 2 else 0.115)   # HKA:1192-1196
 
     # avoid / opponent-target / teammate-target weights in each player's private ordering (HKA:964-1190)
     K = max(N - 1, 0)
@@ -137,9 +137,9 @@ def make_problems(track: Track, batch: int, n_players: int, seed: int, slow_frac
     otw = np.zeros((batch, N, K, 3))
     for i in range(N):
         if N > 2:
-            mult = F32(1.0 if i == 0 else 1.7) / F32(nb)                   # HKA:985-987 (float / int)
+            mult = F32((1.0 if high_mode_mcts else 0.55) if i == 0 else 1.7) / F32(nb)   # HKA:985-987 (float / int)
         else:
-            mult = F32(1.0 if i == 0 else 1.3)                             # HKA:999-1002
+            mult = F32((1.0 if high_mode_mcts else 0.45) if i == 0 else 1.3)             # HKA:999-1002
         n_opp_near = np.zeros(batch, dtype=np.int64)
         for k in range(K):
             o = order[i, 1 + k]

@@ -50,11 +50,12 @@ class Track:
         return self.rows[s % self.n_sections][9][lane - 1]
 
     def lane_table(self) -> np.ndarray:
-        """[n_sections][4][2] lane collider positions (x, z)."""
-        return np.array([[list(p) for p in r[9]] for r in self.rows], dtype=np.float64)
+        """[n_sections][4][2] lane collider positions (x, z).  Unity's transform.position is a float32 Vector3 and SolveLQR subtracts
+        such positions in float32 (HierarchicalKartAgent.cs:819-831) before widening, so the table holds float32-representable values."""
+        return np.array([[list(p) for p in r[9]] for r in self.rows], dtype=np.float32).astype(np.float64)
 
     def trigger_table(self) -> np.ndarray:
-        return np.array([list(r[7]) for r in self.rows], dtype=np.float64)
+        return np.array([list(r[7]) for r in self.rows], dtype=np.float32).astype(np.float64)      # float32-representable, see lane_table
 
     def heading_table(self) -> np.ndarray:
         return np.radians(np.array([r[8] for r in self.rows], dtype=np.float64))

@@ -1,10 +1,13 @@
 // KartMCTS.hpp — C++ host-side mirror of the reference's C# namespace KartGame.AI.MCTS over the C-ABI (include/hk_abi.h).
 //   DiscreteKartAction / DiscreteKartState / DiscreteGameState   Assets/Karting/Scripts/AI/MCTS/KartDiscreteGame.cs:14-34,174-447
 //   KartMCTSNode / KartMCTS                                       Assets/Karting/Scripts/AI/MCTS/KartMCTS.cs:18-38,45-290
-// The game itself (transitions, legal moves, scores, rollouts) is evaluated by libhk_b200 on the GPU; the search tree is
-// host-side as in the reference.  One tree iteration = expand every legal child of the selected leaf and play
-// `rolloutsPerChild` rollouts from each in ONE launch — the reference's own leaf-parallel processLeaf (:124-159) with R > 1.
+// The game itself (transitions, legal moves, scores, playouts) is evaluated by libhk_b200 on the GPU.  constructSearchTree keeps the
+// reference's two modes: parallel == false (what HierarchicalKartAgent calls, HierarchicalKartAgent.cs:250,271) is the sequential
+// search — findLeaf, ONE playout whose every state becomes a node, backpropagate — run on the device (hk_mcts_forest_search) and
+// handed back as a KartMCTSNode graph that a later constructSearchTree(root) continues; parallel == true is the reference's
+// leaf-parallel processLeaf (:124-159) with `rolloutsPerChild` playouts per child, tree on the host.
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <map>
@@ -101,25 +104,96 @@ private:
     std::vector<DiscreteKartAction> moves_gen_;
 };
 
+struct ForestHandle {                                       // device-resident tree behind a root built by the sequential mode
+    hk_mcts_forest* f = nullptr;
+    int maxNodes = 0, iterations = 0;
+    ~ForestHandle() { hk_mcts_forest_destroy(f); }
+};
+
 class KartMCTSNode {                                        // KartMCTS.cs:18-38
 public:
     DiscreteGameState state;
     KartMCTSNode* parent;
     std::map<DiscreteKartAction, std::unique_ptr<KartMCTSNode>, ActionLess> children;
+    std::vector<DiscreteKartAction> insertionOrder;         // the Dictionary's enumeration order (Keys.ElementAt / foreach, :169-177)
     float totalValue = 0.0f;
     int numEpisodes = 0;
     int childrenAsRoot = 0;
     std::string createdBy;
+    std::shared_ptr<ForestHandle> forest;                   // root of a device-resident tree only
+    std::vector<hk_game_state> deviceBestStates;            // getBestStatesSequence as the device walked it (Philox picks)
     KartMCTSNode(DiscreteGameState st, KartMCTSNode* p = nullptr, std::string by = "") : state(std::move(st)), parent(p), createdBy(std::move(by)) {}
+    KartMCTSNode* addChild(const DiscreteKartAction& a, std::unique_ptr<KartMCTSNode> c)
+    {
+        KartMCTSNode* raw = c.get();
+        children[a] = std::move(c);
+        insertionOrder.push_back(a);
+        return raw;
+    }
 };
 
 class KartMCTS {
 public:
     static inline long long rolloutsPerChild = 4096;
+    static inline double iterationsPerSecond = 600.0;       // sequential mode: how the wall-clock budget T (:55) maps to an iteration count
+    static inline int reserveSearches = 3;                  // a new device tree is sized for this many calls (CyclesRootProcessed < 3, HKA:265)
     static inline std::mt19937_64 random{std::random_device{}()};
 
-    static KartMCTSNode* constructSearchTree(KartMCTSNode* root, double T = 0.09, bool /*parallel*/ = false)   // :80-106
+    // The sequential search on the device: a new tree if `root` has none (constructSearchTree(state), :50-78), else the root's tree is
+    // continued (constructSearchTree(root), :80-106).  The node graph below `root` is rebuilt from the device's node records.
+    static KartMCTSNode* constructSequential(KartMCTSNode* root, int iterations)
     {
+        const hk_game_state& rs = root->state.s;
+        int plies = 0;
+        for (int k = 0; k < rs.n_karts; ++k) plies += std::max(0, rs.finalSection - rs.karts[k].section);
+        plies = std::max(plies, 1);
+        hk_game_state best[HK_MCTS_MAX_SEQ];
+        int32_t nBest = 0, nNodes = 0, status = 0, fresh = 0;
+        if (!root->forest) {
+            if (!root->children.empty()) throw std::invalid_argument("constructSearchTree(root): root was not built by the sequential search");
+            auto h = std::make_shared<ForestHandle>();
+            h->maxNodes = 1 + reserveSearches * iterations * plies;
+            hk_check(hk_mcts_forest_create(root->state.tables->handle(), 1, h->maxNodes, &h->f));
+            root->forest = h;
+            fresh = 1;
+        }
+        hk_check(hk_mcts_forest_search(root->forest->f, &rs, &fresh, iterations, random(), best, &nBest, &nNodes, &status));
+        if (status == 2) throw std::domain_error("division by zero");                                        // DivideByZeroException in findLeaf
+        root->forest->iterations += iterations;
+        std::vector<hk_mcts_node> rec((size_t)nNodes);
+        hk_check(hk_mcts_forest_nodes(root->forest->f, 0, rec.data(), nNodes, &nNodes));
+        // states are not stored on the device: replay every node's action path in one batched call
+        std::vector<int> parent((size_t)nNodes, -1), depth((size_t)nNodes, 0);
+        for (int i = 0; i < nNodes; ++i)
+            for (int c = rec[i].first_child; c >= 0; c = rec[c].next_sibling) { parent[c] = i; depth[c] = depth[i] + 1; }
+        int maxDepth = 0;
+        for (int d : depth) maxDepth = std::max(maxDepth, d);
+        const hk_game_params& gp = root->state.tables->params();
+        auto actionOf = [&](int gi) { const int v = 6 + (gi >> 2) * gp.velocityBucketSize; return hk_action{v, std::min(v + gp.velocityBucketSize, vmaxOf(root)), (gi & 3) + 1}; };
+        std::vector<hk_game_state> roots((size_t)nNodes, rs), states((size_t)nNodes * (maxDepth + 1));
+        std::vector<hk_action> acts((size_t)nNodes * std::max(maxDepth, 1), hk_action{6, 6 + gp.velocityBucketSize, 1});
+        for (int i = 1; i < nNodes; ++i)
+            for (int n = i; parent[n] >= 0; n = parent[n]) acts[(size_t)i * maxDepth + depth[n] - 1] = actionOf(rec[n].gen);
+        if (maxDepth > 0)
+            hk_check(hk_game_replay_batch(root->state.tables->handle(), nNodes, maxDepth, roots.data(), acts.data(), states.data(), nullptr, nullptr,
+                                          nullptr, nullptr, nullptr, nullptr, nullptr));
+        root->children.clear(); root->insertionOrder.clear();
+        root->totalValue = rec[0].totalValue; root->numEpisodes = rec[0].numEpisodes; root->childrenAsRoot = nNodes - 1;
+        std::vector<KartMCTSNode*> node((size_t)nNodes, nullptr);
+        node[0] = root;
+        for (int i = 0; i < nNodes; ++i)                                  // creation order: a parent precedes its children
+            for (int c = rec[i].first_child; c >= 0; c = rec[c].next_sibling) {
+                auto ch = std::make_unique<KartMCTSNode>(DiscreteGameState(root->state.tables, states[(size_t)c * (maxDepth + 1) + depth[c]]), node[i]);
+                ch->totalValue = rec[c].totalValue; ch->numEpisodes = rec[c].numEpisodes;
+                node[c] = node[i]->addChild(actionOf(rec[c].gen), std::move(ch));
+            }
+        root->deviceBestStates.assign(best, best + nBest);
+        return root;
+    }
+
+    static KartMCTSNode* constructSearchTree(KartMCTSNode* root, double T = 0.09, bool parallel = false)   // :50-78, :80-106
+    {
+        if (!parallel) return constructSequential(root, std::max(1, (int)(T * iterationsPerSecond)));
         double total = 0.0;
         unsigned long long it = 0;
         const unsigned long long seed = random();
@@ -164,19 +238,18 @@ public:
 
     static DiscreteKartAction upperConfidenceStrategy(KartMCTSNode* node)                                    // :167-192
     {
-        std::uniform_int_distribution<size_t> pick(0, node->children.size() - 1);
-        auto it = node->children.begin();
-        std::advance(it, pick(random));
-        DiscreteKartAction best = it->first;
-        float best_uct = UCTWeight(it->second.get());
-        for (auto& kv : node->children) {
-            const float w = UCTWeight(kv.second.get());
-            if (w > best_uct) { best_uct = w; best = kv.first; }
+        std::uniform_int_distribution<size_t> pick(0, node->insertionOrder.size() - 1);
+        DiscreteKartAction best = node->insertionOrder[pick(random)];                                        // Keys.ElementAt(random.Next(Count))
+        float best_uct = UCTWeight(node->children[best].get());
+        for (auto& key : node->insertionOrder) {                                                             // foreach (var item in node.children)
+            const float w = UCTWeight(node->children[key].get());
+            if (w > best_uct) { best_uct = w; best = key; }
         }
         return best;
     }
 
 private:
+    static int vmaxOf(KartMCTSNode*) { return 15; }                                                          // (int)GetMaxSpeed() of the shipped karts
     static float UCTWeight(KartMCTSNode* n)                                                                   // :162-165 (integer division, no sqrt term)
     {
         if (n->numEpisodes == 0) throw std::domain_error("division by zero");
@@ -201,10 +274,11 @@ private:
         std::vector<KartMCTSNode*> kids;
         std::vector<hk_game_state> leaves;
         for (auto& mv : moves) {
-            auto& slot = node->children[mv];
-            if (!slot) { slot.reset(new KartMCTSNode(node->state.makeMove(mv), node)); ++created; }
-            kids.push_back(slot.get());
-            leaves.push_back(slot->state.s);
+            auto it = node->children.find(mv);
+            KartMCTSNode* kid = it != node->children.end() ? it->second.get()
+                                                           : (++created, node->addChild(mv, std::make_unique<KartMCTSNode>(node->state.makeMove(mv), node)));
+            kids.push_back(kid);
+            leaves.push_back(kid->state.s);
         }
         const int n = (int)kids.size(), K = node->state.s.n_karts;
         std::vector<int64_t> visit((size_t)n * HK_MAX_ACTIONS), nan((size_t)n * HK_MAX_ACTIONS), plies(n);

@@ -56,9 +56,26 @@ int main(int argc, char** argv)
     for (int i = 0; i < 2; ++i) root.karts[i] = hk_kart_state{0, i, 0, 0, 0, 2, 2 + i, 2500, 0, 0};
     MCTS::KartMCTSNode node(MCTS::DiscreteGameState(tables, root));
     MCTS::KartMCTS::rolloutsPerChild = 512;
-    MCTS::KartMCTS::constructSearchTree(&node, 0.2);
+    MCTS::KartMCTS::constructSearchTree(&node, 0.2, /*parallel=*/true);                       // leaf-parallel processLeaf, tree on the host
     auto best = MCTS::KartMCTS::getBestStatesSequence(&node);
     if (node.numEpisodes <= 0 || node.children.empty() || best.empty()) { std::printf("MCTS produced no plan\n"); return 1; }
+    {   // what HierarchicalKartAgent calls: the sequential search (parallel == false), device-resident, then continued on the same root
+        MCTS::KartMCTSNode seq(MCTS::DiscreteGameState(tables, root));
+        MCTS::KartMCTS::iterationsPerSecond = 1000.0;
+        MCTS::KartMCTS::constructSearchTree(&seq, 0.15);                                        // 150 iterations
+        if (seq.numEpisodes != 150 || seq.children.empty()) { std::printf("sequential MCTS: root has %d episodes\n", seq.numEpisodes); return 1; }
+        int sum = 0;
+        for (auto& kv : seq.children) sum += kv.second->numEpisodes;
+        if (sum != 150) { std::printf("sequential MCTS: children hold %d of 150 episodes\n", sum); return 1; }
+        auto chain = MCTS::KartMCTS::getBestStatesSequence(&seq);
+        if (chain.size() != 8 || seq.deviceBestStates.size() != 8) { std::printf("sequential MCTS: best states %zu / %zu, expected the chain to depth 8\n", chain.size(), seq.deviceBestStates.size()); return 1; }
+        for (auto& st : chain)
+            for (int i = 0; i < st.s.n_karts; ++i)
+                if (st.s.karts[i].section != st.s.lastCompletedSection) { std::printf("sequential MCTS: best state with a kart behind\n"); return 1; }
+        const int nodesBefore = seq.childrenAsRoot;
+        MCTS::KartMCTS::constructSearchTree(&seq, 0.1);                                         // constructSearchTree(root): 100 more
+        if (seq.numEpisodes != 250 || seq.childrenAsRoot <= nodesBefore) { std::printf("continued MCTS: %d episodes, %d nodes\n", seq.numEpisodes, seq.childrenAsRoot); return 1; }
+    }
     {   // the same search for several roots at once on the device
         std::vector<hk_game_state> roots(5, root);
         for (int r = 0; r < 5; ++r) { roots[r].initialSection = roots[r].lastCompletedSection = r; roots[r].finalSection = r + 8; for (int i = 0; i < 2; ++i) roots[r].karts[i].section = r; }

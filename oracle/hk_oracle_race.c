@@ -100,9 +100,11 @@ void hk_oracle_race_recipe_one(const hk_section* sections, const double* trig, c
         const int o = 1 - i;
         const hk_race_kart* ki = &karts[i == 0 ? e : 1 - e];
         const hk_race_kart* ko = &karts[o == 0 ? e : 1 - e];
-        const float mult = i == 0 ? 1.0f : 1.3f;                                /* :999-1002 */
+        float mult;                                                              /* :996-1003 (2-agent environment) */
+        if (i == 0) mult = p->highModeMcts ? 1.0f : 0.45f;                       /* k == this: HighMode == Fixed ? 0.45f : 1.0f */
+        else mult = 1.3f;                                                        /* Fixed ? 1.3f : 1.3f */
         const float dist = magnitude2((float)(ko->x - ki->x), (float)(ko->z - ki->z));
-        const int far = dist > 8;
+        const int far = dist > 8 || !ko->active;                                 /* || !o.is_active, :1010 */
         const float w32 = 1.0f / ((float)pow((double)dist, (double)1.5f) * mult);   /* 1f/(Mathf.Pow(d,1.5f)*mult), :1019 */
         const double w = far ? 0.0 : (double)w32;
         aw[i * 2 + 0] = w; aw[i * 2 + 1] = w;

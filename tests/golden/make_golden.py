@@ -59,8 +59,59 @@ GAME_KAT = {
     "lqng_smoke_u0": [0.00558, 0.076146],
 }
 
+def game():
+    """tests/golden/game_golden.npz: 400 (kart state, action) -> kart state transitions and 24 sequential tree searches, produced by the
+    C oracle AFTER the two independent restatements (oracle/np_game.py for the arithmetic, oracle/np_mcts_seq.py for the tree) agreed
+    with it on exactly these inputs."""
+    from hierarchicalkarting_b200 import tracks
+    from oracle import np_game, np_mcts_seq, structs as OS
+    out = {}
+    rng = np.random.default_rng(20260400)
+    for name, track, bucket in (("oval2", tracks.OVAL, 2), ("complex1", tracks.COMPLEX, 1)):
+        karts = tracks.kart_array(2)
+        params = tracks.game_params(track, bucket)
+        g = O.Game(track.sections_array(), track.n_sections, karts, 2, params)
+        ng = np_game.NpGame(track.sections_array(), track.n_sections, karts, 2, params)
+        n = 200
+        ks = np.zeros(n, dtype=OS.np_dtype(OS.hk_kart_state))
+        ks["section"] = rng.integers(0, 3 * track.n_sections, n)
+        ks["lane"] = rng.integers(1, 5, n)
+        vmin = rng.choice([0] + list(range(6, 15, bucket)), n)
+        ks["min_velocity"] = vmin
+        ks["max_velocity"] = np.where(vmin == 0, bucket, np.minimum(vmin + bucket, 15))
+        ks["tireAge"] = rng.choice([0, 2500, 6000, 9999, 13400, 20000], n)
+        ks["laneChanges"] = rng.integers(0, 4, n)
+        ks["timeAtSection"] = rng.integers(0, 2000, n)
+        a_min = rng.choice(list(range(6, 15, bucket)), n).astype(np.int32)
+        acts = np.stack([a_min, np.minimum(a_min + bucket, 15), rng.integers(1, 5, n)], axis=1).astype(np.int32)
+        new = np.zeros_like(ks)
+        for i in range(n):
+            ref = g.apply_action(OS.hk_kart_state.from_buffer_copy(ks[i].tobytes()), tuple(int(v) for v in acts[i]))
+            new[i] = np.frombuffer(bytes(ref), dtype=ks.dtype)[0]
+        assert new.tobytes() == ng.apply_actions(ks, acts[:, 0], acts[:, 1], acts[:, 2]).tobytes()      # second opinion before freezing
+        out[f"{name}_kart_states"], out[f"{name}_actions"], out[f"{name}_new_states"] = ks, acts, new
+        roots = np.zeros(12, dtype=OS.GAME_STATE_DTYPE)
+        for r in range(12):
+            st = tracks.root_state(track, int(rng.integers(0, 2 * track.n_sections)), [int(x) for x in rng.integers(1, 5, 2)], teams=[0, 1],
+                                   tire_age=int(rng.choice([0, 2500, 9900])), times=[0, int(rng.integers(0, 120))])
+            for i in range(2):
+                st.karts[i].max_velocity = bucket
+            roots[r] = np.frombuffer(bytes(st), dtype=OS.GAME_STATE_DTYPE)[0]
+        res = O.tree_search_batch(g, roots, 64, seed=20260401, mode=0, threads=1)
+        for r in (0, 5):                                                                                # second opinion on two of them
+            s = np_mcts_seq.SequentialSearch(ng, 20260401 + r)
+            root = s.constructSearchTree(OS.hk_game_state.from_buffer_copy(roots[r].tobytes()), 64)
+            best = s.getBestStatesSequence(root)
+            assert len(best) == int(res["n_best"][r]) and all(bytes(b) == res["best"][r, k].tobytes() for k, b in enumerate(best))
+        out[f"{name}_roots"] = roots
+        for k in ("best", "n_best", "root_gen", "root_episodes", "root_values", "n_nodes"):
+            out[f"{name}_search_{k}"] = res[k]
+    np.savez_compressed(os.path.join(HERE, "game_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     lqng()
+    game()
     with open(os.path.join(HERE, "game_kat.json"), "w") as f:
         json.dump(GAME_KAT, f, indent=1)
     print("golden written")

@@ -43,9 +43,67 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.hk_section) == 24 and C.sizeof(abi.hk_kart) == 28 and C.sizeof(abi.hk_game_params) == 32
     assert C.sizeof(abi.hk_kart_state) == 40 and C.sizeof(abi.hk_action) == 12 and C.sizeof(abi.hk_game_state) == 16 + 4 * 40
     assert C.sizeof(abi.hk_race_kart) == 64 and C.sizeof(abi.hk_race_plan) == 936 and C.sizeof(abi.hk_race_params) == 56
+    assert C.sizeof(abi.hk_race_mcts_params) == 40 and abi.MCTS_NODE_DTYPE.itemsize == 32
     assert re.search(r"#define HK_MAX_SECTIONS 64\b", HEADER) and abi.HK_MAX_SECTIONS == 64
     for name, val in (("HK_MAX_PLAYERS", 4), ("HK_MAX_ACTIONS", 36), ("HK_MAX_PLIES", 64), ("HK_MAX_KARTS", 4), ("HK_MAX_HORIZON", 31)):
         assert re.search(rf"#define {name} {val}\b", HEADER) and getattr(abi, name) == val
+
+
+def _parse_header_structs():
+    """{struct name: [(field, C type, array length or None)]} of every `typedef struct hk_x { ... } hk_x;` in include/hk_abi.h."""
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    defines = {k: int(v) for k, v in re.findall(r"#define\s+(HK_[A-Z_]+)\s+(\d+)", body)}
+    out = {}
+    for name, fields in re.findall(r"typedef struct (hk_[a-z_]+)\s*\{(.*?)\}\s*\1\s*;", body, flags=re.S):
+        rows = []
+        for decl in fields.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"([a-z0-9_]+(?:\s+[a-z0-9_]+)*?)\s+(.+)$", decl)
+            ctype, names = m.group(1), m.group(2)
+            for nm in names.split(","):
+                nm = nm.strip()
+                am = re.match(r"([A-Za-z0-9_]+)\[([A-Z0-9_]+)\]$", nm)
+                if am:
+                    ln = am.group(2)
+                    rows.append((am.group(1), ctype, defines[ln] if ln in defines else int(ln)))
+                else:
+                    rows.append((nm, ctype, None))
+        out[name] = rows
+    return out
+
+
+_CT = {"float": C.c_float, "double": C.c_double, "int32_t": C.c_int32, "int8_t": C.c_int8, "uint8_t": C.c_uint8, "uint64_t": C.c_uint64}
+
+
+@pytest.mark.parametrize("which", ["product", "oracle"])
+def test_struct_definitions_follow_the_header_field_by_field(which):
+    """Both Python restatements of the ABI's plain-data structs — the product's (hierarchicalkarting_b200/abi.py) and the oracle's OWN
+    (oracle/structs.py, written separately so that a layout bug is not common-mode) — are checked against the header text: field
+    names, order, C types, array lengths, and therefore offsets and sizes."""
+    if which == "product":
+        mod = abi
+    else:
+        from oracle import structs as mod
+    parsed = _parse_header_structs()
+    assert len(parsed) >= 11
+    for name, rows in parsed.items():
+        cls = getattr(mod, name, None)
+        assert cls is not None, f"{which}: no definition of {name}"
+        got = []
+        for fname, ftype in cls._fields_:
+            if issubclass(ftype, C.Array):
+                got.append((fname, ftype._type_, ftype._length_))
+            else:
+                got.append((fname, ftype, None))
+        want = []
+        for fname, ctype, ln in rows:
+            t = _CT.get(ctype) or getattr(mod, ctype)
+            want.append((fname, t, ln))
+        assert [(a, c) for a, _, c in got] == [(a, c) for a, _, c in want], name
+        for (fn, tg, _), (_, tw, _) in zip(got, want):
+            assert tg is tw or (C.sizeof(tg) == C.sizeof(tw) and tg.__name__ == tw.__name__), (name, fn, tg, tw)
 
 
 def test_host_side_argument_validation_needs_no_gpu():

@@ -175,17 +175,55 @@ def test_policy_cdf_and_full_size_rollouts(hk, oracle):
     assert tot[0] == pytest.approx(n - whole["nan_count"].sum(), rel=1e-9) or tot[0] <= n
 
 
-def test_tree_search_api(hk):
-    """KartMCTS.constructSearchTree / getBestStatesSequence drop-in: the plan covers the search depth."""
+def test_tree_search_api(hk, oracle):
+    """KartMCTS.constructSearchTree / getBestStatesSequence drop-in, both modes of the reference's `parallel` argument.
+    parallel=False (what HierarchicalKartAgent calls): the device-resident sequential search handed back as a KartMCTSNode graph —
+    node for node the oracle's tree, states replayed lazily, continued by constructSearchTree(root) — and a best-states walk that
+    reaches the terminal depth.  parallel=True: the leaf-parallel host tree."""
     track = tracks.COMPLEX
     G = mcts.Game(track, 2, 2)
-    root = mcts.DiscreteGameState(G, tracks.root_state(track, 0, [2, 3], teams=[0, 1], tire_age=2500))
+    st = tracks.root_state(track, 0, [2, 3], teams=[0, 1], tire_age=2500)
+    root = mcts.DiscreteGameState(G, st)
     mcts.KartMCTS.random.seed(7)
-    node = mcts.KartMCTS.constructSearchTree(root, T=30.0, seed=1, max_iterations=40)
+    node = mcts.KartMCTS.constructSearchTree(root, T=30.0, seed=1, max_iterations=60, parallel=True)
     assert node.numEpisodes > 0 and len(node.children) == len(root.nextMoves())
     best = mcts.KartMCTS.getBestStatesSequence(node)
     assert len(best) >= 1
     assert all(all(k.section == s.lastCompletedSection for k in s.kartStates) for s in best)
+    # sequential mode
+    OG = _oracle_game(oracle, track, 2, 2)
+    node = mcts.KartMCTS.constructSearchTree(root, seed=4242, max_iterations=200)          # sized for the continued call below
+    ot = oracle.Tree(OG, st, key=4242)
+    assert ot.search(200) == 0
+    d = ot.dump(states=True)
+    flat = []
+    stack = [node]
+    while stack:
+        n = stack.pop()
+        flat.append(n)
+        stack.extend(reversed(list(n.children.values())))
+    assert len(flat) == ot.size and node.numEpisodes == 200 and node.childrenAsRoot == ot.size - 1
+    by_path = {}
+    for i in range(ot.size):                                                                  # oracle nodes keyed by their action path
+        path, j = [], i
+        while d["parent"][j] >= 0:
+            path.append(int(d["gen"][j])); j = int(d["parent"][j])
+        by_path[tuple(reversed(path))] = i
+    for n in flat[::37] + flat[-3:]:
+        path, m = [], n
+        while m.parent is not None:
+            path.append(G.gen_index(next(k for k, v in m.parent.children.items() if v is m))); m = m.parent
+        i = by_path[tuple(reversed(path))]
+        assert n.numEpisodes == int(d["numEpisodes"][i]) and np.float32(n.totalValue) == d["totalValue"][i]
+        assert bytes(n.state.state) == d["states"][i].tobytes()                               # lazily replayed state
+    best = mcts.KartMCTS.getBestStatesSequence(node)
+    assert len(best) == 8 and len(node._device_best) == 8                                     # the chain simulate() grew, to the terminal depth
+    assert all(all(k.section == s.lastCompletedSection for k in s.kartStates) for s in best)
+    with pytest.raises(ValueError):
+        mcts.KartMCTS.constructSearchTree(node, max_iterations=50)                            # node budget of the first call exhausted
+    node = mcts.KartMCTS.constructSearchTree(root, seed=4242, max_iterations=120, reserve_iterations=200)
+    node2 = mcts.KartMCTS.constructSearchTree(node, max_iterations=80)                        # constructSearchTree(root): continues on the device
+    assert node2.numEpisodes == 200 and node2.childrenAsRoot >= node.childrenAsRoot
 
 
 @pytest.mark.parametrize("track_name,n_karts,bucket,teams", [("Complex", 2, 2, [0, 1]), ("Oval", 2, 1, [0, 1]), ("Complex", 4, 2, [0, 0, 1, 1]),
@@ -206,7 +244,7 @@ def test_device_tree_search_equals_host_mirror(hk, track_name, n_karts, bucket, 
         M.KartMCTS.rollouts_per_leaf = R
         for r, root in enumerate(roots):
             M.KartMCTS.random = M.PhiloxPicks(seed + r)
-            tree = M.KartMCTS.constructSearchTree(M.DiscreteGameState(G, root), T=1e9, seed=seed + r, max_iterations=K)
+            tree = M.KartMCTS.constructSearchTree(M.DiscreteGameState(G, root), T=1e9, seed=seed + r, max_iterations=K, parallel=True)
             seq = M.KartMCTS.getBestStatesSequence(tree)
             kids = [tree.children[mv] for mv in tree.state.nextMoves()]
             assert int(dev["n_nodes"][r]) == 1 + tree.childrenAsRoot

@@ -195,3 +195,28 @@ def test_decision_statistics_against_reference_procedures(hk, oracle, root_secti
     stat_len, dof_len = _chi2_two_sample(np.asarray(l_len, np.int64), np.asarray(o_len[:512], np.int64), 17)
     assert stat_len > chi2.isf(1e-4, dof_len)                          # 1-2 states against the reference's chain to the terminal depth
     assert l_len.max() <= 2 and o_len.min() >= 7
+
+
+def test_game_golden_fixture_on_device(hk):
+    """The committed fixture tests/golden/game_golden.npz — kart transitions and sequential tree searches frozen from the CPU oracle after
+    two independent restatements agreed with it — reproduced by the CUDA library through the C-ABI, bit for bit."""
+    G = np.load("tests/golden/game_golden.npz")
+    for name, track, bucket in (("oval2", tracks.OVAL, 2), ("complex1", tracks.COMPLEX, 1)):
+        game = mcts.Game(track, 2, bucket)
+        ks, acts, new = G[f"{name}_kart_states"], G[f"{name}_actions"], G[f"{name}_new_states"]
+        n = len(ks)
+        roots = np.zeros(n, dtype=abi.GAME_STATE_DTYPE)
+        roots["n_karts"] = 1
+        roots["initialSection"] = roots["lastCompletedSection"] = ks["section"]
+        roots["finalSection"] = ks["section"] + 8
+        for f in abi.KART_STATE_FIELDS:
+            roots["karts"][:, 0][f] = ks[f]
+        out = game.replay(roots, acts.reshape(n, 1, 3))
+        got = out["states"][:, 1]["karts"][:, 0]
+        for f in abi.KART_STATE_FIELDS:
+            assert np.array_equal(got[f], new[f]), f
+        res = game.search_seq_batch(G[f"{name}_roots"], 64, 20260401)
+        for k in ("n_best", "root_gen", "root_episodes", "n_nodes"):
+            assert np.array_equal(res[k], G[f"{name}_search_{k}"]), k
+        assert res["best"].tobytes() == G[f"{name}_search_best"].tobytes()
+        assert np.array_equal(res["root_values"].view(np.uint32), G[f"{name}_search_root_values"].view(np.uint32))

@@ -251,3 +251,187 @@ def _walk(node):
     yield node
     for c in node.children:
         yield from _walk(c)
+
+
+@pytest.mark.parametrize("track_name,n_karts,bucket", [("Complex", 2, 2), ("Oval", 3, 1), ("Complex", 4, 2), ("Oval", 1, 2)])
+def test_sequential_tree_search_c_equals_python_restatement(oracle, track_name, n_karts, bucket):
+    """hk_oracle_mcts.c (arrays and indices) against oracle/np_mcts_seq.py — a second restatement written from the C# text with objects,
+    parent references and insertion-ordered dictionaries (KartMCTS.cs:18-38, 50-122, 162-201, 238-289): same nodes in the same creation
+    order, same numEpisodes / float32 totalValue bits / child order, same getBestStatesSequence, also after a continued search on the
+    same root (constructSearchTree(KartMCTSNode), :80-106)."""
+    from oracle import np_mcts_seq as NS
+    track = tracks.TRACKS[track_name]
+    g = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(n_karts), n_karts, tracks.game_params(track, bucket))
+    root = tracks.root_state(track, 7, [2, 3, 1, 4][:n_karts], teams=[0, 1, 0, 1][:n_karts], tire_age=2500, times=[0, 40, 10, 20][:n_karts])
+    for i in range(n_karts):
+        root.karts[i].max_velocity = bucket
+    key = 20260200 + n_karts
+    t = oracle.Tree(g, root, key=key)
+    assert t.search(30) == 0 and t.search(18) == 0
+    s = NS.SequentialSearch(g, key)
+    r = s.constructSearchTree(root, 30)
+    r = s.constructSearchTree(r, 18)
+    d, f = t.dump(), NS.flatten(r)
+    for k in ("parent", "numEpisodes", "n_children", "first_child"):
+        assert np.array_equal(d[k], f[k]), k
+    assert np.array_equal(d["totalValue"].view(np.uint32), f["totalValue"].view(np.uint32))
+    assert [x.astuple() for x in t.best_states()] == [x.astuple() for x in s.getBestStatesSequence(r)]
+    assert t.children_as_root == r.childrenAsRoot == t.size - 1
+    # bookkeeping of simulate / backpropagate: the root saw every iteration, a node's children never hold more episodes than it does
+    assert d["numEpisodes"][0] == 48 and d["numEpisodes"].min() >= 1
+    for i in range(t.size):
+        kids = np.flatnonzero(d["parent"] == i)
+        assert d["numEpisodes"][kids].sum() <= d["numEpisodes"][i]
+
+
+def test_sequential_search_decisions_do_not_depend_on_the_random_source(oracle):
+    """The CUDA library draws the rollout policy's index from the closed-form distribution through Philox (mode 0); the reference draws
+    it with NextGaussian's rejection loop and picks with System.Random (mode 1).  Decision statistics of the sequential search — first
+    waypoint lane of kart 0, len(bestStates), the root's most visited first action — agree between the two sources (chi-square over
+    1,536 trees each, p > 1e-4)."""
+    from scipy.stats import chi2
+    track = tracks.COMPLEX
+    g = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, tracks.game_params(track))
+    root = tracks.root_state(track, 12, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 30])
+    for i in range(2):
+        root.karts[i].max_velocity = 2
+    n, iters = 1536, 96
+    from oracle import structs as OS
+    roots = np.zeros(n, dtype=OS.GAME_STATE_DTYPE)
+    roots[:] = np.frombuffer(bytes(root), dtype=OS.GAME_STATE_DTYPE)[0]
+    a = oracle.tree_search_batch(g, roots, iters, seed=4711, mode=0)
+    b = oracle.tree_search_batch(g, roots, iters, seed=0, mode=1, rng_states=(np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1))
+    assert np.all(a["root_episodes"].sum(axis=1) == iters) and np.all(b["root_episodes"].sum(axis=1) == iters)
+
+    def stats(o):
+        lane = o["best"][:, 0]["karts"][:, 0]["lane"].astype(np.int64)
+        top = np.array([o["root_gen"][r][np.argmax(o["root_episodes"][r])] for r in range(n)], np.int64)
+        return lane, o["n_best"].astype(np.int64), top
+    for x, y, bins in zip(stats(a), stats(b), (5, 17, 36)):
+        ca, cb = np.bincount(x, minlength=bins).astype(float), np.bincount(y, minlength=bins).astype(float)
+        keep = (ca + cb) >= 20
+        ca, cb = np.append(ca[keep], ca[~keep].sum()), np.append(cb[keep], cb[~keep].sum())
+        ok = (ca + cb) > 0
+        stat = float((((ca[ok] - cb[ok]) ** 2) / (ca[ok] + cb[ok])).sum())
+        assert stat < chi2.isf(1e-4, max(int(ok.sum()) - 1, 1)), (stat, ca, cb)
+
+
+def _np_game(track, n_karts, bucket, kart_consts=None):
+    from oracle import np_game
+    karts = tracks.kart_array(n_karts) if kart_consts is None else tracks.kart_array(n_karts, kart_consts)
+    return np_game.NpGame(track.sections_array(), track.n_sections, karts, n_karts, tracks.game_params(track, bucket)), karts
+
+
+@pytest.mark.parametrize("track_name,bucket", [("Oval", 2), ("Complex", 2), ("Complex", 1)])
+def test_game_arithmetic_c_oracle_equals_numpy_restatement(oracle, track_name, bucket):
+    """applyAction / computeTOC / tyre update of hk_oracle_game.c against oracle/np_game.py — a numpy float32 restatement written from
+    the C# text (KartDiscreteGame.cs:58-171, DiscretePositionTracker.cs:72-199, ArcadeKart.cs:517-547), not from the C file — on 40,000
+    random (kart state, action) pairs per case (120,000 in all), bit for bit: sections of every geometry, root (0, b) and action
+    buckets, off-grid buckets, tyre ages beyond the wear where the lateral-g limit turns NaN (> 13,333), large times, illegal lane jumps."""
+    from oracle import structs as OS
+    track = tracks.TRACKS[track_name]
+    ng, karts = _np_game(track, 2, bucket)
+    g = oracle.Game(track.sections_array(), track.n_sections, karts, 2, tracks.game_params(track, bucket))
+    rng = np.random.default_rng(20260300 + bucket + len(track_name))
+    n = 40000
+    ks = np.zeros(n, dtype=OS.np_dtype(OS.hk_kart_state))
+    ks["section"] = rng.integers(0, 4 * track.n_sections, n)
+    ks["lane"] = rng.integers(1, 5, n)
+    vmin = rng.choice([0] + list(range(6, 15, bucket)) + [3, 7, 9, 13], n)
+    ks["min_velocity"] = vmin
+    ks["max_velocity"] = np.where(vmin == 0, bucket, np.minimum(vmin + rng.choice([1, 2, 3], n), 15))
+    ks["tireAge"] = rng.choice([0, 1, 2500, 2501, 6000, 9999, 13333, 13334, 13500, 20000], n) + rng.integers(0, 3, n)
+    ks["laneChanges"] = rng.integers(0, 5, n)
+    ks["timeAtSection"] = rng.choice([0, 1, 150, 99999, 2147483000], n)
+    ks["team"] = rng.integers(0, 2, n)
+    a_min = rng.choice(list(range(6, 15, bucket)), n).astype(np.int32)
+    a_max = np.minimum(a_min + bucket, 15).astype(np.int32)
+    a_lane = rng.integers(1, 5, n).astype(np.int32)
+    got = ng.apply_actions(ks, a_min, a_max, a_lane)
+    import ctypes as C
+    for i in range(n):
+        rec = OS.hk_kart_state.from_buffer_copy(ks[i].tobytes())
+        ref = g.apply_action(rec, (int(a_min[i]), int(a_max[i]), int(a_lane[i])))
+        assert bytes(ref) == got[i].tobytes(), (i, ref.astuple(), got[i])
+    assert (got["infeasible"] == 1).any() and (got["infeasible"] == 0).any()
+
+
+@pytest.mark.parametrize("track_name,n_karts,bucket,teams", [("Oval", 2, 2, [0, 1]), ("Complex", 3, 2, [0, 0, 1]), ("Complex", 4, 1, [0, 1, 0, 1]),
+                                                             ("Oval", 1, 2, [0]), ("Complex", 2, 2, [0, 0])])
+def test_game_level_c_oracle_equals_numpy_restatement(oracle, track_name, n_karts, bucket, teams):
+    """upNext (incl. the unstable 3-element sort network and ties at the root), nextMoves, the rollout policy's order, makeMove and
+    isOver (no-move terminals, team scoring with the never-reset accumulators, integer truncation of the raw scores, NaN when
+    max == min, the single-kart branch) of the C oracle against oracle/np_game.py along random playouts from random roots."""
+    track = tracks.TRACKS[track_name]
+    ng, karts = _np_game(track, n_karts, bucket)
+    g = oracle.Game(track.sections_array(), track.n_sections, karts, n_karts, tracks.game_params(track, bucket))
+    rng = np.random.default_rng(99 + n_karts * 7 + bucket)
+    terminals = nomove = 0
+    for trial in range(30):
+        sec = int(rng.integers(0, 3 * track.n_sections))
+        times = [0] + [int(x) for x in rng.choice([0, 0, 17, 150], n_karts - 1)]                # ties are common at the root
+        st = tracks.root_state(track, sec, [int(x) for x in rng.integers(1, 5, n_karts)], teams=teams,
+                               tire_age=int(rng.choice([0, 2500, 9900, 13500])), lane_changes=int(rng.integers(0, 4)), times=times)
+        for i in range(n_karts):
+            st.karts[i].max_velocity = bucket
+        if trial % 5 == 4:
+            st.finalSection = st.initialSection + 2
+        for ply in range(n_karts * 8 + 2):
+            assert g.up_next(st) == ng.up_next(st)
+            o1, s1 = g.is_over(st)
+            o2, s2 = ng.is_over(st)
+            assert o1 == o2 and s1.tobytes() == s2.tobytes() or (np.isnan(s1).any() and np.array_equal(np.isnan(s1), np.isnan(s2))), (o1, o2, s1, s2)
+            m1, g1, c1 = g.next_moves(st)
+            m2, g2, c2 = ng.next_moves(st)
+            assert (m1, g1, c1) == (m2, g2, c2)
+            p1, pg1, _ = g.policy_moves(st)
+            p2, pg2, _ = ng.policy_moves(st)
+            assert (p1, pg1) == (p2, pg2)
+            if o1:
+                terminals += 1
+                nomove += int(c1 == 0)
+                break
+            mv = p1[int(min(len(p1) - 1, abs(rng.normal(0, len(p1) / 6.0))))] if rng.random() < 0.8 else m1[int(rng.integers(len(m1)))]
+            n1, n2 = g.make_move(st, mv), ng.make_move(st, mv)
+            assert bytes(n1) == bytes(n2)
+            st = n1
+    assert terminals >= 20
+
+
+def test_sequential_search_on_the_numpy_game_equals_the_c_oracle(oracle):
+    """The two second opinions together: oracle/np_mcts_seq.py (tree bookkeeping from the C# text) running on oracle/np_game.py (game
+    arithmetic from the C# text) — no line of either C file involved — builds the tree hk_oracle_mcts.c builds over hk_oracle_game.c."""
+    from oracle import np_mcts_seq as NS
+    track = tracks.COMPLEX
+    ng, karts = _np_game(track, 2, 2)
+    g = oracle.Game(track.sections_array(), track.n_sections, karts, 2, tracks.game_params(track, 2))
+    root = tracks.root_state(track, 3, [2, 3], teams=[0, 1], tire_age=2500, times=[0, 25])
+    for i in range(2):
+        root.karts[i].max_velocity = 2
+    t = oracle.Tree(g, root, key=31)
+    assert t.search(12) == 0
+    s = NS.SequentialSearch(ng, 31)
+    r = s.constructSearchTree(root, 12)
+    d, f = t.dump(), NS.flatten(r)
+    for k in ("parent", "numEpisodes", "n_children", "first_child"):
+        assert np.array_equal(d[k], f[k]), k
+    assert np.array_equal(d["totalValue"].view(np.uint32), f["totalValue"].view(np.uint32))
+    assert [x.astuple() for x in t.best_states()] == [x.astuple() for x in s.getBestStatesSequence(r)]
+
+
+def test_game_golden_fixture_matches_oracle(oracle):
+    """tests/golden/game_golden.npz (frozen by tests/golden/make_golden.py after both independent restatements agreed with the C oracle
+    on these very inputs): 400 kart transitions and 24 sequential tree searches still come out of the oracle bit for bit."""
+    from oracle import structs as OS
+    G = np.load("tests/golden/game_golden.npz")
+    for name, track, bucket in (("oval2", tracks.OVAL, 2), ("complex1", tracks.COMPLEX, 1)):
+        g = oracle.Game(track.sections_array(), track.n_sections, tracks.kart_array(2), 2, tracks.game_params(track, bucket))
+        ks, acts, new = G[f"{name}_kart_states"], G[f"{name}_actions"], G[f"{name}_new_states"]
+        for i in range(len(ks)):
+            ref = g.apply_action(OS.hk_kart_state.from_buffer_copy(ks[i].tobytes()), tuple(int(v) for v in acts[i]))
+            assert bytes(ref) == new[i].tobytes()
+        res = oracle.tree_search_batch(g, G[f"{name}_roots"], 64, seed=20260401, mode=0)
+        for k in ("n_best", "root_gen", "root_episodes", "n_nodes"):
+            assert np.array_equal(res[k], G[f"{name}_search_{k}"]), k
+        assert res["best"].tobytes() == G[f"{name}_search_best"].tobytes()
+        assert np.array_equal(res["root_values"].view(np.uint32), G[f"{name}_search_root_values"].view(np.uint32))

@@ -192,3 +192,71 @@ def test_batched_mcts_root_states_and_handoff_equal_per_agent_versions():
             R.apply_best_states(track, karts[r], pb[r], e, nb, [_GS(best[r, e, k]) for k in range(int(n_best[r, e]))])
     for f in ("lane", "vel", "oppLane", "oppVel"):
         assert np.array_equal(pa[f], pb[f]), f
+
+
+def _track_tables(track):
+    sec, trig, fwd, lane = R.geometry(track)
+    return dict(trig=trig, lane=lane, straight=[sec[i].insideR == 0.0 for i in range(track.n_sections)])
+
+
+@pytest.mark.parametrize("track", [S.OVAL, S.COMPLEX])
+@pytest.mark.parametrize("mcts", [True, False])
+def test_oracle_recipe_equals_independent_restatement(oracle, track, mcts):
+    """hk_oracle_race.c's recipe against oracle/np_recipe.py — a restatement of SolveLQR's problem construction written from the C#
+    text (HierarchicalKartAgent.cs:699-1201) that lives under oracle/, shares no code with the C file and none with the product
+    package: every compact field of both agents' problems on 1,500 race states (start grids driven forward, plans from planFixed and
+    hand-written beliefs, a finished kart), integers of the weights bit for bit, headings to 1e-14."""
+    from oracle import np_recipe
+    OR, prm = _oracle_races(oracle, track, high_mode_mcts=mcts)
+    tt = _track_tables(track)
+    rng = np.random.default_rng(77)
+    n = 750
+    karts, plans = R.start_grid(track, n, seed=5)
+    L = track.n_sections
+    sec = rng.integers(0, 2 * L, size=(n, 2))
+    sec[:, 1] = sec[:, 0] + rng.integers(-1, 2, size=n)
+    sec = np.maximum(sec, 0)
+    lanes_xy, head = track.lane_table(), track.heading_table()
+    for e in range(2):
+        s0 = sec[:, e] % L
+        ln = rng.integers(1, 5, size=n)
+        p0, p1 = lanes_xy[s0, ln - 1], lanes_xy[(s0 + 1) % L, ln - 1]
+        fr = rng.random(n)[:, None]
+        pos = (p0 + (p1 - p0) * fr + rng.normal(0, 0.5, size=(n, 2))).astype(np.float32)
+        karts["x"][:, e], karts["z"][:, e] = pos[:, 0], pos[:, 1]
+        karts["v"][:, e] = np.where(rng.random(n) < 0.15, rng.uniform(0, 5, n), rng.uniform(5, 15, n)).astype(np.float32)
+        karts["h"][:, e] = np.mod(head[s0] + rng.normal(0, 0.2, n), 2 * np.pi)
+        karts["section"][:, e] = sec[:, e]
+        karts["lane"][:, e] = ln
+    karts["active"][::97, 1] = 0
+    for key, vk in (("lane", "vel"), ("oppLane", "oppVel")):
+        on = rng.random((n, 2, abi.HK_MAX_SECTIONS)) < 0.6
+        plans[key][:] = np.where(on, rng.integers(1, 5, size=on.shape), 0)
+        plans[vk][:] = np.where(on, rng.choice([8, 10, 12, 14, 15], size=on.shape), 0)
+    ref = OR.recipe(karts, plans)
+    for r in range(n):
+        for e in range(2):
+            got = np_recipe.race_recipe_2kart(tt, prm, karts[r], plans[r], e)
+            b = 2 * r + e
+            assert got["players"] == [e, 1 - e]
+            for k in ("x0", "tw", "cw", "aw", "otgt", "otw"):
+                assert np.array_equal(np.asarray(got[k]).reshape(ref[k][b].shape), ref[k][b]), (k, r, e, got[k], ref[k][b])
+            assert np.max(np.abs(got["target"] - ref["target"][b])) <= 1e-14
+
+
+def test_fixed_mode_avoid_weight_known_answer(oracle):
+    """the ego's avoid-weight multiplier is `HighMode == Fixed ? 0.45f : 1.0f` (HierarchicalKartAgent.cs:999-1002), the
+    other player's 1.3f.  Known answers worked out by hand from :1019 for two karts 4 m apart (d^1.5 = 8 exactly):
+      Fixed, ego:  0.45f = 0.449999988079071044921875, x 8 = 3.599999904632568359375 (exact), 1 / that = 0.277777785136... ->
+                   nearest float32 0.2777777910232543945 (the 1.0f multiplier of round 1 gave 0.125: 2.2x too small a weight)
+      MCTS,  ego:  1 / (8 x 1.0f) = 0.125
+      other:       1.3f = 1.2999999523162841796875, x 8 = 10.3999996185302734375, 1 / that = 0.0961538496... -> float32 0.09615384787321091"""
+    track = S.OVAL
+    for mcts, want_ego in ((False, 0.2777777910232544), (True, 0.125)):
+        OR, prm = _oracle_races(oracle, track, high_mode_mcts=mcts)
+        karts, plans = R.start_grid(track, 1, seed=1)
+        karts["x"][0], karts["z"][0] = [14.0, 14.0], [0.0, 4.0]
+        out = OR.recipe(karts, plans)
+        assert out["aw"][0, 0, 0, 0] == out["aw"][0, 0, 0, 1] == want_ego
+        assert out["aw"][0, 1, 0, 0] == 0.09615384787321091
+        assert out["aw"][1, 0, 0, 0] == want_ego and out["aw"][1, 1, 0, 0] == 0.09615384787321091     # the other agent's own problem

@@ -175,7 +175,7 @@ def test_batched_mcts_planning_equals_per_agent_host_search(hk):
         for r in range(n_races):
             for ego in range(2):
                 M.KartMCTS.random = M.PhiloxPicks(seed + 2 * r + ego)
-                root, best = R.plan_with_mcts(track, prm, game, karts[r], pb[r], ego, T=1e9, max_iterations=K, seed=seed + 2 * r + ego)
+                root, best = R.plan_with_mcts(track, prm, game, karts[r], pb[r], ego, T=1e9, max_iterations=K, seed=seed + 2 * r + ego, parallel=True)
                 assert len(best) == int(out["n_best"][2 * r + ego])
     finally:
         M.KartMCTS.random, M.KartMCTS.rollouts_per_leaf = old_random, old_R
