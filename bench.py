@@ -99,18 +99,26 @@ class ClockSampler(threading.Thread):
                 pass
             self._halt.wait(0.1)
 
-    def finish(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+    @staticmethod
+    def _stats(rows):
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+    def finish(self, head: int | None = None):
+        """Clocks of the timed region of `value` (the first `head` samples) with the whole run's beside them."""
+        self._halt.set()
+        self.join(timeout=6)
+        out = self._stats(self.rows[:head] if head else self.rows)
+        if head:
+            out["whole_run"] = self._stats(self.rows)
+        return out
 
 
 def bind_to_gpu_numa(index: int):
@@ -139,7 +147,7 @@ def cpu_baseline(seconds: float = 12.0, threads: int | None = None):
     from hierarchicalkarting_b200 import scenarios as S
     from oracle import oracle as O
     threads = threads or os.cpu_count() or 1
-    sample = 16384
+    sample = BATCH
     A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(S.OVAL, sample, 2, seed=20260001))
     O.lqng_solve_batch(A[:256], B[:256], Q[:256], q[:256], R[:256], x0[:256], HORIZON, threads=threads, full=False)
     done, t0 = 0, time.perf_counter()
@@ -153,7 +161,7 @@ def cpu_baseline(seconds: float = 12.0, threads: int | None = None):
     O.lqng_solve_batch(A[:4096], B[:4096], Q[:4096], q[:4096], R[:4096], x0[:4096], HORIZON, threads=1, full=False)
     single = 4096 / (time.perf_counter() - t1)
     return {"value": done / el, "unit": "solves/s", "cores": threads, "kind": "port",
-            "sample": f"{done} solves of BASELINE config 2 (16384-problem sample of the 65,536 batch, repeated for {el:.1f} s); "
+            "sample": f"{done} solves of BASELINE config 2 (the whole 65,536-problem batch, repeated for {el:.1f} s); "
                       f"C oracle restatement of KartLQR.solveFeedbackLQR, OpenMP static split; single thread: {single:.0f} solves/s",
             "single_thread_value": single}
 
@@ -167,9 +175,9 @@ def run_reference(args):
     from hierarchicalkarting_b200 import scenarios as S
     from oracle import oracle as O
     threads = os.cpu_count() or 1
-    sample = 16384
+    sample = args.batch                                  # the b200 arm's batch: same config, same problems (seed 20260001, rank 0's shard)
     A, B, Q, q, R, x0 = S.assemble_dense(S.make_problems(S.OVAL, sample, 2, seed=20260001))
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(min(args.warmup, 2), 1)):
         O.lqng_solve_batch(A, B, Q, q, R, x0, HORIZON, threads=threads, full=False)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -179,8 +187,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "lqng_solves_per_s", "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: independent 2-kart Oval LQNG problems, horizon 3, dt=(double)0.02f; "
-                                   f"bounded sample of {sample} problems per step", "batch_per_step": sample},
+            "config": {"workload": "BASELINE config 2: 65,536 independent 2-kart LQNG problems per GPU (random linearisation points along "
+                                   "the Oval track, seed 20260001+rank), horizon 3, dt=(double)0.02f; output u0 of every player + status",
+                       "batch_per_gpu": sample, "horizon": HORIZON, "players": 2,
+                       "note": "the CPU arm solves rank 0's whole batch per step on the host cores (N > 1: rank 0 only)"},
             "cpu_baseline": {"value": v, "unit": "solves/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} problems per step x {args.steps} steps; C oracle port of KartLQR.solveFeedbackLQR "
                                        "(reference C# not compilable: no .NET in image), OpenMP over all host threads"},
@@ -218,6 +228,8 @@ def main():
     ap.add_argument("--no-mcts", action="store_true")
     ap.add_argument("--no-race", action="store_true")
     ap.add_argument("--no-lqng4", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -281,6 +293,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- the FP64 roofline denominator of THIS box, burst (clocks at boost, like the short timed region below) ---------------------
+    def probe(seconds):
+        tf, mhz, ran = (C.c_double(0.0) for _ in range(3))
+        abi.check(lib.hk_probe_fp64_peak(seconds, C.byref(tf), C.byref(mhz), C.byref(ran)))
+        return {"tflops": tf.value, "sm_mhz_effective": mhz.value, "seconds": ran.value}
+    import ctypes as C
+    probe(0.01)
+    time.sleep(0.5)                                # let the clocks return to idle boost
+    peak_burst = probe(0.004)
+
     # ---- HBM-resident throughput (`value`) -------------------------------------------------------------------------------
     for k in range(args.warmup):
         step_device(k)
@@ -309,6 +331,35 @@ def main():
         a0.record(stream); step_device(k); a1.record(stream); a1.synchronize()
         per.append(a0.elapsed_time(a1))
     isolated_ms = float(np.mean(per))
+    value_rows = len(sampler.rows)
+
+    # ---- sustained: the same launch back to back for >= 2 s (clocks settle under FP64 power), then the FP64 stream for 2 s ------------
+    sustained = None
+    if not args.no_sustained:
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        row0 = len(sampler.rows)
+        n_sus, t_begin = 0, time.perf_counter()
+        s0.record(stream)
+        while time.perf_counter() - t_begin < args.sustained_seconds:
+            for k in range(256):
+                step_device(n_sus + k)
+            n_sus += 256
+            stream.synchronize()
+        s1.record(stream)
+        s1.synchronize()
+        sus_ms = s0.elapsed_time(s1)
+        rows = sampler.rows[row0:]
+        tail = rows[len(rows) // 2:] or rows                                   # second half: settled
+        peak_sus = probe(args.sustained_seconds)
+        sus_tf = batch * FLOPS_PER_SOLVE * n_sus / (sus_ms * 1e-3) / 1e12
+        sustained = {"seconds": sus_ms * 1e-3, "launches": n_sus, "solves_per_s": batch * n_sus / (sus_ms * 1e-3), "achieved": sus_tf,
+                     "sm_mhz_median_second_half": float(np.median([float(r[0]) for r in tail])) if tail else None,
+                     "power_w_median_second_half": float(np.median([float(r[2]) for r in tail])) if tail else None,
+                     "power_w_max": float(max(float(r[2]) for r in rows)) if rows else None,
+                     "reasons": sorted({n for r in rows for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]) if v.lower().startswith("active")}),
+                     "peak": peak_sus}
+        launches = 0
     sampler.period = 0.25              # the legs below are timed on the host and are sensitive to driver-lock contention
 
     # ---- end to end through the host-pointer C-ABI call (`e2e`) ----------------------------------------------------------
@@ -359,6 +410,17 @@ def main():
             big_d.copy_(big_h, non_blocking=True)
         torch.cuda.synchronize()
         gbs = 10 * compact_bytes / (time.perf_counter() - t0) / 1e9
+        # the call's pipeline copies on four streams at once; what four concurrent copies of a quarter each reach
+        streams4 = [torch.cuda.Stream(device=dev) for _ in range(4)]
+        q4 = (compact_bytes // 8) // 4
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            for i, st4 in enumerate(streams4):
+                with torch.cuda.stream(st4):
+                    big_d[i * q4:(i + 1) * q4].copy_(big_h[i * q4:(i + 1) * q4], non_blocking=True)
+        torch.cuda.synchronize()
+        gbs4 = 10 * 4 * q4 * 8 / (time.perf_counter() - t0) / 1e9
         t0 = time.perf_counter()
         for _ in range(200):
             small_d.copy_(small_h, non_blocking=True)
@@ -372,7 +434,7 @@ def main():
             drv = drv.decode() if isinstance(drv, bytes) else drv
         except Exception:
             pass
-        return {"h2d_23mb_gbs": gbs, "h2d_8kb_roundtrip_us": us, "driver": drv}
+        return {"h2d_23mb_gbs": gbs, "h2d_23mb_4streams_gbs": gbs4, "h2d_8kb_roundtrip_us": us, "driver": drv}
     try:
         box_probe = _probe()
     except Exception as exc:
@@ -398,19 +460,39 @@ def main():
                     "plies_per_s": world * plies / el, "ms_per_decision": 1e3 * el / reps, "rollouts_per_decision": MCTS_ROLLOUTS,
                     "config": "BASELINE config 4: Complex, 2 karts, depth 8, bucket 2, Philox4x32-10; host call incl. result D2H",
                     "gpu_launches": reps}
-        # the same decision through the reference's own entry points (KartMCTS.constructSearchTree + getBestStatesSequence): host tree
-        # policy, every iteration expands one leaf with a batch of GPU rollouts through each child (processLeaf, KartMCTS.cs:124-159)
+        # the same decision through the reference's own entry points (KartMCTS.constructSearchTree + getBestStatesSequence), both values
+        # of its `parallel` argument: false = the sequential search HierarchicalKartAgent runs (one playout per iteration, device-resident
+        # tree, hk_mcts_forest_search); true = processLeaf with 4,096 playouts per child (host tree, GPU rollout batches)
         try:
             root_state = M.DiscreteGameState(G, leaf)
-            M.KartMCTS.rollouts_per_leaf = 4096
-            M.KartMCTS.constructSearchTree(root_state, T=1e9, seed=7, max_iterations=3)          # warm-up
+            M.KartMCTS.constructSearchTree(root_state, seed=7, max_iterations=32)                 # warm-up
             t0 = time.perf_counter()
-            root = M.KartMCTS.constructSearchTree(root_state, T=1e9, seed=20260003, max_iterations=14)
+            root = M.KartMCTS.constructSearchTree(root_state, seed=20260003, max_iterations=512)
+            el_seq = time.perf_counter() - t0
+            seq = M.KartMCTS.getBestStatesSequence(root)
+            mcts_obj["tree_search"] = {"ms_per_decision": 1e3 * el_seq, "iterations": 512, "episodes_at_root": int(root.numEpisodes),
+                                       "nodes": int(root.childrenAsRoot), "best_sequence_states": len(seq), "parallel": False,
+                                       "api": "KartMCTS.constructSearchTree(state, parallel=false) + getBestStatesSequence (Python mirror of the C# API "
+                                              "over the C-ABI): the reference's sequential search, one GPU thread, incl. the node-record download"}
+            M.KartMCTS.rollouts_per_leaf = 4096
+            M.KartMCTS.constructSearchTree(root_state, T=1e9, seed=7, max_iterations=3, parallel=True)          # warm-up
+            t0 = time.perf_counter()
+            root = M.KartMCTS.constructSearchTree(root_state, T=1e9, seed=20260003, max_iterations=14, parallel=True)
             seq = M.KartMCTS.getBestStatesSequence(root)
             el_tree = time.perf_counter() - t0
-            mcts_obj["tree_search"] = {"ms_per_decision": 1e3 * el_tree, "iterations": 14, "episodes_at_root": int(root.numEpisodes),
-                                       "nodes": int(root.childrenAsRoot), "best_sequence_states": len(seq),
-                                       "api": "KartMCTS.constructSearchTree + getBestStatesSequence (Python mirror of the C# API over the C-ABI)"}
+            mcts_obj["tree_search_leaf_parallel"] = {"ms_per_decision": 1e3 * el_tree, "iterations": 14, "episodes_at_root": int(root.numEpisodes),
+                                                     "nodes": int(root.childrenAsRoot), "best_sequence_states": len(seq), "parallel": True}
+            # many trees at once: what config 5 needs at every planning event (32,768 agents)
+            roots_b = M._states_array([leaf] * 32768)
+            for its in (64, 512):
+                F_b = M.Forest(G, 32768, 1 + its * 16)
+                F_b.search(roots_b, 2, 1)
+                t0 = time.perf_counter()
+                F_b.search(roots_b, its, 20260003)
+                el_b = time.perf_counter() - t0
+                mcts_obj.setdefault("forest_search", []).append({"trees": 32768, "iterations": its, "ms": 1e3 * el_b, "decisions_per_s": 32768 / el_b,
+                                                                 "playouts_per_s": 32768 * its / el_b})
+                F_b.close()
         except Exception as exc:                         # reported, never fatal to the bench line
             mcts_obj["tree_search"] = {"error": repr(exc)[:200]}
         try:                                             # the rollouts are bound by the SM issue rate, not by DRAM
@@ -493,9 +575,18 @@ def main():
     lqng4_obj = None
     if not args.no_lqng4:
         uniq, rep = 65536, 16
-        h4 = S.assemble_dense(S.make_problems(S.COMPLEX, uniq, 4, seed=20260002 + rank))
-        d4 = [torch.from_numpy(a).to(dev).repeat((rep,) + (1,) * (a.ndim - 1)).contiguous() for a in h4]
         b4 = uniq * rep
+        # 1,048,576 DISTINCT problems (16 seeded chunks of 65,536, 10.7 GB of dense operands in HBM): generated and assembled chunk by
+        # chunk on the host, so that nothing in the launch can be served by L2 from an earlier copy of the same problem
+        shapes4 = None
+        d4 = None
+        for ch in range(rep):
+            h4 = S.assemble_dense(S.make_problems(S.COMPLEX, uniq, 4, seed=20260002 + 1000 * ch + rank))
+            if d4 is None:
+                d4 = [torch.empty((b4,) + a.shape[1:], dtype=torch.float64, device=dev) for a in h4]
+            for t, a in zip(d4, h4):
+                t[ch * uniq:(ch + 1) * uniq].copy_(torch.from_numpy(a), non_blocking=False)
+        del h4
         u4 = torch.empty((b4, 8), dtype=torch.float64, device=dev)
         s4 = torch.empty((b4,), dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
@@ -514,13 +605,13 @@ def main():
         f1.synchronize()
         ms4 = max_over_ranks(f0.elapsed_time(f1)) / reps4
         bad4 = int(s4.sum().item())
-        _, _, fp64_pk, _ = _peaks()
+        fp64_pk = peak_burst["tflops"]
         lqng4_obj = {"metric": "lqng4_solves_per_s", "value": world * b4 / (ms4 * 1e-3), "unit": "solves/s", "ms_per_launch": ms4,
                      "batch_per_gpu": b4, "status_nonzero": bad4,
                      "roofline": {"bound": "tensor", "achieved": b4 * FLOPS_PER_SOLVE_4 / (ms4 * 1e-3) / 1e12, "peak": fp64_pk, "unit": "TFLOP/s",
                                   "frac": b4 * FLOPS_PER_SOLVE_4 / (ms4 * 1e-3) / 1e12 / fp64_pk,
                                   "note": f"dense count {FLOPS_PER_SOLVE_4} flops per 4-kart solve (SURVEY.md 8d); kernel lqng_mma4_kernel"},
-                     "config": f"BASELINE config 3: 4-kart 2v2 Complex problems, horizon 3; {uniq} distinct seeded problems tiled x{rep} in HBM "
+                     "config": f"BASELINE config 3: 4-kart 2v2 Complex problems, horizon 3; {b4} DISTINCT seeded problems in HBM "
                                f"({sum(t.numel() for t in d4) * 8 / 1e9:.1f} GB of operands per launch, u0 + status out)"}
         del d4, u4, s4
         torch.cuda.empty_cache()
@@ -579,29 +670,44 @@ def main():
             game_m = M2.Game(S.OVAL, 2, prm_m.velocityBucketSize)
             km, pm = RC.start_grid(S.OVAL, RACES, seed=20260004 + rank)
             RM.run(km, pm, 0, 100)                                              # standing start, no plan yet
-            MCTS_K, MCTS_R, blocks_m = 24, 16, 2
-            RM.run_mcts(km.copy(), pm.copy(), game_m, MCTS_K, MCTS_R, 1, 100, 101)                # warm-up at full size (one planning event; scratch allocated)
-            barrier()
-            k0m = lib.hk_kernel_launch_count()
-            t0 = time.perf_counter()
-            _, badm = RM.run_mcts(km, pm, game_m, MCTS_K, MCTS_R, 20260006 + 1000 * rank, 100, 100 * blocks_m)   # plans at steps 100, 200
-            el_m = max_over_ranks(time.perf_counter() - t0)
+            blocks_m = 2
             step_ms = race_obj["ms_per_step"] if race_obj else 0.0
-            race_mcts_obj = {"metric": "race_agent_steps_per_s", "value": world * 2 * RACES * 100 * blocks_m / el_m, "unit": "agent-steps/s",
-                             "races_per_gpu": RACES, "steps": 100 * blocks_m, "planning_events": blocks_m, "ms_total": 1e3 * el_m,
-                             "ms_per_planning_event_derived": (1e3 * el_m - 100 * blocks_m * step_ms) / blocks_m,
-                             "plans_per_s_derived": world * 2 * RACES * blocks_m / max(1e-9, el_m - 1e-3 * 100 * blocks_m * step_ms),
-                             "tree_search": {"iterations": MCTS_K, "rollouts_per_leaf": MCTS_R},
-                             "lqng_status_nonzero": int(badm), "gpu_launches": int(lib.hk_kernel_launch_count() - k0m),
-                             "sections_mean": float(km["section"].mean()), "waypoints_set": int(((pm["lane"] != 0) | (pm["oppLane"] != 0)).sum()),
-                             "config": "BASELINE config 5 with the MCTS high level, GPU-resident (hk_race_run_mcts): 2-kart Oval races, every agent "
-                                       "replans every 100 steps by KartMCTS.constructSearchTree + getBestStatesSequence (one thread block per "
-                                       "tree), root states and waypoint hand-off as kernels, LQNG every step; one host call incl. the upload "
-                                       "and download of the race states; the planning time is derived from the Fixed-mode step time"}
+            modes = {}
+            # the planner as the reference runs it (sequential search, 512 iterations per replan ~ 0.9 s of its C# simulate(), trees kept
+            # for 3 cycles, results landing 45 steps = 0.9 s after the search started), and the leaf-parallel mode of round 1
+            for name, kw in (("faithful", dict(mode=0, iterations=512, reuse_cycles=3, apply_delay=45)),
+                             ("leaf_parallel", dict(mode=1, iterations=24, rollouts_per_leaf=16, reuse_cycles=0, apply_delay=0))):
+                kk, pp = km.copy(), pm.copy()
+                pl = RC.Planner(game_m, RACES, seed=20260006 + 1000 * rank, **kw)
+                RM.run_planned(kk.copy(), pp.copy(), pl, 100, 101)                              # warm-up at full size (one planning event)
+                pl.close()
+                pl = RC.Planner(game_m, RACES, seed=20260006 + 1000 * rank, **kw)
+                barrier()
+                k0m = lib.hk_kernel_launch_count()
+                t0 = time.perf_counter()
+                _, badm = RM.run_planned(kk, pp, pl, 100, 100 * blocks_m)                       # plans at steps 100, 200
+                el_m = max_over_ranks(time.perf_counter() - t0)
+                _, _, tree_status = pl.state()
+                modes[name] = {"value": world * 2 * RACES * 100 * blocks_m / el_m, "unit": "agent-steps/s", "ms_total": 1e3 * el_m,
+                               "ms_per_planning_event_derived": (1e3 * el_m - 100 * blocks_m * step_ms) / blocks_m,
+                               "plans_per_s_derived": world * 2 * RACES * blocks_m / max(1e-9, el_m - 1e-3 * 100 * blocks_m * step_ms),
+                               "planner": {k: v for k, v in kw.items()}, "lqng_status_nonzero": int(badm),
+                               "gpu_launches": int(lib.hk_kernel_launch_count() - k0m), "sections_mean": float(kk["section"].mean()),
+                               "waypoints_set": int(((pp["lane"] != 0) | (pp["oppLane"] != 0)).sum()),
+                               "trees_out_of_nodes": int((tree_status == 3).sum())}
+                pl.close()
+            race_mcts_obj = dict(modes["faithful"])
+            race_mcts_obj.update({"metric": "race_agent_steps_per_s", "races_per_gpu": RACES, "steps": 100 * blocks_m, "planning_events": blocks_m,
+                                  "leaf_parallel": modes["leaf_parallel"],
+                                  "config": "BASELINE config 5 with the MCTS high level, GPU-resident (hk_race_run_planned): 2-kart Oval races, every "
+                                            "agent replans every 100 steps by the reference's sequential KartMCTS.constructSearchTree (one GPU thread "
+                                            "per tree) + getBestStatesSequence, root states and waypoint hand-off as kernels, LQNG every step; one "
+                                            "host call incl. the upload and download of the race states; the planning time is derived from the "
+                                            "Fixed-mode step time"})
         except Exception as exc:
             race_mcts_obj = {"error": repr(exc)[:300]}
 
-    clocks = sampler.finish()
+    clocks = sampler.finish(value_rows)
 
     # ---- final gather of per-rank summaries (the only communication) ------------------------------------------------------
     summary = torch.tensor([float(st_d.sum().item()), float(u0_d.sum().item()), float(batch)], dtype=torch.float64, device=dev)
@@ -614,7 +720,10 @@ def main():
             dist.destroy_process_group()
         return
 
-    hbm, hbm_src, fp64, fp64_src = _peaks()
+    hbm, hbm_src, fp64_r1, fp64_r1_src = _peaks()
+    fp64 = peak_burst["tflops"]                                                # measured on this box, seconds before the timed region
+    fp64_src = (f"DMMA m8n8k4 f64 stream on this box (hk_probe_fp64_peak, {1e3 * peak_burst['seconds']:.1f} ms burst at an effective "
+                f"{peak_burst['sm_mhz_effective']:.0f} MHz); round-1 pool figure {fp64_r1} TFLOP/s")
     value = world * batch * args.steps / (dev_ms * 1e-3)
     ach_tf = batch * FLOPS_PER_SOLVE / (kern_ms * 1e-3) / 1e12
     ach_gb = batch * (IN_BYTES_PER_SOLVE + OUT_BYTES_PER_SOLVE) / (kern_ms * 1e-3) / 1e9
@@ -638,10 +747,15 @@ def main():
                              f"kernel avg {kern_ms:.4f} ms per launch over the timed region (CUDA events, back-to-back launches overlap their ramp-up "
                              f"with the predecessor's tail through programmatic dependent launch); isolated launch {isolated_ms:.4f} ms; peak = {fp64_src}",
                      "isolated_launch_ms": isolated_ms, "isolated_frac": batch * FLOPS_PER_SOLVE / (isolated_ms * 1e-3) / 1e12 / fp64,
+                     "peak_burst": peak_burst,
+                     "sustained_frac": (sustained["achieved"] / sustained["peak"]["tflops"]) if sustained else None,
+                     "sustained": sustained,
                      "hbm": {"achieved": ach_gb, "peak": hbm, "unit": "GB/s", "frac": ach_gb / hbm, "peak_source": hbm_src,
                              "bytes_per_solve": IN_BYTES_PER_SOLVE + OUT_BYTES_PER_SOLVE}},
         "e2e": {"value": world * batch * args.steps / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": compact_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "host_link": box_probe,
+                "pcie_floor_ms": (1e3 * compact_bytes / (max(box_probe["h2d_23mb_gbs"], box_probe["h2d_23mb_4streams_gbs"]) * 1e9))
+                                 if "h2d_23mb_gbs" in box_probe else None,     # the H2D bytes at the best copy rate this box showed; D2H overlaps
                 "api": "hk_lqng_assemble_solve_batch: pinned host buffers holding the reference's provider constructor arguments "
                        "(LinearizedBicycle / LQRCheckpointReachAvoidCost), A,B,Q,q,R assembled on the GPU, u0 + status copied back",
                 "dense": {"value": world * batch * args.steps / e2e_dense_s, "unit": "solves/s", "h2d_bytes_per_step": h2d_bytes,
@@ -666,6 +780,10 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)                                      # the CPU baseline gets every core of the box
         line["cpu_baseline"] = cpu_baseline()
+        cb = line["cpu_baseline"]["value"]
+        line["e2e"]["ratio_vs_cpu_baseline"] = line["e2e"]["value"] / cb       # hk_lqng_assemble_solve_batch (the headline e2e)
+        line["e2e"]["dense"]["ratio_vs_cpu_baseline"] = line["e2e"]["dense"]["value"] / cb   # hk_lqng_solve_batch (dense records)
+        line["e2e"]["single_call_ratio_vs_cpu_single_thread"] = (1e6 / single_us) / line["cpu_baseline"]["single_thread_value"]   # hk_lqng_solve_one, what the C# shim calls per agent and step
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -137,6 +137,7 @@ PROTOTYPES = {
     "hk_last_error": (C.c_char_p, []),
     "hk_device_count": (C.c_int, []),
     "hk_kernel_launch_count": (C.c_longlong, []),
+    "hk_probe_fp64_peak": (C.c_int, [C.c_double, _dp, _dp, _dp]),
     "hk_lqng_solve_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
     "hk_lqng_solve_batch_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 11 + [C.c_void_p]),
     "hk_lqng_solve_one": (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),

@@ -57,6 +57,12 @@ const char* hk_last_error(void);                 /* thread-local */
 int         hk_device_count(void);
 long long   hk_kernel_launch_count(void);        /* kernels launched by this library so far (all threads); for benchmarks */
 
+/* Measurement aid (bench.py): the FP64 roofline denominator of THIS device, now.  Runs a DMMA m8n8k4 f64 stream (32 warps per SM) back to
+ * back for at least `seconds` and reports its flop rate, the SM clock it actually ran at (clock64 cycles / event time of the last launch;
+ * may be NULL) and the time it ran (may be NULL).  A short run gives the burst peak (boost clocks), a run of a second or more the
+ * sustained one (clocks settled under FP64 power). */
+int         hk_probe_fp64_peak(double seconds, double* tflops, double* sm_mhz_effective, double* seconds_run);
+
 /* ---- LQNG: batched feedback linear-quadratic Nash game ------------------------------------------------------ */
 /*
  * Replaces the body of KartLQR.solveFeedbackLQR (KartLQR.cs:17-128) for `batch` independent problems.
