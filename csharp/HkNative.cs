@@ -28,7 +28,7 @@ namespace KartGame.AI.Native
     [StructLayout(LayoutKind.Sequential)] public struct HkRaceKart
     {
         public double x, z, v, h; public float steer;
-        public int section, lane, laneChanges, illegalLaneChanges, sectionStep, active, pad_;
+        public int section, lane, laneChanges, illegalLaneChanges, sectionStep, active, team;
     }
     [StructLayout(LayoutKind.Sequential)] public unsafe struct HkRacePlan
     {

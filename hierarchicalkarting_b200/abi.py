@@ -74,7 +74,7 @@ class hk_game_state(C.Structure):
 class hk_race_kart(C.Structure):
     _fields_ = [("x", C.c_double), ("z", C.c_double), ("v", C.c_double), ("h", C.c_double), ("steer", C.c_float),
                 ("section", C.c_int32), ("lane", C.c_int32), ("laneChanges", C.c_int32), ("illegalLaneChanges", C.c_int32),
-                ("sectionStep", C.c_int32), ("active", C.c_int32), ("pad_", C.c_int32)]
+                ("sectionStep", C.c_int32), ("active", C.c_int32), ("team", C.c_int32)]
 
 
 class hk_race_plan(C.Structure):
@@ -82,6 +82,10 @@ class hk_race_plan(C.Structure):
                 ("oppLane", C.c_int8 * HK_MAX_SECTIONS), ("oppVel", C.c_float * HK_MAX_SECTIONS),
                 ("sectionTimes", C.c_int32 * HK_MAX_SECTIONS), ("lapStep", C.c_int32 * HK_MAX_LAPS),
                 ("avgLaneDiff", C.c_float), ("avgVelDiff", C.c_float)]
+
+
+class hk_race_belief(C.Structure):
+    _fields_ = [("lane", C.c_int8 * HK_MAX_SECTIONS), ("vel", C.c_float * HK_MAX_SECTIONS)]
 
 
 class hk_race_params(C.Structure):
@@ -105,11 +109,13 @@ class hk_race_mcts_params(C.Structure):
 # numpy views of the same layouts (for batched buffers)
 RACE_KART_DTYPE = np.dtype([("x", np.float64), ("z", np.float64), ("v", np.float64), ("h", np.float64), ("steer", np.float32),
                             ("section", np.int32), ("lane", np.int32), ("laneChanges", np.int32),
-                            ("illegalLaneChanges", np.int32), ("sectionStep", np.int32), ("active", np.int32), ("pad_", np.int32)])
+                            ("illegalLaneChanges", np.int32), ("sectionStep", np.int32), ("active", np.int32), ("team", np.int32)])
 RACE_PLAN_DTYPE = np.dtype([("lane", np.int8, (HK_MAX_SECTIONS,)), ("vel", np.float32, (HK_MAX_SECTIONS,)),
                             ("oppLane", np.int8, (HK_MAX_SECTIONS,)), ("oppVel", np.float32, (HK_MAX_SECTIONS,)),
                             ("sectionTimes", np.int32, (HK_MAX_SECTIONS,)), ("lapStep", np.int32, (HK_MAX_LAPS,)),
                             ("avgLaneDiff", np.float32), ("avgVelDiff", np.float32)])
+RACE_BELIEF_DTYPE = np.dtype([("lane", np.int8, (HK_MAX_SECTIONS,)), ("vel", np.float32, (HK_MAX_SECTIONS,))])
+assert RACE_BELIEF_DTYPE.itemsize == C.sizeof(hk_race_belief) == 320
 assert RACE_KART_DTYPE.itemsize == C.sizeof(hk_race_kart) == 64
 assert RACE_PLAN_DTYPE.itemsize == C.sizeof(hk_race_plan) == 936
 KART_STATE_DTYPE = np.dtype([(k, np.int32) for k in KART_STATE_FIELDS])
@@ -166,6 +172,10 @@ PROTOTYPES = {
     "hk_race_planner_destroy": (None, [C.c_void_p]),
     "hk_race_planner_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hk_race_run_planned": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, _dp, _lp]),
+    "hk_raceN_recipe": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_int, C.c_int] + [C.c_void_p] * 12),
+    "hk_raceN_planner_create": (C.c_int, [C.c_void_p, C.POINTER(hk_race_mcts_params), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "hk_raceN_run": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, _lp]),
     "hk_race_run_mcts": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, _dp, _lp]),
 }

@@ -48,6 +48,6 @@ int lqng_launch(int batch, int N, int horizon, int time_varying, const double* d
                 double* dtraj, int* dstatus, cudaStream_t stream);
 int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double* dx0, const double* dtarget,
                          const double* dtw, const double* dcw, const double* daw, const double* dotgt, const double* dotw,
-                         double* du0, int* dstatus, cudaStream_t stream, int scratch_slot);
+                         double* du0, int* dstatus, cudaStream_t stream, int scratch_slot, const int* dn_players = nullptr);
 
 }  // namespace hk

@@ -323,11 +323,24 @@ static int launch_generic(const LqngParams& p, cudaStream_t stream)
 __global__ void lqng_assemble_kernel(int batch, int N, double dt, const double* __restrict__ x0, const double* __restrict__ target,
                                      const double* __restrict__ tw, const double* __restrict__ cw, const double* __restrict__ aw,
                                      const double* __restrict__ otgt, const double* __restrict__ otw,
-                                     double* A, double* B, double* Q, double* q, double* R, double* xj)
+                                     double* A, double* B, double* Q, double* q, double* R, double* xj,
+                                     const int* __restrict__ n_players = nullptr)
 {
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= (long long)batch * N) return;
     const int n = 4 * N, K = N - 1;
+    if (n_players && (int)(id % N) >= n_players[id / N]) {
+        // decoupled dummy player of a game with fewer than N real players (hk_raceN_*: HierarchicalKartAgent.cs:709-725 keeps only the karts
+        // within 8 m): A = I, B = 0, Q = 0, q = 0, R = I, x = 0 — its gains, Z and eta stay exactly zero, the coupled system gets an
+        // identity block, the real players' results are those of the smaller game
+        for (int e = 0; e < 16; ++e) A[id * 16 + e] = (e % 5 == 0) ? 1.0 : 0.0;
+        for (int e = 0; e < 8; ++e) B[id * 8 + e] = 0.0;
+        R[id * 4 + 0] = 1.0; R[id * 4 + 1] = 0.0; R[id * 4 + 2] = 0.0; R[id * 4 + 3] = 1.0;
+        for (int e = 0; e < 4; ++e) xj[id * 4 + e] = 0.0;
+        for (int e = 0; e < n * n; ++e) Q[id * n * n + e] = 0.0;
+        for (int e = 0; e < n; ++e) q[id * n + e] = 0.0;
+        return;
+    }
     const double* x = x0 + id * 4;
     double* Ai = A + id * 16;
     for (int e = 0; e < 16; ++e) Ai[e] = (e % 5 == 0) ? 1.0 : 0.0;                 // SparseIdentity (:44)
@@ -454,7 +467,7 @@ __global__ void lqng_trig_kernel(long long n_players_total, const double* __rest
 
 int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double* dx0, const double* dtarget,
                          const double* dtw, const double* dcw, const double* daw, const double* dotgt, const double* dotw,
-                         double* du0, int* dstatus, cudaStream_t stream, int scratch_slot)
+                         double* du0, int* dstatus, cudaStream_t stream, int scratch_slot, const int* dn_players)
 {
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
@@ -462,7 +475,7 @@ int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double*
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(dx0) | reinterpret_cast<uintptr_t>(dtarget) | reinterpret_cast<uintptr_t>(dtw) |
                              reinterpret_cast<uintptr_t>(dcw) | reinterpret_cast<uintptr_t>(daw) | reinterpret_cast<uintptr_t>(dotgt) |
                              reinterpret_cast<uintptr_t>(dotw)) & 15) == 0;
-    if (N == 2 && fused && aligned16 && batch > 0) {
+    if (N == 2 && fused && aligned16 && batch > 0 && !dn_players) {
         // 2-kart game: no dense records in HBM at all — the solve kernel stages the 352-byte description by TMA and assembles
         // A, B, Q, q, R in shared memory (hk_lqng_mma2p.cuh, COMPACT)
         double* dcs = (double*)dscratch(c, scratch_slot, sizeof(double) * 4 * (size_t)batch);
@@ -482,7 +495,7 @@ int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double*
            *dR = dq + (size_t)batch * N * n, *dx = dR + (size_t)batch * N * 4;
     const long long threads = (long long)batch * N;
     count_launch(); lqng_assemble_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(batch, N, dt, dx0, dtarget, dtw, dcw, daw, dotgt, dotw,
-                                                                              dA, dB, dQ, dq, dR, dx);
+                                                                              dA, dB, dQ, dq, dR, dx, dn_players);
     HK_CUDA(cudaGetLastError());
     return lqng_launch(batch, N, horizon, 0, dA, dB, dQ, dq, dR, dx, du0, nullptr, nullptr, nullptr, dstatus, stream);
 }

@@ -443,7 +443,8 @@ __global__ void race_mcts_apply_kernel(const DevTrack* __restrict__ tr, int n_ag
 struct hk_race_planner {
     const hk_game* game = nullptr;
     hk_race_mcts_params mp{};
-    int n_agents = 0;
+    int n_agents = 0, karts_per_race = 2;
+    bool n_layout = false;                // made by hk_raceN_planner_create: `nearby` has HK_MAX_KARTS entries per agent
     hk_mcts_forest* forest = nullptr;     // mode 0: every agent's currentRoot
     char* dev = nullptr;                  // one allocation: roots | best | nearby | n_best | fresh | root_valid | cycles | status
     hk_game_state *roots = nullptr, *best = nullptr;
@@ -520,7 +521,7 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
         set_error("hk_race_run: invalid argument");
         return HK_ERR_INVALID_ARGUMENT;
     }
-    if (pl && (pl->n_agents != 2 * n_races || !p->highModeMcts || pl->mp.apply_delay >= p->planEvery)) {
+    if (pl && (pl->n_layout || pl->n_agents != 2 * n_races || !p->highModeMcts || pl->mp.apply_delay >= p->planEvery)) {
         set_error("hk_race_run_planned: planner made for %d races, highModeMcts must be 1, apply_delay < planEvery", pl->n_agents / 2);
         return HK_ERR_INVALID_ARGUMENT;
     }
@@ -644,4 +645,403 @@ extern "C" int hk_race_run_mcts(const hk_track* t, const hk_race_params* p, cons
     rc = race_run_impl(t, p, pl, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
     hk_race_planner_destroy(pl);
     return rc;
+}
+
+// =====================================================================================================================================
+// Races with up to 4 karts and teams (hk_raceN_*, include/hk_abi.h): what SolveLQR / planWithMCTS do when the environment has more
+// than two agents (HierarchicalKartAgent.cs:702-725, 930-1003, 1004-1190; 182-233).  One thread per agent id = K race + e.
+// =====================================================================================================================================
+namespace hk {
+
+struct PlanView { const int8_t* lane; const float* vel; };
+
+// One thread per agent: the whole N-player problem of that agent's game in the 4-player layout (dummy players zero, cw = 1).
+__global__ void raceN_recipe_kernel(const DevTrack* __restrict__ t, hk_race_params p, int K, int n_agents, const hk_race_kart* __restrict__ karts,
+                                    const hk_race_plan* __restrict__ plans, const hk_race_belief* __restrict__ beliefs, int* __restrict__ n_players,
+                                    int* __restrict__ players_out, double* x0, double* target, double* tw, double* cw, double* aw, double* otgt,
+                                    double* otw)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_agents) return;
+    const int e = id % K;
+    const hk_race_kart* rk = karts + (id - e);
+    const bool fixed = !p.highModeMcts;
+    // [this] + teamAgents + otherAgents in environment order (:702), kept if within 8 m of the ego when the environment has > 2 agents (:709-721)
+    int all[HK_MAX_KARTS], na = 0;
+    all[na++] = e;
+    for (int a = 0; a < K; ++a) if (a != e && rk[a].team == rk[e].team) all[na++] = a;
+    for (int a = 0; a < K; ++a) if (rk[a].team != rk[e].team) all[na++] = a;
+    int act[HK_MAX_KARTS], N = 0, nearby = -1;
+    if (K > 2) {
+        for (int i = 0; i < na; ++i) {
+            const hk_race_kart& k = rk[all[i]];
+            if (magnitude2((float)(k.x - rk[e].x), (float)(k.z - rk[e].z)) < 8) { nearby += 1; act[N++] = all[i]; }
+        }
+    } else {
+        for (int i = 0; i < na; ++i) act[N++] = all[i];
+    }
+    nearby = nearby > 1 ? nearby : 1;                                    // Math.Max(nearbyAgents, 1) :726
+    n_players[id] = N;
+    for (int i = 0; i < HK_MAX_KARTS; ++i) players_out[id * 4 + i] = i < N ? act[i] : -1;
+    unsigned in_game = 0;
+    for (int i = 0; i < N; ++i) in_game |= 1u << act[i];
+    const double max_speed = (double)p.topSpeed;
+    auto view = [&](int k) -> PlanView {                                 // own plan (k == this) or the ego's belief about kart k
+        if (k == e) return PlanView{plans[id].lane, plans[id].vel};
+        const hk_race_belief& b = beliefs[(size_t)id * K + k];
+        return PlanView{b.lane, b.vel};
+    };
+    auto plan_xzv = [&](int k, int idx, double& x, double& z, double& v) {
+        const PlanView pv = view(k);
+        const int ln = pv.lane[idx];
+        if (ln != 0) {
+            x = t->lane[idx][ln - 1][0]; z = t->lane[idx][ln - 1][1];
+            const double vv = (double)pv.vel[idx] + (p.highModeMcts ? p.velocityBucketSize * 2 : 0);
+            v = max_speed < vv ? max_speed : vv;
+        } else { x = t->trig[idx][0]; z = t->trig[idx][1]; v = max_speed; }
+    };
+    for (int i = 0; i < HK_MAX_KARTS; ++i) {
+        const size_t o4 = ((size_t)id * 4 + i) * 4;
+        double* xo = x0 + o4; double* tg = target + o4; double* w = tw + o4;
+        double* awi = aw + ((size_t)id * 4 + i) * 6; double* ogi = otgt + ((size_t)id * 4 + i) * 12; double* owi = otw + ((size_t)id * 4 + i) * 9;
+        for (int c = 0; c < 6; ++c) awi[c] = 0.0;
+        for (int c = 0; c < 12; ++c) ogi[c] = 0.0;
+        for (int c = 0; c < 9; ++c) owi[c] = 0.0;
+        if (i >= N) {                                                    // dummy player
+            for (int c = 0; c < 4; ++c) { xo[c] = 0.0; tg[c] = 0.0; w[c] = 0.0; }
+            cw[(size_t)id * 4 + i] = 1.0;
+            continue;
+        }
+        const int kI = act[i];
+        const hk_race_kart k = rk[kI];
+        xo[0] = k.x; xo[1] = k.z; xo[2] = k.v; xo[3] = k.h;              // :730-736
+        const int s = k.section + 1;                                     // :745
+        const int idx = s % t->n, idx2 = (s + 1) % t->n;
+        double lx, lz, vel, nlx, nlz, nvel;
+        plan_xzv(kI, idx, lx, lz, vel);
+        plan_xzv(kI, idx2, nlx, nlz, nvel);
+        const bool stopped = (float)k.v <= 5.0f;                         // :808
+        double tx = lx, tz = lz, tv = stopped ? 0.0 : vel;
+        const float d_t = magnitude2((float)(lx - k.x), (float)(lz - k.z));
+        const bool near = d_t <= (is_straight(t, k.section) ? 10.5f : 7.5f);           // :823
+        const float d_c = magnitude2((float)(t->trig[idx][0] - k.x), (float)(t->trig[idx][1] - k.z));
+        const bool follow = near && (d_c <= 4.0f);                       // :877-890, centre-line distance stand-in
+        const double h0 = k.h;
+        double th;
+        if (follow) {
+            const double f6w = (double)wrap2pi_f(mathf_atan2((float)(nlz - k.z), (float)(nlx - k.x)));
+            th = h0 - angle_difference(h0, f6w);                         // :887
+            tx = nlx; tz = nlz;
+            if (!stopped) tv = nvel;
+        } else {
+            const double f1w = (double)wrap2pi_f(mathf_atan2((float)(lz - k.z), (float)(lx - k.x)));
+            if (near) {
+                const double f2w = (double)wrap2pi_f(mathf_atan2((float)(nlz - lz), (float)(nlx - lx)));
+                double blend = f1w - angle_difference(f2w, f1w) * (double)0.4f;         // :896
+                if (blend < 0) blend += 2 * (double)3.14159274f;
+                th = h0 - angle_difference(h0, blend);                   // :898
+            } else {
+                th = h0 - angle_difference(h0, f1w);                     // :921
+            }
+        }
+        tg[0] = tx; tg[1] = tz; tg[2] = tv; tg[3] = th;
+        const double vmax1 = k.v > 1.0 ? k.v : 1.0;                      // own target weights :928-962
+        w[3] = N > 2 ? (fixed ? 2.5 : 3.5) * nearby : (fixed ? 1.9 : 3.5);
+        const double wxz = stopped ? nearby * 0.3 * 3.1 : nearby * 0.3 * 3.1 / vmax1;
+        w[0] = wxz; w[1] = wxz; w[2] = stopped ? (double)(nearby * -2) : nearby * 5e-4;
+        cw[(size_t)id * 4 + i] = N > 2 ? (fixed ? 0.135 : 0.25) : 0.115;               // :1192-1196
+        float mult;                                                      // :977-1003
+        if (K > 2 && N > 2) mult = kI == e ? (fixed ? 0.55f : 1.0f) / nearby : 1.7f / nearby;
+        else mult = kI == e ? (fixed ? 0.45f : 1.0f) : 1.3f;
+        int slot = 0, nearby_opponents = 0;
+        for (int pass = 0; pass < 2; ++pass) {                           // player k's otherAgents (:1004-1096), then its teamAgents (:1099-1190)
+            for (int o = 0; o < K; ++o) {
+                const bool mate = rk[o].team == k.team;
+                if (o == kI ? true : (pass == 0 ? mate : !mate)) continue;
+                if (!((in_game >> o) & 1u)) continue;                    // !actualAllPlayers.Contains(o)
+                const hk_race_kart ko = rk[o];
+                const float dist = magnitude2((float)(ko.x - k.x), (float)(ko.z - k.z));
+                const bool off = dist > 8 || !ko.active;
+                const float m_eff = pass == 0 ? mult : mult / 2.0f;       // multiplier2 :1113
+                const float w32 = 1.0f / ((float)pow((double)dist, (double)1.5f) * m_eff);
+                const double wa = off ? 0.0 : (double)w32;
+                awi[slot * 2] = wa; awi[slot * 2 + 1] = wa;
+                if (pass == 0 && !off) nearby_opponents += 1;
+                double ox, oz, ov;
+                plan_xzv(o, (ko.section + 1) % t->n, ox, oz, ov);
+                ogi[slot * 4] = ox; ogi[slot * 4 + 1] = oz; ogi[slot * 4 + 2] = pass == 0 ? ov : max_speed; ogi[slot * 4 + 3] = 0.0;
+                double oxz = 0.0, ovw = 0.0;
+                if (pass == 0) {
+                    if (!off) {
+                        if (N > 2) { oxz = (fixed ? 0.1 : 0.2) / (vmax1 * nearby); ovw = 0.08 / nearby; }   // :1083-1085
+                        else { oxz = (fixed ? 0.1 : 0.2) / vmax1; ovw = 0.08; }                            // :1089-1091
+                    }
+                } else if (!off && nearby_opponents >= 1) {
+                    if (N > 2) oxz = -(fixed ? 0.0 : 3e-5) / (vmax1 * nearby);                             // :1178-1180
+                    else oxz = -(fixed ? 1e-4 : 2e-4) / vmax1;                                             // :1184-1186
+                }
+                owi[slot * 3] = oxz; owi[slot * 3 + 1] = oxz; owi[slot * 3 + 2] = ovw;
+                ++slot;
+            }
+        }
+    }
+}
+
+// planWithMCTS's root state (:180-245) for K-kart races: every agent of the race within sectionWindow sections of the ego, in
+// environment order, placed at the furthest one's section; team = getTeamID.  nearby [id][HK_MAX_KARTS].
+__global__ void raceN_mcts_root_kernel(const DevTrack* __restrict__ tr, hk_race_params p, int K, int section_window, int time_precision, int n_agents,
+                                       const hk_race_kart* __restrict__ karts, const hk_race_plan* __restrict__ plans,
+                                       hk_game_state* __restrict__ roots, int* __restrict__ nearby, const int* __restrict__ root_valid,
+                                       const int* __restrict__ cycles, int reuse_cycles, int* __restrict__ fresh, bool build_all)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_agents) return;
+    int f = 1;
+    if (!karts[id].active) f = -1;
+    else if (reuse_cycles > 0 && root_valid[id]) f = cycles[id] < reuse_cycles ? 0 : -1;
+    fresh[id] = f;
+    if (f != 1 && !build_all) return;
+    const int e = id % K, r0 = id - e, L = tr->n;
+    const int me_sec = karts[id].section;
+    int initial = me_sec, furthest = e, n = 0, near[HK_MAX_KARTS];
+    for (int a = 0; a < K; ++a)                                          // :182-193
+        if (abs(karts[r0 + a].section - me_sec) < section_window) {
+            near[n++] = a;
+            if (karts[r0 + a].section > initial) initial = karts[r0 + a].section;
+            if (initial == karts[r0 + a].section) furthest = a;
+        }
+    hk_game_state st;
+    st.n_karts = n; st.initialSection = initial; st.lastCompletedSection = initial; st.finalSection = initial + p.treeSearchDepth;
+    for (int slot = 0; slot < HK_MAX_KARTS; ++slot) {
+        hk_kart_state ks = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (slot < n) {
+            const int a = near[slot];
+            const hk_race_kart& k = karts[r0 + a];
+            int t_at = 0;
+            if (k.section != initial) {
+                const int d = plans[r0 + a].sectionTimes[k.section % L] - plans[r0 + furthest].sectionTimes[k.section % L];
+                t_at = (int)(((float)d * 0.02f) * (float)time_precision);
+            }
+            const float wear = (4.0f - k.steer) / 3.0f;
+            ks.player = 0; ks.team = k.team; ks.section = initial; ks.timeAtSection = t_at; ks.min_velocity = 0;
+            ks.max_velocity = min(p.velocityBucketSize, (int)p.topSpeed); ks.lane = k.lane; ks.tireAge = (int)(wear * 10000.0f);
+            ks.laneChanges = k.laneChanges; ks.infeasible = 0;
+            nearby[id * HK_MAX_KARTS + slot] = a;
+        } else nearby[id * HK_MAX_KARTS + slot] = -1;
+        st.karts[slot] = ks;
+    }
+    roots[id] = st;
+}
+
+// the waypoint hand-off (:366-402) for K-kart races: own lanes / velocities, and the belief tables about every other kart of the game
+__global__ void raceN_mcts_apply_kernel(const DevTrack* __restrict__ tr, int K, int n_agents, const hk_race_kart* __restrict__ karts,
+                                        const int* __restrict__ nearby, const hk_game_state* __restrict__ best, const int* __restrict__ n_best,
+                                        hk_race_plan* __restrict__ plans, hk_race_belief* __restrict__ beliefs, const int* __restrict__ fresh,
+                                        int* __restrict__ root_valid, int* __restrict__ cycles)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_agents) return;
+    if (fresh[id] < 0) return;
+    root_valid[id] = 1;
+    cycles[id] = fresh[id] ? 1 : cycles[id] + 1;
+    const int e = id % K, L = tr->n, sec = karts[id].section, bound = sec + (sec == 0 ? 0 : 1);
+    hk_race_plan& pl = plans[id];
+    for (int k = 0; k < n_best[id]; ++k) {
+        const hk_game_state& gs = best[(size_t)id * HK_MCTS_MAX_SEQ + k];
+        for (int slot = 0; slot < gs.n_karts && slot < HK_MAX_KARTS; ++slot) {
+            const hk_kart_state& ks = gs.karts[slot];
+            const int who = nearby[id * HK_MAX_KARTS + slot], key = ks.section % L;
+            if (who == e) {
+                if (ks.section > bound) { pl.lane[key] = (int8_t)ks.lane; pl.vel[key] = (float)ks.max_velocity; }
+            } else if (who >= 0) {
+                hk_race_belief& b = beliefs[(size_t)id * K + who];
+                b.lane[key] = (int8_t)ks.lane; b.vel[key] = (float)ks.max_velocity;
+            }
+        }
+    }
+}
+
+}  // namespace hk
+
+static int raceN_check(const hk_track* t, const hk_race_params* p, int K, int n_races, const char* who)
+{
+    int rc = check_track(t, p, who);
+    if (rc) return rc;
+    if (K < 2 || K > HK_MAX_KARTS || n_races < 0) { set_error("%s: karts_per_race must be 2..%d", who, HK_MAX_KARTS); return HK_ERR_INVALID_ARGUMENT; }
+    return HK_OK;
+}
+
+extern "C" int hk_raceN_recipe(const hk_track* t, const hk_race_params* p, int K, int n_races, const hk_race_kart* karts, const hk_race_plan* plans,
+                               const hk_race_belief* beliefs, int32_t* n_players, int32_t* players, double* x0, double* target, double* tw,
+                               double* cw, double* aw, double* otgt, double* otw)
+{
+    int rc = raceN_check(t, p, K, n_races, "hk_raceN_recipe");
+    if (rc) return rc;
+    if (n_races > 0 && (!karts || !plans || !beliefs || !n_players || !players || !x0 || !target || !tw || !cw || !aw || !otgt || !otw)) {
+        set_error("hk_raceN_recipe: invalid argument");
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    if (n_races == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const size_t nb = (size_t)K * n_races;
+    const size_t per[7] = {16, 16, 16, 4, 24, 48, 36};
+    size_t out_elems = 0;
+    for (size_t v : per) out_elems += v;
+    const size_t in_bytes = nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan)) + nb * K * sizeof(hk_race_belief);
+    char* d = (char*)dscratch(c, 8, in_bytes + nb * (5 * sizeof(int) + out_elems * sizeof(double)) + 256);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    hk_race_kart* dk = (hk_race_kart*)d;
+    hk_race_plan* dp = (hk_race_plan*)(dk + nb);
+    hk_race_belief* db = (hk_race_belief*)(dp + nb);
+    double* o = (double*)(((uintptr_t)(db + nb * K) + 15) & ~(uintptr_t)15);
+    double* dout[7];
+    for (int i = 0; i < 7; ++i) { dout[i] = o; o += nb * per[i]; }
+    int* dn = (int*)o; int* dpl = dn + nb;
+    cudaStream_t s = c->stream;
+    HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(db, beliefs, nb * K * sizeof(hk_race_belief), cudaMemcpyHostToDevice, s));
+    count_launch();
+    raceN_recipe_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(t->dev, *p, K, (int)nb, dk, dp, db, dn, dpl, dout[0], dout[1], dout[2], dout[3],
+                                                                   dout[4], dout[5], dout[6]);
+    HK_CUDA_DRAIN(cudaGetLastError());
+    double* hout[7] = {x0, target, tw, cw, aw, otgt, otw};
+    for (int i = 0; i < 7; ++i) HK_CUDA_DRAIN(cudaMemcpyAsync(hout[i], dout[i], nb * per[i] * sizeof(double), cudaMemcpyDeviceToHost, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(n_players, dn, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(players, dpl, nb * 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    HK_CUDA_DRAIN(cudaStreamSynchronize(s));
+    return HK_OK;
+}
+
+extern "C" int hk_raceN_planner_create(const hk_game* game, const hk_race_mcts_params* mp, int K, int n_races, hk_race_planner** out)
+{
+    if (!game || !mp || !out || n_races < 1 || K < 2 || K > HK_MAX_KARTS || mp->iterations < 0 || mp->first_iterations < 0 || mp->reuse_cycles < 0 ||
+        mp->apply_delay < 0 || (mp->mode != 0 && mp->mode != 1) || (mp->mode == 1 && mp->rollouts_per_leaf < 1)) {
+        set_error("hk_raceN_planner_create: invalid argument");
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    if (game_karts_of(game) < K) { set_error("hk_raceN_planner_create: the game has fewer karts than a race"); return HK_ERR_INVALID_ARGUMENT; }
+    int rc = ensure_device();
+    if (rc != HK_OK) return rc;
+    hk_race_planner* pl = new hk_race_planner();
+    pl->game = game; pl->mp = *mp; pl->n_agents = K * n_races; pl->karts_per_race = K; pl->n_layout = true;
+    const size_t nb = (size_t)pl->n_agents;
+    const int depth = game_params_of(game).treeSearchDepth;
+    if (mp->mode == 0) {
+        const long long big = mp->first_iterations > mp->iterations ? mp->first_iterations : mp->iterations;
+        const long long life = big + (long long)mp->reuse_cycles * mp->iterations;
+        const long long max_nodes = mp->max_tree_nodes > 0 ? mp->max_tree_nodes : 1 + life * K * depth;
+        if (max_nodes > (1ll << 30) || K * depth > HK_MAX_PLIES) { delete pl; set_error("hk_raceN_planner_create: trees too large"); return HK_ERR_INVALID_ARGUMENT; }
+        rc = hk_mcts_forest_create(game, pl->n_agents, (int)max_nodes, &pl->forest);
+        if (rc) { delete pl; return rc; }
+    }
+    const size_t sz[8] = {sizeof(hk_game_state) * nb, sizeof(hk_game_state) * nb * HK_MCTS_MAX_SEQ, 4 * nb * HK_MAX_KARTS, 4 * nb, 4 * nb, 4 * nb, 4 * nb, 4 * nb};
+    size_t off[9]; off[0] = 0;
+    for (int i = 0; i < 8; ++i) off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t)255);
+    cudaError_t e = cudaMalloc(&pl->dev, off[8]);
+    if (e == cudaSuccess) e = cudaMemset(pl->dev, 0, off[8]);
+    if (e != cudaSuccess) { set_error("hk_raceN_planner_create: %s", cudaGetErrorString(e)); cudaGetLastError(); hk_race_planner_destroy(pl); return HK_ERR_OUT_OF_MEMORY; }
+    pl->roots = (hk_game_state*)pl->dev; pl->best = (hk_game_state*)(pl->dev + off[1]); pl->nearby = (int*)(pl->dev + off[2]);
+    pl->n_best = (int*)(pl->dev + off[3]); pl->fresh = (int*)(pl->dev + off[4]); pl->root_valid = (int*)(pl->dev + off[5]);
+    pl->cycles = (int*)(pl->dev + off[6]); pl->status = (int*)(pl->dev + off[7]);
+    *out = pl;
+    return HK_OK;
+}
+
+extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_planner* pl, int K, int lqr_every, int n_races, int first_step,
+                            int n_steps, hk_race_kart* karts, hk_race_plan* plans, hk_race_belief* beliefs, double* u_hold,
+                            int64_t* lqng_status_nonzero)
+{
+    int rc = raceN_check(t, p, K, n_races, "hk_raceN_run");
+    if (rc) return rc;
+    if (n_steps < 0 || first_step < 0 || lqr_every < 1 || (n_races > 0 && (!karts || !plans || !beliefs || !u_hold))) { set_error("hk_raceN_run: invalid argument"); return HK_ERR_INVALID_ARGUMENT; }
+    if (pl && (!pl->n_layout || pl->n_agents != K * n_races || pl->karts_per_race != K || !p->highModeMcts || pl->mp.apply_delay >= p->planEvery)) {
+        set_error("hk_raceN_run: planner made for another batch, highModeMcts must be 1, apply_delay < planEvery");
+        return HK_ERR_INVALID_ARGUMENT;
+    }
+    if (lqng_status_nonzero) *lqng_status_nonzero = 0;
+    if (n_races == 0 || n_steps == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    const size_t nb = (size_t)K * n_races;
+    const size_t per[7] = {16, 16, 16, 4, 24, 48, 36};
+    size_t out_elems = 8;                                              // + the u0 record of the 4-player frame
+    for (size_t v : per) out_elems += v;
+    const size_t in_bytes = nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan)) + nb * K * sizeof(hk_race_belief);
+    char* d = (char*)dscratch(c, 8, in_bytes + nb * (6 * sizeof(int) + out_elems * sizeof(double)) + 512);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    hk_race_kart* dk = (hk_race_kart*)d;
+    hk_race_plan* dp = (hk_race_plan*)(dk + nb);
+    hk_race_belief* db = (hk_race_belief*)(dp + nb);
+    double* o = (double*)(((uintptr_t)(db + nb * K) + 15) & ~(uintptr_t)15);
+    double* dout[7];
+    for (int i = 0; i < 7; ++i) { dout[i] = o; o += nb * per[i]; }
+    double* du = o; o += nb * 8;
+    unsigned long long* dcount = (unsigned long long*)o;
+    int* dn = (int*)(dcount + 2); int* dpl = dn + nb; int* dst = dpl + nb * 4;
+    cudaStream_t s = c->stream;
+    HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(db, beliefs, nb * K * sizeof(hk_race_belief), cudaMemcpyHostToDevice, s));
+    HK_CUDA_DRAIN(cudaMemsetAsync(du, 0, nb * 8 * sizeof(double), s));
+    HK_CUDA_DRAIN(cudaMemcpy2DAsync(du, 8 * sizeof(double), u_hold, 2 * sizeof(double), 2 * sizeof(double), nb, cudaMemcpyHostToDevice, s));
+    HK_CUDA_DRAIN(cudaMemsetAsync(dcount, 0, 2 * sizeof(unsigned long long), s));
+    const unsigned blocks = (unsigned)((nb + 127) / 128);
+    int searches = 0;
+    for (int step = first_step; step < first_step + n_steps; ++step) {
+        const bool replan = step > 0 && step % p->planEvery == 0;
+        if (replan && !p->highModeMcts) {
+            count_launch();
+            race_plan_fixed_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp);
+        } else if (pl) {
+            const hk_game_params& gp = game_params_of(pl->game);
+            const hk_race_mcts_params& mp = pl->mp;
+            const bool begin = step == 0 && mp.first_iterations > 0;
+            if ((replan && step < gp.maxEpisodeSteps) || begin) {
+                const int budget = begin ? mp.first_iterations : mp.iterations;
+                const uint64_t seed = mp.seed + (uint64_t)(step / p->planEvery) * (uint64_t)nb;
+                count_launch();
+                raceN_mcts_root_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, K, gp.sectionWindow, gp.timePrecision, (int)nb, dk, dp, pl->roots, pl->nearby,
+                                                             pl->root_valid, pl->cycles, mp.mode == 0 ? mp.reuse_cycles : 0, pl->fresh, mp.mode == 1);
+                HK_CUDA_DRAIN(cudaGetLastError());
+                if (mp.mode == 0) rc = mcts_seq_search_device(pl->forest, pl->roots, pl->fresh, budget, seed, pl->best, pl->n_best, nullptr, pl->status, s, false);
+                else rc = mcts_search_device(pl->game, pl->roots, (int)nb, budget, mp.rollouts_per_leaf, seed, pl->best, pl->n_best, nullptr, nullptr, nullptr, pl->status, c, s);
+                if (rc) { drain(c); return rc; }
+                pl->pending_step = step + mp.apply_delay;
+                ++searches;
+            }
+            if (pl->pending_step == step) {
+                count_launch();
+                raceN_mcts_apply_kernel<<<blocks, 128, 0, s>>>(t->dev, K, (int)nb, dk, pl->nearby, pl->best, pl->n_best, dp, db, pl->fresh, pl->root_valid, pl->cycles);
+                HK_CUDA_DRAIN(cudaGetLastError());
+                pl->pending_step = -1;
+            }
+        }
+        const bool solve = step % lqr_every == 0;                        // 50 Hz with 2 agents, every 4th step with more (:317)
+        if (solve) {
+            count_launch();
+            raceN_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, K, (int)nb, dk, dp, db, dn, dpl, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6]);
+            HK_CUDA_DRAIN(cudaGetLastError());
+            rc = lqng_assemble_launch((int)nb, 4, p->horizon, p->dt, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6], du, dst, s, 9, dn);
+            if (rc) { drain(c); return rc; }
+        }
+        count_launch();
+        race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 8, solve ? dst : nullptr, dcount, dk, dp, pl ? pl->root_valid : nullptr,
+                                                pl ? pl->cycles : nullptr);
+        HK_CUDA_DRAIN(cudaGetLastError());
+    }
+    HK_CUDA_DRAIN(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(plans, dp, nb * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, s));
+    HK_CUDA_DRAIN(cudaMemcpyAsync(beliefs, db, nb * K * sizeof(hk_race_belief), cudaMemcpyDeviceToHost, s));
+    HK_CUDA_DRAIN(cudaMemcpy2DAsync(u_hold, 2 * sizeof(double), du, 8 * sizeof(double), 2 * sizeof(double), nb, cudaMemcpyDeviceToHost, s));
+    unsigned long long count = 0;
+    HK_CUDA_DRAIN(cudaMemcpyAsync(&count, dcount, sizeof(count), cudaMemcpyDeviceToHost, s));
+    std::vector<int> mst;
+    if (pl && searches) { mst.resize(nb); HK_CUDA_DRAIN(cudaMemcpyAsync(mst.data(), pl->status, 4 * nb, cudaMemcpyDeviceToHost, s)); }
+    HK_CUDA_DRAIN(cudaStreamSynchronize(s));
+    if (lqng_status_nonzero) *lqng_status_nonzero = (int64_t)count;
+    for (size_t a = 0; a < mst.size(); ++a)
+        if (mst[a] == 1) { set_error("hk_raceN_run: upNext() == -1 reached in the tree of agent %zu (KartDiscreteGame.cs:326 would throw)", a); return HK_ERR_NO_UPNEXT; }
+    return HK_OK;
 }

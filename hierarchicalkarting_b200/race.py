@@ -137,18 +137,81 @@ class Races:
         return u, bad.value
 
 
+def start_grid_n(track: Track, n_races: int, karts_per_race: int, seed: int, teams=None, wear: float = 0.25, jitter: float = 0.3):
+    """Race / Experiment-mode start of the Duos scenes (RacingEnvController.cs:526-527: lanes {2,3,2,3} at sections {0,0,1,1}, tyre wear
+    0.25) for races of `karts_per_race` karts; teams default to [0, 0, 1, 1][:K].  Returns (karts [n_races][K], plans [n_races][K],
+    beliefs [n_races][K][K], u_hold [n_races][K][2])."""
+    K = karts_per_race
+    teams = [0, 0, 1, 1][:K] if teams is None else list(teams)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    karts = np.zeros((n_races, K), dtype=abi.RACE_KART_DTYPE)
+    plans = np.zeros((n_races, K), dtype=abi.RACE_PLAN_DTYPE)
+    beliefs = np.zeros((n_races, K, K), dtype=abi.RACE_BELIEF_DTYPE)
+    lanes_xy, head = track.lane_table(), track.heading_table()
+    for e in range(K):
+        lane, sec = (2, 3, 2, 3)[e], (0, 0, 1, 1)[e]
+        p0 = lanes_xy[sec, lane - 1]
+        fwd = np.array([np.cos(head[sec]), np.sin(head[sec])])
+        along = rng.uniform(0.5, 2.5, size=n_races)
+        karts["x"][:, e] = p0[0] + fwd[0] * along + rng.uniform(-jitter, jitter, size=n_races)
+        karts["z"][:, e] = p0[1] + fwd[1] * along + rng.uniform(-jitter, jitter, size=n_races)
+        karts["v"][:, e] = rng.uniform(0.0, 3.0, size=n_races)
+        karts["h"][:, e] = np.mod(head[sec] + rng.normal(0.0, 0.05, size=n_races), 2 * np.pi)
+        karts["lane"][:, e] = lane
+        karts["section"][:, e] = sec
+        karts["team"][:, e] = teams[e]
+    karts["steer"] = steer_for_wear(wear)
+    karts["active"] = 1
+    return karts, plans, beliefs, np.zeros((n_races, K, 2))
+
+
+class RacesN(Races):
+    """Races of K = 2..4 karts with teams (hk_raceN_*): SolveLQR's more-than-two-agents branches (8 m nearby filter, N in 1..4 players per
+    problem, teammates, private / joint ordering), the solve every `lqr_every`-th step, MCTS with the game's team scoring."""
+
+    def __init__(self, track: Track, params: abi.hk_race_params | None = None, karts_per_race: int = 4, lqr_every: int | None = None):
+        super().__init__(track, params)
+        self.K = karts_per_race
+        self.lqr_every = lqr_every if lqr_every is not None else (4 if karts_per_race > 2 else 1)     # HierarchicalKartAgent.cs:317
+
+    def recipe_n(self, karts: np.ndarray, plans: np.ndarray, beliefs: np.ndarray) -> dict:
+        n = karts.size
+        out = dict(n_players=np.zeros(n, np.int32), players=np.zeros((n, 4), np.int32), x0=np.zeros((n, 4, 4)), target=np.zeros((n, 4, 4)),
+                   tw=np.zeros((n, 4, 4)), cw=np.zeros((n, 4)), aw=np.zeros((n, 4, 3, 2)), otgt=np.zeros((n, 4, 3, 4)), otw=np.zeros((n, 4, 3, 3)))
+        abi.check(abi.load_library().hk_raceN_recipe(self._h, C.byref(self.params), self.K, karts.shape[0], abi.vptr(karts), abi.vptr(plans),
+                                                     abi.vptr(beliefs), abi.vptr(out["n_players"]), abi.vptr(out["players"]),
+                                                     *(abi.vptr(out[k]) for k in ("x0", "target", "tw", "cw", "aw", "otgt", "otw"))))
+        out["dt"] = self.params.dt
+        return out
+
+    def planner(self, game, n_races: int, iterations: int, seed: int = 0, **kw) -> "Planner":
+        return Planner(game, n_races, iterations, seed, karts_per_race=self.K, n_api=True, **kw)
+
+    def run_n(self, karts, plans, beliefs, u_hold, first_step: int, n_steps: int, planner: "Planner | None" = None):
+        bad = C.c_int64(0)
+        abi.check(abi.load_library().hk_raceN_run(self._h, C.byref(self.params), planner._h if planner is not None else None, self.K, self.lqr_every,
+                                                  karts.shape[0], first_step, n_steps, abi.vptr(karts), abi.vptr(plans), abi.vptr(beliefs),
+                                                  abi.vptr(u_hold), C.byref(bad)))
+        return bad.value
+
+
 class Planner:
     """hk_race_planner: the MCTS high level of a batch of races — per agent the device-resident tree (currentRoot), CyclesRootProcessed
     and the pending result of a search (HierarchicalKartAgent.cs:172-283, 331-353, 660-661)."""
 
     def __init__(self, game, n_races: int, iterations: int, seed: int = 0, mode: int = 0, first_iterations: int = 0,
-                 rollouts_per_leaf: int = 0, reuse_cycles: int = 3, apply_delay: int = 0, max_tree_nodes: int = 0):
+                 rollouts_per_leaf: int = 0, reuse_cycles: int = 3, apply_delay: int = 0, max_tree_nodes: int = 0, karts_per_race: int = 2,
+                 n_api: bool = False):
         self.params = abi.hk_race_mcts_params(mode=mode, iterations=iterations, first_iterations=first_iterations,
                                               rollouts_per_leaf=rollouts_per_leaf, reuse_cycles=reuse_cycles, apply_delay=apply_delay, seed=seed,
                                               max_tree_nodes=max_tree_nodes)
-        self.game, self.n_races = game, n_races
+        self.game, self.n_races, self.K = game, n_races, karts_per_race
         self._h = C.c_void_p()
-        abi.check(abi.load_library().hk_race_planner_create(game._h, C.byref(self.params), n_races, C.byref(self._h)))
+        if not n_api:
+            assert karts_per_race == 2
+            abi.check(abi.load_library().hk_race_planner_create(game._h, C.byref(self.params), n_races, C.byref(self._h)))
+        else:
+            abi.check(abi.load_library().hk_raceN_planner_create(game._h, C.byref(self.params), karts_per_race, n_races, C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -162,8 +225,8 @@ class Planner:
             pass
 
     def state(self):
-        """(root_valid, cycles, tree_status), each [n_races][2]"""
-        rv, cy, ts = (np.zeros((self.n_races, 2), np.int32) for _ in range(3))
+        """(root_valid, cycles, tree_status), each [n_races][karts_per_race]"""
+        rv, cy, ts = (np.zeros((self.n_races, self.K), np.int32) for _ in range(3))
         abi.check(abi.load_library().hk_race_planner_state(self._h, abi.vptr(rv), abi.vptr(cy), abi.vptr(ts)))
         return rv, cy, ts
 

@@ -298,7 +298,7 @@ typedef struct hk_race_kart {    /* one kart of one race; 64 bytes */
     int32_t illegalLaneChanges;  /* m_IllegalLaneChanges */
     int32_t sectionStep;         /* sectionTimes[m_SectionIndex]: episodeSteps at the last crossing (:650) */
     int32_t active;              /* 0 once the kart has reached goalSection (:651-654) */
-    int32_t pad_;
+    int32_t team;                /* RacingEnvController.getTeamID (:786-796); ignored by the 2-kart entry points (every kart its own team) */
 } hk_race_kart;
 
 #define HK_MAX_LAPS 8
@@ -402,6 +402,37 @@ int  hk_race_run_planned(const hk_track* t, const hk_race_params* p, hk_race_pla
 int hk_race_run_mcts(const hk_track* t, const hk_race_params* p, const hk_game* game, int iterations, int rollouts_per_leaf,
                      uint64_t seed, int n_races, int first_step, int n_steps, hk_race_kart* karts, hk_race_plan* plans,
                      double* u_last, int64_t* lqng_status_nonzero);
+
+/* ---- races with up to 4 karts and teams (the Duos scenes: 4 agents, 2 teams) ----------------------------------------------------------
+ * The same closed loop for n_races races of karts_per_race (K = 2..4) karts each, agent id = K race + e, with everything SolveLQR does when
+ * the environment has more than two agents (HierarchicalKartAgent.cs:702-725, 930-1003, 1004-1190):
+ *   - players of agent e's game: [e] + its teammates + its opponents (environment order), of which only those within 8 m of e take part
+ *     (float32 magnitude, :709-725) => N in 1..4 per problem and step; nearbyAgents = max(N - 1, 1) scales the weights (:932-962,
+ *     :985-987, :1083-1085); teammates use multiplier / 2 (:1113) and the teammate-target weights (:1168-1187);
+ *   - every player's cost is built in ITS private order [its opponents..., its teammates...] but multiplies the joint state ordered for
+ *     the ego (quirk Q3 of SURVEY.md A.3) — reproduced, not fixed;
+ *   - the solve runs every lqr_every-th step (4 when the environment has more than 2 agents, :317) and the controls are held in between;
+ *   - a problem with N < 4 players is solved in the 4-player frame with decoupled dummy players (A = I, B = 0, Q = 0, R = I): their
+ *     gains stay exactly zero and the real players' results are those of the N-player game.
+ * beliefs [n_races][K][K]: agent e's opponentUpcomingLanes / opponentUpcomingVelocities about kart o (entry [e][e] unused).
+ */
+typedef struct hk_race_belief { int8_t lane[HK_MAX_SECTIONS]; float vel[HK_MAX_SECTIONS]; } hk_race_belief;
+
+/* Problem recipe only.  Outputs in the 4-player layout of hk_lqng_assemble_solve_batch (N = 4): x0 [n][4][4], target [n][4][4],
+ * tw [n][4][4], cw [n][4], aw [n][4][3][2], otgt [n][4][3][4], otw [n][4][3][3] with n = K n_races, dummy players zero (cw 1);
+ * n_players [n] and players [n][4] (race-local kart of joint slot i, -1 = dummy). */
+int hk_raceN_recipe(const hk_track* t, const hk_race_params* p, int karts_per_race, int n_races, const hk_race_kart* karts,
+                    const hk_race_plan* plans, const hk_race_belief* beliefs, int32_t* n_players, int32_t* players,
+                    double* x0, double* target, double* tw, double* cw, double* aw, double* otgt, double* otw);
+
+/* The loop.  u_hold [n_races][K][2] carries the controls held between two solves across calls (in/out; zeros at the start).  planner may
+ * be NULL (Fixed high level / the caller plans); with a planner made by hk_raceN_planner_create the MCTS high level runs on the device as
+ * in hk_race_run_planned, with the game's team scoring (KartDiscreteGame.cs:271-310) deciding: root states hold every agent within
+ * sectionWindow sections (HierarchicalKartAgent.cs:182-233) with its team, the hand-off also fills the beliefs about the other karts. */
+int hk_raceN_planner_create(const hk_game* game, const hk_race_mcts_params* mp, int karts_per_race, int n_races, hk_race_planner** out);
+int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_planner* planner, int karts_per_race, int lqr_every, int n_races,
+                 int first_step, int n_steps, hk_race_kart* karts, hk_race_plan* plans, hk_race_belief* beliefs, double* u_hold,
+                 int64_t* lqng_status_nonzero);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,9 @@ environment (2-kart head-to-head scenes and the 4-kart Duos scenes):
   avoid / opponent-target / teammate-target weights in player k's PRIVATE order [its otherAgents..., its teamAgents...]  :964-1190
   control weight          :1192-1196
 Unity's Mathf.X(float) is (float)Math.X((double)x); Vector3.magnitude is (float)Math.Sqrt((double)(x*x + y*y + z*z)) on float32 components.
+Unity subtracts float32 positions; the kinematic stand-in keeps kart positions in double, so a position difference is formed in double
+and rounded to float32 once — identical to Unity's float32 subtraction whenever both positions are float32 values (the difference of two
+float32 numbers is exact in double).
 otherAgents / teamAgents are serialized scene arrays; they are taken in environment order (opponents = other teams, mates = same team)."""
 import math
 
@@ -52,7 +55,7 @@ def solve_lqr_recipe(track, karts, ego, own_lane, own_vel, belief_lane, belief_v
     fixed = not high_mode_mcts
 
     def dist(a, b):                                                     # (a.position - b.position).magnitude, y equal
-        return _mag(F(karts[a]["x"]) - F(karts[b]["x"]), F(karts[a]["z"]) - F(karts[b]["z"]))
+        return _mag(F(karts[a]["x"] - karts[b]["x"]), F(karts[a]["z"] - karts[b]["z"]))
     nearby = -1
     if n_env > 2:                                                       # :709-721
         actual = []
@@ -91,15 +94,15 @@ def solve_lqr_recipe(track, karts, ego, own_lane, own_vel, belief_lane, belief_v
         cx, cz = float(track["trig"][idx][0]), float(track["trig"][idx][1])
         stopped = F(v) <= F(5.0)                                          # :808
         tx, tz, tv = lx, lz, (0.0 if stopped else vel)
-        th_tgt = _atan2f(F(lz) - F(z), F(lx) - F(x))                      # :819
+        th_tgt = _atan2f(F(lz - z), F(lx - x))                      # :819
         if th_tgt < 0:
             th_tgt = F(th_tgt + F(2) * PI_F)
-        near = _mag(F(lx) - F(x), F(lz) - F(z)) <= (F(10.5) if track["straight"][kk["section"] % L] else F(7.5))   # :821
+        near = _mag(F(lx - x), F(lz - z)) <= (F(10.5) if track["straight"][kk["section"] % L] else F(7.5))   # :821
         if near:
-            f1 = _atan2f(F(lz) - F(z), F(lx) - F(x))
-            f2 = _atan2f(F(nz) - F(lz), F(nx) - F(lx))
-            f6 = _atan2f(F(nz) - F(z), F(nx) - F(x))
-            if _mag(F(cx) - F(x), F(cz) - F(z)) <= F(4.0):               # :877-890 (ClosestPoint stand-in: the trigger centre)
+            f1 = _atan2f(F(lz - z), F(lx - x))
+            f2 = _atan2f(F(nz - lz), F(nx - lx))
+            f6 = _atan2f(F(nz - z), F(nx - x))
+            if _mag(F(cx - x), F(cz - z)) <= F(4.0):               # :877-890 (ClosestPoint stand-in: the trigger centre)
                 tx, tz = nx, nz
                 if F(v) > F(5.0):
                     tv = nvel

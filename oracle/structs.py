@@ -61,13 +61,17 @@ class hk_game_state(_S):
 
 class hk_race_kart(_S):
     _fields_ = [("x", f64), ("z", f64), ("v", f64), ("h", f64), ("steer", f32), ("section", i32), ("lane", i32),
-                ("laneChanges", i32), ("illegalLaneChanges", i32), ("sectionStep", i32), ("active", i32), ("pad_", i32)]
+                ("laneChanges", i32), ("illegalLaneChanges", i32), ("sectionStep", i32), ("active", i32), ("team", i32)]
 
 
 class hk_race_plan(_S):
     _fields_ = [("lane", i8 * HK_MAX_SECTIONS), ("vel", f32 * HK_MAX_SECTIONS), ("oppLane", i8 * HK_MAX_SECTIONS),
                 ("oppVel", f32 * HK_MAX_SECTIONS), ("sectionTimes", i32 * HK_MAX_SECTIONS), ("lapStep", i32 * HK_MAX_LAPS),
                 ("avgLaneDiff", f32), ("avgVelDiff", f32)]
+
+
+class hk_race_belief(_S):
+    _fields_ = [("lane", i8 * HK_MAX_SECTIONS), ("vel", f32 * HK_MAX_SECTIONS)]
 
 
 class hk_race_params(_S):
@@ -87,7 +91,7 @@ class hk_mcts_node(_S):
 
 
 STRUCTS = {c.__name__: c for c in (hk_section, hk_kart, hk_game_params, hk_kart_state, hk_action, hk_game_state, hk_race_kart,
-                                   hk_race_plan, hk_race_params, hk_race_mcts_params, hk_mcts_node)}
+                                   hk_race_plan, hk_race_belief, hk_race_params, hk_race_mcts_params, hk_mcts_node)}
 
 _NP = {i32: np.int32, f32: np.float32, f64: np.float64, i8: np.int8, C.c_uint64: np.uint64, C.c_uint8: np.uint8}
 
