@@ -707,6 +707,53 @@ def main():
         except Exception as exc:
             race_mcts_obj = {"error": repr(exc)[:300]}
 
+    # ---- Duos: 4-kart 2v2 races on Complex (BASELINE config 3's game inside the loop): N in 1..4 players per problem after the 8 m filter,
+    #      solved in the 4-player frame every 4th step; Fixed high level, then the MCTS planner with team scoring ---------------------------
+    race4_obj = None
+    if not args.no_race:
+        try:
+            from hierarchicalkarting_b200 import mcts as M2
+            R4 = 8192
+            RN = RC.RacesN(S.COMPLEX, RC.race_params(S.COMPLEX), 4)
+            k4, p4r, b4r, u4r = RC.start_grid_n(S.COMPLEX, R4, 4, seed=20260007 + rank)
+            RN.plan_fixed(k4, p4r)
+            RN.run_n(k4, p4r, b4r, u4r, 0, 100)                                 # standing start
+            barrier()
+            k0n = lib.hk_kernel_launch_count()
+            t0 = time.perf_counter()
+            bad4r = RN.run_n(k4, p4r, b4r, u4r, 100, RACE_STEPS)
+            el4r = max_over_ranks(time.perf_counter() - t0)
+            npl = RN.recipe_n(k4, p4r, b4r)["n_players"]
+            race4_obj = {"metric": "race_agent_steps_per_s", "value": world * 4 * R4 * RACE_STEPS / el4r, "unit": "agent-steps/s", "races_per_gpu": R4,
+                         "karts_per_race": 4, "steps": RACE_STEPS, "ms_per_step": 1e3 * el4r / RACE_STEPS, "lqr_every": RN.lqr_every,
+                         "lqng_solves_per_s": world * 4 * R4 * (RACE_STEPS // RN.lqr_every) / el4r, "lqng_status_nonzero": int(bad4r),
+                         "gpu_launches": int(lib.hk_kernel_launch_count() - k0n), "sections_mean": float(k4["section"].mean()),
+                         "players_per_problem_at_end": {str(n): int((npl == n).sum()) for n in (1, 2, 3, 4)},
+                         "config": "Duos: 4-kart 2v2 races on Complex (teams [0,0,1,1], start lanes {2,3,2,3} at sections {0,0,1,1}), kinematic plant, "
+                                   "planFixed every 100 steps, every agent's LQNG problem (8 m nearby filter, N in 1..4, 4-player frame with dummy players, "
+                                   "lqng_mma4_kernel) every 4th step; host call incl. upload and download of the race states"}
+            prm4m = RC.race_params(S.COMPLEX, high_mode_mcts=True)
+            RNm = RC.RacesN(S.COMPLEX, prm4m, 4)
+            game4 = M2.Game(S.COMPLEX, 4, prm4m.velocityBucketSize)
+            km4, pm4, bm4, um4 = RC.start_grid_n(S.COMPLEX, R4, 4, seed=20260007 + rank)
+            RNm.run_n(km4, pm4, bm4, um4, 0, 100)
+            pl4 = RNm.planner(game4, R4, 256, 20260008 + 1000 * rank, mode=0, reuse_cycles=3, apply_delay=45)
+            RNm.run_n(km4.copy(), pm4.copy(), bm4.copy(), um4.copy(), 100, 101, planner=pl4)        # warm-up
+            pl4.close()
+            pl4 = RNm.planner(game4, R4, 256, 20260008 + 1000 * rank, mode=0, reuse_cycles=3, apply_delay=45)
+            barrier()
+            t0 = time.perf_counter()
+            bad4m = RNm.run_n(km4, pm4, bm4, um4, 100, 200, planner=pl4)
+            el4m = max_over_ranks(time.perf_counter() - t0)
+            race4_obj["mcts"] = {"value": world * 4 * R4 * 200 / el4m, "unit": "agent-steps/s", "ms_total": 1e3 * el4m, "planning_events": 2,
+                                 "ms_per_planning_event_derived": (1e3 * el4m - 200 * race4_obj["ms_per_step"]) / 2,
+                                 "planner": {"mode": 0, "iterations": 256, "reuse_cycles": 3, "apply_delay": 45}, "lqng_status_nonzero": int(bad4m),
+                                 "waypoints_set": int((pm4["lane"] != 0).sum()), "beliefs_set": int((bm4["lane"] != 0).sum()),
+                                 "trees_out_of_nodes": int((pl4.state()[2] == 3).sum())}
+            pl4.close()
+        except Exception as exc:
+            race4_obj = {"error": repr(exc)[:300]}
+
     clocks = sampler.finish(value_rows)
 
     # ---- final gather of per-rank summaries (the only communication) ------------------------------------------------------
@@ -773,6 +820,8 @@ def main():
         line["race"] = race_obj
     if race_mcts_obj:
         line["race_mcts"] = race_mcts_obj
+    if race4_obj:
+        line["race4"] = race4_obj
     line["full_outputs"] = full_obj
     line["time_varying"] = tv_obj
     if lqng4_obj:
