@@ -33,7 +33,11 @@ int ensure_device()
         return HK_OK;
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_device_state.load() == 1) return HK_OK;
+    if (g_device_state.load() == 1) {                  // lost the initialisation race: still bind THIS thread to the device
+        cudaError_t e2 = cudaSetDevice(g_device.load());
+        if (e2 != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e2)); return HK_ERR_CUDA; }
+        return HK_OK;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n < 1) {
@@ -58,24 +62,41 @@ int ensure_device()
     return HK_OK;
 }
 
-ThreadCtx::~ThreadCtx()
+void ThreadCtx::release()
 {
-    // Streams/buffers of a dying host thread; ignore errors (the context may already be gone at process exit).
+    // Streams/buffers of this host thread; ignore errors (the context may already be gone at process exit).
     if (!ready) return;
-    for (auto& b : dbuf) if (b) cudaFree(b);
-    for (auto& b : hbuf) if (b) cudaFreeHost(b);
-    for (auto& e : ev) if (e) cudaEventDestroy(e);
-    for (auto& e : pev) if (e) cudaEventDestroy(e);
-    for (auto& st : cstream) if (st) cudaStreamDestroy(st);
+    for (auto& b : dbuf) { if (b) cudaFree(b); b = nullptr; }
+    for (auto& cp : dcap) cp = 0;
+    for (auto& b : hbuf) { if (b) cudaFreeHost(b); b = nullptr; }
+    for (auto& cp : hcap) cp = 0;
+    for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : pev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    for (auto& st : cstream) { if (st) cudaStreamDestroy(st); st = nullptr; }
     if (stream) cudaStreamDestroy(stream);
     if (stream2) cudaStreamDestroy(stream2);
+    stream = stream2 = nullptr;
+    ready = false;
 }
+
+ThreadCtx::~ThreadCtx() { release(); }
+
+void drain_ctx(ThreadCtx* c)
+{
+    if (!c || !c->ready) return;
+    cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2);
+    for (auto& st : c->cstream) if (st) cudaStreamSynchronize(st);
+}
+
+static ThreadCtx& thread_ctx() { static thread_local ThreadCtx c; return c; }
 
 ThreadCtx* ctx()
 {
-    static thread_local ThreadCtx c;
+    ThreadCtx& c = thread_ctx();
     if (ensure_device() != HK_OK) return nullptr;
+    if (c.ready && c.device != g_device.load()) c.release();      // hk_shutdown() + hk_init(other device): streams / buffers of the old device
     if (!c.ready) {
+        c.device = g_device.load();
         if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking) != cudaSuccess) {
             set_error("cudaStreamCreate failed");
@@ -138,8 +159,9 @@ extern "C" int hk_init(int device)
 
 extern "C" void hk_shutdown(void)
 {
-    // Per-thread contexts are released by their owning threads; this only forgets the device binding.
-    if (g_device_state.load() == 1) cudaDeviceSynchronize();
+    // Releases the CALLING thread's streams and scratch buffers and forgets the device binding; other threads' contexts are
+    // released by their owners (when they end, or at their next call after a re-initialisation on another device).
+    if (g_device_state.load() == 1) { cudaDeviceSynchronize(); thread_ctx().release(); }
     g_device_state.store(0);
     g_device.store(-1);
 }
@@ -187,6 +209,7 @@ extern "C" int hk_lqng_solve_batch(int batch, int n_players, int horizon, int ti
     if (batch == 0) return HK_OK;
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
+    struct DrainOnError { ThreadCtx* c; bool ok = false; ~DrainOnError() { if (!ok) drain_ctx(c); } } drain_guard{c};   // an error return must not leave copies in flight on the caller's buffers
     const int N = n_players, T = horizon + 1, Tm = time_varying ? T : 1, n = 4 * N, m = 2 * N;
     const size_t eA = (size_t)Tm * N * 16, eB = (size_t)Tm * N * 8, eQ = (size_t)Tm * N * n * n, eq = (size_t)Tm * N * n, eR = (size_t)Tm * N * 4;
     const size_t in_elems = eA + eB + eQ + eq + eR + n;
@@ -237,6 +260,7 @@ extern "C" int hk_lqng_solve_batch(int batch, int n_players, int horizon, int ti
         }
         if (traj) { std::memcpy(traj, ho, sizeof(double) * (T + 1) * n * batch); ho += sizeof(double) * (T + 1) * n * batch; }
         if (status) std::memcpy(status, ho, sizeof(int) * batch);
+        drain_guard.ok = true;
         return HK_OK;
     }
     const int nchunks = batch >= 8192 ? 4 : 1;
@@ -278,6 +302,7 @@ extern "C" int hk_lqng_solve_batch(int batch, int n_players, int horizon, int ti
     }
     HK_CUDA(cudaStreamSynchronize(c->stream));
     HK_CUDA(cudaStreamSynchronize(c->stream2));
+    drain_guard.ok = true;
     return HK_OK;
 }
 
@@ -312,6 +337,7 @@ extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizo
     if (batch == 0) return HK_OK;
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
+    struct DrainOnError { ThreadCtx* c; bool ok = false; ~DrainOnError() { if (!ok) drain_ctx(c); } } drain_guard{c};   // an error return must not leave copies in flight on the caller's buffers
     const int K = N - 1, m = 2 * N;
     const size_t e[7] = {(size_t)N * 4, (size_t)N * 4, (size_t)N * 4, (size_t)N, (size_t)N * K * 2, (size_t)N * K * 4, (size_t)N * K * 3};
     const double* src[7] = {x0, target, tw, cw, aw, otgt, otw};
@@ -391,5 +417,6 @@ extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizo
     }
     HK_CUDA(cudaStreamSynchronize(c->stream));
     HK_CUDA(cudaStreamSynchronize(c->stream2));
+    drain_guard.ok = true;
     return HK_OK;
 }

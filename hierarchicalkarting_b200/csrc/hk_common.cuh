@@ -24,6 +24,8 @@ struct ThreadCtx {
     void* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};      // pinned
     size_t hcap[4] = {0, 0, 0, 0};
     bool ready = false;
+    int device = -1;                                          // the device the streams / buffers belong to
+    void release();
     unsigned launch_id = 0;                                   // alternates the redo counters of the LQNG fast path
     ~ThreadCtx();
 };
@@ -32,6 +34,7 @@ int  ensure_device();                       // HK_OK or HK_ERR_NO_DEVICE / HK_ER
 ThreadCtx* ctx();                           // nullptr on failure (error set)
 void* dscratch(ThreadCtx* c, int slot, size_t bytes);     // nullptr on OOM (error set)
 void* hscratch(ThreadCtx* c, int slot, size_t bytes);
+void drain_ctx(ThreadCtx* c);                // synchronises every stream the context owns (error paths of the pipelines)
 
 #define HK_CUDA(call)                                                                                   \
     do {                                                                                                \

@@ -1194,8 +1194,9 @@ static int rollouts_impl(const hk_game* g, const hk_game_state* leaves, int n_le
     HK_CUDA(cudaMemcpyAsync(d, leaves, sz[0], cudaMemcpyHostToDevice, c->stream));
     HK_CUDA(cudaMemsetAsync(d + off[1], 0, off[6] - off[1], c->stream));
     if (rollouts_per_leaf > 0) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        int sms = 148, cur_dev = 0;
+        cudaGetDevice(&cur_dev);                                          // the device this process is bound to (hk_init), not device 0
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev);
         long long want = (rollouts_per_leaf + 127) / 128;
         long long cap = (long long)sms * 16 / (n_leaves < sms * 16 ? 1 : 1);          // persistent-ish grid: 16 CTAs of 128 threads per SM
         if (n_leaves > 1) cap = (cap + n_leaves - 1) / n_leaves > 0 ? (cap + n_leaves - 1) / n_leaves : 1;

@@ -497,11 +497,7 @@ extern "C" int hk_race_planner_create(const hk_game* game, const hk_race_mcts_pa
 }
 
 // Synchronises every stream the calling thread's context owns: an error return must not leave copies in flight on the caller's buffers.
-static void drain(ThreadCtx* c)
-{
-    cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2);
-    for (auto& st : c->cstream) if (st) cudaStreamSynchronize(st);
-}
+static void drain(ThreadCtx* c) { drain_ctx(c); }
 #define HK_CUDA_DRAIN(call)                                                                             \
     do {                                                                                                \
         cudaError_t e_ = (call);                                                                        \

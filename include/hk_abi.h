@@ -220,6 +220,9 @@ int hk_mcts_rollouts_multi(const hk_game* g, const hk_game_state* leaves, int n_
  * :124-159), then backpropagates (:280-289).  Root r uses Philox key seed + r for its rollouts (ids it * R * HK_MAX_ACTIONS +
  * child * R + k, as hk_mcts_rollouts_multi numbers them) and counter stream (seed + r) ^ 0x9E3779B97F4A7C15 for the random
  * initial pick of upperConfidenceStrategy, so a host mirror driven by the same streams builds the same tree.
+ * Terminal nodes: this mode is a HYBRID of the reference's two — the expansion is processLeaf's, but a terminal leaf (and a terminal
+ * child, R times) backpropagates its terminal scores as the sequential simulate() path does (:246-249, :280-289), whereas the reference's
+ * processLeaf returns without backpropagating (:126-129).  For what the reference's callers execute, use hk_mcts_forest_search.
  *   best_states   [n_roots][HK_MCTS_MAX_SEQ]  the states of getBestStatesSequence, n_best [n_roots] of them
  *   root_episodes [n_roots][HK_MAX_ACTIONS]   numEpisodes of the root's children in nextMoves() order (may be NULL)
  *   root_values   [n_roots][HK_MAX_ACTIONS]   their totalValue (may be NULL);  n_nodes [n_roots] tree sizes (may be NULL)

@@ -223,7 +223,7 @@ def test_edge_cases(hk):
 
 def test_full_size_properties(hk, oracle):
     """BASELINE config 2 size (65,536 problems): determinism, batch-permutation equivariance, duplicate problems give
-    identical answers, and a strided sample checked against the oracle."""
+    identical answers, and EVERY problem checked against the oracle (all host threads: ~50 ms)."""
     p = S.config2(65536)
     A, B, Q, q, R, x0 = S.assemble_dense(p)
     a = lqr.solve_batch(A, B, Q, q, R, x0, 3, full=False)
@@ -232,11 +232,12 @@ def test_full_size_properties(hk, oracle):
     perm = np.random.default_rng(0).permutation(65536)
     c = lqr.solve_batch(A[perm], B[perm], Q[perm], q[perm], R[perm], x0[perm], 3, full=False)
     assert np.array_equal(c["u0"], a["u0"][perm])
-    idx = np.arange(0, 65536, 257)
-    ref = oracle.lqng_solve_batch(A[idx], B[idx], Q[idx], q[idx], R[idx], x0[idx], 3, full=False)
-    for k, i in enumerate(idx):
-        assert rel_err(a["u0"][i], ref["u0"][k]) <= TOL
-    assert np.all(a["status"] == 0)
+    import os
+    ref = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 3, full=False, threads=os.cpu_count() or 1)
+    scale = np.maximum(np.abs(ref["u0"]), np.max(np.abs(ref["u0"]), axis=1, keepdims=True))
+    err = np.abs(a["u0"] - ref["u0"]) / np.where(scale == 0, 1.0, scale)                 # SURVEY.md A.7 metric, per problem
+    assert float(err.max()) <= TOL, (float(err.max()), int(np.argmax(err.max(axis=1))))
+    assert np.all(a["status"] == 0) and np.all(ref["status"] == 0)
 
 
 def test_full_size_properties_4kart(hk, oracle):
@@ -251,10 +252,13 @@ def test_full_size_properties_4kart(hk, oracle):
     perm = np.random.default_rng(1).permutation(n)[:32768]
     c = lqr.solve_batch(A[perm], B[perm], Q[perm], q[perm], R[perm], x0[perm], 3, full=False)
     assert np.array_equal(c["u0"], a["u0"][perm])
+    import os
+    every = oracle.lqng_solve_batch(A, B, Q, q, R, x0, 3, full=False, threads=os.cpu_count() or 1)     # all 131,072 problems
+    scale = np.maximum(np.abs(every["u0"]), np.max(np.abs(every["u0"]), axis=1, keepdims=True))
+    err = np.abs(a["u0"] - every["u0"]) / np.where(scale == 0, 1.0, scale)
+    assert float(err.max()) <= TOL, (float(err.max()), int(np.argmax(err.max(axis=1))))
     idx = np.arange(0, n, 509)
     ref = oracle.lqng_solve_batch(A[idx], B[idx], Q[idx], q[idx], R[idx], x0[idx], 3)
-    for k, i in enumerate(idx):
-        assert rel_err(a["u0"][i], ref["u0"][k]) <= TOL
     full = lqr.solve_batch(A[idx], B[idx], Q[idx], q[idx], R[idx], x0[idx], 3)
     _check(full, ref)
 
