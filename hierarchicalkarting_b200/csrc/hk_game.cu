@@ -1329,10 +1329,15 @@ int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, cons
     const float* lt = seq_log_table();
     if (!lt) { set_error("hk_mcts_forest_search: log table allocation failed"); return HK_ERR_OUT_OF_MEMORY; }
     if (d_best && clear_best) HK_CUDA(cudaMemsetAsync(d_best, 0, sizeof(hk_game_state) * (size_t)f->n_trees * HK_MCTS_MAX_SEQ, s));   // entries past n_best stay zero
-    constexpr int TPB = 32;                            // one warp per block: 32,768 trees spread over the 148 SMs as 1,024 blocks
+    // One warp per block, 32 trees per warp.  Fewer trees per warp (HK_SEQ_LANES = 16 / 8 / 4: more, less divergent warps) was measured and
+    // is SLOWER — 32,768 trees x 512 iterations: 69 / 107 / 136 / 208 ms of host call at 32 / 16 / 8 / 4 — a warp's time is set by its
+    // longest lane (dependent node-chain latency), not by the sum of its lanes' paths, so halving the lanes only doubles the warps.
+    static const int lanes_env = getenv("HK_SEQ_LANES") ? atoi(getenv("HK_SEQ_LANES")) : 0;
+    int lanes = 32;
+    if (lanes_env == 8 || lanes_env == 16 || lanes_env == 32 || lanes_env == 4) lanes = lanes_env;
     count_launch();
-    seq_search_kernel<<<(unsigned)((f->n_trees + TPB - 1) / TPB), TPB, 0, s>>>(f->g->dev, f->trees, f->slabs, f->max_nodes, f->n_trees, iterations, seed, 0,
-                                                                              d_roots, d_fresh, lt, SEQ_LOG_TABLE, d_best, d_nbest, d_nnodes, d_status);
+    seq_search_kernel<<<(unsigned)((f->n_trees + lanes - 1) / lanes), 32, 0, s>>>(f->g->dev, f->trees, f->slabs, f->max_nodes, f->n_trees, iterations, seed, 0,
+                                                                                 d_roots, d_fresh, lt, SEQ_LOG_TABLE, d_best, d_nbest, d_nnodes, d_status, lanes);
     HK_CUDA(cudaGetLastError());
     return HK_OK;
 }

@@ -401,6 +401,7 @@ static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact, bool fu
         kern = lqng_mma2p_kernel<16, 1, false, true>;
     } else if (variant == 2) {
         kern = minb >= 32 ? lqng_mma2p_kernel<32, 1> : minb >= 24 ? lqng_mma2p_kernel<24, 1> : minb >= 20 ? lqng_mma2p_kernel<20, 1>
+               : minb >= 18 ? lqng_mma2p_kernel<18, 1> : minb >= 17 ? lqng_mma2p_kernel<17, 1>
                : minb >= 16 ? lqng_mma2p_kernel<16, 1> : lqng_mma2p_kernel<12, 1>;
     } else {
         kern = minb >= 8 ? lqng_mma2p_kernel<8, 4> : minb >= 6 ? lqng_mma2p_kernel<6, 4> : minb == 5 ? lqng_mma2p_kernel<5, 4>

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
                                                         const hk_game_state* __restrict__ roots, const int* __restrict__ fresh,
                                                         const float* __restrict__ logtab, int n_log,
                                                         hk_game_state* __restrict__ best_out, int* __restrict__ n_best_out,
-                                                        int* __restrict__ n_nodes_out, int* __restrict__ status_out)
+                                                        int* __restrict__ n_nodes_out, int* __restrict__ status_out, int active_lanes)
 {
     __shared__ DevGame g;
     {
@@ -91,7 +91,10 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
         for (int i = threadIdx.x; i < (int)(sizeof(DevGame) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // Only the first `active_lanes` lanes of a warp own a tree (32 in production; the experiment with fewer is recorded at the launch site).
+    const int wl = threadIdx.x & 31;
+    if (wl >= active_lanes) return;
+    const int t = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * active_lanes + wl;
     if (t >= n_trees) return;
     if (fresh && fresh[t] < 0) {                                       // this tree does not search in this call (its outputs stay untouched)
         if (status_out) status_out[t] = 0;
