@@ -1302,6 +1302,10 @@ struct hk_mcts_forest {
     int n_trees = 0, max_nodes = 0;
     hk::SeqTree* trees = nullptr;
     hk_mcts_node* slabs = nullptr;
+    unsigned* recs = nullptr;             // fast path: playout records of one chunk of iterations [n_trees][chunk][SEQ_REC_HEAD + cap]
+    size_t recs_bytes = 0;
+    int* remaining = nullptr;             // fast path: -1 while a tree is on it, else the iterations the general kernel still owes it
+    int max_plies = 0;                    // largest playout length any root given through the host entry can have
 };
 
 namespace hk {
@@ -1324,7 +1328,7 @@ static const float* seq_log_table()
 }
 
 int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, const int* d_fresh, int iterations, uint64_t seed,
-                           hk_game_state* d_best, int* d_nbest, int* d_nnodes, int* d_status, cudaStream_t s, bool clear_best)
+                           hk_game_state* d_best, int* d_nbest, int* d_nnodes, int* d_status, cudaStream_t s, bool clear_best, int max_plies)
 {
     const float* lt = seq_log_table();
     if (!lt) { set_error("hk_mcts_forest_search: log table allocation failed"); return HK_ERR_OUT_OF_MEMORY; }
@@ -1335,9 +1339,54 @@ int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, cons
     static const int lanes_env = getenv("HK_SEQ_LANES") ? atoi(getenv("HK_SEQ_LANES")) : 0;
     int lanes = 32;
     if (lanes_env == 8 || lanes_env == 16 || lanes_env == 32 || lanes_env == 4) lanes = lanes_env;
+    const unsigned tree_blocks = (unsigned)((f->n_trees + lanes - 1) / lanes);
+    const char* fast_env = getenv("HK_SEQ_FAST");                    // read per call: tests run both paths in one process
+    const bool fast = !(fast_env && atoi(fast_env) == 0);
+    if (!fast || iterations == 0) {                                   // the general kernel alone: init, every iteration, best states
+        count_launch();
+        seq_search_kernel<<<tree_blocks, 32, 0, s>>>(f->g->dev, f->trees, f->slabs, f->max_nodes, f->n_trees, iterations, nullptr, seed, 0, d_roots, d_fresh,
+                                                     lt, SEQ_LOG_TABLE, d_best, d_nbest, d_nnodes, d_status, lanes, true, true);
+        HK_CUDA(cudaGetLastError());
+        return HK_OK;
+    }
+    // fast path (hk_mcts_seq.cuh): init; per chunk of iterations the playouts of every (tree, iteration) in parallel and their insertion in
+    // order; then the general kernel for trees whose root became fully expanded on the way, and getBestStatesSequence for all
+    const int cap = max_plies > 0 && max_plies < HK_MAX_PLIES ? max_plies : HK_MAX_PLIES;
+    const size_t words = (size_t)SEQ_REC_HEAD + cap;
+    long long chunk = (long long)(768.0e6 / ((double)f->n_trees * words * 4));
+    chunk = chunk < 16 ? 16 : chunk > 512 ? 512 : chunk;
+    if (chunk > iterations) chunk = iterations;
+    const size_t need = (size_t)f->n_trees * (size_t)chunk * words * 4;
+    if (need > f->recs_bytes) {
+        HK_CUDA(cudaStreamSynchronize(s));
+        if (f->recs) cudaFree(f->recs);
+        f->recs = nullptr; f->recs_bytes = 0;
+        HK_CUDA(cudaMalloc(&f->recs, need));
+        f->recs_bytes = need;
+    }
+    if (!f->remaining) HK_CUDA(cudaMalloc(&f->remaining, sizeof(int) * (size_t)f->n_trees));
+    HK_CUDA(cudaMemsetAsync(f->remaining, 0xff, sizeof(int) * (size_t)f->n_trees, s));
     count_launch();
-    seq_search_kernel<<<(unsigned)((f->n_trees + lanes - 1) / lanes), 32, 0, s>>>(f->g->dev, f->trees, f->slabs, f->max_nodes, f->n_trees, iterations, seed, 0,
-                                                                                 d_roots, d_fresh, lt, SEQ_LOG_TABLE, d_best, d_nbest, d_nnodes, d_status, lanes);
+    seq_search_kernel<<<tree_blocks, 32, 0, s>>>(f->g->dev, f->trees, f->slabs, f->max_nodes, f->n_trees, 0, nullptr, seed, 0, d_roots, d_fresh, lt,
+                                                 SEQ_LOG_TABLE, nullptr, nullptr, nullptr, nullptr, lanes, true, false);
+    HK_CUDA(cudaGetLastError());
+    // Playouts and insertion alternate on the caller's stream.  Running the playouts of chunk c + 1 on a second stream beside the insertion
+    // of chunk c (two record buffers) was measured and does not pay: 61.6 ms per 32,768 x 512 call against 48.8 ms (the playout grid's blocks
+    // crowd the 1,024 one-warp insertion blocks off the SMs), 49.6 ms with the playout stream at the lowest priority.
+    for (int base = 0; base < iterations; base += (int)chunk) {
+        const int count = base + chunk <= iterations ? (int)chunk : iterations - base;
+        const long long threads = (long long)f->n_trees * count;
+        count_launch();
+        seq_playouts_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(f->g->dev, f->trees, f->n_trees, d_fresh, f->remaining, count, base, cap, f->recs);
+        HK_CUDA(cudaGetLastError());
+        count_launch();
+        seq_insert_kernel<<<(unsigned)((f->n_trees + 31) / 32), 32, 0, s>>>(f->trees, f->slabs, f->max_nodes, f->n_trees, d_fresh, f->remaining, count, count,
+                                                                          iterations - base - count, cap, f->recs);
+        HK_CUDA(cudaGetLastError());
+    }
+    count_launch();
+    seq_search_kernel<<<tree_blocks, 32, 0, s>>>(f->g->dev, f->trees, f->slabs, f->max_nodes, f->n_trees, 0, f->remaining, seed, 0, d_roots, d_fresh, lt,
+                                                 SEQ_LOG_TABLE, d_best, d_nbest, d_nnodes, d_status, lanes, false, true);
     HK_CUDA(cudaGetLastError());
     return HK_OK;
 }
@@ -1370,6 +1419,8 @@ extern "C" void hk_mcts_forest_destroy(hk_mcts_forest* f)
     if (!f) return;
     if (f->trees) cudaFree(f->trees);
     if (f->slabs) cudaFree(f->slabs);
+    if (f->recs) cudaFree(f->recs);
+    if (f->remaining) cudaFree(f->remaining);
     delete f;
 }
 
@@ -1385,6 +1436,10 @@ extern "C" int hk_mcts_forest_search(hk_mcts_forest* f, const hk_game_state* roo
         if (!roots) { set_error("hk_mcts_forest_search: roots is NULL but tree %d is fresh", r); return HK_ERR_INVALID_ARGUMENT; }
         int rc = check_state(f->g, &roots[r], "hk_mcts_forest_search");
         if (rc) return rc;
+        long long pl = 0;
+        for (int k = 0; k < roots[r].n_karts; ++k) { const long long dd = (long long)roots[r].finalSection - roots[r].karts[k].section; pl += dd > 0 ? dd : 0; }
+        if (pl > HK_MAX_PLIES) { set_error("hk_mcts_forest_search: a playout of tree %d could take %lld plies (> %d)", r, pl, HK_MAX_PLIES); return HK_ERR_INVALID_ARGUMENT; }
+        if ((int)pl > f->max_plies) f->max_plies = (int)pl;
     }
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
@@ -1396,7 +1451,7 @@ extern "C" int hk_mcts_forest_search(hk_mcts_forest* f, const hk_game_state* roo
     if (any_fresh) HK_CUDA(cudaMemcpyAsync(d, roots, sz[0], cudaMemcpyHostToDevice, c->stream));
     if (fresh) HK_CUDA(cudaMemcpyAsync(d + off[1], fresh, sz[1], cudaMemcpyHostToDevice, c->stream));
     int rc = mcts_seq_search_device(f, (const hk_game_state*)d, fresh ? (const int*)(d + off[1]) : nullptr, iterations, seed,
-                                    (hk_game_state*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (int*)(d + off[5]), c->stream);
+                                    (hk_game_state*)(d + off[2]), (int*)(d + off[3]), (int*)(d + off[4]), (int*)(d + off[5]), c->stream, true, f->max_plies);
     if (rc) { cudaStreamSynchronize(c->stream); return rc; }
     std::vector<int> st((size_t)n);
     cudaError_t e = cudaMemcpyAsync(best_states, d + off[2], sz[2], cudaMemcpyDeviceToHost, c->stream);

@@ -46,8 +46,10 @@ int mcts_search_device(const hk_game* g, const hk_game_state* d_roots, int n_roo
                        hk_game_state* d_best, int* d_nbest, int* d_eps, double* d_vals, int* d_nnodes, int* d_status, ThreadCtx* c,
                        cudaStream_t s);
 // hk_mcts_forest_search on device pointers (d_fresh may be null = all fresh; a negative entry skips that tree), enqueued on `s`.
+// max_plies: upper bound on the plies of a playout from any root of the forest (sizes the fast path's records; 0 = HK_MAX_PLIES).
 int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, const int* d_fresh, int iterations, uint64_t seed,
-                           hk_game_state* d_best, int* d_nbest, int* d_nnodes, int* d_status, cudaStream_t s, bool clear_best = true);
+                           hk_game_state* d_best, int* d_nbest, int* d_nnodes, int* d_status, cudaStream_t s, bool clear_best = true,
+                           int max_plies = 0);
 const hk_game_params& game_params_of(const hk_game* g);
 int game_karts_of(const hk_game* g);
 

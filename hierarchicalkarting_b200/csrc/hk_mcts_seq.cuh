@@ -22,6 +22,7 @@
 struct SeqTree {                                  // per-tree header; persists between calls like HierarchicalKartAgent.currentRoot
     hk_game_state root;
     unsigned long long key, picks, iters;
+    unsigned long long iters0;                    // iters when the current call started (the fast path's playouts are numbered from it)
     int n_nodes, status, root_upnext, pad_;
     signed char root_cnt[HK_MAX_KARTS];           // prepared policy-ordered legal lists of karts that start from a non-action bucket
     unsigned char root_order[HK_MAX_KARTS][HK_MAX_ACTIONS];   // (quirk B.6-1: the root's (0, bucket)); -1 = not prepared
@@ -77,34 +78,111 @@ __device__ __forceinline__ void seq_apply(const DevGame& g, const Tables& tb, hk
 
 constexpr int SEQ_MAX_PATH = HK_MAX_PLIES + 1;
 
+// One ply of simulate (:243-269) on the carried state: the legal moves of kart np in policy order, isOver, the index draw, the move.
+// Returns false when the state is terminal (scores filled), true after applying the chosen move (cnt = nextMoves().Count, gi = the move).
+__device__ __forceinline__ bool seq_ply(const DevGame& g, const Tables& tb, const SeqTree& tr, hk_game_state& st, int& lcs_idx, unsigned& moved, int np,
+                                        unsigned long long key, unsigned long long iters, unsigned ply, float* scores, int& n_scores, int& cnt, int& gi)
+{
+    const int lvl = (g.tables_ok && st.karts[np].player == 0) ? velocity_level(g, st.karts[np].min_velocity, st.karts[np].max_velocity) : -1;
+    int sidx = 0, kind;
+    unsigned long long mask = 0ull;
+    const unsigned char* ord = nullptr;
+    unsigned long long keys[HK_MAX_ACTIONS];
+    if (lvl >= 0) { kind = 1; cnt = fast_legal(g, tb, st, np, lvl, mask, ord, sidx, lcs_idx); }
+    else if (!((moved >> np) & 1u) && tr.root_cnt[np] >= 0) { kind = 0; cnt = tr.root_cnt[np]; }
+    else { kind = 2; cnt = legal_moves(g, st, np, keys); }
+    if (is_over(g, st, cnt, np, scores, n_scores)) return false;       // :243-249
+    const int index = policy_index(g, cnt, philox_first(key, iters, ply));   // :266-269
+    if (kind == 1) gi = __ldg(&ord[nth_set_bit(mask, index)]);
+    else if (kind == 0) gi = tr.root_order[np][index];
+    else gi = select_kth(keys, g.n_cand, index);
+    if (kind == 1) fast_move(g, tb, st, np, lvl, gi, sidx, lcs_idx);
+    else { make_move(g, st, np, action_of(g, gi)); lcs_idx = st.lastCompletedSection % g.n_sections; }
+    moved |= 1u << np;
+    return true;
+}
+
+// leaf.children.ContainsKey(move) ? leaf.children[move] : new KartMCTSNode(...) (:271-276) on the node records.  `nd` is the register copy of
+// nodes[node] (dirty: differs from memory); cnt = nextMoves().Count of the node's state, up_after = upNext() of the state after the move.
+// Returns the child (its record in nd, node updated), or -1 when the slab is full.
+__device__ __forceinline__ int seq_descend(hk_mcts_node* __restrict__ nodes, int& node, hk_mcts_node& nd, bool& dirty, int cnt, int gi, int up_after,
+                                           int& n_nodes, int max_nodes)
+{
+    if (nd.n_legal == 255) { nd.n_legal = (unsigned char)cnt; dirty = true; }
+    int child;
+    hk_mcts_node ch;
+    if ((nd.child_mask >> gi) & 1ull) {
+        if (dirty) { nodes[node] = nd; dirty = false; }
+        child = nd.first_child;
+        for (;;) {
+            ch = nodes[child];
+            if (ch.gen == gi) break;
+            child = ch.next_sibling;
+        }
+    } else {                                                           // new KartMCTSNode(state.makeMove(move), leaf) :273
+        if (n_nodes >= max_nodes) return -1;
+        child = n_nodes++;
+        if (nd.last_child >= 0) nodes[nd.last_child].next_sibling = child; else nd.first_child = child;
+        nd.last_child = child;
+        nd.child_mask |= 1ull << gi;
+        nodes[node] = nd; dirty = false;
+        ch.child_mask = 0ull; ch.totalValue = 0.0f; ch.numEpisodes = 0; ch.first_child = -1; ch.last_child = -1; ch.next_sibling = -1;
+        ch.gen = (unsigned char)gi; ch.n_legal = 255; ch.upnext = (signed char)up_after; ch.pad_ = 0;
+        nodes[child] = ch;
+    }
+    node = child; nd = ch;
+    return child;
+}
+
+__device__ __forceinline__ void seq_backprop(hk_mcts_node* __restrict__ nodes, const int* path, int depth, const float* scores, int n_scores)   // :280-289
+{
+    for (int d = depth; d >= 0; --d) {
+        hk_mcts_node* p = &nodes[path[d]];
+        const int up = p->upnext;
+        float tot = p->totalValue;
+        if (up >= 0 && up < n_scores) tot += scores[up];
+        p->totalValue = tot;
+        p->numEpisodes += 1;
+    }
+}
+
+#define SEQ_LOAD_GAME()                                                                                      \
+    __shared__ DevGame g;                                                                                    \
+    {                                                                                                        \
+        const int* src = reinterpret_cast<const int*>(gg);                                                   \
+        int* dst = reinterpret_cast<int*>(&g);                                                               \
+        for (int i_ = threadIdx.x; i_ < (int)(sizeof(DevGame) / 4); i_ += blockDim.x) dst[i_] = src[i_];     \
+    }                                                                                                        \
+    __syncthreads();
+
+// The general sequential kernel, one thread per tree, in three optional phases: INIT (new KartMCTSNode(state) for fresh trees), `iterations`
+// (or remaining[t], if given) full iterations — findLeaf by upperConfidenceStrategy, simulate, backpropagate —, BEST (getBestStatesSequence
+// and the outputs).  The fast path below (seq_playouts_kernel + seq_insert_kernel) takes the iterations whose findLeaf returns the root;
+// this kernel takes the rest, and is the whole search when the fast path is switched off.
 __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restrict__ gg, SeqTree* __restrict__ trees, hk_mcts_node* __restrict__ slabs,
-                                                        int max_nodes, int n_trees, int iterations, unsigned long long seed, int tree_base,
+                                                        int max_nodes, int n_trees, int iterations, const int* __restrict__ remaining,
+                                                        unsigned long long seed, int tree_base,
                                                         const hk_game_state* __restrict__ roots, const int* __restrict__ fresh,
                                                         const float* __restrict__ logtab, int n_log,
                                                         hk_game_state* __restrict__ best_out, int* __restrict__ n_best_out,
-                                                        int* __restrict__ n_nodes_out, int* __restrict__ status_out, int active_lanes)
+                                                        int* __restrict__ n_nodes_out, int* __restrict__ status_out, int active_lanes,
+                                                        bool do_init, bool do_best)
 {
-    __shared__ DevGame g;
-    {
-        const int* src = reinterpret_cast<const int*>(gg);
-        int* dst = reinterpret_cast<int*>(&g);
-        for (int i = threadIdx.x; i < (int)(sizeof(DevGame) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
+    SEQ_LOAD_GAME();
     // Only the first `active_lanes` lanes of a warp own a tree (32 in production; the experiment with fewer is recorded at the launch site).
     const int wl = threadIdx.x & 31;
     if (wl >= active_lanes) return;
     const int t = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * active_lanes + wl;
     if (t >= n_trees) return;
     if (fresh && fresh[t] < 0) {                                       // this tree does not search in this call (its outputs stay untouched)
-        if (status_out) status_out[t] = 0;
+        if (status_out && do_best) status_out[t] = 0;
         return;
     }
     const Tables tb(g);
     SeqTree& tr = trees[t];
     hk_mcts_node* nodes = slabs + (size_t)t * max_nodes;
     int status = 0;
-    if (!fresh || fresh[t]) {                                          // new KartMCTSNode(state) :52
+    if (do_init && (!fresh || fresh[t])) {                             // new KartMCTSNode(state) :52
         tr.root = roots[t];
         tr.key = seed + (unsigned long long)(tree_base + t);
         tr.picks = 0; tr.iters = 0; tr.n_nodes = 1; tr.status = 0;
@@ -134,14 +212,16 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
     } else {
         status = tr.status;
     }
+    if (do_init) tr.iters0 = tr.iters;
     const unsigned long long key = tr.key;
     unsigned long long picks = tr.picks, iters = tr.iters;
     int n_nodes = tr.n_nodes;
     const hk_game_state root = tr.root;
     const int root_lcs_idx = root.lastCompletedSection % g.n_sections;
     int path[SEQ_MAX_PATH];
+    const int my_iterations = remaining ? remaining[t] : iterations;
 
-    for (int it = 0; it < iterations && status == 0; ++it, ++iters) {
+    for (int it = 0; it < my_iterations && status == 0; ++it, ++iters) {
         hk_game_state st = root;
         int lcs_idx = root_lcs_idx;
         unsigned moved = 0;
@@ -170,64 +250,17 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
         for (unsigned ply = 0;; ++ply) {
             const int np = nd.upnext;
             if (np < 0) { status = 1; break; }                         // ArgumentOutOfRangeException at KartDiscreteGame.cs:326
-            const int lvl = (g.tables_ok && st.karts[np].player == 0) ? velocity_level(g, st.karts[np].min_velocity, st.karts[np].max_velocity) : -1;
-            int cnt, gi, sidx = 0;
-            unsigned long long mask = 0ull;
-            const unsigned char* ord = nullptr;
-            unsigned long long keys[HK_MAX_ACTIONS];
-            int kind;
-            if (lvl >= 0) { kind = 1; cnt = fast_legal(g, tb, st, np, lvl, mask, ord, sidx, lcs_idx); }
-            else if (!((moved >> np) & 1u) && tr.root_cnt[np] >= 0) { kind = 0; cnt = tr.root_cnt[np]; }
-            else { kind = 2; cnt = legal_moves(g, st, np, keys); }
-            if (is_over(g, st, cnt, np, scores, n_scores)) break;      // :243-249
-            if (nd.n_legal == 255) { nd.n_legal = (unsigned char)cnt; dirty = true; }
-            const int index = policy_index(g, cnt, philox_first(key, iters, ply));   // :266-269
-            if (kind == 1) gi = __ldg(&ord[nth_set_bit(mask, index)]);
-            else if (kind == 0) gi = tr.root_order[np][index];
-            else gi = select_kth(keys, g.n_cand, index);
-            // leaf.children.ContainsKey(move) :271
-            int child;
-            hk_mcts_node ch;
-            if ((nd.child_mask >> gi) & 1ull) {
-                if (dirty) { nodes[node] = nd; dirty = false; }
-                child = nd.first_child;
-                for (;;) {
-                    ch = nodes[child];
-                    if (ch.gen == gi) break;
-                    child = ch.next_sibling;
-                }
-                if (kind == 1) fast_move(g, tb, st, np, lvl, gi, sidx, lcs_idx);
-                else { make_move(g, st, np, action_of(g, gi)); lcs_idx = st.lastCompletedSection % g.n_sections; }
-            } else {                                                   // new KartMCTSNode(state.makeMove(move), leaf) :273
-                if (n_nodes >= max_nodes) { status = 3; break; }
-                child = n_nodes++;
-                if (nd.last_child >= 0) nodes[nd.last_child].next_sibling = child; else nd.first_child = child;
-                nd.last_child = child;
-                nd.child_mask |= 1ull << gi;
-                nodes[node] = nd; dirty = false;
-                if (kind == 1) fast_move(g, tb, st, np, lvl, gi, sidx, lcs_idx);
-                else { make_move(g, st, np, action_of(g, gi)); lcs_idx = st.lastCompletedSection % g.n_sections; }
-                ch.child_mask = 0ull; ch.totalValue = 0.0f; ch.numEpisodes = 0; ch.first_child = -1; ch.last_child = -1; ch.next_sibling = -1;
-                ch.gen = (unsigned char)gi; ch.n_legal = 255; ch.upnext = (signed char)up_next(st); ch.pad_ = 0;
-                nodes[child] = ch;
-            }
-            moved |= 1u << np;
-            node = child; nd = ch;
-            if (depth + 1 < SEQ_MAX_PATH) path[++depth] = child; else { status = 3; break; }
+            int cnt, gi;
+            if (!seq_ply(g, tb, tr, st, lcs_idx, moved, np, key, iters, ply, scores, n_scores, cnt, gi)) break;
+            if (seq_descend(nodes, node, nd, dirty, cnt, gi, up_next(st), n_nodes, max_nodes) < 0) { status = 3; break; }
+            if (depth + 1 < SEQ_MAX_PATH) path[++depth] = node; else { status = 3; break; }
         }
         if (status) break;
         if (dirty) nodes[node] = nd;
-        // ---- backpropagate :280-289 ---------------------------------------------------------------------------------------------------
-        for (int d = depth; d >= 0; --d) {
-            hk_mcts_node* p = &nodes[path[d]];
-            const int up = p->upnext;
-            float tot = p->totalValue;
-            if (up >= 0 && up < n_scores) tot += scores[up];
-            p->totalValue = tot;
-            p->numEpisodes += 1;
-        }
+        seq_backprop(nodes, path, depth, scores, n_scores);
     }
     tr.picks = picks; tr.iters = iters; tr.n_nodes = n_nodes; tr.status = status;
+    if (!do_best) return;
 
     // ---- getBestStatesSequence :108-122 (it consumes picks like any other upperConfidenceStrategy call; the counter persists) ----------
     int nb = 0;
@@ -250,4 +283,129 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
     if (n_best_out) n_best_out[t] = nb < HK_MCTS_MAX_SEQ ? nb : HK_MCTS_MAX_SEQ;
     if (n_nodes_out) n_nodes_out[t] = n_nodes;
     if (status_out) status_out[t] = status;
+}
+
+// ---- fast path: the playouts of many iterations at once, then their insertion in iteration order -------------------------------------------
+// As long as the root does not have a child for every legal move, findLeaf (:194-201) returns the root, and the playout of iteration `it` —
+// its moves and terminal scores — is a function of the root state and the Philox draws (it, ply) only: NOT of the tree, which merely records
+// it.  So the playouts of a whole chunk of iterations are computed in parallel, one thread per (tree, iteration) (seq_playouts_kernel: the
+// machine is full — 32,768 trees alone are only 7 warps per SM), and one thread per tree then replays what the sequential loop would have
+// done to the node records, in order: look up / create the child of every ply, set nextMoves().Count where a node is processed for the first
+// time, backpropagate (seq_insert_kernel: no game arithmetic, ~30 instructions per ply).  The moment a root IS fully expanded (few legal
+// moves), the tree leaves the fast path: remaining[t] counts the iterations the general kernel above still has to run for it.  The node
+// records, counters and float32 sums come out bit-equal to the sequential kernel's (tests/test_mcts_seq_gpu.py runs both).
+//   record of a playout: word 0 = plies | n_scores << 8 | error << 16; words 1..8 = score bits; word 9 + p = gi | nextMoves().Count << 8 |
+//   (upNext() after the move & 0xff) << 16
+constexpr int SEQ_REC_HEAD = 1 + 2 * HK_MAX_KARTS;
+
+__global__ void __launch_bounds__(128) seq_playouts_kernel(const DevGame* __restrict__ gg, const SeqTree* __restrict__ trees, int n_trees,
+                                                           const int* __restrict__ fresh, const int* __restrict__ remaining, int chunk, int base,
+                                                           int cap, unsigned* __restrict__ recs)
+{
+    SEQ_LOAD_GAME();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_trees * chunk) return;
+    const int t = (int)(idx / chunk), i = (int)(idx % chunk);
+    if ((fresh && fresh[t] < 0) || remaining[t] >= 0) return;          // not searching / already on the general path
+    const Tables tb(g);
+    const SeqTree& tr = trees[t];
+    if (tr.status) return;
+    unsigned* rec = recs + (size_t)idx * (SEQ_REC_HEAD + cap);
+    hk_game_state st = tr.root;
+    int lcs_idx = st.lastCompletedSection % g.n_sections;
+    unsigned moved = 0;
+    const unsigned long long it = tr.iters0 + (unsigned long long)(base + i);   // not tr.iters: the insertion of the previous chunk may still be running
+    float scores[2 * HK_MAX_KARTS];
+    int n_scores = 0, np = tr.root_upnext, err = 0;
+    unsigned ply = 0;
+    for (;; ++ply) {
+        if (np < 0) { err = 1; break; }
+        int cnt, gi;
+        if (!seq_ply(g, tb, tr, st, lcs_idx, moved, np, tr.key, it, ply, scores, n_scores, cnt, gi)) break;
+        if ((int)ply >= cap) { err = 3; break; }
+        np = up_next(st);
+        rec[SEQ_REC_HEAD + ply] = (unsigned)gi | ((unsigned)cnt << 8) | (((unsigned)np & 0xffu) << 16);
+    }
+    rec[0] = ply | ((unsigned)n_scores << 8) | ((unsigned)err << 16);
+    for (int k = 0; k < 2 * HK_MAX_KARTS; ++k) rec[1 + k] = k < n_scores ? __float_as_uint(scores[k]) : 0u;
+}
+
+__global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ trees, hk_mcts_node* __restrict__ slabs, int max_nodes, int n_trees,
+                                                        const int* __restrict__ fresh, int* __restrict__ remaining, int chunk, int count, int todo_after,
+                                                        int cap, const unsigned* __restrict__ recs)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    if ((fresh && fresh[t] < 0) || remaining[t] >= 0) return;
+    SeqTree& tr = trees[t];
+    hk_mcts_node* nodes = slabs + (size_t)t * max_nodes;
+    int status = tr.status, n_nodes = tr.n_nodes;
+    unsigned long long iters = tr.iters;
+    int path[SEQ_MAX_PATH];
+    int i = 0;
+    for (; i < count && status == 0; ++i, ++iters) {
+        hk_mcts_node nd = nodes[0];
+        if (nd.first_child >= 0 && __popcll(nd.child_mask) == (int)nd.n_legal) break;     // findLeaf would descend: the general kernel takes over
+        const unsigned* rec = recs + ((size_t)t * chunk + i) * (SEQ_REC_HEAD + cap);
+        const unsigned head = rec[0];
+        const int len = head & 0xff, n_scores = (head >> 8) & 0xff, err = head >> 16;
+        if (err) { status = err; break; }
+        float scores[2 * HK_MAX_KARTS];
+        for (int k = 0; k < 2 * HK_MAX_KARTS; ++k) scores[k] = __uint_as_float(rec[1 + k]);
+        int node = 0;
+        if (n_nodes + len <= max_nodes) {
+            // The terminal scores are known before the descent, so backpropagate (:280-289) is folded into it: a node on the path gets its
+            // totalValue += scores[upNext()] and numEpisodes += 1 while its record is in registers — a walked node is written back once, a
+            // new node is written once with its first episode already in — instead of a second pass that loads every node of the path
+            // again.  Every node still sees its additions in iteration order.  (Not when the slab might fill up in this iteration: the
+            // sequential loop then stops before backpropagating.)
+            auto credit = [&](hk_mcts_node& x) {
+                const int up = x.upnext;
+                if (up >= 0 && up < n_scores) x.totalValue += scores[up];
+                x.numEpisodes += 1;
+            };
+            credit(nd);
+            for (int ply = 0; ply < len; ++ply) {
+                const unsigned w = rec[SEQ_REC_HEAD + ply];
+                const int gi = w & 0xff;
+                if (nd.n_legal == 255) nd.n_legal = (unsigned char)((w >> 8) & 0xff);
+                int child;
+                hk_mcts_node ch;
+                if ((nd.child_mask >> gi) & 1ull) {
+                    nodes[node] = nd;                                  // statistics (and possibly nextMoves().Count) changed
+                    child = nd.first_child;
+                    for (;;) {
+                        ch = nodes[child];
+                        if (ch.gen == gi) break;
+                        child = ch.next_sibling;
+                    }
+                } else {
+                    child = n_nodes++;
+                    if (nd.last_child >= 0) nodes[nd.last_child].next_sibling = child; else nd.first_child = child;
+                    nd.last_child = child;
+                    nd.child_mask |= 1ull << gi;
+                    nodes[node] = nd;
+                    ch.child_mask = 0ull; ch.totalValue = 0.0f; ch.numEpisodes = 0; ch.first_child = -1; ch.last_child = -1; ch.next_sibling = -1;
+                    ch.gen = (unsigned char)gi; ch.n_legal = 255; ch.upnext = (signed char)((w >> 16) & 0xff); ch.pad_ = 0;
+                }
+                credit(ch);
+                node = child; nd = ch;
+            }
+            nodes[node] = nd;
+            continue;
+        }
+        int depth = 0;
+        bool dirty = false;
+        path[0] = 0;
+        for (int ply = 0; ply < len; ++ply) {
+            const unsigned w = rec[SEQ_REC_HEAD + ply];
+            if (seq_descend(nodes, node, nd, dirty, (w >> 8) & 0xff, w & 0xff, (int)(signed char)((w >> 16) & 0xff), n_nodes, max_nodes) < 0) { status = 3; break; }
+            path[++depth] = node;                                      // len <= cap <= HK_MAX_PLIES
+        }
+        if (status) break;
+        if (dirty) nodes[node] = nd;
+        seq_backprop(nodes, path, depth, scores, n_scores);
+    }
+    tr.iters = iters; tr.n_nodes = n_nodes; tr.status = status;
+    if (status == 0 && i < count) remaining[t] = (count - i) + todo_after;            // the rest of this call's iterations, sequentially
 }

@@ -561,7 +561,8 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
                 race_mcts_root_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, gp.sectionWindow, gp.timePrecision, (int)nb, dk, dp, pl->roots, pl->nearby,
                                                             pl->root_valid, pl->cycles, mp.mode == 0 ? mp.reuse_cycles : 0, pl->fresh, mp.mode == 1);
                 HK_CUDA_DRAIN(cudaGetLastError());
-                if (mp.mode == 0) rc = mcts_seq_search_device(pl->forest, pl->roots, pl->fresh, budget, seed, pl->best, pl->n_best, nullptr, pl->status, s, false);
+                if (mp.mode == 0) rc = mcts_seq_search_device(pl->forest, pl->roots, pl->fresh, budget, seed, pl->best, pl->n_best, nullptr, pl->status, s, false,
+                                                              pl->karts_per_race * gp.treeSearchDepth);
                 else rc = mcts_search_device(pl->game, pl->roots, (int)nb, budget, mp.rollouts_per_leaf, seed, pl->best, pl->n_best, nullptr, nullptr, nullptr, pl->status, c, s);
                 if (rc) { drain(c); return rc; }
                 pl->pending_step = step + mp.apply_delay;
@@ -1001,7 +1002,8 @@ extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_
                 raceN_mcts_root_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, K, gp.sectionWindow, gp.timePrecision, (int)nb, dk, dp, pl->roots, pl->nearby,
                                                              pl->root_valid, pl->cycles, mp.mode == 0 ? mp.reuse_cycles : 0, pl->fresh, mp.mode == 1);
                 HK_CUDA_DRAIN(cudaGetLastError());
-                if (mp.mode == 0) rc = mcts_seq_search_device(pl->forest, pl->roots, pl->fresh, budget, seed, pl->best, pl->n_best, nullptr, pl->status, s, false);
+                if (mp.mode == 0) rc = mcts_seq_search_device(pl->forest, pl->roots, pl->fresh, budget, seed, pl->best, pl->n_best, nullptr, pl->status, s, false,
+                                                              pl->karts_per_race * gp.treeSearchDepth);
                 else rc = mcts_search_device(pl->game, pl->roots, (int)nb, budget, mp.rollouts_per_leaf, seed, pl->best, pl->n_best, nullptr, nullptr, nullptr, pl->status, c, s);
                 if (rc) { drain(c); return rc; }
                 pl->pending_step = step + mp.apply_delay;

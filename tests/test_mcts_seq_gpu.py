@@ -101,6 +101,49 @@ def test_faithful_search_trees_bit_equal_oracle(hk, oracle, track_name, n_karts,
             assert b["best"][r, k].tobytes() == bytes(s)
 
 
+def test_fast_path_equals_general_kernel_and_hands_over_when_the_root_fills_up(hk, oracle):
+    """The fast path (playouts of a chunk of iterations in parallel, then inserted in order) against the general sequential kernel
+    (HK_SEQ_FAST=0) and the oracle, on roots chosen so that BOTH regimes occur: ordinary roots (20 legal moves: never fully expanded) and
+    roots with the lane-change budget spent on a straight (3 legal moves: fully expanded after a few iterations, after which findLeaf
+    descends by upperConfidenceStrategy and the general kernel must take over mid-call)."""
+    import os
+    track = tracks.OVAL
+    G = mcts.Game(track, 2, 2)
+    OG = _oracle_game(oracle, track, 2, 2)
+    rng = np.random.default_rng(77)
+    roots = _roots(rng, track, 2, 2, [0, 1], 40)
+    for r in range(0, 40, 2):                                          # every other root: on a straight with laneChanges == MaxLaneChanges
+        roots[r] = tracks.root_state(track, int(rng.choice([0, 1, 10, 11, 12, 22])), [int(x) for x in rng.integers(1, 5, 2)], teams=[0, 1],
+                                     tire_age=2500, lane_changes=3, times=[0, int(rng.integers(0, 100))])
+        for i in range(2):
+            roots[r].karts[i].max_velocity = 2
+    its, seed = 150, 4040
+    out = {}
+    for mode in ("1", "0"):
+        os.environ["HK_SEQ_FAST"] = mode
+        try:
+            F = mcts.Forest(G, 40, 1 + 2 * its * 16)
+            a = F.search(roots, its, seed)
+            b = F.search(None, its // 2, 0, fresh=np.zeros(40, np.int32))        # continued: the fast path starts from a grown tree
+            out[mode] = (a, b, [F.nodes(r).tobytes() for r in range(40)])
+        finally:
+            os.environ.pop("HK_SEQ_FAST", None)
+    for k in ("best", "n_best", "n_nodes", "status"):
+        assert out["1"][0][k].tobytes() == out["0"][0][k].tobytes() and out["1"][1][k].tobytes() == out["0"][1][k].tobytes(), k
+    assert out["1"][2] == out["0"][2]
+    full = 0
+    for r in range(40):
+        ot = oracle.Tree(OG, roots[r], key=seed + r)
+        assert ot.search(its) == 0
+        best1 = ot.best_states()
+        assert int(out["1"][0]["n_best"][r]) == len(best1)
+        assert ot.search(its // 2) == 0
+        nodes = np.frombuffer(out["1"][2][r], dtype=abi.MCTS_NODE_DTYPE)
+        _compare_tree(nodes, ot)
+        full += int(bin(int(nodes["child_mask"][0])).count("1") == int(nodes["n_legal"][0]))
+    assert 5 <= full < 40                                              # both regimes were exercised
+
+
 def test_continued_search_equals_one_long_search(hk):
     """Streams are counted over the life of a tree, so constructSearchTree(root) for k more iterations leaves the tree that one call
     with the total would have built (without the best-states walk in between consuming picks: compared through a fresh forest that
