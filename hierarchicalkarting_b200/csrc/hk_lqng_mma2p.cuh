@@ -15,6 +15,11 @@
 //     no placement select and no reciprocal on the pivot chain — one reciprocal per row, all rows in parallel, at the
 //     end.  All rows carry the same cumulative scale, so the test "partial pivoting (MathNet LU, KartLQR.cs:104-105)
 //     would not exchange rows" stays a plain magnitude comparison, done on the high words in the integer pipe.
+// DRAM writes (ncu: 18.7 MB per 65,536-problem launch against 2.4 MB of outputs): 15.7 MB of it is the kernel's own parameter block —
+// lqng_generic_body takes it by reference, so the compiler keeps the 208-byte LqngParams on every thread's local stack (26 STL.64 at entry,
+// 2,368 warps x 32 lanes x 208 B) and reads p.* from there.  Measured alternatives (round 2): `const __grid_constant__` parameter, or a copy
+// made only in the rare path — both bring the writes down to 4.9 MB and both are SLOWER (4.34e8 vs 4.52e8 solves/s): the parameter fields
+// then live in registers and the 128-register budget spills inside the recursion.  The stack copy is a once-per-thread cost and stays.
 // A problem whose coupled system needs row exchanges is solved a second time by the same warp with `pivot` set: the 4x4
 // system [LHS | I | RHSVec] is then dealt one column per lane and reduced by Gauss-Jordan with partial pivoting (same
 // pivot choice as MathNet's LU: first largest magnitude at or below the diagonal), everything else (all DMMA products)
