@@ -22,6 +22,13 @@ def rollout_shard(n_rollouts: int, rank: int, world: int) -> tuple[int, int]:
     return lo, hi - lo
 
 
+def tree_shard(n_trees: int, seed: int, rank: int, world: int) -> tuple[int, int, int]:
+    """(first tree, count, seed to pass) for hk_mcts_forest_search / hk_mcts_search_seq_batch on this rank: tree r of a call gets Philox key
+    seed + r, so a rank that searches the global trees [lo, hi) passes seed + lo and every tree keeps the key it has in a one-rank call."""
+    lo, hi = shard_range(n_trees, rank, world)
+    return lo, hi - lo, (seed + lo) & 0xFFFFFFFFFFFFFFFF
+
+
 def gather_sum(dist, summary, device=None):
     """Final gather of per-rank summaries: all_gather + sum (summaries are KB-sized; latency-bound, not bandwidth-bound)."""
     import torch

@@ -45,6 +45,23 @@ part = g.rollouts(leaf, cnt, mode=0, seed=20260003, rollout_offset=off)
 summary = np.concatenate([part["visit"].astype(np.float64), part["reward_sum"].ravel(), [part["plies"]]])
 tot = sharding.gather_sum(dist, summary)
 t = sharding.max_over_ranks(dist, 1.0 + rank)
+# the sequential tree search shards over trees: a rank passes seed + first tree, so every tree keeps the key of the one-rank call
+import ctypes
+from oracle import structs as OS
+n_trees, iters, seed = 23, 40, 777
+roots = np.zeros(n_trees, dtype=OS.GAME_STATE_DTYPE)
+for r in range(n_trees):
+    st = tracks.root_state(track, r, [1 + r % 4, 1 + (r + 1) % 4], teams=[0, 1], tire_age=2500, times=[0, 5 * r])
+    roots[r] = np.frombuffer(bytes(st), dtype=OS.GAME_STATE_DTYPE)[0]
+lo, cnt_t, seed_r = sharding.tree_shard(n_trees, seed, rank, world)
+mine = O.tree_search_batch(g, roots[lo:lo + cnt_t], iters, seed=seed_r, mode=0, threads=1)
+digest = np.zeros(n_trees)
+digest[lo:lo + cnt_t] = [float(np.frombuffer(mine["best"][k].tobytes(), dtype=np.uint8).astype(np.float64).sum() + 1000.0 * mine["n_nodes"][k]) for k in range(cnt_t)]
+digest_all = sharding.gather_sum(dist, digest)
+if rank == 0:
+    one = O.tree_search_batch(g, roots, iters, seed=seed, mode=0, threads=1)
+    want = [float(np.frombuffer(one["best"][k].tobytes(), dtype=np.uint8).astype(np.float64).sum() + 1000.0 * one["n_nodes"][k]) for k in range(n_trees)]
+    assert np.array_equal(digest_all, np.array(want)), "sharded tree searches differ from the one-rank call"
 if rank == 0:
     whole = g.rollouts(leaf, total, mode=0, seed=20260003, rollout_offset=0)
     ref = np.concatenate([whole["visit"].astype(np.float64), whole["reward_sum"].ravel(), [whole["plies"]]])
