@@ -148,6 +148,7 @@ PROTOTYPES = {
     "hk_lqng_solve_batch_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 11 + [C.c_void_p]),
     "hk_lqng_solve_one": (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "hk_lqng_assemble_solve_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "hk_lqng_assemble_solve_packed": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _ip]),
     "hk_game_create": (C.c_int, [C.POINTER(hk_section), C.c_int, C.POINTER(hk_kart), C.c_int, C.POINTER(hk_kart), C.c_int,
                                  C.POINTER(hk_game_params), C.POINTER(C.c_void_p)]),
     "hk_game_destroy": (None, [C.c_void_p]),

@@ -420,3 +420,62 @@ extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizo
     drain_guard.ok = true;
     return HK_OK;
 }
+
+// The same call with the seven arrays interleaved per problem (include/hk_abi.h): ONE host-to-device copy per chunk instead of seven — the
+// copy engine's per-copy cost, not the host's issue rate, was what kept the seven-array pipeline above its PCIe floor — and one TMA bulk copy
+// per problem in the 2-kart solve kernel instead of seven.  Same chunk pipeline: copies on dedicated streams, assembly + solve + D2H of chunk
+// k on compute stream k & 1 behind the chunk's "copied in" event, a ring of four chunk buffers.
+extern "C" int hk_lqng_assemble_solve_packed(int batch, int n_players, int horizon, double dt, const double* records, double* u0, int* status)
+{
+    const int N = n_players;
+    if (batch < 0 || N < 1 || N > HK_MAX_PLAYERS || horizon < 0 || horizon > HK_MAX_HORIZON) { set_error("hk_lqng_assemble_solve_packed: invalid dimensions"); return HK_ERR_INVALID_ARGUMENT; }
+    if (batch > 0 && (!records || !u0)) { set_error("hk_lqng_assemble_solve_packed: null operand"); return HK_ERR_INVALID_ARGUMENT; }
+    if (batch == 0) return HK_OK;
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    struct DrainOnError { ThreadCtx* c; bool ok = false; ~DrainOnError() { if (!ok) drain_ctx(c); } } drain_guard{c};
+    const int K = N - 1, m = 2 * N, P = 13 * N + 9 * N * K;
+    static const int chunks_env = getenv("HK_E2E_CHUNKS") ? atoi(getenv("HK_E2E_CHUNKS")) : 0;
+    constexpr int RING = 4;
+    int nchunks = batch >= 16384 ? (chunks_env > 0 ? chunks_env : (batch >= 65536 ? 8 : batch / 8192)) : 1;
+    const int by_size = (int)(((long long)batch + 65535) / 65536);
+    if (nchunks < by_size) nchunks = by_size;
+    const int chunk = ((batch + nchunks - 1) / nchunks + 1) & ~1;
+    const size_t slot_bytes = ((((size_t)P + m) * sizeof(double) + sizeof(int)) * (size_t)chunk + 255) & ~(size_t)255;
+    const int ring = nchunks < RING ? nchunks : RING;
+    char* dring = (char*)dscratch(c, 4, slot_bytes * ring);
+    if (!dring) return HK_ERR_OUT_OF_MEMORY;
+    static const int trig_slot[RING] = {5, 7, 10, 11};
+    {
+        const size_t n = 4 * (size_t)N, dense = (size_t)N * 16 + N * 8 + N * n * n + N * n + N * 4 + n;
+        for (int r = 0; r < ring; ++r)
+            if (!dscratch(c, trig_slot[r], sizeof(double) * (N == 2 ? 4 : dense + P) * (size_t)chunk)) return HK_ERR_OUT_OF_MEMORY;
+    }
+    cudaStream_t compute[2] = {c->stream, c->stream2};
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int b0 = ci * chunk, nb = (b0 + chunk <= batch) ? chunk : batch - b0;
+        if (nb <= 0) break;
+        const int r = ci % ring;
+        cudaStream_t cs = nchunks > 1 ? c->cstream[ci % 4] : compute[0];
+        cudaStream_t s = compute[ci & 1];
+        double* drec = (double*)(dring + slot_bytes * r);
+        double* du = drec + (size_t)P * chunk;
+        int* dst = (int*)(du + (size_t)m * chunk);
+        if (ci >= ring) HK_CUDA(cudaStreamWaitEvent(cs, c->pev[8 + r], 0));                       // the slot's previous tenant has drained
+        // one plain copy per chunk; cudaMemcpyBatchAsync for it (whole or split in four) measured the same (0.550 / 0.558 / 0.553 ms per call)
+        HK_CUDA(cudaMemcpyAsync(drec, records + (size_t)P * b0, sizeof(double) * P * nb, cudaMemcpyHostToDevice, cs));
+        if (nchunks > 1) {
+            HK_CUDA(cudaEventRecord(c->pev[r], cs));
+            HK_CUDA(cudaStreamWaitEvent(s, c->pev[r], 0));
+        }
+        int rc = lqng_assemble_launch_packed(nb, N, horizon, dt, drec, du, dst, s, trig_slot[r]);
+        if (rc) return rc;
+        HK_CUDA(cudaMemcpyAsync(u0 + (size_t)m * b0, du, sizeof(double) * m * nb, cudaMemcpyDeviceToHost, s));
+        if (status) HK_CUDA(cudaMemcpyAsync(status + b0, dst, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+        if (ci + ring < nchunks) HK_CUDA(cudaEventRecord(c->pev[8 + r], s));
+    }
+    HK_CUDA(cudaStreamSynchronize(c->stream));
+    HK_CUDA(cudaStreamSynchronize(c->stream2));
+    drain_guard.ok = true;
+    return HK_OK;
+}

@@ -457,11 +457,11 @@ static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact, bool fu
 
 // (cos h, sin h) of every player: the one transcendental of the assembly, evaluated one thread per player (a warp of the
 // solve kernel would spend a whole sincos instruction sequence on two useful lanes)
-__global__ void lqng_trig_kernel(long long n_players_total, const double* __restrict__ x0, double* __restrict__ cs)
+__global__ void lqng_trig_kernel(long long n_players_total, const double* __restrict__ x0, double* __restrict__ cs, int N = 1, long long stride = 4)
 {
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n_players_total) return;
-    const double h = x0[id * 4 + 3];
+    const double h = x0[(id / N) * stride + (id % N) * 4 + 3];      // stride: doubles between the x0 blocks of consecutive problems
     cs[id * 2] = cos(h);
     cs[id * 2 + 1] = sin(h);
 }
@@ -499,6 +499,56 @@ int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double*
                                                                               dA, dB, dQ, dq, dR, dx, dn_players);
     HK_CUDA(cudaGetLastError());
     return lqng_launch(batch, N, horizon, 0, dA, dB, dQ, dq, dR, dx, du0, nullptr, nullptr, nullptr, dstatus, stream);
+}
+
+// packed record [x0 N x 4 | target N x 4 | tw N x 4 | cw N | aw N x K x 2 | otgt N x K x 4 | otw N x K x 3] -> the seven arrays
+__global__ void lqng_unpack_kernel(int batch, int N, const double* __restrict__ rec, double* x0, double* target, double* tw, double* cw, double* aw,
+                                   double* otgt, double* otw)
+{
+    const int K = N - 1, P = 13 * N + 9 * N * K;
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)batch * P) return;
+    const long long b = id / P;
+    int e = (int)(id % P);
+    const double v = rec[id];
+    if (e < 4 * N) { x0[b * 4 * N + e] = v; return; } e -= 4 * N;
+    if (e < 4 * N) { target[b * 4 * N + e] = v; return; } e -= 4 * N;
+    if (e < 4 * N) { tw[b * 4 * N + e] = v; return; } e -= 4 * N;
+    if (e < N) { cw[b * N + e] = v; return; } e -= N;
+    if (e < 2 * N * K) { aw[b * 2 * N * K + e] = v; return; } e -= 2 * N * K;
+    if (e < 4 * N * K) { otgt[b * 4 * N * K + e] = v; return; } e -= 4 * N * K;
+    otw[b * 3 * N * K + e] = v;
+}
+
+int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const double* drec, double* du0, int* dstatus, cudaStream_t stream,
+                                int scratch_slot)
+{
+    ThreadCtx* c = ctx();
+    if (!c) return HK_ERR_NO_DEVICE;
+    if (batch == 0) return HK_OK;
+    const int K = N - 1, P = 13 * N + 9 * N * K;
+    if (N == 2 && (reinterpret_cast<uintptr_t>(drec) & 15) == 0) {
+        // 2-kart game: the solve kernel stages each 352-byte record with ONE bulk copy (+ the (cos h, sin h) pairs) and assembles in shared memory
+        double* dcs = (double*)dscratch(c, scratch_slot, sizeof(double) * 4 * (size_t)batch);
+        if (!dcs) return HK_ERR_OUT_OF_MEMORY;
+        const long long np = (long long)batch * 2;
+        count_launch(); lqng_trig_kernel<<<(unsigned)((np + 255) / 256), 256, 0, stream>>>(np, drec, dcs, 2, P);
+        HK_CUDA(cudaGetLastError());
+        LqngParams p{batch, horizon, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, du0, nullptr, nullptr, nullptr, dstatus,
+                     nullptr, nullptr, nullptr, nullptr, drec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dcs, dt};
+        return launch_mma2p(p, stream, true);
+    }
+    const int n = 4 * N;
+    const size_t dense = (size_t)N * 16 + N * 8 + (size_t)N * n * n + (size_t)N * n + N * 4 + n;
+    double* d = (double*)dscratch(c, scratch_slot, (dense + P) * sizeof(double) * (size_t)batch);
+    if (!d) return HK_ERR_OUT_OF_MEMORY;
+    double* u = d + dense * (size_t)batch;                          // the seven arrays behind the dense records lqng_assemble_launch builds in the same slot
+    double *ux0 = u, *utg = ux0 + (size_t)batch * 4 * N, *utw = utg + (size_t)batch * 4 * N, *ucw = utw + (size_t)batch * 4 * N,
+           *uaw = ucw + (size_t)batch * N, *uot = uaw + (size_t)batch * 2 * N * K, *uow = uot + (size_t)batch * 4 * N * K;
+    const long long threads = (long long)batch * P;
+    count_launch(); lqng_unpack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(batch, N, drec, ux0, utg, utw, ucw, uaw, uot, uow);
+    HK_CUDA(cudaGetLastError());
+    return lqng_assemble_launch(batch, N, horizon, dt, ux0, utg, utw, ucw, uaw, uot, uow, du0, dstatus, stream, scratch_slot);
 }
 
 int lqng_launch(int batch, int N, int horizon, int time_varying, const double* dA, const double* dB, const double* dQ,

@@ -136,6 +136,12 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of this buffer come first
         if (COMPACT) {
             const unsigned sd = stage_u32 + (unsigned)(b * C2_STRIDE * 8);
+            if (!p.c_target) {                                       // packed records (hk_lqng_assemble_solve_packed): the staged layout IS the record
+                mbar_expect_tx(bar, C2_TX_BYTES);
+                bulk_g2s(sd, p.c_x0 + (size_t)prob * C2_ocs, C2_ocs * 8, bar);           // 352 B: x0 | target | tw | cw | aw | otgt | otw
+                bulk_g2s(sd + C2_ocs * 8, p.c_cs + (size_t)prob * 4, 32, bar);
+                return;
+            }
             mbar_expect_tx(bar, C2_TX_BYTES);
             bulk_g2s(sd + C2_ox * 8, p.c_x0 + (size_t)prob * 8, 64, bar);
             bulk_g2s(sd + C2_otg * 8, p.c_target + (size_t)prob * 8, 64, bar);

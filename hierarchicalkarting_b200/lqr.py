@@ -198,3 +198,24 @@ def assemble_solve_batch(prob: dict, horizon: int):
     abi.check(lib.hk_lqng_assemble_solve_batch(batch, N, int(horizon), float(prob["dt"]), abi.dptr(x0),
                                                *[abi.dptr(a) for a in arrs], abi.dptr(u0), abi.iptr(status)))
     return dict(u0=u0, status=status)
+
+
+def pack_records(prob: dict) -> np.ndarray:
+    """The packed form of a compact problem dict: [batch][13 N + 9 N (N-1)] doubles, fields in the order x0 | target | tw | cw | aw |
+    otgt | otw (hk_lqng_assemble_solve_packed)."""
+    x0 = np.asarray(prob["x0"], dtype=np.float64)
+    batch = x0.shape[0]
+    parts = [np.asarray(prob[k], dtype=np.float64).reshape(batch, -1) for k in ("x0", "target", "tw", "cw", "aw", "otgt", "otw")]
+    return np.ascontiguousarray(np.concatenate(parts, axis=1))
+
+
+def assemble_solve_packed(records: np.ndarray, n_players: int, horizon: int, dt: float, u0: np.ndarray | None = None,
+                          status: np.ndarray | None = None):
+    """hk_lqng_assemble_solve_packed on packed records (pack_records)."""
+    records = np.ascontiguousarray(records, dtype=np.float64)
+    batch = records.shape[0]
+    u0 = np.empty((batch, 2 * n_players)) if u0 is None else u0
+    status = np.zeros(batch, dtype=np.int32) if status is None else status
+    abi.check(abi.load_library().hk_lqng_assemble_solve_packed(batch, n_players, int(horizon), float(dt), abi.dptr(records), abi.dptr(u0),
+                                                               abi.iptr(status)))
+    return dict(u0=u0, status=status)

@@ -119,6 +119,12 @@ int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizon, double d
                                  const double* aw, const double* otgt, const double* otw,
                                  double* u0, int* status);
 
+/* The same call with the seven arrays interleaved per problem — one record of 13 N + 9 N (N-1) doubles (352 bytes for N = 2):
+ *   records [batch][ x0 N x 4 | target N x 4 | tw N x 4 | cw N | aw N x (N-1) x 2 | otgt N x (N-1) x 4 | otw N x (N-1) x 3 ]
+ * (what a C# caller fills as an array of blittable structs).  One host-to-device copy per chunk of the batch instead of seven, and one TMA
+ * bulk copy per problem in the 2-kart kernel: the end-to-end form of the call when the host is the bottleneck. */
+int hk_lqng_assemble_solve_packed(int batch, int n_players, int horizon, double dt, const double* records, double* u0, int* status);
+
 /* ---- discrete race game + leaf-parallel rollouts ------------------------------------------------------------ */
 typedef struct hk_section {      /* DiscretePositionTracker.cs:35-40 */
     float   insideR;             /* trackInsideRadius (0 => straight, :197) */

@@ -272,6 +272,24 @@ def test_assemble_on_device(hk, oracle):
             assert rel_err(got["u0"][b], ref["u0"][b]) <= TOL
 
 
+def test_packed_records_equal_the_seven_array_call(hk, oracle):
+    """hk_lqng_assemble_solve_packed (one interleaved record per problem: one H2D copy per chunk, one TMA bulk copy per problem in the
+    2-kart kernel) returns bit for bit what hk_lqng_assemble_solve_batch returns, for every player count, ragged sizes and the multi-chunk
+    pipeline (131,075 two-kart problems: 9 chunks through the ring of four), and agrees with the oracle."""
+    for N, track, batch in ((2, S.OVAL, 301), (4, S.COMPLEX, 300), (1, S.OVAL, 77), (3, S.COMPLEX, 130), (2, S.OVAL, 131075)):
+        p = S.make_problems(track, batch, N, seed=78)
+        a = lqr.assemble_solve_batch(p, 3)
+        rec = lqr.pack_records(p)
+        assert rec.shape == (batch, 13 * N + 9 * N * (N - 1))
+        b = lqr.assemble_solve_packed(rec, N, 3, p["dt"])
+        assert np.array_equal(a["u0"], b["u0"]) and np.array_equal(a["status"], b["status"]), (N, batch)
+        idx = np.arange(0, batch, max(1, batch // 200))
+        sub = {k: (v[idx] if isinstance(v, np.ndarray) and v.shape[:1] == (batch,) else v) for k, v in p.items()}
+        ref = oracle.lqng_solve_batch(*S.assemble_dense(sub), 3, full=False)
+        for k, i in enumerate(idx):
+            assert rel_err(b["u0"][i], ref["u0"][k]) <= TOL
+
+
 def test_assemble_pipeline_chunks_and_ring(hk, oracle):
     """hk_lqng_assemble_solve_batch at sizes that exercise its chunk pipeline: 2 chunks (20,001 problems, odd), 8 chunks over a ring of
     4 chunk buffers with reuse waits (70,001 problems), pageable and pinned caller buffers; every problem against the dense DMMA path
