@@ -56,12 +56,22 @@ __device__ __forceinline__ void plan_target(const DevTrack* t, const hk_race_par
 }
 
 // One thread per problem b = 2 race + ego; player 0 = ego, player 1 = the other kart (HKA:702).
+// packed != nullptr: the description goes out as ONE 44-double record per problem (x0 | target | tw | cw | aw | otgt | otw, the layout of
+// hk_lqng_assemble_solve_packed) that the solve kernel stages with one bulk copy; else into the seven arrays.
 __global__ void race_recipe_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_problems, const hk_race_kart* __restrict__ karts,
-                                   const hk_race_plan* __restrict__ plans, double* x0, double* target, double* tw, double* cw, double* aw,
-                                   double* otgt, double* otw)
+                                   const hk_race_plan* __restrict__ plans, double* x0_, double* target_, double* tw_, double* cw_, double* aw_,
+                                   double* otgt_, double* otw_, double* packed = nullptr)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_problems) return;
+    double* const rec = packed ? packed + (size_t)b * 44 : nullptr;
+    double* const x0 = packed ? rec - (size_t)b * 8 : x0_;               // biased so that the indexing below (base + b * width) lands in the record
+    double* const target = packed ? rec + 8 - (size_t)b * 8 : target_;
+    double* const tw = packed ? rec + 16 - (size_t)b * 8 : tw_;
+    double* const cw = packed ? rec + 24 - (size_t)b * 2 : cw_;
+    double* const aw = packed ? rec + 26 - (size_t)b * 4 : aw_;
+    double* const otgt = packed ? rec + 30 - (size_t)b * 8 : otgt_;
+    double* const otw = packed ? rec + 38 - (size_t)b * 6 : otw_;
     const int e = b & 1;
     const hk_race_kart* pair = karts + (b - e);
     const hk_race_plan* plan = plans + b;
@@ -576,9 +586,9 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
             }
         }
         count_launch();
-        race_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp, dx0, dtg, dtw, dcw, daw, dot, dow);
+        race_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dx0);
         HK_CUDA_DRAIN(cudaGetLastError());
-        rc = lqng_assemble_launch((int)nb, 2, p->horizon, p->dt, dx0, dtg, dtw, dcw, daw, dot, dow, du, dst, s, 9);
+        rc = lqng_assemble_launch_packed((int)nb, 2, p->horizon, p->dt, dx0, du, dst, s, 9);    // dx0: 44-double records (the seven arrays' space)
         if (rc) { drain(c); return rc; }
         count_launch();
         race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp, pl ? pl->root_valid : nullptr, pl ? pl->cycles : nullptr);
