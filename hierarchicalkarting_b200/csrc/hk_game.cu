@@ -1501,27 +1501,22 @@ extern "C" int hk_mcts_search_seq_batch(const hk_game* g, const hk_game_state* r
     if (rc) return rc;
     rc = hk_mcts_forest_search(f, roots, nullptr, iterations, seed, best_states, n_best, n_nodes, nullptr);
     if (rc == HK_OK && (root_gen || root_episodes || root_values)) {
-        // the root's children in insertion order: walk each tree's child list on the host from its first (at most HK_MAX_ACTIONS + 1) records' links
-        std::vector<hk_mcts_node> buf;
-        for (int r = 0; r < n_roots && rc == HK_OK; ++r) {
-            hk_mcts_node root;
-            cudaError_t e = cudaMemcpy(&root, f->slabs + (size_t)r * f->max_nodes, sizeof(root), cudaMemcpyDeviceToHost);
-            int j = 0;
-            for (int c = root.first_child; e == cudaSuccess && c >= 0 && j < HK_MAX_ACTIONS; ++j) {
-                hk_mcts_node ch;
-                e = cudaMemcpy(&ch, f->slabs + (size_t)r * f->max_nodes + c, sizeof(ch), cudaMemcpyDeviceToHost);
-                if (root_gen) root_gen[(size_t)r * HK_MAX_ACTIONS + j] = ch.gen;
-                if (root_episodes) root_episodes[(size_t)r * HK_MAX_ACTIONS + j] = ch.numEpisodes;
-                if (root_values) root_values[(size_t)r * HK_MAX_ACTIONS + j] = ch.totalValue;
-                c = ch.next_sibling;
-            }
-            for (; j < HK_MAX_ACTIONS; ++j) {
-                if (root_gen) root_gen[(size_t)r * HK_MAX_ACTIONS + j] = -1;
-                if (root_episodes) root_episodes[(size_t)r * HK_MAX_ACTIONS + j] = 0;
-                if (root_values) root_values[(size_t)r * HK_MAX_ACTIONS + j] = 0.0f;
-            }
-            if (e != cudaSuccess) { set_error("hk_mcts_search_seq_batch: %s", cudaGetErrorString(e)); rc = HK_ERR_CUDA; }
+        // the root's children in insertion order, gathered on the device (one thread per tree), three copies back
+        const size_t cnt = (size_t)n_roots * HK_MAX_ACTIONS;
+        int* d_gen = nullptr;
+        cudaError_t e = cudaMalloc(&d_gen, cnt * 12);
+        if (e == cudaSuccess) {
+            int* d_ep = d_gen + cnt;
+            float* d_val = reinterpret_cast<float*>(d_ep + cnt);
+            count_launch();
+            seq_root_children_kernel<<<(unsigned)((n_roots + 127) / 128), 128>>>(f->slabs, f->max_nodes, n_roots, d_gen, d_ep, d_val);
+            e = cudaGetLastError();
+            if (e == cudaSuccess && root_gen) e = cudaMemcpy(root_gen, d_gen, cnt * 4, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && root_episodes) e = cudaMemcpy(root_episodes, d_ep, cnt * 4, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && root_values) e = cudaMemcpy(root_values, d_val, cnt * 4, cudaMemcpyDeviceToHost);
+            cudaFree(d_gen);
         }
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("hk_mcts_search_seq_batch: %s", cudaGetErrorString(e)); rc = e == cudaErrorMemoryAllocation ? HK_ERR_OUT_OF_MEMORY : HK_ERR_CUDA; }
     }
     hk_mcts_forest_destroy(f);
     return rc;

@@ -409,3 +409,26 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
     tr.iters = iters; tr.n_nodes = n_nodes; tr.status = status;
     if (status == 0 && i < count) remaining[t] = (count - i) + todo_after;            // the rest of this call's iterations, sequentially
 }
+
+// root children of every tree in insertion order (generation index, numEpisodes, totalValue; -1 / 0 / 0 past the last child):
+// what hk_mcts_search_seq_batch reports beside the best states
+__global__ void seq_root_children_kernel(const hk_mcts_node* __restrict__ slabs, int max_nodes, int n_trees, int* __restrict__ gen,
+                                         int* __restrict__ episodes, float* __restrict__ values)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    const hk_mcts_node* nodes = slabs + (size_t)t * max_nodes;
+    int j = 0;
+    for (int c = nodes[0].first_child; c >= 0 && j < HK_MAX_ACTIONS; ++j) {
+        const hk_mcts_node ch = nodes[c];
+        gen[(size_t)t * HK_MAX_ACTIONS + j] = ch.gen;
+        episodes[(size_t)t * HK_MAX_ACTIONS + j] = ch.numEpisodes;
+        values[(size_t)t * HK_MAX_ACTIONS + j] = ch.totalValue;
+        c = ch.next_sibling;
+    }
+    for (; j < HK_MAX_ACTIONS; ++j) {
+        gen[(size_t)t * HK_MAX_ACTIONS + j] = -1;
+        episodes[(size_t)t * HK_MAX_ACTIONS + j] = 0;
+        values[(size_t)t * HK_MAX_ACTIONS + j] = 0.0f;
+    }
+}

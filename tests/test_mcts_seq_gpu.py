@@ -263,3 +263,76 @@ def test_game_golden_fixture_on_device(hk):
             assert np.array_equal(res[k], G[f"{name}_search_{k}"]), k
         assert res["best"].tobytes() == G[f"{name}_search_best"].tobytes()
         assert np.array_equal(res["root_values"].view(np.uint32), G[f"{name}_search_root_values"].view(np.uint32))
+
+
+def test_edge_cases(hk, oracle):
+    """The corners the reference's callers can reach (and the ABI's argument checks): zero iterations (best states of a bare root), roots one
+    section before the end of the search window (one-ply games for every kart), a root that is already terminal (a tree of one node that
+    collects every episode), a node slab that is too small (status 3, the tree
+    stays consistent and no neighbour is touched), invalid arguments."""
+    track = tracks.OVAL
+    G = mcts.Game(track, 2, 2)
+    OG = _oracle_game(oracle, track, 2, 2)
+    rng = np.random.default_rng(2)
+    roots = _roots(rng, track, 2, 2, [0, 1], 8)
+    # zero iterations
+    F = mcts.Forest(G, 8, 64)
+    out = F.search(roots, 0, 5)
+    for r in range(8):
+        ot = oracle.Tree(OG, roots[r], key=5 + r)
+        assert ot.search(0) == 0
+        ob = ot.best_states()
+        assert int(out["n_best"][r]) == len(ob) and int(out["n_nodes"][r]) == ot.size == 1 and int(out["status"][r]) == 0
+    # one section left for every kart: playouts of n_karts plies
+    near = []
+    for st in roots:
+        s2 = abi.hk_game_state.from_buffer_copy(bytes(st))
+        s2.finalSection = s2.lastCompletedSection + 1
+        near.append(s2)
+    out = F.search(near, 40, 6)
+    for r in range(8):
+        ot = oracle.Tree(OG, near[r], key=6 + r)
+        assert ot.search(40) == 0
+        _compare_tree(F.nodes(r), ot)
+        ob = ot.best_states()
+        assert int(out["n_best"][r]) == len(ob)
+        for j, s_ in enumerate(ob):
+            assert bytes(s_) == out["best"][r, j].tobytes()
+    # a terminal root
+    done = []
+    for st in roots:
+        s2 = abi.hk_game_state.from_buffer_copy(bytes(st))
+        s2.finalSection = s2.lastCompletedSection
+        for k in range(2):
+            s2.karts[k].section = s2.lastCompletedSection
+        done.append(s2)
+    out = F.search(done, 3, 1)                                       # isOver() at once: simulate returns the root, which collects the episodes
+    for r in range(8):
+        ot = oracle.Tree(OG, done[r], key=1 + r)
+        assert ot.search(3) == 0 and ot.size == 1
+        _compare_tree(F.nodes(r), ot)
+        assert int(out["n_best"][r]) == len(ot.best_states()) == 0 and int(out["status"][r]) == 0
+    # slab too small: 8 trees x 20 nodes, 50 iterations
+    F2 = mcts.Forest(G, 8, 20)
+    fresh = np.ones(8, np.int32)
+    out = F2.search(roots, 50, 7, fresh=fresh)
+    assert np.all(out["status"] == 3) and np.all(out["n_nodes"] <= 20)
+    for r in range(8):
+        nd = F2.nodes(r)
+        ot = oracle.Tree(OG, roots[r], key=7 + r)
+        done_it = int(nd["numEpisodes"][0])                          # the iterations that fitted are exactly the oracle's first ones;
+        assert 0 < done_it < 50 and ot.search(done_it) == 0          # the one that did not left its first nodes behind, without episodes
+        d = ot.dump()
+        assert ot.size <= len(nd) <= 20 and np.array_equal(nd["numEpisodes"][:ot.size], d["numEpisodes"]) and not nd["numEpisodes"][ot.size:].any()
+        assert _same_bits(nd["totalValue"][:ot.size], d["totalValue"])
+    # arguments
+    lib = abi.load_library()
+    assert lib.hk_mcts_forest_search(None, None, None, 1, 0, None, None, None, None) == abi.HK_ERR_INVALID_ARGUMENT
+    with pytest.raises(abi.HKError):
+        mcts.Forest(G, 0, 10)
+    with pytest.raises(abi.HKError):
+        F.search(roots, -1, 0)
+    bad = abi.hk_game_state.from_buffer_copy(bytes(roots[0]))
+    bad.n_karts = 3                                                  # a state of another game
+    with pytest.raises(abi.HKError):
+        F.search([bad] + roots[1:], 1, 0)
