@@ -748,7 +748,8 @@ __device__ int ucs_pick(const TreeNode* nodes, int node, unsigned long long key,
 
 constexpr int TREE_THREADS = 128;
 
-__global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ roots,
+template <int MINB>
+__global__ void __launch_bounds__(TREE_THREADS, MINB) tree_search_kernel(const DevGame* __restrict__ gg, const hk_game_state* __restrict__ roots,
                                                                    int iterations, int R, unsigned long long seed, int root_base, int max_nodes,
                                                                    TreeNode* __restrict__ slabs, hk_game_state* __restrict__ best_out,
                                                                    int* __restrict__ n_best_out, int* __restrict__ root_episodes,
@@ -761,6 +762,8 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
     __shared__ double s_rsum[HK_MAX_ACTIONS][HK_MAX_KARTS];
     __shared__ float s_w[HK_MAX_ACTIONS];
     __shared__ int s_leaf, s_cnt, s_first, s_nnodes, s_stop, s_err;
+    __shared__ RootMoves s_root;
+    __shared__ unsigned long long s_rkeys[HK_MAX_KARTS][HK_MAX_ACTIONS];
     {
         const int* src = reinterpret_cast<const int*>(gg);
         int* dst = reinterpret_cast<int*>(&g);
@@ -776,6 +779,29 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
         r.st = roots[root]; r.total = 0.0; r.episodes = 0; r.parent = -1; r.first_child = -1; r.n_children = 0;
         r.upnext = up_next(r.st);
         s_nnodes = 1; s_stop = 0; s_err = 0; s_leaf = 0;
+    }
+    __syncthreads();
+    // The root's children still hold the root's state for every kart but the mover, and a root kart usually stands at the (0, bucket)
+    // velocity bucket (quirk B.6-1) that the tables do not cover: its policy-ordered legal list is the same in every rollout of
+    // iteration 0 (see RootMoves), so it is built once per tree instead of once per rollout.
+    if (threadIdx.x < HK_MAX_KARTS) {
+        const int k = threadIdx.x;
+        const hk_game_state& st = nodes[0].st;
+        int cnt = -1;
+        if (k < st.n_karts && k != nodes[0].upnext) {
+            const int lvl = (g.tables_ok && st.karts[k].player == 0) ? velocity_level(g, st.karts[k].min_velocity, st.karts[k].max_velocity) : -1;
+            if (lvl < 0) cnt = legal_moves(g, st, k, s_rkeys[k]);
+        }
+        s_root.cnt[k] = cnt;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < HK_MAX_KARTS * HK_MAX_ACTIONS; e += blockDim.x) {
+        const int k = e / HK_MAX_ACTIONS, c = e % HK_MAX_ACTIONS;
+        if (s_root.cnt[k] > 0 && c < g.n_cand && s_rkeys[k][c] != ~0ull) {
+            int rank = 0;
+            for (int j = 0; j < g.n_cand; ++j) rank += s_rkeys[k][j] < s_rkeys[k][c];
+            s_root.order[k][rank] = (unsigned char)c;
+        }
     }
     __syncthreads();
     for (int it = 0; it < iterations; ++it) {
@@ -853,7 +879,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 8) tree_search_kernel(const DevG
             float scores[2 * HK_MAX_KARTS];
             int ns, first_gi;
             const int plies = rollout<false>(g, nodes[first + j].st, rseed, offset + (unsigned long long)j * R + r, scores, ns, first_gi,
-                                             nullptr, nullptr, nullptr);
+                                             nullptr, nullptr, leaf == 0 ? &s_root : nullptr);
             if (plies < 0) { s_err = 1; continue; }
             if (plies == 0) continue;                                            // the child is terminal: handled below
             atomicAdd(&s_vis[j], 1u);
@@ -1255,9 +1281,12 @@ int mcts_search_device(const hk_game* g, const hk_game_state* d_roots, int n_roo
     for (int base = 0; base < n_roots; base += chunk) {
         const int nr = base + chunk <= n_roots ? chunk : n_roots - base;
         count_launch();
-        tree_search_kernel<<<(unsigned)nr, TREE_THREADS, 0, s>>>(g->dev, d_roots + base, iterations, rollouts_per_leaf, seed, base, max_nodes, slabs,
-            d_best + (size_t)base * HK_MCTS_MAX_SEQ, d_nbest + base, d_eps ? d_eps + (size_t)base * HK_MAX_ACTIONS : nullptr,
-            d_vals ? d_vals + (size_t)base * HK_MAX_ACTIONS : nullptr, d_nnodes ? d_nnodes + base : nullptr, d_status + base);
+        static const int minb = getenv("HK_TREE_MINB") ? atoi(getenv("HK_TREE_MINB")) : 8;
+#define HK_TREE_LAUNCH(M) tree_search_kernel<M><<<(unsigned)nr, TREE_THREADS, 0, s>>>(g->dev, d_roots + base, iterations, rollouts_per_leaf, seed, base, max_nodes, slabs, \
+            d_best + (size_t)base * HK_MCTS_MAX_SEQ, d_nbest + base, d_eps ? d_eps + (size_t)base * HK_MAX_ACTIONS : nullptr,                           \
+            d_vals ? d_vals + (size_t)base * HK_MAX_ACTIONS : nullptr, d_nnodes ? d_nnodes + base : nullptr, d_status + base)
+        if (minb == 6) HK_TREE_LAUNCH(6); else if (minb == 5) HK_TREE_LAUNCH(5); else if (minb == 7) HK_TREE_LAUNCH(7); else HK_TREE_LAUNCH(8);
+#undef HK_TREE_LAUNCH
         HK_CUDA(cudaGetLastError());
     }
     return HK_OK;

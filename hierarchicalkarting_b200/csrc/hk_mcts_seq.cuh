@@ -294,6 +294,11 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
 // time, backpropagate (seq_insert_kernel: no game arithmetic, ~30 instructions per ply).  The moment a root IS fully expanded (few legal
 // moves), the tree leaves the fast path: remaining[t] counts the iterations the general kernel above still has to run for it.  The node
 // records, counters and float32 sums come out bit-equal to the sequential kernel's (tests/test_mcts_seq_gpu.py runs both).
+// Measured and rejected (round 2, 32,768 trees x 512 iterations, insertion 14.0 ms): (a) the insertion as ONE flat loop per lane (one node load
+// per trip; hop / descend / create / next iteration as a per-lane state machine, so that the 32 trees of a warp do not wait for each other at
+// every ply) — 19.9 ms: the lanes' different states serialise, 6x the warp-instructions (ncu: 56 k against 9.6 k per tree and chunk) for a
+// third of the long-scoreboard stalls; (b) the search of a planning event on its own stream beside the LQNG steps that pass before its result
+// lands (hk_race_run_planned, apply_delay 45) — 78.6-86 ms against 77.2 ms per 200 steps, at the lowest stream priority too.
 //   record of a playout: word 0 = plies | n_scores << 8 | error << 16; words 1..8 = score bits; word 9 + p = gi | nextMoves().Count << 8 |
 //   (upNext() after the move & 0xff) << 16
 constexpr int SEQ_REC_HEAD = 1 + 2 * HK_MAX_KARTS;
