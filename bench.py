@@ -741,8 +741,8 @@ def main():
                          "gpu_launches": int(lib.hk_kernel_launch_count() - k0n), "sections_mean": float(k4["section"].mean()),
                          "players_per_problem_at_end": {str(n): int((npl == n).sum()) for n in (1, 2, 3, 4)},
                          "config": "Duos: 4-kart 2v2 races on Complex (teams [0,0,1,1], start lanes {2,3,2,3} at sections {0,0,1,1}), kinematic plant, "
-                                   "planFixed every 100 steps, every agent's LQNG problem (8 m nearby filter, N in 1..4, 4-player frame with dummy players, "
-                                   "lqng_mma4_kernel) every 4th step; host call incl. upload and download of the race states"}
+                                   "planFixed every 100 steps, every agent's LQNG problem (8 m nearby filter, N in 1..4: games of 3-4 in the 4-player frame by "
+                                   "lqng_mma4_kernel, games of 1-2 repacked for the 2-kart kernel) every 4th step; host call incl. upload and download of the race states"}
             prm4m = RC.race_params(S.COMPLEX, high_mode_mcts=True)
             RNm = RC.RacesN(S.COMPLEX, prm4m, 4)
             game4 = M2.Game(S.COMPLEX, 4, prm4m.velocityBucketSize)

@@ -48,12 +48,12 @@ void drain_ctx(ThreadCtx* c);                // synchronises every stream the co
 // LQNG device entry (hk_lqng.cu)
 int lqng_launch(int batch, int N, int horizon, int time_varying, const double* dA, const double* dB, const double* dQ,
                 const double* dq, const double* dR, const double* dx0, double* du0, double* dP, double* dalpha,
-                double* dtraj, int* dstatus, cudaStream_t stream);
+                double* dtraj, int* dstatus, cudaStream_t stream, const int* gate = nullptr, int gate_min = 0);
 int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double* dx0, const double* dtarget,
                          const double* dtw, const double* dcw, const double* daw, const double* dotgt, const double* dotw,
-                         double* du0, int* dstatus, cudaStream_t stream, int scratch_slot, const int* dn_players = nullptr);
+                         double* du0, int* dstatus, cudaStream_t stream, int scratch_slot, const int* dn_players = nullptr, int min_players = 0);
 
 int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const double* drec, double* du0, int* dstatus, cudaStream_t stream,
-                                int scratch_slot);
+                                int scratch_slot, const int* dn_players = nullptr);
 
 }  // namespace hk

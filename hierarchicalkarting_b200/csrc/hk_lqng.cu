@@ -32,6 +32,9 @@ struct LqngParams {
     // compact (fused assembly) mode of the 2-kart kernel: hk_lqng_assemble_solve_batch's arrays + (cos h, sin h) per player
     const double *c_x0, *c_target, *c_tw, *c_cw, *c_aw, *c_otgt, *c_otw, *c_cs;
     double dt;
+    // 3-/4-kart kernel: solve only problems with gate[prob] >= gate_min (hk_raceN_run sends games of one or two players to the 2-kart kernel)
+    const int* gate = nullptr;
+    int gate_min = 0;
 };
 
 template <int N>
@@ -324,11 +327,12 @@ __global__ void lqng_assemble_kernel(int batch, int N, double dt, const double* 
                                      const double* __restrict__ tw, const double* __restrict__ cw, const double* __restrict__ aw,
                                      const double* __restrict__ otgt, const double* __restrict__ otw,
                                      double* A, double* B, double* Q, double* q, double* R, double* xj,
-                                     const int* __restrict__ n_players = nullptr)
+                                     const int* __restrict__ n_players = nullptr, int min_players = 0)
 {
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= (long long)batch * N) return;
     const int n = 4 * N, K = N - 1;
+    if (n_players && n_players[id / N] < min_players) return;      // this game goes to another kernel: no record
     if (n_players && (int)(id % N) >= n_players[id / N]) {
         // decoupled dummy player of a game with fewer than N real players (hk_raceN_*: HierarchicalKartAgent.cs:709-725 keeps only the karts
         // within 8 m): A = I, B = 0, Q = 0, q = 0, R = I, x = 0 — its gains, Z and eta stay exactly zero, the coupled system gets an
@@ -457,10 +461,14 @@ static int launch_mma2p(LqngParams p, cudaStream_t stream, bool compact, bool fu
 
 // (cos h, sin h) of every player: the one transcendental of the assembly, evaluated one thread per player (a warp of the
 // solve kernel would spend a whole sincos instruction sequence on two useful lanes)
-__global__ void lqng_trig_kernel(long long n_players_total, const double* __restrict__ x0, double* __restrict__ cs, int N = 1, long long stride = 4)
+// n_players (optional, per problem): players past it are DUMMY players, marked (cos h, sin h) = (0, 0) — the 2-kart kernel then assembles
+// A = I, B = 0 for them (the rest of a dummy's description is zero weights, control weight 1, written by the caller)
+__global__ void lqng_trig_kernel(long long n_players_total, const double* __restrict__ x0, double* __restrict__ cs, int N = 1, long long stride = 4,
+                                 const int* __restrict__ n_players = nullptr)
 {
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n_players_total) return;
+    if (n_players && (int)(id % N) >= n_players[id / N]) { cs[id * 2] = 0.0; cs[id * 2 + 1] = 0.0; return; }
     const double h = x0[(id / N) * stride + (id % N) * 4 + 3];      // stride: doubles between the x0 blocks of consecutive problems
     cs[id * 2] = cos(h);
     cs[id * 2 + 1] = sin(h);
@@ -468,7 +476,7 @@ __global__ void lqng_trig_kernel(long long n_players_total, const double* __rest
 
 int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double* dx0, const double* dtarget,
                          const double* dtw, const double* dcw, const double* daw, const double* dotgt, const double* dotw,
-                         double* du0, int* dstatus, cudaStream_t stream, int scratch_slot, const int* dn_players)
+                         double* du0, int* dstatus, cudaStream_t stream, int scratch_slot, const int* dn_players, int min_players)
 {
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
@@ -495,10 +503,14 @@ int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double*
     double *dA = d, *dB = dA + (size_t)batch * N * 16, *dQ = dB + (size_t)batch * N * 8, *dq = dQ + (size_t)batch * N * n * n,
            *dR = dq + (size_t)batch * N * n, *dx = dR + (size_t)batch * N * 4;
     const long long threads = (long long)batch * N;
+    // games below min_players are left out (no record, no solve) when the kernel that honours the gate takes the launch
+    const bool gated = dn_players && min_players > 0 && (N == 3 || N == 4) && !(getenv("HK_LQNG_MMA4") && atoi(getenv("HK_LQNG_MMA4")) == 0) &&
+                       !getenv("HK_LQNG_FORCE_GENERIC");
     count_launch(); lqng_assemble_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(batch, N, dt, dx0, dtarget, dtw, dcw, daw, dotgt, dotw,
-                                                                              dA, dB, dQ, dq, dR, dx, dn_players);
+                                                                              dA, dB, dQ, dq, dR, dx, dn_players, gated ? min_players : 0);
     HK_CUDA(cudaGetLastError());
-    return lqng_launch(batch, N, horizon, 0, dA, dB, dQ, dq, dR, dx, du0, nullptr, nullptr, nullptr, dstatus, stream);
+    return lqng_launch(batch, N, horizon, 0, dA, dB, dQ, dq, dR, dx, du0, nullptr, nullptr, nullptr, dstatus, stream, gated ? dn_players : nullptr,
+                       gated ? min_players : 0);
 }
 
 // packed record [x0 N x 4 | target N x 4 | tw N x 4 | cw N | aw N x K x 2 | otgt N x K x 4 | otw N x K x 3] -> the seven arrays
@@ -521,7 +533,7 @@ __global__ void lqng_unpack_kernel(int batch, int N, const double* __restrict__ 
 }
 
 int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const double* drec, double* du0, int* dstatus, cudaStream_t stream,
-                                int scratch_slot)
+                                int scratch_slot, const int* dn_players)
 {
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
@@ -532,7 +544,7 @@ int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const 
         double* dcs = (double*)dscratch(c, scratch_slot, sizeof(double) * 4 * (size_t)batch);
         if (!dcs) return HK_ERR_OUT_OF_MEMORY;
         const long long np = (long long)batch * 2;
-        count_launch(); lqng_trig_kernel<<<(unsigned)((np + 255) / 256), 256, 0, stream>>>(np, drec, dcs, 2, P);
+        count_launch(); lqng_trig_kernel<<<(unsigned)((np + 255) / 256), 256, 0, stream>>>(np, drec, dcs, 2, P, dn_players);
         HK_CUDA(cudaGetLastError());
         LqngParams p{batch, horizon, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, du0, nullptr, nullptr, nullptr, dstatus,
                      nullptr, nullptr, nullptr, nullptr, drec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dcs, dt};
@@ -548,16 +560,17 @@ int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const 
     const long long threads = (long long)batch * P;
     count_launch(); lqng_unpack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(batch, N, drec, ux0, utg, utw, ucw, uaw, uot, uow);
     HK_CUDA(cudaGetLastError());
-    return lqng_assemble_launch(batch, N, horizon, dt, ux0, utg, utw, ucw, uaw, uot, uow, du0, dstatus, stream, scratch_slot);
+    return lqng_assemble_launch(batch, N, horizon, dt, ux0, utg, utw, ucw, uaw, uot, uow, du0, dstatus, stream, scratch_slot, dn_players, 0);
 }
 
 int lqng_launch(int batch, int N, int horizon, int time_varying, const double* dA, const double* dB, const double* dQ,
                 const double* dq, const double* dR, const double* dx0, double* du0, double* dP, double* dalpha,
-                double* dtraj, int* dstatus, cudaStream_t stream)
+                double* dtraj, int* dstatus, cudaStream_t stream, const int* gate, int gate_min)
 {
     if (batch == 0) return HK_OK;
     LqngParams p{batch, horizon, time_varying, dA, dB, dQ, dq, dR, dx0, du0, dP, dalpha, dtraj, dstatus, nullptr, nullptr, nullptr, nullptr,
                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0};
+    p.gate = gate; p.gate_min = gate_min;                           // honoured by lqng_mma4_kernel only (lqng_assemble_launch checks that it takes the launch)
     static const bool force_generic = getenv("HK_LQNG_FORCE_GENERIC") != nullptr;
     static const bool tv2 = !(getenv("HK_MMA2_TV") && atoi(getenv("HK_MMA2_TV")) == 0);
     if (N == 2 && time_varying && horizon <= 7 && !force_generic && tv2 &&

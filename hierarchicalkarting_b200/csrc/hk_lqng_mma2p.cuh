@@ -243,8 +243,10 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
             }
             if (lane < 16) {                                        // B_i (:57-59), q_i (KartLQRCosts.cs:109-124)
                 const int e = lane & 7, rr_ = e >> 1, cc = e & 1;
-                r[P2_oB + lane] = ((rr_ == 2 && cc == 0) || (rr_ == 3 && cc == 1)) ? p.dt : 0.0;
                 const int i = lane >> 3, s_ = lane & 7;
+                // (cos h, sin h) = (0, 0) marks a decoupled DUMMY player (lqng_trig_kernel): B = 0, and A = I falls out of the formulas above
+                const bool dummy = c[C2_ocs + 2 * i] == 0.0 && c[C2_ocs + 2 * i + 1] == 0.0;
+                r[P2_oB + lane] = (!dummy && ((rr_ == 2 && cc == 0) || (rr_ == 3 && cc == 1))) ? p.dt : 0.0;
                 double qv;
                 if (s_ < 4) qv = (-c[C2_otg + 4 * i + s_]) * c[C2_otw + 4 * i + s_];
                 else { qv = c[C2_oot + 4 * i + s_ - 4]; if (s_ < 7) qv = qv * -c[C2_oow + 3 * i + s_ - 4]; }

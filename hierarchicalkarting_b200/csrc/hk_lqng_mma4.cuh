@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
     const int yo0 = L::at(2 * t, g), yo1 = L::at(2 * t + 1, g);     // transposed store of a C fragment
 
     for (long long prob = (long long)blockIdx.x * MMA4_WARPS + wib; prob < p.batch; prob += nwarps) {
+        if (p.gate && p.gate[prob] < p.gate_min) continue;         // solved by another kernel (warp-uniform)
         const int T = p.horizon + 1, Tm = p.time_varying ? T : 1;
         const double* gA = p.A + (size_t)prob * Tm * NP * 16;
         const double* gB = p.B + (size_t)prob * Tm * NP * 8;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(32 * MMA4_WARPS, 7) lqng_mma4_kernel(LqngParam
         double* gP = p.P ? p.P + (size_t)prob * T * rm * rn : nullptr;
         double* ga = p.alpha ? p.alpha + (size_t)prob * T * rm : nullptr;
         int singular = 0;
-        if (prob + nwarps < p.batch) {                              // this warp's next record into L2 while this one is solved
+        if (prob + nwarps < p.batch && !(p.gate && p.gate[prob + nwarps] < p.gate_min)) {   // this warp's next record into L2 while this one is solved
             const size_t nx = (size_t)(prob + nwarps) * Tm;
             const char* nq = reinterpret_cast<const char*>(p.Q + nx * NP * rn * rn);
             constexpr int q_lines = (NP * rn * rn * 8 + 127) / 128;                      // 64 (4 karts) / 27 (3 karts)

@@ -921,6 +921,37 @@ extern "C" int hk_raceN_recipe(const hk_track* t, const hk_race_params* p, int K
     return HK_OK;
 }
 
+// Games of one or two players (after the 8 m filter most are) do not need the 4-player frame: their description is repacked as the 44-double
+// record of the 2-kart kernel — player 1 of a one-player game a decoupled dummy (zero weights, control weight 1; lqng_trig_kernel marks it and the
+// kernel assembles A = I, B = 0) — and lqng_mma4_kernel is gated to the games of three and four.  A game of three or four gets an all-dummy
+// record here (the 2-kart launch covers every slot; its answer for those slots is not used).  One thread per record element.
+__global__ void raceN_pack2_kernel(int n_agents, const int* __restrict__ n_players, const double* __restrict__ x0, const double* __restrict__ target,
+                                   const double* __restrict__ tw, const double* __restrict__ cw, const double* __restrict__ aw,
+                                   const double* __restrict__ otgt, const double* __restrict__ otw, double* __restrict__ rec2, int* __restrict__ n2)
+{
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)n_agents * 44) return;
+    const size_t b = (size_t)(id / 44);
+    const int e = (int)(id % 44), N = n_players[b], NN = N <= 2 ? N : 0;
+    if (e == 0) n2[b] = NN;
+    double v = 0.0;
+    if (e < 24) { const int i = (e & 7) >> 2, s = e & 3; if (i < NN) v = (e < 8 ? x0 : e < 16 ? target : tw)[b * 16 + i * 4 + s]; }
+    else if (e < 26) { const int i = e - 24; v = i < NN ? cw[b * 4 + i] : 1.0; }
+    else if (e < 30) { const int i = (e - 26) >> 1, s = (e - 26) & 1; if (i < NN) v = aw[b * 24 + i * 6 + s]; }           // private slot 0: the only other player
+    else if (e < 38) { const int i = (e - 30) >> 2, s = (e - 30) & 3; if (i < NN) v = otgt[b * 48 + i * 12 + s]; }
+    else { const int i = (e - 38) / 3, s = (e - 38) % 3; if (i < NN) v = otw[b * 36 + i * 9 + s]; }
+    rec2[id] = v;
+}
+
+__global__ void raceN_merge2_kernel(int n_agents, const int* __restrict__ n_players, const double* __restrict__ u2, const int* __restrict__ st2,
+                                    double* __restrict__ u, int* __restrict__ st)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_agents || n_players[b] > 2) return;
+    u[(size_t)b * 8] = u2[(size_t)b * 4]; u[(size_t)b * 8 + 1] = u2[(size_t)b * 4 + 1];
+    st[b] = st2[b];
+}
+
 extern "C" int hk_raceN_planner_create(const hk_game* game, const hk_race_mcts_params* mp, int K, int n_races, hk_race_planner** out)
 {
     if (!game || !mp || !out || n_races < 1 || K < 2 || K > HK_MAX_KARTS || mp->iterations < 0 || mp->first_iterations < 0 || mp->reuse_cycles < 0 ||
@@ -976,7 +1007,8 @@ extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_
     size_t out_elems = 8;                                              // + the u0 record of the 4-player frame
     for (size_t v : per) out_elems += v;
     const size_t in_bytes = nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan)) + nb * K * sizeof(hk_race_belief);
-    char* d = (char*)dscratch(c, 8, in_bytes + nb * (6 * sizeof(int) + out_elems * sizeof(double)) + 512);
+    static const bool split = !(getenv("HK_RACEN_SPLIT") && atoi(getenv("HK_RACEN_SPLIT")) == 0);   // measurement knob: every game in the 4-player frame
+    char* d = (char*)dscratch(c, 8, in_bytes + nb * (8 * sizeof(int) + (out_elems + 48) * sizeof(double)) + 512);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
     hk_race_kart* dk = (hk_race_kart*)d;
     hk_race_plan* dp = (hk_race_plan*)(dk + nb);
@@ -986,7 +1018,8 @@ extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_
     for (int i = 0; i < 7; ++i) { dout[i] = o; o += nb * per[i]; }
     double* du = o; o += nb * 8;
     unsigned long long* dcount = (unsigned long long*)o;
-    int* dn = (int*)(dcount + 2); int* dpl = dn + nb; int* dst = dpl + nb * 4;
+    double* drec2 = (double*)(dcount + 2); double* du2 = drec2 + nb * 44;                // 2-kart records and answers of the small games
+    int* dn = (int*)(du2 + nb * 4); int* dpl = dn + nb; int* dst = dpl + nb * 4; int* dn2 = dst + nb; int* dst2 = dn2 + nb;
     cudaStream_t s = c->stream;
     HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
     HK_CUDA_DRAIN(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
@@ -1031,8 +1064,21 @@ extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_
             count_launch();
             raceN_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, K, (int)nb, dk, dp, db, dn, dpl, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6]);
             HK_CUDA_DRAIN(cudaGetLastError());
-            rc = lqng_assemble_launch((int)nb, 4, p->horizon, p->dt, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6], du, dst, s, 9, dn);
+            if (split) {
+                const long long el = (long long)nb * 44;
+                count_launch();
+                raceN_pack2_kernel<<<(unsigned)((el + 255) / 256), 256, 0, s>>>((int)nb, dn, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6], drec2, dn2);
+                HK_CUDA_DRAIN(cudaGetLastError());
+                rc = lqng_assemble_launch_packed((int)nb, 2, p->horizon, p->dt, drec2, du2, dst2, s, 10, dn2);
+                if (rc) { drain(c); return rc; }
+            }
+            rc = lqng_assemble_launch((int)nb, 4, p->horizon, p->dt, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6], du, dst, s, 9, dn, split ? 3 : 0);
             if (rc) { drain(c); return rc; }
+            if (split) {
+                count_launch();
+                raceN_merge2_kernel<<<blocks, 128, 0, s>>>((int)nb, dn, du2, dst2, du, dst);
+                HK_CUDA_DRAIN(cudaGetLastError());
+            }
         }
         count_launch();
         race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 8, solve ? dst : nullptr, dcount, dk, dp, pl ? pl->root_valid : nullptr,

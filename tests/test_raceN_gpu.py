@@ -3,7 +3,8 @@ composition oracle/np_race.py (recipe restated from the C# text in oracle/np_rec
 REAL player count / plant / bookkeeping, the C oracle's sequential tree search), through the C-ABI.  What is new against the 2-kart
 loop: the 8 m nearby filter (N in 1..4 players per problem), nearbyAgents-scaled weights, teammates (multiplier / 2, teammate-target
 weights), every player's cost in its private order on the ego's joint order (quirk Q3), the solve every 4th step with held controls,
-problems with fewer than 4 players solved in the 4-player frame with decoupled dummy players, team scoring in the tree search."""
+games of three players solved in the 4-player frame with a decoupled dummy player, games of one or two sent to the 2-kart kernel (a
+one-player game with a dummy second player), team scoring in the tree search."""
 import numpy as np
 import pytest
 
@@ -77,8 +78,8 @@ def test_recipeN_parity(hk, oracle, track, mcts, K, teams):
 
 
 def test_two_kart_races_through_the_n_kart_path_equal_the_two_kart_path(hk):
-    """K = 2 (no 8 m filter, each kart its own team): hk_raceN_recipe gives the 2-kart recipe, and the loop — the same problems solved in the
-    4-player frame with two dummy players by lqng_mma4_kernel instead of the 2-kart kernel — drives the karts the same way."""
+    """K = 2 (no 8 m filter, each kart its own team): hk_raceN_recipe gives the 2-kart recipe, and the loop — recipe in the 4-player layout,
+    repacked for the 2-kart kernel, every 4th-step machinery at lqr_every = 1 — drives the karts the same way."""
     track = S.OVAL
     prm = R.race_params(track)
     G2, GN = R.Races(track, prm), R.RacesN(track, prm, 2, lqr_every=1)
