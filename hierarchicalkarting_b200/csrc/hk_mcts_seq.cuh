@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
 //   (upNext() after the move & 0xff) << 16
 constexpr int SEQ_REC_HEAD = 1 + 2 * HK_MAX_KARTS;
 
+// 118 registers, 4 resident blocks per SM.  Forcing 5 / 6 / 8 blocks (96 / 80 / 64 registers, spills) was measured: 12.1 / 11.4 / 11.5 ms
+// against 10.6 ms per 32,768 trees x 512 iterations.
 __global__ void __launch_bounds__(128) seq_playouts_kernel(const DevGame* __restrict__ gg, const SeqTree* __restrict__ trees, int n_trees,
                                                            const int* __restrict__ fresh, const int* __restrict__ remaining, int chunk, int base,
                                                            int cap, unsigned* __restrict__ recs)
