@@ -54,6 +54,6 @@ int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double*
                          double* du0, int* dstatus, cudaStream_t stream, int scratch_slot, const int* dn_players = nullptr, int min_players = 0);
 
 int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const double* drec, double* du0, int* dstatus, cudaStream_t stream,
-                                int scratch_slot, const int* dn_players = nullptr);
+                                int scratch_slot, const int* dn_players = nullptr, const double* dcs_ready = nullptr);
 
 }  // namespace hk

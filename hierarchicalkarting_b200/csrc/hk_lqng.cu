@@ -533,7 +533,7 @@ __global__ void lqng_unpack_kernel(int batch, int N, const double* __restrict__ 
 }
 
 int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const double* drec, double* du0, int* dstatus, cudaStream_t stream,
-                                int scratch_slot, const int* dn_players)
+                                int scratch_slot, const int* dn_players, const double* dcs_ready)
 {
     ThreadCtx* c = ctx();
     if (!c) return HK_ERR_NO_DEVICE;
@@ -541,11 +541,16 @@ int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const 
     const int K = N - 1, P = 13 * N + 9 * N * K;
     if (N == 2 && (reinterpret_cast<uintptr_t>(drec) & 15) == 0) {
         // 2-kart game: the solve kernel stages each 352-byte record with ONE bulk copy (+ the (cos h, sin h) pairs) and assembles in shared memory
-        double* dcs = (double*)dscratch(c, scratch_slot, sizeof(double) * 4 * (size_t)batch);
-        if (!dcs) return HK_ERR_OUT_OF_MEMORY;
-        const long long np = (long long)batch * 2;
-        count_launch(); lqng_trig_kernel<<<(unsigned)((np + 255) / 256), 256, 0, stream>>>(np, drec, dcs, 2, P, dn_players);
-        HK_CUDA(cudaGetLastError());
+        // dcs_ready: the caller has the (cos h, sin h) pairs already (the race loop's recipe kernels write them beside the records)
+        const double* dcs = dcs_ready;
+        if (!dcs) {
+            double* w = (double*)dscratch(c, scratch_slot, sizeof(double) * 4 * (size_t)batch);
+            if (!w) return HK_ERR_OUT_OF_MEMORY;
+            const long long np = (long long)batch * 2;
+            count_launch(); lqng_trig_kernel<<<(unsigned)((np + 255) / 256), 256, 0, stream>>>(np, drec, w, 2, P, dn_players);
+            HK_CUDA(cudaGetLastError());
+            dcs = w;
+        }
         LqngParams p{batch, horizon, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, du0, nullptr, nullptr, nullptr, dstatus,
                      nullptr, nullptr, nullptr, nullptr, drec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dcs, dt};
         return launch_mma2p(p, stream, true);

@@ -58,12 +58,12 @@ __device__ __forceinline__ void plan_target(const DevTrack* t, const hk_race_par
 // One thread per problem b = 2 race + ego; player 0 = ego, player 1 = the other kart (HKA:702).
 // packed != nullptr: the description goes out as ONE 44-double record per problem (x0 | target | tw | cw | aw | otgt | otw, the layout of
 // hk_lqng_assemble_solve_packed) that the solve kernel stages with one bulk copy; else into the seven arrays.
-__global__ void race_recipe_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_problems, const hk_race_kart* __restrict__ karts,
-                                   const hk_race_plan* __restrict__ plans, double* x0_, double* target_, double* tw_, double* cw_, double* aw_,
-                                   double* otgt_, double* otw_, double* packed = nullptr)
+// cs != nullptr: also (cos h, sin h) of both players, [problem][2][2] — what lqng_trig_kernel would compute from the record (same double-precision
+// functions; their code does not depend on this file's -fmad=false)
+__device__ __forceinline__ void race_recipe_body(const DevTrack* __restrict__ t, const hk_race_params& p, int b, const hk_race_kart* karts,
+                                                 const hk_race_plan* plans, double* x0_, double* target_, double* tw_, double* cw_, double* aw_,
+                                                 double* otgt_, double* otw_, double* packed, double* cs)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_problems) return;
     double* const rec = packed ? packed + (size_t)b * 44 : nullptr;
     double* const x0 = packed ? rec - (size_t)b * 8 : x0_;               // biased so that the indexing below (base + b * width) lands in the record
     double* const target = packed ? rec + 8 - (size_t)b * 8 : target_;
@@ -83,6 +83,7 @@ __global__ void race_recipe_kernel(const DevTrack* __restrict__ t, hk_race_param
         const float* vels = i == 0 ? plan->vel : plan->oppVel;
         double* x = x0 + (size_t)b * 8 + i * 4;
         x[0] = k.x; x[1] = k.z; x[2] = k.v; x[3] = k.h;              // :730-736
+        if (cs) { cs[(size_t)b * 4 + 2 * i] = cos(k.h); cs[(size_t)b * 4 + 2 * i + 1] = sin(k.h); }
         const int s = k.section + 1;                                 // :745
         const int idx = s % t->n, idx2 = (s + 1) % t->n;
         double nlx, nlz, nvel;
@@ -141,6 +142,15 @@ __global__ void race_recipe_kernel(const DevTrack* __restrict__ t, hk_race_param
     }
 }
 
+__global__ void race_recipe_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_problems, const hk_race_kart* __restrict__ karts,
+                                   const hk_race_plan* __restrict__ plans, double* x0_, double* target_, double* tw_, double* cw_, double* aw_,
+                                   double* otgt_, double* otw_, double* packed = nullptr, double* cs = nullptr)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_problems) return;
+    race_recipe_body(t, p, b, karts, plans, x0_, target_, tw_, cw_, aw_, otgt_, otw_, packed, cs);
+}
+
 // planFixed (:145-166), one thread per agent
 __global__ void race_plan_fixed_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_karts, const hk_race_kart* __restrict__ karts,
                                        hk_race_plan* plans)
@@ -160,12 +170,10 @@ __global__ void race_plan_fixed_kernel(const DevTrack* __restrict__ t, hk_race_p
 
 // actuator map (:1206-1224) + kinematic plant (KartMPCDynamics.cs:55-70) + OnTriggerEnter bookkeeping (:611-662).
 // u has `u_stride` doubles per kart (2: plain controls; 4: the LQNG u0 record of problem = kart, ego first).
-__global__ void race_step_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_karts, int episode_step, const double* __restrict__ u,
-                                 int u_stride, const int* __restrict__ lqng_status, unsigned long long* status_count, hk_race_kart* karts,
-                                 hk_race_plan* plans, int* __restrict__ root_valid = nullptr, int* __restrict__ cycles = nullptr)
+__device__ __forceinline__ void race_step_body(const DevTrack* __restrict__ t, const hk_race_params& p, int i, int episode_step, const double* __restrict__ u,
+                                               int u_stride, const int* __restrict__ lqng_status, unsigned long long* status_count, hk_race_kart* karts,
+                                               hk_race_plan* plans, int* __restrict__ root_valid, int* __restrict__ cycles)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_karts) return;
     if (lqng_status && lqng_status[i] != 0) atomicAdd(status_count, 1ull);
     hk_race_kart k = karts[i];
     if (!k.active) return;
@@ -232,6 +240,28 @@ __global__ void race_step_kernel(const DevTrack* __restrict__ t, hk_race_params 
         if (root_valid) { root_valid[i] = 0; cycles[i] = 0; }        // currentRoot = null; CyclesRootProcessed = 0 (:660-661)
     }
     karts[i] = k;
+}
+
+__global__ void race_step_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_karts, int episode_step, const double* __restrict__ u,
+                                 int u_stride, const int* __restrict__ lqng_status, unsigned long long* status_count, hk_race_kart* karts,
+                                 hk_race_plan* plans, int* __restrict__ root_valid = nullptr, int* __restrict__ cycles = nullptr)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_karts) return;
+    race_step_body(t, p, i, episode_step, u, u_stride, lqng_status, status_count, karts, plans, root_valid, cycles);
+}
+
+// The step of one FixedUpdate and the problem description of the NEXT one in one launch (2-kart races; no planning event between the two):
+// the two karts of a race are neighbouring lanes of a warp, so the partner's new state is there after a __syncwarp.  Two launches and the
+// (cos h, sin h) kernel less per step of the loop.
+__global__ void race_step_recipe_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_karts, int episode_step, const double* __restrict__ u,
+                                        int u_stride, const int* __restrict__ lqng_status, unsigned long long* status_count, hk_race_kart* karts,
+                                        hk_race_plan* plans, int* __restrict__ root_valid, int* __restrict__ cycles, double* packed, double* cs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_karts) race_step_body(t, p, i, episode_step, u, u_stride, lqng_status, status_count, karts, plans, root_valid, cycles);
+    __syncwarp();                                                    // n_karts is even and pairs do not straddle warps: the partner's store is visible
+    if (i < n_karts) race_recipe_body(t, p, i, karts, plans, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, packed, cs);
 }
 
 static int check_track(const hk_track* t, const hk_race_params* p, const char* who)
@@ -537,14 +567,15 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
     if (!c) return HK_ERR_NO_DEVICE;
     const size_t nb = (size_t)2 * n_races;                           // agents = problems per step
     const size_t compact = nb * (8 + 8 + 8 + 2 + 4 + 8 + 6);
-    char* d = (char*)dscratch(c, 8, nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan) + sizeof(int)) + (compact + nb * 4) * sizeof(double) + 64);
+    char* d = (char*)dscratch(c, 8, nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan) + sizeof(int)) + (compact + nb * 8) * sizeof(double) + 64);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
     hk_race_kart* dk = (hk_race_kart*)d;
     hk_race_plan* dp = (hk_race_plan*)(dk + nb);
     double* o = (double*)(dp + nb);
     double *dx0 = o, *dtg = dx0 + nb * 8, *dtw = dtg + nb * 8, *dcw = dtw + nb * 8, *daw = dcw + nb * 2, *dot = daw + nb * 4, *dow = dot + nb * 8;
     double* du = dow + nb * 6;
-    unsigned long long* dcount = (unsigned long long*)(du + nb * 4);
+    double* dcs = du + nb * 4;                                       // (cos h, sin h) of both players of every problem
+    unsigned long long* dcount = (unsigned long long*)(dcs + nb * 4);
     int* dst = (int*)(dcount + 1);
     cudaStream_t s = c->stream;
     HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
@@ -552,6 +583,8 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
     HK_CUDA_DRAIN(cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), s));
     const unsigned blocks = (unsigned)((nb + 127) / 128);
     int searches = 0;
+    static const bool fuse = !(getenv("HK_RACE_FUSE") && atoi(getenv("HK_RACE_FUSE")) == 0);       // measurement knob
+    bool have_recipe = false;                                        // the description of `step` was written by the previous step's launch
     for (int step = first_step; step < first_step + n_steps; ++step) {
         // HKA:331-353 (0.5 Hz): planFixed or planWithMCTS by mode; MCTS agents also plan when the episode begins (:85-93, T = 1.5)
         const bool replan = step > 0 && step % p->planEvery == 0;
@@ -585,13 +618,23 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
                 pl->pending_step = -1;
             }
         }
-        count_launch();
-        race_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dx0);
-        HK_CUDA_DRAIN(cudaGetLastError());
-        rc = lqng_assemble_launch_packed((int)nb, 2, p->horizon, p->dt, dx0, du, dst, s, 9);    // dx0: 44-double records (the seven arrays' space)
+        if (!have_recipe) {
+            count_launch();
+            race_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, dk, dp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dx0, dcs);
+            HK_CUDA_DRAIN(cudaGetLastError());
+        }
+        rc = lqng_assemble_launch_packed((int)nb, 2, p->horizon, p->dt, dx0, du, dst, s, 9, nullptr, dcs);   // dx0: 44-double records (the seven arrays' space)
         if (rc) { drain(c); return rc; }
+        // the next step's description rides with this step's plant update unless a planning event (planFixed, a search, a result landing)
+        // comes between the two
+        const int nx = step + 1;
+        have_recipe = fuse && nx < first_step + n_steps && nx % p->planEvery != 0 && !(pl && pl->pending_step == nx);
         count_launch();
-        race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp, pl ? pl->root_valid : nullptr, pl ? pl->cycles : nullptr);
+        if (have_recipe)
+            race_step_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp, pl ? pl->root_valid : nullptr,
+                                                          pl ? pl->cycles : nullptr, dx0, dcs);
+        else
+            race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp, pl ? pl->root_valid : nullptr, pl ? pl->cycles : nullptr);
         HK_CUDA_DRAIN(cudaGetLastError());
     }
     HK_CUDA_DRAIN(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
