@@ -511,18 +511,27 @@ __device__ __forceinline__ void unpack_k2(const DevGame& g, const K2& k, hk_kart
     o.min_velocity = v; o.max_velocity = min(v + b, g.vmax); o.infeasible = 0;
 }
 
-// continues a playout from `ply` with both karts packed; returns the total number of plies (or -1: upNext() == -1)
+// continues a playout from `ply` with both karts packed; returns the total number of plies (or -1: upNext() == -1).
+// REC (the sequential search's playouts): every ply also leaves its record word gi | nextMoves().Count << 8 | (upNext() after the move) << 16 in
+// rec_plies[ply] — the last field is known one trip later, so a word is written when the next trip has found who moves; -2: more than cap plies.
+template <bool REC = false>
 __device__ int rollout_packed2(const DevGame& g, const Tables& tb, hk_game_state& st, K2 k0, K2 k1, unsigned long long seed, unsigned long long rid,
-                               float* scores, int& n_scores, int& first_gi, int ply)
+                               float* scores, int& n_scores, int& first_gi, int ply, unsigned* rec_plies = nullptr, int cap = 0)
 {
     int last = st.lastCompletedSection, lcs_idx = last % g.n_sections;
     const int fin = st.finalSection, b = g.p.velocityBucketSize;
+    unsigned pending = 0;
+    bool have_pending = false;
     for (;;) {
         // upNext (:188-243): karts not yet at last + 1, minimum (section, time, -avgVelocity), lowest index on ties
         const bool e0 = k0.sec != last + 1, e1 = k1.sec != last + 1;
-        if (!e0 && !e1) return -1;
+        if (!e0 && !e1) {
+            if (REC && have_pending) rec_plies[ply - 1] = pending | (0xffu << 16);
+            return -1;
+        }
         const bool one_first = k1.sec < k0.sec || (k1.sec == k0.sec && (k1.time < k0.time || (k1.time == k0.time && ((k1.misc >> 8) & 15) > ((k0.misc >> 8) & 15))));
         const int np = (e0 && e1) ? (one_first ? 1 : 0) : (e0 ? 0 : 1);
+        if (REC && have_pending) rec_plies[ply - 1] = pending | ((unsigned)np << 16);
         const K2 k = np ? k1 : k0;
         const int l0 = k.misc & 3, sidx = (k.misc >> 2) & 63, lvl = (k.misc >> 8) & 15, lc = k.misc >> 12;
         const int type = g.type_of[sidx], flags = g.sec_flags[sidx];
@@ -555,6 +564,11 @@ __device__ int rollout_packed2(const DevGame& g, const Tables& tb, hk_game_state
         const int index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
         const unsigned long long mvrec = __ldg(&od[nth_set_bit(mask, index)]);
         const int gi = (int)(mvrec & 0xFFull);
+        if (REC) {
+            if (ply >= cap) return -2;
+            pending = (unsigned)gi | ((unsigned)cnt << 8);
+            have_pending = true;
+        }
         // applyAction + makeMove from the tables (:127-171, :420-446)
         const int l1 = gi & 3, j = gi >> 2;
         const int dtv = (int)(unsigned)(mvrec >> 8);
@@ -1335,6 +1349,9 @@ struct hk_mcts_forest {
     size_t recs_bytes = 0;
     int* remaining = nullptr;             // fast path: -1 while a tree is on it, else the iterations the general kernel still owes it
     int max_plies = 0;                    // largest playout length any root given through the host entry can have
+    int* aux = nullptr;                   // fast path: per-tree prefix tables (hk_mcts_seq.cuh, seq_insert_kernel); optional
+    long long aux_stride = 0;             // ints per tree
+    int aux_levels = 0;
 };
 
 namespace hk {
@@ -1399,6 +1416,15 @@ int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, cons
     seq_search_kernel<<<tree_blocks, 32, 0, s>>>(f->g->dev, f->trees, f->slabs, f->max_nodes, f->n_trees, 0, nullptr, seed, 0, d_roots, d_fresh, lt,
                                                  SEQ_LOG_TABLE, nullptr, nullptr, nullptr, nullptr, lanes, true, false);
     HK_CUDA(cudaGetLastError());
+    if (f->aux) {                                                     // fresh trees start with an empty prefix table (and the right to use it)
+        const unsigned bx = (unsigned)((f->aux_stride + 1023) / 1024 < 16 ? (f->aux_stride + 1023) / 1024 : 16);
+        count_launch();
+        for (int t0 = 0; t0 < f->n_trees; t0 += 65535) {              // gridDim.y limit
+            const int nt = f->n_trees - t0 < 65535 ? f->n_trees - t0 : 65535;
+            seq_aux_clear_kernel<<<dim3(bx, (unsigned)nt), 256, 0, s>>>(f->trees + t0, f->aux + (size_t)t0 * f->aux_stride, f->aux_stride, nt, d_fresh ? d_fresh + t0 : nullptr);
+        }
+        HK_CUDA(cudaGetLastError());
+    }
     // Playouts and insertion alternate on the caller's stream.  Running the playouts of chunk c + 1 on a second stream beside the insertion
     // of chunk c (two record buffers) was measured and does not pay: 61.6 ms per 32,768 x 512 call against 48.8 ms (the playout grid's blocks
     // crowd the 1,024 one-warp insertion blocks off the SMs), 49.6 ms with the playout stream at the lowest priority.
@@ -1410,7 +1436,8 @@ int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, cons
         HK_CUDA(cudaGetLastError());
         count_launch();
         seq_insert_kernel<<<(unsigned)((f->n_trees + 31) / 32), 32, 0, s>>>(f->trees, f->slabs, f->max_nodes, f->n_trees, d_fresh, f->remaining, count, count,
-                                                                          iterations - base - count, cap, f->recs);
+                                                                          iterations - base - count, cap, f->recs, f->aux, f->aux_stride, f->aux_levels,
+                                                                          f->g->host.n_cand);
         HK_CUDA(cudaGetLastError());
     }
     count_launch();
@@ -1431,6 +1458,20 @@ extern "C" int hk_mcts_forest_create(const hk_game* g, int n_trees, int max_node
     cudaError_t e = cudaMalloc(&f->trees, sizeof(SeqTree) * (size_t)n_trees);
     if (e == cudaSuccess) e = cudaMalloc(&f->slabs, sizeof(hk_mcts_node) * (size_t)n_trees * max_nodes_per_tree);
     if (e == cudaSuccess) e = cudaMemset(f->trees, 0, sizeof(SeqTree) * (size_t)n_trees);
+    if (e == cudaSuccess && !(getenv("HK_SEQ_AUX") && atoi(getenv("HK_SEQ_AUX")) == 0)) {
+        // prefix tables over the first 3 (2, 1) plies, as many levels as fit 2 GiB for this forest; doing without is only slower
+        const long long nc = g->host.n_cand;
+        long long stride = 0;
+        int levels = 0;
+        const long long budget = getenv("HK_SEQ_AUX_LEVELS") ? 1ll << 40 : 2ll << 30;
+        const int want = getenv("HK_SEQ_AUX_LEVELS") ? atoi(getenv("HK_SEQ_AUX_LEVELS")) : 3;
+        for (int l = 1; l <= want && l <= 3; ++l) {
+            const long long st = l == 1 ? nc : l == 2 ? nc + nc * nc : nc + nc * nc + nc * nc * nc;
+            if (st * 4 * n_trees <= budget) { stride = st; levels = l; }
+        }
+        if (levels && cudaMalloc(&f->aux, (size_t)stride * 4 * (size_t)n_trees) == cudaSuccess) { f->aux_stride = stride; f->aux_levels = levels; }
+        else { f->aux = nullptr; cudaGetLastError(); }
+    }
     if (e != cudaSuccess) {
         set_error("hk_mcts_forest_create: %s (%d trees x %d nodes x 32 B)", cudaGetErrorString(e), n_trees, max_nodes_per_tree);
         cudaGetLastError();
@@ -1450,6 +1491,7 @@ extern "C" void hk_mcts_forest_destroy(hk_mcts_forest* f)
     if (f->slabs) cudaFree(f->slabs);
     if (f->recs) cudaFree(f->recs);
     if (f->remaining) cudaFree(f->remaining);
+    if (f->aux) cudaFree(f->aux);
     delete f;
 }
 

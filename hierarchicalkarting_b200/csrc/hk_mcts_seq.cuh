@@ -23,7 +23,8 @@ struct SeqTree {                                  // per-tree header; persists b
     hk_game_state root;
     unsigned long long key, picks, iters;
     unsigned long long iters0;                    // iters when the current call started (the fast path's playouts are numbered from it)
-    int n_nodes, status, root_upnext, pad_;
+    int n_nodes, status, root_upnext;
+    int aux_ok;                                   // the tree's prefix table (see seq_insert_kernel) describes its top levels
     signed char root_cnt[HK_MAX_KARTS];           // prepared policy-ordered legal lists of karts that start from a non-action bucket
     unsigned char root_order[HK_MAX_KARTS][HK_MAX_ACTIONS];   // (quirk B.6-1: the root's (0, bucket)); -1 = not prepared
 };
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
     if (do_init && (!fresh || fresh[t])) {                             // new KartMCTSNode(state) :52
         tr.root = roots[t];
         tr.key = seed + (unsigned long long)(tree_base + t);
-        tr.picks = 0; tr.iters = 0; tr.n_nodes = 1; tr.status = 0;
+        tr.picks = 0; tr.iters = 0; tr.n_nodes = 1; tr.status = 0; tr.aux_ok = 0;
         const int up = up_next(tr.root);
         tr.root_upnext = up;
         hk_mcts_node r;
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
         seq_backprop(nodes, path, depth, scores, n_scores);
     }
     tr.picks = picks; tr.iters = iters; tr.n_nodes = n_nodes; tr.status = status;
+    if (my_iterations > 0) tr.aux_ok = 0;                              // nodes were created without the prefix table
     if (!do_best) return;
 
     // ---- getBestStatesSequence :108-122 (it consumes picks like any other upperConfidenceStrategy call; the counter persists) ----------
@@ -303,9 +305,10 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
 //   (upNext() after the move & 0xff) << 16
 constexpr int SEQ_REC_HEAD = 1 + 2 * HK_MAX_KARTS;
 
-// 118 registers, 4 resident blocks per SM.  Forcing 5 / 6 / 8 blocks (96 / 80 / 64 registers, spills) was measured: 12.1 / 11.4 / 11.5 ms
-// against 10.6 ms per 32,768 trees x 512 iterations.
-__global__ void __launch_bounds__(128) seq_playouts_kernel(const DevGame* __restrict__ gg, const SeqTree* __restrict__ trees, int n_trees,
+// Once both karts hold action velocity buckets (after their first moves) the playout continues in the packed, register-resident form of the
+// rollout kernel (rollout_packed2<true>, which also leaves the record words): 10.5 -> 7.4 ms per 32,768 trees x 512 iterations.  Resident blocks
+// per SM 3 / 4 / 5 / 6 / 8 (109 / 119 / 96 / 80 / 64 registers): 7.7 / 7.7 / 7.1 / 6.8 / 7.8 ms.
+__global__ void __launch_bounds__(128, 6) seq_playouts_kernel(const DevGame* __restrict__ gg, const SeqTree* __restrict__ trees, int n_trees,
                                                            const int* __restrict__ fresh, const int* __restrict__ remaining, int chunk, int base,
                                                            int cap, unsigned* __restrict__ recs)
 {
@@ -327,6 +330,15 @@ __global__ void __launch_bounds__(128) seq_playouts_kernel(const DevGame* __rest
     unsigned ply = 0;
     for (;; ++ply) {
         if (np < 0) { err = 1; break; }
+        if (g.tables_ok && st.n_karts == 2) {                          // both karts at action buckets: the rest runs packed in registers
+            K2 k0, k1;
+            if (pack_k2(g, st.karts[0], k0) && pack_k2(g, st.karts[1], k1)) {
+                int first_gi = -1;
+                const int r = rollout_packed2<true>(g, tb, st, k0, k1, tr.key, it, scores, n_scores, first_gi, (int)ply, rec + SEQ_REC_HEAD, cap);
+                if (r < 0) err = r == -1 ? 1 : 3; else ply = (unsigned)r;
+                break;
+            }
+        }
         int cnt, gi;
         if (!seq_ply(g, tb, tr, st, lcs_idx, moved, np, tr.key, it, ply, scores, n_scores, cnt, gi)) break;
         if ((int)ply >= cap) { err = 3; break; }
@@ -337,15 +349,34 @@ __global__ void __launch_bounds__(128) seq_playouts_kernel(const DevGame* __rest
     for (int k = 0; k < 2 * HK_MAX_KARTS; ++k) rec[1 + k] = k < n_scores ? __float_as_uint(scores[k]) : 0u;
 }
 
+// Prefix table (auxiliary, per tree, not part of the tree): aux[(gi_0)], aux[nc + gi_0 nc + gi_1], aux[nc + nc^2 + (gi_0 nc + gi_1) nc + gi_2] = index of
+// the node reached from the root by the moves gi_0 (, gi_1 (, gi_2)), 0 = not there.  The child lists of the top levels are the long ones (3.6 /
+// 3.7 / 3.1 sibling hops per visit at depth 0 / 1 / 2 of a 512-iteration tree, 1.7 and less below; up to 8-12 for the unluckiest of a warp's 32
+// lanes, and the warp waits for that one), and every hop is a dependent load.  With the table the three entries are loaded at once — their addresses
+// depend on the playout record only — then the three nodes at once: two dependent stages instead of ~10 (~24 for the warp).  The table is kept by
+// this kernel alone: aux_ok is cleared when anything else creates nodes in the tree (the general kernel, the checked insertion), and the
+// lists are walked again from then on.
+__global__ void seq_aux_clear_kernel(SeqTree* __restrict__ trees, int* __restrict__ aux, long long aux_stride, int n_trees, const int* __restrict__ fresh)
+{
+    const int t = blockIdx.y;                                         // one row of blocks per tree: kept trees leave at once
+    if (fresh && fresh[t] <= 0) return;                               // kept tree (or not searching): its table stays
+    int* a = aux + (size_t)t * aux_stride;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < aux_stride; e += (long long)gridDim.x * blockDim.x) a[e] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trees[t].aux_ok = 1;
+}
+
 __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ trees, hk_mcts_node* __restrict__ slabs, int max_nodes, int n_trees,
                                                         const int* __restrict__ fresh, int* __restrict__ remaining, int chunk, int count, int todo_after,
-                                                        int cap, const unsigned* __restrict__ recs)
+                                                        int cap, const unsigned* __restrict__ recs, int* __restrict__ aux_all, long long aux_stride,
+                                                        int aux_levels, int nc)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_trees) return;
     if ((fresh && fresh[t] < 0) || remaining[t] >= 0) return;
     SeqTree& tr = trees[t];
     hk_mcts_node* nodes = slabs + (size_t)t * max_nodes;
+    int* aux = aux_all ? aux_all + (size_t)t * aux_stride : nullptr;
+    bool aux_ok = aux && tr.aux_ok;
     int status = tr.status, n_nodes = tr.n_nodes;
     unsigned long long iters = tr.iters;
     int path[SEQ_MAX_PATH];
@@ -371,20 +402,42 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
                 if (up >= 0 && up < n_scores) x.totalValue += scores[up];
                 x.numEpisodes += 1;
             };
+            // prefix table: slots and entries of the first plies, then their nodes, each group of loads independent of one another
+            int slot0 = -1, slot1 = -1, slot2 = -1, pre0 = 0, pre1 = 0, pre2 = 0;
+            hk_mcts_node pn0, pn1, pn2;
+            if (aux_ok) {
+                const int g0 = len > 0 ? rec[SEQ_REC_HEAD] & 0xff : 0, g1 = len > 1 ? rec[SEQ_REC_HEAD + 1] & 0xff : 0, g2 = len > 2 ? rec[SEQ_REC_HEAD + 2] & 0xff : 0;
+                if (len > 0) slot0 = g0;
+                if (len > 1 && aux_levels > 1) slot1 = nc + g0 * nc + g1;
+                if (len > 2 && aux_levels > 2) slot2 = nc + nc * nc + (g0 * nc + g1) * nc + g2;
+                if (slot0 >= 0) pre0 = aux[slot0];
+                if (slot1 >= 0) pre1 = aux[slot1];
+                if (slot2 >= 0) pre2 = aux[slot2];
+                if (pre0 > 0) pn0 = nodes[pre0];
+                if (pre1 > 0) pn1 = nodes[pre1];
+                if (pre2 > 0) pn2 = nodes[pre2];
+            }
             credit(nd);
             for (int ply = 0; ply < len; ++ply) {
                 const unsigned w = rec[SEQ_REC_HEAD + ply];
                 const int gi = w & 0xff;
                 if (nd.n_legal == 255) nd.n_legal = (unsigned char)((w >> 8) & 0xff);
+                const int slot = ply == 0 ? slot0 : ply == 1 ? slot1 : ply == 2 ? slot2 : -1;
                 int child;
                 hk_mcts_node ch;
                 if ((nd.child_mask >> gi) & 1ull) {
                     nodes[node] = nd;                                  // statistics (and possibly nextMoves().Count) changed
-                    child = nd.first_child;
-                    for (;;) {
-                        ch = nodes[child];
-                        if (ch.gen == gi) break;
-                        child = ch.next_sibling;
+                    const int pre = ply == 0 ? pre0 : ply == 1 ? pre1 : ply == 2 ? pre2 : 0;
+                    if (slot >= 0 && pre > 0) {
+                        child = pre;
+                        ch = ply == 0 ? pn0 : ply == 1 ? pn1 : pn2;
+                    } else {
+                        child = nd.first_child;
+                        for (;;) {
+                            ch = nodes[child];
+                            if (ch.gen == gi) break;
+                            child = ch.next_sibling;
+                        }
                     }
                 } else {
                     child = n_nodes++;
@@ -394,6 +447,7 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
                     nodes[node] = nd;
                     ch.child_mask = 0ull; ch.totalValue = 0.0f; ch.numEpisodes = 0; ch.first_child = -1; ch.last_child = -1; ch.next_sibling = -1;
                     ch.gen = (unsigned char)gi; ch.n_legal = 255; ch.upnext = (signed char)((w >> 16) & 0xff); ch.pad_ = 0;
+                    if (slot >= 0) aux[slot] = child;
                 }
                 credit(ch);
                 node = child; nd = ch;
@@ -401,6 +455,7 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
             nodes[node] = nd;
             continue;
         }
+        aux_ok = false;                                                // the checked form below does not keep the table
         int depth = 0;
         bool dirty = false;
         path[0] = 0;
@@ -414,6 +469,7 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
         seq_backprop(nodes, path, depth, scores, n_scores);
     }
     tr.iters = iters; tr.n_nodes = n_nodes; tr.status = status;
+    if (aux && !aux_ok) tr.aux_ok = 0;
     if (status == 0 && i < count) remaining[t] = (count - i) + todo_after;            // the rest of this call's iterations, sequentially
 }
 
