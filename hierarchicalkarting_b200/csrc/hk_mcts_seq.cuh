@@ -381,11 +381,22 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
     unsigned long long iters = tr.iters;
     int path[SEQ_MAX_PATH];
     int i = 0;
+    // One iteration ahead: the head and the first three ply words of the next record are loaded while this one is inserted, and the table
+    // entries they select are brought into L2 (a prefetch: this iteration may still change them, the real loads come at their turn)
+    const size_t rec_words = (size_t)SEQ_REC_HEAD + cap;
+    const unsigned* rec0 = recs + (size_t)t * chunk * rec_words;
+    unsigned nh = count > 0 ? rec0[0] : 0u, nw0 = 0u, nw1 = 0u, nw2 = 0u;
+    if (count > 0 && cap >= 3) { nw0 = rec0[SEQ_REC_HEAD]; nw1 = rec0[SEQ_REC_HEAD + 1]; nw2 = rec0[SEQ_REC_HEAD + 2]; }
     for (; i < count && status == 0; ++i, ++iters) {
         hk_mcts_node nd = nodes[0];
         if (nd.first_child >= 0 && __popcll(nd.child_mask) == (int)nd.n_legal) break;     // findLeaf would descend: the general kernel takes over
-        const unsigned* rec = recs + ((size_t)t * chunk + i) * (SEQ_REC_HEAD + cap);
-        const unsigned head = rec[0];
+        const unsigned* rec = rec0 + (size_t)i * rec_words;
+        const unsigned head = nh, w0 = nw0, w1 = nw1, w2 = nw2;
+        if (i + 1 < count) {
+            const unsigned* rn = rec + rec_words;
+            nh = rn[0];
+            if (cap >= 3) { nw0 = rn[SEQ_REC_HEAD]; nw1 = rn[SEQ_REC_HEAD + 1]; nw2 = rn[SEQ_REC_HEAD + 2]; }
+        }
         const int len = head & 0xff, n_scores = (head >> 8) & 0xff, err = head >> 16;
         if (err) { status = err; break; }
         float scores[2 * HK_MAX_KARTS];
@@ -406,7 +417,7 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
             int slot0 = -1, slot1 = -1, slot2 = -1, pre0 = 0, pre1 = 0, pre2 = 0;
             hk_mcts_node pn0, pn1, pn2;
             if (aux_ok) {
-                const int g0 = len > 0 ? rec[SEQ_REC_HEAD] & 0xff : 0, g1 = len > 1 ? rec[SEQ_REC_HEAD + 1] & 0xff : 0, g2 = len > 2 ? rec[SEQ_REC_HEAD + 2] & 0xff : 0;
+                const int g0 = w0 & 0xff, g1 = w1 & 0xff, g2 = w2 & 0xff;                  // cap >= 3 where there is a table (words past len: unused)
                 if (len > 0) slot0 = g0;
                 if (len > 1 && aux_levels > 1) slot1 = nc + g0 * nc + g1;
                 if (len > 2 && aux_levels > 2) slot2 = nc + nc * nc + (g0 * nc + g1) * nc + g2;
@@ -416,6 +427,12 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
                 if (pre0 > 0) pn0 = nodes[pre0];
                 if (pre1 > 0) pn1 = nodes[pre1];
                 if (pre2 > 0) pn2 = nodes[pre2];
+                if (i + 1 < count) {                                   // the next iteration's entries towards L2
+                    const int h0 = min((int)(nw0 & 0xff), nc - 1), h1 = min((int)(nw1 & 0xff), nc - 1), h2 = min((int)(nw2 & 0xff), nc - 1);   // words past a record's length are not initialised
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(aux + h0));
+                    if (aux_levels > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(aux + nc + h0 * nc + h1));
+                    if (aux_levels > 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(aux + nc + nc * nc + (h0 * nc + h1) * nc + h2));
+                }
             }
             credit(nd);
             for (int ply = 0; ply < len; ++ply) {
