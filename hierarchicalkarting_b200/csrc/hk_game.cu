@@ -1345,7 +1345,7 @@ struct hk_mcts_forest {
     int n_trees = 0, max_nodes = 0;
     hk::SeqTree* trees = nullptr;
     hk_mcts_node* slabs = nullptr;
-    unsigned* recs = nullptr;             // fast path: playout records of one chunk of iterations [n_trees][chunk][SEQ_REC_HEAD + cap]
+    unsigned* recs = nullptr;             // fast path: playout records of one chunk of iterations [n_trees][chunk][seq_rec_words(cap)]
     size_t recs_bytes = 0;
     int* remaining = nullptr;             // fast path: -1 while a tree is on it, else the iterations the general kernel still owes it
     int max_plies = 0;                    // largest playout length any root given through the host entry can have
@@ -1398,7 +1398,7 @@ int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, cons
     // fast path (hk_mcts_seq.cuh): init; per chunk of iterations the playouts of every (tree, iteration) in parallel and their insertion in
     // order; then the general kernel for trees whose root became fully expanded on the way, and getBestStatesSequence for all
     const int cap = max_plies > 0 && max_plies < HK_MAX_PLIES ? max_plies : HK_MAX_PLIES;
-    const size_t words = (size_t)SEQ_REC_HEAD + cap;
+    const size_t words = seq_rec_words(cap);
     long long chunk = (long long)(768.0e6 / ((double)f->n_trees * words * 4));
     chunk = chunk < 16 ? 16 : chunk > 512 ? 512 : chunk;
     if (chunk > iterations) chunk = iterations;

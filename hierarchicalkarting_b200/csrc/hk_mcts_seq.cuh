@@ -302,8 +302,10 @@ __global__ void __launch_bounds__(64) seq_search_kernel(const DevGame* __restric
 // third of the long-scoreboard stalls; (b) the search of a planning event on its own stream beside the LQNG steps that pass before its result
 // lands (hk_race_run_planned, apply_delay 45) — 78.6-86 ms against 77.2 ms per 200 steps, at the lowest stream priority too.
 //   record of a playout: word 0 = plies | n_scores << 8 | error << 16; words 1..8 = score bits; word 9 + p = gi | nextMoves().Count << 8 |
-//   (upNext() after the move & 0xff) << 16
-constexpr int SEQ_REC_HEAD = 1 + 2 * HK_MAX_KARTS;
+//   (upNext() after the move & 0xff) << 16; the head is padded to 12 words and the record to a multiple of 4 (16-byte aligned, read as uint4)
+constexpr int SEQ_REC_HEAD = 12;                                    // head, 8 score words, 3 unused: the ply words start 16-byte aligned
+static_assert(SEQ_REC_HEAD >= 1 + 2 * HK_MAX_KARTS && SEQ_REC_HEAD % 4 == 0, "record head");
+__host__ __device__ constexpr size_t seq_rec_words(int cap) { return (size_t)SEQ_REC_HEAD + (size_t)((cap + 3) & ~3); }   // records are read as uint4
 
 // Once both karts hold action velocity buckets (after their first moves) the playout continues in the packed, register-resident form of the
 // rollout kernel (rollout_packed2<true>, which also leaves the record words): 10.5 -> 7.4 ms per 32,768 trees x 512 iterations.  Resident blocks
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(128, 6) seq_playouts_kernel(const DevGame* __r
     const Tables tb(g);
     const SeqTree& tr = trees[t];
     if (tr.status) return;
-    unsigned* rec = recs + (size_t)idx * (SEQ_REC_HEAD + cap);
+    unsigned* rec = recs + (size_t)idx * seq_rec_words(cap);
     hk_game_state st = tr.root;
     int lcs_idx = st.lastCompletedSection % g.n_sections;
     unsigned moved = 0;
@@ -381,26 +383,28 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
     unsigned long long iters = tr.iters;
     int path[SEQ_MAX_PATH];
     int i = 0;
-    // One iteration ahead: the head and the first three ply words of the next record are loaded while this one is inserted, and the table
-    // entries they select are brought into L2 (a prefetch: this iteration may still change them, the real loads come at their turn)
-    const size_t rec_words = (size_t)SEQ_REC_HEAD + cap;
-    const unsigned* rec0 = recs + (size_t)t * chunk * rec_words;
-    unsigned nh = count > 0 ? rec0[0] : 0u, nw0 = 0u, nw1 = 0u, nw2 = 0u;
-    if (count > 0 && cap >= 3) { nw0 = rec0[SEQ_REC_HEAD]; nw1 = rec0[SEQ_REC_HEAD + 1]; nw2 = rec0[SEQ_REC_HEAD + 2]; }
+    // What the loop waits for is memory, so everything whose address does not depend on the tree is fetched ahead: the first 16 words of the
+    // NEXT record (head, scores, ply words 0..3: four 16-byte loads) while this one is inserted, the ply words of this record four at a time
+    // one group ahead, and the next record's table entries as soon as this iteration is through its own top plies (the only place where
+    // the table is written).  The root's record stays in registers (its memory copy is kept current).
+    const int rq = (int)(seq_rec_words(cap) / 4);                      // uint4 per record
+    const uint4* rq0 = reinterpret_cast<const uint4*>(recs) + (size_t)t * chunk * rq;
+    uint4 nA = make_uint4(0, 0, 0, 0), nB = nA, nC = nA, nP = nA;
+    if (count > 0) { nA = rq0[0]; nB = rq0[1]; nC = rq0[2]; nP = rq0[3]; }
+    hk_mcts_node root = nodes[0];
+    int npre0 = 0, npre1 = 0, npre2 = 0;
+    bool npre_valid = false;
     for (; i < count && status == 0; ++i, ++iters) {
-        hk_mcts_node nd = nodes[0];
-        if (nd.first_child >= 0 && __popcll(nd.child_mask) == (int)nd.n_legal) break;     // findLeaf would descend: the general kernel takes over
-        const unsigned* rec = rec0 + (size_t)i * rec_words;
-        const unsigned head = nh, w0 = nw0, w1 = nw1, w2 = nw2;
-        if (i + 1 < count) {
-            const unsigned* rn = rec + rec_words;
-            nh = rn[0];
-            if (cap >= 3) { nw0 = rn[SEQ_REC_HEAD]; nw1 = rn[SEQ_REC_HEAD + 1]; nw2 = rn[SEQ_REC_HEAD + 2]; }
-        }
+        if (root.first_child >= 0 && __popcll(root.child_mask) == (int)root.n_legal) break;   // findLeaf would descend: the general kernel takes over
+        const uint4* rcur = rq0 + (size_t)i * rq;
+        const uint4 A = nA, B = nB, C = nC, P = nP;
+        if (i + 1 < count) { const uint4* rn = rcur + rq; nA = rn[0]; nB = rn[1]; nC = rn[2]; nP = rn[3]; }
+        const unsigned head = A.x;
         const int len = head & 0xff, n_scores = (head >> 8) & 0xff, err = head >> 16;
         if (err) { status = err; break; }
-        float scores[2 * HK_MAX_KARTS];
-        for (int k = 0; k < 2 * HK_MAX_KARTS; ++k) scores[k] = __uint_as_float(rec[1 + k]);
+        const float s0 = __uint_as_float(A.y), s1 = __uint_as_float(A.z), s2 = __uint_as_float(A.w), s3 = __uint_as_float(B.x),
+                    s4 = __uint_as_float(B.y), s5 = __uint_as_float(B.z), s6 = __uint_as_float(B.w), s7 = __uint_as_float(C.x);
+        static_assert(2 * HK_MAX_KARTS == 8, "eight score words");
         int node = 0;
         if (n_nodes + len <= max_nodes) {
             // The terminal scores are known before the descent, so backpropagate (:280-289) is folded into it: a node on the path gets its
@@ -410,33 +414,52 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
             // sequential loop then stops before backpropagating.)
             auto credit = [&](hk_mcts_node& x) {
                 const int up = x.upnext;
-                if (up >= 0 && up < n_scores) x.totalValue += scores[up];
+                float sc = s0;                                         // a select chain: an indexed array would live in local memory
+                sc = up == 1 ? s1 : sc; sc = up == 2 ? s2 : sc; sc = up == 3 ? s3 : sc; sc = up == 4 ? s4 : sc;
+                sc = up == 5 ? s5 : sc; sc = up == 6 ? s6 : sc; sc = up == 7 ? s7 : sc;
+                if (up >= 0 && up < n_scores) x.totalValue += sc;
                 x.numEpisodes += 1;
             };
-            // prefix table: slots and entries of the first plies, then their nodes, each group of loads independent of one another
+            // prefix table: entries of the first plies (already here when the previous iteration fetched them), then their nodes
             int slot0 = -1, slot1 = -1, slot2 = -1, pre0 = 0, pre1 = 0, pre2 = 0;
             hk_mcts_node pn0, pn1, pn2;
             if (aux_ok) {
-                const int g0 = w0 & 0xff, g1 = w1 & 0xff, g2 = w2 & 0xff;                  // cap >= 3 where there is a table (words past len: unused)
+                const int g0 = P.x & 0xff, g1 = P.y & 0xff, g2 = P.z & 0xff;      // words past len: unused
                 if (len > 0) slot0 = g0;
                 if (len > 1 && aux_levels > 1) slot1 = nc + g0 * nc + g1;
                 if (len > 2 && aux_levels > 2) slot2 = nc + nc * nc + (g0 * nc + g1) * nc + g2;
-                if (slot0 >= 0) pre0 = aux[slot0];
-                if (slot1 >= 0) pre1 = aux[slot1];
-                if (slot2 >= 0) pre2 = aux[slot2];
+                if (npre_valid) { pre0 = npre0; pre1 = npre1; pre2 = npre2; }
+                else {
+                    if (slot0 >= 0) pre0 = aux[slot0];
+                    if (slot1 >= 0) pre1 = aux[slot1];
+                    if (slot2 >= 0) pre2 = aux[slot2];
+                }
                 if (pre0 > 0) pn0 = nodes[pre0];
                 if (pre1 > 0) pn1 = nodes[pre1];
                 if (pre2 > 0) pn2 = nodes[pre2];
-                if (i + 1 < count) {                                   // the next iteration's entries towards L2
-                    const int h0 = min((int)(nw0 & 0xff), nc - 1), h1 = min((int)(nw1 & 0xff), nc - 1), h2 = min((int)(nw2 & 0xff), nc - 1);   // words past a record's length are not initialised
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(aux + h0));
-                    if (aux_levels > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(aux + nc + h0 * nc + h1));
-                    if (aux_levels > 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(aux + nc + nc * nc + (h0 * nc + h1) * nc + h2));
-                }
             }
+            npre_valid = false;
+            auto fetch_next_entries = [&]() {                          // after this iteration's last table write
+                if (!aux_ok || i + 1 >= count) return;
+                const int nlen = nA.x & 0xff;
+                const int h0 = min((int)(nP.x & 0xff), nc - 1), h1 = min((int)(nP.y & 0xff), nc - 1), h2 = min((int)(nP.z & 0xff), nc - 1);
+                npre0 = nlen > 0 ? aux[h0] : 0;
+                npre1 = (nlen > 1 && aux_levels > 1) ? aux[nc + h0 * nc + h1] : 0;
+                npre2 = (nlen > 2 && aux_levels > 2) ? aux[nc + nc * nc + (h0 * nc + h1) * nc + h2] : 0;
+                npre_valid = true;
+            };
+            hk_mcts_node nd = root;
             credit(nd);
+            if (len == 0) { nodes[0] = nd; root = nd; fetch_next_entries(); continue; }   // isOver() at the root: it collects the episode
+            uint4 cur4 = P, next4 = P;
+            if (len > 4) next4 = rcur[4];
             for (int ply = 0; ply < len; ++ply) {
-                const unsigned w = rec[SEQ_REC_HEAD + ply];
+                if ((ply & 3) == 0 && ply > 0) {
+                    cur4 = next4;
+                    if (ply + 4 < len) next4 = rcur[3 + (ply >> 2) + 1];
+                }
+                const int q = ply & 3;
+                const unsigned w = q == 0 ? cur4.x : q == 1 ? cur4.y : q == 2 ? cur4.z : cur4.w;
                 const int gi = w & 0xff;
                 if (nd.n_legal == 255) nd.n_legal = (unsigned char)((w >> 8) & 0xff);
                 const int slot = ply == 0 ? slot0 : ply == 1 ? slot1 : ply == 2 ? slot2 : -1;
@@ -444,6 +467,7 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
                 hk_mcts_node ch;
                 if ((nd.child_mask >> gi) & 1ull) {
                     nodes[node] = nd;                                  // statistics (and possibly nextMoves().Count) changed
+                    if (node == 0) root = nd;
                     const int pre = ply == 0 ? pre0 : ply == 1 ? pre1 : ply == 2 ? pre2 : 0;
                     if (slot >= 0 && pre > 0) {
                         child = pre;
@@ -462,17 +486,23 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
                     nd.last_child = child;
                     nd.child_mask |= 1ull << gi;
                     nodes[node] = nd;
+                    if (node == 0) root = nd;
                     ch.child_mask = 0ull; ch.totalValue = 0.0f; ch.numEpisodes = 0; ch.first_child = -1; ch.last_child = -1; ch.next_sibling = -1;
                     ch.gen = (unsigned char)gi; ch.n_legal = 255; ch.upnext = (signed char)((w >> 16) & 0xff); ch.pad_ = 0;
                     if (slot >= 0) aux[slot] = child;
                 }
                 credit(ch);
                 node = child; nd = ch;
+                if (ply == 2 || ply + 1 == len) { if (ply <= 2) fetch_next_entries(); }   // once: at ply 2, or at the last ply of a shorter playout
             }
             nodes[node] = nd;
             continue;
         }
         aux_ok = false;                                                // the checked form below does not keep the table
+        npre_valid = false;
+        const unsigned* rec = reinterpret_cast<const unsigned*>(rcur);
+        const float scores[2 * HK_MAX_KARTS] = {s0, s1, s2, s3, s4, s5, s6, s7};
+        hk_mcts_node nd = root;
         int depth = 0;
         bool dirty = false;
         path[0] = 0;
@@ -484,6 +514,7 @@ __global__ void __launch_bounds__(64) seq_insert_kernel(SeqTree* __restrict__ tr
         if (status) break;
         if (dirty) nodes[node] = nd;
         seq_backprop(nodes, path, depth, scores, n_scores);
+        root = nodes[0];
     }
     tr.iters = iters; tr.n_nodes = n_nodes; tr.status = status;
     if (aux && !aux_ok) tr.aux_ok = 0;
