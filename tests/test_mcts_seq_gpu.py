@@ -336,3 +336,52 @@ def test_edge_cases(hk, oracle):
     bad.n_karts = 3                                                  # a state of another game
     with pytest.raises(abi.HKError):
         F.search([bad] + roots[1:], 1, 0)
+
+
+@pytest.mark.parametrize("levels", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("track_name,bucket", [("Oval", 2), ("Complex", 1)])
+def test_prefix_tables_at_every_depth_leave_the_same_trees(hk, oracle, levels, track_name, bucket):
+    """The insertion kernel's auxiliary prefix tables (first 1, 2 or 3 plies: whatever fits the forest's budget; none with HK_SEQ_AUX=0) are not
+    part of the tree: with every depth — and across a continued search, a tree that is kept while its neighbours start afresh, and a slab
+    that fills up — the node records equal the oracle's."""
+    import os
+    track = tracks.OVAL if track_name == "Oval" else tracks.COMPLEX
+    G = mcts.Game(track, 2, bucket)
+    OG = _oracle_game(oracle, track, 2, bucket)
+    rng = np.random.default_rng(5 + bucket)
+    n = 24
+    roots = _roots(rng, track, 2, bucket, [0, 1], n)
+    roots2 = _roots(rng, track, 2, bucket, [0, 1], n)
+    os.environ["HK_SEQ_AUX_LEVELS"] = levels
+    if levels == "0":
+        os.environ["HK_SEQ_AUX"] = "0"
+    try:
+        F = mcts.Forest(G, n, 3000)
+        F.search(roots, 120, 900)
+        fresh = np.array([1 if r % 3 == 0 else 0 for r in range(n)], np.int32)            # every third tree starts over from another root
+        F.search(roots2, 100, 901, fresh=fresh)
+        F.search(None, 60, 0, fresh=np.zeros(n, np.int32))                                # the last 20 iterations no longer fit the slab
+        got = [F.nodes(r) for r in range(n)]
+    finally:
+        os.environ.pop("HK_SEQ_AUX_LEVELS", None)
+        os.environ.pop("HK_SEQ_AUX", None)
+    full = 0
+    for r in range(n):
+        if fresh[r]:
+            ot = oracle.Tree(OG, roots2[r], key=901 + r)
+            ot.search(100 + 60)
+        else:
+            ot = oracle.Tree(OG, roots[r], key=900 + r)
+            ot.search(120 + 100 + 60)
+        if ot.size <= 3000:
+            _compare_tree(got[r], ot)
+        else:                                                          # the device tree stopped when its slab was full: the iterations that
+            full += 1                                                  # fitted are the oracle's first ones, the one that did not left nodes without episodes
+            done = int(got[r]["numEpisodes"][0])
+            assert 0 < done < 280 and len(got[r]) <= 3000
+            o2 = oracle.Tree(OG, roots[r], key=900 + r)
+            o2.search(done)
+            d = o2.dump()
+            assert np.array_equal(got[r]["numEpisodes"][:o2.size], d["numEpisodes"]) and not got[r]["numEpisodes"][o2.size:].any()
+            assert _same_bits(got[r]["totalValue"][:o2.size], d["totalValue"])
+    assert full > 0
