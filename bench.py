@@ -668,7 +668,18 @@ def main():
                     "sections_mean": float(karts["section"].mean()),
                     "config": "BASELINE config 5: 2-kart Oval races, kinematic plant, planFixed every 100 steps, one LQNG solve per "
                               "agent and step (recipe + assembly + solve + plant + bookkeeping on the GPU); host call incl. the "
-                              "upload and download of the race states"}
+                              "upload and download of the race states; device_resident: the same steps through hk_race_run_device on "
+                              "states that stay in HBM; lap / section figures come from the kinematic stand-in for PhysX and the "
+                              "raycast-free branches of the target-heading heuristic"}
+        dk_r, dp_r = RC.device_state(karts, plans, device=dev)
+        RS.run_device(dk_r, dp_r, 100 + RACE_STEPS, 100)
+        barrier()
+        t0 = time.perf_counter()
+        bad_d = RS.run_device(dk_r, dp_r, 200 + RACE_STEPS, RACE_STEPS)
+        el_d = max_over_ranks(time.perf_counter() - t0)
+        race_obj["device_resident"] = {"value": world * 2 * RACES * RACE_STEPS / el_d, "unit": "agent-steps/s", "ms_per_step": 1e3 * el_d / RACE_STEPS,
+                                       "lqng_status_nonzero": int(bad_d), "api": "hk_race_run_device"}
+        del dk_r, dp_r
 
     # ---- the same loop with the MCTS high level (BASELINE config 5 as written: MCTS waypoints -> batched LQNG -> dynamics rollout):
     #      every 100 steps every agent's tree search runs on the GPU (hk_mcts_search_batch, one thread block per tree) --------------
@@ -707,6 +718,17 @@ def main():
                                "waypoints_set": int(((pp["lane"] != 0) | (pp["oppLane"] != 0)).sum()),
                                "trees_out_of_nodes": int((tree_status == 3).sum())}
                 pl.close()
+                if name == "faithful":                                                         # the same two planning events on HBM-resident states
+                    pl = RC.Planner(game_m, RACES, seed=20260006 + 1000 * rank, **kw)
+                    dk_m, dp_m = RC.device_state(km, pm, device=dev)
+                    barrier()
+                    t0 = time.perf_counter()
+                    bad_dm = RM.run_device(dk_m, dp_m, 100, 100 * blocks_m, planner=pl)
+                    el_dm = max_over_ranks(time.perf_counter() - t0)
+                    modes[name]["device_resident"] = {"value": world * 2 * RACES * 100 * blocks_m / el_dm, "unit": "agent-steps/s", "ms_total": 1e3 * el_dm,
+                                                      "lqng_status_nonzero": int(bad_dm), "api": "hk_race_run_device"}
+                    pl.close()
+                    del dk_m, dp_m
             race_mcts_obj = dict(modes["faithful"])
             race_mcts_obj.update({"metric": "race_agent_steps_per_s", "races_per_gpu": RACES, "steps": 100 * blocks_m, "planning_events": blocks_m,
                                   "leaf_parallel": modes["leaf_parallel"],
@@ -743,6 +765,17 @@ def main():
                          "config": "Duos: 4-kart 2v2 races on Complex (teams [0,0,1,1], start lanes {2,3,2,3} at sections {0,0,1,1}), kinematic plant, "
                                    "planFixed every 100 steps, every agent's LQNG problem (8 m nearby filter, N in 1..4: games of 3-4 in the 4-player frame by "
                                    "lqng_mma4_kernel, games of 1-2 repacked for the 2-kart kernel) every 4th step; host call incl. upload and download of the race states"}
+            dk4, dp4, db4 = RC.device_state(k4, p4r, b4r, device=dev)
+            du4 = torch.zeros((4 * R4, 8), dtype=torch.float64, device=dev)
+            du4[:, :2] = torch.from_numpy(u4r.reshape(-1, 2)).to(dev)
+            RN.run_n_device(dk4, dp4, db4, du4, 100 + RACE_STEPS, 100)
+            barrier()
+            t0 = time.perf_counter()
+            bad4d = RN.run_n_device(dk4, dp4, db4, du4, 200 + RACE_STEPS, RACE_STEPS)
+            el4d = max_over_ranks(time.perf_counter() - t0)
+            race4_obj["device_resident"] = {"value": world * 4 * R4 * RACE_STEPS / el4d, "unit": "agent-steps/s", "ms_per_step": 1e3 * el4d / RACE_STEPS,
+                                            "lqng_status_nonzero": int(bad4d), "api": "hk_raceN_run_device"}
+            del dk4, dp4, db4, du4
             prm4m = RC.race_params(S.COMPLEX, high_mode_mcts=True)
             RNm = RC.RacesN(S.COMPLEX, prm4m, 4)
             game4 = M2.Game(S.COMPLEX, 4, prm4m.velocityBucketSize)
@@ -762,6 +795,20 @@ def main():
                                  "waypoints_set": int((pm4["lane"] != 0).sum()), "beliefs_set": int((bm4["lane"] != 0).sum()),
                                  "trees_out_of_nodes": int((pl4.state()[2] == 3).sum())}
             pl4.close()
+            pl4 = RNm.planner(game4, R4, 256, 20260008 + 1000 * rank, mode=0, reuse_cycles=3, apply_delay=45)
+            km4b, pm4b, bm4b, um4b = RC.start_grid_n(S.COMPLEX, R4, 4, seed=20260007 + rank)
+            RNm.run_n(km4b, pm4b, bm4b, um4b, 0, 100)
+            dk4, dp4, db4 = RC.device_state(km4b, pm4b, bm4b, device=dev)
+            du4 = torch.zeros((4 * R4, 8), dtype=torch.float64, device=dev)
+            du4[:, :2] = torch.from_numpy(um4b.reshape(-1, 2)).to(dev)
+            barrier()
+            t0 = time.perf_counter()
+            bad4dm = RNm.run_n_device(dk4, dp4, db4, du4, 100, 200, planner=pl4)
+            el4dm = max_over_ranks(time.perf_counter() - t0)
+            race4_obj["mcts"]["device_resident"] = {"value": world * 4 * R4 * 200 / el4dm, "unit": "agent-steps/s", "ms_total": 1e3 * el4dm,
+                                                    "lqng_status_nonzero": int(bad4dm), "api": "hk_raceN_run_device"}
+            pl4.close()
+            del dk4, dp4, db4, du4
         except Exception as exc:
             race4_obj = {"error": repr(exc)[:300]}
 

@@ -177,6 +177,10 @@ PROTOTYPES = {
     "hk_raceN_planner_create": (C.c_int, [C.c_void_p, C.POINTER(hk_race_mcts_params), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "hk_raceN_run": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, _lp]),
+    "hk_race_run_device": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _lp,
+                                     C.c_void_p]),
+    "hk_raceN_run_device": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, _lp, C.c_void_p]),
     "hk_race_run_mcts": (C.c_int, [C.c_void_p, C.POINTER(hk_race_params), C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, _dp, _lp]),
 }

@@ -548,8 +548,11 @@ static void drain(ThreadCtx* c) { drain_ctx(c); }
         }                                                                                               \
     } while (0)
 
+// on_device: karts / plans (and u_last, then [agent][4]: the LQNG u0 record, ego controls first) are DEVICE pointers and `user_stream` the stream
+// to work on (hk_race_run_device); else host arrays that are copied in and out around the loop.
 static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_planner* pl, int n_races, int first_step, int n_steps,
-                         hk_race_kart* karts, hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero)
+                         hk_race_kart* karts, hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero, bool on_device = false,
+                         void* user_stream = nullptr)
 {
     int rc = check_track(t, p, "hk_race_run");
     if (rc) return rc;
@@ -569,17 +572,19 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
     const size_t compact = nb * (8 + 8 + 8 + 2 + 4 + 8 + 6);
     char* d = (char*)dscratch(c, 8, nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan) + sizeof(int)) + (compact + nb * 8) * sizeof(double) + 64);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
-    hk_race_kart* dk = (hk_race_kart*)d;
-    hk_race_plan* dp = (hk_race_plan*)(dk + nb);
-    double* o = (double*)(dp + nb);
+    hk_race_kart* dk = on_device ? karts : (hk_race_kart*)d;
+    hk_race_plan* dp = on_device ? plans : (hk_race_plan*)((hk_race_kart*)d + nb);
+    double* o = (double*)((hk_race_plan*)((hk_race_kart*)d + nb) + nb);
     double *dx0 = o, *dtg = dx0 + nb * 8, *dtw = dtg + nb * 8, *dcw = dtw + nb * 8, *daw = dcw + nb * 2, *dot = daw + nb * 4, *dow = dot + nb * 8;
-    double* du = dow + nb * 6;
-    double* dcs = du + nb * 4;                                       // (cos h, sin h) of both players of every problem
+    double* du = (on_device && u_last) ? u_last : dow + nb * 6;
+    double* dcs = dow + nb * 6 + nb * 4;                                       // (cos h, sin h) of both players of every problem
     unsigned long long* dcount = (unsigned long long*)(dcs + nb * 4);
     int* dst = (int*)(dcount + 1);
-    cudaStream_t s = c->stream;
-    HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
-    HK_CUDA_DRAIN(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
+    cudaStream_t s = (on_device && user_stream) ? (cudaStream_t)user_stream : c->stream;
+    if (!on_device) {
+        HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
+        HK_CUDA_DRAIN(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
+    }
     HK_CUDA_DRAIN(cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), s));
     const unsigned blocks = (unsigned)((nb + 127) / 128);
     int searches = 0;
@@ -637,11 +642,13 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
             race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp, pl ? pl->root_valid : nullptr, pl ? pl->cycles : nullptr);
         HK_CUDA_DRAIN(cudaGetLastError());
     }
-    HK_CUDA_DRAIN(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
-    HK_CUDA_DRAIN(cudaMemcpyAsync(plans, dp, nb * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, s));
+    if (!on_device) {
+        HK_CUDA_DRAIN(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
+        HK_CUDA_DRAIN(cudaMemcpyAsync(plans, dp, nb * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, s));
+    }
     unsigned long long count = 0;
     HK_CUDA_DRAIN(cudaMemcpyAsync(&count, dcount, sizeof(count), cudaMemcpyDeviceToHost, s));
-    if (u_last) {
+    if (u_last && !on_device) {
         // u0 records are [problem][4] (ego controls first): compact to [race][2 agents][2] on the host side of the copy
         double* hu = (double*)hscratch(c, 2, nb * 4 * sizeof(double));
         if (!hu) { drain(c); return HK_ERR_OUT_OF_MEMORY; }
@@ -651,7 +658,7 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
     }
     std::vector<int> mst;
     if (pl && searches) { mst.resize(nb); HK_CUDA_DRAIN(cudaMemcpyAsync(mst.data(), pl->status, 4 * nb, cudaMemcpyDeviceToHost, s)); }
-    HK_CUDA_DRAIN(cudaStreamSynchronize(s));
+    HK_CUDA_DRAIN(cudaStreamSynchronize(s));                           // also for device state: the count and the trees' status come back
     if (lqng_status_nonzero) *lqng_status_nonzero = (int64_t)count;
     for (size_t a = 0; a < mst.size(); ++a)
         if (mst[a] == 1) { set_error("hk_race_run_planned: upNext() == -1 reached in the tree of agent %zu (KartDiscreteGame.cs:326 would throw)", a); return HK_ERR_NO_UPNEXT; }
@@ -662,6 +669,12 @@ extern "C" int hk_race_run(const hk_track* t, const hk_race_params* p, int n_rac
                            hk_race_plan* plans, double* u_last, int64_t* lqng_status_nonzero)
 {
     return race_run_impl(t, p, nullptr, n_races, first_step, n_steps, karts, plans, u_last, lqng_status_nonzero);
+}
+
+extern "C" int hk_race_run_device(const hk_track* t, const hk_race_params* p, hk_race_planner* planner, int n_races, int first_step, int n_steps,
+                                  hk_race_kart* d_karts, hk_race_plan* d_plans, double* d_u, int64_t* lqng_status_nonzero, void* cuda_stream)
+{
+    return race_run_impl(t, p, planner, n_races, first_step, n_steps, d_karts, d_plans, d_u, lqng_status_nonzero, true, cuda_stream);
 }
 
 extern "C" int hk_race_run_planned(const hk_track* t, const hk_race_params* p, hk_race_planner* planner, int n_races, int first_step, int n_steps,
@@ -1030,9 +1043,11 @@ extern "C" int hk_raceN_planner_create(const hk_game* game, const hk_race_mcts_p
     return HK_OK;
 }
 
-extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_planner* pl, int K, int lqr_every, int n_races, int first_step,
-                            int n_steps, hk_race_kart* karts, hk_race_plan* plans, hk_race_belief* beliefs, double* u_hold,
-                            int64_t* lqng_status_nonzero)
+// on_device: karts / plans / beliefs are DEVICE pointers, u_hold the device array [agent][8] (the 4-player u0 record, ego controls first) and
+// `user_stream` the stream to work on (hk_raceN_run_device); else host arrays (u_hold [agent][2]) copied in and out around the loop.
+static int raceN_run_impl(const hk_track* t, const hk_race_params* p, hk_race_planner* pl, int K, int lqr_every, int n_races, int first_step,
+                          int n_steps, hk_race_kart* karts, hk_race_plan* plans, hk_race_belief* beliefs, double* u_hold,
+                          int64_t* lqng_status_nonzero, bool on_device, void* user_stream)
 {
     int rc = raceN_check(t, p, K, n_races, "hk_raceN_run");
     if (rc) return rc;
@@ -1053,22 +1068,24 @@ extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_
     static const bool split = !(getenv("HK_RACEN_SPLIT") && atoi(getenv("HK_RACEN_SPLIT")) == 0);   // measurement knob: every game in the 4-player frame
     char* d = (char*)dscratch(c, 8, in_bytes + nb * (8 * sizeof(int) + (out_elems + 48) * sizeof(double)) + 512);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
-    hk_race_kart* dk = (hk_race_kart*)d;
-    hk_race_plan* dp = (hk_race_plan*)(dk + nb);
-    hk_race_belief* db = (hk_race_belief*)(dp + nb);
-    double* o = (double*)(((uintptr_t)(db + nb * K) + 15) & ~(uintptr_t)15);
+    hk_race_kart* dk = on_device ? karts : (hk_race_kart*)d;
+    hk_race_plan* dp = on_device ? plans : (hk_race_plan*)((hk_race_kart*)d + nb);
+    hk_race_belief* db = on_device ? beliefs : (hk_race_belief*)((hk_race_plan*)((hk_race_kart*)d + nb) + nb);
+    double* o = (double*)(((uintptr_t)((hk_race_belief*)((hk_race_plan*)((hk_race_kart*)d + nb) + nb) + nb * K) + 15) & ~(uintptr_t)15);
     double* dout[7];
     for (int i = 0; i < 7; ++i) { dout[i] = o; o += nb * per[i]; }
-    double* du = o; o += nb * 8;
+    double* du = on_device ? u_hold : o; o += nb * 8;
     unsigned long long* dcount = (unsigned long long*)o;
     double* drec2 = (double*)(dcount + 2); double* du2 = drec2 + nb * 44;                // 2-kart records and answers of the small games
     int* dn = (int*)(du2 + nb * 4); int* dpl = dn + nb; int* dst = dpl + nb * 4; int* dn2 = dst + nb; int* dst2 = dn2 + nb;
-    cudaStream_t s = c->stream;
-    HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
-    HK_CUDA_DRAIN(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
-    HK_CUDA_DRAIN(cudaMemcpyAsync(db, beliefs, nb * K * sizeof(hk_race_belief), cudaMemcpyHostToDevice, s));
-    HK_CUDA_DRAIN(cudaMemsetAsync(du, 0, nb * 8 * sizeof(double), s));
-    HK_CUDA_DRAIN(cudaMemcpy2DAsync(du, 8 * sizeof(double), u_hold, 2 * sizeof(double), 2 * sizeof(double), nb, cudaMemcpyHostToDevice, s));
+    cudaStream_t s = (on_device && user_stream) ? (cudaStream_t)user_stream : c->stream;
+    if (!on_device) {
+        HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
+        HK_CUDA_DRAIN(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
+        HK_CUDA_DRAIN(cudaMemcpyAsync(db, beliefs, nb * K * sizeof(hk_race_belief), cudaMemcpyHostToDevice, s));
+        HK_CUDA_DRAIN(cudaMemsetAsync(du, 0, nb * 8 * sizeof(double), s));
+        HK_CUDA_DRAIN(cudaMemcpy2DAsync(du, 8 * sizeof(double), u_hold, 2 * sizeof(double), 2 * sizeof(double), nb, cudaMemcpyHostToDevice, s));
+    }
     HK_CUDA_DRAIN(cudaMemsetAsync(dcount, 0, 2 * sizeof(unsigned long long), s));
     const unsigned blocks = (unsigned)((nb + 127) / 128);
     int searches = 0;
@@ -1128,10 +1145,12 @@ extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_
                                                 pl ? pl->cycles : nullptr);
         HK_CUDA_DRAIN(cudaGetLastError());
     }
-    HK_CUDA_DRAIN(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
-    HK_CUDA_DRAIN(cudaMemcpyAsync(plans, dp, nb * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, s));
-    HK_CUDA_DRAIN(cudaMemcpyAsync(beliefs, db, nb * K * sizeof(hk_race_belief), cudaMemcpyDeviceToHost, s));
-    HK_CUDA_DRAIN(cudaMemcpy2DAsync(u_hold, 2 * sizeof(double), du, 8 * sizeof(double), 2 * sizeof(double), nb, cudaMemcpyDeviceToHost, s));
+    if (!on_device) {
+        HK_CUDA_DRAIN(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
+        HK_CUDA_DRAIN(cudaMemcpyAsync(plans, dp, nb * sizeof(hk_race_plan), cudaMemcpyDeviceToHost, s));
+        HK_CUDA_DRAIN(cudaMemcpyAsync(beliefs, db, nb * K * sizeof(hk_race_belief), cudaMemcpyDeviceToHost, s));
+        HK_CUDA_DRAIN(cudaMemcpy2DAsync(u_hold, 2 * sizeof(double), du, 8 * sizeof(double), 2 * sizeof(double), nb, cudaMemcpyDeviceToHost, s));
+    }
     unsigned long long count = 0;
     HK_CUDA_DRAIN(cudaMemcpyAsync(&count, dcount, sizeof(count), cudaMemcpyDeviceToHost, s));
     std::vector<int> mst;
@@ -1141,4 +1160,18 @@ extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_
     for (size_t a = 0; a < mst.size(); ++a)
         if (mst[a] == 1) { set_error("hk_raceN_run: upNext() == -1 reached in the tree of agent %zu (KartDiscreteGame.cs:326 would throw)", a); return HK_ERR_NO_UPNEXT; }
     return HK_OK;
+}
+
+extern "C" int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_planner* pl, int K, int lqr_every, int n_races, int first_step,
+                            int n_steps, hk_race_kart* karts, hk_race_plan* plans, hk_race_belief* beliefs, double* u_hold,
+                            int64_t* lqng_status_nonzero)
+{
+    return raceN_run_impl(t, p, pl, K, lqr_every, n_races, first_step, n_steps, karts, plans, beliefs, u_hold, lqng_status_nonzero, false, nullptr);
+}
+
+extern "C" int hk_raceN_run_device(const hk_track* t, const hk_race_params* p, hk_race_planner* pl, int K, int lqr_every, int n_races, int first_step,
+                                   int n_steps, hk_race_kart* d_karts, hk_race_plan* d_plans, hk_race_belief* d_beliefs, double* d_u_hold,
+                                   int64_t* lqng_status_nonzero, void* cuda_stream)
+{
+    return raceN_run_impl(t, p, pl, K, lqr_every, n_races, first_step, n_steps, d_karts, d_plans, d_beliefs, d_u_hold, lqng_status_nonzero, true, cuda_stream);
 }

@@ -125,6 +125,24 @@ class Races:
                                                          abi.vptr(karts), abi.vptr(plans), abi.dptr(u), C.byref(bad)))
         return u, bad.value
 
+    def run_device(self, d_karts, d_plans, first_step: int, n_steps: int, planner: "Planner | None" = None, d_u=None, stream: int = 0) -> int:
+        """hk_race_run_device: the loop on race states that stay in device memory.  d_karts / d_plans: objects with data_ptr() (torch uint8
+        tensors holding the hk_race_kart / hk_race_plan records, e.g. device_state()) or raw device addresses; d_u: [n_agents][4] doubles
+        or None; stream: a cudaStream_t handle (0 = the calling thread's own).  Returns the number of solves with a zero pivot."""
+        ptr = lambda x: None if x is None else C.c_void_p(x.data_ptr() if hasattr(x, "data_ptr") else int(x))
+        n_races = self._n_races_of(d_karts, C.sizeof(abi.hk_race_kart) * 2)
+        bad = C.c_int64(0)
+        abi.check(abi.load_library().hk_race_run_device(self._h, C.byref(self.params), planner._h if planner is not None else None, n_races,
+                                                        first_step, n_steps, ptr(d_karts), ptr(d_plans), ptr(d_u), C.byref(bad),
+                                                        C.c_void_p(stream) if stream else None))
+        return bad.value
+
+    @staticmethod
+    def _n_races_of(d_karts, bytes_per_race: int) -> int:
+        n = d_karts.numel() * d_karts.element_size()
+        assert n % bytes_per_race == 0
+        return n // bytes_per_race
+
     def run_mcts(self, karts: np.ndarray, plans: np.ndarray, game, iterations: int, rollouts_per_leaf: int, seed: int, first_step: int,
                  n_steps: int):
         """hk_race_run_mcts: the loop with the MCTS high level entirely on the GPU (root states, tree search, waypoint hand-off between
@@ -193,6 +211,29 @@ class RacesN(Races):
                                                   karts.shape[0], first_step, n_steps, abi.vptr(karts), abi.vptr(plans), abi.vptr(beliefs),
                                                   abi.vptr(u_hold), C.byref(bad)))
         return bad.value
+
+    def run_n_device(self, d_karts, d_plans, d_beliefs, d_u_hold, first_step: int, n_steps: int, planner: "Planner | None" = None, stream: int = 0) -> int:
+        """hk_raceN_run_device: the loop on states that stay in device memory (torch tensors from device_state(); d_u_hold: float64 tensor
+        [n_agents][8], zeros at the start of a race)."""
+        n_races = d_karts.numel() * d_karts.element_size() // (C.sizeof(abi.hk_race_kart) * self.K)
+        bad = C.c_int64(0)
+        abi.check(abi.load_library().hk_raceN_run_device(self._h, C.byref(self.params), planner._h if planner is not None else None, self.K,
+                                                         self.lqr_every, n_races, first_step, n_steps, C.c_void_p(d_karts.data_ptr()),
+                                                         C.c_void_p(d_plans.data_ptr()), C.c_void_p(d_beliefs.data_ptr()),
+                                                         C.c_void_p(d_u_hold.data_ptr()), C.byref(bad), C.c_void_p(stream) if stream else None))
+        return bad.value
+
+
+def device_state(*arrays, device="cuda:0"):
+    """Structured numpy arrays (karts, plans, beliefs, ...) as torch uint8 tensors on the device, for the *_device entries; back with
+    host_state()."""
+    import torch
+    return [torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(device) for a in arrays]
+
+
+def host_state(tensor, like: np.ndarray) -> np.ndarray:
+    """A device tensor made by device_state() back as a numpy array with the dtype and shape of `like`."""
+    return tensor.cpu().numpy().view(like.dtype).reshape(like.shape)
 
 
 class Planner:

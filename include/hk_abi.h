@@ -443,6 +443,22 @@ int hk_raceN_run(const hk_track* t, const hk_race_params* p, hk_race_planner* pl
                  int first_step, int n_steps, hk_race_kart* karts, hk_race_plan* plans, hk_race_belief* beliefs, double* u_hold,
                  int64_t* lqng_status_nonzero);
 
+/*
+ * The loops on race states that STAY in device memory between calls (a long race advanced in blocks, or states produced by other
+ * kernels): the same work as hk_race_run / hk_race_run_planned / hk_raceN_run with DEVICE pointers in the same layouts and no upload or
+ * download — a call to the host-pointer entries moves ~1 KB (2 karts) / ~2.3 KB (Duos) per agent each way, which costs more than 200 steps
+ * of the loop itself.  cuda_stream: a cudaStream_t, NULL = the calling thread's own stream.  The call returns after the work has finished
+ * (it brings back lqng_status_nonzero and the trees' status).  planner may be NULL.
+ *   hk_race_run_device:  d_u (may be NULL) [n_races * 2][4]: the LQNG u0 record of the last step of every agent, its own controls first
+ *   hk_raceN_run_device: d_u_hold [n_races * K][8]: the held u0 record of every agent (4-player frame, its own controls first; in/out,
+ *                        zeros at the start of a race)
+ */
+int hk_race_run_device(const hk_track* t, const hk_race_params* p, hk_race_planner* planner, int n_races, int first_step, int n_steps,
+                       hk_race_kart* d_karts, hk_race_plan* d_plans, double* d_u, int64_t* lqng_status_nonzero, void* cuda_stream);
+int hk_raceN_run_device(const hk_track* t, const hk_race_params* p, hk_race_planner* planner, int karts_per_race, int lqr_every, int n_races,
+                        int first_step, int n_steps, hk_race_kart* d_karts, hk_race_plan* d_plans, hk_race_belief* d_beliefs, double* d_u_hold,
+                        int64_t* lqng_status_nonzero, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

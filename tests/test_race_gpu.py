@@ -281,3 +281,57 @@ def test_planned_loop_parity_against_cpu_oracle(hk, oracle, plan_every, delay, f
     assert ((plans["lane"] != 0) | (plans["oppLane"] != 0)).any() and karts["section"][karts["active"] == 1].min() >= 2
     if plan_every == 20 and reuse > 0:
         assert continued > 0                                                                 # constructSearchTree(currentRoot) was exercised
+
+
+def test_device_resident_entries_equal_the_host_pointer_entries(hk):
+    """hk_race_run_device / hk_raceN_run_device (race states that stay in device memory, advanced in blocks, on a caller's stream) against
+    hk_race_run / hk_race_run_planned / hk_raceN_run on the same states: identical bytes, the planner's state included."""
+    import torch
+    from hierarchicalkarting_b200 import mcts as M
+    track = S.OVAL
+    prm = R.race_params(track)
+    G = R.Races(track, prm)
+    n = 500
+    karts, plans = R.start_grid(track, n, seed=41)
+    G.plan_fixed(karts, plans)
+    hk_, hp_ = karts.copy(), plans.copy()
+    u_host, bad_h = G.run(hk_, hp_, 0, 230)
+    dk, dp = R.device_state(karts, plans)
+    du = torch.zeros((2 * n, 4), dtype=torch.float64, device="cuda:0")
+    stream = torch.cuda.Stream()
+    bad_d = 0
+    for a, b in ((0, 70), (70, 130), (200, 30)):                       # advanced in blocks; plans at steps 100 and 200 fall inside / on a block edge
+        bad_d += G.run_device(dk, dp, a, b, d_u=du, stream=stream.cuda_stream)
+    assert bad_d == bad_h == 0
+    assert R.host_state(dk, karts).tobytes() == hk_.tobytes() and R.host_state(dp, plans).tobytes() == hp_.tobytes()
+    assert np.array_equal(du.cpu().numpy()[:, :2].reshape(n, 2, 2), u_host)
+    # MCTS planner: device-resident blocks against one host-pointer call
+    prm_m = R.race_params(track, high_mode_mcts=True)
+    prm_m.planEvery = 40
+    Gm = R.Races(track, prm_m)
+    game = M.Game(track, 2, prm_m.velocityBucketSize)
+    karts, plans = R.start_grid(track, 64, seed=42)
+    kw = dict(mode=0, first_iterations=24, reuse_cycles=3, apply_delay=9, max_tree_nodes=1 + 16 * (24 + 12 * 30))
+    p1, p2 = R.Planner(game, 64, 30, seed=5, **kw), R.Planner(game, 64, 30, seed=5, **kw)
+    hk_, hp_ = karts.copy(), plans.copy()
+    Gm.run_planned(hk_, hp_, p1, 0, 170)
+    dk, dp = R.device_state(karts, plans)
+    for a, b in ((0, 45), (45, 80), (125, 45)):                        # a search in flight across a block edge (lands 9 steps after 40, 80, ...)
+        Gm.run_device(dk, dp, a, b, planner=p2)
+    assert R.host_state(dk, karts).tobytes() == hk_.tobytes() and R.host_state(dp, plans).tobytes() == hp_.tobytes()
+    for x, y in zip(p1.state(), p2.state()):
+        assert np.array_equal(x, y)
+    # Duos
+    K = 4
+    GN = R.RacesN(S.COMPLEX, R.race_params(S.COMPLEX), K)
+    karts, plans, beliefs, u = R.start_grid_n(S.COMPLEX, 200, K, seed=43)
+    GN.plan_fixed(karts, plans)
+    hk_, hp_, hb_, hu_ = karts.copy(), plans.copy(), beliefs.copy(), u.copy()
+    GN.run_n(hk_, hp_, hb_, hu_, 0, 150)
+    dk, dp, db = R.device_state(karts, plans, beliefs)
+    du8 = torch.zeros((200 * K, 8), dtype=torch.float64, device="cuda:0")
+    for a, b in ((0, 50), (50, 3), (53, 97)):                          # block edges off the every-4th-step solve: the held controls carry over
+        GN.run_n_device(dk, dp, db, du8, a, b)
+    assert R.host_state(dk, karts).tobytes() == hk_.tobytes() and R.host_state(dp, plans).tobytes() == hp_.tobytes()
+    assert R.host_state(db, beliefs).tobytes() == hb_.tobytes()
+    assert np.array_equal(du8.cpu().numpy()[:, :2].reshape(200, K, 2), hu_)
