@@ -588,6 +588,99 @@ __device__ int rollout_packed2(const DevGame& g, const Tables& tb, hk_game_state
     return ply;
 }
 
+// The same for games of three and four karts (Duos: BASELINE config 3's game inside the search): NK packed karts in registers, the
+// moving kart picked and written back by select chains (an indexed array would live in local memory).  upNext (:188-243) as up_next()
+// has it: for four karts the minimum under (section, time, -avgVelocity) among the karts not yet at last + 1, lowest index on ties; for
+// three the unstable 3-exchange network of List.Sort.  Used by the sequential search's playouts (seq_playouts_kernel<4>).
+template <int NK, bool REC>
+__device__ int rollout_packedN(const DevGame& g, const Tables& tb, hk_game_state& st, K2 k0, K2 k1, K2 k2, K2 k3, unsigned long long seed,
+                               unsigned long long rid, float* scores, int& n_scores, int ply, unsigned* rec_plies, int cap)
+{
+    static_assert(NK == 3 || NK == 4, "three or four karts");
+    int last = st.lastCompletedSection, lcs_idx = last % g.n_sections;
+    const int fin = st.finalSection, b = g.p.velocityBucketSize;
+    unsigned pending = 0;
+    bool have_pending = false;
+    auto cmp = [](const K2& a, const K2& c) -> int {                  // cmp_kart on packed karts (the average velocity is monotone in the level)
+        if (a.sec != c.sec) return a.sec < c.sec ? -1 : 1;
+        if (a.time != c.time) return a.time < c.time ? -1 : 1;
+        const int la = (a.misc >> 8) & 15, lc = (c.misc >> 8) & 15;
+        return la > lc ? -1 : (la == lc ? 0 : 1);
+    };
+    for (;;) {
+        int np = -1;
+        if (NK == 3) {
+            int o0 = 0, o1 = 1, o2 = 2, t;
+            auto kk = [&](int i) -> const K2& { return i == 0 ? k0 : i == 1 ? k1 : k2; };
+            if (cmp(kk(o0), kk(o1)) > 0) { t = o0; o0 = o1; o1 = t; }
+            if (cmp(kk(o0), kk(o2)) > 0) { t = o0; o0 = o2; o2 = t; }
+            if (cmp(kk(o1), kk(o2)) > 0) { t = o1; o1 = o2; o2 = t; }
+            if (kk(o0).sec != last + 1) np = o0;
+            else if (kk(o1).sec != last + 1) np = o1;
+            else if (kk(o2).sec != last + 1) np = o2;
+        } else {
+            K2 best = k0;
+            if (k0.sec != last + 1) np = 0;
+            if (k1.sec != last + 1 && (np < 0 || cmp(k1, best) < 0)) { np = 1; best = k1; }
+            if (k2.sec != last + 1 && (np < 0 || cmp(k2, best) < 0)) { np = 2; best = k2; }
+            if (k3.sec != last + 1 && (np < 0 || cmp(k3, best) < 0)) { np = 3; best = k3; }
+        }
+        if (REC && have_pending) rec_plies[ply - 1] = pending | (((unsigned)np & 0xffu) << 16);
+        if (np < 0) return -1;
+        const K2 k = np == 0 ? k0 : np == 1 ? k1 : np == 2 ? k2 : k3;
+        const int l0 = k.misc & 3, sidx = (k.misc >> 2) & 63, lvl = (k.misc >> 8) & 15, lc = k.misc >> 12;
+        const int type = g.type_of[sidx], flags = g.sec_flags[sidx];
+        const int os = (g.sec_flags[lcs_idx] >> 2) & 3;                                                   // KartMCTS.cs:252
+        const float wear = (float)k.tire / 10000.0f;
+        const int maxdl = (flags & 1) ? g.p.maxLaneChanges - lc : 99;                                     // :346
+        const size_t cell = (((size_t)type * 4 + l0) * tb.nv + lvl) * 3 + os;
+        const unsigned long long* od = tb.od + cell * tb.nc;
+        const unsigned long long* lm = tb.lmask + cell * 4 * tb.nv;
+        unsigned long long mv[4];
+        bool okl[4];
+#pragma unroll
+        for (int l1 = 0; l1 < 4; ++l1) {
+            const float ms = max_speed_radius_wear(g.karts[np], g.radius_tab[type * 16 + l0 * 4 + l1], wear);
+            const int mi = (int)fminf(ms, 1000.0f);                                                     // fminf(NaN, x) = x
+            okl[l1] = abs(l1 - l0) <= maxdl && mi >= 6;
+            const int jm = min(div_bucket(max(mi, 6) - 6, b), tb.nv - 1);
+            mv[l1] = __ldg(&lm[l1 * tb.nv + jm]);
+        }
+        unsigned long long mask = 0ull;
+#pragma unroll
+        for (int l1 = 0; l1 < 4; ++l1) mask |= okl[l1] ? mv[l1] : 0ull;
+        const int cnt = __popcll(mask);
+        if (cnt == 0 || last == fin) {                                                                   // isOver (:251-317) on the struct
+            unpack_k2(g, k0, st.karts[0]); unpack_k2(g, k1, st.karts[1]); unpack_k2(g, k2, st.karts[2]);
+            if (NK == 4) unpack_k2(g, k3, st.karts[3]);
+            st.lastCompletedSection = last;
+            if (is_over(g, st, cnt, np, scores, n_scores)) break;
+        }
+        const int index = policy_index(g, cnt, philox_first(seed, rid, (unsigned)ply));
+        const unsigned long long mvrec = __ldg(&od[nth_set_bit(mask, index)]);
+        const int gi = (int)(mvrec & 0xFFull);
+        if (REC) {
+            if (ply >= cap) return -2;
+            pending = (unsigned)gi | ((unsigned)cnt << 8);
+            have_pending = true;
+        }
+        const int l1 = gi & 3, j = gi >> 2;
+        const int dtv = (int)(unsigned)(mvrec >> 8);
+        const float load = __ldg(&tb.load[((size_t)type * 16 + l0 * 4 + l1) * tb.nv + j]);
+        K2 nk;
+        const int nlc = (flags & 2) ? 0 : lc + abs(l1 - l0);
+        const int nsidx = sidx + 1 == g.n_sections ? 0 : sidx + 1;
+        nk.tire = f2i(((float)k.tire / 10000.0f + load * g.env_karts[0].tireWearFactor) * (float)10000);
+        nk.time = (int)((unsigned)k.time + (unsigned)dtv);
+        nk.sec = k.sec + 1;
+        nk.misc = l1 | (nsidx << 2) | (j << 8) | (nlc << 12);
+        if (np == 0) k0 = nk; else if (np == 1) k1 = nk; else if (np == 2) k2 = nk; else k3 = nk;
+        if (k0.sec > last && k1.sec > last && k2.sec > last && (NK == 3 || k3.sec > last)) { last += 1; lcs_idx = lcs_idx + 1 == g.n_sections ? 0 : lcs_idx + 1; }
+        ++ply;
+    }
+    return ply;
+}
+
 template <bool TRACE>
 __device__ int rollout(const DevGame& g, hk_game_state st, unsigned long long seed, unsigned long long rid, float* scores,
                        int& n_scores, int& first_gi, hk_action* act_out, int* choice_out, const RootMoves* root = nullptr)
@@ -1432,7 +1525,11 @@ int mcts_seq_search_device(hk_mcts_forest* f, const hk_game_state* d_roots, cons
         const int count = base + chunk <= iterations ? (int)chunk : iterations - base;
         const long long threads = (long long)f->n_trees * count;
         count_launch();
-        seq_playouts_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(f->g->dev, f->trees, f->n_trees, d_fresh, f->remaining, count, base, cap, f->recs);
+        static const bool packn = !(getenv("HK_SEQ_PACKN") && atoi(getenv("HK_SEQ_PACKN")) == 0);     // measurement knob: struct-based playouts for 3-4 karts
+        if (f->g->host.n_karts >= 3 && packn)
+            seq_playouts_kernel<4><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(f->g->dev, f->trees, f->n_trees, d_fresh, f->remaining, count, base, cap, f->recs);
+        else
+            seq_playouts_kernel<2><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(f->g->dev, f->trees, f->n_trees, d_fresh, f->remaining, count, base, cap, f->recs);
         HK_CUDA(cudaGetLastError());
         count_launch();
         seq_insert_kernel<<<(unsigned)((f->n_trees + 31) / 32), 32, 0, s>>>(f->trees, f->slabs, f->max_nodes, f->n_trees, d_fresh, f->remaining, count, count,

@@ -310,7 +310,10 @@ __host__ __device__ constexpr size_t seq_rec_words(int cap) { return (size_t)SEQ
 // Once both karts hold action velocity buckets (after their first moves) the playout continues in the packed, register-resident form of the
 // rollout kernel (rollout_packed2<true>, which also leaves the record words): 10.5 -> 7.4 ms per 32,768 trees x 512 iterations.  Resident blocks
 // per SM 3 / 4 / 5 / 6 / 8 (109 / 119 / 96 / 80 / 64 registers): 7.7 / 7.7 / 7.1 / 6.8 / 7.8 ms.
-__global__ void __launch_bounds__(128, 6) seq_playouts_kernel(const DevGame* __restrict__ gg, const SeqTree* __restrict__ trees, int n_trees,
+// NKMAX 2: games of one or two karts; 4: three or four karts with their own packed form (rollout_packedN) — 13.1 -> 11.9 ms per 32,768 Duos
+// trees x 256 iterations at 5 blocks per SM (12.3 ms at 4): the select chains and the 4-way upNext keep a ply ~1.7x as expensive as with two karts.
+template <int NKMAX>
+__global__ void __launch_bounds__(128, NKMAX == 2 ? 6 : 5) seq_playouts_kernel(const DevGame* __restrict__ gg, const SeqTree* __restrict__ trees, int n_trees,
                                                            const int* __restrict__ fresh, const int* __restrict__ remaining, int chunk, int base,
                                                            int cap, unsigned* __restrict__ recs)
 {
@@ -332,11 +335,21 @@ __global__ void __launch_bounds__(128, 6) seq_playouts_kernel(const DevGame* __r
     unsigned ply = 0;
     for (;; ++ply) {
         if (np < 0) { err = 1; break; }
-        if (g.tables_ok && st.n_karts == 2) {                          // both karts at action buckets: the rest runs packed in registers
+        if (NKMAX == 2 && g.tables_ok && st.n_karts == 2) {            // both karts at action buckets: the rest runs packed in registers
             K2 k0, k1;
             if (pack_k2(g, st.karts[0], k0) && pack_k2(g, st.karts[1], k1)) {
                 int first_gi = -1;
                 const int r = rollout_packed2<true>(g, tb, st, k0, k1, tr.key, it, scores, n_scores, first_gi, (int)ply, rec + SEQ_REC_HEAD, cap);
+                if (r < 0) err = r == -1 ? 1 : 3; else ply = (unsigned)r;
+                break;
+            }
+        }
+        if (NKMAX == 4 && g.tables_ok && st.n_karts >= 3) {            // every kart at an action bucket
+            K2 k0, k1, k2, k3 = K2{0, 0, 0, 0};
+            if (pack_k2(g, st.karts[0], k0) && pack_k2(g, st.karts[1], k1) && pack_k2(g, st.karts[2], k2) &&
+                (st.n_karts == 3 || pack_k2(g, st.karts[3], k3))) {
+                const int r = st.n_karts == 3 ? rollout_packedN<3, true>(g, tb, st, k0, k1, k2, k3, tr.key, it, scores, n_scores, (int)ply, rec + SEQ_REC_HEAD, cap)
+                                              : rollout_packedN<4, true>(g, tb, st, k0, k1, k2, k3, tr.key, it, scores, n_scores, (int)ply, rec + SEQ_REC_HEAD, cap);
                 if (r < 0) err = r == -1 ? 1 : 3; else ply = (unsigned)r;
                 break;
             }
