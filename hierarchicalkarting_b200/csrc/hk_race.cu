@@ -251,6 +251,18 @@ __global__ void race_step_kernel(const DevTrack* __restrict__ t, hk_race_params 
     race_step_body(t, p, i, episode_step, u, u_stride, lqng_status, status_count, karts, plans, root_valid, cycles);
 }
 
+// n_sub consecutive steps with the same (held) controls in one launch: the loops with a solve every lqr_every-th step (Duos) have nothing
+// between two plant steps unless a planning event falls there.  The LQNG status is counted once, with the first step.
+__global__ void race_steps_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_karts, int first_step, int n_sub, const double* __restrict__ u,
+                                  int u_stride, const int* __restrict__ lqng_status, unsigned long long* status_count, hk_race_kart* karts,
+                                  hk_race_plan* plans, int* __restrict__ root_valid, int* __restrict__ cycles)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_karts) return;
+    for (int k = 0; k < n_sub; ++k)
+        race_step_body(t, p, i, first_step + k, u, u_stride, k == 0 ? lqng_status : nullptr, status_count, karts, plans, root_valid, cycles);
+}
+
 // The step of one FixedUpdate and the problem description of the NEXT one in one launch (2-kart races; no planning event between the two):
 // the two karts of a race are neighbouring lanes of a warp, so the partner's new state is there after a __syncwarp.  Two launches and the
 // (cos h, sin h) kernel less per step of the loop.
@@ -1066,6 +1078,7 @@ static int raceN_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pl
     for (size_t v : per) out_elems += v;
     const size_t in_bytes = nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan)) + nb * K * sizeof(hk_race_belief);
     static const bool split = !(getenv("HK_RACEN_SPLIT") && atoi(getenv("HK_RACEN_SPLIT")) == 0);   // measurement knob: every game in the 4-player frame
+    static const bool multi = !(getenv("HK_RACEN_MULTISTEP") && atoi(getenv("HK_RACEN_MULTISTEP")) == 0);   // measurement knob: one launch per step
     char* d = (char*)dscratch(c, 8, in_bytes + nb * (8 * sizeof(int) + (out_elems + 48) * sizeof(double)) + 512);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
     hk_race_kart* dk = on_device ? karts : (hk_race_kart*)d;
@@ -1140,10 +1153,16 @@ static int raceN_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pl
                 HK_CUDA_DRAIN(cudaGetLastError());
             }
         }
+        // the steps up to the next solve / planning event ride in the same launch (held controls, no kernel in between)
+        int n_sub = 1;
+        while (multi && step + n_sub < first_step + n_steps && (step + n_sub) % lqr_every != 0 && (step + n_sub) % p->planEvery != 0 &&
+               !(pl && pl->pending_step == step + n_sub))
+            ++n_sub;
         count_launch();
-        race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 8, solve ? dst : nullptr, dcount, dk, dp, pl ? pl->root_valid : nullptr,
-                                                pl ? pl->cycles : nullptr);
+        race_steps_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, n_sub, du, 8, solve ? dst : nullptr, dcount, dk, dp, pl ? pl->root_valid : nullptr,
+                                                 pl ? pl->cycles : nullptr);
         HK_CUDA_DRAIN(cudaGetLastError());
+        step += n_sub - 1;
     }
     if (!on_device) {
         HK_CUDA_DRAIN(cudaMemcpyAsync(karts, dk, nb * sizeof(hk_race_kart), cudaMemcpyDeviceToHost, s));
