@@ -730,13 +730,15 @@ namespace hk {
 
 struct PlanView { const int8_t* lane; const float* vel; };
 
-// One thread per agent: the whole N-player problem of that agent's game in the 4-player layout (dummy players zero, cw = 1).
+// Four threads per agent, one per player slot of the 4-player layout (dummy players zero, cw = 1): each repeats the cheap prelude (who takes
+// part) and builds one player's description — the float math of a player (atan2f, pow) is a long dependent chain and the batch is small.
 __global__ void raceN_recipe_kernel(const DevTrack* __restrict__ t, hk_race_params p, int K, int n_agents, const hk_race_kart* __restrict__ karts,
                                     const hk_race_plan* __restrict__ plans, const hk_race_belief* __restrict__ beliefs, int* __restrict__ n_players,
                                     int* __restrict__ players_out, double* x0, double* target, double* tw, double* cw, double* aw, double* otgt,
                                     double* otw)
 {
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int id = gid >> 2, i = gid & 3;
     if (id >= n_agents) return;
     const int e = id % K;
     const hk_race_kart* rk = karts + (id - e);
@@ -756,8 +758,10 @@ __global__ void raceN_recipe_kernel(const DevTrack* __restrict__ t, hk_race_para
         for (int i = 0; i < na; ++i) act[N++] = all[i];
     }
     nearby = nearby > 1 ? nearby : 1;                                    // Math.Max(nearbyAgents, 1) :726
-    n_players[id] = N;
-    for (int i = 0; i < HK_MAX_KARTS; ++i) players_out[id * 4 + i] = i < N ? act[i] : -1;
+    if (i == 0) {
+        n_players[id] = N;
+        for (int j = 0; j < HK_MAX_KARTS; ++j) players_out[id * 4 + j] = j < N ? act[j] : -1;
+    }
     unsigned in_game = 0;
     for (int i = 0; i < N; ++i) in_game |= 1u << act[i];
     const double max_speed = (double)p.topSpeed;
@@ -775,7 +779,7 @@ __global__ void raceN_recipe_kernel(const DevTrack* __restrict__ t, hk_race_para
             v = max_speed < vv ? max_speed : vv;
         } else { x = t->trig[idx][0]; z = t->trig[idx][1]; v = max_speed; }
     };
-    for (int i = 0; i < HK_MAX_KARTS; ++i) {
+    {
         const size_t o4 = ((size_t)id * 4 + i) * 4;
         double* xo = x0 + o4; double* tg = target + o4; double* w = tw + o4;
         double* awi = aw + ((size_t)id * 4 + i) * 6; double* ogi = otgt + ((size_t)id * 4 + i) * 12; double* owi = otw + ((size_t)id * 4 + i) * 9;
@@ -785,7 +789,7 @@ __global__ void raceN_recipe_kernel(const DevTrack* __restrict__ t, hk_race_para
         if (i >= N) {                                                    // dummy player
             for (int c = 0; c < 4; ++c) { xo[c] = 0.0; tg[c] = 0.0; w[c] = 0.0; }
             cw[(size_t)id * 4 + i] = 1.0;
-            continue;
+            return;
         }
         const int kI = act[i];
         const hk_race_kart k = rk[kI];
@@ -978,7 +982,7 @@ extern "C" int hk_raceN_recipe(const hk_track* t, const hk_race_params* p, int K
     HK_CUDA_DRAIN(cudaMemcpyAsync(dp, plans, nb * sizeof(hk_race_plan), cudaMemcpyHostToDevice, s));
     HK_CUDA_DRAIN(cudaMemcpyAsync(db, beliefs, nb * K * sizeof(hk_race_belief), cudaMemcpyHostToDevice, s));
     count_launch();
-    raceN_recipe_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(t->dev, *p, K, (int)nb, dk, dp, db, dn, dpl, dout[0], dout[1], dout[2], dout[3],
+    raceN_recipe_kernel<<<(unsigned)((nb * 4 + 127) / 128), 128, 0, s>>>(t->dev, *p, K, (int)nb, dk, dp, db, dn, dpl, dout[0], dout[1], dout[2], dout[3],
                                                                    dout[4], dout[5], dout[6]);
     HK_CUDA_DRAIN(cudaGetLastError());
     double* hout[7] = {x0, target, tw, cw, aw, otgt, otw};
@@ -1135,7 +1139,7 @@ static int raceN_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pl
         const bool solve = step % lqr_every == 0;                        // 50 Hz with 2 agents, every 4th step with more (:317)
         if (solve) {
             count_launch();
-            raceN_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, K, (int)nb, dk, dp, db, dn, dpl, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6]);
+            raceN_recipe_kernel<<<(unsigned)((nb * 4 + 127) / 128), 128, 0, s>>>(t->dev, *p, K, (int)nb, dk, dp, db, dn, dpl, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6]);
             HK_CUDA_DRAIN(cudaGetLastError());
             if (split) {
                 const long long el = (long long)nb * 44;
