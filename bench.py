@@ -487,7 +487,14 @@ def main():
             mcts_obj["tree_search"] = {"ms_per_decision": 1e3 * el_seq, "iterations": 512, "episodes_at_root": int(root.numEpisodes),
                                        "nodes": int(root.childrenAsRoot), "best_sequence_states": len(seq), "parallel": False,
                                        "api": "KartMCTS.constructSearchTree(state, parallel=false) + getBestStatesSequence (Python mirror of the C# API "
-                                              "over the C-ABI): the reference's sequential search, one GPU thread, incl. the node-record download"}
+                                              "over the C-ABI): the reference's sequential search, one GPU thread, incl. the node-record download and the Python "
+                                              "KartMCTSNode graph; native_call_ms = hk_mcts_forest_search for this one tree alone"}
+            F1 = M.Forest(G, 1, 1 + 512 * 16)                                                     # the native call alone (what the C# shim waits for)
+            F1.search([leaf], 32, 7)
+            t0 = time.perf_counter()
+            F1.search([leaf], 512, 20260003)
+            mcts_obj["tree_search"]["native_call_ms"] = 1e3 * (time.perf_counter() - t0)
+            F1.close()
             M.KartMCTS.rollouts_per_leaf = 4096
             M.KartMCTS.constructSearchTree(root_state, T=1e9, seed=7, max_iterations=3, parallel=True)          # warm-up
             t0 = time.perf_counter()
