@@ -735,8 +735,11 @@ struct PlanView { const int8_t* lane; const float* vel; };
 __global__ void raceN_recipe_kernel(const DevTrack* __restrict__ t, hk_race_params p, int K, int n_agents, const hk_race_kart* __restrict__ karts,
                                     const hk_race_plan* __restrict__ plans, const hk_race_belief* __restrict__ beliefs, int* __restrict__ n_players,
                                     int* __restrict__ players_out, double* x0, double* target, double* tw, double* cw, double* aw, double* otgt,
-                                    double* otw)
+                                    double* otw, double* rec2 = nullptr, double* cs2 = nullptr, int* __restrict__ n2 = nullptr)
 {
+    // rec2 (the loop): a game of one or two players is written straight as the 44-double record of the 2-kart kernel (+ its (cos h, sin h)
+    // pairs, (0, 0) marking a dummy player) and NOT in the 4-player layout; a game of three or four gets an all-dummy record there (the
+    // 2-kart launch covers every slot) and the 4-player layout as before.  n2 = players of the record (0 for the all-dummy one).
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int id = gid >> 2, i = gid & 3;
     if (id >= n_agents) return;
@@ -761,7 +764,17 @@ __global__ void raceN_recipe_kernel(const DevTrack* __restrict__ t, hk_race_para
     if (i == 0) {
         n_players[id] = N;
         for (int j = 0; j < HK_MAX_KARTS; ++j) players_out[id * 4 + j] = j < N ? act[j] : -1;
+        if (n2) n2[id] = N <= 2 ? N : 0;
     }
+    const bool small = rec2 != nullptr && N <= 2;
+    if (rec2 && i < 2 && (N > 2 || i >= N)) {                            // dummy player i of the 2-kart record: zero weights, control weight 1
+        double* r = rec2 + (size_t)id * 44;
+        for (int c = 0; c < 4; ++c) { r[i * 4 + c] = 0.0; r[8 + i * 4 + c] = 0.0; r[16 + i * 4 + c] = 0.0; r[30 + i * 4 + c] = 0.0; }
+        r[24 + i] = 1.0; r[26 + i * 2] = 0.0; r[26 + i * 2 + 1] = 0.0;
+        for (int c = 0; c < 3; ++c) r[38 + i * 3 + c] = 0.0;
+        cs2[(size_t)id * 4 + 2 * i] = 0.0; cs2[(size_t)id * 4 + 2 * i + 1] = 0.0;
+    }
+    if (small && i >= N) return;                                         // nothing of this game goes to the 4-player layout
     unsigned in_game = 0;
     for (int i = 0; i < N; ++i) in_game |= 1u << act[i];
     const double max_speed = (double)p.topSpeed;
@@ -781,19 +794,24 @@ __global__ void raceN_recipe_kernel(const DevTrack* __restrict__ t, hk_race_para
     };
     {
         const size_t o4 = ((size_t)id * 4 + i) * 4;
-        double* xo = x0 + o4; double* tg = target + o4; double* w = tw + o4;
-        double* awi = aw + ((size_t)id * 4 + i) * 6; double* ogi = otgt + ((size_t)id * 4 + i) * 12; double* owi = otw + ((size_t)id * 4 + i) * 9;
-        for (int c = 0; c < 6; ++c) awi[c] = 0.0;
-        for (int c = 0; c < 12; ++c) ogi[c] = 0.0;
-        for (int c = 0; c < 9; ++c) owi[c] = 0.0;
+        double* r2 = small ? rec2 + (size_t)id * 44 : nullptr;
+        double* xo = small ? r2 + i * 4 : x0 + o4; double* tg = small ? r2 + 8 + i * 4 : target + o4; double* w = small ? r2 + 16 + i * 4 : tw + o4;
+        double* awi = small ? r2 + 26 + i * 2 : aw + ((size_t)id * 4 + i) * 6;
+        double* ogi = small ? r2 + 30 + i * 4 : otgt + ((size_t)id * 4 + i) * 12;
+        double* owi = small ? r2 + 38 + i * 3 : otw + ((size_t)id * 4 + i) * 9;
+        double* cwp = small ? r2 + 24 + i : cw + (size_t)id * 4 + i;
+        for (int c = 0; c < (small ? 2 : 6); ++c) awi[c] = 0.0;           // a 2-kart record has one private slot per player
+        for (int c = 0; c < (small ? 4 : 12); ++c) ogi[c] = 0.0;
+        for (int c = 0; c < (small ? 3 : 9); ++c) owi[c] = 0.0;
         if (i >= N) {                                                    // dummy player
             for (int c = 0; c < 4; ++c) { xo[c] = 0.0; tg[c] = 0.0; w[c] = 0.0; }
-            cw[(size_t)id * 4 + i] = 1.0;
+            *cwp = 1.0;
             return;
         }
         const int kI = act[i];
         const hk_race_kart k = rk[kI];
         xo[0] = k.x; xo[1] = k.z; xo[2] = k.v; xo[3] = k.h;              // :730-736
+        if (small) { cs2[(size_t)id * 4 + 2 * i] = cos(k.h); cs2[(size_t)id * 4 + 2 * i + 1] = sin(k.h); }
         const int s = k.section + 1;                                     // :745
         const int idx = s % t->n, idx2 = (s + 1) % t->n;
         double lx, lz, vel, nlx, nlz, nvel;
@@ -828,7 +846,7 @@ __global__ void raceN_recipe_kernel(const DevTrack* __restrict__ t, hk_race_para
         w[3] = N > 2 ? (fixed ? 2.5 : 3.5) * nearby : (fixed ? 1.9 : 3.5);
         const double wxz = stopped ? nearby * 0.3 * 3.1 : nearby * 0.3 * 3.1 / vmax1;
         w[0] = wxz; w[1] = wxz; w[2] = stopped ? (double)(nearby * -2) : nearby * 5e-4;
-        cw[(size_t)id * 4 + i] = N > 2 ? (fixed ? 0.135 : 0.25) : 0.115;               // :1192-1196
+        *cwp = N > 2 ? (fixed ? 0.135 : 0.25) : 0.115;                                  // :1192-1196
         float mult;                                                      // :977-1003
         if (K > 2 && N > 2) mult = kI == e ? (fixed ? 0.55f : 1.0f) / nearby : 1.7f / nearby;
         else mult = kI == e ? (fixed ? 0.45f : 1.0f) : 1.3f;
@@ -993,28 +1011,10 @@ extern "C" int hk_raceN_recipe(const hk_track* t, const hk_race_params* p, int K
     return HK_OK;
 }
 
-// Games of one or two players (after the 8 m filter most are) do not need the 4-player frame: their description is repacked as the 44-double
-// record of the 2-kart kernel — player 1 of a one-player game a decoupled dummy (zero weights, control weight 1; lqng_trig_kernel marks it and the
-// kernel assembles A = I, B = 0) — and lqng_mma4_kernel is gated to the games of three and four.  A game of three or four gets an all-dummy
-// record here (the 2-kart launch covers every slot; its answer for those slots is not used).  One thread per record element.
-__global__ void raceN_pack2_kernel(int n_agents, const int* __restrict__ n_players, const double* __restrict__ x0, const double* __restrict__ target,
-                                   const double* __restrict__ tw, const double* __restrict__ cw, const double* __restrict__ aw,
-                                   const double* __restrict__ otgt, const double* __restrict__ otw, double* __restrict__ rec2, int* __restrict__ n2)
-{
-    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= (long long)n_agents * 44) return;
-    const size_t b = (size_t)(id / 44);
-    const int e = (int)(id % 44), N = n_players[b], NN = N <= 2 ? N : 0;
-    if (e == 0) n2[b] = NN;
-    double v = 0.0;
-    if (e < 24) { const int i = (e & 7) >> 2, s = e & 3; if (i < NN) v = (e < 8 ? x0 : e < 16 ? target : tw)[b * 16 + i * 4 + s]; }
-    else if (e < 26) { const int i = e - 24; v = i < NN ? cw[b * 4 + i] : 1.0; }
-    else if (e < 30) { const int i = (e - 26) >> 1, s = (e - 26) & 1; if (i < NN) v = aw[b * 24 + i * 6 + s]; }           // private slot 0: the only other player
-    else if (e < 38) { const int i = (e - 30) >> 2, s = (e - 30) & 3; if (i < NN) v = otgt[b * 48 + i * 12 + s]; }
-    else { const int i = (e - 38) / 3, s = (e - 38) % 3; if (i < NN) v = otw[b * 36 + i * 9 + s]; }
-    rec2[id] = v;
-}
-
+// Games of one or two players (after the 8 m filter most are) do not need the 4-player frame: raceN_recipe_kernel writes them as the
+// 44-double record of the 2-kart kernel — player 1 of a one-player game a decoupled dummy (zero weights, control weight 1, (cos h, sin h) =
+// (0, 0): the kernel assembles A = I, B = 0) — and lqng_mma4_kernel is gated to the games of three and four.  A game of three or four
+// gets an all-dummy record there (the 2-kart launch covers every slot; its answer for those slots is not used).
 __global__ void raceN_merge2_kernel(int n_agents, const int* __restrict__ n_players, const double* __restrict__ u2, const int* __restrict__ st2,
                                     double* __restrict__ u, int* __restrict__ st)
 {
@@ -1083,7 +1083,7 @@ static int raceN_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pl
     const size_t in_bytes = nb * (sizeof(hk_race_kart) + sizeof(hk_race_plan)) + nb * K * sizeof(hk_race_belief);
     static const bool split = !(getenv("HK_RACEN_SPLIT") && atoi(getenv("HK_RACEN_SPLIT")) == 0);   // measurement knob: every game in the 4-player frame
     static const bool multi = !(getenv("HK_RACEN_MULTISTEP") && atoi(getenv("HK_RACEN_MULTISTEP")) == 0);   // measurement knob: one launch per step
-    char* d = (char*)dscratch(c, 8, in_bytes + nb * (8 * sizeof(int) + (out_elems + 48) * sizeof(double)) + 512);
+    char* d = (char*)dscratch(c, 8, in_bytes + nb * (8 * sizeof(int) + (out_elems + 52) * sizeof(double)) + 512);
     if (!d) return HK_ERR_OUT_OF_MEMORY;
     hk_race_kart* dk = on_device ? karts : (hk_race_kart*)d;
     hk_race_plan* dp = on_device ? plans : (hk_race_plan*)((hk_race_kart*)d + nb);
@@ -1094,7 +1094,8 @@ static int raceN_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pl
     double* du = on_device ? u_hold : o; o += nb * 8;
     unsigned long long* dcount = (unsigned long long*)o;
     double* drec2 = (double*)(dcount + 2); double* du2 = drec2 + nb * 44;                // 2-kart records and answers of the small games
-    int* dn = (int*)(du2 + nb * 4); int* dpl = dn + nb; int* dst = dpl + nb * 4; int* dn2 = dst + nb; int* dst2 = dn2 + nb;
+    double* dcs2 = du2 + nb * 4;
+    int* dn = (int*)(dcs2 + nb * 4); int* dpl = dn + nb; int* dst = dpl + nb * 4; int* dn2 = dst + nb; int* dst2 = dn2 + nb;
     cudaStream_t s = (on_device && user_stream) ? (cudaStream_t)user_stream : c->stream;
     if (!on_device) {
         HK_CUDA_DRAIN(cudaMemcpyAsync(dk, karts, nb * sizeof(hk_race_kart), cudaMemcpyHostToDevice, s));
@@ -1139,14 +1140,11 @@ static int raceN_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pl
         const bool solve = step % lqr_every == 0;                        // 50 Hz with 2 agents, every 4th step with more (:317)
         if (solve) {
             count_launch();
-            raceN_recipe_kernel<<<(unsigned)((nb * 4 + 127) / 128), 128, 0, s>>>(t->dev, *p, K, (int)nb, dk, dp, db, dn, dpl, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6]);
+            raceN_recipe_kernel<<<(unsigned)((nb * 4 + 127) / 128), 128, 0, s>>>(t->dev, *p, K, (int)nb, dk, dp, db, dn, dpl, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6],
+                                                                                 split ? drec2 : nullptr, split ? dcs2 : nullptr, split ? dn2 : nullptr);
             HK_CUDA_DRAIN(cudaGetLastError());
-            if (split) {
-                const long long el = (long long)nb * 44;
-                count_launch();
-                raceN_pack2_kernel<<<(unsigned)((el + 255) / 256), 256, 0, s>>>((int)nb, dn, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6], drec2, dn2);
-                HK_CUDA_DRAIN(cudaGetLastError());
-                rc = lqng_assemble_launch_packed((int)nb, 2, p->horizon, p->dt, drec2, du2, dst2, s, 10, dn2);
+            if (split) {                                                   // the small games: records and (cos h, sin h) pairs come from the recipe kernel
+                rc = lqng_assemble_launch_packed((int)nb, 2, p->horizon, p->dt, drec2, du2, dst2, s, 10, dn2, dcs2);
                 if (rc) { drain(c); return rc; }
             }
             rc = lqng_assemble_launch((int)nb, 4, p->horizon, p->dt, dout[0], dout[1], dout[2], dout[3], dout[4], dout[5], dout[6], du, dst, s, 9, dn, split ? 3 : 0);
