@@ -732,6 +732,10 @@ def main():
                 if name == "faithful":                                                         # the same two planning events on HBM-resident states
                     pl = RC.Planner(game_m, RACES, seed=20260006 + 1000 * rank, **kw)
                     dk_m, dp_m = RC.device_state(km, pm, device=dev)
+                    RM.run_device(dk_m, dp_m, 100, 101, planner=pl)                                 # warm-up: one planning event at full size
+                    pl.close()
+                    pl = RC.Planner(game_m, RACES, seed=20260006 + 1000 * rank, **kw)
+                    dk_m, dp_m = RC.device_state(km, pm, device=dev)
                     barrier()
                     t0 = time.perf_counter()
                     bad_dm = RM.run_device(dk_m, dp_m, 100, 100 * blocks_m, planner=pl)
@@ -806,12 +810,19 @@ def main():
                                  "waypoints_set": int((pm4["lane"] != 0).sum()), "beliefs_set": int((bm4["lane"] != 0).sum()),
                                  "trees_out_of_nodes": int((pl4.state()[2] == 3).sum())}
             pl4.close()
-            pl4 = RNm.planner(game4, R4, 256, 20260008 + 1000 * rank, mode=0, reuse_cycles=3, apply_delay=45)
             km4b, pm4b, bm4b, um4b = RC.start_grid_n(S.COMPLEX, R4, 4, seed=20260007 + rank)
             RNm.run_n(km4b, pm4b, bm4b, um4b, 0, 100)
-            dk4, dp4, db4 = RC.device_state(km4b, pm4b, bm4b, device=dev)
-            du4 = torch.zeros((4 * R4, 8), dtype=torch.float64, device=dev)
-            du4[:, :2] = torch.from_numpy(um4b.reshape(-1, 2)).to(dev)
+            def dev4():
+                a, b_, c_ = RC.device_state(km4b, pm4b, bm4b, device=dev)
+                u_ = torch.zeros((4 * R4, 8), dtype=torch.float64, device=dev)
+                u_[:, :2] = torch.from_numpy(um4b.reshape(-1, 2)).to(dev)
+                return a, b_, c_, u_
+            pl4 = RNm.planner(game4, R4, 256, 20260008 + 1000 * rank, mode=0, reuse_cycles=3, apply_delay=45)
+            dk4, dp4, db4, du4 = dev4()
+            RNm.run_n_device(dk4, dp4, db4, du4, 100, 101, planner=pl4)                                # warm-up: one planning event at full size
+            pl4.close()
+            pl4 = RNm.planner(game4, R4, 256, 20260008 + 1000 * rank, mode=0, reuse_cycles=3, apply_delay=45)
+            dk4, dp4, db4, du4 = dev4()
             barrier()
             t0 = time.perf_counter()
             bad4dm = RNm.run_n_device(dk4, dp4, db4, du4, 100, 200, planner=pl4)
