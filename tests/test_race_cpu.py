@@ -260,3 +260,38 @@ def test_fixed_mode_avoid_weight_known_answer(oracle):
         assert out["aw"][0, 0, 0, 0] == out["aw"][0, 0, 0, 1] == want_ego
         assert out["aw"][0, 1, 0, 0] == 0.09615384787321091
         assert out["aw"][1, 0, 0, 0] == want_ego and out["aw"][1, 1, 0, 0] == 0.09615384787321091     # the other agent's own problem
+
+
+def test_duos_recipe_known_answers():
+    """The more-than-two-agents branches of SolveLQR worked out by hand from the C# text for one configuration — four karts, teams [0, 0, 1, 1],
+    all within 8 m of the ego (kart 0 at (14, 0); its teammate 4 m away at (14, 4); the opponents 4 m away at (14, -4) and (18, 0)), 10 m/s:
+      players [this] + teamAgents + otherAgents = [0, 1, 2, 3] (:702), nearbyAgents = -1 + 4 = 3 (:708-721)
+      target weights (:928-947): h = (Fixed ? 2.5 : 3.5) * 3 = 7.5 / 10.5; x = z = 3 * 0.3 * 3.1 / 10 = 0.279; v = 3 * 5e-4 = 0.0015
+      control cost (:1192-1196): Fixed 0.135, MCTS 0.25
+      avoid weights 1f / (Mathf.Pow(d, 1.5f) * multiplier) (:1019), d = 4 -> d^1.5 = 8:
+        ego, opponents:   multiplier (Fixed ? 0.55f : 1.0f) / 3 (:982-985)     -> Fixed 0.6818181872367859, MCTS 0.375
+        ego, teammate:    multiplier / 2 (:1113)                               -> Fixed 1.3636363744735718, MCTS 0.75
+        another player k: multiplier 1.7f / 3; kart 1's teammate (the ego, 4 m) -> 0.44117647409439087 in its private slot 2 (opponents first)
+      opponent-target weights of the ego (:1083-1085): x = z = (Fixed ? 0.1 : 0.2) / (10 * 3), v = 0.08 / 3; teammate-target weights (:1178-1180):
+        x = z = -(Fixed ? 0 : 3e-5) / (10 * 3), v = 0
+    against oracle/np_recipe.py (the restatement the device recipe is checked against in tests/test_raceN_gpu.py)."""
+    from oracle import np_race
+    track = S.OVAL
+    tt = _track_tables(track)
+    for mcts, w_h, cw, a_opp, a_mate, o_xz, m_xz in ((False, 7.5, 0.135, 0.6818181872367859, 1.3636363744735718, 0.1 / 30, -0.0),
+                                                     (True, 10.5, 0.25, 0.375, 0.75, 0.2 / 30, -3e-5 / 30)):
+        prm = R.race_params(track, high_mode_mcts=mcts)
+        karts, plans, beliefs, _ = R.start_grid_n(track, 1, 4, seed=1, teams=[0, 0, 1, 1])
+        karts["x"][0], karts["z"][0], karts["v"][0] = [14.0, 14.0, 14.0, 18.0], [0.0, 4.0, -4.0, 0.0], [10.0] * 4
+        rec = np_race.recipe_agent(tt, prm, karts[0], plans[0], beliefs[0], 0)
+        assert rec["players"] == [0, 1, 2, 3]
+        assert np.array_equal(rec["tw"][0], [3 * 0.3 * 3.1 / 10, 3 * 0.3 * 3.1 / 10, 3 * 5e-4, w_h])
+        assert np.all(np.asarray(rec["cw"]) == cw)
+        assert np.array_equal(rec["aw"][0], [[a_opp, a_opp], [a_opp, a_opp], [a_mate, a_mate]])         # the ego's opponents (karts 2, 3), then its teammate
+        assert rec["aw"][1][2][0] == rec["aw"][1][2][1] == 0.44117647409439087                          # kart 1 about its teammate, the ego
+        assert np.array_equal(rec["otw"][0][:2], [[o_xz, o_xz, 0.08 / 3]] * 2)
+        assert np.array_equal(rec["otw"][0][2], [m_xz, m_xz, 0.0])
+    # a kart further than 8 m away drops out of the game (:713) and nearbyAgents falls to Math.Max(1, 1)
+    karts["x"][0][3] = 23.0
+    rec = np_race.recipe_agent(tt, prm, karts[0], plans[0], beliefs[0], 0)
+    assert rec["players"] == [0, 1, 2] and rec["tw"][0][3] == 3.5 * 2
