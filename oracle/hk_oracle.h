@@ -58,6 +58,10 @@ int  hk_oracle_tree_search_batch(const hk_oracle_game* g, const hk_game_state* r
 void hk_oracle_race_recipe_one(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
                                const hk_race_params* p, const hk_race_kart* karts, const hk_race_plan* plans, int e,
                                double* x0, double* target, double* tw, double* cw, double* aw, double* otgt, double* otw);
+void hk_oracle_raceN_recipe_one(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                                const hk_race_params* p, int K, const hk_race_kart* karts, const hk_race_plan* plans,
+                                const hk_race_belief* beliefs, int e, int* n_players, int* players, double* x0, double* target, double* tw,
+                                double* cw, double* aw, double* otgt, double* otw);
 void hk_oracle_race_recipe(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
                            const hk_race_params* p, int n_races, const hk_race_kart* karts, const hk_race_plan* plans,
                            double* x0, double* target, double* tw, double* cw, double* aw, double* otgt, double* otw);

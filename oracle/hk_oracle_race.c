@@ -127,6 +127,126 @@ void hk_oracle_race_recipe(const hk_section* sections, const double* trig, const
         }
 }
 
+/* SolveLQR's problem for ANY number of agents (HierarchicalKartAgent.cs:699-1201), written from the C# text like the 2-agent function above;
+ * the Python restatement oracle/np_recipe.py is compared with it in tests/.  One race: karts[K], plans[K] (each kart's own plan), beliefs[K]
+ * = the EGO's beliefs about the other karts (opponentUpcomingLanes / Velocities), e = the ego.  Outputs for the n = *n_players real players
+ * in joint order: players[n] (race-local kart), x0[n][4], target[n][4], tw[n][4], cw[n], and per player its n - 1 private slots (its
+ * otherAgents first, then its teamAgents, each in environment order): aw[n][3][2], otgt[n][3][4], otw[n][3][3] (unused slots zero). */
+void hk_oracle_raceN_recipe_one(const hk_section* sections, const double* trig, const double* fwd, const double* lane, int n_sections,
+                                const hk_race_params* p, int K, const hk_race_kart* karts, const hk_race_plan* plans,
+                                const hk_race_belief* beliefs, int e, int* n_players, int* players, double* x0, double* target, double* tw,
+                                double* cw, double* aw, double* otgt, double* otw)
+{
+    const track_view t = {n_sections, sections, trig, fwd, lane};
+    const int fixed = !p->highModeMcts;
+    const hk_race_kart* me = &karts[e];
+    /* allPlayers = { this } + teamAgents + otherAgents (:702) */
+    int all[HK_MAX_KARTS], n_all = 0;
+    all[n_all++] = e;
+    for (int a = 0; a < K; ++a) if (a != e && karts[a].team == me->team) all[n_all++] = a;
+    for (int a = 0; a < K; ++a) if (karts[a].team != me->team) all[n_all++] = a;
+    /* with more than two agents in the environment only those within 8 m of the ego take part (:709-721) */
+    int act[HK_MAX_KARTS], n = 0, nearbyAgents = -1;
+    if (K > 2) {
+        for (int i = 0; i < n_all; ++i) {
+            const hk_race_kart* k = &karts[all[i]];
+            if (magnitude2((float)(k->x - me->x), (float)(k->z - me->z)) < 8) { nearbyAgents += 1; act[n++] = all[i]; }
+        }
+    } else {
+        for (int i = 0; i < n_all; ++i) act[n++] = all[i];
+    }
+    if (nearbyAgents < 1) nearbyAgents = 1;                                       /* Math.Max(nearbyAgents, 1) :726 */
+    *n_players = n;
+    memset(aw, 0, sizeof(double) * (size_t)n * 6);
+    memset(otgt, 0, sizeof(double) * (size_t)n * 12);
+    memset(otw, 0, sizeof(double) * (size_t)n * 9);
+    for (int i = 0; i < n; ++i) {
+        const int ki = act[i];
+        const hk_race_kart* k = &karts[ki];
+        players[i] = ki;
+        /* the plan the ego holds for kart ki: its own m_UpcomingLanes, or its belief about ki */
+        const int8_t* lanes = ki == e ? plans[e].lane : beliefs[ki].lane;
+        const float* vels = ki == e ? plans[e].vel : beliefs[ki].vel;
+        x0[i * 4 + 0] = k->x; x0[i * 4 + 1] = k->z; x0[i * 4 + 2] = k->v; x0[i * 4 + 3] = k->h;       /* :730-736 */
+        const int s = k->section + 1;                                             /* :745 */
+        const int idx = s % t.n, idx2 = (s + 1) % t.n;
+        double tl[2], nl[2], vel, nvel;
+        plan_target(&t, p, lanes, vels, idx, tl, &vel);
+        plan_target(&t, p, lanes, vels, idx2, nl, &nvel);
+        const int stopped = (float)k->v <= 5.0f;                                  /* :808 */
+        double tx = tl[0], tz = tl[1], tv = stopped ? 0.0 : vel;
+        const float d_t = magnitude2((float)(tl[0] - k->x), (float)(tl[1] - k->z));
+        const int near = d_t <= (is_straight(&t, k->section) ? 10.5f : 7.5f);     /* :823 */
+        const float d_c = magnitude2((float)(t.trig[idx * 2] - k->x), (float)(t.trig[idx * 2 + 1] - k->z));
+        const int follow = near && (d_c <= 4.0f);                                 /* :877-890, centre-line distance stand-in */
+        const double h0 = k->h;
+        double th;
+        if (follow) {
+            const double f6w = (double)wrap2pi_f(mathf_atan2((float)(nl[1] - k->z), (float)(nl[0] - k->x)));
+            th = h0 - angle_difference(h0, f6w);                                  /* :887 */
+            tx = nl[0]; tz = nl[1];
+            if (!stopped) tv = nvel;
+        } else {
+            const double f1w = (double)wrap2pi_f(mathf_atan2((float)(tl[1] - k->z), (float)(tl[0] - k->x)));
+            if (near) {
+                const double f2w = (double)wrap2pi_f(mathf_atan2((float)(nl[1] - tl[1]), (float)(nl[0] - tl[0])));
+                double blend = f1w - angle_difference(f2w, f1w) * (double)0.4f;   /* :896 */
+                if (blend < 0) blend += 2 * (double)PI_F;
+                th = h0 - angle_difference(h0, blend);                            /* :898 */
+            } else th = h0 - angle_difference(h0, f1w);                           /* :921 */
+        }
+        target[i * 4 + 0] = tx; target[i * 4 + 1] = tz; target[i * 4 + 2] = tv; target[i * 4 + 3] = th;
+        /* own target weights (:928-962) */
+        const double vmax1 = k->v > 1.0 ? k->v : 1.0;
+        tw[i * 4 + 3] = n > 2 ? (fixed ? 2.5 : 3.5) * nearbyAgents : (fixed ? 1.9 : 3.5);
+        if (stopped) { tw[i * 4 + 0] = tw[i * 4 + 1] = nearbyAgents * 0.3 * 3.1; tw[i * 4 + 2] = nearbyAgents * -2; }
+        else { tw[i * 4 + 0] = tw[i * 4 + 1] = nearbyAgents * 0.3 * 3.1 / vmax1; tw[i * 4 + 2] = nearbyAgents * 5e-4; }
+        cw[i] = n > 2 ? (fixed ? 0.135 : 0.25) : 0.115;                           /* :1192-1196 */
+        /* avoid-weight multiplier (:977-1003) */
+        float multiplier;
+        if (K > 2 && n > 2) multiplier = ki == e ? (fixed ? 0.55f : 1.0f) / nearbyAgents : 1.7f / nearbyAgents;
+        else multiplier = ki == e ? (fixed ? 0.45f : 1.0f) : 1.3f;
+        int slot = 0, nearbyOpponents = 0;
+        for (int pass = 0; pass < 2; ++pass) {                                    /* k.otherAgents (:1004-1096), then k.teamAgents (:1098-1190) */
+            for (int o = 0; o < K; ++o) {
+                if (o == ki) continue;
+                const int mate = karts[o].team == k->team;
+                if (pass == 0 ? mate : !mate) continue;
+                int in_game = 0;
+                for (int j = 0; j < n; ++j) in_game |= act[j] == o;
+                if (!in_game) continue;                                           /* !actualAllPlayers.Contains(o) */
+                const hk_race_kart* ko = &karts[o];
+                const float dist = magnitude2((float)(ko->x - k->x), (float)(ko->z - k->z));
+                const int off = dist > 8 || !ko->active;
+                const float m = pass == 0 ? multiplier : multiplier / 2.0f;       /* multiplier2 :1113 */
+                const double w = off ? 0.0 : (double)(1.0f / ((float)pow((double)dist, (double)1.5f) * m));    /* :1019, :1114 */
+                aw[(i * 3 + slot) * 2 + 0] = w; aw[(i * 3 + slot) * 2 + 1] = w;
+                if (pass == 0 && !off) nearbyOpponents += 1;
+                /* the other kart's target: the ego's plan / belief for it at ITS next checkpoint (:1036-1066); a teammate's target speed is
+                 * getMaxSpeedForState() (:1138-1160), the stand-in's top speed */
+                const int8_t* ol = o == e ? plans[e].lane : beliefs[o].lane;
+                const float* ov = o == e ? plans[e].vel : beliefs[o].vel;
+                double oxz[2], ovel;
+                plan_target(&t, p, ol, ov, (ko->section + 1) % t.n, oxz, &ovel);
+                otgt[(i * 3 + slot) * 4 + 0] = oxz[0]; otgt[(i * 3 + slot) * 4 + 1] = oxz[1];
+                otgt[(i * 3 + slot) * 4 + 2] = pass == 0 ? ovel : (double)p->topSpeed; otgt[(i * 3 + slot) * 4 + 3] = 0.0;
+                double wxz = 0.0, wv = 0.0;
+                if (pass == 0) {
+                    if (!off) {
+                        if (n > 2) { wxz = (fixed ? 0.1 : 0.2) / (vmax1 * nearbyAgents); wv = 0.08 / nearbyAgents; }   /* :1083-1085 */
+                        else { wxz = (fixed ? 0.1 : 0.2) / vmax1; wv = 0.08; }                                          /* :1089-1091 */
+                    }
+                } else if (!off && nearbyOpponents >= 1) {
+                    if (n > 2) wxz = -(fixed ? 0.0 : 3e-5) / (vmax1 * nearbyAgents);                                    /* :1178-1180 */
+                    else wxz = -(fixed ? 1e-4 : 2e-4) / vmax1;                                                          /* :1184-1186 */
+                }
+                otw[(i * 3 + slot) * 3 + 0] = wxz; otw[(i * 3 + slot) * 3 + 1] = wxz; otw[(i * 3 + slot) * 3 + 2] = wv;
+                ++slot;
+            }
+        }
+    }
+}
+
 /* planFixed (:145-166) */
 void hk_oracle_race_plan_fixed(const hk_section* sections, int n_sections, const hk_race_params* p, int n_karts,
                                const hk_race_kart* karts, hk_race_plan* plans)

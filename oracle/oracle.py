@@ -295,6 +295,26 @@ class Races:
         out["dt"] = self.params.dt
         return out
 
+    def recipe_n_one(self, K, karts_r, plans_r, beliefs_e, e):
+        """hk_oracle_raceN_recipe_one: the ego e's problem in one race of K karts (karts_r [K], plans_r [K], beliefs_e [K]: the ego's
+        beliefs).  Arrays trimmed to the real players: x0/target/tw [n][4], cw [n], aw [n][n-1][2], otgt [n][n-1][4], otw [n][n-1][3]."""
+        L = lib()
+        L.hk_oracle_raceN_recipe_one.argtypes = [_vp, _dp, _dp, _dp, C.c_int, _vp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.POINTER(C.c_int), C.POINTER(C.c_int)] + [_dp] * 7
+        n = C.c_int(0)
+        players = (C.c_int * 4)()
+        o = dict(x0=np.zeros((4, 4)), target=np.zeros((4, 4)), tw=np.zeros((4, 4)), cw=np.zeros(4), aw=np.zeros((4, 3, 2)),
+                 otgt=np.zeros((4, 3, 4)), otw=np.zeros((4, 3, 3)))
+        kr, pr, br = (np.ascontiguousarray(a) for a in (karts_r, plans_r, beliefs_e))
+        L.hk_oracle_raceN_recipe_one(*self._geo(), K, S.ref(kr), S.ref(pr), S.ref(br), e, C.byref(n), players,
+                                     *(_p(o[k]) for k in ("x0", "target", "tw", "cw", "aw", "otgt", "otw")))
+        N = n.value
+        out = {k: o[k][:N] for k in ("x0", "target", "tw", "cw")}
+        for k in ("aw", "otgt", "otw"):
+            out[k] = o[k][:N, :max(N - 1, 0)]
+        out["players"] = [players[i] for i in range(N)]
+        return out
+
     def plan_fixed(self, karts, plans):
         lib().hk_oracle_race_plan_fixed(self.sections, self.n, C.byref(self.params), karts.size, S.ref(karts), S.ref(plans))
 

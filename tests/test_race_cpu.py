@@ -295,3 +295,51 @@ def test_duos_recipe_known_answers():
     karts["x"][0][3] = 23.0
     rec = np_race.recipe_agent(tt, prm, karts[0], plans[0], beliefs[0], 0)
     assert rec["players"] == [0, 1, 2] and rec["tw"][0][3] == 3.5 * 2
+
+
+@pytest.mark.parametrize("track", [S.OVAL, S.COMPLEX])
+@pytest.mark.parametrize("mcts", [True, False])
+@pytest.mark.parametrize("K,teams", [(4, [0, 0, 1, 1]), (4, [0, 1, 0, 1]), (3, [0, 1, 1]), (2, [0, 1])])
+def test_duos_recipe_c_restatement_equals_python_restatement(oracle, track, mcts, K, teams):
+    """The recipe for any number of agents twice, both from the C# text: oracle/hk_oracle_race.c (hk_oracle_raceN_recipe_one) and
+    oracle/np_recipe.py — every field of every real player of 300 x K problems on scattered race states (8 m filter keeping 1..K karts,
+    stopped karts, finished karts, random plans and beliefs): weights bit for bit, target headings to 1e-13."""
+    from oracle import np_race
+    OR, prm = _oracle_races(oracle, track, high_mode_mcts=mcts)
+    tt = _track_tables(track)
+    rng = np.random.default_rng(100 + K)
+    n = 300
+    karts, plans, beliefs, _ = R.start_grid_n(track, n, K, seed=9, teams=teams)
+    L = track.n_sections
+    lanes_xy, head = track.lane_table(), track.heading_table()
+    base = rng.integers(0, 2 * L, size=n)
+    for e in range(K):
+        sec = np.maximum(base + rng.integers(-1, 2, size=n), 0)
+        s0 = sec % L
+        ln = rng.integers(1, 5, size=n)
+        p0, p1 = lanes_xy[s0, ln - 1], lanes_xy[(s0 + 1) % L, ln - 1]
+        fr = rng.random(n)[:, None]
+        pos = p0 + (p1 - p0) * fr + rng.normal(0, 6.0 * rng.random(n)[:, None], size=(n, 2))
+        karts["x"][:, e], karts["z"][:, e] = pos[:, 0], pos[:, 1]
+        karts["v"][:, e] = np.where(rng.random(n) < 0.15, rng.uniform(0, 5, n), rng.uniform(5, 15, n))
+        karts["h"][:, e] = np.mod(head[s0] + rng.normal(0, 0.2, n), 2 * np.pi)
+        karts["section"][:, e], karts["lane"][:, e] = sec, ln
+    karts["active"][::41, K - 1] = 0
+    for arr in (plans, beliefs):
+        on = rng.random(arr["lane"].shape) < 0.6
+        arr["lane"][:] = np.where(on, rng.integers(1, 5, size=on.shape), 0)
+        arr["vel"][:] = np.where(on, rng.choice([8, 10, 12, 14, 15], size=on.shape), 0)
+    seen = set()
+    for r in range(n):
+        for e in range(K):
+            a = np_race.recipe_agent(tt, prm, karts[r], plans[r], beliefs[r], e)
+            b = OR.recipe_n_one(K, karts[r], plans[r], beliefs[r, e], e)
+            assert a["players"] == b["players"], (r, e)
+            N = len(a["players"])
+            seen.add(N)
+            for k in ("x0", "tw", "cw"):
+                assert np.array_equal(np.asarray(a[k]), b[k]), (k, r, e)
+            assert np.max(np.abs(np.asarray(a["target"]) - b["target"])) <= 1e-13
+            for k in ("aw", "otgt", "otw"):
+                assert np.array_equal(np.asarray(a[k]).reshape(b[k].shape), b[k]), (k, r, e, a[k], b[k])
+    assert seen == set(range(1, K + 1)) if K > 2 else seen == {2}
