@@ -60,86 +60,101 @@ __device__ __forceinline__ void plan_target(const DevTrack* t, const hk_race_par
 // hk_lqng_assemble_solve_packed) that the solve kernel stages with one bulk copy; else into the seven arrays.
 // cs != nullptr: also (cos h, sin h) of both players, [problem][2][2] — what lqng_trig_kernel would compute from the record (same double-precision
 // functions; their code does not depend on this file's -fmad=false)
+struct RecipeOut { double *x0, *target, *tw, *cw, *aw, *otgt, *otw, *cs; };   // bases such that base + b * width addresses problem b
+
+__device__ __forceinline__ RecipeOut recipe_out(int b, double* x0_, double* target_, double* tw_, double* cw_, double* aw_, double* otgt_, double* otw_,
+                                                double* packed, double* cs)
+{
+    double* const rec = packed ? packed + (size_t)b * 44 : nullptr;     // biased so that the indexing (base + b * width) lands in the record
+    return RecipeOut{packed ? rec - (size_t)b * 8 : x0_, packed ? rec + 8 - (size_t)b * 8 : target_, packed ? rec + 16 - (size_t)b * 8 : tw_,
+                     packed ? rec + 24 - (size_t)b * 2 : cw_, packed ? rec + 26 - (size_t)b * 4 : aw_, packed ? rec + 30 - (size_t)b * 8 : otgt_,
+                     packed ? rec + 38 - (size_t)b * 6 : otw_, cs};
+}
+
+// player i of problem b, first part: state, target, own weights; returns the player's target point / speed for the other player's second part
+__device__ __forceinline__ void race_recipe_player_a(const DevTrack* __restrict__ t, const hk_race_params& p, int b, int i, const hk_race_kart* karts,
+                                                     const hk_race_plan* plans, const RecipeOut& o, double& tlx, double& tlz, double& vel)
+{
+    const int e = b & 1;
+    const hk_race_kart* pair = karts + (b - e);
+    const hk_race_plan* plan = plans + b;
+    const hk_race_kart k = pair[i == 0 ? e : 1 - e];
+    const int8_t* lanes = i == 0 ? plan->lane : plan->oppLane;       // own plan / belief about the other (:745-817)
+    const float* vels = i == 0 ? plan->vel : plan->oppVel;
+    double* x = o.x0 + (size_t)b * 8 + i * 4;
+    x[0] = k.x; x[1] = k.z; x[2] = k.v; x[3] = k.h;                  // :730-736
+    if (o.cs) { o.cs[(size_t)b * 4 + 2 * i] = cos(k.h); o.cs[(size_t)b * 4 + 2 * i + 1] = sin(k.h); }
+    const int s = k.section + 1;                                     // :745
+    const int idx = s % t->n, idx2 = (s + 1) % t->n;
+    double nlx, nlz, nvel;
+    plan_target(t, p, lanes, vels, idx, tlx, tlz, vel);
+    plan_target(t, p, lanes, vels, idx2, nlx, nlz, nvel);
+    const bool stopped = (float)k.v <= 5.0f;                         // :808
+    double tx = tlx, tz = tlz, tv = stopped ? 0.0 : vel;
+    const float d_t = magnitude2((float)(tlx - k.x), (float)(tlz - k.z));
+    const bool near = d_t <= (is_straight(t, k.section) ? 10.5f : 7.5f);               // :823
+    const float d_c = magnitude2((float)(t->trig[idx][0] - k.x), (float)(t->trig[idx][1] - k.z));
+    const bool follow = near && (d_c <= 4.0f);                       // :877-890, centre-line distance stand-in
+    const double h0 = k.h;
+    double th;
+    if (follow) {
+        const double f6w = (double)wrap2pi_f(mathf_atan2((float)(nlz - k.z), (float)(nlx - k.x)));
+        th = h0 - angle_difference(h0, f6w);                         // :887
+        tx = nlx; tz = nlz;
+        if (!stopped) tv = nvel;
+    } else {
+        const double f1w = (double)wrap2pi_f(mathf_atan2((float)(tlz - k.z), (float)(tlx - k.x)));
+        if (near) {
+            const double f2w = (double)wrap2pi_f(mathf_atan2((float)(nlz - tlz), (float)(nlx - tlx)));
+            double blend = f1w - angle_difference(f2w, f1w) * (double)0.4f;             // :896
+            if (blend < 0) blend += 2 * (double)3.14159274f;
+            th = h0 - angle_difference(h0, blend);                   // :898
+        } else {
+            th = h0 - angle_difference(h0, f1w);                     // :921
+        }
+    }
+    double* tg = o.target + (size_t)b * 8 + i * 4;
+    tg[0] = tx; tg[1] = tz; tg[2] = tv; tg[3] = th;
+    const double vmax1 = k.v > 1.0 ? k.v : 1.0;                      // own target weights, 2-agent branch (:930-962)
+    const double w_xz = stopped ? 0.3 * 3.1 : 0.3 * 3.1 / vmax1;
+    double* w = o.tw + (size_t)b * 8 + i * 4;
+    w[0] = w_xz; w[1] = w_xz; w[2] = stopped ? -2.0 : 5e-4; w[3] = p.highModeMcts ? 3.5 : 1.9;
+    o.cw[(size_t)b * 2 + i] = 0.115;                                 // :1192-1196
+}
+
+// player i of problem b, second part: avoid + opponent-target weights (:964-1190); (otx, otz, ovel) = the OTHER player's target from its first part
+__device__ __forceinline__ void race_recipe_player_b(const hk_race_params& p, int b, int i, const hk_race_kart* karts, const RecipeOut& o, double otx,
+                                                     double otz, double ovel)
+{
+    const int e = b & 1;
+    const hk_race_kart* pair = karts + (b - e);
+    const hk_race_kart ki = pair[i == 0 ? e : 1 - e];
+    const hk_race_kart ko = pair[i == 0 ? 1 - e : e];
+    const float mult = i == 0 ? (p.highModeMcts ? 1.0f : 0.45f) : 1.3f;   // k == this ? (Fixed ? 0.45f : 1.0f) : 1.3f, :999-1002
+    const float dist = magnitude2((float)(ko.x - ki.x), (float)(ko.z - ki.z));
+    const bool far = dist > 8 || !ko.active;                          // ... .magnitude > 8 || !o.is_active, :1010
+    const float w32 = 1.0f / ((float)pow((double)dist, (double)1.5f) * mult);          // 1f/(Mathf.Pow(d,1.5f)*mult), :1019
+    const double w = far ? 0.0 : (double)w32;
+    o.aw[(size_t)b * 4 + i * 2 + 0] = w;
+    o.aw[(size_t)b * 4 + i * 2 + 1] = w;
+    double* og = o.otgt + (size_t)b * 8 + i * 4;
+    og[0] = otx; og[1] = otz; og[2] = ovel; og[3] = 0.0;
+    const double vmax1 = ki.v > 1.0 ? ki.v : 1.0;
+    const double wxz = (p.highModeMcts ? 0.2 : 0.1) / vmax1;         // :1089-1091
+    double* ow = o.otw + (size_t)b * 6 + i * 3;
+    ow[0] = far ? 0.0 : wxz; ow[1] = far ? 0.0 : wxz; ow[2] = far ? 0.0 : 0.08;
+}
+
 __device__ __forceinline__ void race_recipe_body(const DevTrack* __restrict__ t, const hk_race_params& p, int b, const hk_race_kart* karts,
                                                  const hk_race_plan* plans, double* x0_, double* target_, double* tw_, double* cw_, double* aw_,
                                                  double* otgt_, double* otw_, double* packed, double* cs)
 {
-    double* const rec = packed ? packed + (size_t)b * 44 : nullptr;
-    double* const x0 = packed ? rec - (size_t)b * 8 : x0_;               // biased so that the indexing below (base + b * width) lands in the record
-    double* const target = packed ? rec + 8 - (size_t)b * 8 : target_;
-    double* const tw = packed ? rec + 16 - (size_t)b * 8 : tw_;
-    double* const cw = packed ? rec + 24 - (size_t)b * 2 : cw_;
-    double* const aw = packed ? rec + 26 - (size_t)b * 4 : aw_;
-    double* const otgt = packed ? rec + 30 - (size_t)b * 8 : otgt_;
-    double* const otw = packed ? rec + 38 - (size_t)b * 6 : otw_;
-    const int e = b & 1;
-    const hk_race_kart* pair = karts + (b - e);
-    const hk_race_plan* plan = plans + b;
+    const RecipeOut o = recipe_out(b, x0_, target_, tw_, cw_, aw_, otgt_, otw_, packed, cs);
     double tlx[2], tlz[2], vel[2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const hk_race_kart k = pair[i == 0 ? e : 1 - e];
-        const int8_t* lanes = i == 0 ? plan->lane : plan->oppLane;   // own plan / belief about the other (:745-817)
-        const float* vels = i == 0 ? plan->vel : plan->oppVel;
-        double* x = x0 + (size_t)b * 8 + i * 4;
-        x[0] = k.x; x[1] = k.z; x[2] = k.v; x[3] = k.h;              // :730-736
-        if (cs) { cs[(size_t)b * 4 + 2 * i] = cos(k.h); cs[(size_t)b * 4 + 2 * i + 1] = sin(k.h); }
-        const int s = k.section + 1;                                 // :745
-        const int idx = s % t->n, idx2 = (s + 1) % t->n;
-        double nlx, nlz, nvel;
-        plan_target(t, p, lanes, vels, idx, tlx[i], tlz[i], vel[i]);
-        plan_target(t, p, lanes, vels, idx2, nlx, nlz, nvel);
-        const bool stopped = (float)k.v <= 5.0f;                     // :808
-        double tx = tlx[i], tz = tlz[i], tv = stopped ? 0.0 : vel[i];
-        const float d_t = magnitude2((float)(tlx[i] - k.x), (float)(tlz[i] - k.z));
-        const bool near = d_t <= (is_straight(t, k.section) ? 10.5f : 7.5f);           // :823
-        const float d_c = magnitude2((float)(t->trig[idx][0] - k.x), (float)(t->trig[idx][1] - k.z));
-        const bool follow = near && (d_c <= 4.0f);                   // :877-890, centre-line distance stand-in
-        const double h0 = k.h;
-        double th;
-        if (follow) {
-            const double f6w = (double)wrap2pi_f(mathf_atan2((float)(nlz - k.z), (float)(nlx - k.x)));
-            th = h0 - angle_difference(h0, f6w);                     // :887
-            tx = nlx; tz = nlz;
-            if (!stopped) tv = nvel;
-        } else {
-            const double f1w = (double)wrap2pi_f(mathf_atan2((float)(tlz[i] - k.z), (float)(tlx[i] - k.x)));
-            if (near) {
-                const double f2w = (double)wrap2pi_f(mathf_atan2((float)(nlz - tlz[i]), (float)(nlx - tlx[i])));
-                double blend = f1w - angle_difference(f2w, f1w) * (double)0.4f;         // :896
-                if (blend < 0) blend += 2 * (double)3.14159274f;
-                th = h0 - angle_difference(h0, blend);               // :898
-            } else {
-                th = h0 - angle_difference(h0, f1w);                 // :921
-            }
-        }
-        double* tg = target + (size_t)b * 8 + i * 4;
-        tg[0] = tx; tg[1] = tz; tg[2] = tv; tg[3] = th;
-        const double vmax1 = k.v > 1.0 ? k.v : 1.0;                  // own target weights, 2-agent branch (:930-962)
-        const double w_xz = stopped ? 0.3 * 3.1 : 0.3 * 3.1 / vmax1;
-        double* w = tw + (size_t)b * 8 + i * 4;
-        w[0] = w_xz; w[1] = w_xz; w[2] = stopped ? -2.0 : 5e-4; w[3] = p.highModeMcts ? 3.5 : 1.9;
-        cw[(size_t)b * 2 + i] = 0.115;                               // :1192-1196
-    }
+    for (int i = 0; i < 2; ++i) race_recipe_player_a(t, p, b, i, karts, plans, o, tlx[i], tlz[i], vel[i]);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {                                    // avoid + opponent-target weights (:964-1190)
-        const int o = 1 - i;
-        const hk_race_kart ki = pair[i == 0 ? e : 1 - e];
-        const hk_race_kart ko = pair[o == 0 ? e : 1 - e];
-        const float mult = i == 0 ? (p.highModeMcts ? 1.0f : 0.45f) : 1.3f;   // k == this ? (Fixed ? 0.45f : 1.0f) : 1.3f, :999-1002
-        const float dist = magnitude2((float)(ko.x - ki.x), (float)(ko.z - ki.z));
-        const bool far = dist > 8 || !ko.active;                      // ... .magnitude > 8 || !o.is_active, :1010
-        const float w32 = 1.0f / ((float)pow((double)dist, (double)1.5f) * mult);      // 1f/(Mathf.Pow(d,1.5f)*mult), :1019
-        const double w = far ? 0.0 : (double)w32;
-        aw[(size_t)b * 4 + i * 2 + 0] = w;
-        aw[(size_t)b * 4 + i * 2 + 1] = w;
-        double* og = otgt + (size_t)b * 8 + i * 4;
-        og[0] = tlx[o]; og[1] = tlz[o]; og[2] = vel[o]; og[3] = 0.0;
-        const double vmax1 = ki.v > 1.0 ? ki.v : 1.0;
-        const double wxz = (p.highModeMcts ? 0.2 : 0.1) / vmax1;     // :1089-1091
-        double* ow = otw + (size_t)b * 6 + i * 3;
-        ow[0] = far ? 0.0 : wxz; ow[1] = far ? 0.0 : wxz; ow[2] = far ? 0.0 : 0.08;
-    }
+    for (int i = 0; i < 2; ++i) race_recipe_player_b(p, b, i, karts, o, tlx[1 - i], tlz[1 - i], vel[1 - i]);
 }
 
 __global__ void race_recipe_kernel(const DevTrack* __restrict__ t, hk_race_params p, int n_problems, const hk_race_kart* __restrict__ karts,
@@ -270,10 +285,21 @@ __global__ void race_step_recipe_kernel(const DevTrack* __restrict__ t, hk_race_
                                         int u_stride, const int* __restrict__ lqng_status, unsigned long long* status_count, hk_race_kart* karts,
                                         hk_race_plan* plans, int* __restrict__ root_valid, int* __restrict__ cycles, double* packed, double* cs)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_karts) race_step_body(t, p, i, episode_step, u, u_stride, lqng_status, status_count, karts, plans, root_valid, cycles);
-    __syncwarp();                                                    // n_karts is even and pairs do not straddle warps: the partner's store is visible
-    if (i < n_karts) race_recipe_body(t, p, i, karts, plans, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, packed, cs);
+    // two threads per agent: thread (b, i) builds player i of agent b's problem (the float math of a player is a long dependent chain and
+    // the batch is small); the four threads of a race are neighbouring lanes, thread (b, 0) also does agent b's plant step
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = gid >> 1, i = gid & 1;
+    const bool live = b < n_karts;                                   // n_karts is even and blockDim a multiple of 4: races do not straddle warps
+    if (live && i == 0) race_step_body(t, p, b, episode_step, u, u_stride, lqng_status, status_count, karts, plans, root_valid, cycles);
+    __syncwarp();                                                    // both karts' new states are visible to the race's four threads
+    double tlx = 0.0, tlz = 0.0, vel = 0.0;
+    RecipeOut o{};
+    if (live) {
+        o = recipe_out(b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, packed, cs);
+        race_recipe_player_a(t, p, b, i, karts, plans, o, tlx, tlz, vel);
+    }
+    const double otx = __shfl_xor_sync(0xffffffffu, tlx, 1), otz = __shfl_xor_sync(0xffffffffu, tlz, 1), ovel = __shfl_xor_sync(0xffffffffu, vel, 1);
+    if (live) race_recipe_player_b(p, b, i, karts, o, otx, otz, ovel);
 }
 
 static int check_track(const hk_track* t, const hk_race_params* p, const char* who)
@@ -648,7 +674,7 @@ static int race_run_impl(const hk_track* t, const hk_race_params* p, hk_race_pla
         have_recipe = fuse && nx < first_step + n_steps && nx % p->planEvery != 0 && !(pl && pl->pending_step == nx);
         count_launch();
         if (have_recipe)
-            race_step_recipe_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp, pl ? pl->root_valid : nullptr,
+            race_step_recipe_kernel<<<(unsigned)((2 * nb + 127) / 128), 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp, pl ? pl->root_valid : nullptr,
                                                           pl ? pl->cycles : nullptr, dx0, dcs);
         else
             race_step_kernel<<<blocks, 128, 0, s>>>(t->dev, *p, (int)nb, step, du, 4, dst, dcount, dk, dp, pl ? pl->root_valid : nullptr, pl ? pl->cycles : nullptr);
