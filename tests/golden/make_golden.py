@@ -109,9 +109,68 @@ def game():
     np.savez_compressed(os.path.join(HERE, "game_golden.npz"), **out)
 
 
+def recipe():
+    """tests/golden/recipe_golden.npz: race states of 40 Duos races (4 karts, teams [0, 0, 1, 1], Complex, both high-level modes) and 60
+    2-kart Oval races, and every agent's SolveLQR problem in the 4-player layout, produced by the C oracle AFTER the Python restatement
+    (oracle/np_recipe.py) agreed with it on exactly these inputs."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from hierarchicalkarting_b200 import race as R
+    from oracle import np_race
+    from test_race_cpu import _oracle_races, _track_tables
+    out = {}
+    for name, track, K, teams, n in (("duos", S.COMPLEX, 4, [0, 0, 1, 1], 40), ("pair", S.OVAL, 2, [0, 1], 60)):
+        rng = np.random.default_rng(20260500 + K)
+        karts, plans, beliefs, _ = R.start_grid_n(track, n, K, seed=3, teams=teams)
+        L = track.n_sections
+        lanes_xy, head = track.lane_table(), track.heading_table()
+        base = rng.integers(0, 2 * L, size=n)
+        for e in range(K):
+            sec = np.maximum(base + rng.integers(-1, 2, size=n), 0)
+            s0 = sec % L
+            ln = rng.integers(1, 5, size=n)
+            p0, p1 = lanes_xy[s0, ln - 1], lanes_xy[(s0 + 1) % L, ln - 1]
+            pos = p0 + (p1 - p0) * rng.random(n)[:, None] + rng.normal(0, 5.0 * rng.random(n)[:, None], size=(n, 2))
+            karts["x"][:, e], karts["z"][:, e] = pos[:, 0], pos[:, 1]
+            karts["v"][:, e] = np.where(rng.random(n) < 0.15, rng.uniform(0, 5, n), rng.uniform(5, 15, n))
+            karts["h"][:, e] = np.mod(head[s0] + rng.normal(0, 0.2, n), 2 * np.pi)
+            karts["section"][:, e], karts["lane"][:, e] = sec, ln
+        karts["active"][::13, K - 1] = 0
+        for arr in (plans, beliefs):
+            on = rng.random(arr["lane"].shape) < 0.6
+            arr["lane"][:] = np.where(on, rng.integers(1, 5, size=on.shape), 0)
+            arr["vel"][:] = np.where(on, rng.choice([8, 10, 12, 14, 15], size=on.shape), 0)
+        out[f"{name}_karts"], out[f"{name}_plans"], out[f"{name}_beliefs"] = karts, plans, beliefs
+        for mcts in (False, True):
+            OR, prm = _oracle_races(O, track, high_mode_mcts=mcts)
+            tt = _track_tables(track)
+            res = dict(n_players=np.zeros((n, K), np.int32), players=np.full((n, K, 4), -1, np.int32), x0=np.zeros((n, K, 4, 4)),
+                       target=np.zeros((n, K, 4, 4)), tw=np.zeros((n, K, 4, 4)), cw=np.ones((n, K, 4)), aw=np.zeros((n, K, 4, 3, 2)),
+                       otgt=np.zeros((n, K, 4, 3, 4)), otw=np.zeros((n, K, 4, 3, 3)))
+            for r in range(n):
+                for e in range(K):
+                    c = OR.recipe_n_one(K, karts[r], plans[r], beliefs[r, e], e)
+                    a = np_race.recipe_agent(tt, prm, karts[r], plans[r], beliefs[r], e)                # second opinion before freezing
+                    N = len(c["players"])
+                    assert a["players"] == c["players"]
+                    for k in ("x0", "tw", "cw", "aw", "otgt", "otw"):
+                        assert np.array_equal(np.asarray(a[k]).reshape(c[k].shape), c[k]), (k, r, e)
+                    assert np.max(np.abs(np.asarray(a["target"]) - c["target"])) <= 1e-13
+                    res["n_players"][r, e] = N
+                    res["players"][r, e, :N] = c["players"]
+                    for k in ("x0", "target", "tw"):
+                        res[k][r, e, :N] = c[k]
+                    res["cw"][r, e, :N] = c["cw"]
+                    for k in ("aw", "otgt", "otw"):
+                        res[k][r, e, :N, :max(N - 1, 0)] = c[k]
+            for k, v in res.items():
+                out[f"{name}_{'mcts' if mcts else 'fixed'}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "recipe_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     lqng()
     game()
+    recipe()
     with open(os.path.join(HERE, "game_kat.json"), "w") as f:
         json.dump(GAME_KAT, f, indent=1)
     print("golden written")

@@ -170,3 +170,22 @@ def test_mcts_duos_loop_parity(hk, oracle):
         rv, cy, ts = gpl.state()
         assert np.array_equal(rv.reshape(-1), opl.root_valid) and np.array_equal(cy.reshape(-1), opl.cycles) and not ts.any()
     assert (plans["lane"] != 0).any() and (beliefs["lane"] != 0).any() and karts["section"].min() >= 2
+
+
+def test_recipe_golden_fixture_on_device(hk):
+    """The frozen recipe outputs of tests/golden/recipe_golden.npz (C oracle, cross-checked against the Python restatement before
+    freezing) against hk_raceN_recipe: Duos and 2-kart races, both high-level modes, no oracle loaded."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "recipe_golden.npz"))
+    for name, track, K in (("duos", S.COMPLEX, 4), ("pair", S.OVAL, 2)):
+        karts, plans, beliefs = (np.ascontiguousarray(g[f"{name}_{k}"]) for k in ("karts", "plans", "beliefs"))
+        n = karts.shape[0]
+        for mcts in (False, True):
+            G = R.RacesN(track, R.race_params(track, high_mode_mcts=mcts), K)
+            got = G.recipe_n(karts, plans, beliefs)
+            tag = f"{name}_{'mcts' if mcts else 'fixed'}"
+            assert np.array_equal(got["n_players"].reshape(n, K), g[f"{tag}_n_players"])
+            assert np.array_equal(got["players"].reshape(n, K, 4), g[f"{tag}_players"])
+            for k in ("x0", "tw", "cw", "aw", "otgt", "otw"):
+                assert np.array_equal(got[k].reshape(g[f"{tag}_{k}"].shape), g[f"{tag}_{k}"]), k
+            assert np.max(np.abs(got["target"].reshape(g[f"{tag}_target"].shape) - g[f"{tag}_target"])) <= 1e-13

@@ -343,3 +343,24 @@ def test_duos_recipe_c_restatement_equals_python_restatement(oracle, track, mcts
             for k in ("aw", "otgt", "otw"):
                 assert np.array_equal(np.asarray(a[k]).reshape(b[k].shape), b[k]), (k, r, e, a[k], b[k])
     assert seen == set(range(1, K + 1)) if K > 2 else seen == {2}
+
+
+def test_recipe_golden_fixture_matches_oracle(oracle):
+    """tests/golden/recipe_golden.npz (frozen after the C and the Python restatement agreed, tests/golden/make_golden.py) against the C
+    oracle as it is now: a change of either restatement shows up here."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "recipe_golden.npz"))
+    for name, track, K in (("duos", S.COMPLEX, 4), ("pair", S.OVAL, 2)):
+        karts, plans, beliefs = g[f"{name}_karts"], g[f"{name}_plans"], g[f"{name}_beliefs"]
+        for mcts in (False, True):
+            OR, _ = _oracle_races(oracle, track, high_mode_mcts=mcts)
+            tag = f"{name}_{'mcts' if mcts else 'fixed'}"
+            for r in range(karts.shape[0]):
+                for e in range(K):
+                    c = OR.recipe_n_one(K, karts[r], plans[r], beliefs[r, e], e)
+                    N = len(c["players"])
+                    assert N == int(g[f"{tag}_n_players"][r, e]) and c["players"] == list(g[f"{tag}_players"][r, e, :N])
+                    for k in ("x0", "target", "tw", "cw"):
+                        assert np.array_equal(c[k], g[f"{tag}_{k}"][r, e, :N]), (k, r, e)
+                    for k in ("aw", "otgt", "otw"):
+                        assert np.array_equal(c[k], g[f"{tag}_{k}"][r, e, :N, :max(N - 1, 0)]), (k, r, e)
