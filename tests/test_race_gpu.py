@@ -335,3 +335,21 @@ def test_device_resident_entries_equal_the_host_pointer_entries(hk):
     assert R.host_state(dk, karts).tobytes() == hk_.tobytes() and R.host_state(dp, plans).tobytes() == hp_.tobytes()
     assert R.host_state(db, beliefs).tobytes() == hb_.tobytes()
     assert np.array_equal(du8.cpu().numpy()[:, :2].reshape(200, K, 2), hu_)
+    # Duos with the MCTS planner (team scoring, beliefs handed off): device-resident blocks against one host-pointer call
+    prm4 = R.race_params(S.COMPLEX, high_mode_mcts=True)
+    prm4.planEvery = 40
+    GM = R.RacesN(S.COMPLEX, prm4, K)
+    game4 = M.Game(S.COMPLEX, K, prm4.velocityBucketSize)
+    karts, plans, beliefs, u = R.start_grid_n(S.COMPLEX, 24, K, seed=44, teams=[0, 0, 1, 1])
+    mk = lambda: GM.planner(game4, 24, 16, 9, mode=0, first_iterations=12, reuse_cycles=3, apply_delay=9, max_tree_nodes=1 + 32 * (12 + 12 * 16))
+    q1, q2 = mk(), mk()
+    hk_, hp_, hb_, hu_ = karts.copy(), plans.copy(), beliefs.copy(), u.copy()
+    GM.run_n(hk_, hp_, hb_, hu_, 0, 130, planner=q1)
+    dk, dp, db = R.device_state(karts, plans, beliefs)
+    du8 = torch.zeros((24 * K, 8), dtype=torch.float64, device="cuda:0")
+    for a, b in ((0, 44), (44, 41), (85, 45)):
+        GM.run_n_device(dk, dp, db, du8, a, b, planner=q2)
+    assert R.host_state(dk, karts).tobytes() == hk_.tobytes() and R.host_state(dp, plans).tobytes() == hp_.tobytes()
+    assert R.host_state(db, beliefs).tobytes() == hb_.tobytes() and (hb_["lane"] != 0).any()
+    for x, y in zip(q1.state(), q2.state()):
+        assert np.array_equal(x, y)
