@@ -381,7 +381,7 @@ def main():
         abi.check(lib.hk_lqng_assemble_solve_batch(batch, N, HORIZON, float(prob["dt"]), *[abi.dptr(a) for a in cnp], abi.dptr(u0_np), abi.iptr(st_np)))
 
     def timed(fn):
-        for _ in range(args.warmup):
+        for _ in range(max(args.warmup, 20)):                                  # fresh pinned buffers take more than a few copies to reach the link's rate
             fn()
         barrier()
         t0 = time.perf_counter()
@@ -400,10 +400,33 @@ def main():
     def step_e2e_packed():
         abi.check(lib.hk_lqng_assemble_solve_packed(batch, N, HORIZON, float(prob["dt"]), abi.dptr(rec_np), abi.dptr(u0_np), abi.iptr(st_np)))
 
-    e2e_s = timed(step_e2e)
-    u0_seven = u0_np.copy()
-    e2e_packed_s = timed(step_e2e_packed)
-    packed_equal = bool(np.array_equal(u0_seven, u0_np))
+    # the link before the host-pointer legs (some boxes of the pool slow down after the first tens of ms of sustained traffic: the probe after
+    # the legs then reads 15-40 GB/s although the first leg ran at the full rate)
+    def _link_gbs():
+        h = torch.empty(compact_bytes // 8, dtype=torch.float64).pin_memory()
+        d = torch.empty_like(h, device=dev)
+        for _ in range(20):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        return 10 * compact_bytes / (time.perf_counter() - t0) / 1e9
+    try:
+        link_before = _link_gbs()
+    except Exception:
+        link_before = None
+    if os.environ.get("HK_BENCH_PACKED_FIRST"):                               # measurement aid: order of the two compact legs
+        e2e_packed_s = timed(step_e2e_packed)
+        u0_packed = u0_np.copy()
+        e2e_s = timed(step_e2e)
+        packed_equal = bool(np.array_equal(u0_packed, u0_np))
+    else:
+        e2e_s = timed(step_e2e)
+        u0_seven = u0_np.copy()
+        e2e_packed_s = timed(step_e2e_packed)
+        packed_equal = bool(np.array_equal(u0_seven, u0_np))
     e2e_dense_s = timed(step_e2e_dense)
 
     # what this box's host link gives (the compact e2e call varies 0.57 - 1.4 ms between boxes of the pool at identical code, the 109 MB
@@ -413,7 +436,7 @@ def main():
         big_d = torch.empty_like(big_h, device=dev)
         small_h = torch.empty(1024, dtype=torch.float64).pin_memory()
         small_d = torch.empty_like(small_h, device=dev)
-        for _ in range(3):
+        for _ in range(20):
             big_d.copy_(big_h, non_blocking=True)
         torch.cuda.synchronize()
         barrier()                                                          # N > 1: every rank copies at the same time (shared uplinks / host memory)
@@ -451,6 +474,7 @@ def main():
                 "driver": drv}
     try:
         box_probe = _probe()
+        box_probe["h2d_23mb_gbs_before_the_legs"] = link_before
     except Exception as exc:
         box_probe = {"error": repr(exc)[:200]}
 
@@ -881,7 +905,7 @@ def main():
                              "bytes_per_solve": IN_BYTES_PER_SOLVE + OUT_BYTES_PER_SOLVE}},
         "e2e": {"value": world * batch * args.steps / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": compact_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "host_link": box_probe,
-                "pcie_floor_ms": (1e3 * compact_bytes / (max(box_probe["h2d_23mb_gbs"], box_probe["h2d_23mb_4streams_gbs"]) * 1e9))
+                "pcie_floor_ms": (1e3 * compact_bytes / (max(box_probe["h2d_23mb_gbs"], box_probe["h2d_23mb_4streams_gbs"], link_before or 0.0) * 1e9))
                                  if "h2d_23mb_gbs" in box_probe else None,     # the H2D bytes at the best copy rate this box showed; D2H overlaps
                 "api": "hk_lqng_assemble_solve_batch: pinned host buffers holding the reference's provider constructor arguments "
                        "(LinearizedBicycle / LQRCheckpointReachAvoidCost), A,B,Q,q,R assembled on the GPU, u0 + status copied back",

@@ -323,6 +323,41 @@ __global__ void lqng_ingest_kernel(IngestArgs a)
         for (long long e = id; e < a.n2[i]; e += stride) a.dst[i][e] = a.src[i][e];
 }
 
+// Chunk schedule of the host-pointer pipelines.  The copies are the critical path (PCIe), so what a schedule can lose is (a) a fixed cost per copy
+// and (b) the tail after the last copy — that chunk's solve and its D2H.  Equal chunks trade one against the other; a TAPERED schedule does not:
+// every chunk is half the one before (the solve runs ~3x as fast as the copy, so a chunk's solve still hides behind the next, smaller copy)
+// down to `floor_n` problems (measured optimum 8,192: 32,768 + 16,384 + 8,192 + 8,192 for the 65,536-problem call, 0.565 -> 0.53 ms together with a
+// SINGLE copy stream — copies on several streams share the link and every chunk lands late).  Only for the 2-kart game: a 4-kart solve takes as long
+// as its copy, so there equal chunks on four copy streams stay.  starts[k] .. starts[k + 1] is chunk k; sizes are even (16-byte aligned sub-arrays).
+// HK_E2E_TAPER=0: equal chunks.
+static int chunk_schedule(int batch, int nchunks_equal, int* starts, int max_chunks, int* largest, bool allow_taper)
+{
+    static const bool taper = !(getenv("HK_E2E_TAPER") && atoi(getenv("HK_E2E_TAPER")) == 0);
+    static const int floor_env = getenv("HK_E2E_TAPER_FLOOR") ? atoi(getenv("HK_E2E_TAPER_FLOOR")) : 8192;
+    static const double ratio = getenv("HK_E2E_TAPER_RATIO") ? atof(getenv("HK_E2E_TAPER_RATIO")) : 0.5;
+    int n = 0;
+    starts[0] = 0;
+    if (taper && allow_taper && nchunks_equal > 2 && batch <= 65536 * 2) {
+        const int floor_n = floor_env < 256 ? 256 : floor_env;
+        int left = batch;
+        while (left > 0 && n < max_chunks - 1) {
+            int c = ((int)(left * ratio) + 1) & ~1;
+            if (c < floor_n || left - c < floor_n) c = left;
+            starts[n + 1] = starts[n] + c;
+            left -= c;
+            ++n;
+        }
+        if (left > 0) { starts[n + 1] = starts[n] + left; ++n; }
+    } else {
+        const int chunk = ((batch + nchunks_equal - 1) / nchunks_equal + 1) & ~1;
+        for (int b0 = 0; b0 < batch && n < max_chunks; b0 += chunk) { starts[n + 1] = b0 + chunk < batch ? b0 + chunk : batch; ++n; }
+    }
+    int big = 0;
+    for (int k = 0; k < n; ++k) big = starts[k + 1] - starts[k] > big ? starts[k + 1] - starts[k] : big;
+    *largest = big;
+    return n;
+}
+
 // Host-pointer entry of the compact description.  Pipeline over chunks of the batch: the seven H2D copies of a chunk go to
 // dedicated copy streams (round robin) and never queue behind a solve or a D2H; the assembly + solve of chunk k (compute
 // stream k & 1) waits on the chunk's "copied in" event, its results go back on the same compute stream.  Chunk buffers form a
@@ -344,18 +379,19 @@ extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizo
     size_t per = 0;
     for (int i = 0; i < 7; ++i) per += e[i];
     static const int chunks_env = getenv("HK_E2E_CHUNKS") ? atoi(getenv("HK_E2E_CHUNKS")) : 0;    // tuning knobs
-    static const int ncs_env = getenv("HK_E2E_COPY_STREAMS") ? atoi(getenv("HK_E2E_COPY_STREAMS")) : 4;
+    static const int ncs_env = getenv("HK_E2E_COPY_STREAMS") ? atoi(getenv("HK_E2E_COPY_STREAMS")) : 0;     // 0: one stream for the 2-kart game, four otherwise
     // 0: seven cudaMemcpyAsync per chunk; 1 (default): one cudaMemcpyBatchAsync per chunk — the pipeline is bound by the host's
     // issue rate (~3 us per call) before it is bound by PCIe; 2: ingest kernel (pinned sources only)
     static const int mode_env = getenv("HK_E2E_COPY_MODE") ? atoi(getenv("HK_E2E_COPY_MODE")) : 1;
     static std::atomic<int> batch_copy_ok{1};
     const int mode = (mode_env == 1 && !batch_copy_ok.load()) ? 0 : mode_env;
     constexpr int RING = 4;
-    const int ncs = ncs_env < 1 ? 1 : ncs_env > 4 ? 4 : ncs_env;
+    const int ncs = ncs_env < 1 ? (N <= 2 ? 1 : 4) : ncs_env > 4 ? 4 : ncs_env;
     int nchunks = batch >= 16384 ? (chunks_env > 0 ? chunks_env : (batch >= 65536 ? 8 : batch / 8192)) : 1;
     const int by_size = (int)(((long long)batch + 65535) / 65536);                                // chunks of at most 65,536 problems
     if (nchunks < by_size) nchunks = by_size;
-    const int chunk = ((batch + nchunks - 1) / nchunks + 1) & ~1;                                 // even: keeps every sub-array 16-byte aligned
+    int starts[40], chunk = 0;                                                                    // chunk: the largest one (slot layout)
+    nchunks = chunk_schedule(batch, nchunks, starts, 39, &chunk, N <= 2);
     const size_t slot_bytes = (((per + m) * sizeof(double) + sizeof(int)) * (size_t)chunk + 255) & ~(size_t)255;
     const int ring = nchunks < RING ? nchunks : RING;
     char* dring = (char*)dscratch(c, 4, slot_bytes * ring);
@@ -368,7 +404,7 @@ extern "C" int hk_lqng_assemble_solve_batch(int batch, int n_players, int horizo
     }
     cudaStream_t compute[2] = {c->stream, c->stream2};
     for (int ci = 0; ci < nchunks; ++ci) {
-        const int b0 = ci * chunk, nb = (b0 + chunk <= batch) ? chunk : batch - b0;
+        const int b0 = starts[ci], nb = starts[ci + 1] - starts[ci];
         if (nb <= 0) break;
         const int r = ci % ring;
         cudaStream_t cs = nchunks > 1 ? c->cstream[ci % ncs] : compute[0];
@@ -440,7 +476,10 @@ extern "C" int hk_lqng_assemble_solve_packed(int batch, int n_players, int horiz
     int nchunks = batch >= 16384 ? (chunks_env > 0 ? chunks_env : (batch >= 65536 ? 8 : batch / 8192)) : 1;
     const int by_size = (int)(((long long)batch + 65535) / 65536);
     if (nchunks < by_size) nchunks = by_size;
-    const int chunk = ((batch + nchunks - 1) / nchunks + 1) & ~1;
+    static const int ncs_env_p = getenv("HK_E2E_COPY_STREAMS") ? atoi(getenv("HK_E2E_COPY_STREAMS")) : 0;
+    const int ncs_p = ncs_env_p < 1 ? (N <= 2 ? 1 : 4) : ncs_env_p > 4 ? 4 : ncs_env_p;
+    int starts[40], chunk = 0;
+    nchunks = chunk_schedule(batch, nchunks, starts, 39, &chunk, N <= 2);
     const size_t slot_bytes = ((((size_t)P + m) * sizeof(double) + sizeof(int)) * (size_t)chunk + 255) & ~(size_t)255;
     const int ring = nchunks < RING ? nchunks : RING;
     char* dring = (char*)dscratch(c, 4, slot_bytes * ring);
@@ -453,10 +492,10 @@ extern "C" int hk_lqng_assemble_solve_packed(int batch, int n_players, int horiz
     }
     cudaStream_t compute[2] = {c->stream, c->stream2};
     for (int ci = 0; ci < nchunks; ++ci) {
-        const int b0 = ci * chunk, nb = (b0 + chunk <= batch) ? chunk : batch - b0;
+        const int b0 = starts[ci], nb = starts[ci + 1] - starts[ci];
         if (nb <= 0) break;
         const int r = ci % ring;
-        cudaStream_t cs = nchunks > 1 ? c->cstream[ci % 4] : compute[0];
+        cudaStream_t cs = nchunks > 1 ? c->cstream[ci % ncs_p] : compute[0];
         cudaStream_t s = compute[ci & 1];
         double* drec = (double*)(dring + slot_bytes * r);
         double* du = drec + (size_t)P * chunk;
