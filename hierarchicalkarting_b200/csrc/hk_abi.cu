@@ -471,6 +471,28 @@ extern "C" int hk_lqng_assemble_solve_packed(int batch, int n_players, int horiz
     if (!c) return HK_ERR_NO_DEVICE;
     struct DrainOnError { ThreadCtx* c; bool ok = false; ~DrainOnError() { if (!ok) drain_ctx(c); } } drain_guard{c};
     const int K = N - 1, m = 2 * N, P = 13 * N + 9 * N * K;
+    // Zero-copy form (2-kart game, records / u0 / status all in pinned host memory, which is device-accessible under UVA): ONE launch — the solve
+    // kernel's bulk copies pull each 352-byte record over PCIe exactly once while other warps solve, results are written straight back.  No
+    // staging copies, no chunk pipeline, no (cos h, sin h) pre-pass.  Measured (round 2) and left OFF: 0.545-0.554 ms per 65,536-problem call against
+    // 0.512-0.516 ms for the chunk pipeline — 352-byte reads over PCIe reach ~42 GB/s where the copy engine's large transfers reach 54.
+    static const int zc_env = getenv("HK_E2E_ZEROCOPY") ? atoi(getenv("HK_E2E_ZEROCOPY")) : 0;
+    if (zc_env && N == 2 && (reinterpret_cast<uintptr_t>(records) & 15) == 0) {
+        auto mapped = [](const void* ptr) -> void* {
+            cudaPointerAttributes a{};
+            if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+        };
+        void* drec = mapped(records);
+        void* du = mapped(u0);
+        void* dst = status ? mapped(status) : nullptr;
+        if (drec && du && (!status || dst)) {
+            int rc = lqng_solve_packed_in_place(batch, horizon, dt, (const double*)drec, (double*)du, (int*)dst, c->stream);
+            if (rc) return rc;
+            HK_CUDA(cudaStreamSynchronize(c->stream));
+            drain_guard.ok = true;
+            return HK_OK;
+        }
+    }
     static const int chunks_env = getenv("HK_E2E_CHUNKS") ? atoi(getenv("HK_E2E_CHUNKS")) : 0;
     constexpr int RING = 4;
     int nchunks = batch >= 16384 ? (chunks_env > 0 ? chunks_env : (batch >= 65536 ? 8 : batch / 8192)) : 1;

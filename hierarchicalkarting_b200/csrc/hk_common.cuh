@@ -53,6 +53,7 @@ int lqng_assemble_launch(int batch, int N, int horizon, double dt, const double*
                          const double* dtw, const double* dcw, const double* daw, const double* dotgt, const double* dotw,
                          double* du0, int* dstatus, cudaStream_t stream, int scratch_slot, const int* dn_players = nullptr, int min_players = 0);
 
+int lqng_solve_packed_in_place(int batch, int horizon, double dt, const double* drec, double* du0, int* dstatus, cudaStream_t stream);
 int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const double* drec, double* du0, int* dstatus, cudaStream_t stream,
                                 int scratch_slot, const int* dn_players = nullptr, const double* dcs_ready = nullptr);
 

@@ -568,6 +568,16 @@ int lqng_assemble_launch_packed(int batch, int N, int horizon, double dt, const 
     return lqng_assemble_launch(batch, N, horizon, dt, ux0, utg, utw, ucw, uaw, uot, uow, du0, dstatus, stream, scratch_slot, dn_players, 0);
 }
 
+// 2-kart packed records solved straight from where they lie (e.g. pinned host memory, device-accessible under UVA): no (cos h, sin h) pre-pass —
+// the records are read exactly once, by the solve kernel's bulk copies
+int lqng_solve_packed_in_place(int batch, int horizon, double dt, const double* drec, double* du0, int* dstatus, cudaStream_t stream)
+{
+    if (batch == 0) return HK_OK;
+    LqngParams p{batch, horizon, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, du0, nullptr, nullptr, nullptr, dstatus,
+                 nullptr, nullptr, nullptr, nullptr, drec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dt};
+    return launch_mma2p(p, stream, true);
+}
+
 int lqng_launch(int batch, int N, int horizon, int time_varying, const double* dA, const double* dB, const double* dQ,
                 const double* dq, const double* dR, const double* dx0, double* du0, double* dP, double* dalpha,
                 double* dtraj, int* dstatus, cudaStream_t stream, const int* gate, int gate_min)

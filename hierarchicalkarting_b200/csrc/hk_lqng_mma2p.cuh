@@ -70,6 +70,8 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
     asm volatile("{\n\t.reg .pred p;\n\tHK_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra HK_DONE;\n\tbra HK_WAIT;\n\tHK_DONE:\n\t}"
                  ::"r"(bar), "r"(parity) : "memory");
 }
+// out of line on purpose: the slow paths of sin / cos must not cost the solve loop registers
+__device__ __noinline__ double p2_trig(double h, int want_sin) { return want_sin ? sin(h) : cos(h); }
 __device__ __forceinline__ unsigned abs_hi(double a) { return (unsigned)__double2hiint(a) & 0x7fffffffu; }
 __device__ __forceinline__ bool bits_differ(double a, double b)
 {
@@ -137,6 +139,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
         if (COMPACT) {
             const unsigned sd = stage_u32 + (unsigned)(b * C2_STRIDE * 8);
             if (!p.c_target) {                                       // packed records (hk_lqng_assemble_solve_packed): the staged layout IS the record
+                if (!p.c_cs) {                                       // no (cos h, sin h) array: the warp evaluates them itself (records read once, e.g.
+                    mbar_expect_tx(bar, C2_ocs * 8);                 // straight from pinned host memory)
+                    bulk_g2s(sd, p.c_x0 + (size_t)prob * C2_ocs, C2_ocs * 8, bar);
+                    return;
+                }
                 mbar_expect_tx(bar, C2_TX_BYTES);
                 bulk_g2s(sd, p.c_x0 + (size_t)prob * C2_ocs, C2_ocs * 8, bar);           // 352 B: x0 | target | tw | cw | aw | otgt | otw
                 bulk_g2s(sd + C2_ocs * 8, p.c_cs + (size_t)prob * 4, 32, bar);
@@ -228,7 +235,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) lqng_mma2p_kernel(LqngParams
         if (COMPACT) {
             // assemble the dense record (layout P2_o*) from the staged description; every lane writes a few entries
             double* r = &sm.rec[wib][0][0];
-            const double* c = &sm.stage[wib][buf][0];
+            double* c = &sm.stage[wib][buf][0];
+            if (!p.c_cs) {                                           // warp-uniform: cos / sin of the two headings by lanes 0..3 (the same
+                if (lane < 4) c[C2_ocs + lane] = p2_trig(c[C2_ox + 4 * (lane >> 1) + 3], lane & 1);   // double-precision functions lqng_trig_kernel calls)
+                __syncwarp();
+            }
             *reinterpret_cast<double2*>(r + P2_oQ + 4 * lane) = make_double2(0.0, 0.0);           // Q_0, Q_1 = 0 (128 doubles)
             *reinterpret_cast<double2*>(r + P2_oQ + 4 * lane + 2) = make_double2(0.0, 0.0);
             {   // A_i = I + dt [[0,0,cos h,-v sin h],[0,0,sin h,v cos h],0,0]  (KartLQRDynamics.cs:44-48), entry `lane` of A[2][4][4]
