@@ -41,6 +41,20 @@ namespace KartGame.AI.Native
         public int maxLaneChanges, goalSection, highModeMcts, velocityBucketSize, treeSearchDepth, planEvery, horizon;
     }
 
+    /// <summary>One 2-kart LQNG problem as the reference's providers are constructed (LinearizedBicycle(dt, initial) and
+    /// LQRCheckpointReachAvoidCost(target, weights, ...), KartLQRDynamics.cs:22-38, KartLQRCosts.cs:22-55), player 0 = ego: 44 doubles.</summary>
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct HkLqngRecord2
+    {
+        public fixed double x0[8];        // [player][x, z, v, h]
+        public fixed double target[8];    // [player][x, z, v, h]
+        public fixed double tw[8];        // target weights
+        public fixed double cw[2];        // control weight
+        public fixed double aw[4];        // [player][avoid weight x, z] about the other player
+        public fixed double otgt[8];      // [player][the other player's target x, z, v, h]
+        public fixed double otw[6];       // [player][weights x, z, v on it]
+    }
+
     public static class HkNative
     {
         const string Lib = "hk_b200";                            // libhk_b200.so / hk_b200.dll on the plugin search path
@@ -58,6 +72,10 @@ namespace KartGame.AI.Native
         [DllImport(Lib)] public static extern int hk_lqng_assemble_solve_batch(int batch, int nPlayers, int horizon, double dt, double[] x0, double[] target,
                                                                                double[] tw, double[] cw, double[] aw, double[] otgt, double[] otw,
                                                                                [Out] double[] u0, [Out] int[] status);
+        // the same with one blittable 352-byte record per 2-kart problem (x0 | target | tw | cw | aw | otgt | otw, include/hk_abi.h): an array of
+        // HkLqngRecord2 is what a C# caller fills naturally, and it crosses PCIe as one copy per chunk
+        [DllImport(Lib)] public static extern int hk_lqng_assemble_solve_packed(int batch, int nPlayers, int horizon, double dt, HkLqngRecord2[] records,
+                                                                                [Out] double[] u0, [Out] int[] status);
         [DllImport(Lib)] public static extern int hk_game_create(HkSection[] sections, int nSections, HkKart[] karts, int nKarts, HkKart[] envKarts,
                                                                  int nEnvKarts, ref HkGameParams p, out IntPtr game);
         [DllImport(Lib)] public static extern void hk_game_destroy(IntPtr game);
